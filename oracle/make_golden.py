@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE ONLY - generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_harness.py) on the synthetic workloads of
+vognet_pytorch_b200/synth.py.  Run in the build container:
+
+    python oracle/make_golden.py            # all fixtures
+    python oracle/make_golden.py spat_gt5   # one
+
+Weights and inputs are NOT stored: they are regenerated bit-identically from (name, seed) by
+synth.py; the fixtures hold only what the reference computed from them.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh                      # noqa: E402
+from vognet_pytorch_b200 import synth                      # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def operator_case(name, d, n_heads, n_layers, Bt, N, rel, seed=3):
+    """RelTransformer / Transformer called directly with a dense [Bt,N,N,H] bias tensor
+    (operator-level boundary, code/transformer_code.py:244-279)."""
+    tc = rh.reference_transformers()
+    sd = synth.make_operator_state_dict(d, n_layers, seed=seed)
+    x, pe = synth.make_operator_inputs(d, n_heads, Bt, N, seed=seed)
+    if rel:
+        m = tc.RelTransformer(d, 0, 0, d_hidden=d // 2, n_layers=n_layers, n_heads=n_heads,
+                              drop_ratio=0.2, pe=False, d_pe=5)
+    else:
+        m = tc.Transformer(d, 0, 0, d_hidden=d // 2, n_layers=n_layers, n_heads=n_heads,
+                           drop_ratio=0.2, pe=False)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        y = m(x, pe) if rel else m(x)
+    np.savez(os.path.join(GOLD, f'op_{name}.npz'), y=y.numpy(),
+             meta=np.array([d, n_heads, n_layers, Bt, N, int(rel), seed]))
+    print(f'op_{name}: y {tuple(y.shape)} std {y.std():.3f}')
+
+
+def model_case(name):
+    w, batch = synth.workload(name)
+    sd = synth.make_state_dict()
+    mdl = rh.build_reference_model(w['conc_type'], w['nppf'], sd)
+    keep = {}
+
+    def hook(key):
+        def f(mod, args, out):
+            keep[key + '_in'] = args[0].detach().clone()
+            keep[key + '_out'] = out.detach().clone()
+        return f
+    mdl.obj_txf.register_forward_hook(hook('obj'))
+    mdl.mult_txf.register_forward_hook(hook('mul'))
+    orig = mdl.retrieve_srl_arg_from_lang_encode
+
+    def lang_hook(*a, **k):
+        r = orig(*a, **k)
+        keep['lang'] = r.detach().clone()
+        return r
+    mdl.retrieve_srl_arg_from_lang_encode = lang_hook
+
+    with torch.no_grad():
+        out = mdl(synth.clone_batch(batch))
+        ev = rh.build_reference_evaluator(w['conc_type'], w['nppf'], w['ncmp'])
+        sel = ev.get_out_results_boxes(out, batch)
+    save = {
+        'mdl_outs': out['mdl_outs'].numpy(),
+        'mdl_outs_eval': out['mdl_outs_eval'].numpy(),
+        'boxes': sel['boxes'].contiguous().numpy(),
+        'scores': sel['scores'].contiguous().numpy(),
+        'indexs': sel['indexs'].contiguous().numpy().astype(np.int64),
+        'lang': keep['lang'].numpy(),
+    }
+    # intermediates: everything for the small case, a strided row sample otherwise
+    stride = 1 if name == 'cpu_ref' else (23 if w['nppf'] == 5 else 397)
+    for k in ('obj_out', 'mul_out'):
+        t = keep[k]
+        save[k + '_rows'] = t.reshape(-1, t.shape[-1])[::stride].contiguous().numpy()
+        save[k + '_shape'] = np.array(t.shape)
+    save['row_stride'] = np.array(stride)
+    np.savez(os.path.join(GOLD, f'{name}.npz'), **save)
+    sz = os.path.getsize(os.path.join(GOLD, f'{name}.npz')) / 1e6
+    print(f'{name}: logits {tuple(out["mdl_outs"].shape)} std {out["mdl_outs"].std():.3f} '
+          f'obj {tuple(keep["obj_out"].shape)} mul {tuple(keep["mul_out"].shape)}  {sz:.2f} MB')
+
+
+OPS = {
+    'rel_d512_h3_l2':  dict(d=512, n_heads=3, n_layers=2, Bt=2, N=37, rel=True),
+    'rel_d768_h3_l1':  dict(d=768, n_heads=3, n_layers=1, Bt=3, N=50, rel=True),
+    'rel_d512_h6_l1':  dict(d=512, n_heads=6, n_layers=1, Bt=1, N=130, rel=True),   # EXPTS.md:186-189 ablation
+    'plain_d512_h3_l1': dict(d=512, n_heads=3, n_layers=1, Bt=2, N=64, rel=False),
+}
+
+if __name__ == '__main__':
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    want = sys.argv[1:]
+    for nm, kw in OPS.items():
+        if not want or ('op_' + nm) in want:
+            operator_case(nm, **kw)
+    for nm in synth.WORKLOADS:
+        if not want or nm in want:
+            model_case(nm)

@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE ONLY - imports the UNMODIFIED reference from /root/reference.
+
+Only usable in the build container (the GPU box has no /root/reference).  Used by
+``oracle/make_golden.py`` to produce the committed golden vectors under ``tests/golden/`` and by
+``tests/test_oracle_vs_reference.py`` (skipped when the reference tree is absent) to pin the
+restatement in ``oracle/vog_oracle.py`` against the real code.  Nothing in the product path may
+import this module.
+
+The reference needs two third-party modules that are not installed and carry no arithmetic on
+this path: ``munch.Munch`` (attribute dict; pinned munch==2.5.0,
+conda_env_vog.yml:159) and ``fairseq.utils`` (imported by utils/mdl_srl_utils.py:8, only called
+under left_pad=True which code/mdl_vog.py:172 never sets; pinned fairseq==0.8.0).  The evaluator
+module additionally pulls yacs / fire / fastprogress at import time; all are stubbed.
+"""
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get('VOG_REFERENCE_ROOT', '/root/reference')
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_ROOT, 'code', 'mdl_vog.py'))
+
+
+class Munch(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _install_stubs():
+    if 'munch' not in sys.modules:
+        sys.modules['munch'] = types.SimpleNamespace(Munch=Munch)
+    if 'fairseq' not in sys.modules:
+        m = types.ModuleType('fairseq')
+        m.utils = None
+        sys.modules['fairseq'] = m
+
+    def stub(name, **attrs):
+        if name in sys.modules:
+            return
+        try:
+            __import__(name)
+        except Exception:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+
+    stub('fire', Fire=lambda *a, **k: None)
+    stub('yacs')
+    if isinstance(sys.modules.get('yacs'), types.ModuleType) and not hasattr(sys.modules['yacs'], 'config'):
+        cfgm = types.ModuleType('yacs.config')
+        cfgm.CfgNode = Munch
+        sys.modules['yacs'].config = cfgm
+        sys.modules['yacs.config'] = cfgm
+    stub('fastprogress', progress_bar=lambda x, **k: x, master_bar=lambda x, **k: x)
+    if 'fastprogress.fastprogress' not in sys.modules:
+        fp = types.ModuleType('fastprogress.fastprogress')
+        fp.progress_bar = lambda x, **k: x
+        fp.master_bar = lambda x, **k: x
+        fp.MasterBar = object
+        fp.ProgressBar = object
+        fp.format_time = lambda t: str(t)
+        sys.modules['fastprogress.fastprogress'] = fp
+        sys.modules['fastprogress'].fastprogress = fp
+    for p in (os.path.join(REF_ROOT, 'code'), os.path.join(REF_ROOT, 'utils')):
+        if p not in sys.path:          # what code/_init_stuff.py:38-39 does
+            sys.path.append(p)
+
+
+def to_munch(d):
+    if isinstance(d, dict):
+        return Munch({k: to_munch(v) for k, v in d.items()})
+    return d
+
+
+def reference_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
+    import yaml
+    cfg = to_munch(yaml.safe_load(open(os.path.join(REF_ROOT, 'configs', 'anet_srl_cfg.yml'))))
+    cfg.ds.conc_type = conc_type
+    for tx in (cfg.mdl.obj_tx, cfg.mdl.mul_tx):
+        tx.use_rel = use_rel
+        tx.n_layers = n_layers
+        tx.n_heads = n_heads
+    return cfg
+
+
+def build_reference_model(conc_type, nppf, state_dict, vocab_size=1000, **cfg_kw):
+    """Unmodified reference VOG_SPAT / VOG_TEMP in eval mode with ``state_dict`` loaded strictly."""
+    _install_stubs()
+    import mdl_vog  # noqa: from /root/reference/code
+    cfg = reference_cfg(conc_type, **cfg_kw)
+    comm = Munch(vocab_size=vocab_size, detect_size=10, itod={}, wtoi={'UNK': 0},
+                 num_prop_per_frm=nppf)
+    cls = {'spat': mdl_vog.VOG_SPAT, 'temp': mdl_vog.VOG_TEMP}[conc_type]
+    mdl = cls(cfg, comm)
+    mdl.load_state_dict(state_dict, strict=True)
+    return mdl.eval()
+
+
+def build_reference_evaluator(conc_type, nppf, ncmp):
+    """EvaluatorSPAT/TEMP without its dataset-reading ctor (code/eval_fn_corr.py:54-67)."""
+    _install_stubs()
+    import eval_vsrl_corr  # noqa
+    cls = {'spat': eval_vsrl_corr.EvaluatorSPAT, 'temp': eval_vsrl_corr.EvaluatorTEMP}[conc_type]
+    ev = cls.__new__(cls)
+    import torch
+    torch.nn.Module.__init__(ev)
+    ev.num_sampled_frm = 10
+    ev.num_frms = 10
+    ev.num_prop_per_frm = nppf
+    return ev
+
+
+def reference_transformers():
+    _install_stubs()
+    import transformer_code  # noqa
+    return transformer_code

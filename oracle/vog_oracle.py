@@ -1,0 +1,258 @@
+"""TEST INFRASTRUCTURE ONLY - CPU restatement (torch, fp32) of the reference VOGNet forward
+fusion path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this file; the product path never does.
+
+Parity pin: the reference repo ships no tests, golden vectors or fixtures for this path
+(SURVEY.md section 4), so this restatement is pinned against OUTPUTS OF THE REFERENCE ITSELF,
+executed unmodified in the build container by ``oracle/make_golden.py`` (committed together with
+the vectors in ``tests/golden/``) and re-checked live by ``tests/test_oracle_vs_reference.py``
+whenever /root/reference is present.
+
+The algorithm is restated as stateless functions over a flat ``state_dict`` (the checkpoint
+contract) - same operations, same order of floating-point evaluation wherever the order is
+observable (bias materialised and added before the 1/sqrt(d_model) scaling, heads split with
+uneven ``chunk`` sizes, post-LN residual blocks, eval-mode dropout = identity).  Each function
+cites the reference lines it follows.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------------------------------------
+# operator level: code/transformer_code.py
+# ---------------------------------------------------------------------------------------------
+def chunk_sizes(d, n_heads):
+    """torch.chunk split sizes (transformer_code.py:66-67,182-183): ceil(d/H) per head, last
+    one takes the remainder - d=512,H=3 -> 171,171,170."""
+    c = -(-d // n_heads)
+    sizes = []
+    left = d
+    while left > 0:
+        sizes.append(min(c, left))
+        left -= c
+    return sizes
+
+
+def layer_norm(x, w, b):
+    """nn.LayerNorm(d_model), eps=1e-5 (transformer_code.py:28)."""
+    return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
+
+
+def multihead_attention(x, sd, p, n_heads, bias=None):
+    """RelMultiHead.forward + RelAttention.forward (transformer_code.py:136-160,176-186) and,
+    with bias=None, MultiHead/Attention (:41-50,62-70).
+
+    x [Bt,N,d]; bias [Bt,N,N,H] or None.  softmax((q k^T + bias_h) / sqrt(d_model)) v per head,
+    the scale being sqrt(d_model) (NOT sqrt(d_head)): RelAttention is built with d_key=d_model
+    (:166,:195) and self.scale = sqrt(d_key) (:132).  No mask is ever applied (causal=False)."""
+    d = x.shape[-1]
+    q = x @ sd[p + '.wq.weight'].t()
+    k = x @ sd[p + '.wk.weight'].t()
+    v = x @ sd[p + '.wv.weight'].t()
+    scale = math.sqrt(d)
+    outs = []
+    off = 0
+    for h, dh in enumerate(chunk_sizes(d, n_heads)):
+        qh, kh, vh = q[..., off:off + dh], k[..., off:off + dh], v[..., off:off + dh]
+        off += dh
+        dots = torch.matmul(qh, kh.transpose(1, 2))                     # :141
+        if bias is not None:
+            dots = (dots + bias[..., h]) / scale                          # :149-151
+        else:
+            dots = dots / scale                                           # :50
+        attn = torch.softmax(dots, dim=-1)                                # :153 (dropout off in eval)
+        outs.append(torch.matmul(attn, vh))                               # :155
+    return torch.cat(outs, -1) @ sd[p + '.wo.weight'].t()               # :184-186
+
+
+def encoder_layer(x, sd, p, n_heads, bias=None):
+    """RelEncoderLayer / EncoderLayer (transformer_code.py:84-96,189-203) with ResidualBlock
+    (:21-31) and FeedForward (:73-81): y = LN(x + MHA(x)); out = LN(y + W2 relu(W1 y + b1) + b2)."""
+    a = multihead_attention(x, sd, p + '.selfattn.layer', n_heads, bias)
+    y = layer_norm(x + a, sd[p + '.selfattn.layernorm.weight'], sd[p + '.selfattn.layernorm.bias'])
+    h = F.relu(y @ sd[p + '.feedforward.layer.linear1.weight'].t()
+               + sd[p + '.feedforward.layer.linear1.bias'])
+    f = h @ sd[p + '.feedforward.layer.linear2.weight'].t() + sd[p + '.feedforward.layer.linear2.bias']
+    return layer_norm(y + f, sd[p + '.feedforward.layernorm.weight'],
+                      sd[p + '.feedforward.layernorm.bias'])
+
+
+def transformer(x, sd, prefix, n_heads, bias=None):
+    """RelTransformer / Transformer forward: last layer's output (transformer_code.py:227-241,
+    :252-254,:271-273)."""
+    n_layers = 0
+    while f'{prefix}.encoder.layers.{n_layers}.selfattn.layer.wq.weight' in sd:
+        n_layers += 1
+    for l in range(n_layers):
+        x = encoder_layer(x, sd, f'{prefix}.encoder.layers.{l}', n_heads, bias)
+    return x
+
+
+# ---------------------------------------------------------------------------------------------
+# relative-position bias: code/mdl_vog.py:456-490 + utils/mdl_srl_utils.py:30-69
+# ---------------------------------------------------------------------------------------------
+def compute_pe(props5, nsrl, nfrm, nppf, W, b, vid_w=720.0, vid_h=405.0):
+    """props5 [B, nfrm*nppf, 5] (x1,y1,x2,y2,frame) -> bias [B*nfrm, nsrl*nppf, nsrl*nppf, H].
+
+    Normalise x/720, y/405, frame/nfrm (mdl_vog.py:459-463), pairwise difference p_i - p_j inside
+    each frame group (do_cross 'subtract', mdl_srl_utils.py:55-69), Linear(5,H)+ReLU
+    (mdl_vog.py:446-451,480), then tile nsrl x nsrl (:482-488) - token t = s*nppf + p."""
+    props = props5.clone()
+    props[..., 0] /= vid_w
+    props[..., 1] /= vid_h
+    props[..., 2] /= vid_w
+    props[..., 3] /= vid_h
+    props[..., 4] /= nfrm
+    B = props.shape[0]
+    g = props.view(B * nfrm, nppf, 5)
+    diff = g.unsqueeze(2) - g.unsqueeze(1)                  # [.., i, j, :] = p_i - p_j
+    pe = F.relu(diff @ W.t() + b)                           # [B*nfrm, nppf, nppf, H]
+    H = pe.shape[-1]
+    pe = pe.view(B, nfrm, 1, nppf, 1, nppf, H).expand(B, nfrm, nsrl, nppf, nsrl, nppf, H)
+    return pe.contiguous().view(B * nfrm, nsrl * nppf, nsrl * nppf, H)
+
+
+# ---------------------------------------------------------------------------------------------
+# language side: code/mdl_vog.py:67-140,250-283 ; utils/mdl_srl_utils.py:114-169
+# ---------------------------------------------------------------------------------------------
+def _lstm_from_state_dict(sd):
+    lstm = torch.nn.LSTM(input_size=512, hidden_size=1024, num_layers=2, dropout=0.0,
+                         bidirectional=True)
+    own = lstm.state_dict()
+    for k in own:
+        own[k] = sd['lstm_encoder.lstm.' + k]
+    lstm.load_state_dict(own)
+    return lstm.eval()
+
+
+def language_encode(sd, inp, vocab_size):
+    """-> [B, 1, nsrl, 256] argument encodings (the 'language matrix')."""
+    words = inp['srl_arg_words_ind']
+    B, nv, nsrl, L = words.shape
+    flat = words.reshape(B * nv, nsrl * L)
+    wm = inp['srl_arg_word_mask'].reshape(B * nv, -1).clone()
+    pad = wm == -1
+    wm[pad] = 0
+    toks = torch.gather(flat, 1, wm)                        # mdl_vog.py:83-85
+    toks[pad] = vocab_size                                  # :87
+    lens = inp['srl_arg_word_mask_len'].reshape(B * nv)
+    toks = toks[:, :int(lens.max())].contiguous()           # :257
+    emb = F.embedding(toks, sd['lstm_encoder.embed_tokens.weight'])      # mdl_srl_utils.py:128
+    packed = torch.nn.utils.rnn.pack_padded_sequence(emb.transpose(0, 1), lens.tolist(),
+                                                     enforce_sorted=False)  # :136-137
+    out, _ = _lstm_from_state_dict(sd)(packed)              # zero initial state :145-148
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, padding_value=0.0)  # :151-152
+    full = out.transpose(0, 1).contiguous()                 # [B, T, 2048]  mdl_vog.py:272-273
+    full = F.relu(full @ sd['lstm_out_feat_proj.0.weight'].t() + sd['lstm_out_feat_proj.0.bias'])  # :275
+    cap = inp['srl_arg_words_capture'].reshape(B * nv, nsrl, 2)
+    D = full.shape[-1]
+    st = torch.gather(full, 1, cap[..., 0].unsqueeze(-1).expand(B * nv, nsrl, D))   # :119-120
+    en = torch.gather(full, 1, cap[..., 1].unsqueeze(-1).expand(B * nv, nsrl, D))   # :121-122
+    enc = torch.cat([st, en], 2).view(B, nv, nsrl, 2 * D)   # :126-128
+    enc = F.relu(enc @ sd['srl_arg_words_out_enc.0.weight'].t() + sd['srl_arg_words_out_enc.0.bias'])
+    return enc * inp['srl_arg_inds_msk'].unsqueeze(-1).float()            # :137-139
+
+
+# ---------------------------------------------------------------------------------------------
+# whole forward: code/mdl_conc_single.py:68-127 (TEMP) / :130-177 (SPAT)
+# ---------------------------------------------------------------------------------------------
+def vog_forward(sd, inp, conc_type, nppf, n_heads=3, vocab_size=1000, nfrm0=10,
+                use_rel=True, keep=False):
+    """Restated ConcTEMP.forward / ConcSPAT.forward for mdl.name='vog'.
+
+    returns {'mdl_outs': logits [B,1,nsrl,P], 'mdl_outs_eval': masked sigmoid} (+ intermediates
+    when keep=True)."""
+    ncmp = inp['new_srl_idxs'].shape[1]
+    B, nv, nsrl, _ = inp['srl_arg_words_ind'].shape
+    lang = language_encode(sd, inp, vocab_size)                            # [B,1,nsrl,256]
+
+    prop = F.relu(inp['pad_region_feature'] @ sd['prop_encoder.0.weight'].t()
+                  + sd['prop_encoder.0.bias'])                             # mdl_vog.py:291-299
+    seg = F.relu(inp['seg_feature_for_frms'] @ sd['seg_encoder.0.weight'].t()
+                 + sd['seg_encoder.0.bias'])                               # :301-314
+    P = prop.shape[1]
+    nvf = seg.shape[1]                                                     # ncmp*nfrm0 (frame,vid) slots
+    # every proposal of a (frame,vid) slot gets that slot's segment feature
+    # (mdl_conc_single.py:50-66,156-174)
+    ps = torch.cat([prop.view(B, 1, nvf, nppf, -1),
+                    seg.view(B, 1, nvf, 1, -1).expand(B, 1, nvf, nppf, seg.shape[-1])], -1)
+    ps = ps.reshape(B, 1, P, -1)                                           # [B,1,P,512]
+
+    # ---- object transformer over ALL proposals of the query (mdl_vog.py:492-523, one_frm False)
+    props5 = inp['pad_proposals'][..., :5].clone()
+    x_obj = ps.reshape(B, P, -1)
+    if use_rel:
+        # compute_pe(props, nsrl=1, nfrm=1, nppf=P): frame id divided by 1 (:507-510)
+        bias_obj = compute_pe(props5, 1, 1, P, sd['pe_obj_sub_enc.0.weight'], sd['pe_obj_sub_enc.0.bias'])
+    else:
+        bias_obj = None
+    y_obj = transformer(x_obj, sd, 'obj_txf', n_heads, bias_obj)
+    del bias_obj
+    vis = y_obj.view(B, 1, P, -1)
+
+    # ---- vis/lang concat (mdl_vog.py:316-344): token (s,p) = [vis_p | lang_s]
+    conc = torch.cat([vis.view(B, 1, 1, P, -1).expand(B, 1, nsrl, P, vis.shape[-1]),
+                      lang.view(B, 1, nsrl, 1, -1).expand(B, 1, nsrl, P, lang.shape[-1])], -1)
+
+    # ---- multimodal transformer, one sequence per frame (mdl_vog.py:681-744, int_pfrm=True)
+    if conc_type == 'spat':
+        nfrm, nppf2 = nfrm0, ncmp * nppf                                   # mdl_conc_single.py:131-135
+    else:
+        nfrm, nppf2 = ncmp * nfrm0, nppf                                   # :24-28
+    D = conc.shape[-1]
+    x_mul = conc.view(B, nsrl, nfrm, nppf2, D).transpose(1, 2).contiguous().view(
+        B * nfrm, nsrl * nppf2, D)                                         # mdl_vog.py:693-699
+    if use_rel:
+        bias_mul = compute_pe(inp['pad_proposals'][..., :5].clone(), nsrl, nfrm, nppf2,
+                              sd['pe_mul_sub_enc.0.weight'], sd['pe_mul_sub_enc.0.bias'])  # :710-713
+    else:
+        bias_mul = None
+    y_mul = transformer(x_mul, sd, 'mult_txf', n_heads, bias_mul)
+    del bias_mul
+    y = y_mul.view(B, nfrm, nsrl, nppf2, D).transpose(1, 2).contiguous().view(B, 1, nsrl, P, D)  # :724-737
+
+    h = F.relu(y @ sd['lin2.0.weight'].t() + sd['lin2.0.bias'])
+    logits = (h @ sd['lin2.2.weight'].t() + sd['lin2.2.bias']).squeeze(-1)   # mdl_vog.py:675-677
+
+    # ---- output masks (mdl_conc_single.py:39-48,118-122,144-154)
+    cm = inp['num_cmp_msk']
+    if conc_type == 'spat':
+        cmsk = cm.view(B, 1, 1, 1, ncmp, 1).expand(B, nv, nsrl, nfrm0, ncmp, nppf)
+    else:
+        cmsk = cm.view(B, 1, 1, ncmp, 1).expand(B, nv, nsrl, ncmp, nfrm0 * nppf)
+    cmsk = cmsk.reshape(logits.shape)
+    smsk = inp['srl_arg_inds_msk'].unsqueeze(-1).expand(*logits.shape)
+    ev = torch.sigmoid(logits) * smsk.float() * cmsk.float()
+    out = {'mdl_outs': logits, 'mdl_outs_eval': ev}
+    if keep:
+        out.update(lang=lang, prop_seg=ps, obj_out=y_obj, mul_in=x_mul, mul_out=y_mul)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# selection: code/eval_vsrl_corr.py:289-345 (TEMP) / :357-424 (SPAT)
+# ---------------------------------------------------------------------------------------------
+def select_boxes(mdl_outs_eval, pad_proposals, conc_type, ncmp, nppf, nfrm0=10):
+    """per-(srl,frame,vid) max / argmax over the nppf proposals, gather their 7-float rows,
+    argmax over vids.  Lowest index wins ties (torch.max / argmax semantics).
+
+    -> boxes [B,nsrl,ncmp,nfrm,7], scores [B,nsrl,ncmp,nfrm], indexs [B,nsrl,nfrm] (int64; zeros
+    for TEMP, float zeros in the reference :339-341)."""
+    B, nv, nsrl, P = mdl_outs_eval.shape
+    assert nv == 1
+    pd = pad_proposals.shape[-1]
+    if conc_type == 'spat':
+        s = mdl_outs_eval.view(B, nsrl, nfrm0, ncmp, nppf)
+        sc, ix = torch.max(s, dim=-1)                                       # [B,nsrl,nfrm,ncmp]
+        pr = pad_proposals.view(B, 1, nfrm0, ncmp, nppf, pd).expand(B, nsrl, nfrm0, ncmp, nppf, pd)
+        bx = torch.gather(pr, -2, ix[..., None, None].expand(B, nsrl, nfrm0, ncmp, 1, pd)).squeeze(-2)
+        return {'boxes': bx.transpose(2, 3).contiguous(),
+                'scores': sc.transpose(2, 3).contiguous(),
+                'indexs': sc.argmax(dim=-1)}
+    s = mdl_outs_eval.view(B, nsrl, ncmp, nfrm0, nppf)
+    sc, ix = torch.max(s, dim=-1)
+    pr = pad_proposals.view(B, 1, ncmp, nfrm0, nppf, pd).expand(B, nsrl, ncmp, nfrm0, nppf, pd)
+    bx = torch.gather(pr, -2, ix[..., None, None].expand(B, nsrl, ncmp, nfrm0, 1, pd)).squeeze(-2)
+    return {'boxes': bx, 'scores': sc, 'indexs': torch.zeros(B, nsrl, nfrm0, dtype=torch.int64)}

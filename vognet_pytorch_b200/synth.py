@@ -1,0 +1,311 @@
+"""Deterministic synthetic workloads for the VOGNet forward fusion path.
+
+There is no dataset and no checkpoint on the GPU box, so every test, the smoke
+run and ``bench.py`` build their weights and batches here.  Everything is drawn
+from numpy's PCG64 bit stream through ``Generator.random(dtype=float32)`` (an
+exact integer -> float conversion) followed by plain IEEE float32 arithmetic, so
+the same (name, seed) gives bit-identical tensors in this container (where the
+golden vectors are generated from the real reference) and on the GPU box.
+
+Shapes follow the batch dict produced by the reference collator
+(code/dat_loader_simple.py:1518-1544) and read by the forward
+(code/mdl_vog.py:74-89,112,137,296,309,497-506,624; code/mdl_conc_single.py:25,42,77,81,119):
+
+  srl_arg_words_ind      [B,1,nsrl,L]  int64   word ids of every SRL argument, padded to L
+  srl_arg_word_mask      [B,1,L]       int64   sentence position -> flat (arg*L+word) index, -1 = pad
+  srl_tag_word_ind       [B,1,L]       int64
+  srl_arg_word_mask_len  [B,1]         int64   sentence length
+  srl_arg_words_capture  [B,1,nsrl,2]  int64   first / last sentence position of each argument
+  srl_arg_inds_msk       [B,1,nsrl]    int64   1 = argument slot is populated
+  pad_region_feature     [B,P,2048]    float32
+  seg_feature_for_frms   [B,ncmp*nfrm,3072] float32
+  pad_proposals          [B,P,7]       float32 (x1,y1,x2,y2,frame,class,score  dat_loader_simple.py:191-201)
+  new_srl_idxs           [B,ncmp]      int64   (only its size is read)
+  num_cmp_msk            [B,ncmp]      int64
+
+Proposal rows are ordered [frame][vid][prop] with x shifted by 720*vid for
+``spat`` (dat_loader_simple.py:1067-1103,1151-1153) and [vid][frame][prop] with
+the frame id shifted by 10*vid for ``temp`` (dat_loader_simple.py:1231-1252).
+"""
+import zlib
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+
+class AttrDict(dict):
+    """Attribute-access dict standing in for yacs CfgNode / munch.Munch."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def to_attr(d):
+    if isinstance(d, dict):
+        return AttrDict({k: to_attr(v) for k, v in d.items()})
+    return d
+
+
+# The cfg keys the forward path reads (configs/anet_srl_cfg.yml:16-24,57-81,98-104),
+# with use_rel=True as in every published command (README.md:53, EXPTS.md:14-15).
+def default_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
+    return to_attr({
+        'ds': {'conc_type': conc_type, 'resized_width': 720, 'resized_height': 405,
+               'num_sampled_frm': 10, 't_attn_size': 480, 'max_seq_length': 20},
+        'mdl': {
+            'name': 'vog', 'seg_feat_dim': 3072, 'prop_feat_dim': 2048,
+            'input_encoding_size': 512,
+            'rnn': {'rnn_size': 1024, 'num_layers': 2, 'drop_prob_lm': 0.5},
+            'vsrl': {'prop_encode_size': 256, 'seg_encode_size': 256, 'lang_encode_size': 256},
+            'obj_tx': {'use_ddp': False, 'to_use': True, 'n_layers': n_layers, 'n_heads': n_heads,
+                       'attn_drop': 0.2, 'use_rel': use_rel, 'one_frm': False},
+            'mul_tx': {'use_ddp': False, 'to_use': True, 'n_layers': n_layers, 'n_heads': n_heads,
+                       'attn_drop': 0.2, 'use_rel': use_rel, 'one_frm': True, 'cross_frm': False},
+        },
+        'misc': {'srl_arg_length': 5},
+    })
+
+
+def default_comm(nppf, vocab_size=1000):
+    return AttrDict(vocab_size=vocab_size, detect_size=10, itod={}, wtoi={'UNK': 0},
+                    num_prop_per_frm=nppf)
+
+
+# BASELINE.json configs.  'B' is the per-GPU batch.
+WORKLOADS = OrderedDict([
+    ('cpu_ref',   dict(conc_type='spat', B=1, ncmp=1, nppf=5,   nvalid=4, compute='fp32')),
+    ('spat_gt5',  dict(conc_type='spat', B=4, ncmp=4, nppf=5,   nvalid=None, compute='fp32')),
+    ('spat_p100', dict(conc_type='spat', B=4, ncmp=4, nppf=100, nvalid=None, compute='bf16')),
+    ('temp_gt5',  dict(conc_type='temp', B=4, ncmp=4, nppf=5,   nvalid=None, compute='fp32')),
+    ('temp_p100', dict(conc_type='temp', B=4, ncmp=4, nppf=100, nvalid=None, compute='bf16')),
+])
+
+NFRM0 = 10     # ds.num_sampled_frm
+NSRL = 5       # misc.srl_arg_length
+SEQ_L = 20     # ds.max_seq_length
+WORDS_PER_ARG = 4
+
+
+def _rng(name, seed):
+    return np.random.Generator(np.random.PCG64([zlib.crc32(name.encode()), seed]))
+
+
+def _uniform(name, seed, shape, lo, hi):
+    u = _rng(name, seed).random(size=shape, dtype=np.float32)
+    return (u * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------
+def param_shapes(nppf_unused=None, vocab_size=1000, n_layers_obj=1, n_layers_mul=1, n_heads=3):
+    """state_dict names/shapes of VOG_{SPAT,TEMP} (checkpoint contract)."""
+    S = OrderedDict()
+    S['lstm_encoder.embed_tokens.weight'] = (vocab_size + 1, 512)
+    for layer, in_dim in ((0, 512), (1, 2048)):
+        for sfx in ('', '_reverse'):
+            S[f'lstm_encoder.lstm.weight_ih_l{layer}{sfx}'] = (4096, in_dim)
+            S[f'lstm_encoder.lstm.weight_hh_l{layer}{sfx}'] = (4096, 1024)
+            S[f'lstm_encoder.lstm.bias_ih_l{layer}{sfx}'] = (4096,)
+            S[f'lstm_encoder.lstm.bias_hh_l{layer}{sfx}'] = (4096,)
+    S['lstm_out_feat_proj.0.weight'] = (256, 2048)
+    S['lstm_out_feat_proj.0.bias'] = (256,)
+    S['srl_arg_words_out_enc.0.weight'] = (256, 512)
+    S['srl_arg_words_out_enc.0.bias'] = (256,)
+    S['srl_simple_lin.0.weight'] = (256, 768)
+    S['srl_simple_lin.0.bias'] = (256,)
+    S['prop_encoder.0.weight'] = (256, 2048)
+    S['prop_encoder.0.bias'] = (256,)
+    S['seg_encoder.0.weight'] = (256, 3072)
+    S['seg_encoder.0.bias'] = (256,)
+    S['seg_verb_classf.0.weight'] = (256, 512)
+    S['seg_verb_classf.0.bias'] = (256,)
+    S['seg_verb_classf.2.weight'] = (1, 256)
+    S['seg_verb_classf.2.bias'] = (1,)
+
+    def tx(prefix, d, n_layers):
+        f = d // 2
+        for l in range(n_layers):
+            p = f'{prefix}.encoder.layers.{l}'
+            for w in ('wq', 'wk', 'wv', 'wo'):
+                S[f'{p}.selfattn.layer.{w}.weight'] = (d, d)
+            S[f'{p}.selfattn.layernorm.weight'] = (d,)
+            S[f'{p}.selfattn.layernorm.bias'] = (d,)
+            S[f'{p}.feedforward.layer.linear1.weight'] = (f, d)
+            S[f'{p}.feedforward.layer.linear1.bias'] = (f,)
+            S[f'{p}.feedforward.layer.linear2.weight'] = (d, f)
+            S[f'{p}.feedforward.layer.linear2.bias'] = (d,)
+            S[f'{p}.feedforward.layernorm.weight'] = (d,)
+            S[f'{p}.feedforward.layernorm.bias'] = (d,)
+
+    tx('obj_txf', 512, n_layers_obj)
+    S['pe_obj_sub_enc.0.weight'] = (n_heads, 5)
+    S['pe_obj_sub_enc.0.bias'] = (n_heads,)
+    for nm in ('lin2', 'lin_tmp'):
+        S[f'{nm}.0.weight'] = (256, 768)
+        S[f'{nm}.0.bias'] = (256,)
+        S[f'{nm}.2.weight'] = (1, 256)
+        S[f'{nm}.2.bias'] = (1,)
+    tx('mult_txf', 768, n_layers_mul)
+    S['pe_mul_sub_enc.0.weight'] = (n_heads, 5)
+    S['pe_mul_sub_enc.0.bias'] = (n_heads,)
+    return S
+
+
+def make_state_dict(seed=0, **kw):
+    """Synthetic checkpoint.  torch-default-like uniform(+-1/sqrt(fan_in)) init, sharpened where
+    the default init would make the forward insensitive to the very things the parity tests have
+    to catch: wq/wk x6 (obj) / x4 (mul) so attention logits get O(1) spread instead of ~0.05, pe
+    encoders x8 (obj) / x32 (mul) so the relative-position bias visibly changes the softmax, lin2.2 x4 (top-2 score gaps widen so argmax
+    selection is meaningful), LayerNorm affine != identity."""
+    sd = OrderedDict()
+    for name, shape in param_shapes(**kw).items():
+        if 'layernorm.weight' in name:
+            w = 1.0 + _uniform(name, seed, shape, -0.1, 0.1)
+        elif 'layernorm.bias' in name:
+            w = _uniform(name, seed, shape, -0.1, 0.1)
+        elif name.endswith('embed_tokens.weight'):
+            w = _uniform(name, seed, shape, -1.7320508, 1.7320508)
+            w[-1] = 0.0  # padding_idx row (utils/mdl_srl_utils.py:93-96)
+        elif 'lstm.' in name:
+            w = _uniform(name, seed, shape, -1.0 / 32.0, 1.0 / 32.0)  # 1/sqrt(hidden=1024)
+        elif name.endswith('.bias'):
+            w = _uniform(name, seed, shape, -0.05, 0.05)
+        else:
+            a = 1.0 / np.sqrt(shape[1])
+            w = _uniform(name, seed, shape, -a, a)
+            if '.wq.' in name or '.wk.' in name:
+                w = w * np.float32(6.0 if name.startswith('obj_txf') else 4.0)
+            if name.startswith('pe_'):
+                w = w * np.float32(8.0 if name.startswith('pe_obj') else 32.0)
+            if name == 'lin2.2.weight':
+                w = w * np.float32(4.0)
+        sd[name] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
+    return sd
+
+
+# ---------------------------------------------------------------------------------------------
+# inputs
+# ---------------------------------------------------------------------------------------------
+def make_batch(conc_type='spat', B=4, ncmp=4, nppf=5, nvalid=None, seed=1, vocab_size=1000,
+               **_unused):
+    """One synthetic batch dict (CPU tensors)."""
+    nfrm = NFRM0
+    P = ncmp * nfrm * nppf
+    r = _rng(f'batch/{conc_type}/{B}/{ncmp}/{nppf}', seed)
+
+    # ---- language side -------------------------------------------------------------------
+    if nvalid is None:
+        nval = r.integers(2, NSRL + 1, size=B)           # 2..5 populated argument slots
+    else:
+        nval = np.full(B, nvalid)
+    words = r.integers(0, vocab_size, size=(B, 1, NSRL, SEQ_L)).astype(np.int64)
+    word_mask = np.full((B, 1, SEQ_L), -1, np.int64)
+    capture = np.zeros((B, 1, NSRL, 2), np.int64)
+    inds_msk = np.zeros((B, 1, NSRL), np.int64)
+    lens = np.zeros((B, 1), np.int64)
+    for b in range(B):
+        pos = 0
+        for s in range(int(nval[b])):
+            nw = WORDS_PER_ARG if s % 2 == 0 else WORDS_PER_ARG - 1   # ragged argument lengths
+            for w in range(nw):
+                word_mask[b, 0, pos + w] = s * SEQ_L + w
+            capture[b, 0, s] = (pos, pos + nw - 1)
+            inds_msk[b, 0, s] = 1
+            pos += nw
+        lens[b, 0] = pos
+    tags = r.integers(0, 8, size=(B, 1, SEQ_L)).astype(np.int64)
+
+    # ---- visual side ---------------------------------------------------------------------
+    feat = np.abs(r.standard_normal(size=(B, P, 2048), dtype=np.float32))
+    seg = np.abs(r.standard_normal(size=(B, ncmp * nfrm, 3072), dtype=np.float32))
+    x1 = r.random(size=(B, P), dtype=np.float32) * np.float32(600.0)
+    y1 = r.random(size=(B, P), dtype=np.float32) * np.float32(300.0)
+    w_ = r.random(size=(B, P), dtype=np.float32) * np.float32(100.0) + np.float32(20.0)
+    h_ = r.random(size=(B, P), dtype=np.float32) * np.float32(80.0) + np.float32(20.0)
+    cls = r.integers(0, 10, size=(B, P)).astype(np.float32)
+    score = r.random(size=(B, P), dtype=np.float32)
+    idx = np.arange(P)
+    if conc_type == 'spat':            # rows [frame][vid][prop]
+        frm = idx // (ncmp * nppf)
+        vid = (idx // nppf) % ncmp
+        xoff = (720.0 * vid).astype(np.float32)
+        frame_id = frm.astype(np.float32)
+    else:                              # temp: rows [vid][frame][prop]
+        vid = idx // (nfrm * nppf)
+        frm = (idx // nppf) % nfrm
+        xoff = np.zeros(P, np.float32)
+        frame_id = (frm + nfrm * vid).astype(np.float32)
+    x2 = np.minimum(x1 + w_, np.float32(719.0))
+    y2 = np.minimum(y1 + h_, np.float32(404.0))
+    props = np.stack([x1 + xoff, y1, x2 + xoff, y2,
+                      np.broadcast_to(frame_id, (B, P)), cls, score], axis=-1).astype(np.float32)
+
+    t = torch.from_numpy
+    return {
+        'srl_arg_words_ind': t(words),
+        'srl_arg_word_mask': t(word_mask),
+        'srl_tag_word_ind': t(tags),
+        'srl_arg_word_mask_len': t(lens),
+        'srl_arg_words_capture': t(capture),
+        'srl_arg_inds_msk': t(inds_msk),
+        'pad_region_feature': t(np.ascontiguousarray(feat)),
+        'seg_feature_for_frms': t(np.ascontiguousarray(seg)),
+        'pad_proposals': t(np.ascontiguousarray(props)),
+        'new_srl_idxs': torch.zeros(B, ncmp, dtype=torch.int64),
+        'num_cmp_msk': torch.ones(B, ncmp, dtype=torch.int64),
+    }
+
+
+def clone_batch(batch, device=None):
+    """The reference forward mutates ``srl_arg_word_mask`` in place (code/mdl_vog.py:80-82)."""
+    return {k: (v.clone() if device is None else v.to(device, copy=True)) for k, v in batch.items()}
+
+
+def workload(name, seed=1):
+    w = dict(WORKLOADS[name])
+    return w, make_batch(seed=seed, **w)
+
+
+# ---------------------------------------------------------------------------------------------
+# operator-level cases (RelTransformer / Transformer called directly)
+# ---------------------------------------------------------------------------------------------
+def make_operator_state_dict(d, n_layers, seed=3):
+    """state_dict of a bare RelTransformer/Transformer (names 'encoder.layers.{l}....')."""
+    sd = OrderedDict()
+    f = d // 2
+    for l in range(n_layers):
+        p = f'encoder.layers.{l}'
+        a = 1.0 / np.sqrt(d)
+        for w in ('wq', 'wk', 'wv', 'wo'):
+            m = _uniform(f'op{d}/{p}.{w}', seed, (d, d), -a, a)
+            if w in ('wq', 'wk'):
+                m = m * np.float32(5.0)
+            sd[f'{p}.selfattn.layer.{w}.weight'] = m
+        sd[f'{p}.selfattn.layernorm.weight'] = 1.0 + _uniform(f'op{d}/{p}.ln1w', seed, (d,), -0.1, 0.1)
+        sd[f'{p}.selfattn.layernorm.bias'] = _uniform(f'op{d}/{p}.ln1b', seed, (d,), -0.1, 0.1)
+        sd[f'{p}.feedforward.layer.linear1.weight'] = _uniform(f'op{d}/{p}.l1w', seed, (f, d), -a, a)
+        sd[f'{p}.feedforward.layer.linear1.bias'] = _uniform(f'op{d}/{p}.l1b', seed, (f,), -0.05, 0.05)
+        a2 = 1.0 / np.sqrt(f)
+        sd[f'{p}.feedforward.layer.linear2.weight'] = _uniform(f'op{d}/{p}.l2w', seed, (d, f), -a2, a2)
+        sd[f'{p}.feedforward.layer.linear2.bias'] = _uniform(f'op{d}/{p}.l2b', seed, (d,), -0.05, 0.05)
+        sd[f'{p}.feedforward.layernorm.weight'] = 1.0 + _uniform(f'op{d}/{p}.ln2w', seed, (d,), -0.1, 0.1)
+        sd[f'{p}.feedforward.layernorm.bias'] = _uniform(f'op{d}/{p}.ln2b', seed, (d,), -0.1, 0.1)
+    return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)))
+                       for k, v in sd.items())
+
+
+def make_operator_inputs(d, n_heads, Bt, N, seed=3):
+    """x [Bt,N,d] ~ U(-1,1); dense bias x_pe [Bt,N,N,H] ~ U(0,8) with ~half the entries clamped
+    to 0 (it is a ReLU output in the model)."""
+    x = _uniform(f'opx/{d}/{Bt}/{N}', seed, (Bt, N, d), -1.0, 1.0)
+    pe = np.maximum(_uniform(f'oppe/{n_heads}/{Bt}/{N}', seed, (Bt, N, N, n_heads), -8.0, 8.0),
+                    np.float32(0.0))
+    return torch.from_numpy(x), torch.from_numpy(np.ascontiguousarray(pe))
