@@ -1,0 +1,86 @@
+/* libvog_b200 - C ABI of the B200-native VOGNet forward fusion path.
+ *
+ * The reference (TheShadow29/vognet-pytorch) is pure Python over PyTorch: it has no FFI layer, so
+ * each entry point below replaces a *library-call sequence* of the reference, cited as
+ * path:line relative to the reference root.  The Python host side
+ * (vognet_pytorch_b200/_lib.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller, row-major, with explicit leading
+ *     dimensions (in elements); nothing is allocated inside the library;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, nothing synchronises;
+ *   - return 0 on success, -1 on error; vog_last_error() returns the (thread-local) message;
+ *   - thread-compatible: no mutable global state besides per-function CUDA attributes.
+ */
+#ifndef VOG_B200_H
+#define VOG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOG_MAX_HEADS 8
+
+/* bias modes of the attention entry points */
+#define VOG_BIAS_NONE  0   /* plain Attention          code/transformer_code.py:41-50            */
+#define VOG_BIAS_RANK1 1   /* relu(a_i - a_j + b_h)    code/mdl_vog.py:456-490 in rank-1 form    */
+#define VOG_BIAS_DENSE 2   /* dense x_pe [Bt,N,N,H]    code/transformer_code.py:271-273 operator */
+
+/* low-precision copy kinds */
+#define VOG_LP_NONE 0
+#define VOG_LP_BF16 1
+#define VOG_LP_TF32 2      /* fp32 container, rounded to nearest tf32 */
+
+const char* vog_last_error(void);
+int vog_abi_version(void);
+/* 1 when the current device is sm_100 (B200); the tcgen05 entry points refuse to run otherwise */
+int vog_device_is_sm100(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * exact-fp32 path (CUDA cores)
+ * ------------------------------------------------------------------------------------------- */
+
+/* C[M,N] = (relu?)(A[M,K] . W[N,K]^T + bias[N]) + R[M,N]        (bias, R nullable)
+ * replaces nn.Linear (+ReLU) call sites: code/transformer_code.py:57-60,80-81,169-172,180,186;
+ * code/mdl_vog.py:202-207,224-230,291-314,675-677. */
+int vog_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias,
+                 const float* R, int ldr, float* C, int ldc, int M, int N, int K, int relu,
+                 void* stream);
+
+/* Multi-head attention with relative-position bias, all heads in one launch:
+ *   out[bt*N+i, off[h]+c] = sum_j softmax_j((q_i.k_j + bias_h(i,j)) * inv_scale) v_j[c]
+ * q,k,v: [Bt*N, ld] fp32, head h = columns off[h]..off[h]+dh[h] (torch.chunk split, uneven ok).
+ * bias_mode RANK1: a [Bt*nbox, H] (vog_pe_project output, scale=1), bpe[H] (device); token t
+ * uses box t % nbox.  bias_mode DENSE: dense [Bt,N,N,H].
+ * replaces RelMultiHead/RelAttention + MultiHead/Attention: code/transformer_code.py:34-70,128-186
+ * and the bias materialisation code/mdl_vog.py:477-488, utils/mdl_srl_utils.py:30-69. */
+int vog_attn_fwd_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
+                     int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
+                     int bias_mode, const float* a, int nbox, const float* bpe,
+                     const float* dense, void* stream);
+
+/* out = LayerNorm(x + r) * w + b (eps inside the sqrt), r nullable; optional low-precision copy
+ * out_lp (VOG_LP_*) for the next GEMM.  replaces ResidualBlock: code/transformer_code.py:21-31. */
+int vog_add_layernorm(const float* x, int ldx, const float* r, int ldr, const float* w,
+                      const float* b, float* out, int ldo, void* out_lp, int ldlp, int lp_kind,
+                      int M, int d, float eps, void* stream);
+
+/* a[row,h] = scale * W[h,:] . (x1/vw, y1/vh, x2/vw, y2/vh, frame/fdiv); props row stride ldp.
+ * The rank-1 factor of Linear(5,H) applied to p_i - p_j: code/mdl_vog.py:446-451,459-463,480. */
+int vog_pe_project(const float* props, int ldp, const float* W, float* a, int rows, int H,
+                   float vw, float vh, float fdiv, float scale, void* stream);
+
+/* Selection: scores [B,nsrl,P] (= mdl_outs_eval), props [B,P,pdim] ->
+ *   boxes [B,nsrl,ncmp,nfrm,pdim], out_scores [B,nsrl,ncmp,nfrm], indexs [B,nsrl,nfrm] (int64;
+ *   argmax over vids for spat, zeros for temp).  Lowest index wins ties (torch.max semantics).
+ * replaces EvaluatorSPAT/TEMP.get_out_results_boxes: code/eval_vsrl_corr.py:289-345,357-424. */
+int vog_select_fwd(const float* scores, const float* props, int pdim, float* boxes,
+                   float* out_scores, int64_t* indexs, int B, int nsrl, int ncmp, int nfrm,
+                   int nppf, int spat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOG_B200_H */

@@ -1,0 +1,84 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/vog_b200.h declares,
+the module surface keeps the reference's checkpoint contract, and the selector mirrors
+code/mdl_selector.py.  No GPU compute."""
+import os
+import re
+
+import pytest
+import torch
+
+import vognet_pytorch_b200 as vb
+from vognet_pytorch_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'vog_b200.h')).read()
+    declared = set(re.findall(r'\b(vog_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f'{name} declared in include/vog_b200.h but not exported'
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert L.vog_abi_version() >= 1
+    assert L.vog_last_error() is not None
+
+
+@pytest.mark.parametrize('conc', ['spat', 'temp'])
+def test_checkpoint_contract(conc):
+    cfg, comm = synth.default_cfg(conc), synth.default_comm(5)
+    sel = vb.get_mdl_loss_eval(cfg)
+    mdl = sel['mdl'](cfg, comm)
+    sd = synth.make_state_dict()
+    assert list(mdl.state_dict().keys()) == list(sd.keys()) or set(mdl.state_dict()) == set(sd)
+    mdl.load_state_dict(sd, strict=True)
+    for k, v in mdl.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    assert sum(p.numel() for p in mdl.parameters()) == 45250727       # SURVEY.md section 2b [probed]
+    assert not list(mdl.buffers())
+
+
+def test_selector_surface():
+    for conc, name, cls in (('spat', 'vog', 'VOG_SPAT'), ('temp', 'vog', 'VOG_TEMP'),
+                            ('spat', 'vgrnd', 'VidGrnd_SPAT'), ('temp', 'igrnd', 'ImgGrnd_TEMP')):
+        cfg = synth.default_cfg(conc)
+        cfg.mdl.name = name
+        out = vb.get_mdl_loss_eval(cfg)
+        assert set(out) == {'mdl', 'loss', 'eval'}
+        assert out['mdl'].__name__ == cls
+    cfg = synth.default_cfg('spat')
+    cfg.ds.conc_type = 'sep'
+    with pytest.raises(NotImplementedError):
+        vb.get_mdl_loss_eval(cfg)
+    cfg.ds.conc_type = 'spat'
+    cfg.mdl.name = 'nope'
+    with pytest.raises(NotImplementedError):
+        vb.get_mdl_loss_eval(cfg)
+
+
+def test_ablation_variants_have_reference_parameter_sets():
+    cfg, comm = synth.default_cfg('spat'), synth.default_comm(5)
+    from vognet_pytorch_b200 import mdl_vog
+    ig = set(mdl_vog.ImgGrnd_SPAT(cfg, comm).state_dict())
+    vg = set(mdl_vog.VidGrnd_SPAT(cfg, comm).state_dict())
+    vo_ = set(mdl_vog.VOG_SPAT(cfg, comm).state_dict())
+    assert not any(k.startswith(('obj_txf', 'mult_txf', 'pe_')) for k in ig)
+    assert any(k.startswith('obj_txf') for k in vg) and not any(k.startswith('mult_txf') for k in vg)
+    assert ig < vg < vo_
+
+
+def test_forward_refuses_cpu():
+    cfg, comm = synth.default_cfg('spat'), synth.default_comm(5)
+    mdl = vb.VOG_SPAT(cfg, comm).eval()
+    _, batch = synth.workload('cpu_ref')
+    with pytest.raises(RuntimeError):
+        mdl(batch)
+
+
+def test_synth_is_deterministic():
+    a, b = synth.make_state_dict(), synth.make_state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    _, b1 = synth.workload('spat_gt5')
+    _, b2 = synth.workload('spat_gt5')
+    assert all(torch.equal(b1[k], b2[k]) for k in b1)

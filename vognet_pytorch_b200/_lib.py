@@ -1,0 +1,94 @@
+"""ctypes binding of libvog_b200.so (C ABI declared in include/vog_b200.h).
+
+The library is built in-tree by ``build()`` (called from ``__graft_entry__.build()``) so that the
+``.so`` travels with the repo snapshot to the GPU box.  There is NO fallback: if the library is
+missing or a call fails the caller gets an exception.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+SO_PATH = os.path.join(_HERE, 'libvog_b200.so')
+SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'fused_glue.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-shared', '-Xcompiler', '-fPIC']
+
+_lock = threading.Lock()
+_lib = None
+
+c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+P = c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPE)
+_SIGNATURES = {
+    'vog_last_error': [],
+    'vog_abi_version': [],
+    'vog_device_is_sm100': [],
+    'vog_sgemm_nt': [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P],
+    'vog_attn_fwd_f32': [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, c_float, c_int, P,
+                         c_int, P, P, P],
+    'vog_add_layernorm': [P, c_int, P, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,
+                          c_float, P],
+    'vog_pe_project': [P, c_int, P, P, c_int, c_int, c_float, c_float, c_float, c_float, P],
+    'vog_select_fwd': [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+}
+_RESTYPE = {'vog_last_error': ctypes.c_char_p}
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def needs_build():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
+    deps.append(os.path.join(os.path.dirname(_HERE), 'include', 'vog_b200.h'))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> vognet_pytorch_b200/libvog_b200.so"""
+    if not force and not needs_build():
+        return SO_PATH
+    cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH] + sources()
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return SO_PATH
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(SO_PATH):
+                raise RuntimeError(
+                    f'{SO_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                    '(nvcc, sm_100a).  vognet_pytorch_b200 has no fallback path.')
+            l = ctypes.CDLL(SO_PATH)
+            for name, argtypes in _SIGNATURES.items():
+                fn = getattr(l, name)          # AttributeError if the symbol is not exported
+                fn.argtypes = argtypes
+                fn.restype = _RESTYPE.get(name, c_int)
+            _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().vog_last_error()
+        raise RuntimeError(f'{what} failed: {msg.decode() if msg else "unknown error"}')

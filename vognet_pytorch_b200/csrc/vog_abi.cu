@@ -1,0 +1,99 @@
+// extern "C" surface of libvog_b200 (declared in include/vog_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/vog_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vog {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+}  // namespace vog
+
+using namespace vog;
+
+extern "C" {
+
+const char* vog_last_error(void) { return g_err; }
+int vog_abi_version(void) { return 1; }
+
+int vog_device_is_sm100(void)
+{
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
+
+int vog_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias,
+                 const float* R, int ldr, float* C, int ldc, int M, int N, int K, int relu,
+                 void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "vog_sgemm_nt: negative dimension");
+    VOG_REQUIRE(A && W && C, "vog_sgemm_nt: null operand");
+    VOG_REQUIRE(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N), "vog_sgemm_nt: bad leading dimension");
+    return sgemm_nt(A, lda, W, ldw, bias, R, ldr, C, ldc, M, N, K, relu, (cudaStream_t)stream);
+}
+
+int vog_attn_fwd_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
+                     int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
+                     int bias_mode, const float* a, int nbox, const float* bpe,
+                     const float* dense, void* stream)
+{
+    VOG_REQUIRE(q && k && v && out && off && dh, "vog_attn_fwd_f32: null operand");
+    VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_attn_fwd_f32: negative dimension");
+    VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_attn_fwd_f32: bad bias_mode %d", bias_mode);
+    VOG_REQUIRE(bias_mode != VOG_BIAS_RANK1 || nbox > 0, "vog_attn_fwd_f32: nbox must be > 0");
+    return attn_f32(q, k, v, ld, out, ldo, Bt, N, H, off, dh, inv_scale, bias_mode, a, nbox, bpe,
+                    dense, (cudaStream_t)stream);
+}
+
+int vog_add_layernorm(const float* x, int ldx, const float* r, int ldr, const float* w,
+                      const float* b, float* out, int ldo, void* out_lp, int ldlp, int lp_kind,
+                      int M, int d, float eps, void* stream)
+{
+    VOG_REQUIRE(x && w && b && (out || out_lp), "vog_add_layernorm: null operand");
+    VOG_REQUIRE(!out_lp || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_add_layernorm: bad lp_kind");
+    return add_layernorm(x, ldx, r, ldr, w, b, out, ldo, out_lp, ldlp, lp_kind, M, d, eps,
+                         (cudaStream_t)stream);
+}
+
+int vog_pe_project(const float* props, int ldp, const float* W, float* a, int rows, int H,
+                   float vw, float vh, float fdiv, float scale, void* stream)
+{
+    VOG_REQUIRE(props && W && a, "vog_pe_project: null operand");
+    VOG_REQUIRE(ldp >= 5, "vog_pe_project: proposals need >= 5 columns");
+    return pe_project(props, ldp, W, a, rows, H, vw, vh, fdiv, scale, (cudaStream_t)stream);
+}
+
+int vog_select_fwd(const float* scores, const float* props, int pdim, float* boxes,
+                   float* out_scores, int64_t* indexs, int B, int nsrl, int ncmp, int nfrm,
+                   int nppf, int spat, void* stream)
+{
+    VOG_REQUIRE(scores && props && boxes && out_scores && indexs, "vog_select_fwd: null operand");
+    VOG_REQUIRE(nppf > 0 && ncmp > 0 && nfrm > 0, "vog_select_fwd: empty proposal group");
+    return select_fwd(scores, props, pdim, boxes, out_scores, (long long*)indexs, B, nsrl, ncmp,
+                      nfrm, nppf, spat, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""Model-level boundary: the ``mdl.name in {'igrnd','vgrnd','vog'}`` x ``conc_type in {'temp','spat'}``
+nn.Modules with the reference's constructor protocol ``cls(cfg, comm)`` (code/mdl_base.py:11-75),
+batch-dict ``forward(inp) -> {'mdl_outs', 'mdl_outs_eval'}`` (code/mdl_conc_single.py:68-127) and
+state_dict key names, so ``code/main_dist.py`` can build, ``.to(device)``,
+DDP-wrap, checkpoint and call them unchanged.
+
+What runs where
+  language side (a13)   torch + cuDNN LSTM, optionally on a side stream (code/mdl_vog.py:67-140,250-283)
+  everything else       libvog_b200 CUDA kernels through vognet_pytorch_b200.ops:
+      prop/seg encoders                       code/mdl_vog.py:291-314
+      prop|seg concat                         code/mdl_conc_single.py:50-66,156-174
+      object transformer + rank-1 rel. bias   code/mdl_vog.py:456-523
+      vis|lang concat + per-frame regroup     code/mdl_vog.py:316-344,693-699 (index math, never stored
+                                              in the tensor-core modes)
+      multimodal transformer                  code/mdl_vog.py:681-744
+      lin2 scorer, un-regroup, sigmoid*masks  code/mdl_vog.py:675-677, code/mdl_conc_single.py:118-127
+
+``sep``/``svsq`` concatenation (code/mdl_conc_sep.py) is outside the hot-path scope (SURVEY.md
+section 2 row 7) and raises NotImplementedError in the selector.
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import ops
+from .transformer_code import COMPUTE_MODES, RelBias, RelTransformer, Transformer
+
+
+class _LangEncoder(nn.Module):
+    """Parameter layout of the reference LSTMEncoder (utils/mdl_srl_utils.py:72-112)."""
+
+    def __init__(self, vocab_size, embed_dim, hidden, num_layers):
+        super().__init__()
+        self.padding_idx = vocab_size
+        self.embed_tokens = nn.Embedding(vocab_size + 1, embed_dim, self.padding_idx)
+        self.lstm = nn.LSTM(input_size=embed_dim, hidden_size=hidden, num_layers=num_layers,
+                            dropout=0.1 if num_layers > 1 else 0., bidirectional=True)
+
+
+def _lin_relu(i, o):
+    return nn.Sequential(nn.Linear(i, o), nn.ReLU())
+
+
+def _scorer(i):
+    return nn.Sequential(nn.Linear(i, 256), nn.ReLU(), nn.Linear(256, 1))
+
+
+class VOGNetB200(nn.Module):
+    CONC_TYPE = None       # 'spat' | 'temp'
+    USE_OBJ_TX = True      # VidGrnd / VOGNet
+    USE_MUL_TX = True      # VOGNet
+
+    def __init__(self, cfg, comm):
+        super().__init__()
+        self.cfg = cfg
+        self.comm = comm if comm is not None else {}
+        m = cfg.mdl
+        self.vocab_size = int(comm['vocab_size'])
+        self.num_prop_per_frm = int(comm['num_prop_per_frm'])
+        self.num_sampled_frm = int(cfg.ds.num_sampled_frm)
+        self.vid_w, self.vid_h = float(cfg.ds.resized_width), float(cfg.ds.resized_height)
+        self.srl_arg_len = int(cfg.misc.srl_arg_length)
+        pe_, se_, le_ = m.vsrl.prop_encode_size, m.vsrl.seg_encode_size, m.vsrl.lang_encode_size
+        self.ps_dim = pe_ + se_
+        self.vl_dim = self.ps_dim + le_
+        self.lang_dim = le_
+
+        # ---- language model (code/mdl_vog.py:160-193)
+        self.lstm_encoder = _LangEncoder(self.vocab_size, m.input_encoding_size, m.rnn.rnn_size,
+                                         m.rnn.num_layers)
+        self.lstm_out_feat_proj = _lin_relu(m.rnn.rnn_size * 2, le_)
+        self.srl_arg_words_out_enc = _lin_relu(le_ * 2, le_)
+        self.srl_simple_lin = _lin_relu(le_ * 3, le_)               # unused in temp/spat forward
+        # ---- visual model (:195-218, 417-454)
+        self.prop_encoder = _lin_relu(m.prop_feat_dim, pe_)
+        self.seg_encoder = _lin_relu(m.seg_feat_dim, se_)
+        self.seg_verb_classf = _scorer(se_ + le_)                    # SEP only
+        if self.USE_OBJ_TX:
+            self.obj_txf = self._make_tx(self.ps_dim, m.obj_tx)
+            self.pe_obj_sub_enc = _lin_relu(5, m.obj_tx.n_heads)
+        # ---- fusion model (:220-237, 547-585)
+        self.lin2 = _scorer(self.vl_dim)
+        self.lin_tmp = _scorer(self.vl_dim)                          # unused in temp/spat forward
+        if self.USE_MUL_TX:
+            if not (m.mul_tx.one_frm or m.mul_tx.cross_frm):
+                raise AssertionError('mul_tx needs one_frm or cross_frm (code/mdl_vog.py:622)')
+            if m.mul_tx.cross_frm:
+                raise NotImplementedError('mul_tx.cross_frm is dead code in the reference '
+                                          '(KeyError at code/mdl_vog.py:659-663)')
+            self.mult_txf = self._make_tx(self.vl_dim, m.mul_tx)
+            self.pe_mul_sub_enc = _lin_relu(5, m.mul_tx.n_heads)
+
+        self.compute = 'fp32x'
+        self.lang_side_stream = False
+
+    @staticmethod
+    def _make_tx(d, tx_cfg):
+        cls = RelTransformer if tx_cfg.use_rel else Transformer
+        kw = dict(d_hidden=d // 2, n_layers=tx_cfg.n_layers, n_heads=tx_cfg.n_heads,
+                  drop_ratio=tx_cfg.attn_drop, pe=False)
+        if tx_cfg.use_rel:
+            kw['d_pe'] = 5
+        return cls(d, 0, 0, **kw)
+
+    def set_compute(self, mode):
+        """'fp32x' exact fp32 CUDA cores | 'tf32' tcgen05 tf32 GEMMs + bf16 attention | 'bf16'."""
+        if mode not in COMPUTE_MODES:
+            raise ValueError(f'compute must be one of {COMPUTE_MODES}')
+        self.compute = mode
+        for t in ('obj_txf', 'mult_txf'):
+            if hasattr(self, t):
+                getattr(self, t).set_compute(mode)
+        return self
+
+    # -----------------------------------------------------------------------------------------
+    # language side: torch + cuDNN
+    # -----------------------------------------------------------------------------------------
+    def language_encode(self, inp):
+        """-> [B, nsrl, lang_dim] (num_verbs == 1 for temp/spat)."""
+        words = inp['srl_arg_words_ind']
+        B, nv, nsrl, L = words.shape
+        flat = words.reshape(B * nv, nsrl * L)
+        wm = inp['srl_arg_word_mask'].reshape(B * nv, -1)
+        pad = wm == -1
+        toks = torch.gather(flat, 1, wm.masked_fill(pad, 0))        # no in-place edit of inp
+        toks = toks.masked_fill(pad, self.vocab_size)
+        lens = inp['srl_arg_word_mask_len'].reshape(B * nv)
+        lens_cpu = lens.tolist() if lens.is_cuda else lens.tolist()
+        toks = toks[:, :max(lens_cpu)]
+        emb = self.lstm_encoder.embed_tokens(toks).transpose(0, 1)
+        packed = nn.utils.rnn.pack_padded_sequence(emb, lens_cpu, enforce_sorted=False)
+        out, _ = self.lstm_encoder.lstm(packed)
+        out, _ = nn.utils.rnn.pad_packed_sequence(out, padding_value=0.)
+        full = self.lstm_out_feat_proj(out.transpose(0, 1))          # [B*nv, T, le]
+        cap = inp['srl_arg_words_capture'].reshape(B * nv, nsrl, 2)
+        D = full.shape[-1]
+        st = torch.gather(full, 1, cap[..., 0].unsqueeze(-1).expand(B * nv, nsrl, D))
+        en = torch.gather(full, 1, cap[..., 1].unsqueeze(-1).expand(B * nv, nsrl, D))
+        enc = self.srl_arg_words_out_enc(torch.cat([st, en], 2))
+        enc = enc * inp['srl_arg_inds_msk'].reshape(B * nv, nsrl, 1).float()
+        return enc.view(B, nv * nsrl, D)
+
+    # -----------------------------------------------------------------------------------------
+    def _groups(self, ncmp):
+        """(nfrm, nppf') of the per-frame multimodal sequences (code/mdl_conc_single.py:24-28,131-135)."""
+        if self.CONC_TYPE == 'spat':
+            return self.num_sampled_frm, ncmp * self.num_prop_per_frm
+        return ncmp * self.num_sampled_frm, self.num_prop_per_frm
+
+    def forward(self, inp):
+        if self.training:
+            raise NotImplementedError('vognet_pytorch_b200: forward-only build; call .eval()')
+        feat = inp['pad_region_feature']
+        if not feat.is_cuda:
+            raise RuntimeError('vognet_pytorch_b200 runs on CUDA only (no CPU path); move the batch '
+                               'and the module to a B200 device')
+        if self.compute != 'fp32x':
+            raise NotImplementedError(self.compute)
+        with torch.no_grad():
+            return self._forward_fp32x(inp)
+
+    def _forward_fp32x(self, inp):
+        feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
+        B, P, _ = feat.shape
+        ncmp = inp['new_srl_idxs'].shape[1]
+        nppf = self.num_prop_per_frm
+        nvf = seg.shape[1]
+        assert nvf * nppf == P, (nvf, nppf, P)
+        nv = inp['srl_arg_words_ind'].shape[1]
+        assert nv == 1, 'temp/spat concatenation has one verb slot per query'
+        nsrl = inp['srl_arg_words_ind'].shape[2]
+        lang = self.language_encode(inp)                              # [B, nsrl, 256]
+
+        # prop|seg features: [B*P, 512], prop half written in place by the GEMM
+        x = torch.empty(B * P, self.ps_dim, device=feat.device, dtype=torch.float32)
+        pe_ = self.prop_encoder[0].out_features
+        ops.sgemm_nt(feat.reshape(B * P, -1), self.prop_encoder[0].weight, self.prop_encoder[0].bias,
+                     relu=True, out=x[:, :pe_])
+        segf = ops.sgemm_nt(seg.reshape(B * nvf, -1), self.seg_encoder[0].weight,
+                            self.seg_encoder[0].bias, relu=True)
+        x.view(B * nvf, nppf, self.ps_dim)[:, :, pe_:] = segf.unsqueeze(1)
+        props2 = props.reshape(B * P, props.shape[-1])
+
+        if self.USE_OBJ_TX and self.cfg.mdl.obj_tx.to_use:
+            otx = self.cfg.mdl.obj_tx
+            if otx.one_frm:                                           # code/mdl_vog.py:496-504
+                nfrm_o, nppf_o = self._groups(ncmp)
+                Bt_o, N_o, fdiv = B * nfrm_o, nppf_o, float(nfrm_o)
+            else:
+                Bt_o, N_o, fdiv = B, P, 1.0                           # code/mdl_vog.py:505-510
+            bias = None
+            if otx.use_rel:
+                a = ops.pe_project(props2, self.pe_obj_sub_enc[0].weight, self.vid_w, self.vid_h, fdiv)
+                bias = RelBias(a, self.pe_obj_sub_enc[0].bias, N_o)
+                x = self.obj_txf(x.view(Bt_o, N_o, self.ps_dim), bias)
+            else:
+                x = self.obj_txf(x.view(Bt_o, N_o, self.ps_dim))
+            x = x.reshape(B * P, self.ps_dim)
+
+        nfrm, nppf2 = self._groups(ncmp)
+        # token (b,f,s,p') = [vis[b, f*nppf'+p'] | lang[b,s]]  (code/mdl_vog.py:316-344,693-699)
+        vis = x.view(B, nfrm, 1, nppf2, self.ps_dim).expand(B, nfrm, nsrl, nppf2, self.ps_dim)
+        lng = lang.view(B, 1, nsrl, 1, self.lang_dim).expand(B, nfrm, nsrl, nppf2, self.lang_dim)
+        xm = torch.cat([vis, lng], -1).view(B * nfrm, nsrl * nppf2, self.vl_dim)
+        if self.USE_MUL_TX and self.cfg.mdl.mul_tx.to_use:
+            mtx = self.cfg.mdl.mul_tx
+            if mtx.use_rel:
+                a = ops.pe_project(props2, self.pe_mul_sub_enc[0].weight, self.vid_w, self.vid_h,
+                                   float(nfrm))                       # code/mdl_vog.py:710-713
+                xm = self.mult_txf(xm, RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2))
+            else:
+                xm = self.mult_txf(xm)
+        h = ops.sgemm_nt(xm.reshape(-1, self.vl_dim), self.lin2[0].weight, self.lin2[0].bias, relu=True)
+        lg = ops.sgemm_nt(h, self.lin2[2].weight, self.lin2[2].bias)  # [B*nfrm*nsrl*nppf', 1]
+        logits = lg.view(B, nfrm, nsrl, nppf2).transpose(1, 2).reshape(B, 1, nsrl, P)
+
+        # masks (code/mdl_conc_single.py:39-48,118-122,144-154)
+        cm = inp['num_cmp_msk'].float()
+        if self.CONC_TYPE == 'spat':
+            cmsk = cm.view(B, 1, 1, 1, ncmp, 1).expand(B, 1, nsrl, self.num_sampled_frm, ncmp, nppf)
+        else:
+            cmsk = cm.view(B, 1, 1, ncmp, 1).expand(B, 1, nsrl, ncmp, self.num_sampled_frm * nppf)
+        smsk = inp['srl_arg_inds_msk'].float().view(B, 1, nsrl, 1)
+        ev = torch.sigmoid(logits) * smsk * cmsk.reshape(B, 1, nsrl, P)
+        return {'mdl_outs': logits, 'mdl_outs_eval': ev}
+
+
+def _variant(name, conc, obj, mul):
+    return type(name, (VOGNetB200,), {'CONC_TYPE': conc, 'USE_OBJ_TX': obj, 'USE_MUL_TX': mul,
+                                      '__doc__': f'{name}: code/mdl_vog.py:393-398,526-535,747-756'})
+
+
+ImgGrnd_TEMP = _variant('ImgGrnd_TEMP', 'temp', False, False)
+ImgGrnd_SPAT = _variant('ImgGrnd_SPAT', 'spat', False, False)
+VidGrnd_TEMP = _variant('VidGrnd_TEMP', 'temp', True, False)
+VidGrnd_SPAT = _variant('VidGrnd_SPAT', 'spat', True, False)
+VOG_TEMP = _variant('VOG_TEMP', 'temp', True, True)
+VOG_SPAT = _variant('VOG_SPAT', 'spat', True, True)

@@ -1,0 +1,154 @@
+"""Tensor-level wrappers over the C ABI (include/vog_b200.h).
+
+PyTorch is used here for device memory and streams only: every function checks its operands,
+takes raw ``data_ptr()``s and enqueues the CUDA kernel on torch's current stream.  CPU tensors are
+rejected - there is no fallback implementation.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+BIAS_NONE, BIAS_RANK1, BIAS_DENSE = 0, 1, 2
+LP_NONE, LP_BF16, LP_TF32 = 0, 1, 2
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype, name, dims=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f'{name}: expected a CUDA tensor (vognet_pytorch_b200 has no CPU path)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if dims is not None and t.dim() != dims:
+        raise ValueError(f'{name}: expected {dims} dims, got shape {tuple(t.shape)}')
+
+
+def _rowmajor2d(t, name):
+    """(ld) of a 2-D view whose rows are contiguous (column slices of a wider matrix are fine)."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f'{name}: need a row-major 2-D tensor, got shape {tuple(t.shape)} strides {t.stride()}')
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def chunk_sizes(d, n_heads):
+    """torch.chunk split of the model dimension (code/transformer_code.py:66-67,182-183)."""
+    c = -(-d // n_heads)
+    out, left = [], d
+    while left > 0:
+        out.append(min(c, left))
+        left -= c
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def sgemm_nt(a, w, bias=None, residual=None, relu=False, out=None):
+    """out[M,N] = (relu?)(a[M,K] @ w[N,K]^T + bias) + residual        exact fp32"""
+    _req(a, torch.float32, 'a', 2), _req(w, torch.float32, 'w', 2)
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f'sgemm_nt: a is [{M},{K}] but w is {tuple(w.shape)}')
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _req(out, torch.float32, 'out', 2)
+    if bias is not None:
+        _req(bias, torch.float32, 'bias', 1)
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.float32, 'residual', 2)
+        ldr = _rowmajor2d(residual, 'residual')
+    L = _lib.lib()
+    _lib.check(L.vog_sgemm_nt(_ptr(a), _rowmajor2d(a, 'a'), _ptr(w), _rowmajor2d(w, 'w'), _ptr(bias),
+                              _ptr(residual), ldr, _ptr(out), _rowmajor2d(out, 'out'), M, N, K,
+                              int(relu), _stream()), 'vog_sgemm_nt')
+    return out
+
+
+def attn_fwd_f32(q, k, v, Bt, N, head_dims, inv_scale, out=None, bias_mode=BIAS_NONE, a=None,
+                 nbox=0, bpe=None, dense=None):
+    """q,k,v: [Bt*N, d] (row-major views, same ld); heads are consecutive column chunks."""
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _req(t, torch.float32, n, 2)
+    ld = _rowmajor2d(q, 'q')
+    if _rowmajor2d(k, 'k') != ld or _rowmajor2d(v, 'v') != ld:
+        raise ValueError('attn_fwd_f32: q, k, v must share one leading dimension')
+    H = len(head_dims)
+    d = sum(head_dims)
+    if out is None:
+        out = torch.empty(Bt * N, d, device=q.device, dtype=torch.float32)
+    offs = [sum(head_dims[:h]) for h in range(H)]
+    off_arr = (ctypes.c_int * H)(*offs)
+    dh_arr = (ctypes.c_int * H)(*head_dims)
+    if bias_mode == BIAS_RANK1:
+        _req(a, torch.float32, 'a', 2)
+        if a.shape != (Bt * nbox, H) or not a.is_contiguous():
+            raise ValueError(f'attn_fwd_f32: a must be contiguous [{Bt * nbox},{H}], got {tuple(a.shape)}')
+        _req(bpe, torch.float32, 'bpe', 1)
+    if bias_mode == BIAS_DENSE:
+        _req(dense, torch.float32, 'dense', 4)
+        if tuple(dense.shape) != (Bt, N, N, H) or not dense.is_contiguous():
+            raise ValueError(f'attn_fwd_f32: dense bias must be contiguous [{Bt},{N},{N},{H}]')
+    L = _lib.lib()
+    _lib.check(L.vog_attn_fwd_f32(_ptr(q), _ptr(k), _ptr(v), ld, _ptr(out), _rowmajor2d(out, 'out'),
+                                  Bt, N, H, off_arr, dh_arr, float(inv_scale), bias_mode, _ptr(a),
+                                  nbox, _ptr(bpe), _ptr(dense), _stream()), 'vog_attn_fwd_f32')
+    return out
+
+
+def add_layernorm(x, residual, weight, bias, eps=1e-5, out=None, out_lp=None, lp_kind=LP_NONE):
+    _req(x, torch.float32, 'x', 2)
+    M, d = x.shape
+    if out is None and out_lp is None:
+        out = torch.empty(M, d, device=x.device, dtype=torch.float32)
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.float32, 'residual', 2)
+        ldr = _rowmajor2d(residual, 'residual')
+    L = _lib.lib()
+    _lib.check(L.vog_add_layernorm(_ptr(x), _rowmajor2d(x, 'x'), _ptr(residual), ldr, _ptr(weight),
+                                   _ptr(bias), _ptr(out), _rowmajor2d(out, 'out') if out is not None else 0,
+                                   _ptr(out_lp), _rowmajor2d(out_lp, 'out_lp') if out_lp is not None else 0,
+                                   lp_kind, M, d, float(eps), _stream()), 'vog_add_layernorm')
+    return out if out is not None else out_lp
+
+
+def pe_project(props, W, vid_w, vid_h, fdiv, scale=1.0):
+    """props [rows, >=5] (row-major view) -> a [rows, H] = scale * W . normalised(props[:, :5])"""
+    _req(props, torch.float32, 'props', 2), _req(W, torch.float32, 'W', 2)
+    rows, H = props.shape[0], W.shape[0]
+    a = torch.empty(rows, H, device=props.device, dtype=torch.float32)
+    L = _lib.lib()
+    _lib.check(L.vog_pe_project(_ptr(props), _rowmajor2d(props, 'props'), _ptr(W.contiguous()), _ptr(a),
+                                rows, H, float(vid_w), float(vid_h), float(fdiv), float(scale),
+                                _stream()), 'vog_pe_project')
+    return a
+
+
+def select_fwd(scores, props, ncmp, nfrm, nppf, spat):
+    """scores [B,nsrl,P], props [B,P,pdim] -> boxes, scores, indexs (see vog_select_fwd)."""
+    _req(scores, torch.float32, 'scores', 3), _req(props, torch.float32, 'props', 3)
+    B, nsrl, Pn = scores.shape
+    pdim = props.shape[-1]
+    if Pn != ncmp * nfrm * nppf or props.shape[1] != Pn:
+        raise ValueError(f'select_fwd: P={Pn} != ncmp*nfrm*nppf={ncmp * nfrm * nppf}')
+    scores, props = scores.contiguous(), props.contiguous()
+    boxes = torch.empty(B, nsrl, ncmp, nfrm, pdim, device=scores.device, dtype=torch.float32)
+    sc = torch.empty(B, nsrl, ncmp, nfrm, device=scores.device, dtype=torch.float32)
+    ix = torch.empty(B, nsrl, nfrm, device=scores.device, dtype=torch.int64)
+    L = _lib.lib()
+    _lib.check(L.vog_select_fwd(_ptr(scores), _ptr(props), pdim, _ptr(boxes), _ptr(sc), _ptr(ix),
+                                B, nsrl, ncmp, nfrm, nppf, int(spat), _stream()), 'vog_select_fwd')
+    return boxes, sc, ix
+
+
+def inv_sqrt(d_model):
+    return 1.0 / math.sqrt(d_model)

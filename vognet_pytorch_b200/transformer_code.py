@@ -1,0 +1,169 @@
+"""Operator-level boundary: ``Transformer`` / ``RelTransformer`` with the reference's constructor
+signature, ``forward`` signature and state_dict key names (code/transformer_code.py:244-279), so
+reference checkpoints load with ``strict=True``:
+
+    encoder.layers.{l}.selfattn.layer.{wq,wk,wv,wo}.weight      [d,d]   (no bias, :169-172)
+    encoder.layers.{l}.selfattn.layernorm.{weight,bias}         [d]
+    encoder.layers.{l}.feedforward.layer.linear1.{weight,bias}  [d/2,d]
+    encoder.layers.{l}.feedforward.layer.linear2.{weight,bias}  [d,d/2]
+    encoder.layers.{l}.feedforward.layernorm.{weight,bias}      [d]
+
+The modules below are parameter containers only; the arithmetic of a layer
+(post-LN residual blocks :21-31, multi-head attention with the bias added before the
+1/sqrt(d_model) scaling :136-160,176-186, FFN :73-81) runs in the CUDA kernels of libvog_b200
+driven by ``EncoderExecutor``.  ``x_pe`` may be the reference's dense [Bt,N,N,H] tensor or a
+``RelBias`` descriptor (rank-1 factorisation; never materialises N x N).
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+
+COMPUTE_MODES = ('fp32x', 'tf32', 'bf16')
+
+
+class RelBias:
+    """bias[bt,i,j,h] = relu(a[bt*nbox + i % nbox, h] - a[bt*nbox + j % nbox, h] + b[h])
+
+    ``a`` = pe_enc.weight . normalised boxes (ops.pe_project), ``b`` = pe_enc.bias.  Equal to the
+    reference's Linear(5,H)+ReLU on pairwise box differences tiled nsrl x nsrl
+    (code/mdl_vog.py:477-488) because the Linear is applied to p_i - p_j."""
+
+    def __init__(self, a, b, nbox):
+        self.a, self.b, self.nbox = a, b, int(nbox)
+
+
+class _Heads(nn.Module):
+    def __init__(self, d, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+        self.wq = nn.Linear(d, d, bias=False)
+        self.wk = nn.Linear(d, d, bias=False)
+        self.wv = nn.Linear(d, d, bias=False)
+        self.wo = nn.Linear(d, d, bias=False)
+
+
+class _FFN(nn.Module):
+    def __init__(self, d, f):
+        super().__init__()
+        self.linear1 = nn.Linear(d, f)
+        self.linear2 = nn.Linear(f, d)
+
+
+class _PostLN(nn.Module):
+    def __init__(self, layer, d, drop):
+        super().__init__()
+        self.layer = layer
+        self.dropout = nn.Dropout(drop)
+        self.layernorm = nn.LayerNorm(d)
+
+
+class _Layer(nn.Module):
+    def __init__(self, d, f, n_heads, drop):
+        super().__init__()
+        self.selfattn = _PostLN(_Heads(d, n_heads), d, drop)
+        self.feedforward = _PostLN(_FFN(d, f), d, drop)
+
+
+class _Stack(nn.Module):
+    def __init__(self, d, f, n_layers, n_heads, drop):
+        super().__init__()
+        self.layers = nn.ModuleList([_Layer(d, f, n_heads, drop) for _ in range(n_layers)])
+        self.dropout = nn.Dropout(drop)
+
+
+class EncoderExecutor:
+    """Runs a ``_Stack`` on [Bt,N,d] CUDA input through libvog_b200."""
+
+    def __init__(self, stack, d_model, n_heads, drop_ratio):
+        self.stack = stack
+        self.d = d_model
+        self.H = n_heads
+        self.drop = drop_ratio
+        self.head_dims = ops.chunk_sizes(d_model, n_heads)
+        self._pack = {}
+
+    # -- packed weights, rebuilt whenever a parameter was updated in place or replaced ---------
+    def _packed(self, l, layer):
+        att = layer.selfattn.layer
+        key = tuple((p.data_ptr(), p._version) for p in (att.wq.weight, att.wk.weight, att.wv.weight))
+        ent = self._pack.get(l)
+        if ent is None or ent[0] != key:
+            wqkv = torch.cat([att.wq.weight, att.wk.weight, att.wv.weight], 0).detach().contiguous()
+            ent = (key, wqkv)
+            self._pack[l] = ent
+        return ent[1]
+
+    def run(self, x, bias, compute, training=False):
+        if training and self.drop > 0:
+            raise NotImplementedError('vognet_pytorch_b200: forward-only build (dropout/backward are '
+                                      'scheduled next, SURVEY.md section 8f); call .eval()')
+        if compute != 'fp32x':
+            raise NotImplementedError(f'compute mode {compute!r}')
+        Bt, N, d = x.shape
+        if d != self.d:
+            raise ValueError(f'expected last dim {self.d}, got {d}')
+        x2 = x.reshape(Bt * N, d)
+        if x2.dtype != torch.float32:
+            raise TypeError('activations must be float32')
+        x2 = x2.contiguous()
+        mode, a, bpe, nbox, dense = ops.BIAS_NONE, None, None, 0, None
+        if isinstance(bias, RelBias):
+            mode, a, bpe, nbox = ops.BIAS_RANK1, bias.a, bias.b, bias.nbox
+        elif bias is not None:
+            if tuple(bias.shape) != (Bt, N, N, self.H):
+                raise ValueError(f'x_pe must be [{Bt},{N},{N},{self.H}], got {tuple(bias.shape)}')
+            mode, dense = ops.BIAS_DENSE, bias.contiguous()
+        inv_scale = 1.0 / math.sqrt(d)          # sqrt(d_model), not sqrt(d_head): :132,:195
+        for l, layer in enumerate(self.stack.layers):
+            att, ffn = layer.selfattn, layer.feedforward
+            qkv = ops.sgemm_nt(x2, self._packed(l, layer))
+            o = ops.attn_fwd_f32(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], Bt, N, self.head_dims,
+                                 inv_scale, bias_mode=mode, a=a, nbox=nbox, bpe=bpe, dense=dense)
+            pre = ops.sgemm_nt(o, att.layer.wo.weight, residual=x2)
+            y = ops.add_layernorm(pre, None, att.layernorm.weight, att.layernorm.bias, att.layernorm.eps)
+            h = ops.sgemm_nt(y, ffn.layer.linear1.weight, ffn.layer.linear1.bias, relu=True)
+            pre2 = ops.sgemm_nt(h, ffn.layer.linear2.weight, ffn.layer.linear2.bias, residual=y)
+            x2 = ops.add_layernorm(pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps)
+        return x2.view(Bt, N, d)
+
+
+class _TransformerBase(nn.Module):
+    def __init__(self, d_model, d_hidden, n_layers, n_heads, drop_ratio, pe):
+        super().__init__()
+        if pe:
+            raise NotImplementedError('pe=True is not implemented in the reference either '
+                                      '(code/transformer_code.py:110-113)')
+        self.encoder = _Stack(d_model, d_hidden, n_layers, n_heads, drop_ratio)
+        self.compute = 'fp32x'
+        self._exec = EncoderExecutor(self.encoder, d_model, n_heads, drop_ratio)
+
+    def set_compute(self, mode):
+        if mode not in COMPUTE_MODES:
+            raise ValueError(f'compute must be one of {COMPUTE_MODES}')
+        self.compute = mode
+        return self
+
+
+class Transformer(_TransformerBase):
+    """Plain encoder stack (use_rel=False, the yml default): code/transformer_code.py:244-260."""
+
+    def __init__(self, d_model, n_vocab_src, vocab_trg, d_hidden=2048, n_layers=6, n_heads=8,
+                 drop_ratio=0.1, pe=False):
+        super().__init__(d_model, d_hidden, n_layers, n_heads, drop_ratio, pe)
+
+    def forward(self, x):
+        return self._exec.run(x, None, self.compute, self.training)
+
+
+class RelTransformer(_TransformerBase):
+    """Relative-position-bias encoder stack: code/transformer_code.py:263-279."""
+
+    def __init__(self, d_model, n_vocab_src, vocab_trg, d_hidden=2048, n_layers=6, n_heads=8,
+                 drop_ratio=0.1, pe=False, d_pe=None):
+        super().__init__(d_model, d_hidden, n_layers, n_heads, drop_ratio, pe)
+
+    def forward(self, x, x_pe):
+        return self._exec.run(x, x_pe, self.compute, self.training)
