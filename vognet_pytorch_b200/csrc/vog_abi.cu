@@ -50,6 +50,7 @@ int vog_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* 
                  void* stream)
 {
     VOG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "vog_sgemm_nt: negative dimension");
+    if (M == 0 || N == 0) return 0;
     VOG_REQUIRE(A && W && C, "vog_sgemm_nt: null operand");
     VOG_REQUIRE(lda >= K && ldw >= K && ldc >= N && (!R || ldr >= N), "vog_sgemm_nt: bad leading dimension");
     return sgemm_nt(A, lda, W, ldw, bias, R, ldr, C, ldc, M, N, K, relu, (cudaStream_t)stream);
