@@ -80,6 +80,44 @@ int vog_select_fwd(const float* scores, const float* props, int pdim, float* box
                    float* out_scores, int64_t* indexs, int B, int nsrl, int ncmp, int nfrm,
                    int nppf, int spat, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * tensor-core path (tcgen05.mma + TMA + TMEM, sm_100a only; these refuse to run elsewhere)
+ * ------------------------------------------------------------------------------------------- */
+
+/* dst = bf16(src) (VOG_LP_BF16) or tf32-rounded fp32 (VOG_LP_TF32): A operand of the GEMMs below. */
+int vog_cast_lp(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols,
+                int kind, void* stream);
+
+/* C = (relu?)(A[M,K] . W[N,K]^T + bias) + residual, A/W bf16 (tf32=0) or tf32-rounded fp32
+ * (tf32=1), fp32 accumulation in TMEM.  128 x BN tiles (BN multiple of 32, <= 256), persistent
+ * grid.  Outputs: out_f32 and/or a low-precision copy out_lp (lp_kind); every output row m is
+ * written to rows m*rep .. m*rep+rep-1 (rep > 1 broadcasts a segment feature over the proposals of
+ * its frame: code/mdl_conc_single.py:50-66,156-174).  Same call sites as vog_sgemm_nt. */
+int vog_tc_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                int tf32, int BN, const float* bias, int relu, const float* residual, int64_t ldr,
+                float* out_f32, int64_t ldc, void* out_lp, int64_t ldlp, int lp_kind, int rep,
+                void* stream);
+
+/* Fused Q/K/V projection: A[M,K] . Wqkv[3*H*dhp, K]^T with Wqkv = per-head zero-padded rows of
+ * wq|wk|wv (dhp = head dim rounded up to 64).  Writes bf16 Q,K as [Bt,H,seq_n,dhp] and V
+ * TRANSPOSED as [Bt,H,dhp,npad] (M = Bt*seq_n), the layouts vog_tc_attn_fwd consumes.
+ * replaces wq/wk/wv + chunk: code/transformer_code.py:180-183. */
+int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, int M, int K,
+                    int tf32, int n_heads, int dhp, int seq_n, int npad, void* q, void* k, void* vt,
+                    void* stream);
+
+/* Fused attention, all heads and sequences in one launch (tcgen05 QK^T and PV, online softmax with
+ * on-the-fly relative-position bias; the N x N matrices never reach HBM):
+ *   out[bt*N+i, h*dhp+c] = sum_j softmax_j((q_i.k_j + bias_h(i,j)) * inv_scale) v_j[c]
+ * q,k [Bt,H,N,dhp] bf16, vt [Bt,H,dhp,npad] bf16 (vog_tc_gemm_qkv layouts), dh[H] true head dims
+ * (host array), bias as in vog_attn_fwd_f32 (a, bpe, dense are device pointers).  out is
+ * [Bt*N, ldo >= H*dhp], bf16 (out_kind VOG_LP_BF16) or tf32-rounded fp32 (VOG_LP_TF32); padded
+ * head columns are written as zeros.  Same reference lines as vog_attn_fwd_f32. */
+int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp,
+                    int npad, const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
+                    const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,109 @@
+"""tcgen05 fused attention (vog_tc_attn_fwd) against a float64 softmax-attention of the same
+bf16-rounded Q/K/V.  What is left: P rounded to bf16 before the PV product (relative 2^-9 per
+probability, averaging out over keys), ex2.approx, fp32 accumulation -> 4e-3 absolute on O(1)
+outputs is the stated bf16-attention tolerance here (end-to-end score tolerances are checked in
+test_gpu_model_tc.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vognet_pytorch_b200 import ops      # noqa: E402
+
+DEV = 'cuda:0'
+
+
+def _u(shape, seed, lo=-1.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+
+def _pack(x, Bt, N, hd, dhp, transpose=False):
+    """[Bt*N, d] fp32 -> bf16 [Bt,H,N,dhp] (or [Bt,H,dhp,Npad])"""
+    H = len(hd)
+    out = torch.zeros(Bt, H, N, dhp)
+    off = 0
+    for h, dh in enumerate(hd):
+        out[:, h, :, :dh] = x.view(Bt, N, -1)[:, :, off:off + dh]
+        off += dh
+    out = out.bfloat16()
+    if transpose:
+        npad = ops.round_up(N, 8)
+        t = torch.zeros(Bt, H, dhp, npad, dtype=torch.bfloat16)
+        t[..., :N] = out.transpose(2, 3)
+        return t
+    return out
+
+
+def _ref(qp, kp, vp, N, hd, scale, bias):
+    """float64 reference on the bf16-rounded packed operands -> [Bt, N, H, dhp]"""
+    Bt, H = qp.shape[:2]
+    s = qp.double() @ kp.double().transpose(2, 3)            # [Bt,H,N,N]
+    if bias is not None:
+        s = s + bias.permute(0, 3, 1, 2).double()
+    p = torch.softmax(s * scale, -1)
+    o = p @ vp.double()[..., :N].transpose(2, 3)             # [Bt,H,N,dhp]
+    return o.permute(0, 2, 1, 3)
+
+
+CASES = [
+    # Bt, N, d, H, mode, qk_gain
+    (2, 200, 512, 3, 'rank1', 1.0),      # spat/gt5 obj shape, dh 171/171/170 -> dhp 192
+    (3, 100, 768, 3, 'rank1', 1.0),      # spat/gt5 mul shape, dh 256
+    (2, 64, 512, 3, 'none', 1.0),
+    (1, 130, 512, 6, 'dense', 1.0),      # 6-head ablation: dh 86/82 -> dhp 128
+    (1, 1, 512, 3, 'rank1', 1.0),
+    (2, 257, 64, 1, 'dense', 1.0),       # dhp 64, ragged
+    (1, 1000, 768, 3, 'rank1', 3.0),     # many key tiles, sharper logits
+    (1, 640, 512, 3, 'rank1', 40.0),     # very peaked softmax: exercises the lazy-rescale path
+]
+
+
+@pytest.mark.parametrize('Bt,N,d,H,mode,gain', CASES)
+@pytest.mark.parametrize('out_kind', [ops.LP_BF16, ops.LP_TF32])
+def test_tc_attention(Bt, N, d, H, mode, gain, out_kind):
+    if out_kind == ops.LP_TF32 and N > 300:
+        pytest.skip('fp32 output variant covered on the small cases')
+    hd = ops.chunk_sizes(d, H)
+    dhp = ops.round_up(max(hd), 64)
+    q, k, v = _u((Bt * N, d), 7) * gain, _u((Bt * N, d), 8), _u((Bt * N, d), 9)
+    qp, kp, vtp = _pack(q, Bt, N, hd, dhp), _pack(k, Bt, N, hd, dhp), _pack(v, Bt, N, hd, dhp, True)
+    nbox = N if N < 20 else (N // 5 if N % 5 == 0 else N)
+    a = _u((Bt * nbox, H), 10, -30, 30)
+    bpe = _u((H,), 11, -3, 3)
+    bias, kw = None, {}
+    if mode == 'rank1':
+        ai = a.view(Bt, nbox, H)[:, torch.arange(N) % nbox]
+        bias = torch.relu(ai.unsqueeze(2) - ai.unsqueeze(1) + bpe)
+        kw = dict(bias_mode=ops.BIAS_RANK1, a=a.to(DEV), nbox=nbox, bpe=bpe.to(DEV))
+    elif mode == 'dense':
+        bias = torch.relu(_u((Bt, N, N, H), 12, -40, 40))
+        kw = dict(bias_mode=ops.BIAS_DENSE, dense=bias.to(DEV))
+    scale = 1.0 / d ** 0.5
+    ref = _ref(qp, kp, vtp, N, hd, scale, bias)
+    out = ops.tc_attn_fwd(qp.to(DEV), kp.to(DEV), vtp.to(DEV), N, hd, scale, out_kind=out_kind, **kw)
+    torch.cuda.synchronize()
+    got = out.float().cpu().view(Bt, N, H, dhp)
+    assert torch.isfinite(got).all()
+    for h, dh in enumerate(hd):
+        err = (got[:, :, h, :dh].double() - ref[:, :, h, :dh]).abs().max().item()
+        assert err < (8e-3 if gain > 10 else 4e-3), (h, err)    # peaked rows: one P~1 rounded to bf16
+        if dh < dhp:
+            assert got[:, :, h, dh:].abs().max() == 0, 'padded head columns must be zero'
+
+
+def test_tc_attention_monotone_logits_force_rescale():
+    """keys ordered so that every tile raises the row max by far more than 2^8."""
+    Bt, N, d, H = 1, 512, 64, 1
+    hd, dhp = [64], 64
+    q = torch.ones(N, d)
+    k = (torch.arange(N).float().view(N, 1) / N * 16 - 8).expand(N, d).contiguous()   # logits -512..512 /8
+    v = _u((N, d), 13)
+    qp, kp, vtp = _pack(q, Bt, N, hd, dhp), _pack(k, Bt, N, hd, dhp), _pack(v, Bt, N, hd, dhp, True)
+    scale = 1.0 / 2.0
+    ref = _ref(qp, kp, vtp, N, hd, scale, None)
+    out = ops.tc_attn_fwd(qp.to(DEV), kp.to(DEV), vtp.to(DEV), N, hd, scale)
+    torch.cuda.synchronize()
+    got = out.float().cpu().view(Bt, N, 1, dhp)
+    assert torch.isfinite(got).all()
+    assert (got.double() - ref).abs().max() < 8e-3

@@ -1,0 +1,85 @@
+"""tcgen05 GEMM (vog_tc_gemm / vog_tc_gemm_qkv) against a float64 product of the SAME rounded
+operands: the only differences left are fp32 accumulation order, so the tolerance is tight."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vognet_pytorch_b200 import ops      # noqa: E402
+
+DEV = 'cuda:0'
+
+
+def _u(shape, seed, lo=-1.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+
+def _tf32(x):
+    i = x.view(torch.int32)
+    return (((i + 0x1000) & ~0x1FFF)).view(torch.float32)
+
+
+@pytest.mark.parametrize('M,N,K,BN', [(128, 128, 64, 128), (128, 256, 512, 256), (300, 256, 2048, 256),
+                                      (1000, 768, 768, 256), (77, 384, 768, 128), (4000, 512, 576, 256),
+                                      (200, 192, 64, 192), (129, 64, 8, 64), (5, 32, 3072, 32)])
+@pytest.mark.parametrize('mode', ['bf16', 'tf32'])
+def test_tc_gemm_plain(M, N, K, BN, mode):
+    a, w = _u((M, K), 1), _u((N, K), 2)
+    if mode == 'bf16':
+        al, wl = a.bfloat16(), w.bfloat16()
+    else:
+        al, wl = _tf32(a), _tf32(w)
+    ref = al.double() @ wl.double().t()
+    out, _ = ops.tc_gemm(al.to(DEV), wl.to(DEV), BN=BN)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, (K / 64) ** 0.5), err
+
+
+def test_tc_gemm_epilogue_all_options():
+    M, N, K, rep = 150, 256, 320, 3
+    a, w, b = _u((M, K), 3).bfloat16(), _u((N, K), 4).bfloat16(), _u((N,), 5)
+    res = _u((M, N), 6)
+    ref = torch.relu(a.double() @ w.double().t() + b.double()) + res.double()
+    o32 = torch.zeros(M * rep, 300, device=DEV)
+    olp = torch.zeros(M * rep, 264, device=DEV, dtype=torch.bfloat16)
+    ops.tc_gemm(a.to(DEV), w.to(DEV), bias=b.to(DEV), residual=res.to(DEV), relu=True,
+                out_f32=o32[:, 20:276], out_lp=olp[:, 8:264], rep=rep)
+    got = o32[:, 20:276].cpu().view(M, rep, N)
+    for r in range(rep):
+        assert (got[:, r].double() - ref).abs().max() < 3e-4
+    assert o32[:, :20].abs().max() == 0 and o32[:, 276:].abs().max() == 0
+    lp = olp[:, 8:264].cpu().view(M, rep, N)
+    assert (lp[:, 1].double() - ref).abs().max() < 2e-2
+    assert torch.equal(lp[:, 0], got[:, 0].bfloat16())
+    # tf32-rounded low precision copy
+    _, o2 = ops.tc_gemm(a.to(DEV), w.to(DEV), lp_kind=ops.LP_TF32, want_f32=False)
+    assert torch.equal(o2.cpu(), _tf32((a.double() @ w.double().t()).float())) or \
+        (o2.cpu().double() - a.double() @ w.double().t()).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize('Bt,N,d,H', [(2, 200, 512, 3), (3, 100, 768, 3), (1, 37, 512, 6), (2, 128, 512, 3)])
+def test_tc_gemm_qkv_scatter(Bt, N, d, H):
+    hd = ops.chunk_sizes(d, H)
+    dhp = ops.round_up(max(hd), 64)
+    x = _u((Bt * N, d), 7).bfloat16()
+    ws = [_u((d, d), 8 + i) for i in range(3)]
+    wp = torch.zeros(3 * H * dhp, d)
+    for i, wm in enumerate(ws):
+        off = 0
+        for h, dh in enumerate(hd):
+            wp[(i * H + h) * dhp:(i * H + h) * dhp + dh] = wm[off:off + dh]
+            off += dh
+    wp = wp.bfloat16()
+    q, k, vt = ops.tc_gemm_qkv(x.to(DEV), wp.to(DEV), Bt, N, H, dhp)
+    torch.cuda.synchronize()
+    full = (x.double() @ wp.double().t()).view(Bt, N, 3, H, dhp)
+    for got, which in ((q, 0), (k, 1)):
+        ref = full[:, :, which].permute(0, 2, 1, 3)
+        assert (got.cpu().double() - ref).abs().max() < 3e-2
+    refv = full[:, :, 2].permute(0, 2, 3, 1)                     # [Bt,H,dhp,N]
+    assert (vt.cpu().double()[..., :N] - refv).abs().max() < 3e-2
+    # padded head columns are exact zeros
+    for h, dh in enumerate(hd):
+        assert q[:, h, :, dh:].abs().max() == 0 and vt[:, h, dh:, :].abs().max() == 0

@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 _lock = threading.Lock()
 _lib = None
 
-c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64
 P = c_void_p
 
 # name -> argtypes (restype is int unless listed in _RESTYPE)
@@ -34,6 +34,12 @@ _SIGNATURES = {
                           c_float, P],
     'vog_pe_project': [P, c_int, P, P, c_int, c_int, c_float, c_float, c_float, c_float, P],
     'vog_select_fwd': [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    'vog_cast_lp': [P, c_i64, P, c_i64, c_i64, c_int, c_int, P],
+    'vog_tc_gemm': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64,
+                    P, c_i64, P, c_i64, c_int, c_int, P],
+    'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,
+                        c_i64, c_int, P],
+    'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
 }
 _RESTYPE = {'vog_last_error': ctypes.c_char_p}
 

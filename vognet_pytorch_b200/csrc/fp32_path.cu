@@ -420,4 +420,35 @@ int select_fwd(const float* scores, const float* props, int pdim, float* boxes, 
     return check_launch("select_vid");
 }
 
+// =============================================================================================
+// fp32 -> bf16 / tf32-rounded copy of an activation matrix (A operand of the tcgen05 GEMMs)
+// =============================================================================================
+__global__ void cast_lp_kernel(const float* __restrict__ src, long long lds, void* __restrict__ dst,
+                               long long ldd, long long rows, int cols4, int kind)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols4) return;
+    long long r = idx / cols4; int c = (int)(idx % cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+    if (kind == 1) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + r * ldd + c) = o;
+    } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + r * ldd + c) =
+            make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
+}
+
+int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int kind,
+            cudaStream_t st)
+{
+    if (rows == 0 || cols == 0) return 0;
+    VOG_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cast_lp: cols and leading dims must be multiples of 4");
+    VOG_REQUIRE(kind == 1 || kind == 2, "cast_lp: bad kind");
+    long long n = rows * (cols / 4);
+    cast_lp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, lds, dst, ldd, rows, cols / 4, kind);
+    return check_launch("cast_lp");
+}
+
 }  // namespace vog

@@ -2,6 +2,7 @@
 // vog_abi.cu (declared in include/vog_b200.h) is a thin argument-checking shim over these.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 
 #define VOG_MAX_HEADS 8
 
@@ -23,5 +24,29 @@ int pe_project(const float* props, int ldp, const float* W, float* a, int rows, 
 int select_fwd(const float* scores, const float* props, int pdim, float* boxes, float* out_scores,
                long long* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, int spat,
                cudaStream_t st);
+
+// ---- tc_gemm.cu : tcgen05 / TMA / TMEM GEMM ---------------------------------------------------
+struct TcEpilogue {
+    int mode = 0;                 // 0 standard, 1 QKV scatter
+    const float* bias = nullptr;  // [N]
+    int relu = 0;
+    const float* residual = nullptr; long long ldr = 0;   // fp32 [M,N]
+    float* out_f32 = nullptr; long long ldc = 0;
+    void* out_lp = nullptr; long long ldlp = 0; int lp_kind = 0;   // 1 bf16, 2 tf32-rounded fp32
+    int rep = 1;                  // every output row m is written to rows m*rep .. m*rep+rep-1
+    // mode 1: column block n_blk = which*H + h (BN == dhp); rows m = bt*seq_n + i
+    __nv_bfloat16* q = nullptr; __nv_bfloat16* k = nullptr;   // [Bt,H,seq_n,dhp]
+    __nv_bfloat16* vt = nullptr;                              // [Bt,H,dhp,npad]
+    int seq_n = 0, n_heads = 0, dhp = 0, npad = 0;
+};
+int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int tf32,
+            int BN, const TcEpilogue& epi, cudaStream_t st);
+int num_sms();
+// ---- tc_attn.cu : fused relative-position-bias attention (tcgen05) ---------------------------
+int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
+            const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
+            const float* dense, void* out, long long ldo, int out_kind, cudaStream_t st);
+int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int kind,
+            cudaStream_t st);
 
 }  // namespace vog

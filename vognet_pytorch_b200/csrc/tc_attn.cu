@@ -1,0 +1,369 @@
+// Fused relative-position-bias attention for sm_100a (tcgen05 + TMA + TMEM), one launch for all
+// (sequence, head, 128-query tile) triples:
+//
+//     O[i,:] = sum_j softmax_j((q_i.k_j + relu(a_i - a_j + b_h)) / sqrt(d_model)) v_j
+//
+// replaces, per RelEncoderLayer, the reference's python loop over heads with
+// bmm -> add bias -> div -> softmax -> bmm on materialised [Bt,N,N] fp32 tensors
+// (code/transformer_code.py:136-160,182-186) AND the materialisation of the bias itself
+// (code/mdl_vog.py:477-488, utils/mdl_srl_utils.py:30-69): the N x N score / probability / bias
+// matrices never exist in HBM.
+//
+//   warp 0      TMA producer: Q tile once, then a ring of {K_j [64 keys x dhp], V^T_j [dhp x 64 keys]}
+//               stages; its idle lanes stage the rank-1 bias factor a_j of the 64 keys next to them
+//   warp 1      single-thread tcgen05.mma issuer:  S_j = Q K_j^T  (128 x 64, TMEM, double buffered)
+//               and O += P_j V_j (128 x dh, TMEM); S_{j+1} is issued before P_j is awaited so the
+//               tensor pipe runs while the softmax warps work
+//   warps 2-5   one query row per thread: tcgen05.ld S row, bias + scale (exp2 domain), online
+//               softmax with LAZY rescaling of the TMEM accumulator (only when a row max grows by
+//               more than 2^8), P written as bf16 into a 128B-swizzled smem tile that feeds the PV MMA
+//
+// Layouts (produced by vog_tc_gemm_qkv): Q,K [Bt,H,N,dhp] bf16, V^T [Bt,H,dhp,Npad] bf16, head dim
+// zero-padded to dhp (multiple of 64).  Output [Bt*N, H*dhp] (bf16, or tf32-rounded fp32), heads
+// side by side in padded slots - the A operand of the (column-padded) Wo GEMM.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace vog {
+
+using namespace tc;
+
+constexpr int FA_BQ = 128;          // query rows per CTA
+constexpr int FA_BKV = 64;          // keys per pipeline stage
+constexpr int FA_THREADS = 192;
+constexpr int FA_MAX_STAGES = 8;
+constexpr float FA_RESCALE_T = 8.0f;   // log2 units
+
+struct AttnParams {
+    int Bt, N, H, dhp, npad;
+    int dh[VOG_MAX_HEADS];
+    float c;                    // log2(e) / sqrt(d_model)
+    int bias_mode;              // 0 none, 1 rank-1, 2 dense
+    const float* a; int nbox;   // [Bt*nbox, H]
+    const float* bpe;           // [H]
+    const float* dense;         // [Bt,N,N,H]
+    void* out; long long ldo; int out_kind;   // 1 bf16, 2 tf32-rounded fp32
+    int stages;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+               const __grid_constant__ CUtensorMap tma_vt, const AttnParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
+
+    const int q_tile = blockIdx.x, h = blockIdx.y, bt = blockIdx.z;
+    const int dhp = p.dhp, N = p.N;
+    const int dh = p.dh[h];
+    const int nkk = dhp / 64;                         // 64-wide sub-tiles of the head dimension
+    const int T = (N + FA_BKV - 1) / FA_BKV;          // key tiles
+
+    // ---- shared memory carve-up (all tile bases 1024-aligned)
+    const uint32_t q_bytes = FA_BQ * dhp * 2;
+    const uint32_t k_bytes = FA_BKV * dhp * 2;        // nkk sub-tiles of [64 rows x 128 B]
+    const uint32_t v_bytes = dhp * 128;               // [dhp rows x 128 B]
+    const uint32_t stage_bytes = k_bytes + v_bytes;
+    const uint32_t q_smem = smem_base;
+    const uint32_t p_smem0 = q_smem + q_bytes;        // 2 x [128 x 128 B]
+    const uint32_t kv_smem0 = p_smem0 + 2 * FA_BQ * 128;
+    const uint32_t aux_off = (kv_smem0 - smem_base) + p.stages * stage_bytes;
+    float* ak_gen = reinterpret_cast<float*>(smem_gen + aux_off);          // [stages][64]
+    const uint32_t bar_off = aux_off + p.stages * FA_BKV * 4;
+    const uint32_t bar_base = smem_base + bar_off;
+    auto kv_full = [&](int s) { return bar_base + 8u * s; };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (FA_MAX_STAGES + s); };
+    auto s_full = [&](int b) { return bar_base + 8u * (2 * FA_MAX_STAGES + b); };
+    auto p_full = [&](int b) { return bar_base + 8u * (2 * FA_MAX_STAGES + 2 + b); };
+    auto p_empty = [&](int b) { return bar_base + 8u * (2 * FA_MAX_STAGES + 4 + b); };
+    const uint32_t q_full = bar_base + 8u * (2 * FA_MAX_STAGES + 6);
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(
+        smem_gen + bar_off + 8 * (2 * FA_MAX_STAGES + 7));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_vt);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(kv_full(s), 2); mbar_init(kv_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 128); mbar_init(p_empty(b), 1); }
+        mbar_init(q_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_o = tmem_base;                 // columns [0, dhp)
+    const uint32_t tmem_s0 = tmem_base + dhp;          // 2 x 64 columns
+
+    const int bh = bt * p.H + h;
+
+    if (warp == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, q_bytes);
+            for (int kk = 0; kk < nkk; ++kk)
+                tma_load_3d(q_smem + kk * (FA_BQ * 128), &tma_q, q_full, kk * 64, q_tile * FA_BQ, bh);
+        }
+        int s = 0; uint32_t ph = 0;
+        for (int j = 0; j < T; ++j) {
+            if (lane == 0) mbar_wait(kv_empty(s), ph ^ 1);
+            __syncwarp();
+            const uint32_t kdst = kv_smem0 + s * stage_bytes;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(kv_full(s), stage_bytes);
+                for (int kk = 0; kk < nkk; ++kk)
+                    tma_load_3d(kdst + kk * (FA_BKV * 128), &tma_k, kv_full(s), kk * 64, j * FA_BKV, bh);
+                tma_load_3d(kdst + k_bytes, &tma_vt, kv_full(s), j * FA_BKV, 0, bh);
+            }
+            if (p.bias_mode == 1) {
+#pragma unroll
+                for (int t = lane; t < FA_BKV; t += 32) {
+                    const int key = j * FA_BKV + t;
+                    float v = 0.f;
+                    if (key < N) v = __ldg(p.a + ((size_t)bt * p.nbox + key % p.nbox) * p.H + h) * p.c;
+                    ak_gen[s * FA_BKV + t] = v;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(kv_full(s));
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc(FMT_BF16, FA_BQ, FA_BKV);
+            const int n_pv = (dh + 15) & ~15;
+            const uint32_t idesc_o = umma_idesc(FMT_BF16, FA_BQ, n_pv);
+            const int ksteps = (dh + 15) / 16;           // skip the all-zero padded tail of the head dim
+            auto issue_s = [&](int j) {
+                const int s = j % p.stages;
+                mbar_wait(kv_full(s), (uint32_t)((j / p.stages) & 1));
+                tc_fence_after();
+                const uint32_t kbase = kv_smem0 + s * stage_bytes;
+                const uint32_t d = tmem_s0 + (j & 1) * FA_BKV;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int kk = ks >> 2, k4 = ks & 3;
+                    const uint64_t ad = umma_desc_sw128(q_smem + kk * (FA_BQ * 128)) + 2 * k4;
+                    const uint64_t bd = umma_desc_sw128(kbase + kk * (FA_BKV * 128)) + 2 * k4;
+                    umma<false>(d, ad, bd, idesc_s, ks != 0);
+                }
+                umma_commit(s_full(j & 1));
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) issue_s(j + 1);
+                const int s = j % p.stages, pb = j & 1;
+                mbar_wait(p_full(pb), (uint32_t)((j >> 1) & 1));
+                tc_fence_after();
+                const uint32_t vbase = kv_smem0 + s * stage_bytes + k_bytes;
+                const uint64_t ad0 = umma_desc_sw128(p_smem0 + pb * (FA_BQ * 128));
+                const uint64_t bd0 = umma_desc_sw128(vbase);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    umma<false>(tmem_o, ad0 + 2 * k4, bd0 + 2 * k4, idesc_o, (j | k4) != 0);
+                umma_commit(kv_empty(s));
+                umma_commit(p_empty(pb));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= softmax / correction / epilogue: one query row per thread =================
+        const int g = warp & 3;
+        const int row = 32 * g + lane;                  // row inside the tile == TMEM lane
+        const int qi = q_tile * FA_BQ + row;            // query index inside the sequence
+        const bool row_ok = qi < N;
+        const uint32_t lane_addr = (uint32_t)(32 * g) << 16;
+        float ai = 0.f;
+        if (p.bias_mode == 1 && row_ok)
+            ai = (__ldg(p.a + ((size_t)bt * p.nbox + qi % p.nbox) * p.H + h) + __ldg(p.bpe + h)) * p.c;
+        const float* dense_row = nullptr;
+        if (p.bias_mode == 2 && row_ok) dense_row = p.dense + (((size_t)bt * N + qi) * N) * p.H + h;
+        float m_run = -1e30f, l_run = 0.f;
+        const uint32_t prow = (uint32_t)row * 128u;
+        const uint32_t sw = (uint32_t)(row & 7);
+
+        for (int j = 0; j < T; ++j) {
+            const int sb = j & 1, s = j % p.stages;
+            mbar_wait(kv_full(s), (uint32_t)((j / p.stages) & 1));     // a_j staged (already complete)
+            mbar_wait(s_full(sb), (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tmem_s0 + lane_addr + sb * FA_BKV, r0);
+            tmem_ld32(tmem_s0 + lane_addr + sb * FA_BKV + 32, r1);
+            tmem_wait_ld();
+            float sv[64];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { sv[c] = __uint_as_float(r0[c]) * p.c; sv[32 + c] = __uint_as_float(r1[c]) * p.c; }
+            if (p.bias_mode == 1) {
+                const float4* ak4 = reinterpret_cast<const float4*>(ak_gen + s * FA_BKV);
+#pragma unroll
+                for (int c4 = 0; c4 < 16; ++c4) {
+                    const float4 a4 = ak4[c4];
+                    sv[4 * c4 + 0] += fmaxf(ai - a4.x, 0.f);
+                    sv[4 * c4 + 1] += fmaxf(ai - a4.y, 0.f);
+                    sv[4 * c4 + 2] += fmaxf(ai - a4.z, 0.f);
+                    sv[4 * c4 + 3] += fmaxf(ai - a4.w, 0.f);
+                }
+            } else if (p.bias_mode == 2 && row_ok) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    const int key = j * FA_BKV + c;
+                    if (key < N) sv[c] += __ldg(dense_row + (size_t)key * p.H) * p.c;
+                }
+            }
+            if ((j + 1) * FA_BKV > N) {                // ragged last tile: keys >= N do not exist
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    if (j * FA_BKV + c >= N) sv[c] = -INFINITY;
+            }
+            float mx = sv[0];
+#pragma unroll
+            for (int c = 1; c < 64; ++c) mx = fmaxf(mx, sv[c]);
+            const float m_new = fmaxf(m_run, mx);
+            if (j == 0) {
+                m_run = m_new;
+            } else {
+                const bool grow = (m_new - m_run) > FA_RESCALE_T;
+                if (__any_sync(0xffffffffu, grow)) {
+                    // rescale this warp's 32 accumulator rows; PV_{j-1} must have landed first
+                    const float alpha = grow ? fast_exp2(m_run - m_new) : 1.f;
+                    if (grow) { m_run = m_new; l_run *= alpha; }
+                    mbar_wait(p_empty((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
+                    tc_fence_after();
+                    for (int c0 = 0; c0 < dhp; c0 += 32) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_o + lane_addr + c0, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                        tmem_st32(tmem_o + lane_addr + c0, o);
+                    }
+                    tmem_wait_st();
+                }
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) { sv[c] = fast_exp2(sv[c] - m_run); sum += sv[c]; }
+            l_run += sum;
+            // P buffer (j&1) was last read by PV_{j-2}
+            if (j >= 2) mbar_wait(p_empty(sb), (uint32_t)(((j - 2) >> 1) & 1));
+            const uint32_t pdst = p_smem0 + sb * (FA_BQ * 128) + prow;
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16) {
+                const uint32_t w0 = pack_bf16(sv[8 * c16 + 0], sv[8 * c16 + 1]);
+                const uint32_t w1 = pack_bf16(sv[8 * c16 + 2], sv[8 * c16 + 3]);
+                const uint32_t w2 = pack_bf16(sv[8 * c16 + 4], sv[8 * c16 + 5]);
+                const uint32_t w3 = pack_bf16(sv[8 * c16 + 6], sv[8 * c16 + 7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(pdst + (((uint32_t)c16 ^ sw) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                             : "memory");
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full(sb));
+        }
+        // ---- epilogue: O / l
+        mbar_wait(p_empty((T - 1) & 1), (uint32_t)(((T - 1) >> 1) & 1));
+        tc_fence_after();
+        const float inv_l = 1.f / l_run;
+        const int n_pv = (dh + 15) & ~15;
+        for (int c0 = 0; c0 < dhp; c0 += 32) {
+            uint32_t o[32];
+            float v[32];
+            if (c0 < n_pv) {
+                tmem_ld32(tmem_o + lane_addr + c0, o);
+                tmem_wait_ld();
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = (c0 + c < n_pv) ? __uint_as_float(o[c]) * inv_l : 0.f;
+            if (row_ok) {
+                const size_t off = ((size_t)bt * N + qi) * p.ldo + (size_t)h * dhp + c0;
+                if (p.out_kind == 1) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8)
+                        *reinterpret_cast<uint4*>(dst + c) =
+                            make_uint4(pack_bf16(v[c], v[c + 1]), pack_bf16(v[c + 2], v[c + 3]),
+                                       pack_bf16(v[c + 4], v[c + 5]), pack_bf16(v[c + 6], v[c + 7]));
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.out) + off;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(dst + c) =
+                            make_float4(to_tf32(v[c]), to_tf32(v[c + 1]), to_tf32(v[c + 2]), to_tf32(v[c + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
+            const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
+            const float* dense, void* out, long long ldo, int out_kind, cudaStream_t st)
+{
+    if (Bt == 0 || N == 0) return 0;
+    VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS, "tc_attn: H=%d out of range", H);
+    VOG_REQUIRE(dhp == 64 || dhp == 128 || dhp == 192 || dhp == 256, "tc_attn: dhp=%d must be 64/128/192/256", dhp);
+    VOG_REQUIRE(npad >= N && npad % 8 == 0, "tc_attn: npad=%d must be >= N and a multiple of 8", npad);
+    VOG_REQUIRE(Bt <= 65535 && H <= 65535, "tc_attn: grid too large");
+    VOG_REQUIRE(out_kind == 1 || out_kind == 2, "tc_attn: bad out_kind");
+    VOG_REQUIRE(ldo >= (long long)H * dhp && (ldo * (out_kind == 1 ? 2 : 4)) % 16 == 0, "tc_attn: bad ldo");
+    VOG_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "tc_attn: output must be 16-byte aligned");
+    VOG_REQUIRE(bias_mode != 1 || (a && bpe && nbox > 0), "tc_attn: rank-1 bias needs a, bpe, nbox");
+    VOG_REQUIRE(bias_mode != 2 || dense, "tc_attn: dense bias pointer missing");
+    AttnParams p;
+    p.Bt = Bt; p.N = N; p.H = H; p.dhp = dhp; p.npad = npad;
+    for (int h = 0; h < H; ++h) {
+        VOG_REQUIRE(dh[h] >= 1 && dh[h] <= dhp, "tc_attn: head dim %d does not fit dhp=%d", dh[h], dhp);
+        p.dh[h] = dh[h];
+    }
+    p.c = inv_scale * 1.4426950408889634f;
+    p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.bpe = bpe; p.dense = dense;
+    p.out = out; p.ldo = ldo; p.out_kind = out_kind;
+    const int cols = dhp + 2 * FA_BKV;
+    p.tmem_cols = cols <= 256 ? 256 : 512;
+
+    CUtensorMap tq, tk, tv;
+    const uint64_t BH = (uint64_t)Bt * H;
+    uint64_t dq[3] = {(uint64_t)dhp, (uint64_t)N, BH};
+    uint64_t sq[2] = {(uint64_t)dhp * 2, (uint64_t)N * dhp * 2};
+    uint32_t bq[3] = {64, FA_BQ, 1}, bk[3] = {64, FA_BKV, 1};
+    if (make_tmap(&tq, q, 2, 1, 3, dq, sq, bq)) return -1;
+    if (make_tmap(&tk, k, 2, 1, 3, dq, sq, bk)) return -1;
+    uint64_t dv[3] = {(uint64_t)npad, (uint64_t)dhp, BH};
+    uint64_t sv[2] = {(uint64_t)npad * 2, (uint64_t)dhp * npad * 2};
+    uint32_t bv[3] = {64, (uint32_t)dhp, 1};
+    if (make_tmap(&tv, vt, 2, 1, 3, dv, sv, bv)) return -1;
+
+    const int fixed = FA_BQ * dhp * 2 + 2 * FA_BQ * 128 + 256 /*barriers*/ + 1024 /*alignment*/;
+    const int stage_bytes = 2 * FA_BKV * dhp * 2 + FA_BKV * 4;    // K + V^T + staged a_j
+    int stages = (227 * 1024 - fixed) / stage_bytes;
+    if (stages > FA_MAX_STAGES) stages = FA_MAX_STAGES;
+    VOG_REQUIRE(stages >= 2, "tc_attn: not enough shared memory for dhp=%d", dhp);
+    p.stages = stages;
+    const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
+    VOG_CUDA(cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(N, FA_BQ), H, Bt);
+    tc_attn_kernel<<<grid, FA_THREADS, smem, st>>>(tq, tk, tv, p);
+    return check_launch("tc_attn");
+}
+
+}  // namespace vog

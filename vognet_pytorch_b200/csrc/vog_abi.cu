@@ -97,4 +97,64 @@ int vog_select_fwd(const float* scores, const float* props, int pdim, float* box
                       nfrm, nppf, spat, (cudaStream_t)stream);
 }
 
+static int require_sm100(const char* who)
+{
+    VOG_REQUIRE(vog_device_is_sm100(), "%s: needs an sm_100 (B200) device - tcgen05/TMEM kernels have no other path", who);
+    return 0;
+}
+
+int vog_cast_lp(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, int kind,
+                void* stream)
+{
+    VOG_REQUIRE(rows >= 0 && cols >= 0, "vog_cast_lp: negative dimension");
+    if (rows == 0 || cols == 0) return 0;
+    VOG_REQUIRE(src && dst, "vog_cast_lp: null operand");
+    return cast_lp(src, lds, dst, ldd, rows, cols, kind, (cudaStream_t)stream);
+}
+
+int vog_tc_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int tf32,
+                int BN, const float* bias, int relu, const float* residual, int64_t ldr,
+                float* out_f32, int64_t ldc, void* out_lp, int64_t ldlp, int lp_kind, int rep,
+                void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N >= 0 && K > 0, "vog_tc_gemm: bad dimension");
+    if (M == 0 || N == 0) return 0;
+    if (require_sm100("vog_tc_gemm")) return -1;
+    VOG_REQUIRE(A && W, "vog_tc_gemm: null operand");
+    TcEpilogue e;
+    e.bias = bias; e.relu = relu; e.residual = residual; e.ldr = ldr;
+    e.out_f32 = out_f32; e.ldc = ldc; e.out_lp = out_lp; e.ldlp = ldlp; e.lp_kind = lp_kind; e.rep = rep;
+    VOG_REQUIRE(!out_lp || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_tc_gemm: bad lp_kind");
+    return tc_gemm(A, lda, W, ldw, M, N, K, tf32, BN, e, (cudaStream_t)stream);
+}
+
+int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, int M, int K, int tf32,
+                    int n_heads, int dhp, int seq_n, int npad, void* q, void* k, void* vt, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && K > 0 && n_heads >= 1 && n_heads <= VOG_MAX_HEADS, "vog_tc_gemm_qkv: bad dimension");
+    if (M == 0) return 0;
+    if (require_sm100("vog_tc_gemm_qkv")) return -1;
+    VOG_REQUIRE(A && Wqkv && q && k && vt, "vog_tc_gemm_qkv: null operand");
+    VOG_REQUIRE(dhp % 64 == 0 && dhp <= 256, "vog_tc_gemm_qkv: dhp=%d must be 64/128/192/256", dhp);
+    VOG_REQUIRE(seq_n > 0 && M % seq_n == 0 && npad >= seq_n && npad % 8 == 0, "vog_tc_gemm_qkv: bad sequence geometry");
+    TcEpilogue e;
+    e.mode = 1; e.q = (__nv_bfloat16*)q; e.k = (__nv_bfloat16*)k; e.vt = (__nv_bfloat16*)vt;
+    e.seq_n = seq_n; e.n_heads = n_heads; e.dhp = dhp; e.npad = npad;
+    return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, (cudaStream_t)stream);
+}
+
+int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
+                    const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
+                    const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
+                    void* stream)
+{
+    VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_tc_attn_fwd: negative dimension");
+    if (Bt == 0 || N == 0) return 0;
+    if (require_sm100("vog_tc_attn_fwd")) return -1;
+    VOG_REQUIRE(q && k && vt && out && dh, "vog_tc_attn_fwd: null operand");
+    VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_tc_attn_fwd: bad bias_mode %d", bias_mode);
+    return tc_attn(q, k, vt, Bt, N, H, dhp, npad, dh, inv_scale, bias_mode, a, nbox, bpe, dense, out, ldo,
+                   out_kind, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -152,3 +152,115 @@ def select_fwd(scores, props, ncmp, nfrm, nppf, spat):
 
 def inv_sqrt(d_model):
     return 1.0 / math.sqrt(d_model)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core path
+# ---------------------------------------------------------------------------------------------
+_LP_DTYPE = {LP_BF16: torch.bfloat16, LP_TF32: torch.float32}
+
+
+def cast_lp(src, kind, out=None):
+    """fp32 [rows, cols] (row-major view) -> bf16 or tf32-rounded fp32 copy."""
+    _req(src, torch.float32, 'src', 2)
+    rows, cols = src.shape
+    if out is None:
+        out = torch.empty(rows, cols, device=src.device, dtype=_LP_DTYPE[kind])
+    L = _lib.lib()
+    _lib.check(L.vog_cast_lp(_ptr(src), _rowmajor2d(src, 'src'), _ptr(out), _rowmajor2d(out, 'out'),
+                             rows, cols, kind, _stream()), 'vog_cast_lp')
+    return out
+
+
+def _is_tf32(a, w):
+    if a.dtype != w.dtype or a.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError(f'tc_gemm operands must both be bf16 or both tf32-rounded fp32, got {a.dtype}/{w.dtype}')
+    return int(a.dtype == torch.float32)
+
+
+def pick_bn(N):
+    for bn in (256, 192, 128, 64, 32):
+        if N % bn == 0:
+            return bn
+    return 128 if N > 64 else (64 if N > 32 else 32)
+
+
+def tc_gemm(a, w, bias=None, residual=None, relu=False, out_f32=None, out_lp=None, lp_kind=LP_NONE,
+            rep=1, BN=None, want_f32=True):
+    """tcgen05 GEMM: (relu?)(a @ w^T + bias) + residual -> fp32 and/or low-precision outputs."""
+    if not (isinstance(a, torch.Tensor) and a.is_cuda and w.is_cuda):
+        raise RuntimeError('tc_gemm: expected CUDA tensors (vognet_pytorch_b200 has no CPU path)')
+    tf32 = _is_tf32(a, w)
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f'tc_gemm: a is [{M},{K}] but w is {tuple(w.shape)}')
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty(M * rep, N, device=a.device, dtype=torch.float32)
+    if out_lp is None and lp_kind != LP_NONE:
+        out_lp = torch.empty(M * rep, N, device=a.device, dtype=_LP_DTYPE[lp_kind])
+    if out_lp is not None and lp_kind == LP_NONE:
+        lp_kind = LP_BF16 if out_lp.dtype == torch.bfloat16 else LP_TF32
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.float32, 'residual', 2)
+        ldr = _rowmajor2d(residual, 'residual')
+    if bias is not None:
+        _req(bias, torch.float32, 'bias', 1)
+    L = _lib.lib()
+    _lib.check(L.vog_tc_gemm(_ptr(a), _rowmajor2d(a, 'a'), _ptr(w), _rowmajor2d(w, 'w'), M, N, K, tf32,
+                             BN or pick_bn(N), _ptr(bias), int(relu), _ptr(residual), ldr,
+                             _ptr(out_f32), _rowmajor2d(out_f32, 'out_f32') if out_f32 is not None else 0,
+                             _ptr(out_lp), _rowmajor2d(out_lp, 'out_lp') if out_lp is not None else 0,
+                             lp_kind, rep, _stream()), 'vog_tc_gemm')
+    return out_f32, out_lp
+
+
+def round_up(a, b):
+    return -(-a // b) * b
+
+
+def tc_gemm_qkv(a, wqkv, Bt, N, n_heads, dhp):
+    """-> q,k [Bt,H,N,dhp] bf16 and vt [Bt,H,dhp,Npad] bf16 (Npad = N rounded up to 8)."""
+    tf32 = _is_tf32(a, wqkv)
+    M, K = a.shape
+    assert M == Bt * N and wqkv.shape == (3 * n_heads * dhp, K)
+    npad = round_up(N, 8)
+    q = torch.empty(Bt, n_heads, N, dhp, device=a.device, dtype=torch.bfloat16)
+    k = torch.empty_like(q)
+    vt = torch.zeros(Bt, n_heads, dhp, npad, device=a.device, dtype=torch.bfloat16) if npad != N else \
+        torch.empty(Bt, n_heads, dhp, npad, device=a.device, dtype=torch.bfloat16)
+    L = _lib.lib()
+    _lib.check(L.vog_tc_gemm_qkv(_ptr(a), _rowmajor2d(a, 'a'), _ptr(wqkv), _rowmajor2d(wqkv, 'wqkv'), M, K,
+                                 tf32, n_heads, dhp, N, npad, _ptr(q), _ptr(k), _ptr(vt), _stream()),
+               'vog_tc_gemm_qkv')
+    return q, k, vt
+
+
+def tc_attn_fwd(q, k, vt, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, bias_mode=BIAS_NONE,
+                a=None, nbox=0, bpe=None, dense=None):
+    """q,k [Bt,H,N,dhp], vt [Bt,H,dhp,Npad] bf16 -> out [Bt*N, H*dhp] (bf16 or tf32-rounded fp32)."""
+    for t, n in ((q, 'q'), (k, 'k'), (vt, 'vt')):
+        _req(t, torch.bfloat16, n, 4)
+        if not t.is_contiguous():
+            raise ValueError(f'tc_attn_fwd: {n} must be contiguous')
+    Bt, H, Nq, dhp = q.shape
+    npad = vt.shape[3]
+    if Nq != N or k.shape != q.shape or vt.shape[:3] != (Bt, H, dhp) or len(head_dims) != H:
+        raise ValueError('tc_attn_fwd: inconsistent shapes')
+    if out is None:
+        out = torch.empty(Bt * N, H * dhp, device=q.device, dtype=_LP_DTYPE[out_kind])
+    dh_arr = (ctypes.c_int * H)(*head_dims)
+    if bias_mode == BIAS_RANK1:
+        _req(a, torch.float32, 'a', 2), _req(bpe, torch.float32, 'bpe', 1)
+        if a.shape != (Bt * nbox, H) or not a.is_contiguous():
+            raise ValueError(f'tc_attn_fwd: a must be contiguous [{Bt * nbox},{H}], got {tuple(a.shape)}')
+    if bias_mode == BIAS_DENSE:
+        _req(dense, torch.float32, 'dense', 4)
+        if tuple(dense.shape) != (Bt, N, N, H) or not dense.is_contiguous():
+            raise ValueError(f'tc_attn_fwd: dense bias must be contiguous [{Bt},{N},{N},{H}]')
+    L = _lib.lib()
+    _lib.check(L.vog_tc_attn_fwd(_ptr(q), _ptr(k), _ptr(vt), Bt, N, H, dhp, npad, dh_arr, float(inv_scale),
+                                 bias_mode, _ptr(a), nbox, _ptr(bpe), _ptr(dense), _ptr(out),
+                                 _rowmajor2d(out, 'out'), out_kind, _stream()), 'vog_tc_attn_fwd')
+    return out
