@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py - VOGNet forward queries/sec on B200 (driver contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spat_gt5|spat_p100|temp_gt5|temp_p100]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU oracle port on the host cores, same workload
+
+One "step" = one forward of the fusion hot path (language LSTM, encoders, obj_tx, mul_tx, lin2,
+masks) over one synthetic batch of B queries per GPU + the box selection.  `value` = queries/s
+with inputs resident in HBM; `e2e` = the same through the public nn.Module / evaluator API with the
+batch starting in pinned HOST memory and predictions read back to the host every step.
+
+The default workload is BASELINE.json configs[1] (spat/gt5, bs=4 per GPU, fp32 configuration ->
+compute 'tf32': tf32 tcgen05 GEMMs, bf16 attention operands, fp32 everything else), the one the
+metric is quoted on.  The roofline object is reported for the dominant kernel of the workload;
+`roofline_seq4000` repeats it for the fused attention at the north-star shape (spat/p100, N=4000 /
+2000) so the tensor-pipe target can be read from the same line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'VOGNet fwd queries/sec'
+COMPUTE = {'spat_gt5': 'tf32', 'temp_gt5': 'tf32', 'spat_p100': 'bf16', 'temp_p100': 'bf16', 'cpu_ref': 'tf32'}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def flops_attn(Bt, N, d):
+    """QK^T + PV of the fused attention kernel (multiply-add = 2): SURVEY.md section 8d."""
+    return Bt * 4.0 * N * N * d
+
+
+def workload_shapes(w):
+    B, ncmp, nppf = w['B'], w['ncmp'], w['nppf']
+    P = ncmp * 10 * nppf
+    if w['conc_type'] == 'spat':
+        nfrm, nppf2 = 10, ncmp * nppf
+    else:
+        nfrm, nppf2 = ncmp * 10, nppf
+    return dict(P=P, obj=(B, P, 512), mul=(B * nfrm, 5 * nppf2, 768))
+
+
+def flops_query(w):
+    s = workload_shapes(w)
+    P = s['P']
+
+    def layer(Bt, N, d):
+        return Bt * (6.0 * N * d * d + 4.0 * N * N * d) + Bt * (2.0 * N * d * d + 4.0 * N * d * (d / 2))
+    B = w['B']
+    tot = layer(*s['obj']) + layer(*s['mul'])
+    tot += B * (2.0 * P * 2048 * 256 + 2.0 * 40 * 3072 * 256 + 2.0 * 5 * P * (768 * 256 + 256))
+    return tot / B
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle port (oracle/vog_oracle.py - the restated reference
+    algorithm; the Python reference itself cannot travel to the GPU box) on the host cores."""
+    import torch
+    from oracle import vog_oracle as vo
+    from vognet_pytorch_b200 import synth
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    w, batch = synth.workload(args.workload)
+    sd = synth.make_state_dict()
+    B = w['B']
+    sample = f'whole batch B={B}'
+    if w['nppf'] >= 100:           # ~2 s per query on 8 cores: bound the sample to one query
+        batch = {k: v[:1].clone() for k, v in batch.items()}
+        B, sample = 1, 'first query of the batch (B=1)'
+
+    def step():
+        with torch.no_grad():
+            out = vo.vog_forward(sd, batch, w['conc_type'], w['nppf'])
+            vo.select_boxes(out['mdl_outs_eval'], batch['pad_proposals'], w['conc_type'], w['ncmp'], w['nppf'])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = B / dt
+    line = {'impl': 'reference', 'metric': f'{METRIC} ({args.workload})', 'value': v, 'unit': 'queries/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': {'workload': args.workload, 'per_step_queries': B},
+            'cpu_baseline': {'value': v, 'unit': 'queries/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': v, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--workload', default='spat_gt5')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--compute', default=None, help="override: fp32x | tf32 | bf16")
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-seq4000', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        if args.steps == 30:
+            args.steps = 5
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import vognet_pytorch_b200 as vb
+    from vognet_pytorch_b200 import _lib, ops, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    L = _lib.lib()
+
+    w, batch = synth.workload(args.workload, seed=1 + rank)       # every rank its own shard of queries
+    compute = args.compute or COMPUTE[args.workload]
+    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
+    sel = vb.get_mdl_loss_eval(cfg)
+    mdl = sel['mdl'](cfg, comm)
+    mdl.load_state_dict(synth.make_state_dict(), strict=True)
+    mdl = mdl.to(dev).eval().set_compute(compute)
+    ev = sel['eval'](cfg, comm, dev)
+    B = w['B']
+
+    host = {k: v.pin_memory() for k, v in batch.items()}
+    resident = {k: v.to(dev) for k, v in batch.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(b):
+        out = mdl(b)
+        sel_out = ev.get_out_results_boxes(out, b)
+        return out, sel_out
+
+    # ---- kernel-resident timing: K steps, L2 flushed between steps, CUDA events per step ---------
+    for _ in range(args.warmup):
+        step(resident)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    n0 = L.vog_launch_count()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        ev0[i].record()
+        step(resident)
+        ev1[i].record()
+    barrier()
+    launches = (L.vog_launch_count() - n0) // args.steps
+    t_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    clocks = sampler.stop()
+    tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = tt.item()
+    value = world * B * args.steps / (t_ms / 1e3)
+
+    # ---- end to end: pinned host batch -> H2D -> forward + selection -> D2H of the predictions ----
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = 0
+
+    def e2e_step():
+        nonlocal d2h
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out, s = step(b)
+        res = [s['boxes'].cpu(), s['scores'].cpu(), s['indexs'].cpu()]
+        d2h = sum(r.numel() * r.element_size() for r in res)
+        return res
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * B * args.steps / te.item()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused attention), timed alone with CUDA events ---------
+    pk, pk_kind = peaks()
+
+    def attn_roofline(shape, n_iter=10):
+        Bt, N, d = shape
+        hd = ops.chunk_sizes(d, 3)
+        dhp = ops.round_up(max(hd), 64)
+        g = torch.Generator(device='cpu').manual_seed(0)
+        q = (torch.rand(Bt, 3, N, dhp, generator=g) - 0.5).bfloat16().to(dev)
+        k = (torch.rand(Bt, 3, N, dhp, generator=g) - 0.5).bfloat16().to(dev)
+        vt = (torch.rand(Bt, 3, dhp, ops.round_up(N, 8), generator=g) - 0.5).bfloat16().to(dev)
+        nbox = N // 5 if N % 5 == 0 else N
+        a = torch.rand(Bt * nbox, 3, generator=g).to(dev)
+        bpe = torch.zeros(3, device=dev)
+        out = torch.empty(Bt * N, 3 * dhp, device=dev, dtype=torch.bfloat16)
+
+        def run():
+            ops.tc_attn_fwd(q, k, vt, N, hd, 1.0 / d ** 0.5, out=out, bias_mode=ops.BIAS_RANK1, a=a,
+                            nbox=nbox, bpe=bpe)
+        for _ in range(3):
+            run()
+        ts = []
+        for _ in range(n_iter):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sum(ts) / len(ts)
+        fl = flops_attn(Bt, N, d)
+        ach = fl / (ms * 1e-3) / 1e12
+        return {'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
+                'frac': ach / pk['bf16_tflops'], 'traffic': None, 'kernel': 'tc_attn_kernel',
+                'shape': {'Bt': Bt, 'N': N, 'd_model': d, 'heads': 3}, 'ms_per_launch': ms,
+                'flops_per_launch': fl, 'peak_source': f'{pk_kind} bf16 burst (kernel timed alone)'}
+
+    shapes = workload_shapes(w)
+    roof = attn_roofline(shapes['mul'])
+    line = {
+        'metric': f'{METRIC} ({args.workload})', 'value': value, 'unit': 'queries/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'tf32': 'tf32 GEMM + bf16 attention operands, fp32 accumulate/softmax/LayerNorm',
+                  'bf16': 'bf16 operands, fp32 accumulate/softmax/LayerNorm', 'fp32x': 'f32'}[compute],
+        'data': 'synthetic',
+        'config': {'workload': args.workload, 'conc_type': w['conc_type'], 'per_gpu_batch': B,
+                   'global_batch': B * world, 'ncmp': w['ncmp'], 'nfrm': 10, 'nppf': w['nppf'],
+                   'obj_attn': list(shapes['obj']), 'mul_attn': list(shapes['mul']), 'compute': compute,
+                   'parallelism': f'dp{world} (queries sharded, no data-path collective)',
+                   'l2': 'flushed (256 MB memset) between timed iterations',
+                   'gflop_per_query_algorithmic': flops_query(w) / 1e9},
+        'clocks': clocks,
+        'e2e': {'value': e2e, 'unit': 'queries/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': int(launches),
+        'roofline': roof,
+    }
+    if not args.no_seq4000 and world == 1:
+        p100 = dict(synth.WORKLOADS['spat_p100'])
+        s4 = workload_shapes(p100)
+        r_obj, r_mul = attn_roofline(s4['obj'], 5), attn_roofline(s4['mul'], 5)
+        fl = r_obj['flops_per_launch'] + r_mul['flops_per_launch']
+        ms = r_obj['ms_per_launch'] + r_mul['ms_per_launch']
+        line['roofline_seq4000'] = {'bound': 'tensor', 'achieved': fl / ms / 1e9, 'peak': pk['bf16_tflops'],
+                                    'unit': 'TFLOP/s', 'frac': fl / ms / 1e9 / pk['bf16_tflops'],
+                                    'obj_tx': r_obj, 'mul_tx': r_mul,
+                                    'note': 'fused obj_tx+mul_tx attention at spat/p100 bs=4 (N=4000 / 2000)'}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import vog_oracle as vo                           # cpu_baseline leg only
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        sd = synth.make_state_dict()
+        cb = batch
+        nq, sample = B, f'whole batch B={B}, median of 3 after 1 warm-up'
+        if w['nppf'] >= 100:
+            cb = {k: v[:1].clone() for k, v in batch.items()}
+            nq, sample = 1, 'first query of the batch (B=1), median of 3 after 1 warm-up'
+        ts = []
+        with torch.no_grad():
+            for i in range(4):
+                t0 = time.perf_counter()
+                o = vo.vog_forward(sd, cb, w['conc_type'], w['nppf'])
+                vo.select_boxes(o['mdl_outs_eval'], cb['pad_proposals'], w['conc_type'], w['ncmp'], w['nppf'])
+                if i:
+                    ts.append(time.perf_counter() - t0)
+        line['cpu_baseline'] = {'value': nq / statistics.median(ts), 'unit': 'queries/s', 'cores': cores,
+                                'kind': 'port', 'sample': sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -35,6 +35,8 @@ extern "C" {
 
 const char* vog_last_error(void);
 int vog_abi_version(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
+long long vog_launch_count(void);
 /* 1 when the current device is sm_100 (B200); the tcgen05 entry points refuse to run otherwise */
 int vog_device_is_sm100(void);
 

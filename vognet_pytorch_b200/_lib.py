@@ -26,6 +26,7 @@ P = c_void_p
 _SIGNATURES = {
     'vog_last_error': [],
     'vog_abi_version': [],
+    'vog_launch_count': [],
     'vog_device_is_sm100': [],
     'vog_sgemm_nt': [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P],
     'vog_attn_fwd_f32': [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, c_float, c_int, P,
@@ -41,7 +42,7 @@ _SIGNATURES = {
                         c_i64, c_int, P],
     'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
 }
-_RESTYPE = {'vog_last_error': ctypes.c_char_p}
+_RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong}
 
 
 def sources():

@@ -1,5 +1,6 @@
 // extern "C" surface of libvog_b200 (declared in include/vog_b200.h).
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "../../include/vog_b200.h"
@@ -18,8 +19,11 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+
 int check_launch(const char* what)
 {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -36,6 +40,7 @@ extern "C" {
 
 const char* vog_last_error(void) { return g_err; }
 int vog_abi_version(void) { return 1; }
+long long vog_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int vog_device_is_sm100(void)
 {

@@ -154,10 +154,96 @@ class VOGNetB200(nn.Module):
         if not feat.is_cuda:
             raise RuntimeError('vognet_pytorch_b200 runs on CUDA only (no CPU path); move the batch '
                                'and the module to a B200 device')
-        if self.compute != 'fp32x':
-            raise NotImplementedError(self.compute)
         with torch.no_grad():
-            return self._forward_fp32x(inp)
+            if self.compute == 'fp32x':
+                return self._forward_fp32x(inp)
+            return self._forward_tc(inp)
+
+    # -----------------------------------------------------------------------------------------
+    # tensor-core path ('tf32' / 'bf16')
+    # -----------------------------------------------------------------------------------------
+    def _lp_weight(self, name, param, kind):
+        cache = self.__dict__.setdefault('_lp_cache', {})
+        sig = (param.data_ptr(), param._version, kind)
+        ent = cache.get(name)
+        if ent is None or ent[0] != sig:
+            ent = (sig, ops.cast_lp(param.detach().contiguous(), kind))
+            cache[name] = ent
+        return ent[1]
+
+    def _forward_tc(self, inp):
+        kind = ops.LP_BF16 if self.compute == 'bf16' else ops.LP_TF32
+        lp_dtype = torch.bfloat16 if kind == ops.LP_BF16 else torch.float32
+        feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
+        dev = feat.device
+        B, P, _ = feat.shape
+        ncmp = inp['new_srl_idxs'].shape[1]
+        nppf = self.num_prop_per_frm
+        nvf = seg.shape[1]
+        assert nvf * nppf == P, (nvf, nppf, P)
+        assert inp['srl_arg_words_ind'].shape[1] == 1, 'temp/spat concatenation has one verb slot per query'
+        nsrl = inp['srl_arg_words_ind'].shape[2]
+        lang = self.language_encode(inp)                              # [B, nsrl, 256] fp32
+
+        # prop|seg features, fp32 + low-precision copy, both halves written by GEMM epilogues
+        # (the seg half with row replication over the nppf proposals of its (frame,vid) slot)
+        x = torch.empty(B * P, self.ps_dim, device=dev, dtype=torch.float32)
+        x_lp = torch.empty(B * P, self.ps_dim, device=dev, dtype=lp_dtype)
+        pe_ = self.prop_encoder[0].out_features
+        ops.tc_gemm(ops.cast_lp(feat.reshape(B * P, -1), kind),
+                    self._lp_weight('prop', self.prop_encoder[0].weight, kind),
+                    bias=self.prop_encoder[0].bias, relu=True, out_f32=x[:, :pe_], out_lp=x_lp[:, :pe_])
+        ops.tc_gemm(ops.cast_lp(seg.reshape(B * nvf, -1), kind),
+                    self._lp_weight('seg', self.seg_encoder[0].weight, kind),
+                    bias=self.seg_encoder[0].bias, relu=True, out_f32=x[:, pe_:], out_lp=x_lp[:, pe_:],
+                    rep=nppf)
+        props2 = props.reshape(B * P, props.shape[-1])
+
+        if self.USE_OBJ_TX and self.cfg.mdl.obj_tx.to_use:
+            otx = self.cfg.mdl.obj_tx
+            if otx.one_frm:
+                nfrm_o, nppf_o = self._groups(ncmp)
+                Bt_o, N_o, fdiv = B * nfrm_o, nppf_o, float(nfrm_o)
+            else:
+                Bt_o, N_o, fdiv = B, P, 1.0
+            bias = None
+            if otx.use_rel:
+                a = ops.pe_project(props2, self.pe_obj_sub_enc[0].weight, self.vid_w, self.vid_h, fdiv)
+                bias = RelBias(a, self.pe_obj_sub_enc[0].bias, N_o)
+            x, x_lp = self.obj_txf._exec.run(x.view(Bt_o, N_o, self.ps_dim), bias, self.compute,
+                                             x_lp=x_lp, want_lp=True)
+            x = x.reshape(B * P, self.ps_dim)
+
+        nfrm, nppf2 = self._groups(ncmp)
+        vis = x.view(B, nfrm, 1, nppf2, self.ps_dim).expand(B, nfrm, nsrl, nppf2, self.ps_dim)
+        lng = lang.view(B, 1, nsrl, 1, self.lang_dim).expand(B, nfrm, nsrl, nppf2, self.lang_dim)
+        xm = torch.cat([vis, lng], -1).view(B * nfrm, nsrl * nppf2, self.vl_dim)
+        xm_lp = None
+        if self.USE_MUL_TX and self.cfg.mdl.mul_tx.to_use:
+            mtx = self.cfg.mdl.mul_tx
+            bias = None
+            if mtx.use_rel:
+                a = ops.pe_project(props2, self.pe_mul_sub_enc[0].weight, self.vid_w, self.vid_h, float(nfrm))
+                bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
+            xm, xm_lp = self.mult_txf._exec.run(xm, bias, self.compute, want_lp=True)
+        xm2 = xm.reshape(-1, self.vl_dim)
+        if xm_lp is None:
+            xm_lp = ops.cast_lp(xm2, kind)
+        h, _ = ops.tc_gemm(xm_lp.reshape(-1, self.vl_dim), self._lp_weight('lin2', self.lin2[0].weight, kind),
+                           bias=self.lin2[0].bias, relu=True)
+        lg = ops.sgemm_nt(h, self.lin2[2].weight, self.lin2[2].bias)
+        logits = lg.view(B, nfrm, nsrl, nppf2).transpose(1, 2).reshape(B, 1, nsrl, P)
+        return self._mask_outputs(logits, inp, B, nsrl, ncmp, nppf, P)
+
+    def _mask_outputs(self, logits, inp, B, nsrl, ncmp, nppf, P):
+        cm = inp['num_cmp_msk'].float()
+        if self.CONC_TYPE == 'spat':
+            cmsk = cm.view(B, 1, 1, 1, ncmp, 1).expand(B, 1, nsrl, self.num_sampled_frm, ncmp, nppf)
+        else:
+            cmsk = cm.view(B, 1, 1, ncmp, 1).expand(B, 1, nsrl, ncmp, self.num_sampled_frm * nppf)
+        smsk = inp['srl_arg_inds_msk'].float().view(B, 1, nsrl, 1)
+        ev = torch.sigmoid(logits) * smsk * cmsk.reshape(B, 1, nsrl, P)
+        return {'mdl_outs': logits, 'mdl_outs_eval': ev}
 
     def _forward_fp32x(self, inp):
         feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']

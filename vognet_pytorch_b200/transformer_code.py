@@ -83,32 +83,48 @@ class EncoderExecutor:
         self.H = n_heads
         self.drop = drop_ratio
         self.head_dims = ops.chunk_sizes(d_model, n_heads)
+        self.dhp = ops.round_up(max(self.head_dims), 64)
         self._pack = {}
 
     # -- packed weights, rebuilt whenever a parameter was updated in place or replaced ---------
-    def _packed(self, l, layer):
-        att = layer.selfattn.layer
-        key = tuple((p.data_ptr(), p._version) for p in (att.wq.weight, att.wk.weight, att.wv.weight))
-        ent = self._pack.get(l)
-        if ent is None or ent[0] != key:
-            wqkv = torch.cat([att.wq.weight, att.wk.weight, att.wv.weight], 0).detach().contiguous()
-            ent = (key, wqkv)
-            self._pack[l] = ent
+    def _cached(self, key, params, build):
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        ent = self._pack.get(key)
+        if ent is None or ent[0] != sig:
+            with torch.no_grad():
+                ent = (sig, build())
+            self._pack[key] = ent
         return ent[1]
 
-    def run(self, x, bias, compute, training=False):
-        if training and self.drop > 0:
-            raise NotImplementedError('vognet_pytorch_b200: forward-only build (dropout/backward are '
-                                      'scheduled next, SURVEY.md section 8f); call .eval()')
-        if compute != 'fp32x':
-            raise NotImplementedError(f'compute mode {compute!r}')
-        Bt, N, d = x.shape
-        if d != self.d:
-            raise ValueError(f'expected last dim {self.d}, got {d}')
-        x2 = x.reshape(Bt * N, d)
-        if x2.dtype != torch.float32:
-            raise TypeError('activations must be float32')
-        x2 = x2.contiguous()
+    def _packed(self, l, layer):
+        att = layer.selfattn.layer
+        ws = (att.wq.weight, att.wk.weight, att.wv.weight)
+        return self._cached(('qkv32', l), ws, lambda: torch.cat(ws, 0).detach().contiguous())
+
+    def _packed_tc(self, l, layer, kind):
+        """Tensor-core operands of one layer: per-head zero-padded Wq|Wk|Wv rows ([3*H*dhp, d]), Wo
+        with matching zero-padded columns ([d, H*dhp]), FFN weights - all in bf16 or tf32-rounded."""
+        att, ffn = layer.selfattn.layer, layer.feedforward.layer
+        ws = (att.wq.weight, att.wk.weight, att.wv.weight, att.wo.weight, ffn.linear1.weight,
+              ffn.linear2.weight)
+        H, dhp, d = self.H, self.dhp, self.d
+
+        def lp(t):
+            return ops.cast_lp(t.detach().float().contiguous(), kind)
+
+        def build():
+            wqkv = torch.zeros(3 * H * dhp, d, device=ws[0].device, dtype=torch.float32)
+            wo = torch.zeros(d, H * dhp, device=ws[0].device, dtype=torch.float32)
+            off = 0
+            for h, dh in enumerate(self.head_dims):
+                for i in range(3):
+                    wqkv[(i * H + h) * dhp:(i * H + h) * dhp + dh] = ws[i][off:off + dh]
+                wo[:, h * dhp:h * dhp + dh] = ws[3][:, off:off + dh]
+                off += dh
+            return dict(wqkv=lp(wqkv), wo=lp(wo), w1=lp(ws[4]), w2=lp(ws[5]))
+        return self._cached(('tc', l, kind), ws, build)
+
+    def _bias_args(self, bias, Bt, N):
         mode, a, bpe, nbox, dense = ops.BIAS_NONE, None, None, 0, None
         if isinstance(bias, RelBias):
             mode, a, bpe, nbox = ops.BIAS_RANK1, bias.a, bias.b, bias.nbox
@@ -116,18 +132,69 @@ class EncoderExecutor:
             if tuple(bias.shape) != (Bt, N, N, self.H):
                 raise ValueError(f'x_pe must be [{Bt},{N},{N},{self.H}], got {tuple(bias.shape)}')
             mode, dense = ops.BIAS_DENSE, bias.contiguous()
+        return dict(bias_mode=mode, a=a, nbox=nbox, bpe=bpe, dense=dense)
+
+    def run(self, x, bias, compute, training=False, x_lp=None, want_lp=False):
+        """x [Bt,N,d] fp32 (+ optional low-precision copy x_lp) -> y [Bt,N,d] fp32, or (y, y_lp)."""
+        if training and self.drop > 0:
+            raise NotImplementedError('vognet_pytorch_b200: forward-only build (dropout/backward are '
+                                      'scheduled next, SURVEY.md section 8f); call .eval()')
+        if compute not in COMPUTE_MODES:
+            raise ValueError(f'compute must be one of {COMPUTE_MODES}')
+        Bt, N, d = x.shape
+        if d != self.d:
+            raise ValueError(f'expected last dim {self.d}, got {d}')
+        if x.dtype != torch.float32:
+            raise TypeError('activations must be float32')
+        x2 = x.reshape(Bt * N, d).contiguous()
+        bkw = self._bias_args(bias, Bt, N)
         inv_scale = 1.0 / math.sqrt(d)          # sqrt(d_model), not sqrt(d_head): :132,:195
+        if compute == 'fp32x':
+            y = self._run_fp32x(x2, Bt, N, bkw, inv_scale)
+            return (y.view(Bt, N, d), None) if want_lp else y.view(Bt, N, d)
+        kind = ops.LP_BF16 if compute == 'bf16' else ops.LP_TF32
+        if x_lp is None:
+            x_lp = ops.cast_lp(x2, kind)
+        y, y_lp = self._run_tc(x2, x_lp.reshape(Bt * N, d), Bt, N, bkw, inv_scale, kind)
+        return (y.view(Bt, N, d), y_lp) if want_lp else y.view(Bt, N, d)
+
+    def _run_fp32x(self, x2, Bt, N, bkw, inv_scale):
+        d = self.d
         for l, layer in enumerate(self.stack.layers):
             att, ffn = layer.selfattn, layer.feedforward
             qkv = ops.sgemm_nt(x2, self._packed(l, layer))
             o = ops.attn_fwd_f32(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], Bt, N, self.head_dims,
-                                 inv_scale, bias_mode=mode, a=a, nbox=nbox, bpe=bpe, dense=dense)
+                                 inv_scale, **bkw)
             pre = ops.sgemm_nt(o, att.layer.wo.weight, residual=x2)
             y = ops.add_layernorm(pre, None, att.layernorm.weight, att.layernorm.bias, att.layernorm.eps)
             h = ops.sgemm_nt(y, ffn.layer.linear1.weight, ffn.layer.linear1.bias, relu=True)
             pre2 = ops.sgemm_nt(h, ffn.layer.linear2.weight, ffn.layer.linear2.bias, residual=y)
             x2 = ops.add_layernorm(pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps)
-        return x2.view(Bt, N, d)
+        return x2
+
+    def _run_tc(self, x2, x_lp, Bt, N, bkw, inv_scale, kind):
+        """tcgen05 path.  GEMM operands in `kind` (bf16 / tf32-rounded), attention operands always
+        bf16, residual stream / LayerNorm / softmax statistics in fp32."""
+        M, d, H, dhp = Bt * N, self.d, self.H, self.dhp
+        lp_dtype = torch.bfloat16 if kind == ops.LP_BF16 else torch.float32
+        for l, layer in enumerate(self.stack.layers):
+            att, ffn = layer.selfattn, layer.feedforward
+            w = self._packed_tc(l, layer, kind)
+            q, k, vt = ops.tc_gemm_qkv(x_lp, w['wqkv'], Bt, N, H, dhp)
+            o_lp = ops.tc_attn_fwd(q, k, vt, N, self.head_dims, inv_scale, out_kind=kind, **bkw)
+            pre, _ = ops.tc_gemm(o_lp, w['wo'], residual=x2)
+            y = torch.empty(M, d, device=x2.device, dtype=torch.float32)
+            y_lp = torch.empty(M, d, device=x2.device, dtype=lp_dtype)
+            ops.add_layernorm(pre, None, att.layernorm.weight, att.layernorm.bias, att.layernorm.eps,
+                              out=y, out_lp=y_lp, lp_kind=kind)
+            _, h_lp = ops.tc_gemm(y_lp, w['w1'], bias=ffn.layer.linear1.bias, relu=True, lp_kind=kind,
+                                  want_f32=False)
+            pre2, _ = ops.tc_gemm(h_lp, w['w2'], bias=ffn.layer.linear2.bias, residual=y)
+            x2 = torch.empty(M, d, device=x2.device, dtype=torch.float32)
+            x_lp = torch.empty(M, d, device=x2.device, dtype=lp_dtype)
+            ops.add_layernorm(pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps,
+                              out=x2, out_lp=x_lp, lp_kind=kind)
+        return x2, x_lp
 
 
 class _TransformerBase(nn.Module):
