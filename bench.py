@@ -163,6 +163,7 @@ def main():
     ap.add_argument('--compute', default=None, help="override: fp32x | tf32 | bf16")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-seq4000', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graphs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
@@ -192,6 +193,7 @@ def main():
     mdl = sel['mdl'](cfg, comm)
     mdl.load_state_dict(synth.make_state_dict(), strict=True)
     mdl = mdl.to(dev).eval().set_compute(compute)
+    mdl.use_cuda_graph = not args.no_graph and compute != 'fp32x'
     ev = sel['eval'](cfg, comm, dev)
     B = w['B']
 

@@ -94,11 +94,14 @@ int vog_cast_lp(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t r
  * (tf32=1), fp32 accumulation in TMEM.  128 x BN tiles (BN multiple of 32, <= 256), persistent
  * grid.  Outputs: out_f32 and/or a low-precision copy out_lp (lp_kind); every output row m is
  * written to rows m*rep .. m*rep+rep-1 (rep > 1 broadcasts a segment feature over the proposals of
- * its frame: code/mdl_conc_single.py:50-66,156-174).  Same call sites as vog_sgemm_nt. */
+ * its frame: code/mdl_conc_single.py:50-66,156-174).  Small-M problems split K across CTAs when
+ * the caller passes a workspace of vog_tc_gemm_workspace_bytes() bytes (fp32 partials, reduced by
+ * a second kernel); workspace may be NULL.  Same call sites as vog_sgemm_nt. */
+int64_t vog_tc_gemm_workspace_bytes(int M, int N, int K, int tf32, int BN);
 int vog_tc_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                 int tf32, int BN, const float* bias, int relu, const float* residual, int64_t ldr,
                 float* out_f32, int64_t ldc, void* out_lp, int64_t ldlp, int lp_kind, int rep,
-                void* stream);
+                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Fused Q/K/V projection: A[M,K] . Wqkv[3*H*dhp, K]^T with Wqkv = per-head zero-padded rows of
  * wq|wk|wv (dhp = head dim rounded up to 64).  Writes bf16 Q,K as [Bt,H,seq_n,dhp] and V
@@ -119,6 +122,19 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
                     int npad, const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
                     const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
                     void* stream);
+
+/* One layer of the bidirectional LSTM recurrence of the language encoder, both directions, all
+ * timesteps, in one persistent launch (packed-sequence semantics from the device-side `lens`, no
+ * host synchronisation):  gx [T*Bq, ldg >= 8H] = W_ih x + b_ih + b_hh for every (t, b) (time-major
+ * rows t*Bq+b; forward gates in columns [0,4H), reverse in [4H,8H), gate order i,f,g,o), whh
+ * [2,4H,H] fp32, lens [Bq] int64.  Writes h as [T*Bq, ld_out >= 2H] (forward | reverse) in bf16 or
+ * tf32-rounded fp32, zeros where t >= len.  Bq <= 8 per call.  workspace:
+ * vog_lstm_workspace_bytes() bytes.  replaces nn.LSTM + pack/pad:
+ * utils/mdl_srl_utils.py:102-108,135-152. */
+int64_t vog_lstm_workspace_bytes(int Bq, int H);
+int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int64_t* lens, int T,
+                       int Bq, int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace,
+                       void* stream);
 
 #ifdef __cplusplus
 }

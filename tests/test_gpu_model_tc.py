@@ -85,3 +85,23 @@ def test_operator_tc_golden(golden, name, mode):
     # and wq/wk x5: attention operands are bf16 in BOTH modes, so the operator-level bound is set
     # by bf16 attention (10x / 4x the score tolerance)
     assert err < (1e-2 if mode == 'tf32' else 4e-2), err
+
+
+@pytest.mark.parametrize('name,mode', [('spat_gt5', 'tf32'), ('temp_gt5', 'bf16')])
+def test_cuda_graph_execution_matches_eager(name, mode):
+    """use_cuda_graph replays two captured graphs (visual side || language side, then fusion) and
+    must give the eager results for every new batch fed through the same static buffers."""
+    w, batch, mdl, ev = _model(name)
+    mdl.set_compute(mode)
+    outs = []
+    for seed in (1, 2, 3):
+        _, b = synth.workload(name, seed=seed)
+        db = synth.clone_batch(b, DEV)
+        mdl.use_cuda_graph = False
+        eager = mdl(db)['mdl_outs_eval'].clone()
+        mdl.use_cuda_graph = True
+        graph = mdl(db)['mdl_outs_eval'].clone()
+        torch.cuda.synchronize()
+        assert torch.equal(eager, graph), (seed, (eager - graph).abs().max().item())
+        outs.append(graph)
+    assert not torch.equal(outs[0], outs[1])

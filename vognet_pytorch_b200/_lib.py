@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libvog_b200.so')
-SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'fused_glue.cu']
+SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'lstm_rec.cu', 'fused_glue.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -36,13 +36,17 @@ _SIGNATURES = {
     'vog_pe_project': [P, c_int, P, P, c_int, c_int, c_float, c_float, c_float, c_float, P],
     'vog_select_fwd': [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'vog_cast_lp': [P, c_i64, P, c_i64, c_i64, c_int, c_int, P],
+    'vog_tc_gemm_workspace_bytes': [c_int, c_int, c_int, c_int, c_int],
     'vog_tc_gemm': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64,
-                    P, c_i64, P, c_i64, c_int, c_int, P],
+                    P, c_i64, P, c_i64, c_int, c_int, P, c_i64, P],
+    'vog_lstm_workspace_bytes': [c_int, c_int],
+    'vog_lstm_layer_fwd': [P, c_i64, P, P, c_int, c_int, c_int, P, c_i64, c_int, P, P],
     'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,
                         c_i64, c_int, P],
     'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
 }
-_RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong}
+_RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong,
+            'vog_tc_gemm_workspace_bytes': ctypes.c_int64, 'vog_lstm_workspace_bytes': ctypes.c_int64}
 
 
 def sources():

@@ -40,7 +40,8 @@ struct TcEpilogue {
     int seq_n = 0, n_heads = 0, dhp = 0, npad = 0;
 };
 int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int tf32,
-            int BN, const TcEpilogue& epi, cudaStream_t st);
+            int BN, const TcEpilogue& epi, void* workspace, long long workspace_bytes, cudaStream_t st);
+long long tc_gemm_workspace_bytes(int M, int N, int K, int tf32, int BN);
 int num_sms();
 // ---- tc_attn.cu : fused relative-position-bias attention (tcgen05) ---------------------------
 int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
@@ -48,5 +49,10 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
             const float* dense, void* out, long long ldo, int out_kind, cudaStream_t st);
 int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int kind,
             cudaStream_t st);
+
+// ---- lstm_rec.cu : persistent bidirectional LSTM recurrence -----------------------------------
+long long lstm_workspace_bytes(int Bq, int H);
+int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
+                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st);
 
 }  // namespace vog

@@ -2,15 +2,22 @@
 // contiguous), operands bf16 (kind::f16) or tf32-rounded fp32 (kind::tf32), fp32 accumulation in
 // TMEM.
 //
-//   persistent grid (one CTA per SM), static tile schedule, 128 x BN output tiles (BN <= 256)
+//   persistent grid (one CTA per SM), static schedule over (128 x BN output tile, K-split) work
+//   items; BN <= 256
 //   warp 0      TMA producer: {128 B x 128 rows} A box + {128 B x BN rows} W box per stage,
 //               128B-swizzled, ring of `stages` slots guarded by full/empty mbarriers
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=32 B per stage),
 //               tcgen05.commit releases the smem slot / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time from one of two TMEM accumulators
-//               (so the next tile's MMAs overlap this tile's epilogue), fused bias / ReLU /
-//               residual / low-precision copy / row replication, or the QKV scatter that writes
-//               Q,K as [Bt,H,N,dhp] bf16 and V transposed as [Bt,H,dhp,Npad] for the attention kernel
+//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time from one of two TMEM accumulators (so
+//               the next item's MMAs overlap this item's epilogue); each warp transposes its
+//               32x32 chunk through a swizzled smem patch so that global loads (residual) and
+//               stores (fp32 / bf16 / tf32 copies) are 128-byte coalesced row segments
+//   split-K     small-M problems (the gt5 configurations) cannot fill 148 SMs with 128-row tiles:
+//               K is split across CTAs, raw fp32 partials go to a caller-provided workspace and a
+//               second, elementwise kernel sums them and applies the epilogue
+//
+// epilogues: bias / ReLU / fp32 residual / low-precision copy / row replication, or the QKV scatter
+// that writes Q,K as [Bt,H,N,dhp] bf16 and V transposed as [Bt,H,dhp,Npad] for the attention kernel.
 //
 // Replaces the cuBLAS calls behind nn.Linear in code/transformer_code.py:57-60,80-81,169-172,180,186
 // and code/mdl_vog.py:202-207,224-230,291-314,675-677.
@@ -26,97 +33,80 @@ constexpr int GM_BM = 128;
 constexpr int GM_THREADS = 192;
 constexpr int GM_MAX_STAGES = 8;
 constexpr int GM_A_BYTES = GM_BM * 128;
+constexpr int GM_EPI_BYTES = 4 * 32 * 32 * 4;      // one 32x32 fp32 patch per epilogue warp
 
 struct GemmParams {
     int M, N, K, BN;
     int num_k_blocks, num_m_blocks, num_n_blocks, bk_elems;
+    int splits, kb_per_split;
+    float* partial;               // [splits, M, N] when splits > 1
     uint32_t idesc, tmem_cols;
     int stages;
     TcEpilogue e;
 };
 
-// ---- epilogues --------------------------------------------------------------------------------
-__device__ __forceinline__ void store_row_f32(float* dst, const float (&v)[32], int nvalid) {
-    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+// ---- epilogue on a coalesced float4 (4 consecutive columns of one row) ---------------------------
+__device__ __forceinline__ void epi_apply_store(const TcEpilogue& e, int M, int N, int m, int n, float4 v,
+                                                bool add_bias_relu)
+{
+    if (m >= M || n >= N) return;
+    const bool full = n + 3 < N;
+    float x[4] = {v.x, v.y, v.z, v.w};
+    if (add_bias_relu) {
+        if (e.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
+            for (int j = 0; j < 4; ++j)
+                if (n + j < N) x[j] += __ldg(e.bias + n + j);
+        }
+        if (e.relu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) dst[j] = v[j];
-    }
-}
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[32], int nvalid) {
-    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(dst + j) =
-                make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                           pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) dst[j] = __float2bfloat16_rn(v[j]);
-    }
-}
-
-__device__ __forceinline__ void epilogue_std(const GemmParams& p, int m, int n0, const uint32_t (&r)[32]) {
-    const TcEpilogue& e = p.e;
-    const int nvalid = min(32, p.N - n0);
-    if (m >= p.M || nvalid <= 0) return;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (e.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += __ldg(e.bias + n0 + j);
-    }
-    if (e.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
     }
     if (e.residual) {
-        const float* rr = e.residual + (size_t)m * e.ldr + n0;
+        const float* rr = e.residual + (size_t)m * e.ldr + n;
+        if (full && (reinterpret_cast<uintptr_t>(rr) & 15) == 0) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rr);
+            x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += rr[j];
+            for (int j = 0; j < 4; ++j)
+                if (n + j < N) x[j] += rr[j];
+        }
     }
     for (int rep = 0; rep < e.rep; ++rep) {
         const size_t row = (size_t)m * e.rep + rep;
-        if (e.out_f32) store_row_f32(e.out_f32 + row * e.ldc + n0, v, nvalid);
-        if (e.out_lp) {
-            if (e.lp_kind == 1) {
-                store_row_bf16(reinterpret_cast<__nv_bfloat16*>(e.out_lp) + row * e.ldlp + n0, v, nvalid);
+        if (e.out_f32) {
+            float* dst = e.out_f32 + row * e.ldc + n;
+            if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
             } else {
-                float t[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) t[j] = to_tf32(v[j]);
-                store_row_f32(reinterpret_cast<float*>(e.out_lp) + row * e.ldlp + n0, t, nvalid);
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < N) dst[j] = x[j];
             }
         }
-    }
-}
-
-// QKV scatter: N = 3*H*dhp, BN == dhp, tile column block n_blk = which*H + h
-__device__ __forceinline__ void epilogue_qkv(const GemmParams& p, int m, int n_blk, int c0,
-                                             const uint32_t (&r)[32]) {
-    const TcEpilogue& e = p.e;
-    if (m >= p.M) return;
-    const int which = n_blk / e.n_heads, h = n_blk % e.n_heads;
-    const int bt = m / e.seq_n, i = m % e.seq_n;
-    float v[32];
+        if (e.out_lp) {
+            if (e.lp_kind == 1) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out_lp) + row * e.ldlp + n;
+                if (full && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
+                } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (which < 2) {
-        __nv_bfloat16* dst = (which == 0 ? e.q : e.k) +
-                             (((size_t)bt * e.n_heads + h) * e.seq_n + i) * e.dhp + c0;
-        store_row_bf16(dst, v, 32);
-    } else {
-        __nv_bfloat16* dst = e.vt + (((size_t)bt * e.n_heads + h) * e.dhp + c0) * e.npad + i;
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < N) dst[j] = __float2bfloat16_rn(x[j]);
+                }
+            } else {
+                float* dst = reinterpret_cast<float*>(e.out_lp) + row * e.ldlp + n;
+                if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(to_tf32(x[0]), to_tf32(x[1]), to_tf32(x[2]), to_tf32(x[3]));
+                } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[(size_t)j * e.npad] = __float2bfloat16_rn(v[j]);
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < N) dst[j] = to_tf32(x[j]);
+                }
+            }
+        }
     }
 }
 
@@ -131,9 +121,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
     const uint32_t stage_bytes = GM_A_BYTES + p.BN * 128;
-    const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+    const uint32_t epi_off = p.stages * stage_bytes;
+    const uint32_t bar_off = epi_off + GM_EPI_BYTES;
+    const uint32_t bar_base = smem_base + bar_off;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(
-        smem_gen + p.stages * stage_bytes + 8 * (2 * GM_MAX_STAGES + 4));
+        smem_gen + bar_off + 8 * (2 * GM_MAX_STAGES + 4));
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (GM_MAX_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * GM_MAX_STAGES + a); };
@@ -154,14 +146,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const int ntiles = p.num_m_blocks * p.num_n_blocks;
+    const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
+    // item -> (m_blk, n_blk, split): splits innermost so that the CTAs of one wave share A/W tiles in L2
+    auto decode = [&](int item, int& m_blk, int& n_blk, int& kb0, int& kb1) {
+        const int split = item % p.splits;
+        const int tile = item / p.splits;
+        m_blk = tile / p.num_n_blocks;
+        n_blk = tile % p.num_n_blocks;
+        kb0 = split * p.kb_per_split;
+        kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        return split;
+    };
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                int m_blk, n_blk, kb0, kb1;
+                decode(item, m_blk, n_blk, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_arrive_expect_tx(full_bar(s), stage_bytes);
                     tma_load_2d(a_smem(s), &tma_a, full_bar(s), kb * p.bk_elems, m_blk * GM_BM);
@@ -174,18 +177,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                int m_blk, n_blk, kb0, kb1;
+                decode(item, m_blk, n_blk, kb0, kb1);
                 mbar_wait(tempty_bar(acc), acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.BN;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint64_t ad = umma_desc_sw128(a_smem(s));
                     const uint64_t bd = umma_desc_sw128(b_smem(s));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma<kTF32>(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0);
+                        umma<kTF32>(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb > kb0) || (k != 0));
                     umma_commit(empty_bar(s));
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
@@ -197,18 +202,64 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
     } else {
         const int g = warp & 3;                    // TMEM lane quarter this warp may access
+        float* patch = reinterpret_cast<float*>(smem_gen + epi_off) + g * 1024;     // [32 rows][8 float4]
         int acc = 0; uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+        TcEpilogue pe = p.e;                       // split-K: raw partials, no epilogue math
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            int m_blk, n_blk, kb0, kb1;
+            const int split = decode(item, m_blk, n_blk, kb0, kb1);
+            if (p.splits > 1) {
+                pe = TcEpilogue();
+                pe.out_f32 = p.partial + (size_t)split * p.M * p.N;
+                pe.ldc = p.N;
+            }
             mbar_wait(tfull_bar(acc), acc_ph);
             tc_fence_after();
-            const int m = m_blk * GM_BM + 32 * g + lane;
+            const int m_base = m_blk * GM_BM + 32 * g;
             for (int c0 = 0; c0 < p.BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * g) << 16) + acc * p.BN + c0, r);
                 tmem_wait_ld();
-                if (p.e.mode == 1) epilogue_qkv(p, m, n_blk, c0, r);
-                else epilogue_std(p, m, n_blk * p.BN + c0, r);
+                const int n0 = n_blk * p.BN + c0;
+                if (pe.mode == 1 && n_blk / pe.n_heads == 2) {
+                    // V^T scatter straight from registers: lanes are consecutive tokens -> coalesced
+                    const int m = m_base + lane;
+                    if (m < p.M) {
+                        const int h = n_blk % pe.n_heads, bt = m / pe.seq_n, i = m % pe.seq_n;
+                        __nv_bfloat16* dst = pe.vt + (((size_t)bt * pe.n_heads + h) * pe.dhp + c0) * pe.npad + i;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            dst[(size_t)j * pe.npad] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                    }
+                    continue;
+                }
+                // transpose the 32x32 chunk through smem: row = lane on the way in ...
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(patch + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                        make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                                    __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+                __syncwarp();
+                // ... 4 rows x 8 float4 per instruction on the way out (128 B coalesced row segments)
+                const int c4 = lane & 7;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + (lane >> 3);
+                    const float4 v = *reinterpret_cast<const float4*>(patch + row * 32 + ((c4 ^ (row & 7)) << 2));
+                    const int m = m_base + row, n = n0 + c4 * 4;
+                    if (pe.mode == 1) {
+                        if (m < p.M) {
+                            const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
+                            const int bt = m / pe.seq_n, ii = m % pe.seq_n;
+                            __nv_bfloat16* dst = (which == 0 ? pe.q : pe.k) +
+                                (((size_t)bt * pe.n_heads + h) * pe.seq_n + ii) * pe.dhp + c0 + c4 * 4;
+                            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                        }
+                    } else {
+                        epi_apply_store(pe, p.M, p.N, m, n, v, true);
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -220,6 +271,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// sum of split-K partials + epilogue, one float4 per thread
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, TcEpilogue e)
+{
+    const int n4 = (N + 3) / 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * n4) return;
+    const int m = (int)(idx / n4), n = (int)(idx % n4) * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool vec = (N % 4) == 0;
+    for (int s = 0; s < splits; ++s) {
+        const float* src = partial + ((size_t)s * M + m) * N + n;
+        if (vec) {
+            const float4 v = *reinterpret_cast<const float4*>(src);
+            x[0] += v.x; x[1] += v.y; x[2] += v.z; x[3] += v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n + j < N) x[j] += src[j];
+        }
+    }
+    epi_apply_store(e, M, N, m, n, make_float4(x[0], x[1], x[2], x[3]), true);
 }
 
 // ---- host ---------------------------------------------------------------------------------------
@@ -274,8 +349,29 @@ int num_sms()
     return n;
 }
 
+// K-split factor: only when the tile grid leaves most SMs idle and K is deep enough to be worth it
+int tc_gemm_splits(int M, int N, int K, int tf32, int BN, int qkv_mode)
+{
+    if (qkv_mode) return 1;
+    const int bk = tf32 ? 32 : 64;
+    const int nkb = cdiv(K, bk);
+    const int tiles = cdiv(M, GM_BM) * cdiv(N, BN);
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    if (tiles * 2 > sms || nkb < 8) return 1;
+    int s = sms / tiles;
+    if (s > nkb / 4) s = nkb / 4;            // at least 4 k-blocks per split
+    if (s > 32) s = 32;
+    return s < 2 ? 1 : s;
+}
+
+long long tc_gemm_workspace_bytes(int M, int N, int K, int tf32, int BN)
+{
+    const int s = tc_gemm_splits(M, N, K, tf32, BN, 0);
+    return s > 1 ? (long long)s * M * N * 4 : 0;
+}
+
 int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int tf32,
-            int BN, const TcEpilogue& epi, cudaStream_t st)
+            int BN, const TcEpilogue& epi, void* workspace, long long workspace_bytes, cudaStream_t st)
 {
     if (M == 0 || N == 0) return 0;
     const int eb = tf32 ? 4 : 2;
@@ -303,18 +399,24 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     p.num_k_blocks = cdiv(K, bk);
     p.num_m_blocks = cdiv(M, GM_BM);
     p.num_n_blocks = cdiv(N, BN);
+    p.splits = tc_gemm_splits(M, N, K, tf32, BN, epi.mode == 1);
+    if (p.splits > 1 && (workspace == nullptr || workspace_bytes < (long long)p.splits * M * N * 4))
+        p.splits = 1;                          // caller gave no workspace: plain schedule
+    p.kb_per_split = cdiv(p.num_k_blocks, p.splits);
+    p.splits = cdiv(p.num_k_blocks, p.kb_per_split);
+    p.partial = reinterpret_cast<float*>(workspace);
     p.idesc = umma_idesc(tf32 ? FMT_TF32 : FMT_BF16, GM_BM, BN);
     p.tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     const int stage_bytes = GM_A_BYTES + BN * 128;
-    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
+    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - GM_EPI_BYTES;
     int stages = budget / stage_bytes;
     if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
     VOG_REQUIRE(stages >= 2, "tc_gemm: tile does not fit shared memory");
     p.stages = stages;
     p.e = epi;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    const int ntiles = p.num_m_blocks * p.num_n_blocks;
-    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + GM_EPI_BYTES;
+    const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
+    const int grid = nitems < num_sms() ? nitems : num_sms();
     if (tf32) {
         VOG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_gemm_kernel<true><<<grid, GM_THREADS, smem, st>>>(ta, tb, p);
@@ -322,7 +424,13 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
         VOG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_gemm_kernel<false><<<grid, GM_THREADS, smem, st>>>(ta, tb, p);
     }
-    return check_launch("tc_gemm");
+    if (check_launch("tc_gemm")) return -1;
+    if (p.splits > 1) {
+        const long long n = (long long)M * ((N + 3) / 4);
+        splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.partial, p.splits, M, N, epi);
+        return check_launch("splitk_reduce");
+    }
+    return 0;
 }
 
 }  // namespace vog

@@ -117,10 +117,16 @@ int vog_cast_lp(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t r
     return cast_lp(src, lds, dst, ldd, rows, cols, kind, (cudaStream_t)stream);
 }
 
+int64_t vog_tc_gemm_workspace_bytes(int M, int N, int K, int tf32, int BN)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return tc_gemm_workspace_bytes(M, N, K, tf32, BN);
+}
+
 int vog_tc_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int tf32,
                 int BN, const float* bias, int relu, const float* residual, int64_t ldr,
                 float* out_f32, int64_t ldc, void* out_lp, int64_t ldlp, int lp_kind, int rep,
-                void* stream)
+                void* workspace, int64_t workspace_bytes, void* stream)
 {
     VOG_REQUIRE(M >= 0 && N >= 0 && K > 0, "vog_tc_gemm: bad dimension");
     if (M == 0 || N == 0) return 0;
@@ -130,7 +136,7 @@ int vog_tc_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, i
     e.bias = bias; e.relu = relu; e.residual = residual; e.ldr = ldr;
     e.out_f32 = out_f32; e.ldc = ldc; e.out_lp = out_lp; e.ldlp = ldlp; e.lp_kind = lp_kind; e.rep = rep;
     VOG_REQUIRE(!out_lp || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_tc_gemm: bad lp_kind");
-    return tc_gemm(A, lda, W, ldw, M, N, K, tf32, BN, e, (cudaStream_t)stream);
+    return tc_gemm(A, lda, W, ldw, M, N, K, tf32, BN, e, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, int M, int K, int tf32,
@@ -145,7 +151,7 @@ int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, i
     TcEpilogue e;
     e.mode = 1; e.q = (__nv_bfloat16*)q; e.k = (__nv_bfloat16*)k; e.vt = (__nv_bfloat16*)vt;
     e.seq_n = seq_n; e.n_heads = n_heads; e.dhp = dhp; e.npad = npad;
-    return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, (cudaStream_t)stream);
+    return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
 
 int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
@@ -160,6 +166,18 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
     VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_tc_attn_fwd: bad bias_mode %d", bias_mode);
     return tc_attn(q, k, vt, Bt, N, H, dhp, npad, dh, inv_scale, bias_mode, a, nbox, bpe, dense, out, ldo,
                    out_kind, (cudaStream_t)stream);
+}
+
+int64_t vog_lstm_workspace_bytes(int Bq, int H) { return lstm_workspace_bytes(Bq, H); }
+
+int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int64_t* lens, int T, int Bq,
+                       int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace, void* stream)
+{
+    VOG_REQUIRE(T >= 0 && Bq >= 0 && H > 0, "vog_lstm_layer_fwd: bad dimension");
+    if (T == 0 || Bq == 0) return 0;
+    VOG_REQUIRE(gx && whh && lens && out_lp && workspace, "vog_lstm_layer_fwd: null operand");
+    return lstm_layer_fwd(gx, ldg, whh, (const long long*)lens, T, Bq, H, out_lp, ld_out, lp_kind, workspace,
+                          (cudaStream_t)stream);
 }
 
 }  // extern "C"

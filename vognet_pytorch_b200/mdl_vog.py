@@ -91,7 +91,7 @@ class VOGNetB200(nn.Module):
             self.pe_mul_sub_enc = _lin_relu(5, m.mul_tx.n_heads)
 
         self.compute = 'fp32x'
-        self.lang_side_stream = False
+        self.use_cuda_graph = False
 
     @staticmethod
     def _make_tx(d, tx_cfg):
@@ -140,6 +140,63 @@ class VOGNetB200(nn.Module):
         enc = enc * inp['srl_arg_inds_msk'].reshape(B * nv, nsrl, 1).float()
         return enc.view(B, nv * nsrl, D)
 
+    def _lang_weights(self, kind):
+        """cached tensor-core operands of the language side: per layer the forward|reverse W_ih
+        stacked to [8H, in] (low precision) with b_ih+b_hh, and W_hh stacked to [2,4H,H] fp32."""
+        lstm = self.lstm_encoder.lstm
+        params = [p for p in lstm.parameters()]
+        cache = self.__dict__.setdefault('_lang_cache', {})
+        sig = tuple((p.data_ptr(), p._version) for p in params) + (kind,)
+        ent = cache.get(kind)
+        if ent is None or ent[0] != sig:
+            layers = []
+            with torch.no_grad():
+                for l in range(lstm.num_layers):
+                    g = lambda n: getattr(lstm, f'{n}_l{l}').detach()              # noqa: E731
+                    gr = lambda n: getattr(lstm, f'{n}_l{l}_reverse').detach()     # noqa: E731
+                    wih = torch.cat([g('weight_ih'), gr('weight_ih')], 0).float().contiguous()
+                    bias = torch.cat([g('bias_ih') + g('bias_hh'), gr('bias_ih') + gr('bias_hh')], 0).float().contiguous()
+                    whh = torch.stack([g('weight_hh'), gr('weight_hh')], 0).float().contiguous()
+                    layers.append((ops.cast_lp(wih, kind), bias, whh))
+            ent = (sig, layers)
+            cache[kind] = ent
+        return ent[1]
+
+    def language_encode_tc(self, inp):
+        """Language side without host synchronisation (CUDA-graph capturable): embedding gather,
+        one tcgen05 GEMM per layer for the input projections of all timesteps and both directions,
+        the persistent LSTM recurrence kernel, tcgen05 GEMMs for the two output projections.
+        Same arithmetic as ``language_encode`` (packed-sequence semantics from the device lengths)."""
+        kind = ops.LP_BF16 if self.compute == 'bf16' else ops.LP_TF32
+        words = inp['srl_arg_words_ind']
+        B, nv, nsrl, L = words.shape
+        Bq = B * nv
+        flat = words.reshape(Bq, nsrl * L)
+        wm = inp['srl_arg_word_mask'].reshape(Bq, -1)
+        pad = wm == -1
+        toks = torch.gather(flat, 1, wm.masked_fill(pad, 0)).masked_fill(pad, self.vocab_size)
+        T = toks.shape[1]
+        lens = inp['srl_arg_word_mask_len'].reshape(Bq).contiguous()
+        emb = self.lstm_encoder.embed_tokens(toks.t().contiguous()).reshape(T * Bq, -1)   # time-major rows
+        x_lp = ops.cast_lp(emb, kind)
+        for wih_lp, bias, whh in self._lang_weights(kind):
+            gx, _ = ops.tc_gemm(x_lp, wih_lp, bias=bias)
+            x_lp = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, kind)
+        full, _ = ops.tc_gemm(x_lp, self._lp_weight('lstm_proj', self.lstm_out_feat_proj[0].weight, kind),
+                              bias=self.lstm_out_feat_proj[0].bias, relu=True)               # [T*Bq, le]
+        D = full.shape[-1]
+        full = full.view(T, Bq, D)
+        cap = inp['srl_arg_words_capture'].reshape(Bq, nsrl, 2)
+        bidx = torch.arange(Bq, device=full.device).view(Bq, 1).expand(Bq, nsrl)
+        st = full[cap[..., 0], bidx]                                     # [Bq, nsrl, D]
+        en = full[cap[..., 1], bidx]
+        cat = torch.cat([st, en], 2).reshape(Bq * nsrl, 2 * D)
+        enc, _ = ops.tc_gemm(ops.cast_lp(cat, kind),
+                             self._lp_weight('srl_enc', self.srl_arg_words_out_enc[0].weight, kind),
+                             bias=self.srl_arg_words_out_enc[0].bias, relu=True)
+        enc = enc.view(Bq, nsrl, D) * inp['srl_arg_inds_msk'].reshape(Bq, nsrl, 1).float()
+        return enc.view(B, nv * nsrl, D)
+
     # -----------------------------------------------------------------------------------------
     def _groups(self, ncmp):
         """(nfrm, nppf') of the per-frame multimodal sequences (code/mdl_conc_single.py:24-28,131-135)."""
@@ -172,21 +229,27 @@ class VOGNetB200(nn.Module):
         return ent[1]
 
     def _forward_tc(self, inp):
+        feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
+        assert inp['srl_arg_words_ind'].shape[1] == 1, 'temp/spat concatenation has one verb slot per query'
+        ncmp = inp['new_srl_idxs'].shape[1]
+        if self.use_cuda_graph:
+            return self._forward_tc_graph(inp, ncmp)
+        lang = self.language_encode_tc(inp)                           # [B, nsrl, 256] fp32
+        x, x_lp = self._visual_tc(feat, seg, props, ncmp)
+        return self._fusion_tc(x, x_lp, lang, props, inp['srl_arg_inds_msk'], inp['num_cmp_msk'], ncmp)
+
+    def _visual_tc(self, feat, seg, props, ncmp):
+        """prop/seg encoders -> prop|seg rows -> object transformer.  Independent of the language
+        side.  -> x [B*P, 512] fp32 and its low-precision copy."""
         kind = ops.LP_BF16 if self.compute == 'bf16' else ops.LP_TF32
         lp_dtype = torch.bfloat16 if kind == ops.LP_BF16 else torch.float32
-        feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
         dev = feat.device
         B, P, _ = feat.shape
-        ncmp = inp['new_srl_idxs'].shape[1]
         nppf = self.num_prop_per_frm
         nvf = seg.shape[1]
         assert nvf * nppf == P, (nvf, nppf, P)
-        assert inp['srl_arg_words_ind'].shape[1] == 1, 'temp/spat concatenation has one verb slot per query'
-        nsrl = inp['srl_arg_words_ind'].shape[2]
-        lang = self.language_encode(inp)                              # [B, nsrl, 256] fp32
-
-        # prop|seg features, fp32 + low-precision copy, both halves written by GEMM epilogues
-        # (the seg half with row replication over the nppf proposals of its (frame,vid) slot)
+        # both halves of the prop|seg row are written by GEMM epilogues (the seg half with row
+        # replication over the nppf proposals of its (frame,vid) slot)
         x = torch.empty(B * P, self.ps_dim, device=dev, dtype=torch.float32)
         x_lp = torch.empty(B * P, self.ps_dim, device=dev, dtype=lp_dtype)
         pe_ = self.prop_encoder[0].out_features
@@ -197,8 +260,6 @@ class VOGNetB200(nn.Module):
                     self._lp_weight('seg', self.seg_encoder[0].weight, kind),
                     bias=self.seg_encoder[0].bias, relu=True, out_f32=x[:, pe_:], out_lp=x_lp[:, pe_:],
                     rep=nppf)
-        props2 = props.reshape(B * P, props.shape[-1])
-
         if self.USE_OBJ_TX and self.cfg.mdl.obj_tx.to_use:
             otx = self.cfg.mdl.obj_tx
             if otx.one_frm:
@@ -208,12 +269,20 @@ class VOGNetB200(nn.Module):
                 Bt_o, N_o, fdiv = B, P, 1.0
             bias = None
             if otx.use_rel:
-                a = ops.pe_project(props2, self.pe_obj_sub_enc[0].weight, self.vid_w, self.vid_h, fdiv)
+                a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_obj_sub_enc[0].weight,
+                                   self.vid_w, self.vid_h, fdiv)
                 bias = RelBias(a, self.pe_obj_sub_enc[0].bias, N_o)
             x, x_lp = self.obj_txf._exec.run(x.view(Bt_o, N_o, self.ps_dim), bias, self.compute,
                                              x_lp=x_lp, want_lp=True)
             x = x.reshape(B * P, self.ps_dim)
+        return x, x_lp
 
+    def _fusion_tc(self, x, x_lp, lang, props, srl_msk, cmp_msk, ncmp):
+        """vis|lang tokens regrouped per frame -> multimodal transformer -> lin2 -> masked scores."""
+        kind = ops.LP_BF16 if self.compute == 'bf16' else ops.LP_TF32
+        B, nsrl = lang.shape[0], lang.shape[1]
+        P = x.shape[0] // B
+        nppf = self.num_prop_per_frm
         nfrm, nppf2 = self._groups(ncmp)
         vis = x.view(B, nfrm, 1, nppf2, self.ps_dim).expand(B, nfrm, nsrl, nppf2, self.ps_dim)
         lng = lang.view(B, 1, nsrl, 1, self.lang_dim).expand(B, nfrm, nsrl, nppf2, self.lang_dim)
@@ -223,7 +292,8 @@ class VOGNetB200(nn.Module):
             mtx = self.cfg.mdl.mul_tx
             bias = None
             if mtx.use_rel:
-                a = ops.pe_project(props2, self.pe_mul_sub_enc[0].weight, self.vid_w, self.vid_h, float(nfrm))
+                a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
+                                   self.vid_w, self.vid_h, float(nfrm))
                 bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
             xm, xm_lp = self.mult_txf._exec.run(xm, bias, self.compute, want_lp=True)
         xm2 = xm.reshape(-1, self.vl_dim)
@@ -233,7 +303,48 @@ class VOGNetB200(nn.Module):
                            bias=self.lin2[0].bias, relu=True)
         lg = ops.sgemm_nt(h, self.lin2[2].weight, self.lin2[2].bias)
         logits = lg.view(B, nfrm, nsrl, nppf2).transpose(1, 2).reshape(B, 1, nsrl, P)
-        return self._mask_outputs(logits, inp, B, nsrl, ncmp, nppf, P)
+        return self._mask_outputs(logits, {'num_cmp_msk': cmp_msk, 'srl_arg_inds_msk': srl_msk},
+                                  B, nsrl, ncmp, nppf, P)
+
+    # -- CUDA-graph execution: the whole forward is ONE graph per (compute, shapes) signature with
+    #    two parallel branches - language side (embedding, LSTM, projections) and visual side
+    #    (encoders, object transformer) - joined before the multimodal transformer.  Nothing in it
+    #    synchronises with the host; inputs are copied into the graph's static buffers.
+    _GRAPH_KEYS = ('pad_region_feature', 'seg_feature_for_frms', 'pad_proposals', 'srl_arg_inds_msk',
+                   'num_cmp_msk', 'srl_arg_words_ind', 'srl_arg_word_mask', 'srl_arg_word_mask_len',
+                   'srl_arg_words_capture')
+
+    def _forward_tc_graph(self, inp, ncmp):
+        feat = inp['pad_region_feature']
+        key = (self.compute, ncmp, feat.device.index) + tuple(tuple(inp[k].shape) for k in self._GRAPH_KEYS)
+        graphs = self.__dict__.setdefault('_graphs', {})
+        g = graphs.get(key)
+        if g is None:
+            st = {k: inp[k].clone() for k in self._GRAPH_KEYS}
+
+            def body(side):
+                cur = torch.cuda.current_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    lang = self.language_encode_tc(st)
+                x, x_lp = self._visual_tc(st['pad_region_feature'], st['seg_feature_for_frms'],
+                                          st['pad_proposals'], ncmp)
+                cur.wait_stream(side)
+                return self._fusion_tc(x, x_lp, lang, st['pad_proposals'], st['srl_arg_inds_msk'],
+                                       st['num_cmp_msk'], ncmp)
+            side = torch.cuda.Stream(device=feat.device)
+            body(side)                              # eager warm-up: packs weights, sets kernel attributes
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(device=feat.device)
+            with torch.cuda.graph(graph, stream=cap):
+                out = body(side)
+            g = dict(st=st, graph=graph, out=out)
+            graphs[key] = g
+        for k, buf in g['st'].items():
+            buf.copy_(inp[k], non_blocking=True)
+        g['graph'].replay()
+        return {k: v.clone() for k, v in g['out'].items()}
 
     def _mask_outputs(self, logits, inp, B, nsrl, ncmp, nppf, P):
         cm = inp['num_cmp_msk'].float()

@@ -208,11 +208,15 @@ def tc_gemm(a, w, bias=None, residual=None, relu=False, out_f32=None, out_lp=Non
     if bias is not None:
         _req(bias, torch.float32, 'bias', 1)
     L = _lib.lib()
+    BN = BN or pick_bn(N)
+    ws, ws_bytes = None, L.vog_tc_gemm_workspace_bytes(M, N, K, tf32, BN)
+    if ws_bytes:
+        ws = torch.empty(ws_bytes, device=a.device, dtype=torch.uint8)
     _lib.check(L.vog_tc_gemm(_ptr(a), _rowmajor2d(a, 'a'), _ptr(w), _rowmajor2d(w, 'w'), M, N, K, tf32,
-                             BN or pick_bn(N), _ptr(bias), int(relu), _ptr(residual), ldr,
+                             BN, _ptr(bias), int(relu), _ptr(residual), ldr,
                              _ptr(out_f32), _rowmajor2d(out_f32, 'out_f32') if out_f32 is not None else 0,
                              _ptr(out_lp), _rowmajor2d(out_lp, 'out_lp') if out_lp is not None else 0,
-                             lp_kind, rep, _stream()), 'vog_tc_gemm')
+                             lp_kind, rep, _ptr(ws), ws_bytes, _stream()), 'vog_tc_gemm')
     return out_f32, out_lp
 
 
@@ -263,4 +267,23 @@ def tc_attn_fwd(q, k, vt, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, b
     _lib.check(L.vog_tc_attn_fwd(_ptr(q), _ptr(k), _ptr(vt), Bt, N, H, dhp, npad, dh_arr, float(inv_scale),
                                  bias_mode, _ptr(a), nbox, _ptr(bpe), _ptr(dense), _ptr(out),
                                  _rowmajor2d(out, 'out'), out_kind, _stream()), 'vog_tc_attn_fwd')
+    return out
+
+
+def lstm_layer_fwd(gx, whh, lens, T, Bq, kind):
+    """gx [T*Bq, 8H] fp32, whh [2,4H,H] fp32, lens [Bq] int64 -> h [T*Bq, 2H] (bf16 / tf32-rounded)."""
+    _req(gx, torch.float32, 'gx', 2), _req(whh, torch.float32, 'whh', 3), _req(lens, torch.int64, 'lens', 1)
+    H = whh.shape[2]
+    if whh.shape != (2, 4 * H, H) or not whh.is_contiguous() or gx.shape != (T * Bq, 8 * H):
+        raise ValueError('lstm_layer_fwd: inconsistent shapes')
+    L = _lib.lib()
+    out = torch.empty(T * Bq, 2 * H, device=gx.device, dtype=_LP_DTYPE[kind])
+    for b0 in range(0, Bq, 8):                      # the kernel takes <= 8 sequences per launch
+        nb = min(8, Bq - b0)
+        if Bq > 8:
+            raise NotImplementedError('lstm_layer_fwd: more than 8 sequences per batch')
+        ws = torch.empty(L.vog_lstm_workspace_bytes(nb, H), device=gx.device, dtype=torch.uint8)
+        _lib.check(L.vog_lstm_layer_fwd(_ptr(gx), _rowmajor2d(gx, 'gx'), _ptr(whh), _ptr(lens), T, nb, H,
+                                        _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _stream()),
+                   'vog_lstm_layer_fwd')
     return out
