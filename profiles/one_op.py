@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Run ONE hot-path op a few times (for `ncu --set full -k regex:<kernel>` captures).
+usage: one_op.py gemm M N K [bf16|tf32] [residual] | attn Bt N d | lstm"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vognet_pytorch_b200 import ops  # noqa: E402
+
+dev = 'cuda:0'
+what = sys.argv[1]
+if what == 'gemm':
+    M, N, K = [int(v) for v in sys.argv[2:5]]
+    kind = ops.LP_TF32 if 'tf32' in sys.argv else ops.LP_BF16
+    dt = torch.bfloat16 if kind == ops.LP_BF16 else torch.float32
+    a = (torch.rand(M, K, device=dev) - 0.5).to(dt)
+    w = (torch.rand(N, K, device=dev) - 0.5).to(dt)
+    r = torch.rand(M, N, device=dev) if 'residual' in sys.argv else None
+    o32 = torch.empty(M, N, device=dev) if r is not None else None
+    olp = torch.empty(M, N, device=dev, dtype=dt) if r is None else None
+    for _ in range(4):
+        ops.tc_gemm(a, w, residual=r, out_f32=o32, out_lp=olp, want_f32=r is not None,
+                    lp_kind=(kind if r is None else ops.LP_NONE))
+elif what == 'attn':
+    Bt, N, d = [int(v) for v in sys.argv[2:5]]
+    hd = ops.chunk_sizes(d, 3)
+    dhp = ops.round_up(max(hd), 64)
+    q = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
+    k = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
+    vt = (torch.rand(Bt, 3, dhp, ops.round_up(N, 8), device=dev) - 0.5).bfloat16()
+    nbox = N // 5 if N % 5 == 0 else N
+    a = torch.rand(Bt * nbox, 3, device=dev)
+    bpe = torch.zeros(3, device=dev)
+    for _ in range(4):
+        ops.tc_attn_fwd(q, k, vt, N, hd, 1.0 / d ** 0.5, bias_mode=ops.BIAS_RANK1, a=a, nbox=nbox, bpe=bpe)
+torch.cuda.synchronize()
+print('done')

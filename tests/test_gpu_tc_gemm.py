@@ -51,7 +51,7 @@ def test_tc_gemm_epilogue_all_options():
         assert (got[:, r].double() - ref).abs().max() < 3e-4
     assert o32[:, :20].abs().max() == 0 and o32[:, 276:].abs().max() == 0
     lp = olp[:, 8:264].cpu().view(M, rep, N)
-    assert (lp[:, 1].double() - ref).abs().max() < 2e-2
+    assert ((lp[:, 1].double() - ref).abs() / (1 + ref.abs())).max() < 8e-3     # bf16 rounding of values up to ~16
     assert torch.equal(lp[:, 0], got[:, 0].bfloat16())
     # tf32-rounded low precision copy
     _, o2 = ops.tc_gemm(a.to(DEV), w.to(DEV), lp_kind=ops.LP_TF32, want_f32=False)
@@ -77,9 +77,10 @@ def test_tc_gemm_qkv_scatter(Bt, N, d, H):
     full = (x.double() @ wp.double().t()).view(Bt, N, 3, H, dhp)
     for got, which in ((q, 0), (k, 1)):
         ref = full[:, :, which].permute(0, 2, 1, 3)
-        assert (got.cpu().double() - ref).abs().max() < 3e-2
+        assert ((got.cpu().double() - ref).abs() / (1 + ref.abs())).max() < 8e-3      # bf16 outputs
     refv = full[:, :, 2].permute(0, 2, 3, 1)                     # [Bt,H,dhp,N]
-    assert (vt.cpu().double()[..., :N] - refv).abs().max() < 3e-2
+    assert ((vt.cpu().double()[..., :N] - refv).abs() / (1 + refv.abs())).max() < 8e-3
     # padded head columns are exact zeros
     for h, dh in enumerate(hd):
-        assert q[:, h, :, dh:].abs().max() == 0 and vt[:, h, dh:, :].abs().max() == 0
+        if dh < dhp:
+            assert q[:, h, :, dh:].abs().max() == 0 and vt[:, h, dh:, :].abs().max() == 0

@@ -75,43 +75,55 @@ lstm_rec_kernel(const LstmParams p)
     for (int step = 0; step < Tmax; ++step) {
         const int t = d == 0 ? step : Tmax - 1 - step;
         // ---- recurrent matvecs: row ri = gate*nu + uu, one warp per row, all Bq sequences at once
-        for (int ri = warp; ri < 4 * nu; ri += nwarps) {
-            const int gate = ri / nu, uu = ri % nu;
-            const int row = gate * H + u0 + uu;
-            const float4* w4 = reinterpret_cast<const float4*>(whh + (size_t)row * H);
-            float acc[LS_MAXB];
+        // the loads of a whole row (H/128 float4 per lane) are issued before any is consumed and the
+        // next row's loads are in flight while this one is reduced: the loop is L2-latency bound
+        {
+            constexpr int NQ = 8;                       // float4 per lane per row: H <= 1024
+            const int nrows = 4 * nu;
+            float4 wn[NQ];
+            auto row_of = [&](int ri) { return (ri / nu) * H + u0 + (ri % nu); };
+            auto load_row = [&](int ri, float4 (&w)[NQ]) {
+                const float4* w4 = reinterpret_cast<const float4*>(whh + (size_t)row_of(ri) * H);
 #pragma unroll
-            for (int b = 0; b < LS_MAXB; ++b) acc[b] = 0.f;
-            for (int k4 = lane; k4 < H / 4; k4 += 128) {
-                float4 w[4];
+                for (int q = 0; q < NQ; ++q)
+                    w[q] = (lane + 32 * q < H / 4) ? __ldg(w4 + lane + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            if (warp < nrows) load_row(warp, wn);
+            for (int ri = warp; ri < nrows; ri += nwarps) {
+                float4 w[NQ];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    w[q] = (k4 + 32 * q < H / 4) ? __ldg(w4 + k4 + 32 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < NQ; ++q) w[q] = wn[q];
+                if (ri + nwarps < nrows) load_row(ri + nwarps, wn);
+                const int gate = ri / nu, uu = ri % nu;
+                float acc[LS_MAXB];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (k4 + 32 * q >= H / 4) continue;
+                for (int b = 0; b < LS_MAXB; ++b) acc[b] = 0.f;
 #pragma unroll
-                    for (int b = 0; b < LS_MAXB; ++b) {
-                        if (b < Bq) {
-                            const float4 hv = *reinterpret_cast<const float4*>(h_s + b * H + 4 * (k4 + 32 * q));
-                            acc[b] = fmaf(w[q].x, hv.x, acc[b]);
-                            acc[b] = fmaf(w[q].y, hv.y, acc[b]);
-                            acc[b] = fmaf(w[q].z, hv.z, acc[b]);
-                            acc[b] = fmaf(w[q].w, hv.w, acc[b]);
+                for (int q = 0; q < NQ; ++q) {
+                    if (lane + 32 * q < H / 4) {
+#pragma unroll
+                        for (int b = 0; b < LS_MAXB; ++b) {
+                            if (b < Bq) {
+                                const float4 hv = *reinterpret_cast<const float4*>(h_s + b * H + 4 * (lane + 32 * q));
+                                acc[b] = fmaf(w[q].x, hv.x, acc[b]);
+                                acc[b] = fmaf(w[q].y, hv.y, acc[b]);
+                                acc[b] = fmaf(w[q].z, hv.z, acc[b]);
+                                acc[b] = fmaf(w[q].w, hv.w, acc[b]);
+                            }
                         }
                     }
                 }
-            }
-#pragma unroll
-            for (int b = 0; b < LS_MAXB; ++b)
-                if (b < Bq) acc[b] = warp_sum(acc[b]);
-            if (lane < Bq) {
-                float v = 0.f;
 #pragma unroll
                 for (int b = 0; b < LS_MAXB; ++b)
-                    if (b == lane) v = acc[b];
-                v += p.gx[((size_t)t * Bq + lane) * p.ldg + (size_t)d * 4 * H + row];
-                gate_s[(gate * LS_MAXU + uu) * LS_MAXB + lane] = v;
+                    if (b < Bq) acc[b] = warp_sum(acc[b]);
+                if (lane < Bq) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int b = 0; b < LS_MAXB; ++b)
+                        if (b == lane) v = acc[b];
+                    v += p.gx[((size_t)t * Bq + lane) * p.ldg + (size_t)d * 4 * H + row_of(ri)];
+                    gate_s[(gate * LS_MAXU + uu) * LS_MAXB + lane] = v;
+                }
             }
         }
         __syncthreads();
@@ -174,7 +186,7 @@ int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long 
 {
     if (T == 0 || Bq == 0) return 0;
     VOG_REQUIRE(Bq <= LS_MAXB, "lstm_layer_fwd: at most %d sequences per call (got %d)", LS_MAXB, Bq);
-    VOG_REQUIRE(H % 4 == 0 && H >= 4, "lstm_layer_fwd: H must be a multiple of 4");
+    VOG_REQUIRE(H % 4 == 0 && H >= 4 && H <= 1024, "lstm_layer_fwd: H must be a multiple of 4, <= 1024");
     VOG_REQUIRE(lp_kind == 1 || lp_kind == 2, "lstm_layer_fwd: bad lp_kind");
     VOG_REQUIRE(ldg >= 8LL * H && ld_out >= 2LL * H, "lstm_layer_fwd: bad leading dimension");
     VOG_REQUIRE((reinterpret_cast<uintptr_t>(whh) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,

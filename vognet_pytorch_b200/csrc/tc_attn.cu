@@ -73,29 +73,38 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     const uint32_t q_bytes = FA_BQ * dhp * 2;
     const uint32_t k_bytes = FA_BKV * dhp * 2;        // nkk sub-tiles of [64 rows x 128 B]
     const uint32_t v_bytes = dhp * 128;               // [dhp rows x 128 B]
-    const uint32_t stage_bytes = k_bytes + v_bytes;
+    // K and V^T live in SEPARATE rings: a K slot is released as soon as S_j = Q K_j^T has been
+    // computed (one whole softmax earlier than the V slot, which PV_j still needs), so the next K
+    // tile is requested early enough for its L2 latency to hide behind the softmax of tile j
+    const int NS = p.stages;
     const uint32_t q_smem = smem_base;
     const uint32_t p_smem0 = q_smem + q_bytes;        // 2 x [128 x 128 B]
-    const uint32_t kv_smem0 = p_smem0 + 2 * FA_BQ * 128;
-    const uint32_t aux_off = (kv_smem0 - smem_base) + p.stages * stage_bytes;
-    float* ak_gen = reinterpret_cast<float*>(smem_gen + aux_off);          // [stages][64]
-    const uint32_t bar_off = aux_off + p.stages * FA_BKV * 4;
+    const uint32_t k_smem0 = p_smem0 + 2 * FA_BQ * 128;
+    const uint32_t v_smem0 = k_smem0 + NS * k_bytes;
+    const uint32_t aux_off = (v_smem0 - smem_base) + NS * v_bytes;
+    float* ak_gen = reinterpret_cast<float*>(smem_gen + aux_off);          // [stages][64], rides with V
+    const uint32_t bar_off = aux_off + NS * FA_BKV * 4;
     const uint32_t bar_base = smem_base + bar_off;
-    auto kv_full = [&](int s) { return bar_base + 8u * s; };
-    auto kv_empty = [&](int s) { return bar_base + 8u * (FA_MAX_STAGES + s); };
-    auto s_full = [&](int b) { return bar_base + 8u * (2 * FA_MAX_STAGES + b); };
-    auto p_full = [&](int b) { return bar_base + 8u * (2 * FA_MAX_STAGES + 2 + b); };
-    auto p_empty = [&](int b) { return bar_base + 8u * (2 * FA_MAX_STAGES + 4 + b); };
-    const uint32_t q_full = bar_base + 8u * (2 * FA_MAX_STAGES + 6);
+    auto k_full = [&](int s) { return bar_base + 8u * s; };
+    auto k_empty = [&](int s) { return bar_base + 8u * (FA_MAX_STAGES + s); };
+    auto v_full = [&](int s) { return bar_base + 8u * (2 * FA_MAX_STAGES + s); };
+    auto v_empty = [&](int s) { return bar_base + 8u * (3 * FA_MAX_STAGES + s); };
+    auto s_full = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + b); };
+    auto p_full = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 2 + b); };
+    auto p_empty = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 4 + b); };
+    const uint32_t q_full = bar_base + 8u * (4 * FA_MAX_STAGES + 6);
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(
-        smem_gen + bar_off + 8 * (2 * FA_MAX_STAGES + 7));
+        smem_gen + bar_off + 8 * (4 * FA_MAX_STAGES + 7));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_q);
         tma_prefetch_desc(&tma_k);
         tma_prefetch_desc(&tma_vt);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(kv_full(s), 2); mbar_init(kv_empty(s), 1); }
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+            mbar_init(v_full(s), 2); mbar_init(v_empty(s), 1);
+        }
         for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 128); mbar_init(p_empty(b), 1); }
         mbar_init(q_full, 1);
         fence_barrier_init();
@@ -117,29 +126,49 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
             for (int kk = 0; kk < nkk; ++kk)
                 tma_load_3d(q_smem + kk * (FA_BQ * 128), &tma_q, q_full, kk * 64, q_tile * FA_BQ, bh);
         }
-        int s = 0; uint32_t ph = 0;
-        for (int j = 0; j < T; ++j) {
-            if (lane == 0) mbar_wait(kv_empty(s), ph ^ 1);
-            __syncwarp();
-            const uint32_t kdst = kv_smem0 + s * stage_bytes;
+        int jk = 0, jv = 0;
+        long long t_idle = 0;
+        while (jk < T || jv < T) {
+            int do_k = 0, do_v = 0;
             if (lane == 0) {
-                mbar_arrive_expect_tx(kv_full(s), stage_bytes);
-                for (int kk = 0; kk < nkk; ++kk)
-                    tma_load_3d(kdst + kk * (FA_BKV * 128), &tma_k, kv_full(s), kk * 64, j * FA_BKV, bh);
-                tma_load_3d(kdst + k_bytes, &tma_vt, kv_full(s), j * FA_BKV, 0, bh);
+                if (jk < T) do_k = mbar_try_wait(k_empty(jk % NS), (uint32_t)(((jk / NS) & 1) ^ 1));
+                if (jv < T) do_v = mbar_try_wait(v_empty(jv % NS), (uint32_t)(((jv / NS) & 1) ^ 1));
+                if (!(do_k | do_v)) {                  // bounded polling: a protocol bug traps instead of hanging
+                    if (t_idle == 0) t_idle = clock64();
+                    else if (clock64() - t_idle > 4000000000LL) { printf("vog: attention producer timeout\n"); __trap(); }
+                } else t_idle = 0;
             }
-            if (p.bias_mode == 1) {
-#pragma unroll
-                for (int t = lane; t < FA_BKV; t += 32) {
-                    const int key = j * FA_BKV + t;
-                    float v = 0.f;
-                    if (key < N) v = __ldg(p.a + ((size_t)bt * p.nbox + key % p.nbox) * p.H + h) * p.c;
-                    ak_gen[s * FA_BKV + t] = v;
+            do_k = __shfl_sync(0xffffffffu, do_k, 0);
+            do_v = __shfl_sync(0xffffffffu, do_v, 0);
+            if (do_k) {
+                if (lane == 0) {
+                    const int s = jk % NS;
+                    mbar_arrive_expect_tx(k_full(s), k_bytes);
+                    for (int kk = 0; kk < nkk; ++kk)
+                        tma_load_3d(k_smem0 + s * k_bytes + kk * (FA_BKV * 128), &tma_k, k_full(s), kk * 64,
+                                    jk * FA_BKV, bh);
                 }
+                ++jk;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(kv_full(s));
-            if (++s == p.stages) { s = 0; ph ^= 1; }
+            if (do_v) {
+                const int s = jv % NS;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(v_full(s), v_bytes);
+                    tma_load_3d(v_smem0 + s * v_bytes, &tma_vt, v_full(s), jv * FA_BKV, 0, bh);
+                }
+                if (p.bias_mode == 1) {
+#pragma unroll
+                    for (int t = lane; t < FA_BKV; t += 32) {
+                        const int key = jv * FA_BKV + t;
+                        float v = 0.f;
+                        if (key < N) v = __ldg(p.a + ((size_t)bt * p.nbox + key % p.nbox) * p.H + h) * p.c;
+                        ak_gen[s * FA_BKV + t] = v;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(v_full(s));
+                ++jv;
+            }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -150,10 +179,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
             const uint32_t idesc_o = umma_idesc(FMT_BF16, FA_BQ, n_pv);
             const int ksteps = (dh + 15) / 16;           // skip the all-zero padded tail of the head dim
             auto issue_s = [&](int j) {
-                const int s = j % p.stages;
-                mbar_wait(kv_full(s), (uint32_t)((j / p.stages) & 1));
+                const int s = j % NS;
+                mbar_wait(k_full(s), (uint32_t)((j / NS) & 1));
                 tc_fence_after();
-                const uint32_t kbase = kv_smem0 + s * stage_bytes;
+                const uint32_t kbase = k_smem0 + s * k_bytes;
                 const uint32_t d = tmem_s0 + (j & 1) * FA_BKV;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const int kk = ks >> 2, k4 = ks & 3;
@@ -161,22 +190,24 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                     const uint64_t bd = umma_desc_sw128(kbase + kk * (FA_BKV * 128)) + 2 * k4;
                     umma<false>(d, ad, bd, idesc_s, ks != 0);
                 }
+                umma_commit(k_empty(s));
                 umma_commit(s_full(j & 1));
             };
             mbar_wait(q_full, 0);
             issue_s(0);
             for (int j = 0; j < T; ++j) {
                 if (j + 1 < T) issue_s(j + 1);
-                const int s = j % p.stages, pb = j & 1;
+                const int s = j % NS, pb = j & 1;
+                mbar_wait(v_full(s), (uint32_t)((j / NS) & 1));
                 mbar_wait(p_full(pb), (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
-                const uint32_t vbase = kv_smem0 + s * stage_bytes + k_bytes;
+                const uint32_t vbase = v_smem0 + s * v_bytes;
                 const uint64_t ad0 = umma_desc_sw128(p_smem0 + pb * (FA_BQ * 128));
                 const uint64_t bd0 = umma_desc_sw128(vbase);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
                     umma<false>(tmem_o, ad0 + 2 * k4, bd0 + 2 * k4, idesc_o, (j | k4) != 0);
-                umma_commit(kv_empty(s));
+                umma_commit(v_empty(s));
                 umma_commit(p_empty(pb));
             }
         }
@@ -198,8 +229,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         const uint32_t sw = (uint32_t)(row & 7);
 
         for (int j = 0; j < T; ++j) {
-            const int sb = j & 1, s = j % p.stages;
-            mbar_wait(kv_full(s), (uint32_t)((j / p.stages) & 1));     // a_j staged (already complete)
+            const int sb = j & 1, s = j % NS;
+            mbar_wait(v_full(s), (uint32_t)((j / NS) & 1));            // a_j staged next to V^T_j
             mbar_wait(s_full(sb), (uint32_t)((j >> 1) & 1));
             tc_fence_after();
             uint32_t r0[32], r1[32];
@@ -353,7 +384,7 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     uint32_t bv[3] = {64, (uint32_t)dhp, 1};
     if (make_tmap(&tv, vt, 2, 1, 3, dv, sv, bv)) return -1;
 
-    const int fixed = FA_BQ * dhp * 2 + 2 * FA_BQ * 128 + 256 /*barriers*/ + 1024 /*alignment*/;
+    const int fixed = FA_BQ * dhp * 2 + 2 * FA_BQ * 128 + 384 /*barriers*/ + 1024 /*alignment*/;
     const int stage_bytes = 2 * FA_BKV * dhp * 2 + FA_BKV * 4;    // K + V^T + staged a_j
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > FA_MAX_STAGES) stages = FA_MAX_STAGES;
