@@ -117,11 +117,14 @@ int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, i
  * q,k [Bt,H,N,dhp] bf16, vt [Bt,H,dhp,npad] bf16 (vog_tc_gemm_qkv layouts), dh[H] true head dims
  * (host array), bias as in vog_attn_fwd_f32 (a, bpe, dense are device pointers).  out is
  * [Bt*N, ldo >= H*dhp], bf16 (out_kind VOG_LP_BF16) or tf32-rounded fp32 (VOG_LP_TF32); padded
- * head columns are written as zeros.  Same reference lines as vog_attn_fwd_f32. */
+ * head columns are written as zeros.  VOG_BIAS_RANK1 needs a workspace of
+ * vog_tc_attn_workspace_bytes() bytes (per-key bias factors expanded to [Bt*H, N] by a small
+ * pre-kernel).  Same reference lines as vog_attn_fwd_f32. */
+int64_t vog_tc_attn_workspace_bytes(int Bt, int N, int H);
 int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp,
                     int npad, const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
                     const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
-                    void* stream);
+                    void* workspace, int64_t workspace_bytes, void* stream);
 
 /* One layer of the bidirectional LSTM recurrence of the language encoder, both directions, all
  * timesteps, in one persistent launch (packed-sequence semantics from the device-side `lens`, no

@@ -41,12 +41,14 @@ _SIGNATURES = {
                     P, c_i64, P, c_i64, c_int, c_int, P, c_i64, P],
     'vog_lstm_workspace_bytes': [c_int, c_int],
     'vog_lstm_layer_fwd': [P, c_i64, P, P, c_int, c_int, c_int, P, c_i64, c_int, P, P],
+    'vog_tc_attn_workspace_bytes': [c_int, c_int, c_int],
     'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,
-                        c_i64, c_int, P],
+                        c_i64, c_int, P, c_i64, P],
     'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
 }
 _RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong,
-            'vog_tc_gemm_workspace_bytes': ctypes.c_int64, 'vog_lstm_workspace_bytes': ctypes.c_int64}
+            'vog_tc_gemm_workspace_bytes': ctypes.c_int64, 'vog_lstm_workspace_bytes': ctypes.c_int64,
+            'vog_tc_attn_workspace_bytes': ctypes.c_int64}
 
 
 def sources():

@@ -46,7 +46,9 @@ int num_sms();
 // ---- tc_attn.cu : fused relative-position-bias attention (tcgen05) ---------------------------
 int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
-            const float* dense, void* out, long long ldo, int out_kind, cudaStream_t st);
+            const float* dense, void* out, long long ldo, int out_kind, void* workspace,
+            long long workspace_bytes, cudaStream_t st);
+long long tc_attn_workspace_bytes(int Bt, int N, int H);
 int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int kind,
             cudaStream_t st);
 

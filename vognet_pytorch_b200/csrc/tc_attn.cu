@@ -41,6 +41,7 @@ struct AttnParams {
     float c;                    // log2(e) / sqrt(d_model)
     int bias_mode;              // 0 none, 1 rank-1, 2 dense
     const float* a; int nbox;   // [Bt*nbox, H]
+    const float* ak_seq; int ak_ld;   // [Bt*H, ak_ld]: c * a[key % nbox] per key, zero padded to 64
     const float* bpe;           // [H]
     const float* dense;         // [Bt,N,N,H]
     void* out; long long ldo; int out_kind;   // 1 bf16, 2 tf32-rounded fp32
@@ -81,9 +82,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     const uint32_t p_smem0 = q_smem + q_bytes;        // 2 x [128 x 128 B]
     const uint32_t k_smem0 = p_smem0 + 2 * FA_BQ * 128;
     const uint32_t v_smem0 = k_smem0 + NS * k_bytes;
-    const uint32_t aux_off = (v_smem0 - smem_base) + NS * v_bytes;
-    float* ak_gen = reinterpret_cast<float*>(smem_gen + aux_off);          // [stages][64], rides with V
-    const uint32_t bar_off = aux_off + NS * FA_BKV * 4;
+    const uint32_t bar_off = (v_smem0 - smem_base) + NS * v_bytes;
     const uint32_t bar_base = smem_base + bar_off;
     auto k_full = [&](int s) { return bar_base + 8u * s; };
     auto k_empty = [&](int s) { return bar_base + 8u * (FA_MAX_STAGES + s); };
@@ -103,7 +102,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         tma_prefetch_desc(&tma_vt);
         for (int s = 0; s < NS; ++s) {
             mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
-            mbar_init(v_full(s), 2); mbar_init(v_empty(s), 1);
+            mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 128); mbar_init(p_empty(b), 1); }
         mbar_init(q_full, 1);
@@ -156,17 +155,6 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                     mbar_arrive_expect_tx(v_full(s), v_bytes);
                     tma_load_3d(v_smem0 + s * v_bytes, &tma_vt, v_full(s), jv * FA_BKV, 0, bh);
                 }
-                if (p.bias_mode == 1) {
-#pragma unroll
-                    for (int t = lane; t < FA_BKV; t += 32) {
-                        const int key = jv * FA_BKV + t;
-                        float v = 0.f;
-                        if (key < N) v = __ldg(p.a + ((size_t)bt * p.nbox + key % p.nbox) * p.H + h) * p.c;
-                        ak_gen[s * FA_BKV + t] = v;
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(v_full(s));
                 ++jv;
             }
         }
@@ -230,7 +218,6 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
 
         for (int j = 0; j < T; ++j) {
             const int sb = j & 1, s = j % NS;
-            mbar_wait(v_full(s), (uint32_t)((j / NS) & 1));            // a_j staged next to V^T_j
             mbar_wait(s_full(sb), (uint32_t)((j >> 1) & 1));
             tc_fence_after();
             uint32_t r0[32], r1[32];
@@ -241,10 +228,11 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
 #pragma unroll
             for (int c = 0; c < 32; ++c) { sv[c] = __uint_as_float(r0[c]) * p.c; sv[32 + c] = __uint_as_float(r1[c]) * p.c; }
             if (p.bias_mode == 1) {
-                const float4* ak4 = reinterpret_cast<const float4*>(ak_gen + s * FA_BKV);
+                // rank-1 bias factor of the 64 keys: L1-resident broadcast loads (same address in every lane)
+                const float4* ak4 = reinterpret_cast<const float4*>(p.ak_seq + (size_t)bh * p.ak_ld + (size_t)j * FA_BKV);
 #pragma unroll
                 for (int c4 = 0; c4 < 16; ++c4) {
-                    const float4 a4 = ak4[c4];
+                    const float4 a4 = __ldg(ak4 + c4);
                     sv[4 * c4 + 0] += fmaxf(ai - a4.x, 0.f);
                     sv[4 * c4 + 1] += fmaxf(ai - a4.y, 0.f);
                     sv[4 * c4 + 2] += fmaxf(ai - a4.z, 0.f);
@@ -346,9 +334,28 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ak_seq[bt*H + h, key] = c * a[(bt*nbox + key % nbox), h] for key < N, 0 up to the 64-padded row end:
+// the per-key factor of the rank-1 bias in the order and scaling the softmax warps consume it
+__global__ void bias_expand_kernel(const float* __restrict__ a, float* __restrict__ ak, int Bt, int N, int H,
+                                   int nbox, int ld, float c)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)Bt * H * ld) return;
+    const int key = (int)(idx % ld);
+    const int bh = (int)(idx / ld);
+    const int bt = bh / H, h = bh % H;
+    ak[idx] = key < N ? a[((size_t)bt * nbox + key % nbox) * H + h] * c : 0.f;
+}
+
+long long tc_attn_workspace_bytes(int Bt, int N, int H)
+{
+    return (long long)Bt * H * round_up(N, FA_BKV) * 4;
+}
+
 int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
-            const float* dense, void* out, long long ldo, int out_kind, cudaStream_t st)
+            const float* dense, void* out, long long ldo, int out_kind, void* workspace,
+            long long workspace_bytes, cudaStream_t st)
 {
     if (Bt == 0 || N == 0) return 0;
     VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS, "tc_attn: H=%d out of range", H);
@@ -369,6 +376,17 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     p.c = inv_scale * 1.4426950408889634f;
     p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.bpe = bpe; p.dense = dense;
     p.out = out; p.ldo = ldo; p.out_kind = out_kind;
+    p.ak_seq = nullptr; p.ak_ld = round_up(N, FA_BKV);
+    if (bias_mode == 1) {
+        VOG_REQUIRE(workspace && workspace_bytes >= tc_attn_workspace_bytes(Bt, N, H) &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                    "tc_attn: rank-1 bias needs a 16-byte aligned workspace of tc_attn_workspace_bytes()");
+        p.ak_seq = reinterpret_cast<const float*>(workspace);
+        const long long n = (long long)Bt * H * p.ak_ld;
+        bias_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<float*>(workspace), Bt, N, H,
+                                                                         p.nbox, p.ak_ld, p.c);
+        if (check_launch("bias_expand")) return -1;
+    }
     const int cols = dhp + 2 * FA_BKV;
     p.tmem_cols = cols <= 256 ? 256 : 512;
 
@@ -385,7 +403,7 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     if (make_tmap(&tv, vt, 2, 1, 3, dv, sv, bv)) return -1;
 
     const int fixed = FA_BQ * dhp * 2 + 2 * FA_BQ * 128 + 384 /*barriers*/ + 1024 /*alignment*/;
-    const int stage_bytes = 2 * FA_BKV * dhp * 2 + FA_BKV * 4;    // K + V^T + staged a_j
+    const int stage_bytes = 2 * FA_BKV * dhp * 2;                  // one K slot + one V^T slot
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > FA_MAX_STAGES) stages = FA_MAX_STAGES;
     VOG_REQUIRE(stages >= 2, "tc_attn: not enough shared memory for dhp=%d", dhp);

@@ -154,10 +154,16 @@ int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, i
     return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
 
+int64_t vog_tc_attn_workspace_bytes(int Bt, int N, int H)
+{
+    if (Bt <= 0 || N <= 0 || H <= 0) return 0;
+    return tc_attn_workspace_bytes(Bt, N, H);
+}
+
 int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
                     const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
                     const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
-                    void* stream)
+                    void* workspace, int64_t workspace_bytes, void* stream)
 {
     VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_tc_attn_fwd: negative dimension");
     if (Bt == 0 || N == 0) return 0;
@@ -165,7 +171,7 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
     VOG_REQUIRE(q && k && vt && out && dh, "vog_tc_attn_fwd: null operand");
     VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_tc_attn_fwd: bad bias_mode %d", bias_mode);
     return tc_attn(q, k, vt, Bt, N, H, dhp, npad, dh, inv_scale, bias_mode, a, nbox, bpe, dense, out, ldo,
-                   out_kind, (cudaStream_t)stream);
+                   out_kind, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int64_t vog_lstm_workspace_bytes(int Bq, int H) { return lstm_workspace_bytes(Bq, H); }

@@ -264,9 +264,14 @@ def tc_attn_fwd(q, k, vt, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, b
         if tuple(dense.shape) != (Bt, N, N, H) or not dense.is_contiguous():
             raise ValueError(f'tc_attn_fwd: dense bias must be contiguous [{Bt},{N},{N},{H}]')
     L = _lib.lib()
+    ws, ws_bytes = None, 0
+    if bias_mode == BIAS_RANK1:
+        ws_bytes = L.vog_tc_attn_workspace_bytes(Bt, N, H)
+        ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
     _lib.check(L.vog_tc_attn_fwd(_ptr(q), _ptr(k), _ptr(vt), Bt, N, H, dhp, npad, dh_arr, float(inv_scale),
                                  bias_mode, _ptr(a), nbox, _ptr(bpe), _ptr(dense), _ptr(out),
-                                 _rowmajor2d(out, 'out'), out_kind, _stream()), 'vog_tc_attn_fwd')
+                                 _rowmajor2d(out, 'out'), out_kind, _ptr(ws), ws_bytes, _stream()),
+               'vog_tc_attn_fwd')
     return out
 
 
