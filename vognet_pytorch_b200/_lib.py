@@ -68,7 +68,8 @@ def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> vognet_pytorch_b200/libvog_b200.so"""
     if not force and not needs_build():
         return SO_PATH
-    cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH] + sources()
+    extra = os.environ.get('VOG_NVCC_EXTRA', '').split()       # e.g. -DVOG_ATTN_PROFILE
+    cmd = ['nvcc'] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH] + sources()
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)

@@ -31,7 +31,7 @@ using namespace tc;
 
 constexpr int FA_BQ = 128;          // query rows per CTA
 constexpr int FA_BKV = 64;          // keys per pipeline stage
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS = 384;          // warpgroups 0-1: softmax (2 threads per row); warpgroup 2: TMA warp, MMA warp, 2 idle
 constexpr int FA_MAX_STAGES = 8;
 constexpr float FA_RESCALE_T = 8.0f;   // log2 units
 
@@ -47,6 +47,7 @@ struct AttnParams {
     void* out; long long ldo; int out_kind;   // 1 bf16, 2 tf32-rounded fp32
     int stages;
     uint32_t tmem_cols;
+    long long* prof;            // optional [8] phase cycle counters (block 0, first softmax warp)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -59,10 +60,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                const __grid_constant__ CUtensorMap tma_vt, const AttnParams p)
 {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
-    const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
-    uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
+    const uint32_t smem_base = raw_u32;              // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t* smem_gen = smem_raw;
+    if ((raw_u32 & 1023u) != 0) { if (threadIdx.x == 0) printf("vog: dynamic smem not 1024-aligned\n"); __trap(); }
 
     const int q_tile = blockIdx.x, h = blockIdx.y, bt = blockIdx.z;
     const int dhp = p.dhp, N = p.N;
@@ -89,14 +91,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     auto v_full = [&](int s) { return bar_base + 8u * (2 * FA_MAX_STAGES + s); };
     auto v_empty = [&](int s) { return bar_base + 8u * (3 * FA_MAX_STAGES + s); };
     auto s_full = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + b); };
-    auto p_full = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 2 + b); };
-    auto p_empty = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 4 + b); };
-    const uint32_t q_full = bar_base + 8u * (4 * FA_MAX_STAGES + 6);
+    auto p_full = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 3 + b); };
+    auto p_empty = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 5 + b); };
+    const uint32_t q_full = bar_base + 8u * (4 * FA_MAX_STAGES + 7);
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(
-        smem_gen + bar_off + 8 * (4 * FA_MAX_STAGES + 7));
+        smem_gen + bar_off + 8 * (4 * FA_MAX_STAGES + 8));
+    float* xchg = reinterpret_cast<float*>(smem_gen + bar_off + 384);     // [2 parity][128 rows][2 halves]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
+    // roles: warps 0-7 softmax (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer; the control
+    // warps carry the HIGHEST warp ids because the SM's issue arbiter favours them
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tma_q);
         tma_prefetch_desc(&tma_k);
         tma_prefetch_desc(&tma_vt);
@@ -104,21 +109,24 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
             mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
             mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
         }
-        for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 128); mbar_init(p_empty(b), 1); }
+        for (int b = 0; b < 3; ++b) mbar_init(s_full(b), 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(p_full(b), 256); mbar_init(p_empty(b), 1); }
         mbar_init(q_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
+    if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_o = tmem_base;                 // columns [0, dhp)
-    const uint32_t tmem_s0 = tmem_base + dhp;          // 2 x 64 columns
+    const uint32_t tmem_s0 = tmem_base + dhp;          // 3 x 64 columns: score tiles are produced two ahead
 
     const int bh = bt * p.H + h;
 
-    if (warp == 0) {
+    if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // the control warpgroup hands registers ...
+    if (warp == 8) {
         // ================= producer =================
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, q_bytes);
@@ -130,8 +138,8 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         while (jk < T || jv < T) {
             int do_k = 0, do_v = 0;
             if (lane == 0) {
-                if (jk < T) do_k = mbar_try_wait(k_empty(jk % NS), (uint32_t)(((jk / NS) & 1) ^ 1));
-                if (jv < T) do_v = mbar_try_wait(v_empty(jv % NS), (uint32_t)(((jv / NS) & 1) ^ 1));
+                if (jk < T) do_k = mbar_test_wait(k_empty(jk % NS), (uint32_t)(((jk / NS) & 1) ^ 1));
+                if (jv < T) do_v = mbar_test_wait(v_empty(jv % NS), (uint32_t)(((jv / NS) & 1) ^ 1));
                 if (!(do_k | do_v)) {                  // bounded polling: a protocol bug traps instead of hanging
                     if (t_idle == 0) t_idle = clock64();
                     else if (clock64() - t_idle > 4000000000LL) { printf("vog: attention producer timeout\n"); __trap(); }
@@ -159,54 +167,81 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 9) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc(FMT_BF16, FA_BQ, FA_BKV);
             const int n_pv = (dh + 15) & ~15;
             const uint32_t idesc_o = umma_idesc(FMT_BF16, FA_BQ, n_pv);
             const int ksteps = (dh + 15) / 16;           // skip the all-zero padded tail of the head dim
+#ifdef VOG_ATTN_PROFILE
+            const bool mprof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            long long mc[4] = {0, 0, 0, 0};
+            long long mt = clock64();
+#define VOG_MPROF(i) if (mprof) { const long long tn = clock64(); mc[i] += tn - mt; mt = tn; }
+#else
+#define VOG_MPROF(i)
+#endif
+            const uint32_t q_lo = umma_desc_lo(q_smem);
             auto issue_s = [&](int j) {
                 const int s = j % NS;
                 mbar_wait(k_full(s), (uint32_t)((j / NS) & 1));
                 tc_fence_after();
-                const uint32_t kbase = k_smem0 + s * k_bytes;
-                const uint32_t d = tmem_s0 + (j & 1) * FA_BKV;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const int kk = ks >> 2, k4 = ks & 3;
-                    const uint64_t ad = umma_desc_sw128(q_smem + kk * (FA_BQ * 128)) + 2 * k4;
-                    const uint64_t bd = umma_desc_sw128(kbase + kk * (FA_BKV * 128)) + 2 * k4;
-                    umma<false>(d, ad, bd, idesc_s, ks != 0);
+                VOG_MPROF(0)
+                const uint32_t b_lo = umma_desc_lo(k_smem0 + s * k_bytes);
+                const uint32_t d = tmem_s0 + (j % 3) * FA_BKV;
+                umma_bf16_lo<false>(d, q_lo, b_lo, idesc_s);
+#pragma unroll
+                for (int ks = 1; ks < 16; ++ks) {          // descriptor offsets are immediates
+                    if (ks < ksteps)
+                        umma_bf16_lo<true>(d, q_lo + (ks >> 2) * (FA_BQ * 128 / 16) + (ks & 3) * 2,
+                                           b_lo + (ks >> 2) * (FA_BKV * 128 / 16) + (ks & 3) * 2, idesc_s);
                 }
                 umma_commit(k_empty(s));
-                umma_commit(s_full(j & 1));
+                umma_commit(s_full(j % 3));
+                VOG_MPROF(1)
             };
             mbar_wait(q_full, 0);
             issue_s(0);
+            if (T > 1) issue_s(1);
             for (int j = 0; j < T; ++j) {
-                if (j + 1 < T) issue_s(j + 1);
+                if (j + 2 < T) issue_s(j + 2);      // buffer (j+2)%3 held S_{j-1}: consumed before P_{j-1} was published
                 const int s = j % NS, pb = j & 1;
                 mbar_wait(v_full(s), (uint32_t)((j / NS) & 1));
                 mbar_wait(p_full(pb), (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
-                const uint32_t vbase = v_smem0 + s * v_bytes;
-                const uint64_t ad0 = umma_desc_sw128(p_smem0 + pb * (FA_BQ * 128));
-                const uint64_t bd0 = umma_desc_sw128(vbase);
+                VOG_MPROF(2)
+                const uint32_t pa_lo = umma_desc_lo(p_smem0 + pb * (FA_BQ * 128));
+                const uint32_t vb_lo = umma_desc_lo(v_smem0 + s * v_bytes);
+                if (j == 0) umma_bf16_lo<false>(tmem_o, pa_lo, vb_lo, idesc_o);
+                else umma_bf16_lo<true>(tmem_o, pa_lo, vb_lo, idesc_o);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    umma<false>(tmem_o, ad0 + 2 * k4, bd0 + 2 * k4, idesc_o, (j | k4) != 0);
+                for (int k4 = 1; k4 < 4; ++k4)
+                    umma_bf16_lo<true>(tmem_o, pa_lo + 2 * k4, vb_lo + 2 * k4, idesc_o);
                 umma_commit(v_empty(s));
                 umma_commit(p_empty(pb));
+                VOG_MPROF(3)
             }
+#ifdef VOG_ATTN_PROFILE
+            if (mprof) for (int i = 0; i < 4; ++i) p.prof[8 + i] = mc[i];
+#endif
         }
         __syncwarp();
+    }
     } else {
-        // ================= softmax / correction / epilogue: one query row per thread =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");     // ... to the two softmax warpgroups
+        // ================= softmax / correction / epilogue =================
+        // two threads per query row: warps 0-3 take key columns [0,32) of every 64-key tile, warps 4-7
+        // columns [32,64); the pair (same TMEM lane quarter) exchanges its row maxima through smem and
+        // a 64-thread named barrier, keeps PARTIAL row sums (combined once at the end) and splits the
+        // accumulator columns between them for the lazy rescale and the epilogue
         const int g = warp & 3;
+        const int half = warp >> 2;
         const int row = 32 * g + lane;                  // row inside the tile == TMEM lane
         const int qi = q_tile * FA_BQ + row;            // query index inside the sequence
         const bool row_ok = qi < N;
         const uint32_t lane_addr = (uint32_t)(32 * g) << 16;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory"); };
         float ai = 0.f;
         if (p.bias_mode == 1 && row_ok)
             ai = (__ldg(p.a + ((size_t)bt * p.nbox + qi % p.nbox) * p.H + h) + __ldg(p.bpe + h)) * p.c;
@@ -215,56 +250,88 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         float m_run = -1e30f, l_run = 0.f;
         const uint32_t prow = (uint32_t)row * 128u;
         const uint32_t sw = (uint32_t)(row & 7);
+        const int ocols = dhp >> 1;                     // accumulator columns owned by this thread's half
 
-        for (int j = 0; j < T; ++j) {
-            const int sb = j & 1, s = j % NS;
-            mbar_wait(s_full(sb), (uint32_t)((j >> 1) & 1));
+#ifdef VOG_ATTN_PROFILE     // build with -DVOG_ATTN_PROFILE for the clock64 phase breakdown (profiles/attn_phases.py)
+        const bool do_prof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0;
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = do_prof ? clock64() : 0;
+#define VOG_PROF(i) if (do_prof) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
+#else
+#define VOG_PROF(i)
+#endif
+        // software pipeline: the score tile S_{j+1} (TMEM) and its bias factors (global, L1/L2) are
+        // requested while tile j is exponentiated / packed, so their latencies are off the critical path
+        uint32_t rn[32];
+        float4 an[8];
+        auto load_bias = [&](int jj) {
+            const float4* ak4 = reinterpret_cast<const float4*>(p.ak_seq + (size_t)bh * p.ak_ld +
+                                                                (size_t)jj * FA_BKV + half * 32);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) an[c4] = __ldg(ak4 + c4);
+        };
+        auto load_scores = [&](int jj) {
+            mbar_wait(s_full(jj % 3), (uint32_t)((jj / 3) & 1));
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            tmem_ld32(tmem_s0 + lane_addr + sb * FA_BKV, r0);
-            tmem_ld32(tmem_s0 + lane_addr + sb * FA_BKV + 32, r1);
+            tmem_ld32(tmem_s0 + lane_addr + (jj % 3) * FA_BKV + half * 32, rn);
+        };
+        if (p.bias_mode == 1) load_bias(0);
+        load_scores(0);
+        for (int j = 0; j < T; ++j) {
+            const int sb = j & 1;
             tmem_wait_ld();
-            float sv[64];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) { sv[c] = __uint_as_float(r0[c]) * p.c; sv[32 + c] = __uint_as_float(r1[c]) * p.c; }
+            VOG_PROF(0)
+            uint32_t (&r0)[32] = rn;
+            float4 (&a4)[8] = an;
+            VOG_PROF(1)
+            float sv[32];
             if (p.bias_mode == 1) {
-                // rank-1 bias factor of the 64 keys: L1-resident broadcast loads (same address in every lane)
-                const float4* ak4 = reinterpret_cast<const float4*>(p.ak_seq + (size_t)bh * p.ak_ld + (size_t)j * FA_BKV);
 #pragma unroll
-                for (int c4 = 0; c4 < 16; ++c4) {
-                    const float4 a4 = __ldg(ak4 + c4);
-                    sv[4 * c4 + 0] += fmaxf(ai - a4.x, 0.f);
-                    sv[4 * c4 + 1] += fmaxf(ai - a4.y, 0.f);
-                    sv[4 * c4 + 2] += fmaxf(ai - a4.z, 0.f);
-                    sv[4 * c4 + 3] += fmaxf(ai - a4.w, 0.f);
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    sv[4 * c4 + 0] = fmaf(__uint_as_float(r0[4 * c4 + 0]), p.c, fmaxf(ai - a4[c4].x, 0.f));
+                    sv[4 * c4 + 1] = fmaf(__uint_as_float(r0[4 * c4 + 1]), p.c, fmaxf(ai - a4[c4].y, 0.f));
+                    sv[4 * c4 + 2] = fmaf(__uint_as_float(r0[4 * c4 + 2]), p.c, fmaxf(ai - a4[c4].z, 0.f));
+                    sv[4 * c4 + 3] = fmaf(__uint_as_float(r0[4 * c4 + 3]), p.c, fmaxf(ai - a4[c4].w, 0.f));
                 }
-            } else if (p.bias_mode == 2 && row_ok) {
+            } else {
 #pragma unroll
-                for (int c = 0; c < 64; ++c) {
-                    const int key = j * FA_BKV + c;
-                    if (key < N) sv[c] += __ldg(dense_row + (size_t)key * p.H) * p.c;
+                for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(r0[c]) * p.c;
+                if (p.bias_mode == 2 && row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int key = j * FA_BKV + half * 32 + c;
+                        if (key < N) sv[c] += __ldg(dense_row + (size_t)key * p.H) * p.c;
+                    }
                 }
             }
             if ((j + 1) * FA_BKV > N) {                // ragged last tile: keys >= N do not exist
 #pragma unroll
-                for (int c = 0; c < 64; ++c)
-                    if (j * FA_BKV + c >= N) sv[c] = -INFINITY;
+                for (int c = 0; c < 32; ++c)
+                    if (j * FA_BKV + half * 32 + c >= N) sv[c] = -INFINITY;
             }
-            float mx = sv[0];
+            float mx0 = fmaxf(sv[0], sv[1]), mx1 = fmaxf(sv[2], sv[3]), mx2 = fmaxf(sv[4], sv[5]), mx3 = fmaxf(sv[6], sv[7]);
 #pragma unroll
-            for (int c = 1; c < 64; ++c) mx = fmaxf(mx, sv[c]);
-            const float m_new = fmaxf(m_run, mx);
+            for (int c = 8; c < 32; c += 4) {
+                mx0 = fmaxf(mx0, sv[c]); mx1 = fmaxf(mx1, sv[c + 1]); mx2 = fmaxf(mx2, sv[c + 2]); mx3 = fmaxf(mx3, sv[c + 3]);
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));     // -inf when this half has no valid key
+            float* xr = xchg + ((j & 1) * FA_BQ + row) * 2;
+            VOG_PROF(2)
+            xr[half] = mx;
+            pair_sync();
+            VOG_PROF(3)
+            const float m_new = fmaxf(m_run, fmaxf(mx, xr[half ^ 1]));
             if (j == 0) {
                 m_run = m_new;
             } else {
                 const bool grow = (m_new - m_run) > FA_RESCALE_T;
                 if (__any_sync(0xffffffffu, grow)) {
-                    // rescale this warp's 32 accumulator rows; PV_{j-1} must have landed first
+                    // rescale this thread's half of the accumulator row; PV_{j-1} must have landed first
                     const float alpha = grow ? fast_exp2(m_run - m_new) : 1.f;
                     if (grow) { m_run = m_new; l_run *= alpha; }
                     mbar_wait(p_empty((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
                     tc_fence_after();
-                    for (int c0 = 0; c0 < dhp; c0 += 32) {
+                    for (int c0 = half * ocols; c0 < (half + 1) * ocols; c0 += 32) {
                         uint32_t o[32];
                         tmem_ld32(tmem_o + lane_addr + c0, o);
                         tmem_wait_ld();
@@ -275,33 +342,56 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                     tmem_wait_st();
                 }
             }
-            float sum = 0.f;
+            if (j + 1 < T) {                           // sv holds tile j now: rn / an are free again
+                if (p.bias_mode == 1) load_bias(j + 1);
+                load_scores(j + 1);
+            }
+            VOG_PROF(7)
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c) { sv[c] = fast_exp2(sv[c] - m_run); sum += sv[c]; }
-            l_run += sum;
+            for (int c = 0; c < 32; c += 4) {
+                sv[c] = fast_exp2(sv[c] - m_run); s0 += sv[c];
+                sv[c + 1] = fast_exp2(sv[c + 1] - m_run); s1 += sv[c + 1];
+                sv[c + 2] = fast_exp2(sv[c + 2] - m_run); s2 += sv[c + 2];
+                sv[c + 3] = fast_exp2(sv[c + 3] - m_run); s3 += sv[c + 3];
+            }
+            l_run += (s0 + s1) + (s2 + s3);
+            VOG_PROF(4)
             // P buffer (j&1) was last read by PV_{j-2}
             if (j >= 2) mbar_wait(p_empty(sb), (uint32_t)(((j - 2) >> 1) & 1));
+            VOG_PROF(5)
             const uint32_t pdst = p_smem0 + sb * (FA_BQ * 128) + prow;
 #pragma unroll
-            for (int c16 = 0; c16 < 8; ++c16) {
-                const uint32_t w0 = pack_bf16(sv[8 * c16 + 0], sv[8 * c16 + 1]);
-                const uint32_t w1 = pack_bf16(sv[8 * c16 + 2], sv[8 * c16 + 3]);
-                const uint32_t w2 = pack_bf16(sv[8 * c16 + 4], sv[8 * c16 + 5]);
-                const uint32_t w3 = pack_bf16(sv[8 * c16 + 6], sv[8 * c16 + 7]);
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t c16 = (uint32_t)(half * 4 + i);
+                const uint32_t w0 = pack_bf16(sv[8 * i + 0], sv[8 * i + 1]);
+                const uint32_t w1 = pack_bf16(sv[8 * i + 2], sv[8 * i + 3]);
+                const uint32_t w2 = pack_bf16(sv[8 * i + 4], sv[8 * i + 5]);
+                const uint32_t w3 = pack_bf16(sv[8 * i + 6], sv[8 * i + 7]);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                             ::"r"(pdst + (((uint32_t)c16 ^ sw) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                             ::"r"(pdst + ((c16 ^ sw) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
                              : "memory");
             }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full(sb));
+            VOG_PROF(6)
         }
-        // ---- epilogue: O / l
+#ifdef VOG_ATTN_PROFILE
+        if (do_prof) { for (int i = 0; i < 8; ++i) p.prof[i] = pc[i]; p.prof[12] = T; }
+#endif
+        // ---- epilogue: O / l  (row sum = the two partial sums of the pair)
+        {
+            float* xr = xchg + ((T & 1) * FA_BQ + row) * 2;
+            xr[half] = l_run;
+            pair_sync();
+            l_run += xr[half ^ 1];
+        }
         mbar_wait(p_empty((T - 1) & 1), (uint32_t)(((T - 1) >> 1) & 1));
         tc_fence_after();
         const float inv_l = 1.f / l_run;
         const int n_pv = (dh + 15) & ~15;
-        for (int c0 = 0; c0 < dhp; c0 += 32) {
+        for (int c0 = half * ocols; c0 < (half + 1) * ocols; c0 += 32) {
             uint32_t o[32];
             float v[32];
             if (c0 < n_pv) {
@@ -331,7 +421,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (warp == 9) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ak_seq[bt*H + h, key] = c * a[(bt*nbox + key % nbox), h] for key < N, 0 up to the 64-padded row end:
@@ -351,6 +441,9 @@ long long tc_attn_workspace_bytes(int Bt, int N, int H)
 {
     return (long long)Bt * H * round_up(N, FA_BKV) * 4;
 }
+
+static long long* g_attn_prof = nullptr;
+void tc_attn_set_prof(long long* buf) { g_attn_prof = buf; }
 
 int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
@@ -376,6 +469,7 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     p.c = inv_scale * 1.4426950408889634f;
     p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.bpe = bpe; p.dense = dense;
     p.out = out; p.ldo = ldo; p.out_kind = out_kind;
+    p.prof = g_attn_prof;
     p.ak_seq = nullptr; p.ak_ld = round_up(N, FA_BKV);
     if (bias_mode == 1) {
         VOG_REQUIRE(workspace && workspace_bytes >= tc_attn_workspace_bytes(Bt, N, H) &&
@@ -387,7 +481,7 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
                                                                          p.nbox, p.ak_ld, p.c);
         if (check_launch("bias_expand")) return -1;
     }
-    const int cols = dhp + 2 * FA_BKV;
+    const int cols = dhp + 3 * FA_BKV;
     p.tmem_cols = cols <= 256 ? 256 : 512;
 
     CUtensorMap tq, tk, tv;
@@ -402,7 +496,7 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     uint32_t bv[3] = {64, (uint32_t)dhp, 1};
     if (make_tmap(&tv, vt, 2, 1, 3, dv, sv, bv)) return -1;
 
-    const int fixed = FA_BQ * dhp * 2 + 2 * FA_BQ * 128 + 384 /*barriers*/ + 1024 /*alignment*/;
+    const int fixed = FA_BQ * dhp * 2 + 2 * FA_BQ * 128 + 384 /*barriers*/ + 2 * FA_BQ * 2 * 4 /*pair exchange*/;
     const int stage_bytes = 2 * FA_BKV * dhp * 2;                  // one K slot + one V^T slot
     int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > FA_MAX_STAGES) stages = FA_MAX_STAGES;

@@ -45,6 +45,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time before failing)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug becomes a trap (kernel error) after ~2 s instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -170,6 +182,22 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
             ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
     }
+}
+// Cheap issue path for unrolled MMA chains: the upper descriptor word (SBO / version / swizzle) is
+// loop invariant, only the 14-bit start-address field in the lower word moves, and the accumulate
+// flag is a compile-time constant - a handful of SASS instructions per tcgen05.mma instead of ~25.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
+constexpr uint32_t UMMA_DESC_HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(UMMA_DESC_HI_SW128)
+        : "memory");
 }
 // arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

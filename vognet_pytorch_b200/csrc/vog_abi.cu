@@ -154,6 +154,9 @@ int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, i
     return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
 
+/* debug: device buffer of 8 int64 that receives per-phase cycle counts of one softmax warp */
+void vog_debug_attn_prof(void* buf) { vog::tc_attn_set_prof((long long*)buf); }
+
 int64_t vog_tc_attn_workspace_bytes(int Bt, int N, int H)
 {
     if (Bt <= 0 || N <= 0 || H <= 0) return 0;
