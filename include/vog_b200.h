@@ -139,6 +139,20 @@ int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int
                        int Bq, int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace,
                        void* stream);
 
+/* Multimodal-transformer input: row ((b*nfrm+f)*nsrl+s)*nppf2+p of out / out_lp =
+ * [vis[b*nfrm*nppf2 + f*nppf2 + p, 0:dv] | lang[b*nsrl + s, 0:dl]] as fp32 and/or low precision.
+ * replaces concate_vis_lang_feats + the per-frame regroup: code/mdl_vog.py:316-344,693-699. */
+int vog_build_xmul(const float* vis, const float* lang, float* out, void* out_lp, int lp_kind, int B,
+                   int nfrm, int nsrl, int nppf2, int dv, int dl, void* stream);
+
+/* Scorer tail: logit = h[row,0:K] . w2 + b2, inverse regroup to logits[B,nsrl,P] (P = nfrm*nppf2 =
+ * ncmp*nfrm0*nppf), scores = sigmoid(logit) * srl_msk[b,s] * cmp_msk[b, vid(p)] (int64 masks).
+ * replaces lin2[2], the un-regroup and the output masks: code/mdl_vog.py:675-677,724-737,
+ * code/mdl_conc_single.py:39-48,118-122,144-154. */
+int vog_lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const int64_t* srl_msk,
+                  const int64_t* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl,
+                  int nppf2, int K, int ncmp, int nppf, int nfrm0, int spat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

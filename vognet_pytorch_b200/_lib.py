@@ -39,6 +39,8 @@ _SIGNATURES = {
     'vog_tc_gemm_workspace_bytes': [c_int, c_int, c_int, c_int, c_int],
     'vog_tc_gemm': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64,
                     P, c_i64, P, c_i64, c_int, c_int, P, c_i64, P],
+    'vog_build_xmul': [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    'vog_lin2_tail': [P, c_int, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'vog_lstm_workspace_bytes': [c_int, c_int],
     'vog_lstm_layer_fwd': [P, c_i64, P, P, c_int, c_int, c_int, P, c_i64, c_int, P, P],
     'vog_tc_attn_workspace_bytes': [c_int, c_int, c_int],

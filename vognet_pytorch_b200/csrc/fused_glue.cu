@@ -1,0 +1,107 @@
+// Glue of the fusion path as two bandwidth-bound kernels instead of ~12 library launches:
+//
+//  build_xmul   the multimodal transformer's input.  Token (b, f, s, p') of per-frame sequence
+//               (b,f) is [vis[b, f*nppf'+p'] | lang[b,s]] (code/mdl_vog.py:316-344 concat,
+//               :693-699 per-frame regroup): written once as fp32 (residual stream) + low-precision
+//               copy (GEMM operand), replacing expand/cat/transpose/contiguous/cast.
+//  lin2_tail    the scorer's last layer and everything after it: logit = h . w2 + b2
+//               (code/mdl_vog.py:675-677), inverse regroup to [B,1,nsrl,P] (:724-737),
+//               mdl_outs_eval = sigmoid(logit) * srl_arg_inds_msk * num_cmp_msk
+//               (code/mdl_conc_single.py:39-48,118-122,144-154).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vog {
+
+__global__ void __launch_bounds__(256)
+build_xmul_kernel(const float* __restrict__ vis, const float* __restrict__ lang, float* __restrict__ out,
+                  void* __restrict__ out_lp, int lp_kind, int B, int nfrm, int nsrl, int nppf2, int dv, int dl)
+{
+    const int d4 = (dv + dl) / 4;
+    const long long total = (long long)B * nfrm * nsrl * nppf2 * d4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % d4) * 4;
+    long long m = idx / d4;
+    const int pp = (int)(m % nppf2); m /= nppf2;
+    const int s = (int)(m % nsrl); m /= nsrl;
+    const int f = (int)(m % nfrm);
+    const int b = (int)(m / nfrm);
+    float4 v;
+    if (c < dv) v = *reinterpret_cast<const float4*>(vis + ((size_t)b * nfrm * nppf2 + (size_t)f * nppf2 + pp) * dv + c);
+    else v = *reinterpret_cast<const float4*>(lang + ((size_t)b * nsrl + s) * dl + (c - dv));
+    const size_t o = (size_t)(idx / d4) * (dv + dl) + c;
+    if (out) *reinterpret_cast<float4*>(out + o) = v;
+    if (out_lp) {
+        if (lp_kind == 1) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_lp) + o) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_lp) + o) =
+                make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        }
+    }
+}
+
+int build_xmul(const float* vis, const float* lang, float* out, void* out_lp, int lp_kind, int B, int nfrm,
+               int nsrl, int nppf2, int dv, int dl, cudaStream_t st)
+{
+    VOG_REQUIRE(dv % 4 == 0 && dl % 4 == 0, "build_xmul: feature dims must be multiples of 4");
+    const long long total = (long long)B * nfrm * nsrl * nppf2 * ((dv + dl) / 4);
+    if (total == 0) return 0;
+    build_xmul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(vis, lang, out, out_lp, lp_kind, B, nfrm,
+                                                                       nsrl, nppf2, dv, dl);
+    return check_launch("build_xmul");
+}
+
+// one warp per token row m = ((b*nfrm + f)*nsrl + s)*nppf2 + p'
+__global__ void __launch_bounds__(256)
+lin2_tail_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ w2, const float* __restrict__ b2,
+                 const long long* __restrict__ srl_msk, const long long* __restrict__ cmp_msk,
+                 float* __restrict__ logits, float* __restrict__ scores, int B, int nfrm, int nsrl, int nppf2,
+                 int K, int ncmp, int nppf, int nfrm0, int spat)
+{
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const long long M = (long long)B * nfrm * nsrl * nppf2;
+    if (row >= M) return;
+    const float* hr = h + (size_t)row * ldh;
+    float acc = 0.f;
+    for (int c = lane * 4; c < K; c += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(hr + c);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + c));
+        acc = fmaf(a.x, w.x, acc); acc = fmaf(a.y, w.y, acc); acc = fmaf(a.z, w.z, acc); acc = fmaf(a.w, w.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane != 0) return;
+    long long m = row;
+    const int pp = (int)(m % nppf2); m /= nppf2;
+    const int s = (int)(m % nsrl); m /= nsrl;
+    const int f = (int)(m % nfrm);
+    const int b = (int)(m / nfrm);
+    const int P = nfrm * nppf2;
+    const int pidx = f * nppf2 + pp;                       // proposal index inside the query
+    // which concatenated video the proposal belongs to (rows are [frame][vid][prop] for spat,
+    // [vid][frame][prop] for temp)
+    const int vid = spat ? (pidx / nppf) % ncmp : pidx / (nfrm0 * nppf);
+    const float logit = acc + b2[0];
+    const size_t o = ((size_t)b * nsrl + s) * P + pidx;
+    logits[o] = logit;
+    const float mk = (float)srl_msk[(size_t)b * nsrl + s] * (float)cmp_msk[(size_t)b * ncmp + vid];
+    scores[o] = (1.f / (1.f + expf(-logit))) * mk;
+}
+
+int lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const long long* srl_msk,
+              const long long* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl, int nppf2,
+              int K, int ncmp, int nppf, int nfrm0, int spat, cudaStream_t st)
+{
+    VOG_REQUIRE(K % 4 == 0 && ldh % 4 == 0, "lin2_tail: K and ldh must be multiples of 4");
+    const long long M = (long long)B * nfrm * nsrl * nppf2;
+    if (M == 0) return 0;
+    lin2_tail_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(h, ldh, w2, b2, srl_msk, cmp_msk, logits, scores, B,
+                                                             nfrm, nsrl, nppf2, K, ncmp, nppf, nfrm0, spat);
+    return check_launch("lin2_tail");
+}
+
+}  // namespace vog

@@ -58,4 +58,11 @@ long long lstm_workspace_bytes(int Bq, int H);
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
                    int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st);
 
+// ---- fused_glue.cu ------------------------------------------------------------------------------
+int build_xmul(const float* vis, const float* lang, float* out, void* out_lp, int lp_kind, int B, int nfrm,
+               int nsrl, int nppf2, int dv, int dl, cudaStream_t st);
+int lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const long long* srl_msk,
+              const long long* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl, int nppf2,
+              int K, int ncmp, int nppf, int nfrm0, int spat, cudaStream_t st);
+
 }  // namespace vog

@@ -189,4 +189,27 @@ int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int
                           (cudaStream_t)stream);
 }
 
+int vog_build_xmul(const float* vis, const float* lang, float* out, void* out_lp, int lp_kind, int B,
+                   int nfrm, int nsrl, int nppf2, int dv, int dl, void* stream)
+{
+    VOG_REQUIRE(B >= 0 && nfrm >= 0 && nsrl >= 0 && nppf2 >= 0, "vog_build_xmul: negative dimension");
+    if ((long long)B * nfrm * nsrl * nppf2 == 0) return 0;
+    VOG_REQUIRE(vis && lang && (out || out_lp), "vog_build_xmul: null operand");
+    VOG_REQUIRE(!out_lp || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_build_xmul: bad lp_kind");
+    return build_xmul(vis, lang, out, out_lp, lp_kind, B, nfrm, nsrl, nppf2, dv, dl, (cudaStream_t)stream);
+}
+
+int vog_lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const int64_t* srl_msk,
+                  const int64_t* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl, int nppf2,
+                  int K, int ncmp, int nppf, int nfrm0, int spat, void* stream)
+{
+    VOG_REQUIRE(B >= 0 && nfrm >= 0 && nsrl >= 0 && nppf2 >= 0, "vog_lin2_tail: negative dimension");
+    if ((long long)B * nfrm * nsrl * nppf2 == 0) return 0;
+    VOG_REQUIRE(h && w2 && b2 && srl_msk && cmp_msk && logits && scores, "vog_lin2_tail: null operand");
+    VOG_REQUIRE(ncmp > 0 && nppf > 0 && nfrm0 > 0 && nfrm * nppf2 == ncmp * nfrm0 * nppf,
+                "vog_lin2_tail: inconsistent frame/proposal grouping");
+    return lin2_tail(h, ldh, w2, b2, (const long long*)srl_msk, (const long long*)cmp_msk, logits, scores, B, nfrm,
+                     nsrl, nppf2, K, ncmp, nppf, nfrm0, spat, (cudaStream_t)stream);
+}
+
 }  // extern "C"

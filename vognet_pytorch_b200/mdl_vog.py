@@ -284,10 +284,10 @@ class VOGNetB200(nn.Module):
         P = x.shape[0] // B
         nppf = self.num_prop_per_frm
         nfrm, nppf2 = self._groups(ncmp)
-        vis = x.view(B, nfrm, 1, nppf2, self.ps_dim).expand(B, nfrm, nsrl, nppf2, self.ps_dim)
-        lng = lang.view(B, 1, nsrl, 1, self.lang_dim).expand(B, nfrm, nsrl, nppf2, self.lang_dim)
-        xm = torch.cat([vis, lng], -1).view(B * nfrm, nsrl * nppf2, self.vl_dim)
-        xm_lp = None
+        # token (b,f,s,p') = [vis[b, f*nppf'+p'] | lang[b,s]] written once, fp32 + low precision
+        xm, xm_lp = ops.build_xmul(x.contiguous(), lang.reshape(B * nsrl, self.lang_dim).contiguous(), B, nfrm,
+                                   nsrl, nppf2, kind)
+        xm = xm.view(B * nfrm, nsrl * nppf2, self.vl_dim)
         if self.USE_MUL_TX and self.cfg.mdl.mul_tx.to_use:
             mtx = self.cfg.mdl.mul_tx
             bias = None
@@ -295,16 +295,14 @@ class VOGNetB200(nn.Module):
                 a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
                                    self.vid_w, self.vid_h, float(nfrm))
                 bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
-            xm, xm_lp = self.mult_txf._exec.run(xm, bias, self.compute, want_lp=True)
-        xm2 = xm.reshape(-1, self.vl_dim)
-        if xm_lp is None:
-            xm_lp = ops.cast_lp(xm2, kind)
+            xm, xm_lp = self.mult_txf._exec.run(xm, bias, self.compute, x_lp=xm_lp, want_lp=True)
         h, _ = ops.tc_gemm(xm_lp.reshape(-1, self.vl_dim), self._lp_weight('lin2', self.lin2[0].weight, kind),
                            bias=self.lin2[0].bias, relu=True)
-        lg = ops.sgemm_nt(h, self.lin2[2].weight, self.lin2[2].bias)
-        logits = lg.view(B, nfrm, nsrl, nppf2).transpose(1, 2).reshape(B, 1, nsrl, P)
-        return self._mask_outputs(logits, {'num_cmp_msk': cmp_msk, 'srl_arg_inds_msk': srl_msk},
-                                  B, nsrl, ncmp, nppf, P)
+        # lin2[2] + inverse regroup + sigmoid * masks in one kernel
+        logits, ev = ops.lin2_tail(h, self.lin2[2].weight, self.lin2[2].bias, srl_msk.reshape(B, nsrl),
+                                   cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, self.num_sampled_frm,
+                                   self.CONC_TYPE == 'spat')
+        return {'mdl_outs': logits, 'mdl_outs_eval': ev}
 
     # -- CUDA-graph execution: the whole forward is ONE graph per (compute, shapes) signature with
     #    two parallel branches - language side (embedding, LSTM, projections) and visual side
@@ -337,10 +335,14 @@ class VOGNetB200(nn.Module):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             cap = torch.cuda.Stream(device=feat.device)
+            from . import _lib
+            n0 = _lib.lib().vog_launch_count()
             with torch.cuda.graph(graph, stream=cap):
                 out = body(side)
-            g = dict(st=st, graph=graph, out=out)
+            # kernels of libvog_b200 captured into the graph = launches per replay
+            g = dict(st=st, graph=graph, out=out, launches=_lib.lib().vog_launch_count() - n0)
             graphs[key] = g
+        self.graph_launches = g['launches']
         for k, buf in g['st'].items():
             buf.copy_(inp[k], non_blocking=True)
         g['graph'].replay()

@@ -292,3 +292,31 @@ def lstm_layer_fwd(gx, whh, lens, T, Bq, kind):
                                         _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _stream()),
                    'vog_lstm_layer_fwd')
     return out
+
+
+def build_xmul(vis, lang, B, nfrm, nsrl, nppf2, kind):
+    """vis [B*nfrm*nppf2, dv] f32, lang [B*nsrl, dl] f32 -> x_mul [B*nfrm*nsrl*nppf2, dv+dl] f32 + lp copy."""
+    _req(vis, torch.float32, 'vis', 2), _req(lang, torch.float32, 'lang', 2)
+    if not (vis.is_contiguous() and lang.is_contiguous()):
+        raise ValueError('build_xmul: contiguous inputs required')
+    dv, dl = vis.shape[1], lang.shape[1]
+    M = B * nfrm * nsrl * nppf2
+    out = torch.empty(M, dv + dl, device=vis.device, dtype=torch.float32)
+    out_lp = torch.empty(M, dv + dl, device=vis.device, dtype=_LP_DTYPE[kind])
+    L = _lib.lib()
+    _lib.check(L.vog_build_xmul(_ptr(vis), _ptr(lang), _ptr(out), _ptr(out_lp), kind, B, nfrm, nsrl, nppf2,
+                                dv, dl, _stream()), 'vog_build_xmul')
+    return out, out_lp
+
+
+def lin2_tail(h, w2, b2, srl_msk, cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, nfrm0, spat):
+    """h [M,K] f32 -> logits, scores [B,1,nsrl,P] (see vog_lin2_tail)."""
+    _req(h, torch.float32, 'h', 2), _req(srl_msk, torch.int64, 'srl_msk'), _req(cmp_msk, torch.int64, 'cmp_msk')
+    P = nfrm * nppf2
+    logits = torch.empty(B, 1, nsrl, P, device=h.device, dtype=torch.float32)
+    scores = torch.empty_like(logits)
+    L = _lib.lib()
+    _lib.check(L.vog_lin2_tail(_ptr(h), _rowmajor2d(h, 'h'), _ptr(w2.contiguous()), _ptr(b2), _ptr(srl_msk.contiguous()),
+                               _ptr(cmp_msk.contiguous()), _ptr(logits), _ptr(scores), B, nfrm, nsrl, nppf2,
+                               h.shape[1], ncmp, nppf, nfrm0, int(spat), _stream()), 'vog_lin2_tail')
+    return logits, scores
