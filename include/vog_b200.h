@@ -135,6 +135,7 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
  * vog_lstm_workspace_bytes() bytes.  replaces nn.LSTM + pack/pad:
  * utils/mdl_srl_utils.py:102-108,135-152. */
 int64_t vog_lstm_workspace_bytes(int Bq, int H);
+void vog_debug_lstm_force_streaming(int on);   /* debug: 1 = weight-streaming kernel even when H == 1024 */
 int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int64_t* lens, int T,
                        int Bq, int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace,
                        void* stream);
@@ -152,6 +153,16 @@ int vog_build_xmul(const float* vis, const float* lang, float* out, void* out_lp
 int vog_lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const int64_t* srl_msk,
                   const int64_t* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl,
                   int nppf2, int K, int ncmp, int nppf, int nfrm0, int spat, void* stream);
+
+/* ---- debug hooks (not part of the data path) ----------------------------------------------------
+ * vog_debug_gemm_trace: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of every
+ * following vog_tc_gemm launch (entry, setup done, first TMA issued, first stage landed, last MMA
+ * committed, accumulator visible to the epilogue, epilogue done, exit); NULL switches it off.
+ * vog_debug_attn_prof: device buffer of 16 int64 for the per-phase cycle counters of one softmax
+ * warp / the MMA issuer of vog_tc_attn_fwd (library built with -DVOG_ATTN_PROFILE). */
+void vog_debug_gemm_trace(void* buf);
+void vog_debug_lstm_trace(void* buf);          /* 8 int64: matvec, reduce, cell+publish, poll, barrier cycles, steps */
+void vog_debug_attn_prof(void* buf);
 
 #ifdef __cplusplus
 }

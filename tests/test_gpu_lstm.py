@@ -40,18 +40,8 @@ def test_language_side_matches_reference(golden, name, mode, tol):
     assert err < tol
 
 
-def test_ragged_lengths_and_zero_rows():
-    """lengths 1..20, including a full-length and a single-token sentence."""
-    from vognet_pytorch_b200 import ops
-    w, batch, mdl = _model('spat_gt5')
-    mdl.set_compute('tf32')
-    T, Bq, H = 20, 4, 1024
-    lens = torch.tensor([1, 20, 7, 13], device=DEV)
-    gx = (torch.rand(T * Bq, 8 * H, generator=torch.Generator().manual_seed(3)) - 0.5).to(DEV)
-    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0]
-    out = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32).view(T, Bq, 2 * H)
-    torch.cuda.synchronize()
-    # reference recurrence in float64 on the host
+def _ref_recurrence(gx, whh, lens, T, Bq, H):
+    """reference recurrence in float64 on the host"""
     gxh, wh = gx.cpu().double().view(T, Bq, 2, 4 * H), whh.cpu().double()
     ref = torch.zeros(T, Bq, 2 * H, dtype=torch.float64)
     for b in range(Bq):
@@ -65,6 +55,54 @@ def test_ragged_lengths_and_zero_rows():
                 c = f * c + i * gg
                 h = o * c.tanh()
                 ref[t, b, d * H:(d + 1) * H] = h
+    return ref
+
+
+@pytest.mark.parametrize('streaming', [0, 1], ids=['resident', 'streaming'])
+@pytest.mark.parametrize('lens_list', [[1, 20, 7, 13], [5], [20, 3], [2, 9, 4], [1, 1, 1, 1], [20] * 8,
+                                       [3, 17, 20, 1, 8, 12]])
+def test_ragged_lengths_and_zero_rows(lens_list, streaming):
+    """lengths 1..20, including full-length and single-token sentences, 1..8 sequences per launch;
+    both recurrence kernels (weight-resident: W_hh in registers + shared memory, tagged h exchange;
+    weight-streaming: W_hh from L2 every step, counter barrier) against a float64 host recurrence."""
+    from vognet_pytorch_b200 import ops, _lib
+    w, batch, mdl = _model('spat_gt5')
+    mdl.set_compute('tf32')
+    T, Bq, H = 20, len(lens_list), 1024
+    lens = torch.tensor(lens_list, device=DEV)
+    gx = (torch.rand(T * Bq, 8 * H, generator=torch.Generator().manual_seed(3)) - 0.5).to(DEV)
+    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0]
+    _lib.lib().vog_debug_lstm_force_streaming(streaming)
+    try:
+        outs = [ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32).view(T, Bq, 2 * H) for _ in range(3)]
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().vog_debug_lstm_force_streaming(0)
+    out = outs[0]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])      # deterministic across launches
+    ref = _ref_recurrence(gx, whh, lens, T, Bq, H)
     assert (out.cpu().double() - ref).abs().max() < 1e-3         # tf32 rounding of the stored h
     for b in range(Bq):
         assert out[int(lens[b]):, b].abs().max() == 0 if int(lens[b]) < T else True
+
+
+def test_resident_kernel_in_cuda_graph_replays():
+    """the tagged exchange buffer is re-zeroed by a memset node inside the captured work, so graph
+    replays (same kernel parameters every time) never see stale tags"""
+    from vognet_pytorch_b200 import ops
+    w, batch, mdl = _model('spat_gt5')
+    T, Bq, H = 20, 4, 1024
+    lens = torch.tensor([11, 20, 7, 13], device=DEV)
+    gx = (torch.rand(T * Bq, 8 * H, generator=torch.Generator().manual_seed(5)) - 0.5).to(DEV)
+    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0]
+    eager = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32).clone()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.graph(g, stream=s):
+        out = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32)
+    for _ in range(4):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager)

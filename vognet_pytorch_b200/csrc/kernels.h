@@ -43,6 +43,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
             int BN, const TcEpilogue& epi, void* workspace, long long workspace_bytes, cudaStream_t st);
 long long tc_gemm_workspace_bytes(int M, int N, int K, int tf32, int BN);
 int num_sms();
+void tc_gemm_set_trace(long long* buf);  // debug: 8 clock64 stamps of CTA 0
 // ---- tc_attn.cu : fused relative-position-bias attention (tcgen05) ---------------------------
 int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
@@ -55,6 +56,8 @@ int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long
 
 // ---- lstm_rec.cu : persistent bidirectional LSTM recurrence -----------------------------------
 long long lstm_workspace_bytes(int Bq, int H);
+void lstm_set_trace(long long* buf);     // debug: phase cycle counters of CTA 0
+void lstm_force_streaming(int on);       // debug: disable the weight-resident kernel
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
                    int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st);
 

@@ -176,9 +176,259 @@ lstm_rec_kernel(const LstmParams p)
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Weight-resident variant (H == 1024, >= 128 SMs): the W_hh rows of a CTA's hidden units never leave
+// the SM.  A CTA owns U = ceil(H / ctas_per_dir) units of one direction; warp w owns unit w (its 4
+// gate rows), lane l the columns {128 i + 4 l .. +3 : i < 8} of those rows - 128 weights per thread,
+// half of them in REGISTERS (i < 4), half in shared memory (i >= 4, float4-interleaved by thread so
+// every LDS.128 is conflict free).  2 x 4H x H fp32 = 32 MiB of recurrent weights are thus spread
+// over the register files and shared memories of 148 SMs and are read from L2/HBM exactly once per
+// launch instead of once per timestep.
+//
+// Per step a warp computes its 4 x BQ partial dot products, reduce-scatters them over the 32 lanes
+// (4*BQ - 1 + log-tail shuffles instead of 5 * 4 * BQ), adds the input projection and runs the cell
+// update for its unit in-warp.  h_t is exchanged between the CTAs of a direction WITHOUT a grid
+// barrier: every value travels as one 64-bit word {fp32 bits, step tag} written with a relaxed
+// gpu-scope store into a double-buffered global array; consumers poll the words they need until
+// the tag matches (one L2 round trip after the producer's store instead of atomic + flag + reload).
+// The array is zeroed by a memset node in front of the launch, so tags never alias across replays.
+// -------------------------------------------------------------------------------------------------
+constexpr int LR_H = 1024;
+constexpr int LR_NI = LR_H / 128;          // float4 per gate row per lane
+constexpr int LR_NREG = 3;                 // of which register resident
+constexpr int LR_MAXU = 14;                // warps (= hidden units) per CTA
+constexpr int LR_THREADS = 32 * LR_MAXU;   // 448 threads
+constexpr int LR_PB = 5;                   // 16-byte exchange loads in flight per thread
+
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_relaxed_u64x2(const unsigned long long* p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct LstmResParams {
+    const float* gx; long long ldg;
+    const float* whh;
+    const long long* lens;
+    unsigned long long* hx;               // [2 parity, 2 dir, Bq, H] {value, tag}
+    void* out_lp; long long ld_out; int lp_kind;
+    int T, Bq, U, ctas_per_dir;
+    long long* trace;                     // debug: [8] accumulated clock64 phases of CTA 0 / thread 0
+};
+
+// v[0..V) per lane -> lane holds the warp-wide sum of v[idx], idx = the top log2(V) bits of (lane >> (5 - log2 V))
+template <int V>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[V], int lane) {
+    static_assert(V == 4 || V == 8 || V == 16 || V == 32, "V must be 4..32");
+    int width = 16;
+#pragma unroll
+    for (int n = V / 2; n >= 1; n >>= 1) {
+        const bool up = (lane & width) != 0;
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+            const float keep = up ? v[k + n] : v[k];
+            const float send = up ? v[k] : v[k + n];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+        }
+        width >>= 1;
+    }
+    float r = v[0];
+    for (; width >= 1; width >>= 1) r += __shfl_xor_sync(0xffffffffu, r, width);
+    return r;
+}
+
+template <int BQ>
+__global__ void __launch_bounds__(LR_THREADS, 1)
+lstm_rec_resident_kernel(const LstmResParams p)
+{
+    constexpr int H = LR_H;
+    constexpr int V = 4 * BQ;
+    extern __shared__ __align__(16) float sm[];
+    const int NT = blockDim.x;                               // 32 * U
+    float4* w_s = reinterpret_cast<float4*>(sm);             // [4 gates][NI - NREG][NT]
+    float* h_s = sm + 4 * (LR_NI - LR_NREG) * NT * 4;        // [2 parity][BQ][H]
+    float* gate_s = h_s + 2 * BQ * H;                        // [U][V]
+    __shared__ int len_s[LS_MAXB];
+    __shared__ int tmax_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = blockIdx.x / p.ctas_per_dir, c = blockIdx.x % p.ctas_per_dir;
+    const int Bq = p.Bq;
+    const int u = c * p.U + warp;                            // hidden unit of this warp
+    const bool unit_ok = u < H;
+
+    if (tid < LS_MAXB) len_s[tid] = tid < Bq ? (int)min((long long)p.T, max(0LL, p.lens[tid])) : 0;
+    for (int i = tid; i < 2 * BQ * H; i += NT) h_s[i] = 0.f;
+    // ---- one-time weight load: row (gate, u), columns 128 i + 4 lane
+    float4 wr[4][LR_NREG];
+    {
+        const float* wbase = p.whh + (size_t)d * 4 * H * H;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4* row = reinterpret_cast<const float4*>(wbase + ((size_t)g * H + (unit_ok ? u : 0)) * H);
+#pragma unroll
+            for (int i = 0; i < LR_NI; ++i) {
+                float4 w4 = unit_ok ? __ldg(row + 32 * i + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < LR_NREG) wr[g][i] = w4;
+                else w_s[(g * (LR_NI - LR_NREG) + (i - LR_NREG)) * NT + tid] = w4;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int b = 0; b < Bq; ++b) m = max(m, len_s[b]);
+        tmax_s = m;
+    }
+    __syncthreads();
+    const int Tmax = tmax_s;
+
+    // after the reduce-scatter lane l holds output idx = l >> (5 - log2 V), laid out idx = b * 4 + gate
+    constexpr int LOGV = V == 4 ? 2 : V == 8 ? 3 : V == 16 ? 4 : 5;
+    const int my_idx = lane >> (5 - LOGV);
+    const int my_b = my_idx >> 2, my_g = my_idx & 3;
+    const bool gx_lane = unit_ok && my_b < Bq && (lane & ((1 << (5 - LOGV)) - 1)) == 0;
+    const int npairs = Bq * H / 2;                           // exchange words travel in pairs
+    const int NP = (npairs + NT - 1) / NT;                   // pairs per thread
+    float c_reg = 0.f, h_reg = 0.f;                          // cell / hidden state of (unit u, sequence lane)
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tc[5] = {0, 0, 0, 0, 0};
+    long long tprev = tr ? clock64() : 0;
+#define LR_TRACE(i) if (tr) { const long long tn = clock64(); tc[i] += tn - tprev; tprev = tn; }
+
+    for (int step = 0; step < Tmax; ++step) {
+        const int t = d == 0 ? step : Tmax - 1 - step;
+        const float* hcur = h_s + (step & 1) * BQ * H;
+        float gxv = 0.f;
+        if (gx_lane) gxv = __ldg(p.gx + ((size_t)t * Bq + my_b) * p.ldg + (size_t)d * 4 * H + (size_t)my_g * H + u);
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        if (step > 0) {                                      // h_{-1} = 0
+#pragma unroll
+            for (int i = 0; i < LR_NI; ++i) {
+                float4 w4[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    w4[g] = i < LR_NREG ? wr[g][i < LR_NREG ? i : 0]
+                                        : w_s[(g * (LR_NI - LR_NREG) + (i - LR_NREG)) * NT + tid];
+#pragma unroll
+                for (int b = 0; b < BQ; ++b) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hcur + b * H + 128 * i + 4 * lane);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float a = acc[b * 4 + g];
+                        a = fmaf(w4[g].x, hv.x, a);
+                        a = fmaf(w4[g].y, hv.y, a);
+                        a = fmaf(w4[g].z, hv.z, a);
+                        a = fmaf(w4[g].w, hv.w, a);
+                        acc[b * 4 + g] = a;
+                    }
+                }
+            }
+        }
+        LR_TRACE(0)
+        const float tot = warp_reduce_scatter<V>(acc, lane);
+        if (gx_lane) gate_s[warp * V + my_idx] = tot + gxv;
+        __syncwarp();
+        LR_TRACE(1)
+        // ---- cell update: lane b of the warp owns (unit u, sequence b)
+        if (lane < Bq && unit_ok) {
+            const bool live = t < len_s[lane];
+            float hval = 0.f;
+            if (live) {
+                const float* gs = gate_s + warp * V + lane * 4;
+                const float gi = sigmoidf_(gs[0]);
+                const float gf = sigmoidf_(gs[1]);
+                const float gg = tanhf(gs[2]);
+                const float go = sigmoidf_(gs[3]);
+                c_reg = gf * c_reg + gi * gg;
+                hval = go * tanhf(c_reg);
+                h_reg = hval;
+            }
+            if (step + 1 < Tmax)
+                st_relaxed_u64(p.hx + (((size_t)(step & 1) * 2 + d) * Bq + lane) * H + u,
+                               ((unsigned long long)(unsigned)(step + 1) << 32) | __float_as_uint(h_reg));
+            store_lp(p.out_lp, ((long long)t * Bq + lane) * p.ld_out + (long long)d * H + u, hval, p.lp_kind);
+        }
+        __syncwarp();
+        LR_TRACE(2)
+        // ---- collect h_t of the whole direction: poll the tagged words
+        if (step + 1 < Tmax) {
+            const unsigned long long* src = p.hx + ((size_t)(step & 1) * 2 + d) * Bq * H;
+            float* hnext = h_s + ((step + 1) & 1) * BQ * H;
+            const unsigned want = (unsigned)(step + 1);
+            long long t0 = 0;
+            // pairs of adjacent words (16-byte loads; each 64-bit half is single-copy atomic), up to
+            // LR_PB pairs in flight per thread: normally the whole share of a thread is one batch
+            for (int q0 = 0; q0 < NP; q0 += LR_PB) {
+                ulonglong2 w[LR_PB];
+                bool pending = true;
+                while (pending) {
+                    pending = false;
+#pragma unroll
+                    for (int k = 0; k < LR_PB; ++k) {
+                        const int q = (q0 + k) * NT + tid;
+                        if (q0 + k < NP && q < npairs) w[k] = ld_relaxed_u64x2(src + 2 * (size_t)q);
+                        else w[k] = make_ulonglong2((unsigned long long)want << 32, (unsigned long long)want << 32);
+                    }
+#pragma unroll
+                    for (int k = 0; k < LR_PB; ++k)
+                        pending |= ((unsigned)(w[k].x >> 32) != want) | ((unsigned)(w[k].y >> 32) != want);
+                    if (pending) {
+                        if (t0 == 0) t0 = clock64();
+                        else if (clock64() - t0 > 4000000000LL) {
+                            printf("vog: lstm h-exchange timeout block %d step %d\n", (int)blockIdx.x, step);
+                            __trap();
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < LR_PB; ++k) {
+                    const int q = (q0 + k) * NT + tid;
+                    if (q0 + k < NP && q < npairs)
+                        *reinterpret_cast<float2*>(hnext + 2 * q) =
+                            make_float2(__uint_as_float((unsigned)w[k].x), __uint_as_float((unsigned)w[k].y));
+                }
+            }
+            LR_TRACE(3)
+            __syncthreads();
+            LR_TRACE(4)
+        }
+    }
+    if (tr) { for (int i = 0; i < 5; ++i) p.trace[i] = tc[i]; p.trace[5] = Tmax; }
+    // rows past the longest sentence: zeros (pad_packed_sequence padding_value=0)
+    if (lane < Bq && unit_ok)
+        for (int t = Tmax; t < p.T; ++t)
+            store_lp(p.out_lp, ((long long)t * Bq + lane) * p.ld_out + (long long)d * H + u, 0.f, p.lp_kind);
+}
+
+template <int BQ>
+static int launch_resident(const LstmResParams& p, int ctas, int threads, cudaStream_t st)
+{
+    const size_t smem = (size_t)4 * (LR_NI - LR_NREG) * threads * 16 + (size_t)2 * BQ * LR_H * 4 + (size_t)LR_MAXU * 4 * BQ * 4;
+    VOG_CUDA(cudaFuncSetAttribute(lstm_rec_resident_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_rec_resident_kernel<BQ><<<ctas, threads, smem, st>>>(p);
+    return check_launch("lstm_rec_resident");
+}
+
+static int g_lstm_force_streaming = 0;
+static long long* g_lstm_trace = nullptr;
+void lstm_set_trace(long long* buf) { g_lstm_trace = buf; }
+void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
+
 long long lstm_workspace_bytes(int Bq, int H)
 {
-    return (long long)2 * 2 * Bq * H * 4 + 64;
+    return (long long)2 * 2 * Bq * H * 8 + 64;        // tagged 64-bit exchange words (resident kernel)
 }
 
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
@@ -193,6 +443,24 @@ int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long 
                 "lstm_layer_fwd: whh and workspace must be 16-byte aligned");
     int sms = num_sms();
     if (sms < 2) sms = 2;
+    if (H == LR_H && cdiv(H, sms / 2) <= LR_MAXU && !g_lstm_force_streaming) {
+        // weight-resident kernel: one warp per hidden unit, <= 16 units per CTA
+        const int per_dir_r = sms / 2;
+        const int U = cdiv(H, per_dir_r);
+        const int per_dir_u = cdiv(H, U);
+        LstmResParams rp;
+        rp.gx = gx; rp.ldg = ldg; rp.whh = whh; rp.lens = lens;
+        rp.hx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 64);
+        rp.out_lp = out_lp; rp.ld_out = ld_out; rp.lp_kind = lp_kind;
+        rp.T = T; rp.Bq = Bq; rp.U = U; rp.ctas_per_dir = per_dir_u;
+        rp.trace = g_lstm_trace;
+        VOG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)lstm_workspace_bytes(Bq, H), st));
+        const int ctas = 2 * per_dir_u, threads = 32 * U;
+        if (Bq == 1) return launch_resident<1>(rp, ctas, threads, st);
+        if (Bq == 2) return launch_resident<2>(rp, ctas, threads, st);
+        if (Bq <= 4) return launch_resident<4>(rp, ctas, threads, st);
+        return launch_resident<8>(rp, ctas, threads, st);
+    }
     int per_dir = sms / 2;
     int U = cdiv(H, per_dir);
     if (U > LS_MAXU) { U = LS_MAXU; }

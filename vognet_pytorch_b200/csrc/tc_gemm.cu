@@ -42,8 +42,11 @@ struct GemmParams {
     float* partial;               // [splits, M, N] when splits > 1
     uint32_t idesc, tmem_cols;
     int stages;
+    long long* trace;             // debug: [8] clock64 stamps of CTA 0 (vog_debug_gemm_trace)
     TcEpilogue e;
 };
+
+#define GM_TRACE(i) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[i] = clock64(); } while (0)
 
 // ---- epilogue on a coalesced float4 (4 consecutive columns of one row) ---------------------------
 __device__ __forceinline__ void epi_apply_store(const TcEpilogue& e, int M, int N, int m, int n, float4 v,
@@ -110,8 +113,176 @@ __device__ __forceinline__ void epi_apply_store(const TcEpilogue& e, int M, int 
     }
 }
 
+// ---- epilogues: one per kernel instantiation so that each kernel carries only the code it runs ----
+// All three read the accumulator 32 columns at a time (thread = TMEM lane = output row); the next
+// chunk's tcgen05.ld is issued before the current chunk is stored so TMEM latency is hidden.
+enum { EPI_FAST = 0, EPI_QKV = 1, EPI_GENERIC = 2 };
+
+// transpose a 32x32 fp32 chunk through the warp's swizzled smem patch: row = lane on the way in ...
+__device__ __forceinline__ void patch_store(float* patch, int lane, const uint32_t (&r)[32]) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<float4*>(patch + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                        __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+}
+// ... 4 rows x 8 float4 per instruction on the way out (128 B coalesced row segments)
+__device__ __forceinline__ float4 patch_load(const float* patch, int row, int c4) {
+    return *reinterpret_cast<const float4*>(patch + row * 32 + ((c4 ^ (row & 7)) << 2));
+}
+
+// EPI_FAST (host-verified: N % 32 == 0, rep == 1, every row segment 16-byte aligned): unguarded
+// float4 traffic, bias / residual of the next chunk prefetched while the current one is stored - the
+// first chunk even before the accumulator is ready - so their latency hides behind the MMAs
+__device__ __forceinline__ void epi_fast(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
+                                         uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane,
+                                         bool trace)
+{
+    const int r_in = lane >> 3, c4 = lane & 7;
+    const int m0 = m_blk * GM_BM + 32 * g;
+    const int rows = p.M - m0;                                  // rows of this warp's slab that exist
+    const size_t col = (size_t)n_blk * p.BN + c4 * 4;
+    const float* resp = pe.residual ? pe.residual + (size_t)(m0 + r_in) * pe.ldr + col : nullptr;
+    const float* biasp = pe.bias ? pe.bias + col : nullptr;
+    float* o32 = pe.out_f32 ? pe.out_f32 + (size_t)(m0 + r_in) * pe.ldc + col : nullptr;
+    __nv_bfloat16* obf = (pe.out_lp && pe.lp_kind == 1)
+        ? reinterpret_cast<__nv_bfloat16*>(pe.out_lp) + (size_t)(m0 + r_in) * pe.ldlp + col : nullptr;
+    float* otf = (pe.out_lp && pe.lp_kind != 1)
+        ? reinterpret_cast<float*>(pe.out_lp) + (size_t)(m0 + r_in) * pe.ldlp + col : nullptr;
+    const size_t res_step = 4 * (size_t)pe.ldr, o32_step = 4 * (size_t)pe.ldc, lp_step = 4 * (size_t)pe.ldlp;
+    float4 res[8];
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto prefetch = [&](int c0) {
+        if (resp) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i * 4 + r_in < rows) res[i] = __ldg(reinterpret_cast<const float4*>(resp + i * res_step + c0));
+        }
+        if (biasp) b4 = __ldg(reinterpret_cast<const float4*>(biasp + c0));
+    };
+    prefetch(0);
+    mbar_wait(tfull, parity);
+    tc_fence_after();
+    if (trace) GM_TRACE(5);
+    uint32_t r[32];
+    tmem_ld32(t_acc, r);
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        tmem_wait_ld();
+        patch_store(patch, lane, r);
+        if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);       // in flight while this chunk is stored
+        __syncwarp();
+        float4 cur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = res[i];
+        const float4 bc = b4;
+        if (c0 + 32 < p.BN) prefetch(c0 + 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + r_in;
+            float4 v = patch_load(patch, row, c4);
+            if (row < rows) {
+                v.x += bc.x; v.y += bc.y; v.z += bc.z; v.w += bc.w;
+                if (pe.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                v.x += cur[i].x; v.y += cur[i].y; v.z += cur[i].z; v.w += cur[i].w;
+                if (o32) *reinterpret_cast<float4*>(o32 + i * o32_step + c0) = v;
+                if (obf) *reinterpret_cast<uint2*>(obf + i * lp_step + c0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                if (otf) *reinterpret_cast<float4*>(otf + i * lp_step + c0) =
+                    make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// EPI_QKV: column block n_blk = which*H + h (BN == dhp).  Q / K go through the transpose patch and
+// are written as [Bt,H,N,dhp] bf16 rows (64 B row segments); V is written TRANSPOSED ([Bt,H,dhp,Npad])
+// straight from registers: lanes are consecutive tokens, so every store instruction is one 64 B run
+__device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
+                                        uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane)
+{
+    const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
+    const int m0 = m_blk * GM_BM + 32 * g;
+    uint32_t r[32];
+    if (which == 2) {
+        const int m = m0 + lane;
+        const bool ok = m < p.M;
+        const int bt = ok ? m / pe.seq_n : 0, ii = ok ? m % pe.seq_n : 0;
+        __nv_bfloat16* dst = pe.vt + (((size_t)bt * pe.n_heads + h) * pe.dhp) * pe.npad + ii;
+        mbar_wait(tfull, parity);
+        tc_fence_after();
+        tmem_ld32(t_acc, r);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            tmem_wait_ld();
+            uint32_t cur[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cur[j] = r[j];
+            if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    dst[(size_t)(c0 + j) * pe.npad] = __float2bfloat16_rn(__uint_as_float(cur[j]));
+            }
+        }
+        return;
+    }
+    const int r_in = lane >> 3, c4 = lane & 7;
+    __nv_bfloat16* base = which == 0 ? pe.q : pe.k;
+    __nv_bfloat16* dst[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + i * 4 + r_in;
+        const int bt = m / pe.seq_n, ii = m % pe.seq_n;
+        dst[i] = m < p.M ? base + (((size_t)bt * pe.n_heads + h) * pe.seq_n + ii) * pe.dhp + c4 * 4 : nullptr;
+    }
+    mbar_wait(tfull, parity);
+    tc_fence_after();
+    tmem_ld32(t_acc, r);
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        tmem_wait_ld();
+        patch_store(patch, lane, r);
+        if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = patch_load(patch, i * 4 + r_in, c4);
+            if (dst[i]) *reinterpret_cast<uint2*>(dst[i] + c0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        }
+        __syncwarp();
+    }
+}
+
+// EPI_GENERIC: any N / alignment / row replication (guarded element-wise fallbacks inside)
+__device__ __forceinline__ void epi_generic(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
+                                            uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane)
+{
+    const int r_in = lane >> 3, c4 = lane & 7;
+    const int m0 = m_blk * GM_BM + 32 * g;
+    mbar_wait(tfull, parity);
+    tc_fence_after();
+    uint32_t r[32];
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        tmem_ld32(t_acc + c0, r);
+        tmem_wait_ld();
+        patch_store(patch, lane, r);
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + r_in;
+            const float4 v = patch_load(patch, row, c4);
+            epi_apply_store(pe, p.M, p.N, m0 + row, n_blk * p.BN + c0 + c4 * 4, v, true);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- kernel -----------------------------------------------------------------------------------
-template <bool kTF32>
+template <bool kTF32, int kEpi>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmParams p)
@@ -134,6 +305,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     auto b_smem = [&](int s) { return smem_base + s * stage_bytes + GM_A_BYTES; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) GM_TRACE(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
@@ -146,6 +318,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 0) GM_TRACE(1);
     const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
     // item -> (m_blk, n_blk, split): splits innermost so that the CTAs of one wave share A/W tiles in L2
     auto decode = [&](int item, int& m_blk, int& n_blk, int& kb0, int& kb1) {
@@ -169,6 +342,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     mbar_arrive_expect_tx(full_bar(s), stage_bytes);
                     tma_load_2d(a_smem(s), &tma_a, full_bar(s), kb * p.bk_elems, m_blk * GM_BM);
                     tma_load_2d(b_smem(s), &tma_b, full_bar(s), kb * p.bk_elems, n_blk * p.BN);
+                    if (item == (int)blockIdx.x && kb == kb0) GM_TRACE(2);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -186,6 +360,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
+                    if (item == (int)blockIdx.x && kb == kb0) GM_TRACE(3);
                     const uint64_t ad = umma_desc_sw128(a_smem(s));
                     const uint64_t bd = umma_desc_sw128(b_smem(s));
 #pragma unroll
@@ -195,6 +370,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(tfull_bar(acc));
+                if (item == (int)blockIdx.x) GM_TRACE(4);
                 acc ^= 1;
                 if (acc == 0) acc_ph ^= 1;
             }
@@ -204,111 +380,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int g = warp & 3;                    // TMEM lane quarter this warp may access
         float* patch = reinterpret_cast<float*>(smem_gen + epi_off) + g * 1024;     // [32 rows][8 float4]
         int acc = 0; uint32_t acc_ph = 0;
-        TcEpilogue pe = p.e;                       // split-K: raw partials, no epilogue math
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             int m_blk, n_blk, kb0, kb1;
             const int split = decode(item, m_blk, n_blk, kb0, kb1);
-            if (p.splits > 1) {
-                pe = TcEpilogue();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(32 * g) << 16) + acc * p.BN;
+            const bool trace = item == (int)blockIdx.x && threadIdx.x == 64;
+            if (p.splits > 1) {                    // split-K: raw partials, no epilogue math
+                TcEpilogue pe;
                 pe.out_f32 = p.partial + (size_t)split * p.M * p.N;
                 pe.ldc = p.N;
-            }
-            const int m_base = m_blk * GM_BM + 32 * g;
-            const int c4 = lane & 7;
-            // fast path (host-verified: N % 32 == 0, 16-byte aligned rows, rep == 1): unguarded float4
-            // traffic; the residual tile is prefetched one 32-column chunk ahead - the first chunk
-            // even before the accumulator is ready - so its latency hides behind the MMAs
-            const bool fast = p.fast && pe.mode == 0;
-            float4 res[8];
-            auto load_res = [&](int c0n) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int m = m_base + i * 4 + (lane >> 3);
-                    res[i] = (m < p.M) ? __ldg(reinterpret_cast<const float4*>(
-                                             pe.residual + (size_t)m * pe.ldr + n_blk * p.BN + c0n + c4 * 4))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            const bool pre_res = fast && pe.residual != nullptr;
-            if (pre_res) load_res(0);
-            mbar_wait(tfull_bar(acc), acc_ph);
-            tc_fence_after();
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * g) << 16) + acc * p.BN + c0, r);
-                const int n0 = n_blk * p.BN + c0;
-                float4 cur[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cur[i] = res[i];
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (fast && pe.bias) b4 = __ldg(reinterpret_cast<const float4*>(pe.bias + n0 + c4 * 4));
-                tmem_wait_ld();
-                if (pe.mode == 1 && n_blk / pe.n_heads == 2) {
-                    // V^T scatter straight from registers: lanes are consecutive tokens -> coalesced
-                    const int m = m_base + lane;
-                    if (m < p.M) {
-                        const int h = n_blk % pe.n_heads, bt = m / pe.seq_n, i = m % pe.seq_n;
-                        __nv_bfloat16* dst = pe.vt + (((size_t)bt * pe.n_heads + h) * pe.dhp + c0) * pe.npad + i;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            dst[(size_t)j * pe.npad] = __float2bfloat16_rn(__uint_as_float(r[j]));
-                    }
-                    continue;
-                }
-                // transpose the 32x32 chunk through smem: row = lane on the way in ...
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                    *reinterpret_cast<float4*>(patch + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
-                        make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
-                                    __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
-                __syncwarp();
-                if (pre_res && c0 + 32 < p.BN) load_res(c0 + 32);
-                // ... 4 rows x 8 float4 per instruction on the way out (128 B coalesced row segments)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = i * 4 + (lane >> 3);
-                    float4 v = *reinterpret_cast<const float4*>(patch + row * 32 + ((c4 ^ (row & 7)) << 2));
-                    const int m = m_base + row, n = n0 + c4 * 4;
-                    if (fast) {
-                        if (m < p.M) {
-                            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                            if (pe.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                            if (pre_res) { v.x += cur[i].x; v.y += cur[i].y; v.z += cur[i].z; v.w += cur[i].w; }
-                            if (pe.out_f32) *reinterpret_cast<float4*>(pe.out_f32 + (size_t)m * pe.ldc + n) = v;
-                            if (pe.out_lp) {
-                                if (pe.lp_kind == 1)
-                                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(pe.out_lp) + (size_t)m * pe.ldlp + n) =
-                                        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                                else
-                                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(pe.out_lp) + (size_t)m * pe.ldlp + n) =
-                                        make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-                            }
-                        }
-                    } else if (pe.mode == 1) {
-                        if (m < p.M) {
-                            const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
-                            const int bt = m / pe.seq_n, ii = m % pe.seq_n;
-                            __nv_bfloat16* dst = (which == 0 ? pe.q : pe.k) +
-                                (((size_t)bt * pe.n_heads + h) * pe.seq_n + ii) * pe.dhp + c0 + c4 * 4;
-                            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                        }
-                    } else {
-                        epi_apply_store(pe, p.M, p.N, m, n, v, true);
-                    }
-                }
-                __syncwarp();
+                if constexpr (kEpi == EPI_FAST) epi_fast(p, pe, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane, trace);
+                else epi_generic(p, pe, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
+            } else {
+                if constexpr (kEpi == EPI_FAST) epi_fast(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane, trace);
+                else if constexpr (kEpi == EPI_QKV) epi_qkv(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
+                else epi_generic(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (trace) GM_TRACE(6);
             acc ^= 1;
             if (acc == 0) acc_ph ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) GM_TRACE(7);
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
+
+static long long* g_gemm_trace = nullptr;
+void tc_gemm_set_trace(long long* buf) { g_gemm_trace = buf; }
 
 // sum of split-K partials + epilogue, one float4 per thread
 __global__ void __launch_bounds__(256)
@@ -450,11 +553,12 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
     VOG_REQUIRE(stages >= 2, "tc_gemm: tile does not fit shared memory");
     p.stages = stages;
+    p.trace = g_gemm_trace;
     p.e = epi;
     {   // unguarded float4 epilogue when every row segment the kernel touches is 16-byte aligned
         auto al = [](const void* q, int a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
-        bool ok = (N % 32 == 0) && epi.rep == 1 && epi.mode == 0;
-        if (p.splits > 1) ok = (N % 32 == 0) && epi.mode == 0 && al(workspace, 16);
+        bool ok = (N % BN == 0) && epi.rep == 1 && epi.mode == 0;
+        if (p.splits > 1) ok = (N % BN == 0) && epi.mode == 0 && al(workspace, 16);
         else {
             ok = ok && (!epi.bias || al(epi.bias, 16));
             ok = ok && (!epi.residual || (al(epi.residual, 16) && epi.ldr % 4 == 0));
@@ -467,13 +571,22 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + GM_EPI_BYTES;
     const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
     const int grid = nitems < num_sms() ? nitems : num_sms();
+    const int epi_kind = epi.mode == 1 ? EPI_QKV : (p.fast ? EPI_FAST : EPI_GENERIC);
+#define VOG_GEMM_LAUNCH(TF, EP)                                                                                   \
+    do {                                                                                                          \
+        VOG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TF, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        tc_gemm_kernel<TF, EP><<<grid, GM_THREADS, smem, st>>>(ta, tb, p);                                         \
+    } while (0)
     if (tf32) {
-        VOG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gemm_kernel<true><<<grid, GM_THREADS, smem, st>>>(ta, tb, p);
+        if (epi_kind == EPI_FAST) VOG_GEMM_LAUNCH(true, EPI_FAST);
+        else if (epi_kind == EPI_QKV) VOG_GEMM_LAUNCH(true, EPI_QKV);
+        else VOG_GEMM_LAUNCH(true, EPI_GENERIC);
     } else {
-        VOG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gemm_kernel<false><<<grid, GM_THREADS, smem, st>>>(ta, tb, p);
+        if (epi_kind == EPI_FAST) VOG_GEMM_LAUNCH(false, EPI_FAST);
+        else if (epi_kind == EPI_QKV) VOG_GEMM_LAUNCH(false, EPI_QKV);
+        else VOG_GEMM_LAUNCH(false, EPI_GENERIC);
     }
+#undef VOG_GEMM_LAUNCH
     if (check_launch("tc_gemm")) return -1;
     if (p.splits > 1) {
         const long long n = (long long)M * ((N + 3) / 4);

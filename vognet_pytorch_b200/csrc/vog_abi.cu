@@ -154,6 +154,9 @@ int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, i
     return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
 
+/* debug: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of the next tc_gemm launches */
+void vog_debug_gemm_trace(void* buf) { vog::tc_gemm_set_trace((long long*)buf); }
+
 /* debug: device buffer of 8 int64 that receives per-phase cycle counts of one softmax warp */
 void vog_debug_attn_prof(void* buf) { vog::tc_attn_set_prof((long long*)buf); }
 
@@ -178,6 +181,12 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
 }
 
 int64_t vog_lstm_workspace_bytes(int Bq, int H) { return lstm_workspace_bytes(Bq, H); }
+
+/* debug / A-B testing: 1 = always use the weight-streaming recurrence kernel */
+void vog_debug_lstm_force_streaming(int on) { vog::lstm_force_streaming(on); }
+/* debug: device buffer of 8 int64: accumulated clock64 cycles of CTA 0 in {matvec, reduce, cell + publish,
+ * poll, barrier} and the step count of the weight-resident recurrence kernel */
+void vog_debug_lstm_trace(void* buf) { vog::lstm_set_trace((long long*)buf); }
 
 int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int64_t* lens, int T, int Bq,
                        int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace, void* stream)
