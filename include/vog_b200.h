@@ -126,6 +126,28 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
                     const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* FACTORISED Q/K/V projection of the multimodal transformer's first layer.  A token (bt, s, p) of the
+ * per-frame sequence bt = b*nfrm + f is [vis[bt*nppf2 + p] | lang[b*nsrl + s]] (code/mdl_vog.py:316-344,
+ * 693-699), so W.token = W[:, :dv].vis + W[:, dv:].lang: A [M = Bt*nppf2, K = dv] holds the VISUAL rows
+ * only, Wvis = the first dv columns of the packed Wq|Wk|Wv (row stride ldw), lq [B*nsrl, ldq >= 3*H*dhp]
+ * fp32 the separately projected language rows (a [B*nsrl x dl] GEMM through vog_tc_gemm).  The epilogue
+ * writes every accumulator row nsrl times, adding lq[b*nsrl + s]: q,k [Bt,H,nsrl*nppf2,dhp] bf16 and
+ * vt [Bt,H,dhp,npad] exactly as vog_tc_gemm_qkv would from the materialised [vis|lang] matrix - with
+ * nsrl x fewer MMA FLOPs and without that matrix.  replaces concate_vis_lang_feats + regroup + wq/wk/wv:
+ * code/mdl_vog.py:316-344,693-699, code/transformer_code.py:180. */
+int vog_tc_gemm_qkv_factored(const void* A, int64_t lda, const void* Wvis, int64_t ldw, int M, int K,
+                             int tf32, int n_heads, int dhp, const float* lq, int64_t ldq, int nfrm,
+                             int nsrl, int nppf2, int npad, void* q, void* k, void* vt, void* stream);
+
+/* vog_tc_gemm with a GATHERED fp32 residual: the residual row of token m = (bt, s, p) is
+ * [res_vis[bt*nppf2 + p, 0:dv] | res_lang[(bt / nfrm)*nsrl + s, 0:N-dv]] - the multimodal transformer's
+ * input read from its two factors (dv % BN == 0, rows 16-byte aligned).  replaces the residual add of
+ * the first RelEncoderLayer on the materialised concat: code/transformer_code.py:30-31,201-203. */
+int vog_tc_gemm_gres(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int tf32,
+                     int BN, const float* bias, int relu, const float* res_vis, int64_t ldv,
+                     const float* res_lang, int64_t ldl, int dv, int nfrm, int nsrl, int nppf2,
+                     float* out_f32, int64_t ldc, void* out_lp, int64_t ldlp, int lp_kind, void* stream);
+
 /* One layer of the bidirectional LSTM recurrence of the language encoder, both directions, all
  * timesteps, in one persistent launch (packed-sequence semantics from the device-side `lens`, no
  * host synchronisation):  gx [T*Bq, ldg >= 8H] = W_ih x + b_ih + b_hh for every (t, b) (time-major

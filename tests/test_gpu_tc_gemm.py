@@ -84,3 +84,41 @@ def test_tc_gemm_qkv_scatter(Bt, N, d, H):
     for h, dh in enumerate(hd):
         if dh < dhp:
             assert q[:, h, :, dh:].abs().max() == 0 and vt[:, h, dh:, :].abs().max() == 0
+
+
+@pytest.mark.parametrize('B,nfrm,nsrl,nppf2,mode', [(2, 10, 5, 20, 'bf16'), (1, 3, 5, 7, 'tf32'), (2, 4, 3, 100, 'bf16'),
+                                                      (4, 10, 5, 20, 'tf32')])
+def test_factored_qkv_and_gathered_residual_match_materialised_tokens(B, nfrm, nsrl, nppf2, mode):
+    """vog_tc_gemm_qkv_factored / vog_tc_gemm_gres (the [vis|lang] token matrix is never written)
+    against the same GEMMs on the materialised token matrix (vog_build_xmul + vog_tc_gemm_qkv /
+    vog_tc_gemm with a plain residual) and against float64."""
+    dv, dl, H = 512, 256, 3
+    d = dv + dl
+    dhp = 256
+    kind = ops.LP_BF16 if mode == 'bf16' else ops.LP_TF32
+    Bt, N = B * nfrm, nsrl * nppf2
+    vis = _u((Bt * nppf2, dv), 21).to(DEV)
+    lang = _u((B * nsrl, dl), 22).to(DEV)
+    wqkv = ops.cast_lp((_u((3 * H * dhp, d), 23) * 0.05).to(DEV), kind)
+    vis_lp, lang_lp = ops.cast_lp(vis, kind), ops.cast_lp(lang, kind)
+    xm, xm_lp = ops.build_xmul(vis, lang, B, nfrm, nsrl, nppf2, kind)
+    q0, k0, vt0 = ops.tc_gemm_qkv(xm_lp, wqkv, Bt, N, H, dhp)
+    lq, _ = ops.tc_gemm(lang_lp, wqkv[:, dv:])
+    q1, k1, vt1 = ops.tc_gemm_qkv_factored(vis_lp, wqkv[:, :dv], lq, Bt, nfrm, nsrl, nppf2, H, dhp)
+    torch.cuda.synchronize()
+    full = (xm_lp.double().cpu() @ wqkv.double().cpu().t()).view(Bt, N, 3, H, dhp)
+    for got0, got1, which in ((q0, q1, 0), (k0, k1, 1)):
+        ref = full[:, :, which].permute(0, 2, 1, 3)
+        assert ((got1.cpu().double() - ref).abs() / (1 + ref.abs())).max() < 8e-3
+        assert ((got1.float() - got0.float()).abs() / (1 + got0.float().abs())).max() < 8e-3
+    refv = full[:, :, 2].permute(0, 2, 3, 1)
+    assert ((vt1.cpu().double()[..., :N] - refv).abs() / (1 + refv.abs())).max() < 8e-3
+    if vt1.shape[-1] > N:
+        assert vt1[..., N:].abs().max() == 0
+    # gathered residual
+    a = ops.cast_lp(_u((Bt * N, H * dhp), 24).to(DEV), kind)
+    wo = ops.cast_lp((_u((d, H * dhp), 25) * 0.05).to(DEV), kind)
+    ref_out, _ = ops.tc_gemm(a, wo, residual=xm)
+    got_out, _ = ops.tc_gemm_gres(a, wo, vis, lang, nfrm, nsrl, nppf2)
+    torch.cuda.synchronize()
+    assert torch.equal(ref_out, got_out)

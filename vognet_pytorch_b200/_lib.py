@@ -50,6 +50,10 @@ _SIGNATURES = {
     'vog_tc_attn_workspace_bytes': [c_int, c_int, c_int],
     'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,
                         c_i64, c_int, P, c_i64, P],
+    'vog_tc_gemm_qkv_factored': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_i64, c_int, c_int,
+                                 c_int, c_int, P, P, P, P],
+    'vog_tc_gemm_gres': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64, P, c_i64,
+                         c_int, c_int, c_int, c_int, P, c_i64, P, c_i64, c_int, P],
     'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
 }
 _RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong,

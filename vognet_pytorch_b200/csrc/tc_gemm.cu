@@ -116,7 +116,7 @@ __device__ __forceinline__ void epi_apply_store(const TcEpilogue& e, int M, int 
 // ---- epilogues: one per kernel instantiation so that each kernel carries only the code it runs ----
 // All three read the accumulator 32 columns at a time (thread = TMEM lane = output row); the next
 // chunk's tcgen05.ld is issued before the current chunk is stored so TMEM latency is hidden.
-enum { EPI_FAST = 0, EPI_QKV = 1, EPI_GENERIC = 2 };
+enum { EPI_FAST = 0, EPI_QKV = 1, EPI_GENERIC = 2, EPI_QKVF = 3 };
 
 // transpose a 32x32 fp32 chunk through the warp's swizzled smem patch: row = lane on the way in ...
 __device__ __forceinline__ void patch_store(float* patch, int lane, const uint32_t (&r)[32]) {
@@ -142,23 +142,41 @@ __device__ __forceinline__ void epi_fast(const GemmParams& p, const TcEpilogue& 
     const int m0 = m_blk * GM_BM + 32 * g;
     const int rows = p.M - m0;                                  // rows of this warp's slab that exist
     const size_t col = (size_t)n_blk * p.BN + c4 * 4;
-    const float* resp = pe.residual ? pe.residual + (size_t)(m0 + r_in) * pe.ldr + col : nullptr;
+    // residual row pointers of this lane's 8 rows: plain [M,N] matrix, or gathered [vis | lang] rows
+    const float* rp[8];
+    const bool has_res = pe.residual != nullptr || pe.res_vis != nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + i * 4 + r_in;
+        rp[i] = nullptr;
+        if (i * 4 + r_in < rows) {
+            if (pe.residual) rp[i] = pe.residual + (size_t)m * pe.ldr + col;
+            else if (pe.res_vis) {
+                const int seq = pe.nsrl * pe.nppf2;
+                const int bt = m / seq, rem = m - bt * seq;
+                const int s_ = rem / pe.nppf2, pp = rem - s_ * pe.nppf2;
+                const int cb = n_blk * p.BN;
+                rp[i] = cb < pe.dv ? pe.res_vis + ((size_t)bt * pe.nppf2 + pp) * pe.ldv + cb + c4 * 4
+                                   : pe.res_lang + ((size_t)(bt / pe.nfrm) * pe.nsrl + s_) * pe.ldl + (cb - pe.dv) + c4 * 4;
+            }
+        }
+    }
     const float* biasp = pe.bias ? pe.bias + col : nullptr;
     float* o32 = pe.out_f32 ? pe.out_f32 + (size_t)(m0 + r_in) * pe.ldc + col : nullptr;
     __nv_bfloat16* obf = (pe.out_lp && pe.lp_kind == 1)
         ? reinterpret_cast<__nv_bfloat16*>(pe.out_lp) + (size_t)(m0 + r_in) * pe.ldlp + col : nullptr;
     float* otf = (pe.out_lp && pe.lp_kind != 1)
         ? reinterpret_cast<float*>(pe.out_lp) + (size_t)(m0 + r_in) * pe.ldlp + col : nullptr;
-    const size_t res_step = 4 * (size_t)pe.ldr, o32_step = 4 * (size_t)pe.ldc, lp_step = 4 * (size_t)pe.ldlp;
+    const size_t o32_step = 4 * (size_t)pe.ldc, lp_step = 4 * (size_t)pe.ldlp;
     float4 res[8];
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     auto prefetch = [&](int c0) {
-        if (resp) {
+        if (has_res) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                if (i * 4 + r_in < rows) res[i] = __ldg(reinterpret_cast<const float4*>(resp + i * res_step + c0));
+                if (rp[i]) res[i] = __ldg(reinterpret_cast<const float4*>(rp[i] + c0));
         }
         if (biasp) b4 = __ldg(reinterpret_cast<const float4*>(biasp + c0));
     };
@@ -251,6 +269,88 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& p
         for (int i = 0; i < 8; ++i) {
             const float4 v = patch_load(patch, i * 4 + r_in, c4);
             if (dst[i]) *reinterpret_cast<uint2*>(dst[i] + c0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        }
+        __syncwarp();
+    }
+}
+
+// EPI_QKVF: factorised QKV (TcEpilogue mode 2).  Rows are visual tokens m = bt*nppf2 + p; every row is
+// written for each of the nsrl language slots with the projected language row added:
+//     out(bt, s, p)[col] = acc[m, col] + lq[(bt / nfrm)*nsrl + s, col]
+__device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
+                                         uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane)
+{
+    const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
+    const int m0 = m_blk * GM_BM + 32 * g;
+    const int colbase = n_blk * p.BN;
+    uint32_t r[32];
+    if (which == 2) {
+        const int m = m0 + lane;
+        const bool ok = m < p.M;
+        const int bt = ok ? m / pe.nppf2 : 0, pp = ok ? m % pe.nppf2 : 0;
+        const float* lqrow = pe.lq + (size_t)((bt / pe.nfrm) * pe.nsrl) * pe.ldq + colbase;
+        __nv_bfloat16* dst = pe.vt + (((size_t)bt * pe.n_heads + h) * pe.dhp) * pe.npad + pp;
+        mbar_wait(tfull, parity);
+        tc_fence_after();
+        tmem_ld32(t_acc, r);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            tmem_wait_ld();
+            float cur[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cur[j] = __uint_as_float(r[j]);
+            if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
+            if (ok) {
+#pragma unroll 1
+                for (int s_ = 0; s_ < pe.nsrl; ++s_) {
+                    const float4* lq4 = reinterpret_cast<const float4*>(lqrow + (size_t)s_ * pe.ldq + c0);
+                    __nv_bfloat16* d = dst + (size_t)c0 * pe.npad + s_ * pe.nppf2;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 l = __ldg(lq4 + j4);
+                        d[(size_t)(4 * j4 + 0) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 0] + l.x);
+                        d[(size_t)(4 * j4 + 1) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 1] + l.y);
+                        d[(size_t)(4 * j4 + 2) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 2] + l.z);
+                        d[(size_t)(4 * j4 + 3) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 3] + l.w);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    const int r_in = lane >> 3, c4 = lane & 7;
+    __nv_bfloat16* base = which == 0 ? pe.q : pe.k;
+    __nv_bfloat16* dst[8];
+    const float* lqi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + i * 4 + r_in;
+        const int bt = m / pe.nppf2, pp = m % pe.nppf2;
+        const bool ok = m < p.M;
+        dst[i] = ok ? base + (((size_t)bt * pe.n_heads + h) * pe.seq_n + pp) * pe.dhp + c4 * 4 : nullptr;
+        lqi[i] = pe.lq + (ok ? (size_t)((bt / pe.nfrm) * pe.nsrl) * pe.ldq : 0) + colbase + c4 * 4;
+    }
+    const size_t slot_step = (size_t)pe.nppf2 * pe.dhp;
+    mbar_wait(tfull, parity);
+    tc_fence_after();
+    tmem_ld32(t_acc, r);
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        tmem_wait_ld();
+        patch_store(patch, lane, r);
+        if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = patch_load(patch, i * 4 + r_in, c4);
+            if (dst[i]) {
+#pragma unroll 1
+                for (int s_ = 0; s_ < pe.nsrl; ++s_) {
+                    const float4 l = __ldg(reinterpret_cast<const float4*>(lqi[i] + (size_t)s_ * pe.ldq + c0));
+                    *reinterpret_cast<uint2*>(dst[i] + s_ * slot_step + c0) =
+                        make_uint2(pack_bf16(v.x + l.x, v.y + l.y), pack_bf16(v.z + l.z, v.w + l.w));
+                }
+            }
         }
         __syncwarp();
     }
@@ -394,6 +494,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             } else {
                 if constexpr (kEpi == EPI_FAST) epi_fast(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane, trace);
                 else if constexpr (kEpi == EPI_QKV) epi_qkv(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
+                else if constexpr (kEpi == EPI_QKVF) epi_qkvf(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
                 else epi_generic(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
             }
             tc_fence_before();
@@ -492,7 +593,7 @@ int num_sms()
 // K-split factor: only when the tile grid leaves most SMs idle and K is deep enough to be worth it
 int tc_gemm_splits(int M, int N, int K, int tf32, int BN, int qkv_mode)
 {
-    if (qkv_mode) return 1;
+    if (qkv_mode) return 1;                  // also: gathered residual (no split-K epilogue for it)
     const int bk = tf32 ? 32 : 64;
     const int nkb = cdiv(K, bk);
     const int tiles = cdiv(M, GM_BM) * cdiv(N, BN);
@@ -520,9 +621,16 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     VOG_REQUIRE(K > 0 && (K * eb) % 16 == 0, "tc_gemm: K=%d rows must be 16-byte multiples", K);
     VOG_REQUIRE(lda >= K && ldw >= K, "tc_gemm: bad leading dimension");
     VOG_REQUIRE(epi.rep >= 1, "tc_gemm: rep must be >= 1");
-    if (epi.mode == 1) {
+    if (epi.mode == 1 || epi.mode == 2) {
         VOG_REQUIRE(BN == epi.dhp && N == 3 * epi.n_heads * epi.dhp, "tc_gemm: qkv epilogue needs BN == dhp, N == 3*H*dhp");
         VOG_REQUIRE(epi.q && epi.k && epi.vt && epi.seq_n > 0 && epi.npad >= epi.seq_n, "tc_gemm: bad qkv epilogue");
+        if (epi.mode == 2) {
+            VOG_REQUIRE(epi.lq && epi.nsrl > 0 && epi.nppf2 > 0 && epi.nfrm > 0 && epi.seq_n == epi.nsrl * epi.nppf2 &&
+                        M % epi.nppf2 == 0 && (M / epi.nppf2) % epi.nfrm == 0,
+                        "tc_gemm: bad factorised-qkv geometry");
+            VOG_REQUIRE(epi.ldq >= N && epi.ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.lq) & 15) == 0,
+                        "tc_gemm: language projection must be 16-byte aligned rows");
+        }
     } else {
         VOG_REQUIRE(epi.out_f32 || epi.out_lp, "tc_gemm: no output");
     }
@@ -539,7 +647,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     p.num_k_blocks = cdiv(K, bk);
     p.num_m_blocks = cdiv(M, GM_BM);
     p.num_n_blocks = cdiv(N, BN);
-    p.splits = tc_gemm_splits(M, N, K, tf32, BN, epi.mode == 1);
+    p.splits = tc_gemm_splits(M, N, K, tf32, BN, epi.mode != 0 || epi.res_vis != nullptr);
     if (p.splits > 1 && (workspace == nullptr || workspace_bytes < (long long)p.splits * M * N * 4))
         p.splits = 1;                          // caller gave no workspace: plain schedule
     p.kb_per_split = cdiv(p.num_k_blocks, p.splits);
@@ -562,6 +670,9 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
         else {
             ok = ok && (!epi.bias || al(epi.bias, 16));
             ok = ok && (!epi.residual || (al(epi.residual, 16) && epi.ldr % 4 == 0));
+            if (epi.res_vis)
+                ok = ok && al(epi.res_vis, 16) && al(epi.res_lang, 16) && epi.ldv % 4 == 0 && epi.ldl % 4 == 0 &&
+                     epi.dv % BN == 0;
             ok = ok && (!epi.out_f32 || (al(epi.out_f32, 16) && epi.ldc % 4 == 0));
             if (epi.out_lp) ok = ok && (epi.lp_kind == 1 ? (al(epi.out_lp, 8) && epi.ldlp % 4 == 0)
                                                          : (al(epi.out_lp, 16) && epi.ldlp % 4 == 0));
@@ -571,7 +682,9 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + GM_EPI_BYTES;
     const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
     const int grid = nitems < num_sms() ? nitems : num_sms();
-    const int epi_kind = epi.mode == 1 ? EPI_QKV : (p.fast ? EPI_FAST : EPI_GENERIC);
+    const int epi_kind = epi.mode == 1 ? EPI_QKV : epi.mode == 2 ? EPI_QKVF : (p.fast ? EPI_FAST : EPI_GENERIC);
+    VOG_REQUIRE(!epi.res_vis || epi_kind == EPI_FAST, "tc_gemm: gathered residual needs the aligned fast epilogue "
+                "(N %% BN == 0, dv %% BN == 0, 16-byte aligned rows)");
 #define VOG_GEMM_LAUNCH(TF, EP)                                                                                   \
     do {                                                                                                          \
         VOG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TF, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -580,10 +693,12 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     if (tf32) {
         if (epi_kind == EPI_FAST) VOG_GEMM_LAUNCH(true, EPI_FAST);
         else if (epi_kind == EPI_QKV) VOG_GEMM_LAUNCH(true, EPI_QKV);
+        else if (epi_kind == EPI_QKVF) VOG_GEMM_LAUNCH(true, EPI_QKVF);
         else VOG_GEMM_LAUNCH(true, EPI_GENERIC);
     } else {
         if (epi_kind == EPI_FAST) VOG_GEMM_LAUNCH(false, EPI_FAST);
         else if (epi_kind == EPI_QKV) VOG_GEMM_LAUNCH(false, EPI_QKV);
+        else if (epi_kind == EPI_QKVF) VOG_GEMM_LAUNCH(false, EPI_QKVF);
         else VOG_GEMM_LAUNCH(false, EPI_GENERIC);
     }
 #undef VOG_GEMM_LAUNCH

@@ -154,6 +154,45 @@ int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, i
     return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
 
+int vog_tc_gemm_qkv_factored(const void* A, int64_t lda, const void* Wvis, int64_t ldw, int M, int K, int tf32,
+                             int n_heads, int dhp, const float* lq, int64_t ldq, int nfrm, int nsrl, int nppf2,
+                             int npad, void* q, void* k, void* vt, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && K > 0 && n_heads >= 1 && n_heads <= VOG_MAX_HEADS, "vog_tc_gemm_qkv_factored: bad dimension");
+    if (M == 0) return 0;
+    if (require_sm100("vog_tc_gemm_qkv_factored")) return -1;
+    VOG_REQUIRE(A && Wvis && lq && q && k && vt, "vog_tc_gemm_qkv_factored: null operand");
+    VOG_REQUIRE(dhp % 64 == 0 && dhp <= 256, "vog_tc_gemm_qkv_factored: dhp=%d must be 64/128/192/256", dhp);
+    VOG_REQUIRE(nfrm > 0 && nsrl > 0 && nppf2 > 0 && npad >= nsrl * nppf2 && npad % 8 == 0,
+                "vog_tc_gemm_qkv_factored: bad sequence geometry");
+    TcEpilogue e;
+    e.mode = 2; e.q = (__nv_bfloat16*)q; e.k = (__nv_bfloat16*)k; e.vt = (__nv_bfloat16*)vt;
+    e.seq_n = nsrl * nppf2; e.n_heads = n_heads; e.dhp = dhp; e.npad = npad;
+    e.lq = lq; e.ldq = ldq; e.nsrl = nsrl; e.nppf2 = nppf2; e.nfrm = nfrm;
+    return tc_gemm(A, lda, Wvis, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
+}
+
+int vog_tc_gemm_gres(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int tf32,
+                     int BN, const float* bias, int relu, const float* res_vis, int64_t ldv,
+                     const float* res_lang, int64_t ldl, int dv, int nfrm, int nsrl, int nppf2,
+                     float* out_f32, int64_t ldc, void* out_lp, int64_t ldlp, int lp_kind, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N >= 0 && K > 0, "vog_tc_gemm_gres: bad dimension");
+    if (M == 0 || N == 0) return 0;
+    if (require_sm100("vog_tc_gemm_gres")) return -1;
+    VOG_REQUIRE(A && W && res_vis && res_lang, "vog_tc_gemm_gres: null operand");
+    VOG_REQUIRE(nfrm > 0 && nsrl > 0 && nppf2 > 0 && dv > 0 && dv < N && M % (nsrl * nppf2) == 0 &&
+                (M / (nsrl * nppf2)) % nfrm == 0 && ldv >= dv && ldl >= N - dv,
+                "vog_tc_gemm_gres: bad token geometry");
+    TcEpilogue e;
+    e.bias = bias; e.relu = relu; e.out_f32 = out_f32; e.ldc = ldc; e.out_lp = out_lp; e.ldlp = ldlp;
+    e.lp_kind = lp_kind; e.rep = 1;
+    e.res_vis = res_vis; e.ldv = ldv; e.res_lang = res_lang; e.ldl = ldl; e.dv = dv;
+    e.nfrm = nfrm; e.nsrl = nsrl; e.nppf2 = nppf2;
+    VOG_REQUIRE(!out_lp || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_tc_gemm_gres: bad lp_kind");
+    return tc_gemm(A, lda, W, ldw, M, N, K, tf32, BN, e, nullptr, 0, (cudaStream_t)stream);
+}
+
 /* debug: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of the next tc_gemm launches */
 void vog_debug_gemm_trace(void* buf) { vog::tc_gemm_set_trace((long long*)buf); }
 

@@ -23,7 +23,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import ops
-from .transformer_code import COMPUTE_MODES, RelBias, RelTransformer, Transformer
+from .transformer_code import COMPUTE_MODES, FactoredTokens, RelBias, RelTransformer, Transformer
 
 
 class _LangEncoder(nn.Module):
@@ -284,18 +284,20 @@ class VOGNetB200(nn.Module):
         P = x.shape[0] // B
         nppf = self.num_prop_per_frm
         nfrm, nppf2 = self._groups(ncmp)
-        # token (b,f,s,p') = [vis[b, f*nppf'+p'] | lang[b,s]] written once, fp32 + low precision
-        xm, xm_lp = ops.build_xmul(x.contiguous(), lang.reshape(B * nsrl, self.lang_dim).contiguous(), B, nfrm,
-                                   nsrl, nppf2, kind)
-        xm = xm.view(B * nfrm, nsrl * nppf2, self.vl_dim)
+        lang2 = lang.reshape(B * nsrl, self.lang_dim).contiguous()
         if self.USE_MUL_TX and self.cfg.mdl.mul_tx.to_use:
+            # token (b,f,s,p') = [vis[b, f*nppf'+p'] | lang[b,s]] is NEVER written: the first layer of the
+            # multimodal transformer projects the two factors separately and reads its residual from them
             mtx = self.cfg.mdl.mul_tx
             bias = None
             if mtx.use_rel:
                 a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
                                    self.vid_w, self.vid_h, float(nfrm))
                 bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
-            xm, xm_lp = self.mult_txf._exec.run(xm, bias, self.compute, x_lp=xm_lp, want_lp=True)
+            ft = FactoredTokens(x.contiguous(), x_lp, lang2, ops.cast_lp(lang2, kind), nfrm, nsrl, nppf2)
+            xm, xm_lp = self.mult_txf._exec.run_factored(ft, bias, self.compute)
+        else:
+            xm, xm_lp = ops.build_xmul(x.contiguous(), lang2, B, nfrm, nsrl, nppf2, kind)
         h, _ = ops.tc_gemm(xm_lp.reshape(-1, self.vl_dim), self._lp_weight('lin2', self.lin2[0].weight, kind),
                            bias=self.lin2[0].bias, relu=True)
         # lin2[2] + inverse regroup + sigmoid * masks in one kernel

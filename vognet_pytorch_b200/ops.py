@@ -241,6 +241,55 @@ def tc_gemm_qkv(a, wqkv, Bt, N, n_heads, dhp):
     return q, k, vt
 
 
+def tc_gemm_qkv_factored(vis_lp, wqkv_vis, lq, Bt, nfrm, nsrl, nppf2, n_heads, dhp):
+    """Factorised QKV projection (see vog_tc_gemm_qkv_factored): vis_lp [Bt*nppf2, dv] low precision,
+    wqkv_vis [3*H*dhp, dv] (a column-slice view of the packed weight is fine), lq [B*nsrl, 3*H*dhp] fp32
+    -> q,k [Bt,H,nsrl*nppf2,dhp] bf16 and vt [Bt,H,dhp,Npad] bf16."""
+    tf32 = _is_tf32(vis_lp, wqkv_vis)
+    M, K = vis_lp.shape
+    _req(lq, torch.float32, 'lq', 2)
+    N = nsrl * nppf2
+    if M != Bt * nppf2 or wqkv_vis.shape != (3 * n_heads * dhp, K) or Bt % nfrm != 0 or \
+            lq.shape != ((Bt // nfrm) * nsrl, 3 * n_heads * dhp):
+        raise ValueError('tc_gemm_qkv_factored: inconsistent shapes')
+    npad = round_up(N, 8)
+    q = torch.empty(Bt, n_heads, N, dhp, device=vis_lp.device, dtype=torch.bfloat16)
+    k = torch.empty_like(q)
+    vt = torch.zeros(Bt, n_heads, dhp, npad, device=vis_lp.device, dtype=torch.bfloat16) if npad != N else \
+        torch.empty(Bt, n_heads, dhp, npad, device=vis_lp.device, dtype=torch.bfloat16)
+    L = _lib.lib()
+    _lib.check(L.vog_tc_gemm_qkv_factored(_ptr(vis_lp), _rowmajor2d(vis_lp, 'vis_lp'), _ptr(wqkv_vis),
+                                          _rowmajor2d(wqkv_vis, 'wqkv_vis'), M, K, tf32, n_heads, dhp, _ptr(lq),
+                                          _rowmajor2d(lq, 'lq'), nfrm, nsrl, nppf2, npad, _ptr(q), _ptr(k),
+                                          _ptr(vt), _stream()), 'vog_tc_gemm_qkv_factored')
+    return q, k, vt
+
+
+def tc_gemm_gres(a, w, res_vis, res_lang, nfrm, nsrl, nppf2, bias=None, relu=False, lp_kind=LP_NONE,
+                 want_f32=True, BN=None):
+    """tc_gemm whose fp32 residual row for token m = (bt, s, p) is [res_vis[bt*nppf2+p] | res_lang[b*nsrl+s]]."""
+    tf32 = _is_tf32(a, w)
+    M, K = a.shape
+    N = w.shape[0]
+    _req(res_vis, torch.float32, 'res_vis', 2), _req(res_lang, torch.float32, 'res_lang', 2)
+    dv = res_vis.shape[1]
+    if w.shape[1] != K or dv + res_lang.shape[1] != N:
+        raise ValueError('tc_gemm_gres: inconsistent shapes')
+    out_f32 = torch.empty(M, N, device=a.device, dtype=torch.float32) if want_f32 else None
+    out_lp = torch.empty(M, N, device=a.device, dtype=_LP_DTYPE[lp_kind]) if lp_kind != LP_NONE else None
+    if bias is not None:
+        _req(bias, torch.float32, 'bias', 1)
+    BN = BN or pick_bn(N)
+    L = _lib.lib()
+    _lib.check(L.vog_tc_gemm_gres(_ptr(a), _rowmajor2d(a, 'a'), _ptr(w), _rowmajor2d(w, 'w'), M, N, K, tf32, BN,
+                                  _ptr(bias), int(relu), _ptr(res_vis), _rowmajor2d(res_vis, 'res_vis'),
+                                  _ptr(res_lang), _rowmajor2d(res_lang, 'res_lang'), dv, nfrm, nsrl, nppf2,
+                                  _ptr(out_f32), N if out_f32 is not None else 0,
+                                  _ptr(out_lp), N if out_lp is not None else 0, lp_kind, _stream()),
+               'vog_tc_gemm_gres')
+    return out_f32, out_lp
+
+
 def tc_attn_fwd(q, k, vt, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, bias_mode=BIAS_NONE,
                 a=None, nbox=0, bpe=None, dense=None):
     """q,k [Bt,H,N,dhp], vt [Bt,H,dhp,Npad] bf16 -> out [Bt*N, H*dhp] (bf16 or tf32-rounded fp32)."""

@@ -35,6 +35,21 @@ class RelBias:
         self.a, self.b, self.nbox = a, b, int(nbox)
 
 
+class FactoredTokens:
+    """The multimodal transformer's input in factored form: token (bt, s, p) of per-frame sequence
+    bt = b*nfrm + f is [vis[bt*nppf2 + p] | lang[b*nsrl + s]] (code/mdl_vog.py:316-344,693-699).
+    vis [Bt*nppf2, dv] fp32 + low-precision copy, lang [B*nsrl, dl] fp32 + low-precision copy.  The
+    executor projects the two factors separately and reads the residual from them, so the
+    [Bt, nsrl*nppf2, dv+dl] matrix is never written."""
+
+    def __init__(self, vis, vis_lp, lang, lang_lp, nfrm, nsrl, nppf2):
+        self.vis, self.vis_lp, self.lang, self.lang_lp = vis, vis_lp, lang, lang_lp
+        self.nfrm, self.nsrl, self.nppf2 = int(nfrm), int(nsrl), int(nppf2)
+        self.Bt = vis.shape[0] // self.nppf2
+        self.N = self.nsrl * self.nppf2
+        self.d = vis.shape[1] + lang.shape[1]
+
+
 class _Heads(nn.Module):
     def __init__(self, d, n_heads):
         super().__init__()
@@ -172,7 +187,18 @@ class EncoderExecutor:
             x2 = ops.add_layernorm(pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps)
         return x2
 
-    def _run_tc(self, x2, x_lp, Bt, N, bkw, inv_scale, kind):
+    def run_factored(self, ft, bias, compute):
+        """tensor-core path on a FactoredTokens input -> (y [Bt,N,d] fp32, y_lp)."""
+        if compute not in ('tf32', 'bf16'):
+            raise ValueError('run_factored: tensor-core compute modes only')
+        if ft.d != self.d:
+            raise ValueError(f'expected token width {self.d}, got {ft.d}')
+        bkw = self._bias_args(bias, ft.Bt, ft.N)
+        kind = ops.LP_BF16 if compute == 'bf16' else ops.LP_TF32
+        y, y_lp = self._run_tc(None, None, ft.Bt, ft.N, bkw, 1.0 / math.sqrt(self.d), kind, ft=ft)
+        return y.view(ft.Bt, ft.N, self.d), y_lp
+
+    def _run_tc(self, x2, x_lp, Bt, N, bkw, inv_scale, kind, ft=None):
         """tcgen05 path.  GEMM operands in `kind` (bf16 / tf32-rounded), attention operands always
         bf16, residual stream / LayerNorm / softmax statistics in fp32."""
         M, d, H, dhp = Bt * N, self.d, self.H, self.dhp
@@ -180,18 +206,28 @@ class EncoderExecutor:
         for l, layer in enumerate(self.stack.layers):
             att, ffn = layer.selfattn, layer.feedforward
             w = self._packed_tc(l, layer, kind)
-            q, k, vt = ops.tc_gemm_qkv(x_lp, w['wqkv'], Bt, N, H, dhp)
+            fact = ft is not None and l == 0
+            if fact:
+                dv = ft.vis.shape[1]
+                lq, _ = ops.tc_gemm(ft.lang_lp, w['wqkv'][:, dv:])          # language rows projected once
+                q, k, vt = ops.tc_gemm_qkv_factored(ft.vis_lp, w['wqkv'][:, :dv], lq, Bt, ft.nfrm, ft.nsrl,
+                                                    ft.nppf2, H, dhp)
+            else:
+                q, k, vt = ops.tc_gemm_qkv(x_lp, w['wqkv'], Bt, N, H, dhp)
             o_lp = ops.tc_attn_fwd(q, k, vt, N, self.head_dims, inv_scale, out_kind=kind, **bkw)
-            pre, _ = ops.tc_gemm(o_lp, w['wo'], residual=x2)
-            y = torch.empty(M, d, device=x2.device, dtype=torch.float32)
-            y_lp = torch.empty(M, d, device=x2.device, dtype=lp_dtype)
+            if fact:
+                pre, _ = ops.tc_gemm_gres(o_lp, w['wo'], ft.vis, ft.lang, ft.nfrm, ft.nsrl, ft.nppf2)
+            else:
+                pre, _ = ops.tc_gemm(o_lp, w['wo'], residual=x2)
+            y = torch.empty(M, d, device=pre.device, dtype=torch.float32)
+            y_lp = torch.empty(M, d, device=pre.device, dtype=lp_dtype)
             ops.add_layernorm(pre, None, att.layernorm.weight, att.layernorm.bias, att.layernorm.eps,
                               out=y, out_lp=y_lp, lp_kind=kind)
             _, h_lp = ops.tc_gemm(y_lp, w['w1'], bias=ffn.layer.linear1.bias, relu=True, lp_kind=kind,
                                   want_f32=False)
             pre2, _ = ops.tc_gemm(h_lp, w['w2'], bias=ffn.layer.linear2.bias, residual=y)
-            x2 = torch.empty(M, d, device=x2.device, dtype=torch.float32)
-            x_lp = torch.empty(M, d, device=x2.device, dtype=lp_dtype)
+            x2 = torch.empty(M, d, device=pre.device, dtype=torch.float32)
+            x_lp = torch.empty(M, d, device=pre.device, dtype=lp_dtype)
             ops.add_layernorm(pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps,
                               out=x2, out_lp=x_lp, lp_kind=kind)
         return x2, x_lp
