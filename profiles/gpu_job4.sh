@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 100 python profiles/lstm_trace.py > gpurun_out/lstm_trace.log 2>&1
+timeout 300 python bench.py --no-seq4000 > gpurun_out/bench_spat_gt5.json 2> gpurun_out/bench_spat_gt5.err
+timeout 300 python bench.py --workload spat_p100 --steps 10 --no-seq4000 > gpurun_out/bench_spat_p100.json 2> gpurun_out/bench_spat_p100.err
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_spat_gt5.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-seq4000 > gpurun_out/ncu_gt5.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_spat_p100.csv python bench.py --workload spat_p100 --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-seq4000 > gpurun_out/ncu_p100.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/lstm_trace.log; cut -c1-330 gpurun_out/bench_spat_gt5.json; cut -c1-330 gpurun_out/bench_spat_p100.json

@@ -121,4 +121,4 @@ def test_factored_qkv_and_gathered_residual_match_materialised_tokens(B, nfrm, n
     ref_out, _ = ops.tc_gemm(a, wo, residual=xm)
     got_out, _ = ops.tc_gemm_gres(a, wo, vis, lang, nfrm, nsrl, nppf2)
     torch.cuda.synchronize()
-    assert torch.equal(ref_out, got_out)
+    assert torch.allclose(ref_out, got_out, atol=2e-4, rtol=0)      # split-K vs single pass: summation order only

@@ -305,11 +305,88 @@ add_layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restri
     }
 }
 
+// register-cached variant: d % 128 == 0, d <= 1024, 16-byte aligned rows - the row is read from
+// global memory exactly once (float4 per lane, fully coalesced) and kept in registers for the
+// mean / variance / normalise passes (two-pass variance as in the generic kernel)
+template <int NV>
+__global__ void __launch_bounds__(256)
+add_layernorm_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ r, int ldr,
+                         const float* __restrict__ w, const float* __restrict__ b,
+                         float* __restrict__ out, int ldo, void* __restrict__ out_lp, int ldlp, int lp_kind,
+                         int M, float eps)
+{
+    constexpr int d = NV * 128;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    if (r) {
+        const float4* rr = reinterpret_cast<const float4*>(r + (size_t)row * ldr);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 t = rr[lane + 32 * i];
+            v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q = fmaf(v[i].x, v[i].x, q); q = fmaf(v[i].y, v[i].y, q);
+        q = fmaf(v[i].z, v[i].z, q); q = fmaf(v[i].w, v[i].w, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+        float4 t;
+        t.x = v[i].x * rstd * w4.x + b4.x; t.y = v[i].y * rstd * w4.y + b4.y;
+        t.z = v[i].z * rstd * w4.z + b4.z; t.w = v[i].w * rstd * w4.w + b4.w;
+        const size_t c = (size_t)(lane + 32 * i) * 4;
+        if (out) *reinterpret_cast<float4*>(out + (size_t)row * ldo + c) = t;
+        if (out_lp) {
+            if (lp_kind == 1) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_lp) + (size_t)row * ldlp + c) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_lp) + (size_t)row * ldlp + c) =
+                    make_float4(to_tf32(t.x), to_tf32(t.y), to_tf32(t.z), to_tf32(t.w));
+            }
+        }
+    }
+}
+
 int add_layernorm(const float* x, int ldx, const float* r, int ldr, const float* w, const float* b,
                   float* out, int ldo, void* out_lp, int ldlp, int lp_kind, int M, int d, float eps,
                   cudaStream_t st)
 {
     if (M == 0) return 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec = d % 128 == 0 && d <= 1024 && al16(x) && ldx % 4 == 0 && (!r || (al16(r) && ldr % 4 == 0)) &&
+                     al16(w) && al16(b) && (!out || (al16(out) && ldo % 4 == 0)) &&
+                     (!out_lp || ((reinterpret_cast<uintptr_t>(out_lp) & (lp_kind == 1 ? 7 : 15)) == 0 && ldlp % 4 == 0));
+    if (vec) {
+#define VOG_LN_CASE(NV)                                                                                   \
+    case NV:                                                                                              \
+        add_layernorm_vec_kernel<NV><<<cdiv(M, 8), 256, 0, st>>>(x, ldx, r, ldr, w, b, out, ldo, out_lp,  \
+                                                                 ldlp, lp_kind, M, eps);                  \
+        break;
+        switch (d / 128) {
+            VOG_LN_CASE(1) VOG_LN_CASE(2) VOG_LN_CASE(3) VOG_LN_CASE(4) VOG_LN_CASE(5) VOG_LN_CASE(6)
+            VOG_LN_CASE(7) VOG_LN_CASE(8)
+        }
+#undef VOG_LN_CASE
+        return check_launch("add_layernorm_vec");
+    }
     add_layernorm_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, ldx, r, ldr, w, b, out, ldo, out_lp, ldlp,
                                                      lp_kind, M, d, eps);
     return check_launch("add_layernorm");

@@ -215,6 +215,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {      // (a.x*b.x + c.x, a.y*b.y + c.y), one FFMA2
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 struct LstmResParams {
     const float* gx; long long ldg;
     const float* whh;
@@ -314,24 +323,50 @@ lstm_rec_resident_kernel(const LstmResParams p)
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] = 0.f;
         if (step > 0) {                                      // h_{-1} = 0
+            if constexpr (BQ <= 4) {
+                // packed fp32 FMAs (FFMA2): even / odd columns accumulate in the two halves of a register pair
+                float2 acc2[V];
 #pragma unroll
-            for (int i = 0; i < LR_NI; ++i) {
-                float4 w4[4];
+                for (int k = 0; k < V; ++k) acc2[k] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    w4[g] = i < LR_NREG ? wr[g][i < LR_NREG ? i : 0]
-                                        : w_s[(g * (LR_NI - LR_NREG) + (i - LR_NREG)) * NT + tid];
+                for (int i = 0; i < LR_NI; ++i) {
+                    float4 w4[4];
 #pragma unroll
-                for (int b = 0; b < BQ; ++b) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hcur + b * H + 128 * i + 4 * lane);
+                    for (int g = 0; g < 4; ++g)
+                        w4[g] = i < LR_NREG ? wr[g][i < LR_NREG ? i : 0]
+                                            : w_s[(g * (LR_NI - LR_NREG) + (i - LR_NREG)) * NT + tid];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float a = acc[b * 4 + g];
-                        a = fmaf(w4[g].x, hv.x, a);
-                        a = fmaf(w4[g].y, hv.y, a);
-                        a = fmaf(w4[g].z, hv.z, a);
-                        a = fmaf(w4[g].w, hv.w, a);
-                        acc[b * 4 + g] = a;
+                    for (int b = 0; b < BQ; ++b) {
+                        const float4 hv = *reinterpret_cast<const float4*>(hcur + b * H + 128 * i + 4 * lane);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            acc2[b * 4 + g] = ffma2(make_float2(w4[g].x, w4[g].y), make_float2(hv.x, hv.y), acc2[b * 4 + g]);
+                            acc2[b * 4 + g] = ffma2(make_float2(w4[g].z, w4[g].w), make_float2(hv.z, hv.w), acc2[b * 4 + g]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[k] = acc2[k].x + acc2[k].y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < LR_NI; ++i) {
+                    float4 w4[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        w4[g] = i < LR_NREG ? wr[g][i < LR_NREG ? i : 0]
+                                            : w_s[(g * (LR_NI - LR_NREG) + (i - LR_NREG)) * NT + tid];
+#pragma unroll
+                    for (int b = 0; b < BQ; ++b) {
+                        const float4 hv = *reinterpret_cast<const float4*>(hcur + b * H + 128 * i + 4 * lane);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float a = acc[b * 4 + g];
+                            a = fmaf(w4[g].x, hv.x, a);
+                            a = fmaf(w4[g].y, hv.y, a);
+                            a = fmaf(w4[g].z, hv.z, a);
+                            a = fmaf(w4[g].w, hv.w, a);
+                            acc[b * 4 + g] = a;
+                        }
                     }
                 }
             }

@@ -39,6 +39,7 @@ struct GemmParams {
     int M, N, K, BN;
     int num_k_blocks, num_m_blocks, num_n_blocks, bk_elems;
     int splits, kb_per_split, fast;
+    int lq_stage;                 // bytes of the factorised-QKV language staging area (0 = read through L1)
     float* partial;               // [splits, M, N] when splits > 1
     uint32_t idesc, tmem_cols;
     int stages;
@@ -277,18 +278,42 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& p
 // EPI_QKVF: factorised QKV (TcEpilogue mode 2).  Rows are visual tokens m = bt*nppf2 + p; every row is
 // written for each of the nsrl language slots with the projected language row added:
 //     out(bt, s, p)[col] = acc[m, col] + lq[(bt / nfrm)*nsrl + s, col]
-__device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
-                                         uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane)
+// The lq rows this tile needs (<= 2 queries x nsrl slots x BN columns when a query has >= 127 visual
+// rows) are staged in shared memory by the four epilogue warps while the MMAs of the tile run; tiny
+// configurations with more queries per tile read them through L1 instead (lqs == nullptr).
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& pe, float* patch, float* lqs,
+                                         uint32_t t_acc, uint32_t tfull, uint32_t parity, int m_blk, int n_blk,
+                                         int g, int lane)
 {
     const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
     const int m0 = m_blk * GM_BM + 32 * g;
     const int colbase = n_blk * p.BN;
+    const int b0 = (m_blk * GM_BM / pe.nppf2) / pe.nfrm;          // query of the tile's first row
+    if (lqs) {
+        const int nq = (p.M / pe.nppf2) / pe.nfrm;
+        const int bn4 = p.BN >> 2;
+        const int nvec = 2 * pe.nsrl * bn4;
+        epi_bar();                                                // the previous tile's readers are done
+        for (int v = g * 32 + lane; v < nvec; v += 128) {
+            const int row = v / bn4, c = v - row * bn4;            // row = slot*nsrl + s
+            const int b = b0 + row / pe.nsrl;
+            if (b < nq)
+                reinterpret_cast<float4*>(lqs)[v] = __ldg(reinterpret_cast<const float4*>(
+                    pe.lq + ((size_t)b * pe.nsrl + row % pe.nsrl) * pe.ldq + colbase) + c);
+        }
+        epi_bar();
+    }
     uint32_t r[32];
     if (which == 2) {
         const int m = m0 + lane;
         const bool ok = m < p.M;
         const int bt = ok ? m / pe.nppf2 : 0, pp = ok ? m % pe.nppf2 : 0;
-        const float* lqrow = pe.lq + (size_t)((bt / pe.nfrm) * pe.nsrl) * pe.ldq + colbase;
+        const int b = bt / pe.nfrm;
+        const float* lrow = lqs ? lqs + (size_t)(b - b0) * pe.nsrl * p.BN
+                                : pe.lq + (size_t)b * pe.nsrl * pe.ldq + colbase;
+        const size_t lstep = lqs ? (size_t)p.BN : (size_t)pe.ldq;
         __nv_bfloat16* dst = pe.vt + (((size_t)bt * pe.n_heads + h) * pe.dhp) * pe.npad + pp;
         mbar_wait(tfull, parity);
         tc_fence_after();
@@ -303,15 +328,17 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
             if (ok) {
 #pragma unroll 1
                 for (int s_ = 0; s_ < pe.nsrl; ++s_) {
-                    const float4* lq4 = reinterpret_cast<const float4*>(lqrow + (size_t)s_ * pe.ldq + c0);
+                    const float4* lq4 = reinterpret_cast<const float4*>(lrow + s_ * lstep + c0);
                     __nv_bfloat16* d = dst + (size_t)c0 * pe.npad + s_ * pe.nppf2;
+                    float4 l[8];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) l[j4] = lq4[j4];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 l = __ldg(lq4 + j4);
-                        d[(size_t)(4 * j4 + 0) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 0] + l.x);
-                        d[(size_t)(4 * j4 + 1) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 1] + l.y);
-                        d[(size_t)(4 * j4 + 2) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 2] + l.z);
-                        d[(size_t)(4 * j4 + 3) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 3] + l.w);
+                        d[(size_t)(4 * j4 + 0) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 0] + l[j4].x);
+                        d[(size_t)(4 * j4 + 1) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 1] + l[j4].y);
+                        d[(size_t)(4 * j4 + 2) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 2] + l[j4].z);
+                        d[(size_t)(4 * j4 + 3) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 3] + l[j4].w);
                     }
                 }
             }
@@ -325,11 +352,14 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + i * 4 + r_in;
-        const int bt = m / pe.nppf2, pp = m % pe.nppf2;
         const bool ok = m < p.M;
+        const int bt = ok ? m / pe.nppf2 : 0, pp = ok ? m % pe.nppf2 : 0;
+        const int b = bt / pe.nfrm;
         dst[i] = ok ? base + (((size_t)bt * pe.n_heads + h) * pe.seq_n + pp) * pe.dhp + c4 * 4 : nullptr;
-        lqi[i] = pe.lq + (ok ? (size_t)((bt / pe.nfrm) * pe.nsrl) * pe.ldq : 0) + colbase + c4 * 4;
+        lqi[i] = (lqs ? lqs + (size_t)(ok ? b - b0 : 0) * pe.nsrl * p.BN
+                      : pe.lq + (size_t)b * pe.nsrl * pe.ldq + colbase) + c4 * 4;
     }
+    const size_t lstep = lqs ? (size_t)p.BN : (size_t)pe.ldq;
     const size_t slot_step = (size_t)pe.nppf2 * pe.dhp;
     mbar_wait(tfull, parity);
     tc_fence_after();
@@ -340,17 +370,19 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
         patch_store(patch, lane, r);
         if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
         __syncwarp();
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 v = patch_load(patch, i * 4 + r_in, c4);
-            if (dst[i]) {
+        for (int i = 0; i < 8; ++i) v[i] = patch_load(patch, i * 4 + r_in, c4);
 #pragma unroll 1
-                for (int s_ = 0; s_ < pe.nsrl; ++s_) {
-                    const float4 l = __ldg(reinterpret_cast<const float4*>(lqi[i] + (size_t)s_ * pe.ldq + c0));
+        for (int s_ = 0; s_ < pe.nsrl; ++s_) {
+            float4 l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) l[i] = *reinterpret_cast<const float4*>(lqi[i] + s_ * lstep + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (dst[i])
                     *reinterpret_cast<uint2*>(dst[i] + s_ * slot_step + c0) =
-                        make_uint2(pack_bf16(v.x + l.x, v.y + l.y), pack_bf16(v.z + l.z, v.w + l.w));
-                }
-            }
+                        make_uint2(pack_bf16(v[i].x + l[i].x, v[i].y + l[i].y), pack_bf16(v[i].z + l[i].z, v[i].w + l[i].w));
         }
         __syncwarp();
     }
@@ -393,7 +425,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
     const uint32_t stage_bytes = GM_A_BYTES + p.BN * 128;
     const uint32_t epi_off = p.stages * stage_bytes;
-    const uint32_t bar_off = epi_off + GM_EPI_BYTES;
+    const uint32_t bar_off = epi_off + GM_EPI_BYTES + p.lq_stage;
     const uint32_t bar_base = smem_base + bar_off;
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(
         smem_gen + bar_off + 8 * (2 * GM_MAX_STAGES + 4));
@@ -494,7 +526,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             } else {
                 if constexpr (kEpi == EPI_FAST) epi_fast(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane, trace);
                 else if constexpr (kEpi == EPI_QKV) epi_qkv(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
-                else if constexpr (kEpi == EPI_QKVF) epi_qkvf(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
+                else if constexpr (kEpi == EPI_QKVF)
+                    epi_qkvf(p, p.e, patch, p.lq_stage ? reinterpret_cast<float*>(smem_gen + epi_off + GM_EPI_BYTES) : nullptr,
+                             t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
                 else epi_generic(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
             }
             tc_fence_before();
@@ -656,7 +690,10 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     p.idesc = umma_idesc(tf32 ? FMT_TF32 : FMT_BF16, GM_BM, BN);
     p.tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
     const int stage_bytes = GM_A_BYTES + BN * 128;
-    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - GM_EPI_BYTES;
+    p.lq_stage = 0;
+    if (epi.mode == 2 && epi.nfrm * epi.nppf2 >= GM_BM - 1 && epi.nsrl <= 16)
+        p.lq_stage = 2 * epi.nsrl * BN * 4;       // a 128-row tile then spans at most two queries
+    const int budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - GM_EPI_BYTES - p.lq_stage;
     int stages = budget / stage_bytes;
     if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
     VOG_REQUIRE(stages >= 2, "tc_gemm: tile does not fit shared memory");
@@ -679,7 +716,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
         }
         p.fast = ok ? 1 : 0;
     }
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + GM_EPI_BYTES;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + GM_EPI_BYTES + p.lq_stage;
     const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
     const int grid = nitems < num_sms() ? nitems : num_sms();
     const int epi_kind = epi.mode == 1 ? EPI_QKV : epi.mode == 2 ? EPI_QKVF : (p.fast ? EPI_FAST : EPI_GENERIC);

@@ -295,7 +295,7 @@ class VOGNetB200(nn.Module):
                                    self.vid_w, self.vid_h, float(nfrm))
                 bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
             ft = FactoredTokens(x.contiguous(), x_lp, lang2, ops.cast_lp(lang2, kind), nfrm, nsrl, nppf2)
-            xm, xm_lp = self.mult_txf._exec.run_factored(ft, bias, self.compute)
+            xm, xm_lp = self.mult_txf._exec.run_factored(ft, bias, self.compute, need_f32=False)
         else:
             xm, xm_lp = ops.build_xmul(x.contiguous(), lang2, B, nfrm, nsrl, nppf2, kind)
         h, _ = ops.tc_gemm(xm_lp.reshape(-1, self.vl_dim), self._lp_weight('lin2', self.lin2[0].weight, kind),

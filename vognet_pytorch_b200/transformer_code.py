@@ -187,18 +187,19 @@ class EncoderExecutor:
             x2 = ops.add_layernorm(pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps)
         return x2
 
-    def run_factored(self, ft, bias, compute):
-        """tensor-core path on a FactoredTokens input -> (y [Bt,N,d] fp32, y_lp)."""
+    def run_factored(self, ft, bias, compute, need_f32=True):
+        """tensor-core path on a FactoredTokens input -> (y [Bt,N,d] fp32 or None, y_lp)."""
         if compute not in ('tf32', 'bf16'):
             raise ValueError('run_factored: tensor-core compute modes only')
         if ft.d != self.d:
             raise ValueError(f'expected token width {self.d}, got {ft.d}')
         bkw = self._bias_args(bias, ft.Bt, ft.N)
         kind = ops.LP_BF16 if compute == 'bf16' else ops.LP_TF32
-        y, y_lp = self._run_tc(None, None, ft.Bt, ft.N, bkw, 1.0 / math.sqrt(self.d), kind, ft=ft)
-        return y.view(ft.Bt, ft.N, self.d), y_lp
+        y, y_lp = self._run_tc(None, None, ft.Bt, ft.N, bkw, 1.0 / math.sqrt(self.d), kind, ft=ft,
+                               need_f32=need_f32)
+        return (y.view(ft.Bt, ft.N, self.d) if y is not None else None), y_lp
 
-    def _run_tc(self, x2, x_lp, Bt, N, bkw, inv_scale, kind, ft=None):
+    def _run_tc(self, x2, x_lp, Bt, N, bkw, inv_scale, kind, ft=None, need_f32=True):
         """tcgen05 path.  GEMM operands in `kind` (bf16 / tf32-rounded), attention operands always
         bf16, residual stream / LayerNorm / softmax statistics in fp32."""
         M, d, H, dhp = Bt * N, self.d, self.H, self.dhp
@@ -226,7 +227,9 @@ class EncoderExecutor:
             _, h_lp = ops.tc_gemm(y_lp, w['w1'], bias=ffn.layer.linear1.bias, relu=True, lp_kind=kind,
                                   want_f32=False)
             pre2, _ = ops.tc_gemm(h_lp, w['w2'], bias=ffn.layer.linear2.bias, residual=y)
-            x2 = torch.empty(M, d, device=pre.device, dtype=torch.float32)
+            last = l == len(self.stack.layers) - 1
+            # the fp32 copy of the stack's output is skipped when the caller only feeds a GEMM with it
+            x2 = torch.empty(M, d, device=pre.device, dtype=torch.float32) if (need_f32 or not last) else None
             x_lp = torch.empty(M, d, device=pre.device, dtype=lp_dtype)
             ops.add_layernorm(pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps,
                               out=x2, out_lp=x_lp, lp_kind=kind)
