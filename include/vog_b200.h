@@ -176,6 +176,21 @@ int vog_lin2_tail(const float* h, int ldh, const float* w2, const float* b2, con
                   const int64_t* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl,
                   int nppf2, int K, int ncmp, int nppf, int nfrm0, int spat, void* stream);
 
+/* Language-side glue.  vog_lang_embed: time-major LSTM input rows x_lp[t*Bq + b] = lp(emb[tok]) with
+ * tok = mask[b,t] == -1 ? pad_idx : words[b, mask[b,t]] (words [Bq,nwords], mask [Bq,T] int64) - replaces
+ * get_srl_arg_seq_to_sent_seq + embed_tokens: code/mdl_vog.py:67-95, utils/mdl_srl_utils.py:124-127.
+ * vog_lang_gather: out_lp[b*nsrl + s] = lp([full[cap[b,s,0]*Bq + b] | full[cap[b,s,1]*Bq + b]]), full
+ * [T*Bq, D] fp32 time-major, cap [Bq,nsrl,2] int64 - the first/last-word gather + concat of
+ * retrieve_srl_arg_from_lang_encode: code/mdl_vog.py:97-131.
+ * vog_mask_rows: out[r] = x[r] * msk[r] (+ low-precision copy), msk int64 - the srl_arg_inds_msk product:
+ * code/mdl_vog.py:137-140. */
+int vog_lang_embed(const int64_t* words, int nwords, const int64_t* mask, int T, const float* emb, int E,
+                   int64_t pad_idx, int Bq, void* out_lp, int lp_kind, void* stream);
+int vog_lang_gather(const float* full, int D, const int64_t* cap, int T, int Bq, int nsrl, void* out_lp,
+                    int lp_kind, void* stream);
+int vog_mask_rows(const float* x, const int64_t* msk, int rows, int D, float* out, void* out_lp, int lp_kind,
+                  void* stream);
+
 /* ---- debug hooks (not part of the data path) ----------------------------------------------------
  * vog_debug_gemm_trace: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of every
  * following vog_tc_gemm launch (entry, setup done, first TMA issued, first stage landed, last MMA
@@ -183,6 +198,7 @@ int vog_lin2_tail(const float* h, int ldh, const float* w2, const float* b2, con
  * vog_debug_attn_prof: device buffer of 16 int64 for the per-phase cycle counters of one softmax
  * warp / the MMA issuer of vog_tc_attn_fwd (library built with -DVOG_ATTN_PROFILE). */
 void vog_debug_gemm_trace(void* buf);
+void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 0 tagged 64-bit words, 1 per-CTA release flags */
 void vog_debug_lstm_trace(void* buf);          /* 8 int64: matvec, reduce, cell+publish, poll, barrier cycles, steps */
 void vog_debug_attn_prof(void* buf);
 

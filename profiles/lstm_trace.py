@@ -12,7 +12,8 @@ from vognet_pytorch_b200 import ops, _lib  # noqa: E402
 dev = 'cuda:0'
 L = _lib.lib()
 T, H = 20, 1024
-for Bq in (4, 8):
+for Bq, xmode in ((4, 0), (4, 1), (8, 0), (8, 1)):
+    L.vog_debug_lstm_exchange(xmode)
     gx = torch.rand(T * Bq, 8 * H, device=dev) - 0.5
     whh = (torch.rand(2, 4 * H, H, device=dev) - 0.5) / 32
     lens = torch.tensor([7, 18, 11, 7, 20, 3, 9, 14], device=dev)[:Bq]
@@ -29,5 +30,14 @@ for Bq in (4, 8):
     L.vog_debug_lstm_trace(None)
     v = buf.cpu().tolist()
     n = max(v[5], 1)
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    print(f'Bq={Bq} exchange={"flags" if xmode else "tagged"}: median {sorted(ts)[5]:.1f} us (10 launches, no trace)')
     print(f'Bq={Bq}: {e0.elapsed_time(e1) * 1e3:.1f} us for {v[5]} steps; per step (cycles): '
           f'matvec {v[0] / n:.0f}  reduce {v[1] / n:.0f}  cell+publish {v[2] / n:.0f}  poll {v[3] / n:.0f}  barrier {v[4] / n:.0f}')

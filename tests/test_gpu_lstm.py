@@ -58,10 +58,10 @@ def _ref_recurrence(gx, whh, lens, T, Bq, H):
     return ref
 
 
-@pytest.mark.parametrize('streaming', [0, 1], ids=['resident', 'streaming'])
+@pytest.mark.parametrize('streaming,xmode', [(0, 0), (0, 1), (1, 0)], ids=['resident-tagged', 'resident-flags', 'streaming'])
 @pytest.mark.parametrize('lens_list', [[1, 20, 7, 13], [5], [20, 3], [2, 9, 4], [1, 1, 1, 1], [20] * 8,
                                        [3, 17, 20, 1, 8, 12]])
-def test_ragged_lengths_and_zero_rows(lens_list, streaming):
+def test_ragged_lengths_and_zero_rows(lens_list, streaming, xmode):
     """lengths 1..20, including full-length and single-token sentences, 1..8 sequences per launch;
     both recurrence kernels (weight-resident: W_hh in registers + shared memory, tagged h exchange;
     weight-streaming: W_hh from L2 every step, counter barrier) against a float64 host recurrence."""
@@ -73,11 +73,13 @@ def test_ragged_lengths_and_zero_rows(lens_list, streaming):
     gx = (torch.rand(T * Bq, 8 * H, generator=torch.Generator().manual_seed(3)) - 0.5).to(DEV)
     _, _, whh = mdl._lang_weights(ops.LP_TF32)[0]
     _lib.lib().vog_debug_lstm_force_streaming(streaming)
+    _lib.lib().vog_debug_lstm_exchange(xmode)
     try:
         outs = [ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32).view(T, Bq, 2 * H) for _ in range(3)]
         torch.cuda.synchronize()
     finally:
         _lib.lib().vog_debug_lstm_force_streaming(0)
+        _lib.lib().vog_debug_lstm_exchange(0)
     out = outs[0]
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])      # deterministic across launches
     ref = _ref_recurrence(gx, whh, lens, T, Bq, H)

@@ -41,10 +41,14 @@ _SIGNATURES = {
                     P, c_i64, P, c_i64, c_int, c_int, P, c_i64, P],
     'vog_build_xmul': [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'vog_lin2_tail': [P, c_int, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    'vog_lang_embed': [P, c_int, P, c_int, P, c_int, c_i64, c_int, P, c_int, P],
+    'vog_lang_gather': [P, c_int, P, c_int, c_int, c_int, P, c_int, P],
+    'vog_mask_rows': [P, P, c_int, c_int, P, P, c_int, P],
     'vog_lstm_workspace_bytes': [c_int, c_int],
     'vog_debug_lstm_force_streaming': [c_int],
     'vog_debug_gemm_trace': [P],
     'vog_debug_lstm_trace': [P],
+    'vog_debug_lstm_exchange': [c_int],
     'vog_debug_attn_prof': [P],
     'vog_lstm_layer_fwd': [P, c_i64, P, P, c_int, c_int, c_int, P, c_i64, c_int, P, P],
     'vog_tc_attn_workspace_bytes': [c_int, c_int, c_int],

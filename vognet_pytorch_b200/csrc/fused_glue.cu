@@ -104,4 +104,93 @@ int lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const l
     return check_launch("lin2_tail");
 }
 
+// -------------------------------------------------------------------------------------------------
+// Language-side glue (code/mdl_vog.py:67-140): three kernels instead of ~15 library launches.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_lp4(void* base, size_t idx, float4 v, int kind) {
+    if (kind == 1) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) =
+            make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
+}
+
+// x_lp[t*Bq + b, :] = lp(emb[tok]),  tok = mask[b,t] == -1 ? pad_idx : words[b, mask[b,t]]
+// (get_srl_arg_seq_to_sent_seq :67-95 + embed_tokens, time-major rows for the LSTM)
+__global__ void __launch_bounds__(128)
+lang_embed_kernel(const long long* __restrict__ words, int nwords, const long long* __restrict__ mask, int T,
+                  const float* __restrict__ emb, int E, long long pad_idx, int Bq, void* __restrict__ out_lp,
+                  int lp_kind)
+{
+    const int row = blockIdx.x;                 // t*Bq + b
+    const int t = row / Bq, b = row % Bq;
+    const long long mk = mask[(size_t)b * T + t];
+    long long tok = pad_idx;
+    if (mk != -1) tok = words[(size_t)b * nwords + (mk < 0 ? 0 : (mk >= nwords ? nwords - 1 : mk))];
+    const float4* src = reinterpret_cast<const float4*>(emb + (size_t)tok * E);
+    for (int c = threadIdx.x; c < E / 4; c += blockDim.x) store_lp4(out_lp, (size_t)row * E + 4 * c, __ldg(src + c), lp_kind);
+}
+
+int lang_embed(const long long* words, int nwords, const long long* mask, int T, const float* emb, int E,
+               long long pad_idx, int Bq, void* out_lp, int lp_kind, cudaStream_t st)
+{
+    VOG_REQUIRE(E % 4 == 0, "lang_embed: embedding width must be a multiple of 4");
+    if (T * Bq == 0) return 0;
+    lang_embed_kernel<<<T * Bq, 128, 0, st>>>(words, nwords, mask, T, emb, E, pad_idx, Bq, out_lp, lp_kind);
+    return check_launch("lang_embed");
+}
+
+// out_lp[b*nsrl + s, :] = lp([full[cap[b,s,0]*Bq + b, :] | full[cap[b,s,1]*Bq + b, :]])
+// (retrieve_srl_arg_from_lang_encode :97-131: first / last word of every SRL argument)
+__global__ void __launch_bounds__(128)
+lang_gather_kernel(const float* __restrict__ full, int D, const long long* __restrict__ cap, int T, int Bq,
+                   int nsrl, void* __restrict__ out_lp, int lp_kind)
+{
+    const int row = blockIdx.x;                 // b*nsrl + s
+    const int b = row / nsrl;
+    for (int c = threadIdx.x; c < 2 * D / 4; c += blockDim.x) {
+        const int which = (4 * c) / D, col = 4 * c - which * D;
+        long long t = cap[(size_t)row * 2 + which];
+        t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+        const float4 v = *reinterpret_cast<const float4*>(full + ((size_t)t * Bq + b) * D + col);
+        store_lp4(out_lp, (size_t)row * 2 * D + 4 * c, v, lp_kind);
+    }
+}
+
+int lang_gather(const float* full, int D, const long long* cap, int T, int Bq, int nsrl, void* out_lp, int lp_kind,
+                cudaStream_t st)
+{
+    VOG_REQUIRE(D % 4 == 0, "lang_gather: feature width must be a multiple of 4");
+    if (Bq * nsrl == 0) return 0;
+    lang_gather_kernel<<<Bq * nsrl, 128, 0, st>>>(full, D, cap, T, Bq, nsrl, out_lp, lp_kind);
+    return check_launch("lang_gather");
+}
+
+// out[r, :] = x[r, :] * (float)msk[r]  (+ low-precision copy)    (srl_arg_inds_msk :137-140)
+__global__ void __launch_bounds__(128)
+mask_rows_kernel(const float* __restrict__ x, const long long* __restrict__ msk, int D, float* __restrict__ out,
+                 void* __restrict__ out_lp, int lp_kind)
+{
+    const int row = blockIdx.x;
+    const float m = (float)msk[row];
+    for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+        float4 v = *reinterpret_cast<const float4*>(x + (size_t)row * D + 4 * c);
+        v.x *= m; v.y *= m; v.z *= m; v.w *= m;
+        *reinterpret_cast<float4*>(out + (size_t)row * D + 4 * c) = v;
+        if (out_lp) store_lp4(out_lp, (size_t)row * D + 4 * c, v, lp_kind);
+    }
+}
+
+int mask_rows(const float* x, const long long* msk, int rows, int D, float* out, void* out_lp, int lp_kind,
+              cudaStream_t st)
+{
+    VOG_REQUIRE(D % 4 == 0, "mask_rows: feature width must be a multiple of 4");
+    if (rows == 0) return 0;
+    mask_rows_kernel<<<rows, 128, 0, st>>>(x, msk, D, out, out_lp, lp_kind);
+    return check_launch("mask_rows");
+}
+
 }  // namespace vog

@@ -69,6 +69,7 @@ int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long
 // ---- lstm_rec.cu : persistent bidirectional LSTM recurrence -----------------------------------
 long long lstm_workspace_bytes(int Bq, int H);
 void lstm_set_trace(long long* buf);     // debug: phase cycle counters of CTA 0
+void lstm_set_exchange(int mode);        // debug: 0 tagged 64-bit words, 1 per-CTA release flags
 void lstm_force_streaming(int on);       // debug: disable the weight-resident kernel
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
                    int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st);
@@ -79,5 +80,12 @@ int build_xmul(const float* vis, const float* lang, float* out, void* out_lp, in
 int lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const long long* srl_msk,
               const long long* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl, int nppf2,
               int K, int ncmp, int nppf, int nfrm0, int spat, cudaStream_t st);
+
+int lang_embed(const long long* words, int nwords, const long long* mask, int T, const float* emb, int E,
+               long long pad_idx, int Bq, void* out_lp, int lp_kind, cudaStream_t st);
+int lang_gather(const float* full, int D, const long long* cap, int T, int Bq, int nsrl, void* out_lp, int lp_kind,
+                cudaStream_t st);
+int mask_rows(const float* x, const long long* msk, int rows, int D, float* out, void* out_lp, int lp_kind,
+              cudaStream_t st);
 
 }  // namespace vog

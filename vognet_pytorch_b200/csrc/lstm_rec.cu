@@ -23,6 +23,7 @@ namespace vog {
 constexpr int LS_THREADS = 512;
 constexpr int LS_MAXB = 8;          // sequences per launch
 constexpr int LS_MAXU = 16;         // hidden units per CTA
+constexpr int LS_WS_HEADER = 1024;  // workspace header: barrier counters / per-CTA flags
 
 struct LstmParams {
     const float* gx; long long ldg;       // [T*Bq, ldg]; direction d at columns d*4H
@@ -196,13 +197,20 @@ lstm_rec_kernel(const LstmParams p)
 // -------------------------------------------------------------------------------------------------
 constexpr int LR_H = 1024;
 constexpr int LR_NI = LR_H / 128;          // float4 per gate row per lane
-constexpr int LR_NREG = 3;                 // of which register resident
 constexpr int LR_MAXU = 14;                // warps (= hidden units) per CTA
 constexpr int LR_THREADS = 32 * LR_MAXU;   // 448 threads
 constexpr int LR_PB = 5;                   // 16-byte exchange loads in flight per thread
 
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ ulonglong2 ld_relaxed_u64x2(const unsigned long long* p) {
     ulonglong2 v;
@@ -228,7 +236,9 @@ struct LstmResParams {
     const float* gx; long long ldg;
     const float* whh;
     const long long* lens;
-    unsigned long long* hx;               // [2 parity, 2 dir, Bq, H] {value, tag}
+    unsigned long long* hx;               // [2 parity, 2 dir, Bq, H] {value, tag} (xmode 0) / fp32 values (xmode 1)
+    unsigned* flags;                      // [2 dir * ctas_per_dir] last published step + 1 (xmode 1)
+    int xmode;
     void* out_lp; long long ld_out; int lp_kind;
     int T, Bq, U, ctas_per_dir;
     long long* trace;                     // debug: [8] accumulated clock64 phases of CTA 0 / thread 0
@@ -255,11 +265,16 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[V], int lane) {
     return r;
 }
 
+// float4 per gate row per lane that stay in registers (the rest lives in shared memory): bounded by the
+// 128-register budget of a 448-thread CTA on one side and by 227 KB of shared memory on the other
+template <int BQ> struct LrCfg { static constexpr int NREG = BQ <= 4 ? 2 : 3; };
+
 template <int BQ>
 __global__ void __launch_bounds__(LR_THREADS, 1)
 lstm_rec_resident_kernel(const LstmResParams p)
 {
     constexpr int H = LR_H;
+    constexpr int LR_NREG = LrCfg<BQ>::NREG;
     constexpr int V = 4 * BQ;
     extern __shared__ __align__(16) float sm[];
     const int NT = blockDim.x;                               // 32 * U
@@ -309,10 +324,14 @@ lstm_rec_resident_kernel(const LstmResParams p)
     const int npairs = Bq * H / 2;                           // exchange words travel in pairs
     const int NP = (npairs + NT - 1) / NT;                   // pairs per thread
     float c_reg = 0.f, h_reg = 0.f;                          // cell / hidden state of (unit u, sequence lane)
+#ifdef VOG_LSTM_TRACE      // build with -DVOG_LSTM_TRACE for the clock64 phase breakdown (profiles/lstm_trace.py)
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
     long long tc[5] = {0, 0, 0, 0, 0};
     long long tprev = tr ? clock64() : 0;
 #define LR_TRACE(i) if (tr) { const long long tn = clock64(); tc[i] += tn - tprev; tprev = tn; }
+#else
+#define LR_TRACE(i)
+#endif
 
     for (int step = 0; step < Tmax; ++step) {
         const int t = d == 0 ? step : Tmax - 1 - step;
@@ -390,15 +409,47 @@ lstm_rec_resident_kernel(const LstmResParams p)
                 hval = go * tanhf(c_reg);
                 h_reg = hval;
             }
-            if (step + 1 < Tmax)
-                st_relaxed_u64(p.hx + (((size_t)(step & 1) * 2 + d) * Bq + lane) * H + u,
-                               ((unsigned long long)(unsigned)(step + 1) << 32) | __float_as_uint(h_reg));
+            if (step + 1 < Tmax) {
+                const size_t xi = (((size_t)(step & 1) * 2 + d) * Bq + lane) * H + u;
+                if (p.xmode == 0)
+                    st_relaxed_u64(p.hx + xi, ((unsigned long long)(unsigned)(step + 1) << 32) | __float_as_uint(h_reg));
+                else
+                    __stcg(reinterpret_cast<float*>(p.hx) + xi, h_reg);
+            }
             store_lp(p.out_lp, ((long long)t * Bq + lane) * p.ld_out + (long long)d * H + u, hval, p.lp_kind);
         }
         __syncwarp();
         LR_TRACE(2)
+        if (step + 1 < Tmax && p.xmode == 1) {
+            // ---- flag exchange: plain fp32 values + one release flag per producer CTA; consumers poll the
+            //      <= 74 flags of their direction (little L2 traffic), then read the values once
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                st_relaxed_u32(p.flags + blockIdx.x, (unsigned)(step + 1));
+            }
+            if (tid < p.ctas_per_dir) {
+                const unsigned* f = p.flags + d * p.ctas_per_dir + tid;
+                long long t0 = 0;
+                while (ld_acquire_u32(f) < (unsigned)(step + 1)) {
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > 4000000000LL) {
+                        printf("vog: lstm flag timeout block %d step %d\n", (int)blockIdx.x, step);
+                        __trap();
+                    }
+                }
+            }
+            LR_TRACE(3)
+            __syncthreads();
+            const float4* src4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.hx) +
+                                                                 ((size_t)(step & 1) * 2 + d) * Bq * H);
+            float4* hn4 = reinterpret_cast<float4*>(h_s + ((step + 1) & 1) * BQ * H);
+            for (int i = tid; i < Bq * H / 4; i += NT) hn4[i] = __ldcg(src4 + i);
+            __syncthreads();
+            LR_TRACE(4)
+        }
         // ---- collect h_t of the whole direction: poll the tagged words
-        if (step + 1 < Tmax) {
+        if (step + 1 < Tmax && p.xmode == 0) {
             const unsigned long long* src = p.hx + ((size_t)(step & 1) * 2 + d) * Bq * H;
             float* hnext = h_s + ((step + 1) & 1) * BQ * H;
             const unsigned want = (unsigned)(step + 1);
@@ -407,19 +458,19 @@ lstm_rec_resident_kernel(const LstmResParams p)
             // LR_PB pairs in flight per thread: normally the whole share of a thread is one batch
             for (int q0 = 0; q0 < NP; q0 += LR_PB) {
                 ulonglong2 w[LR_PB];
-                bool pending = true;
-                while (pending) {
-                    pending = false;
+                unsigned pend = 0;                            // bit k: pair k of this batch not yet complete
 #pragma unroll
-                    for (int k = 0; k < LR_PB; ++k) {
-                        const int q = (q0 + k) * NT + tid;
-                        if (q0 + k < NP && q < npairs) w[k] = ld_relaxed_u64x2(src + 2 * (size_t)q);
-                        else w[k] = make_ulonglong2((unsigned long long)want << 32, (unsigned long long)want << 32);
-                    }
+                for (int k = 0; k < LR_PB; ++k)
+                    if (q0 + k < NP && (q0 + k) * NT + tid < npairs) pend |= 1u << k;
+                while (pend) {                                // only the words still missing are re-read
 #pragma unroll
                     for (int k = 0; k < LR_PB; ++k)
-                        pending |= ((unsigned)(w[k].x >> 32) != want) | ((unsigned)(w[k].y >> 32) != want);
-                    if (pending) {
+                        if (pend & (1u << k)) w[k] = ld_relaxed_u64x2(src + 2 * (size_t)((q0 + k) * NT + tid));
+#pragma unroll
+                    for (int k = 0; k < LR_PB; ++k)
+                        if ((pend & (1u << k)) && (unsigned)(w[k].x >> 32) == want && (unsigned)(w[k].y >> 32) == want)
+                            pend &= ~(1u << k);
+                    if (pend) {
                         if (t0 == 0) t0 = clock64();
                         else if (clock64() - t0 > 4000000000LL) {
                             printf("vog: lstm h-exchange timeout block %d step %d\n", (int)blockIdx.x, step);
@@ -440,7 +491,9 @@ lstm_rec_resident_kernel(const LstmResParams p)
             LR_TRACE(4)
         }
     }
+#ifdef VOG_LSTM_TRACE
     if (tr) { for (int i = 0; i < 5; ++i) p.trace[i] = tc[i]; p.trace[5] = Tmax; }
+#endif
     // rows past the longest sentence: zeros (pad_packed_sequence padding_value=0)
     if (lane < Bq && unit_ok)
         for (int t = Tmax; t < p.T; ++t)
@@ -450,20 +503,22 @@ lstm_rec_resident_kernel(const LstmResParams p)
 template <int BQ>
 static int launch_resident(const LstmResParams& p, int ctas, int threads, cudaStream_t st)
 {
-    const size_t smem = (size_t)4 * (LR_NI - LR_NREG) * threads * 16 + (size_t)2 * BQ * LR_H * 4 + (size_t)LR_MAXU * 4 * BQ * 4;
+    const size_t smem = (size_t)4 * (LR_NI - LrCfg<BQ>::NREG) * threads * 16 + (size_t)2 * BQ * LR_H * 4 + (size_t)LR_MAXU * 4 * BQ * 4;
     VOG_CUDA(cudaFuncSetAttribute(lstm_rec_resident_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lstm_rec_resident_kernel<BQ><<<ctas, threads, smem, st>>>(p);
     return check_launch("lstm_rec_resident");
 }
 
 static int g_lstm_force_streaming = 0;
+static int g_lstm_xmode = 0;
+void lstm_set_exchange(int mode) { g_lstm_xmode = mode ? 1 : 0; }
 static long long* g_lstm_trace = nullptr;
 void lstm_set_trace(long long* buf) { g_lstm_trace = buf; }
 void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
 
 long long lstm_workspace_bytes(int Bq, int H)
 {
-    return (long long)2 * 2 * Bq * H * 8 + 64;        // tagged 64-bit exchange words (resident kernel)
+    return (long long)2 * 2 * Bq * H * 8 + LS_WS_HEADER;   // header (counters / flags) + exchange words
 }
 
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
@@ -485,7 +540,10 @@ int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long 
         const int per_dir_u = cdiv(H, U);
         LstmResParams rp;
         rp.gx = gx; rp.ldg = ldg; rp.whh = whh; rp.lens = lens;
-        rp.hx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 64);
+        rp.hx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + LS_WS_HEADER);
+        rp.flags = reinterpret_cast<unsigned*>(workspace);
+        rp.xmode = g_lstm_xmode;
+        VOG_REQUIRE(2 * per_dir_u * 4 <= LS_WS_HEADER, "lstm_layer_fwd: too many CTAs for the flag header");
         rp.out_lp = out_lp; rp.ld_out = ld_out; rp.lp_kind = lp_kind;
         rp.T = T; rp.Bq = Bq; rp.U = U; rp.ctas_per_dir = per_dir_u;
         rp.trace = g_lstm_trace;
@@ -505,7 +563,7 @@ int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long 
     LstmParams p;
     p.gx = gx; p.ldg = ldg; p.whh = whh; p.lens = lens;
     p.counters = reinterpret_cast<unsigned*>(workspace);
-    p.hbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 64);
+    p.hbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + LS_WS_HEADER);
     p.out_lp = out_lp; p.ld_out = ld_out; p.lp_kind = lp_kind;
     p.T = T; p.Bq = Bq; p.H = H; p.U = U; p.ctas_per_dir = per_dir;
     VOG_CUDA(cudaMemsetAsync(workspace, 0, 64, st));

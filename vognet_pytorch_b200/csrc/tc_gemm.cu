@@ -244,6 +244,10 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& p
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     dst[(size_t)(c0 + j) * pe.npad] = __float2bfloat16_rn(__uint_as_float(cur[j]));
+                if (ii == pe.seq_n - 1)                       // the sequence's last token zero-fills the key padding
+                    for (int e = 1; e < pe.npad - pe.seq_n + 1; ++e)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[(size_t)(c0 + j) * pe.npad + e] = __float2bfloat16_rn(0.f);
             }
         }
         return;
@@ -340,6 +344,10 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
                         d[(size_t)(4 * j4 + 2) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 2] + l[j4].z);
                         d[(size_t)(4 * j4 + 3) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 3] + l[j4].w);
                     }
+                    if (s_ == pe.nsrl - 1 && pp == pe.nppf2 - 1)   // last token of the sequence: zero the key padding
+                        for (int e = 1; e < pe.npad - pe.seq_n + 1; ++e)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) d[(size_t)j * pe.npad + e] = __float2bfloat16_rn(0.f);
                 }
             }
         }

@@ -223,6 +223,8 @@ int64_t vog_lstm_workspace_bytes(int Bq, int H) { return lstm_workspace_bytes(Bq
 
 /* debug / A-B testing: 1 = always use the weight-streaming recurrence kernel */
 void vog_debug_lstm_force_streaming(int on) { vog::lstm_force_streaming(on); }
+/* A/B switch of the h_t exchange of the weight-resident kernel: 0 = tagged 64-bit words, 1 = per-CTA flags */
+void vog_debug_lstm_exchange(int mode) { vog::lstm_set_exchange(mode); }
 /* debug: device buffer of 8 int64: accumulated clock64 cycles of CTA 0 in {matvec, reduce, cell + publish,
  * poll, barrier} and the step count of the weight-resident recurrence kernel */
 void vog_debug_lstm_trace(void* buf) { vog::lstm_set_trace((long long*)buf); }
@@ -258,6 +260,37 @@ int vog_lin2_tail(const float* h, int ldh, const float* w2, const float* b2, con
                 "vog_lin2_tail: inconsistent frame/proposal grouping");
     return lin2_tail(h, ldh, w2, b2, (const long long*)srl_msk, (const long long*)cmp_msk, logits, scores, B, nfrm,
                      nsrl, nppf2, K, ncmp, nppf, nfrm0, spat, (cudaStream_t)stream);
+}
+
+int vog_lang_embed(const int64_t* words, int nwords, const int64_t* mask, int T, const float* emb, int E,
+                   int64_t pad_idx, int Bq, void* out_lp, int lp_kind, void* stream)
+{
+    VOG_REQUIRE(T >= 0 && Bq >= 0 && nwords > 0 && E > 0, "vog_lang_embed: bad dimension");
+    if (T * Bq == 0) return 0;
+    VOG_REQUIRE(words && mask && emb && out_lp, "vog_lang_embed: null operand");
+    VOG_REQUIRE(lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_lang_embed: bad lp_kind");
+    return lang_embed((const long long*)words, nwords, (const long long*)mask, T, emb, E, pad_idx, Bq, out_lp,
+                      lp_kind, (cudaStream_t)stream);
+}
+
+int vog_lang_gather(const float* full, int D, const int64_t* cap, int T, int Bq, int nsrl, void* out_lp,
+                    int lp_kind, void* stream)
+{
+    VOG_REQUIRE(T > 0 && Bq >= 0 && nsrl >= 0 && D > 0, "vog_lang_gather: bad dimension");
+    if (Bq * nsrl == 0) return 0;
+    VOG_REQUIRE(full && cap && out_lp, "vog_lang_gather: null operand");
+    VOG_REQUIRE(lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_lang_gather: bad lp_kind");
+    return lang_gather(full, D, (const long long*)cap, T, Bq, nsrl, out_lp, lp_kind, (cudaStream_t)stream);
+}
+
+int vog_mask_rows(const float* x, const int64_t* msk, int rows, int D, float* out, void* out_lp, int lp_kind,
+                  void* stream)
+{
+    VOG_REQUIRE(rows >= 0 && D > 0, "vog_mask_rows: bad dimension");
+    if (rows == 0) return 0;
+    VOG_REQUIRE(x && msk && out, "vog_mask_rows: null operand");
+    VOG_REQUIRE(!out_lp || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_mask_rows: bad lp_kind");
+    return mask_rows(x, (const long long*)msk, rows, D, out, out_lp, lp_kind, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -171,30 +171,25 @@ class VOGNetB200(nn.Module):
         words = inp['srl_arg_words_ind']
         B, nv, nsrl, L = words.shape
         Bq = B * nv
-        flat = words.reshape(Bq, nsrl * L)
         wm = inp['srl_arg_word_mask'].reshape(Bq, -1)
-        pad = wm == -1
-        toks = torch.gather(flat, 1, wm.masked_fill(pad, 0)).masked_fill(pad, self.vocab_size)
-        T = toks.shape[1]
+        T = wm.shape[1]
         lens = inp['srl_arg_word_mask_len'].reshape(Bq).contiguous()
-        emb = self.lstm_encoder.embed_tokens(toks.t().contiguous()).reshape(T * Bq, -1)   # time-major rows
-        x_lp = ops.cast_lp(emb, kind)
+        # token gather + embedding lookup + cast, time-major rows (one kernel)
+        x_lp = ops.lang_embed(words.reshape(Bq, nsrl * L), wm, self.lstm_encoder.embed_tokens.weight,
+                              self.vocab_size, kind)
         for wih_lp, bias, whh in self._lang_weights(kind):
             gx, _ = ops.tc_gemm(x_lp, wih_lp, bias=bias)
             x_lp = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, kind)
         full, _ = ops.tc_gemm(x_lp, self._lp_weight('lstm_proj', self.lstm_out_feat_proj[0].weight, kind),
                               bias=self.lstm_out_feat_proj[0].bias, relu=True)               # [T*Bq, le]
         D = full.shape[-1]
-        full = full.view(T, Bq, D)
-        cap = inp['srl_arg_words_capture'].reshape(Bq, nsrl, 2)
-        bidx = torch.arange(Bq, device=full.device).view(Bq, 1).expand(Bq, nsrl)
-        st = full[cap[..., 0], bidx]                                     # [Bq, nsrl, D]
-        en = full[cap[..., 1], bidx]
-        cat = torch.cat([st, en], 2).reshape(Bq * nsrl, 2 * D)
-        enc, _ = ops.tc_gemm(ops.cast_lp(cat, kind),
-                             self._lp_weight('srl_enc', self.srl_arg_words_out_enc[0].weight, kind),
+        # first / last word of every SRL argument, concatenated and cast (one kernel)
+        cat_lp = ops.lang_gather(full, inp['srl_arg_words_capture'].reshape(Bq, nsrl, 2), T, Bq, kind)
+        enc, _ = ops.tc_gemm(cat_lp, self._lp_weight('srl_enc', self.srl_arg_words_out_enc[0].weight, kind),
                              bias=self.srl_arg_words_out_enc[0].bias, relu=True)
-        enc = enc.view(Bq, nsrl, D) * inp['srl_arg_inds_msk'].reshape(Bq, nsrl, 1).float()
+        # srl_arg_inds_msk product + the low-precision copy the multimodal transformer consumes (one kernel)
+        enc, enc_lp = ops.mask_rows(enc, inp['srl_arg_inds_msk'].reshape(Bq * nsrl), kind)
+        self._lang_lp = enc_lp
         return enc.view(B, nv * nsrl, D)
 
     # -----------------------------------------------------------------------------------------
@@ -294,7 +289,10 @@ class VOGNetB200(nn.Module):
                 a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
                                    self.vid_w, self.vid_h, float(nfrm))
                 bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
-            ft = FactoredTokens(x.contiguous(), x_lp, lang2, ops.cast_lp(lang2, kind), nfrm, nsrl, nppf2)
+            lang_lp = self.__dict__.pop('_lang_lp', None)       # produced next to `lang` by language_encode_tc
+            if lang_lp is None or lang_lp.shape != lang2.shape:
+                lang_lp = ops.cast_lp(lang2, kind)
+            ft = FactoredTokens(x.contiguous(), x_lp, lang2, lang_lp, nfrm, nsrl, nppf2)
             xm, xm_lp = self.mult_txf._exec.run_factored(ft, bias, self.compute, need_f32=False)
         else:
             xm, xm_lp = ops.build_xmul(x.contiguous(), lang2, B, nfrm, nsrl, nppf2, kind)

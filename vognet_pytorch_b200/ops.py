@@ -178,11 +178,30 @@ def _is_tf32(a, w):
     return int(a.dtype == torch.float32)
 
 
-def pick_bn(N):
-    for bn in (256, 192, 128, 64, 32):
-        if N % bn == 0:
+_SMS = {}
+
+
+def _num_sms(device):
+    idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if idx not in _SMS:
+        _SMS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SMS[idx]
+
+
+def pick_bn(N, M=None, sms=148):
+    """Column-tile width of the tcgen05 GEMM: the largest divisor of N in {256,192,128,64,32} that still
+    yields enough 128 x BN tiles to occupy most SMs (small-M problems get narrow tiles instead of split-K
+    partials + a second reduction launch); plain divisibility when M is unknown."""
+    cands = [bn for bn in (256, 192, 128, 64, 32) if N % bn == 0]
+    if not cands:
+        return 128 if N > 64 else (64 if N > 32 else 32)
+    if M is None:
+        return cands[0]
+    mblk = -(-M // 128)
+    for bn in cands:
+        if mblk * (N // bn) >= 0.6 * sms:
             return bn
-    return 128 if N > 64 else (64 if N > 32 else 32)
+    return cands[-1]
 
 
 def tc_gemm(a, w, bias=None, residual=None, relu=False, out_f32=None, out_lp=None, lp_kind=LP_NONE,
@@ -208,7 +227,7 @@ def tc_gemm(a, w, bias=None, residual=None, relu=False, out_f32=None, out_lp=Non
     if bias is not None:
         _req(bias, torch.float32, 'bias', 1)
     L = _lib.lib()
-    BN = BN or pick_bn(N)
+    BN = BN or pick_bn(N, M, _num_sms(a.device))
     ws, ws_bytes = None, L.vog_tc_gemm_workspace_bytes(M, N, K, tf32, BN)
     if ws_bytes:
         ws = torch.empty(ws_bytes, device=a.device, dtype=torch.uint8)
@@ -232,8 +251,7 @@ def tc_gemm_qkv(a, wqkv, Bt, N, n_heads, dhp):
     npad = round_up(N, 8)
     q = torch.empty(Bt, n_heads, N, dhp, device=a.device, dtype=torch.bfloat16)
     k = torch.empty_like(q)
-    vt = torch.zeros(Bt, n_heads, dhp, npad, device=a.device, dtype=torch.bfloat16) if npad != N else \
-        torch.empty(Bt, n_heads, dhp, npad, device=a.device, dtype=torch.bfloat16)
+    vt = torch.empty(Bt, n_heads, dhp, npad, device=a.device, dtype=torch.bfloat16)   # key padding zeroed by the kernel
     L = _lib.lib()
     _lib.check(L.vog_tc_gemm_qkv(_ptr(a), _rowmajor2d(a, 'a'), _ptr(wqkv), _rowmajor2d(wqkv, 'wqkv'), M, K,
                                  tf32, n_heads, dhp, N, npad, _ptr(q), _ptr(k), _ptr(vt), _stream()),
@@ -255,8 +273,7 @@ def tc_gemm_qkv_factored(vis_lp, wqkv_vis, lq, Bt, nfrm, nsrl, nppf2, n_heads, d
     npad = round_up(N, 8)
     q = torch.empty(Bt, n_heads, N, dhp, device=vis_lp.device, dtype=torch.bfloat16)
     k = torch.empty_like(q)
-    vt = torch.zeros(Bt, n_heads, dhp, npad, device=vis_lp.device, dtype=torch.bfloat16) if npad != N else \
-        torch.empty(Bt, n_heads, dhp, npad, device=vis_lp.device, dtype=torch.bfloat16)
+    vt = torch.empty(Bt, n_heads, dhp, npad, device=vis_lp.device, dtype=torch.bfloat16)  # key padding zeroed by the kernel
     L = _lib.lib()
     _lib.check(L.vog_tc_gemm_qkv_factored(_ptr(vis_lp), _rowmajor2d(vis_lp, 'vis_lp'), _ptr(wqkv_vis),
                                           _rowmajor2d(wqkv_vis, 'wqkv_vis'), M, K, tf32, n_heads, dhp, _ptr(lq),
@@ -279,7 +296,9 @@ def tc_gemm_gres(a, w, res_vis, res_lang, nfrm, nsrl, nppf2, bias=None, relu=Fal
     out_lp = torch.empty(M, N, device=a.device, dtype=_LP_DTYPE[lp_kind]) if lp_kind != LP_NONE else None
     if bias is not None:
         _req(bias, torch.float32, 'bias', 1)
-    BN = BN or pick_bn(N)
+    BN = BN or pick_bn(N, M, _num_sms(a.device))
+    if dv % BN:
+        BN = pick_bn(N)
     L = _lib.lib()
     _lib.check(L.vog_tc_gemm_gres(_ptr(a), _rowmajor2d(a, 'a'), _ptr(w), _rowmajor2d(w, 'w'), M, N, K, tf32, BN,
                                   _ptr(bias), int(relu), _ptr(res_vis), _rowmajor2d(res_vis, 'res_vis'),
@@ -341,6 +360,42 @@ def lstm_layer_fwd(gx, whh, lens, T, Bq, kind):
                                         _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _stream()),
                    'vog_lstm_layer_fwd')
     return out
+
+
+def lang_embed(words, mask, emb, pad_idx, kind):
+    """words [Bq,nwords] int64, mask [Bq,T] int64 (-1 = pad), emb [V+1,E] fp32 -> x_lp [T*Bq, E] time-major."""
+    _req(words, torch.int64, 'words', 2), _req(mask, torch.int64, 'mask', 2), _req(emb, torch.float32, 'emb', 2)
+    words, mask, emb = words.contiguous(), mask.contiguous(), emb.contiguous()
+    Bq, T = mask.shape
+    out = torch.empty(T * Bq, emb.shape[1], device=emb.device, dtype=_LP_DTYPE[kind])
+    L = _lib.lib()
+    _lib.check(L.vog_lang_embed(_ptr(words), words.shape[1], _ptr(mask), T, _ptr(emb), emb.shape[1], int(pad_idx),
+                                Bq, _ptr(out), kind, _stream()), 'vog_lang_embed')
+    return out
+
+
+def lang_gather(full, cap, T, Bq, kind):
+    """full [T*Bq, D] fp32 time-major, cap [Bq,nsrl,2] int64 -> [Bq*nsrl, 2D] low precision."""
+    _req(full, torch.float32, 'full', 2), _req(cap, torch.int64, 'cap', 3)
+    full, cap = full.contiguous(), cap.contiguous()
+    D, nsrl = full.shape[1], cap.shape[1]
+    out = torch.empty(Bq * nsrl, 2 * D, device=full.device, dtype=_LP_DTYPE[kind])
+    L = _lib.lib()
+    _lib.check(L.vog_lang_gather(_ptr(full), D, _ptr(cap), T, Bq, nsrl, _ptr(out), kind, _stream()),
+               'vog_lang_gather')
+    return out
+
+
+def mask_rows(x, msk, kind=LP_NONE):
+    """x [rows, D] fp32, msk [rows] int64 -> x * msk (fp32) and, if kind is given, its low-precision copy."""
+    _req(x, torch.float32, 'x', 2), _req(msk, torch.int64, 'msk', 1)
+    x, msk = x.contiguous(), msk.contiguous()
+    out = torch.empty_like(x)
+    out_lp = torch.empty(x.shape, device=x.device, dtype=_LP_DTYPE[kind]) if kind != LP_NONE else None
+    L = _lib.lib()
+    _lib.check(L.vog_mask_rows(_ptr(x), _ptr(msk), x.shape[0], x.shape[1], _ptr(out), _ptr(out_lp), kind,
+                               _stream()), 'vog_mask_rows')
+    return out, out_lp
 
 
 def build_xmul(vis, lang, B, nfrm, nsrl, nppf2, kind):
