@@ -287,7 +287,7 @@ def main():
         g = torch.Generator(device='cpu').manual_seed(0)
         q = (torch.rand(Bt, 3, N, dhp, generator=g) - 0.5).bfloat16().to(dev)
         k = (torch.rand(Bt, 3, N, dhp, generator=g) - 0.5).bfloat16().to(dev)
-        vt = (torch.rand(Bt, 3, dhp, ops.round_up(N, 8), generator=g) - 0.5).bfloat16().to(dev)
+        vt = (torch.rand(Bt, 3, N, dhp, generator=g) - 0.5).bfloat16().to(dev)
         nbox = N // 5 if N % 5 == 0 else N
         a = torch.rand(Bt * nbox, 3, generator=g).to(dev)
         bpe = torch.zeros(3, device=dev)

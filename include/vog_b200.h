@@ -104,25 +104,24 @@ int vog_tc_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, i
                 void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Fused Q/K/V projection: A[M,K] . Wqkv[3*H*dhp, K]^T with Wqkv = per-head zero-padded rows of
- * wq|wk|wv (dhp = head dim rounded up to 64).  Writes bf16 Q,K as [Bt,H,seq_n,dhp] and V
- * TRANSPOSED as [Bt,H,dhp,npad] (M = Bt*seq_n), the layouts vog_tc_attn_fwd consumes.
+ * wq|wk|wv (dhp = head dim rounded up to 64).  Writes bf16 Q, K and V as [Bt,H,seq_n,dhp]
+ * (M = Bt*seq_n), the layouts vog_tc_attn_fwd consumes (V as an MN-major tcgen05 operand).
  * replaces wq/wk/wv + chunk: code/transformer_code.py:180-183. */
 int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, int M, int K,
-                    int tf32, int n_heads, int dhp, int seq_n, int npad, void* q, void* k, void* vt,
-                    void* stream);
+                    int tf32, int n_heads, int dhp, int seq_n, void* q, void* k, void* v, void* stream);
 
 /* Fused attention, all heads and sequences in one launch (tcgen05 QK^T and PV, online softmax with
  * on-the-fly relative-position bias; the N x N matrices never reach HBM):
  *   out[bt*N+i, h*dhp+c] = sum_j softmax_j((q_i.k_j + bias_h(i,j)) * inv_scale) v_j[c]
- * q,k [Bt,H,N,dhp] bf16, vt [Bt,H,dhp,npad] bf16 (vog_tc_gemm_qkv layouts), dh[H] true head dims
+ * q,k,v [Bt,H,N,dhp] bf16 (vog_tc_gemm_qkv layouts), dh[H] true head dims
  * (host array), bias as in vog_attn_fwd_f32 (a, bpe, dense are device pointers).  out is
  * [Bt*N, ldo >= H*dhp], bf16 (out_kind VOG_LP_BF16) or tf32-rounded fp32 (VOG_LP_TF32); padded
  * head columns are written as zeros.  VOG_BIAS_RANK1 needs a workspace of
  * vog_tc_attn_workspace_bytes() bytes (per-key bias factors expanded to [Bt*H, N] by a small
  * pre-kernel).  Same reference lines as vog_attn_fwd_f32. */
 int64_t vog_tc_attn_workspace_bytes(int Bt, int N, int H);
-int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp,
-                    int npad, const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
+int vog_tc_attn_fwd(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
+                    const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
                     const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -131,13 +130,13 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
  * 693-699), so W.token = W[:, :dv].vis + W[:, dv:].lang: A [M = Bt*nppf2, K = dv] holds the VISUAL rows
  * only, Wvis = the first dv columns of the packed Wq|Wk|Wv (row stride ldw), lq [B*nsrl, ldq >= 3*H*dhp]
  * fp32 the separately projected language rows (a [B*nsrl x dl] GEMM through vog_tc_gemm).  The epilogue
- * writes every accumulator row nsrl times, adding lq[b*nsrl + s]: q,k [Bt,H,nsrl*nppf2,dhp] bf16 and
- * vt [Bt,H,dhp,npad] exactly as vog_tc_gemm_qkv would from the materialised [vis|lang] matrix - with
+ * writes every accumulator row nsrl times, adding lq[b*nsrl + s]: q,k,v [Bt,H,nsrl*nppf2,dhp] bf16
+ * exactly as vog_tc_gemm_qkv would from the materialised [vis|lang] matrix - with
  * nsrl x fewer MMA FLOPs and without that matrix.  replaces concate_vis_lang_feats + regroup + wq/wk/wv:
  * code/mdl_vog.py:316-344,693-699, code/transformer_code.py:180. */
 int vog_tc_gemm_qkv_factored(const void* A, int64_t lda, const void* Wvis, int64_t ldw, int M, int K,
                              int tf32, int n_heads, int dhp, const float* lq, int64_t ldq, int nfrm,
-                             int nsrl, int nppf2, int npad, void* q, void* k, void* vt, void* stream);
+                             int nsrl, int nppf2, void* q, void* k, void* v, void* stream);
 
 /* vog_tc_gemm with a GATHERED fp32 residual: the residual row of token m = (bt, s, p) is
  * [res_vis[bt*nppf2 + p, 0:dv] | res_lang[(bt / nfrm)*nsrl + s, 0:N-dv]] - the multimodal transformer's

@@ -14,7 +14,7 @@ for Bt, N, d in ((40, 2000, 768), (4, 4000, 512)):
     hd = ops.chunk_sizes(d, 3); dhp = ops.round_up(max(hd), 64)
     q = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
     k = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
-    vt = (torch.rand(Bt, 3, dhp, ops.round_up(N, 8), device=dev) - 0.5).bfloat16()
+    vt = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
     nbox = N // 5
     a = torch.rand(Bt * nbox, 3, device=dev); bpe = torch.zeros(3, device=dev)
     buf = torch.zeros(16, dtype=torch.int64, device=dev)

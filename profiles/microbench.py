@@ -51,7 +51,7 @@ def attn_case(name, Bt, N, d, H=3):
     dhp = ops.round_up(max(hd), 64)
     q = (torch.rand(Bt, H, N, dhp, device=dev) - 0.5).bfloat16()
     k = (torch.rand(Bt, H, N, dhp, device=dev) - 0.5).bfloat16()
-    vt = (torch.rand(Bt, H, dhp, ops.round_up(N, 8), device=dev) - 0.5).bfloat16()
+    vt = (torch.rand(Bt, H, N, dhp, device=dev) - 0.5).bfloat16()
     nbox = N // 5 if N % 5 == 0 else N
     a = torch.rand(Bt * nbox, H, device=dev)
     bpe = torch.zeros(H, device=dev)

@@ -29,7 +29,7 @@ elif what == 'attn':
     dhp = ops.round_up(max(hd), 64)
     q = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
     k = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
-    vt = (torch.rand(Bt, 3, dhp, ops.round_up(N, 8), device=dev) - 0.5).bfloat16()
+    vt = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
     nbox = N // 5 if N % 5 == 0 else N
     a = torch.rand(Bt * nbox, 3, device=dev)
     bpe = torch.zeros(3, device=dev)

@@ -18,21 +18,15 @@ def _u(shape, seed, lo=-1.0, hi=1.0):
     return torch.rand(*shape, generator=g) * (hi - lo) + lo
 
 
-def _pack(x, Bt, N, hd, dhp, transpose=False):
-    """[Bt*N, d] fp32 -> bf16 [Bt,H,N,dhp] (or [Bt,H,dhp,Npad])"""
+def _pack(x, Bt, N, hd, dhp):
+    """[Bt*N, d] fp32 -> bf16 [Bt,H,N,dhp]"""
     H = len(hd)
     out = torch.zeros(Bt, H, N, dhp)
     off = 0
     for h, dh in enumerate(hd):
         out[:, h, :, :dh] = x.view(Bt, N, -1)[:, :, off:off + dh]
         off += dh
-    out = out.bfloat16()
-    if transpose:
-        npad = ops.round_up(N, 8)
-        t = torch.zeros(Bt, H, dhp, npad, dtype=torch.bfloat16)
-        t[..., :N] = out.transpose(2, 3)
-        return t
-    return out
+    return out.bfloat16()
 
 
 def _ref(qp, kp, vp, N, hd, scale, bias):
@@ -42,7 +36,7 @@ def _ref(qp, kp, vp, N, hd, scale, bias):
     if bias is not None:
         s = s + bias.permute(0, 3, 1, 2).double()
     p = torch.softmax(s * scale, -1)
-    o = p @ vp.double()[..., :N].transpose(2, 3)             # [Bt,H,N,dhp]
+    o = p @ vp.double()                                      # [Bt,H,N,dhp]
     return o.permute(0, 2, 1, 3)
 
 
@@ -67,7 +61,7 @@ def test_tc_attention(Bt, N, d, H, mode, gain, out_kind):
     hd = ops.chunk_sizes(d, H)
     dhp = ops.round_up(max(hd), 64)
     q, k, v = _u((Bt * N, d), 7) * gain, _u((Bt * N, d), 8), _u((Bt * N, d), 9)
-    qp, kp, vtp = _pack(q, Bt, N, hd, dhp), _pack(k, Bt, N, hd, dhp), _pack(v, Bt, N, hd, dhp, True)
+    qp, kp, vtp = _pack(q, Bt, N, hd, dhp), _pack(k, Bt, N, hd, dhp), _pack(v, Bt, N, hd, dhp)
     nbox = N if N < 20 else (N // 5 if N % 5 == 0 else N)
     a = _u((Bt * nbox, H), 10, -30, 30)
     bpe = _u((H,), 11, -3, 3)
@@ -99,7 +93,7 @@ def test_tc_attention_monotone_logits_force_rescale():
     q = torch.ones(N, d)
     k = (torch.arange(N).float().view(N, 1) / N * 16 - 8).expand(N, d).contiguous()   # logits -512..512 /8
     v = _u((N, d), 13)
-    qp, kp, vtp = _pack(q, Bt, N, hd, dhp), _pack(k, Bt, N, hd, dhp), _pack(v, Bt, N, hd, dhp, True)
+    qp, kp, vtp = _pack(q, Bt, N, hd, dhp), _pack(k, Bt, N, hd, dhp), _pack(v, Bt, N, hd, dhp)
     scale = 1.0 / 2.0
     ref = _ref(qp, kp, vtp, N, hd, scale, None)
     out = ops.tc_attn_fwd(qp.to(DEV), kp.to(DEV), vtp.to(DEV), N, hd, scale)

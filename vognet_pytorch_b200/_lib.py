@@ -52,13 +52,13 @@ _SIGNATURES = {
     'vog_debug_attn_prof': [P],
     'vog_lstm_layer_fwd': [P, c_i64, P, P, c_int, c_int, c_int, P, c_i64, c_int, P, P],
     'vog_tc_attn_workspace_bytes': [c_int, c_int, c_int],
-    'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,
+    'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,
                         c_i64, c_int, P, c_i64, P],
     'vog_tc_gemm_qkv_factored': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_i64, c_int, c_int,
-                                 c_int, c_int, P, P, P, P],
+                                 c_int, P, P, P, P],
     'vog_tc_gemm_gres': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64, P, c_i64,
                          c_int, c_int, c_int, c_int, P, c_i64, P, c_i64, c_int, P],
-    'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
+    'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
 }
 _RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong,
             'vog_tc_gemm_workspace_bytes': ctypes.c_int64, 'vog_lstm_workspace_bytes': ctypes.c_int64,

@@ -36,8 +36,8 @@ struct TcEpilogue {
     int rep = 1;                  // every output row m is written to rows m*rep .. m*rep+rep-1
     // mode 1: column block n_blk = which*H + h (BN == dhp); rows m = bt*seq_n + i
     __nv_bfloat16* q = nullptr; __nv_bfloat16* k = nullptr;   // [Bt,H,seq_n,dhp]
-    __nv_bfloat16* vt = nullptr;                              // [Bt,H,dhp,npad]
-    int seq_n = 0, n_heads = 0, dhp = 0, npad = 0;
+    __nv_bfloat16* v = nullptr;                               // [Bt,H,seq_n,dhp] (natural layout, like K)
+    int seq_n = 0, n_heads = 0, dhp = 0;
     // mode 2: FACTORISED QKV projection of the multimodal transformer.  A token (bt, s, p) of sequence
     // bt = b*nfrm + f is [vis[bt*nppf2 + p] | lang[b*nsrl + s]], so W.token = W[:, :dv].vis + W[:, dv:].lang:
     // the GEMM runs over the VISUAL rows only (m = bt*nppf2 + p) and its epilogue writes every row
@@ -57,7 +57,7 @@ long long tc_gemm_workspace_bytes(int M, int N, int K, int tf32, int BN);
 int num_sms();
 void tc_gemm_set_trace(long long* buf);  // debug: 8 clock64 stamps of CTA 0
 // ---- tc_attn.cu : fused relative-position-bias attention (tcgen05) ---------------------------
-int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
+int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
             const float* dense, void* out, long long ldo, int out_kind, void* workspace,
             long long workspace_bytes, cudaStream_t st);

@@ -9,7 +9,8 @@
 // (code/mdl_vog.py:477-488, utils/mdl_srl_utils.py:30-69): the N x N score / probability / bias
 // matrices never exist in HBM.
 //
-//   warp 0      TMA producer: Q tile once, then a ring of {K_j [64 keys x dhp], V^T_j [dhp x 64 keys]}
+//   warp 0      TMA producer: Q tile once, then rings of K_j and V_j tiles ([64 keys x dhp] each; V is
+//               consumed in its natural layout as an MN-major B operand of the PV MMA - no transposed copy)
 //               stages; its idle lanes stage the rank-1 bias factor a_j of the 64 keys next to them
 //   warp 1      single-thread tcgen05.mma issuer:  S_j = Q K_j^T  (128 x 64, TMEM, double buffered)
 //               and O += P_j V_j (128 x dh, TMEM); S_{j+1} is issued before P_j is awaited so the
@@ -18,8 +19,8 @@
 //               softmax with LAZY rescaling of the TMEM accumulator (only when a row max grows by
 //               more than 2^8), P written as bf16 into a 128B-swizzled smem tile that feeds the PV MMA
 //
-// Layouts (produced by vog_tc_gemm_qkv): Q,K [Bt,H,N,dhp] bf16, V^T [Bt,H,dhp,Npad] bf16, head dim
-// zero-padded to dhp (multiple of 64).  Output [Bt*N, H*dhp] (bf16, or tf32-rounded fp32), heads
+// Layouts (produced by vog_tc_gemm_qkv): Q,K,V [Bt,H,N,dhp] bf16, head dim zero-padded to dhp
+// (multiple of 64); key rows beyond N are zero-filled by TMA.  Output [Bt*N, H*dhp] (bf16, or tf32-rounded fp32), heads
 // side by side in padded slots - the A operand of the (column-padded) Wo GEMM.
 #include "common.cuh"
 #include "kernels.h"
@@ -36,7 +37,7 @@ constexpr int FA_MAX_STAGES = 8;
 constexpr float FA_RESCALE_T = 8.0f;   // log2 units
 
 struct AttnParams {
-    int Bt, N, H, dhp, npad;
+    int Bt, N, H, dhp;
     int dh[VOG_MAX_HEADS];
     float c;                    // log2(e) / sqrt(d_model)
     int bias_mode;              // 0 none, 1 rank-1, 2 dense
@@ -58,7 +59,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
 tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-               const __grid_constant__ CUtensorMap tma_vt, const AttnParams p)
+               const __grid_constant__ CUtensorMap tma_v, const AttnParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -75,7 +76,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     // ---- shared memory carve-up (all tile bases 1024-aligned)
     const uint32_t q_bytes = FA_BQ * dhp * 2;
     const uint32_t k_bytes = FA_BKV * dhp * 2;        // nkk sub-tiles of [64 rows x 128 B]
-    const uint32_t v_bytes = dhp * 128;               // [dhp rows x 128 B]
+    const uint32_t v_bytes = FA_BKV * dhp * 2;        // nkk sub-tiles of [64 keys x 128 B] (64 head-dim columns each)
     // K and V^T live in SEPARATE rings: a K slot is released as soon as S_j = Q K_j^T has been
     // computed (one whole softmax earlier than the V slot, which PV_j still needs), so the next K
     // tile is requested early enough for its L2 latency to hide behind the softmax of tile j
@@ -104,7 +105,7 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tma_q);
         tma_prefetch_desc(&tma_k);
-        tma_prefetch_desc(&tma_vt);
+        tma_prefetch_desc(&tma_v);
         for (int s = 0; s < NS; ++s) {
             mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
             mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
@@ -161,7 +162,9 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                 const int s = jv % NS;
                 if (lane == 0) {
                     mbar_arrive_expect_tx(v_full(s), v_bytes);
-                    tma_load_3d(v_smem0 + s * v_bytes, &tma_vt, v_full(s), jv * FA_BKV, 0, bh);
+                    for (int kk = 0; kk < nkk; ++kk)
+                        tma_load_3d(v_smem0 + s * v_bytes + kk * (FA_BKV * 128), &tma_v, v_full(s), kk * 64,
+                                    jv * FA_BKV, bh);
                 }
                 ++jv;
             }
@@ -172,7 +175,10 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc(FMT_BF16, FA_BQ, FA_BKV);
             const int n_pv = (dh + 15) & ~15;
-            const uint32_t idesc_o = umma_idesc(FMT_BF16, FA_BQ, n_pv);
+            // B = V tile in its natural [key][head-dim] layout = MN-major: 8-key x 128 B swizzle atoms, the next
+            // 8 keys 1024 B further (SBO), the next 64 head-dim columns one [64 x 128 B] sub-tile further (LBO)
+            const uint32_t idesc_o = umma_idesc(FMT_BF16, FA_BQ, n_pv) | (1u << 16);
+            const uint32_t v_lbo = ((uint32_t)(FA_BKV * 128) >> 4) << 16;
             const int ksteps = (dh + 15) / 16;           // skip the all-zero padded tail of the head dim
 #ifdef VOG_ATTN_PROFILE
             const bool mprof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -212,12 +218,12 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
                 tc_fence_after();
                 VOG_MPROF(2)
                 const uint32_t pa_lo = umma_desc_lo(p_smem0 + pb * (FA_BQ * 128));
-                const uint32_t vb_lo = umma_desc_lo(v_smem0 + s * v_bytes);
+                const uint32_t vb_lo = (((v_smem0 + s * v_bytes) >> 4) & 0x3FFF) | v_lbo;
                 if (j == 0) umma_bf16_lo<false>(tmem_o, pa_lo, vb_lo, idesc_o);
                 else umma_bf16_lo<true>(tmem_o, pa_lo, vb_lo, idesc_o);
 #pragma unroll
-                for (int k4 = 1; k4 < 4; ++k4)
-                    umma_bf16_lo<true>(tmem_o, pa_lo + 2 * k4, vb_lo + 2 * k4, idesc_o);
+                for (int k4 = 1; k4 < 4; ++k4)         // 16 keys = two 8-key atoms = 2048 B further per step
+                    umma_bf16_lo<true>(tmem_o, pa_lo + 2 * k4, vb_lo + k4 * (2048 >> 4), idesc_o);
                 umma_commit(v_empty(s));
                 umma_commit(p_empty(pb));
                 VOG_MPROF(3)
@@ -445,7 +451,7 @@ long long tc_attn_workspace_bytes(int Bt, int N, int H)
 static long long* g_attn_prof = nullptr;
 void tc_attn_set_prof(long long* buf) { g_attn_prof = buf; }
 
-int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
+int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
             const float* dense, void* out, long long ldo, int out_kind, void* workspace,
             long long workspace_bytes, cudaStream_t st)
@@ -453,7 +459,6 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     if (Bt == 0 || N == 0) return 0;
     VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS, "tc_attn: H=%d out of range", H);
     VOG_REQUIRE(dhp == 64 || dhp == 128 || dhp == 192 || dhp == 256, "tc_attn: dhp=%d must be 64/128/192/256", dhp);
-    VOG_REQUIRE(npad >= N && npad % 8 == 0, "tc_attn: npad=%d must be >= N and a multiple of 8", npad);
     VOG_REQUIRE(Bt <= 65535 && H <= 65535, "tc_attn: grid too large");
     VOG_REQUIRE(out_kind == 1 || out_kind == 2, "tc_attn: bad out_kind");
     VOG_REQUIRE(ldo >= (long long)H * dhp && (ldo * (out_kind == 1 ? 2 : 4)) % 16 == 0, "tc_attn: bad ldo");
@@ -461,7 +466,7 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     VOG_REQUIRE(bias_mode != 1 || (a && bpe && nbox > 0), "tc_attn: rank-1 bias needs a, bpe, nbox");
     VOG_REQUIRE(bias_mode != 2 || dense, "tc_attn: dense bias pointer missing");
     AttnParams p;
-    p.Bt = Bt; p.N = N; p.H = H; p.dhp = dhp; p.npad = npad;
+    p.Bt = Bt; p.N = N; p.H = H; p.dhp = dhp;
     for (int h = 0; h < H; ++h) {
         VOG_REQUIRE(dh[h] >= 1 && dh[h] <= dhp, "tc_attn: head dim %d does not fit dhp=%d", dh[h], dhp);
         p.dh[h] = dh[h];
@@ -491,10 +496,7 @@ int tc_attn(const void* q, const void* k, const void* vt, int Bt, int N, int H, 
     uint32_t bq[3] = {64, FA_BQ, 1}, bk[3] = {64, FA_BKV, 1};
     if (make_tmap(&tq, q, 2, 1, 3, dq, sq, bq)) return -1;
     if (make_tmap(&tk, k, 2, 1, 3, dq, sq, bk)) return -1;
-    uint64_t dv[3] = {(uint64_t)npad, (uint64_t)dhp, BH};
-    uint64_t sv[2] = {(uint64_t)npad * 2, (uint64_t)dhp * npad * 2};
-    uint32_t bv[3] = {64, (uint32_t)dhp, 1};
-    if (make_tmap(&tv, vt, 2, 1, 3, dv, sv, bv)) return -1;
+    if (make_tmap(&tv, v, 2, 1, 3, dq, sq, bk)) return -1;
 
     const int fixed = FA_BQ * dhp * 2 + 2 * FA_BQ * 128 + 384 /*barriers*/ + 2 * FA_BQ * 2 * 4 /*pair exchange*/;
     const int stage_bytes = 2 * FA_BKV * dhp * 2;                  // one K slot + one V^T slot

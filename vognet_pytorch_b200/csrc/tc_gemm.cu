@@ -216,44 +216,17 @@ __device__ __forceinline__ void epi_fast(const GemmParams& p, const TcEpilogue& 
     }
 }
 
-// EPI_QKV: column block n_blk = which*H + h (BN == dhp).  Q / K go through the transpose patch and
-// are written as [Bt,H,N,dhp] bf16 rows (64 B row segments); V is written TRANSPOSED ([Bt,H,dhp,Npad])
-// straight from registers: lanes are consecutive tokens, so every store instruction is one 64 B run
+// EPI_QKV: column block n_blk = which*H + h (BN == dhp).  Q, K and V all go through the transpose patch
+// and are written as [Bt,H,N,dhp] bf16 rows (64 B row segments per lane group); the attention kernel takes
+// V in this natural layout as an MN-major tcgen05 operand, so no transposed copy is ever produced
 __device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
                                         uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane)
 {
     const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
     const int m0 = m_blk * GM_BM + 32 * g;
     uint32_t r[32];
-    if (which == 2) {
-        const int m = m0 + lane;
-        const bool ok = m < p.M;
-        const int bt = ok ? m / pe.seq_n : 0, ii = ok ? m % pe.seq_n : 0;
-        __nv_bfloat16* dst = pe.vt + (((size_t)bt * pe.n_heads + h) * pe.dhp) * pe.npad + ii;
-        mbar_wait(tfull, parity);
-        tc_fence_after();
-        tmem_ld32(t_acc, r);
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-            tmem_wait_ld();
-            uint32_t cur[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = r[j];
-            if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
-            if (ok) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    dst[(size_t)(c0 + j) * pe.npad] = __float2bfloat16_rn(__uint_as_float(cur[j]));
-                if (ii == pe.seq_n - 1)                       // the sequence's last token zero-fills the key padding
-                    for (int e = 1; e < pe.npad - pe.seq_n + 1; ++e)
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[(size_t)(c0 + j) * pe.npad + e] = __float2bfloat16_rn(0.f);
-            }
-        }
-        return;
-    }
     const int r_in = lane >> 3, c4 = lane & 7;
-    __nv_bfloat16* base = which == 0 ? pe.q : pe.k;
+    __nv_bfloat16* base = which == 0 ? pe.q : (which == 1 ? pe.k : pe.v);
     __nv_bfloat16* dst[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -310,51 +283,8 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
         epi_bar();
     }
     uint32_t r[32];
-    if (which == 2) {
-        const int m = m0 + lane;
-        const bool ok = m < p.M;
-        const int bt = ok ? m / pe.nppf2 : 0, pp = ok ? m % pe.nppf2 : 0;
-        const int b = bt / pe.nfrm;
-        const float* lrow = lqs ? lqs + (size_t)(b - b0) * pe.nsrl * p.BN
-                                : pe.lq + (size_t)b * pe.nsrl * pe.ldq + colbase;
-        const size_t lstep = lqs ? (size_t)p.BN : (size_t)pe.ldq;
-        __nv_bfloat16* dst = pe.vt + (((size_t)bt * pe.n_heads + h) * pe.dhp) * pe.npad + pp;
-        mbar_wait(tfull, parity);
-        tc_fence_after();
-        tmem_ld32(t_acc, r);
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-            tmem_wait_ld();
-            float cur[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cur[j] = __uint_as_float(r[j]);
-            if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
-            if (ok) {
-#pragma unroll 1
-                for (int s_ = 0; s_ < pe.nsrl; ++s_) {
-                    const float4* lq4 = reinterpret_cast<const float4*>(lrow + s_ * lstep + c0);
-                    __nv_bfloat16* d = dst + (size_t)c0 * pe.npad + s_ * pe.nppf2;
-                    float4 l[8];
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) l[j4] = lq4[j4];
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        d[(size_t)(4 * j4 + 0) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 0] + l[j4].x);
-                        d[(size_t)(4 * j4 + 1) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 1] + l[j4].y);
-                        d[(size_t)(4 * j4 + 2) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 2] + l[j4].z);
-                        d[(size_t)(4 * j4 + 3) * pe.npad] = __float2bfloat16_rn(cur[4 * j4 + 3] + l[j4].w);
-                    }
-                    if (s_ == pe.nsrl - 1 && pp == pe.nppf2 - 1)   // last token of the sequence: zero the key padding
-                        for (int e = 1; e < pe.npad - pe.seq_n + 1; ++e)
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) d[(size_t)j * pe.npad + e] = __float2bfloat16_rn(0.f);
-                }
-            }
-        }
-        return;
-    }
     const int r_in = lane >> 3, c4 = lane & 7;
-    __nv_bfloat16* base = which == 0 ? pe.q : pe.k;
+    __nv_bfloat16* base = which == 0 ? pe.q : (which == 1 ? pe.k : pe.v);
     __nv_bfloat16* dst[8];
     const float* lqi[8];
 #pragma unroll
@@ -665,7 +595,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     VOG_REQUIRE(epi.rep >= 1, "tc_gemm: rep must be >= 1");
     if (epi.mode == 1 || epi.mode == 2) {
         VOG_REQUIRE(BN == epi.dhp && N == 3 * epi.n_heads * epi.dhp, "tc_gemm: qkv epilogue needs BN == dhp, N == 3*H*dhp");
-        VOG_REQUIRE(epi.q && epi.k && epi.vt && epi.seq_n > 0 && epi.npad >= epi.seq_n, "tc_gemm: bad qkv epilogue");
+        VOG_REQUIRE(epi.q && epi.k && epi.v && epi.seq_n > 0, "tc_gemm: bad qkv epilogue");
         if (epi.mode == 2) {
             VOG_REQUIRE(epi.lq && epi.nsrl > 0 && epi.nppf2 > 0 && epi.nfrm > 0 && epi.seq_n == epi.nsrl * epi.nppf2 &&
                         M % epi.nppf2 == 0 && (M / epi.nppf2) % epi.nfrm == 0,

@@ -140,34 +140,33 @@ int vog_tc_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, i
 }
 
 int vog_tc_gemm_qkv(const void* A, int64_t lda, const void* Wqkv, int64_t ldw, int M, int K, int tf32,
-                    int n_heads, int dhp, int seq_n, int npad, void* q, void* k, void* vt, void* stream)
+                    int n_heads, int dhp, int seq_n, void* q, void* k, void* v, void* stream)
 {
     VOG_REQUIRE(M >= 0 && K > 0 && n_heads >= 1 && n_heads <= VOG_MAX_HEADS, "vog_tc_gemm_qkv: bad dimension");
     if (M == 0) return 0;
     if (require_sm100("vog_tc_gemm_qkv")) return -1;
-    VOG_REQUIRE(A && Wqkv && q && k && vt, "vog_tc_gemm_qkv: null operand");
+    VOG_REQUIRE(A && Wqkv && q && k && v, "vog_tc_gemm_qkv: null operand");
     VOG_REQUIRE(dhp % 64 == 0 && dhp <= 256, "vog_tc_gemm_qkv: dhp=%d must be 64/128/192/256", dhp);
-    VOG_REQUIRE(seq_n > 0 && M % seq_n == 0 && npad >= seq_n && npad % 8 == 0, "vog_tc_gemm_qkv: bad sequence geometry");
+    VOG_REQUIRE(seq_n > 0 && M % seq_n == 0, "vog_tc_gemm_qkv: bad sequence geometry");
     TcEpilogue e;
-    e.mode = 1; e.q = (__nv_bfloat16*)q; e.k = (__nv_bfloat16*)k; e.vt = (__nv_bfloat16*)vt;
-    e.seq_n = seq_n; e.n_heads = n_heads; e.dhp = dhp; e.npad = npad;
+    e.mode = 1; e.q = (__nv_bfloat16*)q; e.k = (__nv_bfloat16*)k; e.v = (__nv_bfloat16*)v;
+    e.seq_n = seq_n; e.n_heads = n_heads; e.dhp = dhp;
     return tc_gemm(A, lda, Wqkv, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
 
 int vog_tc_gemm_qkv_factored(const void* A, int64_t lda, const void* Wvis, int64_t ldw, int M, int K, int tf32,
                              int n_heads, int dhp, const float* lq, int64_t ldq, int nfrm, int nsrl, int nppf2,
-                             int npad, void* q, void* k, void* vt, void* stream)
+                             void* q, void* k, void* v, void* stream)
 {
     VOG_REQUIRE(M >= 0 && K > 0 && n_heads >= 1 && n_heads <= VOG_MAX_HEADS, "vog_tc_gemm_qkv_factored: bad dimension");
     if (M == 0) return 0;
     if (require_sm100("vog_tc_gemm_qkv_factored")) return -1;
-    VOG_REQUIRE(A && Wvis && lq && q && k && vt, "vog_tc_gemm_qkv_factored: null operand");
+    VOG_REQUIRE(A && Wvis && lq && q && k && v, "vog_tc_gemm_qkv_factored: null operand");
     VOG_REQUIRE(dhp % 64 == 0 && dhp <= 256, "vog_tc_gemm_qkv_factored: dhp=%d must be 64/128/192/256", dhp);
-    VOG_REQUIRE(nfrm > 0 && nsrl > 0 && nppf2 > 0 && npad >= nsrl * nppf2 && npad % 8 == 0,
-                "vog_tc_gemm_qkv_factored: bad sequence geometry");
+    VOG_REQUIRE(nfrm > 0 && nsrl > 0 && nppf2 > 0, "vog_tc_gemm_qkv_factored: bad sequence geometry");
     TcEpilogue e;
-    e.mode = 2; e.q = (__nv_bfloat16*)q; e.k = (__nv_bfloat16*)k; e.vt = (__nv_bfloat16*)vt;
-    e.seq_n = nsrl * nppf2; e.n_heads = n_heads; e.dhp = dhp; e.npad = npad;
+    e.mode = 2; e.q = (__nv_bfloat16*)q; e.k = (__nv_bfloat16*)k; e.v = (__nv_bfloat16*)v;
+    e.seq_n = nsrl * nppf2; e.n_heads = n_heads; e.dhp = dhp;
     e.lq = lq; e.ldq = ldq; e.nsrl = nsrl; e.nppf2 = nppf2; e.nfrm = nfrm;
     return tc_gemm(A, lda, Wvis, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
@@ -205,7 +204,7 @@ int64_t vog_tc_attn_workspace_bytes(int Bt, int N, int H)
     return tc_attn_workspace_bytes(Bt, N, H);
 }
 
-int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N, int H, int dhp, int npad,
+int vog_tc_attn_fwd(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
                     const int* dh, float inv_scale, int bias_mode, const float* a, int nbox,
                     const float* bpe, const float* dense, void* out, int64_t ldo, int out_kind,
                     void* workspace, int64_t workspace_bytes, void* stream)
@@ -213,9 +212,9 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* vt, int Bt, int N,
     VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_tc_attn_fwd: negative dimension");
     if (Bt == 0 || N == 0) return 0;
     if (require_sm100("vog_tc_attn_fwd")) return -1;
-    VOG_REQUIRE(q && k && vt && out && dh, "vog_tc_attn_fwd: null operand");
+    VOG_REQUIRE(q && k && v && out && dh, "vog_tc_attn_fwd: null operand");
     VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_tc_attn_fwd: bad bias_mode %d", bias_mode);
-    return tc_attn(q, k, vt, Bt, N, H, dhp, npad, dh, inv_scale, bias_mode, a, nbox, bpe, dense, out, ldo,
+    return tc_attn(q, k, v, Bt, N, H, dhp, dh, inv_scale, bias_mode, a, nbox, bpe, dense, out, ldo,
                    out_kind, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

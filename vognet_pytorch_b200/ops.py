@@ -244,25 +244,23 @@ def round_up(a, b):
 
 
 def tc_gemm_qkv(a, wqkv, Bt, N, n_heads, dhp):
-    """-> q,k [Bt,H,N,dhp] bf16 and vt [Bt,H,dhp,Npad] bf16 (Npad = N rounded up to 8)."""
+    """-> q,k,v [Bt,H,N,dhp] bf16."""
     tf32 = _is_tf32(a, wqkv)
     M, K = a.shape
     assert M == Bt * N and wqkv.shape == (3 * n_heads * dhp, K)
-    npad = round_up(N, 8)
     q = torch.empty(Bt, n_heads, N, dhp, device=a.device, dtype=torch.bfloat16)
-    k = torch.empty_like(q)
-    vt = torch.empty(Bt, n_heads, dhp, npad, device=a.device, dtype=torch.bfloat16)   # key padding zeroed by the kernel
+    k, v = torch.empty_like(q), torch.empty_like(q)
     L = _lib.lib()
     _lib.check(L.vog_tc_gemm_qkv(_ptr(a), _rowmajor2d(a, 'a'), _ptr(wqkv), _rowmajor2d(wqkv, 'wqkv'), M, K,
-                                 tf32, n_heads, dhp, N, npad, _ptr(q), _ptr(k), _ptr(vt), _stream()),
+                                 tf32, n_heads, dhp, N, _ptr(q), _ptr(k), _ptr(v), _stream()),
                'vog_tc_gemm_qkv')
-    return q, k, vt
+    return q, k, v
 
 
 def tc_gemm_qkv_factored(vis_lp, wqkv_vis, lq, Bt, nfrm, nsrl, nppf2, n_heads, dhp):
     """Factorised QKV projection (see vog_tc_gemm_qkv_factored): vis_lp [Bt*nppf2, dv] low precision,
     wqkv_vis [3*H*dhp, dv] (a column-slice view of the packed weight is fine), lq [B*nsrl, 3*H*dhp] fp32
-    -> q,k [Bt,H,nsrl*nppf2,dhp] bf16 and vt [Bt,H,dhp,Npad] bf16."""
+    -> q,k,v [Bt,H,nsrl*nppf2,dhp] bf16."""
     tf32 = _is_tf32(vis_lp, wqkv_vis)
     M, K = vis_lp.shape
     _req(lq, torch.float32, 'lq', 2)
@@ -270,16 +268,14 @@ def tc_gemm_qkv_factored(vis_lp, wqkv_vis, lq, Bt, nfrm, nsrl, nppf2, n_heads, d
     if M != Bt * nppf2 or wqkv_vis.shape != (3 * n_heads * dhp, K) or Bt % nfrm != 0 or \
             lq.shape != ((Bt // nfrm) * nsrl, 3 * n_heads * dhp):
         raise ValueError('tc_gemm_qkv_factored: inconsistent shapes')
-    npad = round_up(N, 8)
     q = torch.empty(Bt, n_heads, N, dhp, device=vis_lp.device, dtype=torch.bfloat16)
-    k = torch.empty_like(q)
-    vt = torch.empty(Bt, n_heads, dhp, npad, device=vis_lp.device, dtype=torch.bfloat16)  # key padding zeroed by the kernel
+    k, v = torch.empty_like(q), torch.empty_like(q)
     L = _lib.lib()
     _lib.check(L.vog_tc_gemm_qkv_factored(_ptr(vis_lp), _rowmajor2d(vis_lp, 'vis_lp'), _ptr(wqkv_vis),
                                           _rowmajor2d(wqkv_vis, 'wqkv_vis'), M, K, tf32, n_heads, dhp, _ptr(lq),
-                                          _rowmajor2d(lq, 'lq'), nfrm, nsrl, nppf2, npad, _ptr(q), _ptr(k),
-                                          _ptr(vt), _stream()), 'vog_tc_gemm_qkv_factored')
-    return q, k, vt
+                                          _rowmajor2d(lq, 'lq'), nfrm, nsrl, nppf2, _ptr(q), _ptr(k),
+                                          _ptr(v), _stream()), 'vog_tc_gemm_qkv_factored')
+    return q, k, v
 
 
 def tc_gemm_gres(a, w, res_vis, res_lang, nfrm, nsrl, nppf2, bias=None, relu=False, lp_kind=LP_NONE,
@@ -309,16 +305,15 @@ def tc_gemm_gres(a, w, res_vis, res_lang, nfrm, nsrl, nppf2, bias=None, relu=Fal
     return out_f32, out_lp
 
 
-def tc_attn_fwd(q, k, vt, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, bias_mode=BIAS_NONE,
+def tc_attn_fwd(q, k, v, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, bias_mode=BIAS_NONE,
                 a=None, nbox=0, bpe=None, dense=None):
-    """q,k [Bt,H,N,dhp], vt [Bt,H,dhp,Npad] bf16 -> out [Bt*N, H*dhp] (bf16 or tf32-rounded fp32)."""
-    for t, n in ((q, 'q'), (k, 'k'), (vt, 'vt')):
+    """q,k,v [Bt,H,N,dhp] bf16 -> out [Bt*N, H*dhp] (bf16 or tf32-rounded fp32)."""
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
         _req(t, torch.bfloat16, n, 4)
         if not t.is_contiguous():
             raise ValueError(f'tc_attn_fwd: {n} must be contiguous')
     Bt, H, Nq, dhp = q.shape
-    npad = vt.shape[3]
-    if Nq != N or k.shape != q.shape or vt.shape[:3] != (Bt, H, dhp) or len(head_dims) != H:
+    if Nq != N or k.shape != q.shape or v.shape != q.shape or len(head_dims) != H:
         raise ValueError('tc_attn_fwd: inconsistent shapes')
     if out is None:
         out = torch.empty(Bt * N, H * dhp, device=q.device, dtype=_LP_DTYPE[out_kind])
@@ -336,7 +331,7 @@ def tc_attn_fwd(q, k, vt, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, b
     if bias_mode == BIAS_RANK1:
         ws_bytes = L.vog_tc_attn_workspace_bytes(Bt, N, H)
         ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
-    _lib.check(L.vog_tc_attn_fwd(_ptr(q), _ptr(k), _ptr(vt), Bt, N, H, dhp, npad, dh_arr, float(inv_scale),
+    _lib.check(L.vog_tc_attn_fwd(_ptr(q), _ptr(k), _ptr(v), Bt, N, H, dhp, dh_arr, float(inv_scale),
                                  bias_mode, _ptr(a), nbox, _ptr(bpe), _ptr(dense), _ptr(out),
                                  _rowmajor2d(out, 'out'), out_kind, _ptr(ws), ws_bytes, _stream()),
                'vog_tc_attn_fwd')

@@ -211,11 +211,11 @@ class EncoderExecutor:
             if fact:
                 dv = ft.vis.shape[1]
                 lq, _ = ops.tc_gemm(ft.lang_lp, w['wqkv'][:, dv:])          # language rows projected once
-                q, k, vt = ops.tc_gemm_qkv_factored(ft.vis_lp, w['wqkv'][:, :dv], lq, Bt, ft.nfrm, ft.nsrl,
+                q, k, v = ops.tc_gemm_qkv_factored(ft.vis_lp, w['wqkv'][:, :dv], lq, Bt, ft.nfrm, ft.nsrl,
                                                     ft.nppf2, H, dhp)
             else:
-                q, k, vt = ops.tc_gemm_qkv(x_lp, w['wqkv'], Bt, N, H, dhp)
-            o_lp = ops.tc_attn_fwd(q, k, vt, N, self.head_dims, inv_scale, out_kind=kind, **bkw)
+                q, k, v = ops.tc_gemm_qkv(x_lp, w['wqkv'], Bt, N, H, dhp)
+            o_lp = ops.tc_attn_fwd(q, k, v, N, self.head_dims, inv_scale, out_kind=kind, **bkw)
             if fact:
                 pre, _ = ops.tc_gemm_gres(o_lp, w['wo'], ft.vis, ft.lang, ft.nfrm, ft.nsrl, ft.nppf2)
             else:
