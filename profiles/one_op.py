@@ -35,5 +35,25 @@ elif what == 'attn':
     bpe = torch.zeros(3, device=dev)
     for _ in range(4):
         ops.tc_attn_fwd(q, k, vt, N, hd, 1.0 / d ** 0.5, bias_mode=ops.BIAS_RANK1, a=a, nbox=nbox, bpe=bpe)
+elif what == 'qkvf':                       # factorised mul_tx QKV at spat/p100: B=4, nfrm=10, nsrl=5, nppf2=400
+    B, nfrm, nsrl, nppf2 = [int(v) for v in sys.argv[2:6]]
+    kind = ops.LP_TF32 if 'tf32' in sys.argv else ops.LP_BF16
+    Bt = B * nfrm
+    vis = ops.cast_lp(torch.rand(Bt * nppf2, 512, device=dev) - 0.5, kind)
+    lq = torch.rand(B * nsrl, 2304, device=dev) - 0.5
+    w = ops.cast_lp((torch.rand(2304, 768, device=dev) - 0.5) * 0.05, kind)
+    for _ in range(4):
+        ops.tc_gemm_qkv_factored(vis, w[:, :512], lq, Bt, nfrm, nsrl, nppf2, 3, 256)
+elif what == 'gres':                       # mul_tx wo GEMM with the gathered [vis|lang] residual
+    B, nfrm, nsrl, nppf2 = [int(v) for v in sys.argv[2:6]]
+    kind = ops.LP_TF32 if 'tf32' in sys.argv else ops.LP_BF16
+    Bt = B * nfrm
+    M = Bt * nsrl * nppf2
+    a = ops.cast_lp(torch.rand(M, 768, device=dev) - 0.5, kind)
+    w = ops.cast_lp((torch.rand(768, 768, device=dev) - 0.5) * 0.05, kind)
+    vis = torch.rand(Bt * nppf2, 512, device=dev)
+    lang = torch.rand(B * nsrl, 256, device=dev)
+    for _ in range(4):
+        ops.tc_gemm_gres(a, w, vis, lang, nfrm, nsrl, nppf2)
 torch.cuda.synchronize()
 print('done')

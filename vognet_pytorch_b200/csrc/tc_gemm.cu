@@ -30,10 +30,11 @@ namespace vog {
 using namespace tc;
 
 constexpr int GM_BM = 128;
-constexpr int GM_THREADS = 192;
+constexpr int GM_EPI_WARPS = 8;                    // two per TMEM lane quarter: they split the column chunks
+constexpr int GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 constexpr int GM_MAX_STAGES = 8;
 constexpr int GM_A_BYTES = GM_BM * 128;
-constexpr int GM_EPI_BYTES = 4 * 32 * 32 * 4;      // one 32x32 fp32 patch per epilogue warp
+constexpr int GM_EPI_BYTES = GM_EPI_WARPS * 32 * 32 * 4;      // one 32x32 fp32 patch per epilogue warp
 
 struct GemmParams {
     int M, N, K, BN;
@@ -136,8 +137,8 @@ __device__ __forceinline__ float4 patch_load(const float* patch, int row, int c4
 // float4 traffic, bias / residual of the next chunk prefetched while the current one is stored - the
 // first chunk even before the accumulator is ready - so their latency hides behind the MMAs
 __device__ __forceinline__ void epi_fast(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
-                                         uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane,
-                                         bool trace)
+                                         uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int half,
+                                         int lane, bool trace)
 {
     const int r_in = lane >> 3, c4 = lane & 7;
     const int m0 = m_blk * GM_BM + 32 * g;
@@ -181,36 +182,66 @@ __device__ __forceinline__ void epi_fast(const GemmParams& p, const TcEpilogue& 
         }
         if (biasp) b4 = __ldg(reinterpret_cast<const float4*>(biasp + c0));
     };
-    prefetch(0);
+    const int cfirst = 32 * half;                               // this warp's chunks: cfirst, cfirst + 64, ...
+    if (cfirst < p.BN) prefetch(cfirst);
     mbar_wait(tfull, parity);
     tc_fence_after();
     if (trace) GM_TRACE(5);
     uint32_t r[32];
-    tmem_ld32(t_acc, r);
+    if (cfirst < p.BN) tmem_ld32(t_acc + cfirst, r);
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    for (int c0 = cfirst; c0 < p.BN; c0 += 64) {
         tmem_wait_ld();
         patch_store(patch, lane, r);
-        if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);       // in flight while this chunk is stored
         __syncwarp();
-        float4 cur[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = res[i];
         const float4 bc = b4;
-        if (c0 + 32 < p.BN) prefetch(c0 + 32);
+        const bool more = c0 + 64 < p.BN;
+        if (more && biasp) b4 = __ldg(reinterpret_cast<const float4*>(biasp + c0 + 64));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int row = i * 4 + r_in;
             float4 v = patch_load(patch, row, c4);
-            if (row < rows) {
-                v.x += bc.x; v.y += bc.y; v.z += bc.z; v.w += bc.w;
-                if (pe.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                v.x += cur[i].x; v.y += cur[i].y; v.z += cur[i].z; v.w += cur[i].w;
-                if (o32) *reinterpret_cast<float4*>(o32 + i * o32_step + c0) = v;
-                if (obf) *reinterpret_cast<uint2*>(obf + i * lp_step + c0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                if (otf) *reinterpret_cast<float4*>(otf + i * lp_step + c0) =
-                    make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-            }
+            const bool ok = row < rows;                        // guards single memory instructions -> predication, no branches
+            v.x += bc.x; v.y += bc.y; v.z += bc.z; v.w += bc.w;
+            if (pe.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
+            // this row's residual for the NEXT chunk is requested as soon as the current one is consumed
+            if (has_res && more && ok) res[i] = __ldg(reinterpret_cast<const float4*>(rp[i] + c0 + 64));
+            if (o32 && ok) *reinterpret_cast<float4*>(o32 + i * o32_step + c0) = v;
+            if (obf && ok) *reinterpret_cast<uint2*>(obf + i * lp_step + c0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            if (otf && ok) *reinterpret_cast<float4*>(otf + i * lp_step + c0) =
+                make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        }
+        if (c0 + 64 < p.BN) tmem_ld32(t_acc + c0 + 64, r);       // r is dead during the stores: fewer live registers
+        __syncwarp();
+    }
+}
+
+// split-K partial tile: raw fp32 accumulator rows into partial[split][M][N] (N % BN == 0, 16-byte aligned)
+__device__ __forceinline__ void epi_partial(const GemmParams& p, float* out, float* patch, uint32_t t_acc,
+                                            uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int half,
+                                            int lane)
+{
+    const int r_in = lane >> 3, c4 = lane & 7;
+    const int m0 = m_blk * GM_BM + 32 * g;
+    const int rows = p.M - m0;
+    float* o32 = out + (size_t)(m0 + r_in) * p.N + (size_t)n_blk * p.BN + c4 * 4;
+    const size_t step = 4 * (size_t)p.N;
+    const int cfirst = 32 * half;
+    mbar_wait(tfull, parity);
+    tc_fence_after();
+    uint32_t r[32];
+    if (cfirst < p.BN) tmem_ld32(t_acc + cfirst, r);
+#pragma unroll 1
+    for (int c0 = cfirst; c0 < p.BN; c0 += 64) {
+        tmem_wait_ld();
+        patch_store(patch, lane, r);
+        if (c0 + 64 < p.BN) tmem_ld32(t_acc + c0 + 64, r);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = patch_load(patch, i * 4 + r_in, c4);
+            if (i * 4 + r_in < rows) *reinterpret_cast<float4*>(o32 + i * step + c0) = v;
         }
         __syncwarp();
     }
@@ -220,7 +251,8 @@ __device__ __forceinline__ void epi_fast(const GemmParams& p, const TcEpilogue& 
 // and are written as [Bt,H,N,dhp] bf16 rows (64 B row segments per lane group); the attention kernel takes
 // V in this natural layout as an MN-major tcgen05 operand, so no transposed copy is ever produced
 __device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
-                                        uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane)
+                                        uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int half,
+                                        int lane)
 {
     const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
     const int m0 = m_blk * GM_BM + 32 * g;
@@ -234,19 +266,21 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& p
         const int bt = m / pe.seq_n, ii = m % pe.seq_n;
         dst[i] = m < p.M ? base + (((size_t)bt * pe.n_heads + h) * pe.seq_n + ii) * pe.dhp + c4 * 4 : nullptr;
     }
+    const int cfirst = 32 * half;
     mbar_wait(tfull, parity);
     tc_fence_after();
-    tmem_ld32(t_acc, r);
+    if (cfirst < p.BN) tmem_ld32(t_acc + cfirst, r);
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    for (int c0 = cfirst; c0 < p.BN; c0 += 64) {
         tmem_wait_ld();
         patch_store(patch, lane, r);
-        if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
+        if (c0 + 64 < p.BN) tmem_ld32(t_acc + c0 + 64, r);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float4 v = patch_load(patch, i * 4 + r_in, c4);
-            if (dst[i]) *reinterpret_cast<uint2*>(dst[i] + c0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            const uint2 o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            if (dst[i]) *reinterpret_cast<uint2*>(dst[i] + c0) = o;
         }
         __syncwarp();
     }
@@ -258,11 +292,11 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, const TcEpilogue& p
 // The lq rows this tile needs (<= 2 queries x nsrl slots x BN columns when a query has >= 127 visual
 // rows) are staged in shared memory by the four epilogue warps while the MMAs of the tile run; tiny
 // configurations with more queries per tile read them through L1 instead (lqs == nullptr).
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * GM_EPI_WARPS) : "memory"); }
 
 __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& pe, float* patch, float* lqs,
                                          uint32_t t_acc, uint32_t tfull, uint32_t parity, int m_blk, int n_blk,
-                                         int g, int lane)
+                                         int g, int half, int lane)
 {
     const int which = n_blk / pe.n_heads, h = n_blk % pe.n_heads;
     const int m0 = m_blk * GM_BM + 32 * g;
@@ -273,7 +307,7 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
         const int bn4 = p.BN >> 2;
         const int nvec = 2 * pe.nsrl * bn4;
         epi_bar();                                                // the previous tile's readers are done
-        for (int v = g * 32 + lane; v < nvec; v += 128) {
+        for (int v = (half * 4 + g) * 32 + lane; v < nvec; v += 32 * GM_EPI_WARPS) {
             const int row = v / bn4, c = v - row * bn4;            // row = slot*nsrl + s
             const int b = b0 + row / pe.nsrl;
             if (b < nq)
@@ -299,14 +333,15 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
     }
     const size_t lstep = lqs ? (size_t)p.BN : (size_t)pe.ldq;
     const size_t slot_step = (size_t)pe.nppf2 * pe.dhp;
+    const int cfirst = 32 * half;
     mbar_wait(tfull, parity);
     tc_fence_after();
-    tmem_ld32(t_acc, r);
+    if (cfirst < p.BN) tmem_ld32(t_acc + cfirst, r);
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    for (int c0 = cfirst; c0 < p.BN; c0 += 64) {
         tmem_wait_ld();
         patch_store(patch, lane, r);
-        if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
+        if (c0 + 64 < p.BN) tmem_ld32(t_acc + c0 + 64, r);
         __syncwarp();
         float4 v[8];
 #pragma unroll
@@ -317,10 +352,10 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
 #pragma unroll
             for (int i = 0; i < 8; ++i) l[i] = *reinterpret_cast<const float4*>(lqi[i] + s_ * lstep + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (dst[i])
-                    *reinterpret_cast<uint2*>(dst[i] + s_ * slot_step + c0) =
-                        make_uint2(pack_bf16(v[i].x + l[i].x, v[i].y + l[i].y), pack_bf16(v[i].z + l[i].z, v[i].w + l[i].w));
+            for (int i = 0; i < 8; ++i) {
+                const uint2 o = make_uint2(pack_bf16(v[i].x + l[i].x, v[i].y + l[i].y), pack_bf16(v[i].z + l[i].z, v[i].w + l[i].w));
+                if (dst[i]) *reinterpret_cast<uint2*>(dst[i] + s_ * slot_step + c0) = o;
+            }
         }
         __syncwarp();
     }
@@ -328,7 +363,8 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
 
 // EPI_GENERIC: any N / alignment / row replication (guarded element-wise fallbacks inside)
 __device__ __forceinline__ void epi_generic(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
-                                            uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int lane)
+                                            uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int half,
+                                            int lane)
 {
     const int r_in = lane >> 3, c4 = lane & 7;
     const int m0 = m_blk * GM_BM + 32 * g;
@@ -336,7 +372,7 @@ __device__ __forceinline__ void epi_generic(const GemmParams& p, const TcEpilogu
     tc_fence_after();
     uint32_t r[32];
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    for (int c0 = 32 * half; c0 < p.BN; c0 += 64) {
         tmem_ld32(t_acc + c0, r);
         tmem_wait_ld();
         patch_store(patch, lane, r);
@@ -380,7 +416,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), GM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
@@ -448,26 +484,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __syncwarp();
     } else {
         const int g = warp & 3;                    // TMEM lane quarter this warp may access
-        float* patch = reinterpret_cast<float*>(smem_gen + epi_off) + g * 1024;     // [32 rows][8 float4]
+        const int half = (warp - 2) >> 2;          // which of the quarter's two warps: even / odd 32-column chunks
+        float* patch = reinterpret_cast<float*>(smem_gen + epi_off) + (warp - 2) * 1024;     // [32 rows][8 float4]
+        float* lqs = p.lq_stage ? reinterpret_cast<float*>(smem_gen + epi_off + GM_EPI_BYTES) : nullptr;
         int acc = 0; uint32_t acc_ph = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             int m_blk, n_blk, kb0, kb1;
             const int split = decode(item, m_blk, n_blk, kb0, kb1);
             const uint32_t t_acc = tmem_base + ((uint32_t)(32 * g) << 16) + acc * p.BN;
             const bool trace = item == (int)blockIdx.x && threadIdx.x == 64;
+            const uint32_t tf = tfull_bar(acc);
             if (p.splits > 1) {                    // split-K: raw partials, no epilogue math
-                TcEpilogue pe;
-                pe.out_f32 = p.partial + (size_t)split * p.M * p.N;
-                pe.ldc = p.N;
-                if constexpr (kEpi == EPI_FAST) epi_fast(p, pe, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane, trace);
-                else epi_generic(p, pe, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
+                float* part = p.partial + (size_t)split * p.M * p.N;
+                if constexpr (kEpi == EPI_FAST) {
+                    if (trace) GM_TRACE(5);
+                    epi_partial(p, part, patch, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
+                } else {
+                    TcEpilogue pe;
+                    pe.out_f32 = part;
+                    pe.ldc = p.N;
+                    epi_generic(p, pe, patch, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
+                }
+            } else if constexpr (kEpi == EPI_FAST) {
+                epi_fast(p, p.e, patch, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane, trace);
+            } else if constexpr (kEpi == EPI_QKV) {
+                epi_qkv(p, p.e, patch, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
+            } else if constexpr (kEpi == EPI_QKVF) {
+                epi_qkvf(p, p.e, patch, lqs, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
             } else {
-                if constexpr (kEpi == EPI_FAST) epi_fast(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane, trace);
-                else if constexpr (kEpi == EPI_QKV) epi_qkv(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
-                else if constexpr (kEpi == EPI_QKVF)
-                    epi_qkvf(p, p.e, patch, p.lq_stage ? reinterpret_cast<float*>(smem_gen + epi_off + GM_EPI_BYTES) : nullptr,
-                             t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
-                else epi_generic(p, p.e, patch, t_acc, tfull_bar(acc), acc_ph, m_blk, n_blk, g, lane);
+                epi_generic(p, p.e, patch, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
             }
             tc_fence_before();
             __syncwarp();
