@@ -45,6 +45,7 @@ struct AttnParams {
     const float* ak_seq; int ak_ld;   // [Bt*H, ak_ld]: c * a[key % nbox] per key, zero padded to 64
     const float* bpe;           // [H]
     const float* dense;         // [Bt,N,N,H]
+    const __nv_bfloat16* q;     // [Bt,H,N,dhp] (v2 kernel: Q rows are read directly, not through TMA)
     void* out; long long ldo; int out_kind;   // 1 bf16, 2 tf32-rounded fp32
     int stages;
     uint32_t tmem_cols;
@@ -430,6 +431,391 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     if (warp == 9) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// =================================================================================================
+// v2: Q and P in TENSOR MEMORY.  The v1 kernel above re-reads the 128 x dhp Q tile from shared memory
+// for every 64-key score MMA (64 KB per tile at dhp = 256: the score MMAs are shared-memory-bandwidth
+// bound) and round-trips P through shared memory.  Here
+//   * the softmax warps load the CTA's Q rows straight from global memory once and park them in TMEM
+//     (128 columns of bf16 pairs); S = Q K^T is issued in the TS form (A from TMEM, B = K tile via smem
+//     descriptor), so a tile's smem traffic is just the K and V tiles;
+//   * P_j (bf16 pairs, 32 columns) overwrites S_j in place with tcgen05.st and feeds PV_j as a TMEM A
+//     operand - no st.shared / fence.proxy.async / P buffers;
+//   * the freed 96 KB of shared memory turn the K / V rings from 2 into 3+ stages.
+// S is double buffered; the issue order S_0 S_1 | PV_0 S_2 | PV_1 S_3 ... makes the in-order tensor pipe
+// resolve the write-after-read on the buffer P_j was read from.  TMEM: O [0,256) | Q [256,384) | S/P 2 x 64.
+// =================================================================================================
+__global__ void __launch_bounds__(FA_THREADS, 1)
+tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
+                const AttnParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t smem_base = raw_u32;              // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t* smem_gen = smem_raw;
+    if ((raw_u32 & 1023u) != 0) { if (threadIdx.x == 0) printf("vog: dynamic smem not 1024-aligned\n"); __trap(); }
+
+    const int q_tile = blockIdx.x, h = blockIdx.y, bt = blockIdx.z;
+    const int dhp = p.dhp, N = p.N;
+    const int dh = p.dh[h];
+    const int nkk = dhp / 64;                         // 64-wide sub-tiles of the head dimension
+    const int T = (N + FA_BKV - 1) / FA_BKV;          // key tiles
+
+    // ---- shared memory: ONLY the K and V rings (Q and P live in tensor memory)
+    const uint32_t k_bytes = FA_BKV * dhp * 2;        // nkk sub-tiles of [64 rows x 128 B]
+    const uint32_t v_bytes = FA_BKV * dhp * 2;        // nkk sub-tiles of [64 keys x 128 B] (64 head-dim columns each)
+    const int NS = p.stages;
+    const uint32_t k_smem0 = smem_base;
+    const uint32_t v_smem0 = k_smem0 + NS * k_bytes;
+    const uint32_t bar_off = (v_smem0 - smem_base) + NS * v_bytes;
+    const uint32_t bar_base = smem_base + bar_off;
+    auto k_full = [&](int s) { return bar_base + 8u * s; };
+    auto k_empty = [&](int s) { return bar_base + 8u * (FA_MAX_STAGES + s); };
+    auto v_full = [&](int s) { return bar_base + 8u * (2 * FA_MAX_STAGES + s); };
+    auto v_empty = [&](int s) { return bar_base + 8u * (3 * FA_MAX_STAGES + s); };
+    auto s_full = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + b); };        // S_j landed in buffer b
+    auto p_full = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 2 + b); };    // P_j written over S_j
+    auto pv_done = [&](int b) { return bar_base + 8u * (4 * FA_MAX_STAGES + 4 + b); };   // PV_j accumulated into O
+    const uint32_t q_ready = bar_base + 8u * (4 * FA_MAX_STAGES + 6);
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(
+        smem_gen + bar_off + 8 * (4 * FA_MAX_STAGES + 8));
+    float* xchg = reinterpret_cast<float*>(smem_gen + bar_off + 384);     // [2 parity][128 rows][2 halves]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // roles: warps 0-7 softmax (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer; the control
+    // warps carry the HIGHEST warp ids because the SM's issue arbiter favours them
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tma_k);
+        tma_prefetch_desc(&tma_v);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+            mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 256); mbar_init(pv_done(b), 1); }
+        mbar_init(q_ready, 256);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_o = tmem_base;                 // columns [0, 256): O accumulator (dhp <= 256 used)
+    const uint32_t tmem_q = tmem_base + 256;           // columns [256, 384): Q tile, bf16 pairs (A operand of S = Q K^T)
+    const uint32_t tmem_s0 = tmem_base + 384;          // 2 x 64 columns: S_j (fp32), overwritten in place by P_j (bf16 pairs)
+
+    const int bh = bt * p.H + h;
+
+    if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // the control warpgroup hands registers ...
+    if (warp == 8) {
+        // ================= producer =================
+        int jk = 0, jv = 0;
+        long long t_idle = 0;
+        while (jk < T || jv < T) {
+            int do_k = 0, do_v = 0;
+            if (lane == 0) {
+                if (jk < T) do_k = mbar_test_wait(k_empty(jk % NS), (uint32_t)(((jk / NS) & 1) ^ 1));
+                if (jv < T) do_v = mbar_test_wait(v_empty(jv % NS), (uint32_t)(((jv / NS) & 1) ^ 1));
+                if (!(do_k | do_v)) {                  // bounded polling: a protocol bug traps instead of hanging
+                    if (t_idle == 0) t_idle = clock64();
+                    else if (clock64() - t_idle > 4000000000LL) { printf("vog: attention producer timeout\n"); __trap(); }
+                } else t_idle = 0;
+            }
+            do_k = __shfl_sync(0xffffffffu, do_k, 0);
+            do_v = __shfl_sync(0xffffffffu, do_v, 0);
+            if (do_k) {
+                if (lane == 0) {
+                    const int s = jk % NS;
+                    mbar_arrive_expect_tx(k_full(s), k_bytes);
+                    for (int kk = 0; kk < nkk; ++kk)
+                        tma_load_3d(k_smem0 + s * k_bytes + kk * (FA_BKV * 128), &tma_k, k_full(s), kk * 64,
+                                    jk * FA_BKV, bh);
+                }
+                ++jk;
+            }
+            if (do_v) {
+                const int s = jv % NS;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(v_full(s), v_bytes);
+                    for (int kk = 0; kk < nkk; ++kk)
+                        tma_load_3d(v_smem0 + s * v_bytes + kk * (FA_BKV * 128), &tma_v, v_full(s), kk * 64,
+                                    jv * FA_BKV, bh);
+                }
+                ++jv;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc(FMT_BF16, FA_BQ, FA_BKV);
+            const int n_pv = (dh + 15) & ~15;
+            // B = V tile in its natural [key][head-dim] layout = MN-major: 8-key x 128 B swizzle atoms, the next
+            // 8 keys 1024 B further (SBO), the next 64 head-dim columns one [64 x 128 B] sub-tile further (LBO)
+            const uint32_t idesc_o = umma_idesc(FMT_BF16, FA_BQ, n_pv) | (1u << 16);
+            const uint32_t v_lbo = ((uint32_t)(FA_BKV * 128) >> 4) << 16;
+            const int ksteps = (dh + 15) / 16;           // skip the all-zero padded tail of the head dim
+#ifdef VOG_ATTN_PROFILE
+            const bool mprof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            long long mc[4] = {0, 0, 0, 0};
+            long long mt = clock64();
+#define VOG_MPROF(i) if (mprof) { const long long tn = clock64(); mc[i] += tn - mt; mt = tn; }
+#else
+#define VOG_MPROF(i)
+#endif
+            auto issue_s = [&](int j) {
+                const int s = j % NS;
+                mbar_wait(k_full(s), (uint32_t)((j / NS) & 1));
+                tc_fence_after();
+                VOG_MPROF(0)
+                const uint32_t b_lo = umma_desc_lo(k_smem0 + s * k_bytes);
+                const uint32_t d = tmem_s0 + (j & 1) * FA_BKV;
+                umma_bf16_ts<false>(d, tmem_q, b_lo, idesc_s);
+#pragma unroll
+                for (int ks = 1; ks < 16; ++ks) {          // A: 16 bf16 = 8 TMEM columns per step; B offsets are immediates
+                    if (ks < ksteps)
+                        umma_bf16_ts<true>(d, tmem_q + ks * 8,
+                                           b_lo + (ks >> 2) * (FA_BKV * 128 / 16) + (ks & 3) * 2, idesc_s);
+                }
+                umma_commit(k_empty(s));
+                umma_commit(s_full(j & 1));
+                VOG_MPROF(1)
+            };
+            mbar_wait(q_ready, 0);
+            tc_fence_after();
+            issue_s(0);
+            if (T > 1) issue_s(1);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % NS, pb = j & 1;
+                mbar_wait(v_full(s), (uint32_t)((j / NS) & 1));
+                mbar_wait(p_full(pb), (uint32_t)((j >> 1) & 1));
+                tc_fence_after();
+                VOG_MPROF(2)
+                const uint32_t pa = tmem_s0 + pb * FA_BKV;         // P_j: 64 keys = 32 columns of bf16 pairs
+                const uint32_t vb_lo = (((v_smem0 + s * v_bytes) >> 4) & 0x3FFF) | v_lbo;
+                if (j == 0) umma_bf16_ts<false>(tmem_o, pa, vb_lo, idesc_o);
+                else umma_bf16_ts<true>(tmem_o, pa, vb_lo, idesc_o);
+#pragma unroll
+                for (int k4 = 1; k4 < 4; ++k4)         // 16 keys = 8 P columns / two 8-key V atoms = 2048 B per step
+                    umma_bf16_ts<true>(tmem_o, pa + 8 * k4, vb_lo + k4 * (2048 >> 4), idesc_o);
+                umma_commit(v_empty(s));
+                umma_commit(pv_done(pb));
+                VOG_MPROF(3)
+                // S_{j+2} reuses the buffer P_j was read from: issued after PV_j, and the tensor pipe runs in order
+                if (j + 2 < T) issue_s(j + 2);
+            }
+#ifdef VOG_ATTN_PROFILE
+            if (mprof) for (int i = 0; i < 4; ++i) p.prof[8 + i] = mc[i];
+#endif
+        }
+        __syncwarp();
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");     // ... to the two softmax warpgroups
+        // ================= softmax / correction / epilogue =================
+        // two threads per query row: warps 0-3 take key columns [0,32) of every 64-key tile, warps 4-7
+        // columns [32,64); the pair (same TMEM lane quarter) exchanges its row maxima through smem and
+        // a 64-thread named barrier, keeps PARTIAL row sums (combined once at the end) and splits the
+        // accumulator columns between them for the lazy rescale and the epilogue
+        const int g = warp & 3;
+        const int half = warp >> 2;
+        const int row = 32 * g + lane;                  // row inside the tile == TMEM lane
+        const int qi = q_tile * FA_BQ + row;            // query index inside the sequence
+        const bool row_ok = qi < N;
+        const uint32_t lane_addr = (uint32_t)(32 * g) << 16;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory"); };
+        float ai = 0.f;
+        if (p.bias_mode == 1 && row_ok)
+            ai = (__ldg(p.a + ((size_t)bt * p.nbox + qi % p.nbox) * p.H + h) + __ldg(p.bpe + h)) * p.c;
+        const float* dense_row = nullptr;
+        if (p.bias_mode == 2 && row_ok) dense_row = p.dense + (((size_t)bt * N + qi) * N) * p.H + h;
+        float m_run = -1e30f, l_run = 0.f;
+        const int ocols = dhp >> 1;                     // accumulator columns owned by this thread's half
+
+#ifdef VOG_ATTN_PROFILE     // build with -DVOG_ATTN_PROFILE for the clock64 phase breakdown (profiles/attn_phases.py)
+        const bool do_prof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0;
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = do_prof ? clock64() : 0;
+#define VOG_PROF(i) if (do_prof) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
+#else
+#define VOG_PROF(i)
+#endif
+        // ---- Q tile -> tensor memory (A operand of every S = Q K^T of this CTA: never re-read from smem).  The
+        //      row's head-dim half of this thread: dhp/2 bf16 = dhp/4 packed words at columns half*dhp/4 ...
+        {
+            const uint4* qsrc = reinterpret_cast<const uint4*>(
+                p.q + (((size_t)bh * N + (row_ok ? qi : 0)) * dhp) + half * (dhp >> 1));
+            for (int c16 = 0; c16 < (dhp >> 6); ++c16) {           // 16 words (32 bf16) per tcgen05.st
+                uint32_t w[16];
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const uint4 t = row_ok ? __ldg(qsrc + c16 * 4 + v4) : make_uint4(0u, 0u, 0u, 0u);
+                    w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
+                }
+                tmem_st16(tmem_q + lane_addr + half * (dhp >> 2) + c16 * 16, w);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(q_ready);
+        }
+        // software pipeline: the score tile S_{j+1} (TMEM) and its bias factors (global, L1/L2) are
+        // requested while tile j is exponentiated / packed, so their latencies are off the critical path
+        uint32_t rn[32];
+        float4 an[8];
+        auto load_bias = [&](int jj) {
+            const float4* ak4 = reinterpret_cast<const float4*>(p.ak_seq + (size_t)bh * p.ak_ld +
+                                                                (size_t)jj * FA_BKV + half * 32);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) an[c4] = __ldg(ak4 + c4);
+        };
+        auto load_scores = [&](int jj) {
+            mbar_wait(s_full(jj & 1), (uint32_t)((jj >> 1) & 1));
+            tc_fence_after();
+            tmem_ld32(tmem_s0 + lane_addr + (jj & 1) * FA_BKV + half * 32, rn);
+        };
+        if (p.bias_mode == 1) load_bias(0);
+        load_scores(0);
+        for (int j = 0; j < T; ++j) {
+            const int sb = j & 1;
+            tmem_wait_ld();
+            VOG_PROF(0)
+            uint32_t (&r0)[32] = rn;
+            float4 (&a4)[8] = an;
+            VOG_PROF(1)
+            float sv[32];
+            if (p.bias_mode == 1) {
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    sv[4 * c4 + 0] = fmaf(__uint_as_float(r0[4 * c4 + 0]), p.c, fmaxf(ai - a4[c4].x, 0.f));
+                    sv[4 * c4 + 1] = fmaf(__uint_as_float(r0[4 * c4 + 1]), p.c, fmaxf(ai - a4[c4].y, 0.f));
+                    sv[4 * c4 + 2] = fmaf(__uint_as_float(r0[4 * c4 + 2]), p.c, fmaxf(ai - a4[c4].z, 0.f));
+                    sv[4 * c4 + 3] = fmaf(__uint_as_float(r0[4 * c4 + 3]), p.c, fmaxf(ai - a4[c4].w, 0.f));
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(r0[c]) * p.c;
+                if (p.bias_mode == 2 && row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int key = j * FA_BKV + half * 32 + c;
+                        if (key < N) sv[c] += __ldg(dense_row + (size_t)key * p.H) * p.c;
+                    }
+                }
+            }
+            if ((j + 1) * FA_BKV > N) {                // ragged last tile: keys >= N do not exist
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (j * FA_BKV + half * 32 + c >= N) sv[c] = -INFINITY;
+            }
+            float mx0 = fmaxf(sv[0], sv[1]), mx1 = fmaxf(sv[2], sv[3]), mx2 = fmaxf(sv[4], sv[5]), mx3 = fmaxf(sv[6], sv[7]);
+#pragma unroll
+            for (int c = 8; c < 32; c += 4) {
+                mx0 = fmaxf(mx0, sv[c]); mx1 = fmaxf(mx1, sv[c + 1]); mx2 = fmaxf(mx2, sv[c + 2]); mx3 = fmaxf(mx3, sv[c + 3]);
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));     // -inf when this half has no valid key
+            float* xr = xchg + ((j & 1) * FA_BQ + row) * 2;
+            VOG_PROF(2)
+            xr[half] = mx;
+            pair_sync();
+            VOG_PROF(3)
+            const float m_new = fmaxf(m_run, fmaxf(mx, xr[half ^ 1]));
+            if (j == 0) {
+                m_run = m_new;
+            } else {
+                const bool grow = (m_new - m_run) > FA_RESCALE_T;
+                if (__any_sync(0xffffffffu, grow)) {
+                    // rescale this thread's half of the accumulator row; PV_{j-1} must have landed first
+                    const float alpha = grow ? fast_exp2(m_run - m_new) : 1.f;
+                    if (grow) { m_run = m_new; l_run *= alpha; }
+                    mbar_wait(pv_done((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
+                    tc_fence_after();
+                    for (int c0 = half * ocols; c0 < (half + 1) * ocols; c0 += 32) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_o + lane_addr + c0, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                        tmem_st32(tmem_o + lane_addr + c0, o);
+                    }
+                    tmem_wait_st();
+                }
+            }
+            if (j + 1 < T && p.bias_mode == 1) load_bias(j + 1);   // sv holds tile j now: an is free again
+            VOG_PROF(7)
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                sv[c] = fast_exp2(sv[c] - m_run); s0 += sv[c];
+                sv[c + 1] = fast_exp2(sv[c + 1] - m_run); s1 += sv[c + 1];
+                sv[c + 2] = fast_exp2(sv[c + 2] - m_run); s2 += sv[c + 2];
+                sv[c + 3] = fast_exp2(sv[c + 3] - m_run); s3 += sv[c + 3];
+            }
+            l_run += (s0 + s1) + (s2 + s3);
+            VOG_PROF(4)
+            VOG_PROF(5)
+            // P_j (bf16 pairs) overwrites S_j in place: this thread's 32 probabilities -> 16 words at columns
+            // half*16 of buffer j&1.  Every S_j column was read (both threads of the row passed pair_sync)
+            {
+                uint32_t pw[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pw[i] = pack_bf16(sv[2 * i], sv[2 * i + 1]);
+                tmem_st16(tmem_s0 + lane_addr + sb * FA_BKV + half * 16, pw);
+                tmem_wait_st();
+            }
+            tc_fence_before();
+            mbar_arrive(p_full(sb));
+            VOG_PROF(6)
+            // S_{j+1} (other buffer) was issued right after PV_{j-1}: complete by now in steady state
+            if (j + 1 < T) load_scores(j + 1);
+        }
+#ifdef VOG_ATTN_PROFILE
+        if (do_prof) { for (int i = 0; i < 8; ++i) p.prof[i] = pc[i]; p.prof[12] = T; }
+#endif
+        // ---- epilogue: O / l  (row sum = the two partial sums of the pair)
+        {
+            float* xr = xchg + ((T & 1) * FA_BQ + row) * 2;
+            xr[half] = l_run;
+            pair_sync();
+            l_run += xr[half ^ 1];
+        }
+        mbar_wait(pv_done((T - 1) & 1), (uint32_t)(((T - 1) >> 1) & 1));
+        tc_fence_after();
+        const float inv_l = 1.f / l_run;
+        const int n_pv = (dh + 15) & ~15;
+        for (int c0 = half * ocols; c0 < (half + 1) * ocols; c0 += 32) {
+            uint32_t o[32];
+            float v[32];
+            if (c0 < n_pv) {
+                tmem_ld32(tmem_o + lane_addr + c0, o);
+                tmem_wait_ld();
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = (c0 + c < n_pv) ? __uint_as_float(o[c]) * inv_l : 0.f;
+            if (row_ok) {
+                const size_t off = ((size_t)bt * N + qi) * p.ldo + (size_t)h * dhp + c0;
+                if (p.out_kind == 1) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8)
+                        *reinterpret_cast<uint4*>(dst + c) =
+                            make_uint4(pack_bf16(v[c], v[c + 1]), pack_bf16(v[c + 2], v[c + 3]),
+                                       pack_bf16(v[c + 4], v[c + 5]), pack_bf16(v[c + 6], v[c + 7]));
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.out) + off;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(dst + c) =
+                            make_float4(to_tf32(v[c]), to_tf32(v[c + 1]), to_tf32(v[c + 2]), to_tf32(v[c + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+
 // ak_seq[bt*H + h, key] = c * a[(bt*nbox + key % nbox), h] for key < N, 0 up to the 64-padded row end:
 // the per-key factor of the rank-1 bias in the order and scaling the softmax warps consume it
 __global__ void bias_expand_kernel(const float* __restrict__ a, float* __restrict__ ak, int Bt, int N, int H,
@@ -449,6 +835,8 @@ long long tc_attn_workspace_bytes(int Bt, int N, int H)
 }
 
 static long long* g_attn_prof = nullptr;
+static int g_attn_impl = 2;             // 1 = Q/P through shared memory (v1), 2 = Q/P in tensor memory (v2)
+void tc_attn_set_impl(int impl) { g_attn_impl = impl == 1 ? 1 : 2; }
 void tc_attn_set_prof(long long* buf) { g_attn_prof = buf; }
 
 int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
@@ -485,6 +873,27 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
         bias_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<float*>(workspace), Bt, N, H,
                                                                          p.nbox, p.ak_ld, p.c);
         if (check_launch("bias_expand")) return -1;
+    }
+    p.q = reinterpret_cast<const __nv_bfloat16*>(q);
+    if (g_attn_impl == 2) {
+        p.tmem_cols = 512;
+        CUtensorMap tk2, tv2;
+        const uint64_t BH2 = (uint64_t)Bt * H;
+        uint64_t dq2[3] = {(uint64_t)dhp, (uint64_t)N, BH2};
+        uint64_t sq2[2] = {(uint64_t)dhp * 2, (uint64_t)N * dhp * 2};
+        uint32_t bk2[3] = {64, FA_BKV, 1};
+        if (make_tmap(&tk2, k, 2, 1, 3, dq2, sq2, bk2)) return -1;
+        if (make_tmap(&tv2, v, 2, 1, 3, dq2, sq2, bk2)) return -1;
+        const int fixed2 = 384 /*barriers*/ + 2 * FA_BQ * 2 * 4 /*pair exchange*/;
+        const int stage_bytes2 = 2 * FA_BKV * dhp * 2;
+        int stages2 = (227 * 1024 - fixed2) / stage_bytes2;
+        if (stages2 > FA_MAX_STAGES) stages2 = FA_MAX_STAGES;
+        p.stages = stages2;
+        const size_t smem2 = (size_t)fixed2 + (size_t)stages2 * stage_bytes2;
+        VOG_CUDA(cudaFuncSetAttribute(tc_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        dim3 grid2(cdiv(N, FA_BQ), H, Bt);
+        tc_attn2_kernel<<<grid2, FA_THREADS, smem2, st>>>(tk2, tv2, p);
+        return check_launch("tc_attn2");
     }
     const int cols = dhp + 3 * FA_BKV;
     p.tmem_cols = cols <= 256 ? 256 : 512;

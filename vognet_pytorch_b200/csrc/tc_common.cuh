@@ -146,6 +146,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+// lane i of the warp -> TMEM lane (base lane + i), 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+          "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+          "r"(r[15])
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // UMMA descriptors (layouts per the PTX ISA "tcgen05 matrix descriptor" / instruction descriptor)
 // ---------------------------------------------------------------------------------------------
@@ -197,6 +208,18 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uin
         "mov.b64 db, {%2, %5};\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(UMMA_DESC_HI_SW128)
+        : "memory");
+}
+// TS form: A operand from tensor memory (rows = lanes, K packed as bf16 pairs along the columns, 8 columns
+// per K = 16 step), B through a shared-memory descriptor
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "n"(kAccumulate ? 1 : 0), "r"(UMMA_DESC_HI_SW128)
         : "memory");
 }
 // arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed

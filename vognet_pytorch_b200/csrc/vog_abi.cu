@@ -197,6 +197,8 @@ void vog_debug_gemm_trace(void* buf) { vog::tc_gemm_set_trace((long long*)buf); 
 
 /* debug: device buffer of 8 int64 that receives per-phase cycle counts of one softmax warp */
 void vog_debug_attn_prof(void* buf) { vog::tc_attn_set_prof((long long*)buf); }
+/* A/B switch of the fused attention kernel: 1 = Q and P through shared memory, 2 = Q and P in tensor memory */
+void vog_debug_attn_impl(int impl) { vog::tc_attn_set_impl(impl); }
 
 int64_t vog_tc_attn_workspace_bytes(int Bt, int N, int H)
 {
