@@ -547,7 +547,11 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
         __syncwarp();
     } else if (warp == 9) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The WHOLE warp runs the control flow (waits, loop counters stay warp-uniform) and one elected lane
+        // issues the tcgen05 instructions: under a divergent `if (lane == 0)` the compiler has to wrap every
+        // uniform-datapath instruction (UTCHMMA, UTCBAR) in an ELECT / BRA.U.ANY loop, ~11 SASS instructions
+        // and ~64 cycles per MMA - twice the 32-cycle dispatch floor of a 128x64x16 MMA.
+        {
             const uint32_t idesc_s = umma_idesc(FMT_BF16, FA_BQ, FA_BKV);
             const int n_pv = (dh + 15) & ~15;
             // B = V tile in its natural [key][head-dim] layout = MN-major: 8-key x 128 B swizzle atoms, the next
@@ -556,11 +560,13 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             const uint32_t v_lbo = ((uint32_t)(FA_BKV * 128) >> 4) << 16;
             const int ksteps = (dh + 15) / 16;           // skip the all-zero padded tail of the head dim
 #ifdef VOG_ATTN_PROFILE
-            const bool mprof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+            const bool mprof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
             long long mc[4] = {0, 0, 0, 0};
             long long mt = clock64();
+#undef VOG_MPROF
 #define VOG_MPROF(i) if (mprof) { const long long tn = clock64(); mc[i] += tn - mt; mt = tn; }
 #else
+#undef VOG_MPROF
 #define VOG_MPROF(i)
 #endif
             auto issue_s = [&](int j) {
@@ -570,15 +576,18 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
                 VOG_MPROF(0)
                 const uint32_t b_lo = umma_desc_lo(k_smem0 + s * k_bytes);
                 const uint32_t d = tmem_s0 + (j & 1) * FA_BKV;
-                umma_bf16_ts<false>(d, tmem_q, b_lo, idesc_s);
+                if (elect_one()) {
+                    umma_bf16_ts<false>(d, tmem_q, b_lo, idesc_s);
 #pragma unroll
-                for (int ks = 1; ks < 16; ++ks) {          // A: 16 bf16 = 8 TMEM columns per step; B offsets are immediates
-                    if (ks < ksteps)
-                        umma_bf16_ts<true>(d, tmem_q + ks * 8,
-                                           b_lo + (ks >> 2) * (FA_BKV * 128 / 16) + (ks & 3) * 2, idesc_s);
+                    for (int ks = 1; ks < 16; ++ks) {      // A: 16 bf16 = 8 TMEM columns per step; B offsets are immediates
+                        if (ks < ksteps)
+                            umma_bf16_ts<true>(d, tmem_q + ks * 8,
+                                               b_lo + (ks >> 2) * (FA_BKV * 128 / 16) + (ks & 3) * 2, idesc_s);
+                    }
+                    umma_commit(k_empty(s));
+                    umma_commit(s_full(j & 1));
                 }
-                umma_commit(k_empty(s));
-                umma_commit(s_full(j & 1));
+                __syncwarp();
                 VOG_MPROF(1)
             };
             mbar_wait(q_ready, 0);
@@ -593,13 +602,16 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
                 VOG_MPROF(2)
                 const uint32_t pa = tmem_s0 + pb * FA_BKV;         // P_j: 64 keys = 32 columns of bf16 pairs
                 const uint32_t vb_lo = (((v_smem0 + s * v_bytes) >> 4) & 0x3FFF) | v_lbo;
-                if (j == 0) umma_bf16_ts<false>(tmem_o, pa, vb_lo, idesc_o);
-                else umma_bf16_ts<true>(tmem_o, pa, vb_lo, idesc_o);
+                if (elect_one()) {
+                    if (j == 0) umma_bf16_ts<false>(tmem_o, pa, vb_lo, idesc_o);
+                    else umma_bf16_ts<true>(tmem_o, pa, vb_lo, idesc_o);
 #pragma unroll
-                for (int k4 = 1; k4 < 4; ++k4)         // 16 keys = 8 P columns / two 8-key V atoms = 2048 B per step
-                    umma_bf16_ts<true>(tmem_o, pa + 8 * k4, vb_lo + k4 * (2048 >> 4), idesc_o);
-                umma_commit(v_empty(s));
-                umma_commit(pv_done(pb));
+                    for (int k4 = 1; k4 < 4; ++k4)     // 16 keys = 8 P columns / two 8-key V atoms = 2048 B per step
+                        umma_bf16_ts<true>(tmem_o, pa + 8 * k4, vb_lo + k4 * (2048 >> 4), idesc_o);
+                    umma_commit(v_empty(s));
+                    umma_commit(pv_done(pb));
+                }
+                __syncwarp();
                 VOG_MPROF(3)
                 // S_{j+2} reuses the buffer P_j was read from: issued after PV_j, and the tensor pipe runs in order
                 if (j + 2 < T) issue_s(j + 2);
@@ -608,7 +620,6 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             if (mprof) for (int i = 0; i < 4; ++i) p.prof[8 + i] = mc[i];
 #endif
         }
-        __syncwarp();
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");     // ... to the two softmax warpgroups
