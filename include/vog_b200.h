@@ -200,6 +200,7 @@ void vog_debug_gemm_trace(void* buf);
 void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 0 tagged 64-bit words, 1 per-CTA release flags */
 void vog_debug_lstm_trace(void* buf);          /* 8 int64: matvec, reduce, cell+publish, poll, barrier cycles, steps */
 void vog_debug_attn_prof(void* buf);
+void vog_debug_attn_cluster(int c);            /* v2 attention cluster size: 1, 2, 4, or 0 = automatic */
 void vog_debug_attn_impl(int impl);            /* 1 = Q/P through shared memory, 2 = Q/P in tensor memory (default) */
 
 #ifdef __cplusplus

@@ -22,8 +22,12 @@ for Bt, N, d in ((40, 2000, 768), (4, 4000, 512), (40, 100, 768), (4, 200, 512),
     a = torch.rand(Bt * nbox, 3, device=dev)
     bpe = torch.zeros(3, device=dev)
     outs = {}
-    for impl in (1, 2):
+    qt = -(-N // 128)
+    for impl, cl in ((1, 0), (2, 1), (2, 2), (2, 4)):
+        if cl and qt % cl:
+            continue
         L.vog_debug_attn_impl(impl)
+        L.vog_debug_attn_cluster(cl)
         out = torch.empty(Bt * N, 3 * dhp, device=dev, dtype=torch.bfloat16)
         run = lambda: ops.tc_attn_fwd(q, k, v, N, hd, 1.0 / d ** 0.5, out=out, bias_mode=ops.BIAS_RANK1, a=a, nbox=nbox, bpe=bpe)
         for _ in range(3):
@@ -36,8 +40,12 @@ for Bt, N, d in ((40, 2000, 768), (4, 4000, 512), (40, 100, 768), (4, 200, 512),
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         ts.sort()
-        outs[impl] = out.float().clone()
+        outs[impl] = out.float().clone() if impl == 1 or impl not in outs else outs[impl]
+        if impl == 2 and 1 in outs:
+            assert (outs[1] - out.float()).abs().max().item() < 1e-2, 'v2 differs from v1'
+        outs[2] = out.float().clone()
         fl = 4.0 * Bt * N * N * d
-        print(f'Bt={Bt:4d} N={N:5d} d={d} impl v{impl}: {ts[5]:8.1f} us  {fl / ts[5] / 1e6:7.1f} TF/s')
+        print(f'Bt={Bt:4d} N={N:5d} d={d} impl v{impl} cluster {cl}: {ts[5]:8.1f} us  {fl / ts[5] / 1e6:7.1f} TF/s')
     print(f'    max |v2 - v1| = {(outs[1] - outs[2]).abs().max().item():.3e}')
 L.vog_debug_attn_impl(2)
+L.vog_debug_attn_cluster(0)

@@ -51,6 +51,7 @@ _SIGNATURES = {
     'vog_debug_lstm_exchange': [c_int],
     'vog_debug_attn_prof': [P],
     'vog_debug_attn_impl': [c_int],
+    'vog_debug_attn_cluster': [c_int],
     'vog_lstm_layer_fwd': [P, c_i64, P, P, c_int, c_int, c_int, P, c_i64, c_int, P, P],
     'vog_tc_attn_workspace_bytes': [c_int, c_int, c_int],
     'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,

@@ -63,6 +63,7 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
             long long workspace_bytes, cudaStream_t st);
 long long tc_attn_workspace_bytes(int Bt, int N, int H);
 void tc_attn_set_impl(int impl);         // debug: 1 = Q/P via shared memory, 2 = Q/P in tensor memory (default)
+void tc_attn_set_cluster(int c);         // debug: force the v2 cluster size (0 = auto)
 void tc_attn_set_prof(long long* buf);   // debug: phase cycle counters of one softmax warp
 int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int kind,
             cudaStream_t st);

@@ -48,6 +48,7 @@ struct AttnParams {
     const __nv_bfloat16* q;     // [Bt,H,N,dhp] (v2 kernel: Q rows are read directly, not through TMA)
     void* out; long long ldo; int out_kind;   // 1 bf16, 2 tf32-rounded fp32
     int stages;
+    int cluster;                // v2: CTAs (query tiles of one sequence/head) that share multicast K / V loads
     uint32_t tmem_cols;
     long long* prof;            // optional [8] phase cycle counters (block 0, first softmax warp)
 };
@@ -480,6 +481,11 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
         smem_gen + bar_off + 8 * (4 * FA_MAX_STAGES + 8));
     float* xchg = reinterpret_cast<float*>(smem_gen + bar_off + 384);     // [2 parity][128 rows][2 halves]
 
+    // thread-block cluster of C CTAs = C query tiles of the same (sequence, head): every K / V tile is fetched
+    // from L2 ONCE per cluster - CTA r loads the 64/C-key slice r and multicasts it into all C shared memories
+    const int C = p.cluster;
+    const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << C) - 1u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // roles: warps 0-7 softmax (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer; the control
     // warps carry the HIGHEST warp ids because the SM's issue arbiter favours them
@@ -487,8 +493,8 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
         tma_prefetch_desc(&tma_k);
         tma_prefetch_desc(&tma_v);
         for (int s = 0; s < NS; ++s) {
-            mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
-            mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+            mbar_init(k_full(s), 1); mbar_init(k_empty(s), C);        // a slot is free when ALL CTAs of the cluster read it
+            mbar_init(v_full(s), 1); mbar_init(v_empty(s), C);
         }
         for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 256); mbar_init(pv_done(b), 1); }
         mbar_init(q_ready, 256);
@@ -497,6 +503,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
     if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();                     // peers' barriers are initialised before anyone multicasts
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_o = tmem_base;                 // columns [0, 256): O accumulator (dhp <= 256 used)
@@ -527,9 +534,16 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
                 if (lane == 0) {
                     const int s = jk % NS;
                     mbar_arrive_expect_tx(k_full(s), k_bytes);
-                    for (int kk = 0; kk < nkk; ++kk)
-                        tma_load_3d(k_smem0 + s * k_bytes + kk * (FA_BKV * 128), &tma_k, k_full(s), kk * 64,
-                                    jk * FA_BKV, bh);
+                    if (C == 1) {
+                        for (int kk = 0; kk < nkk; ++kk)
+                            tma_load_3d(k_smem0 + s * k_bytes + kk * (FA_BKV * 128), &tma_k, k_full(s), kk * 64,
+                                        jk * FA_BKV, bh);
+                    } else {
+                        const int rows = FA_BKV / C;               // this CTA's key slice of the tile
+                        for (int kk = 0; kk < nkk; ++kk)
+                            tma_load_3d_mc(k_smem0 + s * k_bytes + kk * (FA_BKV * 128) + crank * rows * 128, &tma_k,
+                                           k_full(s), kk * 64, jk * FA_BKV + crank * rows, bh, cmask);
+                    }
                 }
                 ++jk;
             }
@@ -537,9 +551,16 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
                 const int s = jv % NS;
                 if (lane == 0) {
                     mbar_arrive_expect_tx(v_full(s), v_bytes);
-                    for (int kk = 0; kk < nkk; ++kk)
-                        tma_load_3d(v_smem0 + s * v_bytes + kk * (FA_BKV * 128), &tma_v, v_full(s), kk * 64,
-                                    jv * FA_BKV, bh);
+                    if (C == 1) {
+                        for (int kk = 0; kk < nkk; ++kk)
+                            tma_load_3d(v_smem0 + s * v_bytes + kk * (FA_BKV * 128), &tma_v, v_full(s), kk * 64,
+                                        jv * FA_BKV, bh);
+                    } else {
+                        const int rows = FA_BKV / C;
+                        for (int kk = 0; kk < nkk; ++kk)
+                            tma_load_3d_mc(v_smem0 + s * v_bytes + kk * (FA_BKV * 128) + crank * rows * 128, &tma_v,
+                                           v_full(s), kk * 64, jv * FA_BKV + crank * rows, bh, cmask);
+                    }
                 }
                 ++jv;
             }
@@ -584,7 +605,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
                             umma_bf16_ts<true>(d, tmem_q + ks * 8,
                                                b_lo + (ks >> 2) * (FA_BKV * 128 / 16) + (ks & 3) * 2, idesc_s);
                     }
-                    umma_commit(k_empty(s));
+                    if (C == 1) umma_commit(k_empty(s)); else umma_commit_mc(k_empty(s), cmask);
                     umma_commit(s_full(j & 1));
                 }
                 __syncwarp();
@@ -608,7 +629,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
 #pragma unroll
                     for (int k4 = 1; k4 < 4; ++k4)     // 16 keys = 8 P columns / two 8-key V atoms = 2048 B per step
                         umma_bf16_ts<true>(tmem_o, pa + 8 * k4, vb_lo + k4 * (2048 >> 4), idesc_o);
-                    umma_commit(v_empty(s));
+                    if (C == 1) umma_commit(v_empty(s)); else umma_commit_mc(v_empty(s), cmask);
                     umma_commit(pv_done(pb));
                 }
                 __syncwarp();
@@ -824,6 +845,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 9) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (C > 1) cluster_sync_all();                     // no CTA leaves while a peer may still signal its barriers
 }
 
 
@@ -847,7 +869,9 @@ long long tc_attn_workspace_bytes(int Bt, int N, int H)
 
 static long long* g_attn_prof = nullptr;
 static int g_attn_impl = 2;             // 1 = Q/P through shared memory (v1), 2 = Q/P in tensor memory (v2)
+static int g_attn_cluster = 0;          // 0 = default (no cluster); 2 / 4 = multicast K/V loads across query tiles
 void tc_attn_set_impl(int impl) { g_attn_impl = impl == 1 ? 1 : 2; }
+void tc_attn_set_cluster(int c) { g_attn_cluster = c; }
 void tc_attn_set_prof(long long* buf) { g_attn_prof = buf; }
 
 int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
@@ -888,11 +912,18 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
     p.q = reinterpret_cast<const __nv_bfloat16*>(q);
     if (g_attn_impl == 2) {
         p.tmem_cols = 512;
+        const int qtiles = cdiv(N, FA_BQ);
+        // measured on B200 (profiles/r1/attention.md): multicast clusters LOSE 13-30 % here - the limiter is each SM's
+        // own shared-memory fill rate (every CTA still receives the whole tile), not L2 bandwidth, and the CTAs of a
+        // cluster then run in lock step.  The path stays available for experiments (vog_debug_attn_cluster).
+        const int C = g_attn_cluster > 0 ? g_attn_cluster : 1;
+        VOG_REQUIRE((C == 1 || C == 2 || C == 4) && qtiles % C == 0, "tc_attn: cluster size %d does not divide %d query tiles", C, qtiles);
+        p.cluster = C;
         CUtensorMap tk2, tv2;
         const uint64_t BH2 = (uint64_t)Bt * H;
         uint64_t dq2[3] = {(uint64_t)dhp, (uint64_t)N, BH2};
         uint64_t sq2[2] = {(uint64_t)dhp * 2, (uint64_t)N * dhp * 2};
-        uint32_t bk2[3] = {64, FA_BKV, 1};
+        uint32_t bk2[3] = {64, (uint32_t)(FA_BKV / C), 1};       // every CTA of a cluster loads a 64/C-key slice
         if (make_tmap(&tk2, k, 2, 1, 3, dq2, sq2, bk2)) return -1;
         if (make_tmap(&tv2, v, 2, 1, 3, dq2, sq2, bk2)) return -1;
         const int fixed2 = 384 /*barriers*/ + 2 * FA_BQ * 2 * 4 /*pair exchange*/;
@@ -902,8 +933,16 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
         p.stages = stages2;
         const size_t smem2 = (size_t)fixed2 + (size_t)stages2 * stage_bytes2;
         VOG_CUDA(cudaFuncSetAttribute(tc_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        dim3 grid2(cdiv(N, FA_BQ), H, Bt);
-        tc_attn2_kernel<<<grid2, FA_THREADS, smem2, st>>>(tk2, tv2, p);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(qtiles, H, Bt);
+        cfg.blockDim = dim3(FA_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem2;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        VOG_CUDA(cudaLaunchKernelEx(&cfg, tc_attn2_kernel, tk2, tv2, p));
         return check_launch("tc_attn2");
     }
     const int cols = dhp + 3 * FA_BKV;

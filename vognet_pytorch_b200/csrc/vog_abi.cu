@@ -199,6 +199,8 @@ void vog_debug_gemm_trace(void* buf) { vog::tc_gemm_set_trace((long long*)buf); 
 void vog_debug_attn_prof(void* buf) { vog::tc_attn_set_prof((long long*)buf); }
 /* A/B switch of the fused attention kernel: 1 = Q and P through shared memory, 2 = Q and P in tensor memory */
 void vog_debug_attn_impl(int impl) { vog::tc_attn_set_impl(impl); }
+/* force the thread-block-cluster size of the v2 attention kernel (1, 2, 4; 0 = automatic) */
+void vog_debug_attn_cluster(int c) { vog::tc_attn_set_cluster(c); }
 
 int64_t vog_tc_attn_workspace_bytes(int Bt, int N, int H)
 {
