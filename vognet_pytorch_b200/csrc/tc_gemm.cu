@@ -437,35 +437,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         return split;
     };
 
+    // Producer and MMA issuer run their loops with the WHOLE warp (warp-uniform control flow) and elect one
+    // lane per TMA / tcgen05 instruction: under a divergent `if (lane == 0)` every uniform-datapath
+    // instruction is wrapped in an ELECT / BRA.U.ANY loop (~11 SASS instructions per tcgen05.mma).
     if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                int m_blk, n_blk, kb0, kb1;
-                decode(item, m_blk, n_blk, kb0, kb1);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
+        int s = 0; uint32_t ph = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            int m_blk, n_blk, kb0, kb1;
+            decode(item, m_blk, n_blk, kb0, kb1);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty_bar(s), ph ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(full_bar(s), stage_bytes);
                     tma_load_2d(a_smem(s), &tma_a, full_bar(s), kb * p.bk_elems, m_blk * GM_BM);
                     tma_load_2d(b_smem(s), &tma_b, full_bar(s), kb * p.bk_elems, n_blk * p.BN);
                     if (item == (int)blockIdx.x && kb == kb0) GM_TRACE(2);
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                int m_blk, n_blk, kb0, kb1;
-                decode(item, m_blk, n_blk, kb0, kb1);
-                mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        int s = 0; uint32_t ph = 0; int acc = 0; uint32_t acc_ph = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            int m_blk, n_blk, kb0, kb1;
+            decode(item, m_blk, n_blk, kb0, kb1);
+            mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * p.BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(full_bar(s), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * p.BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
+                if (elect_one()) {
                     if (item == (int)blockIdx.x && kb == kb0) GM_TRACE(3);
                     const uint64_t ad = umma_desc_sw128(a_smem(s));
                     const uint64_t bd = umma_desc_sw128(b_smem(s));
@@ -473,15 +476,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int k = 0; k < 4; ++k)
                         umma<kTF32>(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb > kb0) || (k != 0));
                     umma_commit(empty_bar(s));
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+            if (elect_one()) {
                 umma_commit(tfull_bar(acc));
                 if (item == (int)blockIdx.x) GM_TRACE(4);
-                acc ^= 1;
-                if (acc == 0) acc_ph ^= 1;
             }
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_ph ^= 1;
         }
-        __syncwarp();
     } else {
         const int g = warp & 3;                    // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;          // which of the quarter's two warps: even / odd 32-column chunks
