@@ -246,26 +246,40 @@ def main():
     # every step's batch starts in pinned host memory; the copy of step i+1 overlaps the compute of
     # step i on a copy stream (what a pinned-memory DataLoader feeding the reference does, too)
     pre = BatchPrefetcher((host for _ in range(args.warmup + args.steps)), dev)
-    host_out = None
+    # Two steps are in flight: while step i runs on the GPU the host stages step i+1 and then collects the
+    # predictions of step i from pinned memory (event wait).  Every step still pays its own H2D copy (from
+    # pinned host memory, on the copy stream) and its own D2H read of boxes / scores / indexs.
+    host_out = [None, None]
+    done = [None, None]
 
-    def e2e_step():
-        nonlocal d2h, host_out
+    def launch(i):
+        nonlocal d2h
         b = pre.next()
         out, s = step(b)
         res = (s['boxes'], s['scores'], s['indexs'])
-        if host_out is None:
-            host_out = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
-        for h_, r in zip(host_out, res):
+        if host_out[i & 1] is None:
+            host_out[i & 1] = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
+        for h_, r in zip(host_out[i & 1], res):
             h_.copy_(r, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the step's predictions are on the host
+        ev_ = torch.cuda.Event()
+        ev_.record()
+        done[i & 1] = ev_
         d2h = sum(r.numel() * r.element_size() for r in res)
-        return host_out
-    for _ in range(args.warmup):
-        e2e_step()
+
+    def collect(i):
+        done[i & 1].synchronize()                          # the step's predictions are on the host
+        return host_out[i & 1]
+
+    def e2e_run(n):
+        for i in range(n):
+            launch(i)
+            if i:
+                collect(i - 1)
+        collect(n - 1)
+    e2e_run(args.warmup)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -279,6 +293,15 @@ def main():
 
     # ---- roofline of the dominant kernel (fused attention), timed alone with CUDA events ---------
     pk, pk_kind = peaks()
+
+    def traffic_of(kernel, shape_key):
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+        (profiles/r1/traffic.json); None when this shape was not captured."""
+        try:
+            t = json.load(open(os.path.join(ROOT, 'profiles', 'r1', 'traffic.json')))
+            return t.get(kernel, {}).get(shape_key)
+        except Exception:
+            return None
 
     def attn_roofline(shape, n_iter=10):
         Bt, N, d = shape
@@ -309,12 +332,48 @@ def main():
         fl = flops_attn(Bt, N, d)
         ach = fl / (ms * 1e-3) / 1e12
         return {'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
-                'frac': ach / pk['bf16_tflops'], 'traffic': None, 'kernel': 'tc_attn_kernel',
+                'frac': ach / pk['bf16_tflops'], 'traffic': traffic_of('tc_attn2_kernel', f'Bt{Bt}_N{N}_d{d}'),
+                'kernel': 'tc_attn2_kernel',
                 'shape': {'Bt': Bt, 'N': N, 'd_model': d, 'heads': 3}, 'ms_per_launch': ms,
                 'flops_per_launch': fl, 'peak_source': f'{pk_kind} bf16 burst (kernel timed alone)'}
 
+    def lstm_roofline(n_iter=10):
+        """The recurrence kernel of one LSTM layer (the dominant kernel of the gt5 workloads: 2 launches =
+        about half of the step).  HBM-side roofline: its algorithmic traffic is W_hh once (the weight-resident
+        kernel keeps it on chip for all timesteps) + the input projections in + the hidden states out."""
+        T, Bq, Hh = 20, B, 1024
+        lp = ops.LP_BF16 if compute == 'bf16' else ops.LP_TF32
+        g = torch.Generator(device='cpu').manual_seed(0)
+        gx = (torch.rand(T * Bq, 8 * Hh, generator=g) - 0.5).to(dev)
+        whh = ((torch.rand(2, 4 * Hh, Hh, generator=g) - 0.5) / 32).to(dev)
+        lens = batch['srl_arg_word_mask_len'].reshape(-1)[:Bq].to(dev)
+
+        def run():
+            ops.lstm_layer_fwd(gx, whh, lens, T, Bq, lp)
+        for _ in range(3):
+            run()
+        ts = []
+        for _ in range(n_iter):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); run(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sum(ts) / len(ts)
+        steps_t = int(lens.max().item())
+        by = whh.numel() * 4 + steps_t * Bq * 8 * Hh * 4 + T * Bq * 2 * Hh * (2 if lp == ops.LP_BF16 else 4)
+        ach = by / (ms * 1e-3) / 1e9
+        return {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
+                'traffic': traffic_of('lstm_rec_resident_kernel', f'T{T}_B{Bq}_H{Hh}'),
+                'kernel': 'lstm_rec_resident_kernel', 'shape': {'T': T, 'Bq': Bq, 'H': Hh, 'steps': steps_t},
+                'ms_per_launch': ms, 'bytes_per_launch': by, 'launches_per_step': 2,
+                'peak_source': f'{pk_kind} HBM copy bandwidth',
+                'note': 'latency-bound: one cross-SM h_t exchange per timestep and direction (18 dependent steps); '
+                        'the bytes are W_hh read once + gate pre-activations in + hidden states out'}
+
     shapes = workload_shapes(w)
-    roof = attn_roofline(shapes['mul'])
+    roof_attn = attn_roofline(shapes['mul'])
+    roof = lstm_roofline() if w['nppf'] < 100 else roof_attn
     line = {
         'metric': f'{METRIC} ({args.workload})', 'value': value, 'unit': 'queries/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_ms / args.steps,
@@ -329,9 +388,12 @@ def main():
                    'l2': 'flushed (256 MB memset) between timed iterations',
                    'gflop_per_query_algorithmic': flops_query(w) / 1e9},
         'clocks': clocks,
-        'e2e': {'value': e2e, 'unit': 'queries/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'e2e': {'value': e2e, 'unit': 'queries/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'note': 'public nn.Module + evaluator API, pinned host batch in / predictions out every step, '
+                        'two steps in flight (H2D of step i+1 and D2H of step i-1 overlap the compute of step i)'},
         'gpu_launches': int(launches),
         'roofline': roof,
+        'roofline_attention': roof_attn,
     }
     if not args.no_seq4000 and world == 1:
         p100 = dict(synth.WORKLOADS['spat_p100'])

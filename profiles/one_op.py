@@ -55,5 +55,13 @@ elif what == 'gres':                       # mul_tx wo GEMM with the gathered [v
     lang = torch.rand(B * nsrl, 256, device=dev)
     for _ in range(4):
         ops.tc_gemm_gres(a, w, vis, lang, nfrm, nsrl, nppf2)
+elif what == 'lstm':                       # one recurrence layer: T=20, Bq=4, H=1024, lengths as in the gt5 workload
+    T, Bq, H = 20, 4, 1024
+    kind = ops.LP_TF32
+    gx = torch.rand(T * Bq, 8 * H, device=dev) - 0.5
+    whh = (torch.rand(2, 4 * H, H, device=dev) - 0.5) / 32
+    lens = torch.tensor([20, 20, 20, 20], device=dev)
+    for _ in range(4):
+        ops.lstm_layer_fwd(gx, whh, lens, T, Bq, kind)
 torch.cuda.synchronize()
 print('done')
