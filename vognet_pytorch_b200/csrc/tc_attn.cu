@@ -514,58 +514,37 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
 
     if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // the control warpgroup hands registers ...
-    if (warp == 8) {
-        // ================= producer =================
-        int jk = 0, jv = 0;
-        long long t_idle = 0;
-        while (jk < T || jv < T) {
-            int do_k = 0, do_v = 0;
-            if (lane == 0) {
-                if (jk < T) do_k = mbar_test_wait(k_empty(jk % NS), (uint32_t)(((jk / NS) & 1) ^ 1));
-                if (jv < T) do_v = mbar_test_wait(v_empty(jv % NS), (uint32_t)(((jv / NS) & 1) ^ 1));
-                if (!(do_k | do_v)) {                  // bounded polling: a protocol bug traps instead of hanging
-                    if (t_idle == 0) t_idle = clock64();
-                    else if (clock64() - t_idle > 4000000000LL) { printf("vog: attention producer timeout\n"); __trap(); }
-                } else t_idle = 0;
-            }
-            do_k = __shfl_sync(0xffffffffu, do_k, 0);
-            do_v = __shfl_sync(0xffffffffu, do_v, 0);
-            if (do_k) {
-                if (lane == 0) {
-                    const int s = jk % NS;
-                    mbar_arrive_expect_tx(k_full(s), k_bytes);
-                    if (C == 1) {
-                        for (int kk = 0; kk < nkk; ++kk)
-                            tma_load_3d(k_smem0 + s * k_bytes + kk * (FA_BKV * 128), &tma_k, k_full(s), kk * 64,
-                                        jk * FA_BKV, bh);
-                    } else {
-                        const int rows = FA_BKV / C;               // this CTA's key slice of the tile
-                        for (int kk = 0; kk < nkk; ++kk)
-                            tma_load_3d_mc(k_smem0 + s * k_bytes + kk * (FA_BKV * 128) + crank * rows * 128, &tma_k,
-                                           k_full(s), kk * 64, jk * FA_BKV + crank * rows, bh, cmask);
-                    }
+    if (warp == 8 || warp == 10) {
+        // ================= producers: warp 8 streams the K tiles, warp 10 the V tiles =================
+        // Warp-uniform loops with BLOCKING mbarrier waits (a waiting warp takes no issue slots from the softmax
+        // warps of its scheduler) and one elected lane per TMA instruction.  The former single polling lane
+        // under `if (lane == 0)` issued every K tile ~5000 cycles late (profiles/r1/attention.md): each
+        // UTMALDG sat in an ELECT / BRA.U.ANY loop and the poll loop starved next to two busy softmax warps.
+        const bool is_k = warp == 8;
+        const CUtensorMap* tm = is_k ? &tma_k : &tma_v;
+        const uint32_t ring0 = is_k ? k_smem0 : v_smem0;
+        for (int j = 0; j < T; ++j) {
+            const int s = j % NS;
+            const uint32_t full = is_k ? k_full(s) : v_full(s);
+            mbar_wait(is_k ? k_empty(s) : v_empty(s), (uint32_t)(((j / NS) & 1) ^ 1));
+            if (elect_one()) {
+#ifdef VOG_ATTN_PROFILE
+                if (is_k && p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 32)
+                    p.prof[32 + j] = clock64();                   // K_j requested
+#endif
+                mbar_arrive_expect_tx(full, k_bytes);
+                if (C == 1) {
+                    for (int kk = 0; kk < nkk; ++kk)
+                        tma_load_3d(ring0 + s * k_bytes + kk * (FA_BKV * 128), tm, full, kk * 64, j * FA_BKV, bh);
+                } else {
+                    const int rows = FA_BKV / C;                   // this CTA's key slice of the tile
+                    for (int kk = 0; kk < nkk; ++kk)
+                        tma_load_3d_mc(ring0 + s * k_bytes + kk * (FA_BKV * 128) + crank * rows * 128, tm, full,
+                                       kk * 64, j * FA_BKV + crank * rows, bh, cmask);
                 }
-                ++jk;
             }
-            if (do_v) {
-                const int s = jv % NS;
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(v_full(s), v_bytes);
-                    if (C == 1) {
-                        for (int kk = 0; kk < nkk; ++kk)
-                            tma_load_3d(v_smem0 + s * v_bytes + kk * (FA_BKV * 128), &tma_v, v_full(s), kk * 64,
-                                        jv * FA_BKV, bh);
-                    } else {
-                        const int rows = FA_BKV / C;
-                        for (int kk = 0; kk < nkk; ++kk)
-                            tma_load_3d_mc(v_smem0 + s * v_bytes + kk * (FA_BKV * 128) + crank * rows * 128, &tma_v,
-                                           v_full(s), kk * 64, jv * FA_BKV + crank * rows, bh, cmask);
-                    }
-                }
-                ++jv;
-            }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 9) {
         // ================= MMA issuer =================
         // The WHOLE warp runs the control flow (waits, loop counters stay warp-uniform) and one elected lane
@@ -582,7 +561,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             const int ksteps = (dh + 15) / 16;           // skip the all-zero padded tail of the head dim
 #ifdef VOG_ATTN_PROFILE
             const bool mprof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
-            long long mc[4] = {0, 0, 0, 0};
+            long long mc[5] = {0, 0, 0, 0, 0};
             long long mt = clock64();
 #undef VOG_MPROF
 #define VOG_MPROF(i) if (mprof) { const long long tn = clock64(); mc[i] += tn - mt; mt = tn; }
@@ -592,8 +571,14 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
 #endif
             auto issue_s = [&](int j) {
                 const int s = j % NS;
+#ifdef VOG_ATTN_PROFILE
+                if (mprof && j < 32) p.prof[64 + j] = clock64();  // MMA thread starts waiting for K_j
+#endif
                 mbar_wait(k_full(s), (uint32_t)((j / NS) & 1));
                 tc_fence_after();
+#ifdef VOG_ATTN_PROFILE
+                if (mprof && j < 32) p.prof[96 + j] = clock64();  // K_j observed in shared memory
+#endif
                 VOG_MPROF(0)
                 const uint32_t b_lo = umma_desc_lo(k_smem0 + s * k_bytes);
                 const uint32_t d = tmem_s0 + (j & 1) * FA_BKV;
@@ -618,6 +603,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             for (int j = 0; j < T; ++j) {
                 const int s = j % NS, pb = j & 1;
                 mbar_wait(v_full(s), (uint32_t)((j / NS) & 1));
+                VOG_MPROF(4)
                 mbar_wait(p_full(pb), (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
                 VOG_MPROF(2)
@@ -638,7 +624,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
                 if (j + 2 < T) issue_s(j + 2);
             }
 #ifdef VOG_ATTN_PROFILE
-            if (mprof) for (int i = 0; i < 4; ++i) p.prof[8 + i] = mc[i];
+            if (mprof) { for (int i = 0; i < 4; ++i) p.prof[8 + i] = mc[i]; p.prof[13] = mc[4]; }
 #endif
         }
     }
