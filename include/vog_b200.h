@@ -176,7 +176,8 @@ int vog_lin2_tail(const float* h, int ldh, const float* w2, const float* b2, con
                   int nppf2, int K, int ncmp, int nppf, int nfrm0, int spat, void* stream);
 
 /* Language-side glue.  vog_lang_embed: time-major LSTM input rows x_lp[t*Bq + b] = lp(emb[tok]) with
- * tok = mask[b,t] == -1 ? pad_idx : words[b, mask[b,t]] (words [Bq,nwords], mask [Bq,T] int64) - replaces
+ * tok = mask[b,t] == -1 ? pad_idx : words[b, mask[b,t]] (words [Bq,nwords], mask [Bq,T] int64; lp_kind 0 =
+ * plain fp32 rows, used to gather rows of the per-token input-projection table W_ih.emb + b) - replaces
  * get_srl_arg_seq_to_sent_seq + embed_tokens: code/mdl_vog.py:67-95, utils/mdl_srl_utils.py:124-127.
  * vog_lang_gather: out_lp[b*nsrl + s] = lp([full[cap[b,s,0]*Bq + b] | full[cap[b,s,1]*Bq + b]]), full
  * [T*Bq, D] fp32 time-major, cap [Bq,nsrl,2] int64 - the first/last-word gather + concat of

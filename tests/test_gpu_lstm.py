@@ -71,7 +71,7 @@ def test_ragged_lengths_and_zero_rows(lens_list, streaming, xmode):
     T, Bq, H = 20, len(lens_list), 1024
     lens = torch.tensor(lens_list, device=DEV)
     gx = (torch.rand(T * Bq, 8 * H, generator=torch.Generator().manual_seed(3)) - 0.5).to(DEV)
-    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0]
+    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0][0]
     _lib.lib().vog_debug_lstm_force_streaming(streaming)
     _lib.lib().vog_debug_lstm_exchange(xmode)
     try:
@@ -96,7 +96,7 @@ def test_resident_kernel_in_cuda_graph_replays():
     T, Bq, H = 20, 4, 1024
     lens = torch.tensor([11, 20, 7, 13], device=DEV)
     gx = (torch.rand(T * Bq, 8 * H, generator=torch.Generator().manual_seed(5)) - 0.5).to(DEV)
-    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0]
+    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0][0]
     eager = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32).clone()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()

@@ -108,7 +108,9 @@ int lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const l
 // Language-side glue (code/mdl_vog.py:67-140): three kernels instead of ~15 library launches.
 // -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_lp4(void* base, size_t idx, float4 v, int kind) {
-    if (kind == 1) {
+    if (kind == 0) {                                    // plain fp32 copy
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = v;
+    } else if (kind == 1) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) =
             make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));

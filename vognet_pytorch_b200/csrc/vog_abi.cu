@@ -271,7 +271,7 @@ int vog_lang_embed(const int64_t* words, int nwords, const int64_t* mask, int T,
     VOG_REQUIRE(T >= 0 && Bq >= 0 && nwords > 0 && E > 0, "vog_lang_embed: bad dimension");
     if (T * Bq == 0) return 0;
     VOG_REQUIRE(words && mask && emb && out_lp, "vog_lang_embed: null operand");
-    VOG_REQUIRE(lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_lang_embed: bad lp_kind");
+    VOG_REQUIRE(lp_kind == 0 || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_lang_embed: bad lp_kind");
     return lang_embed((const long long*)words, nwords, (const long long*)mask, T, emb, E, pad_idx, Bq, out_lp,
                       lp_kind, (cudaStream_t)stream);
 }

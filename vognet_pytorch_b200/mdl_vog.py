@@ -144,7 +144,7 @@ class VOGNetB200(nn.Module):
         """cached tensor-core operands of the language side: per layer the forward|reverse W_ih
         stacked to [8H, in] (low precision) with b_ih+b_hh, and W_hh stacked to [2,4H,H] fp32."""
         lstm = self.lstm_encoder.lstm
-        params = [p for p in lstm.parameters()]
+        params = [p for p in lstm.parameters()] + [self.lstm_encoder.embed_tokens.weight]
         cache = self.__dict__.setdefault('_lang_cache', {})
         sig = tuple((p.data_ptr(), p._version) for p in params) + (kind,)
         ent = cache.get(kind)
@@ -158,9 +158,15 @@ class VOGNetB200(nn.Module):
                     bias = torch.cat([g('bias_ih') + g('bias_hh'), gr('bias_ih') + gr('bias_hh')], 0).float().contiguous()
                     whh = torch.stack([g('weight_hh'), gr('weight_hh')], 0).float().contiguous()
                     layers.append((ops.cast_lp(wih, kind), bias, whh))
-            ent = (sig, layers)
+                # layer 0 sees only embedding rows: its input projection W_ih.emb[tok] + b is a function of the
+                # token id alone, so it is tabulated once per weight version (exact fp32) and the per-step GEMM
+                # becomes a row gather
+                emb = self.lstm_encoder.embed_tokens.weight.detach().float().contiguous()
+                wih0 = torch.cat([lstm.weight_ih_l0.detach(), lstm.weight_ih_l0_reverse.detach()], 0).float().contiguous()
+                table = ops.sgemm_nt(emb, wih0, layers[0][1])                            # [V+1, 8H], exact fp32
+            ent = (sig, layers, table)
             cache[kind] = ent
-        return ent[1]
+        return ent[1], ent[2]
 
     def language_encode_tc(self, inp):
         """Language side without host synchronisation (CUDA-graph capturable): embedding gather,
@@ -174,11 +180,14 @@ class VOGNetB200(nn.Module):
         wm = inp['srl_arg_word_mask'].reshape(Bq, -1)
         T = wm.shape[1]
         lens = inp['srl_arg_word_mask_len'].reshape(Bq).contiguous()
-        # token gather + embedding lookup + cast, time-major rows (one kernel)
-        x_lp = ops.lang_embed(words.reshape(Bq, nsrl * L), wm, self.lstm_encoder.embed_tokens.weight,
-                              self.vocab_size, kind)
-        for wih_lp, bias, whh in self._lang_weights(kind):
-            gx, _ = ops.tc_gemm(x_lp, wih_lp, bias=bias)
+        layers, table0 = self._lang_weights(kind)
+        # token gather + layer-0 input projection in one kernel: rows of the per-token table W_ih.emb[tok] + b
+        # (time-major), so the first recurrence starts without a GEMM in front of it
+        gx = ops.lang_embed(words.reshape(Bq, nsrl * L), wm, table0, self.vocab_size, ops.LP_NONE)
+        x_lp = None
+        for l, (wih_lp, bias, whh) in enumerate(layers):
+            if l > 0:
+                gx, _ = ops.tc_gemm(x_lp, wih_lp, bias=bias)
             x_lp = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, kind)
         full, _ = ops.tc_gemm(x_lp, self._lp_weight('lstm_proj', self.lstm_out_feat_proj[0].weight, kind),
                               bias=self.lstm_out_feat_proj[0].bias, relu=True)               # [T*Bq, le]

@@ -362,7 +362,7 @@ def lang_embed(words, mask, emb, pad_idx, kind):
     _req(words, torch.int64, 'words', 2), _req(mask, torch.int64, 'mask', 2), _req(emb, torch.float32, 'emb', 2)
     words, mask, emb = words.contiguous(), mask.contiguous(), emb.contiguous()
     Bq, T = mask.shape
-    out = torch.empty(T * Bq, emb.shape[1], device=emb.device, dtype=_LP_DTYPE[kind])
+    out = torch.empty(T * Bq, emb.shape[1], device=emb.device, dtype=_LP_DTYPE.get(kind, torch.float32))
     L = _lib.lib()
     _lib.check(L.vog_lang_embed(_ptr(words), words.shape[1], _ptr(mask), T, _ptr(emb), emb.shape[1], int(pad_idx),
                                 Bq, _ptr(out), kind, _stream()), 'vog_lang_embed')
