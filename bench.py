@@ -40,20 +40,45 @@ def peaks():
         return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+idx = int(sys.argv[1])
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(idx)
+    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    get = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+    print('max', mx, flush=True)
+    while True:
+        print(repr(time.time()), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(get(h)), flush=True)
+        time.sleep(0.002)
+except Exception as e:
+    print('err', repr(e), flush=True)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle reasons sampled DURING the timed region by a separate PROCESS polling NVML every
+    ~2 ms (a thread would fight the launching thread for the GIL, and `nvidia-smi -lms` is too coarse for a
+    timed region of a few tens of milliseconds); samples are time-stamped and filtered to the window
+    [mark_begin(), mark_end()]."""
+    BITS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def start(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = self.index
+        if vis:
+            try:
+                phys = int(vis.split(',')[self.index])
+            except Exception:
+                phys = self.index
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen([sys.executable, '-c', _SAMPLER_SRC, str(phys)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -61,28 +86,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.lines.append(line)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['sampler unavailable'], 'samples': 0}
+        time.sleep(0.01)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-            except Exception:
+        self.t.join(timeout=1)
+        mx, sm, mask, err = None, [], 0, None
+        for ln in self.lines:
+            f = ln.split()
+            if not f:
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+            if f[0] == 'max':
+                mx = float(f[1])
+            elif f[0] == 'err':
+                err = ln.strip()
+            else:
+                try:
+                    t, c, m = float(f[0]), float(f[1]), int(f[2])
+                except Exception:
+                    continue
+                if (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1):
+                    sm.append(c)
+                    mask |= m
+        reasons = sorted(n for n, b in self.BITS.items() if mask & b)
+        out = {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx, 'reasons': reasons,
+               'samples': len(sm), 'source': 'nvml polled every 2 ms by a side process, samples inside the timed window'}
+        if err:
+            out['error'] = err
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -156,8 +200,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--workload', default='spat_gt5')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--compute', default=None, help="override: fp32x | tf32 | bf16")
@@ -167,7 +211,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
-        if args.steps == 30:
+        if args.steps == 100:
             args.steps = 5
         return run_reference(args)
 
@@ -185,6 +229,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     L = _lib.lib()
+    sampler = ClockSampler(local)
+    sampler.start()              # side process: up and polling NVML long before the timed region starts
 
     w, batch = synth.workload(args.workload, seed=1 + rank)       # every rank its own shard of queries
     compute = args.compute or COMPUTE[args.workload]
@@ -215,18 +261,18 @@ def main():
     for _ in range(args.warmup):
         step(resident)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     n0 = L.vog_launch_count()
     barrier()
+    sampler.mark_begin()
     for i in range(args.steps):
         flush.zero_()
         ev0[i].record()
         step(resident)
         ev1[i].record()
     barrier()
+    sampler.mark_end()
     launches = (L.vog_launch_count() - n0) // args.steps      # eager launches of libvog_b200 per step
     if mdl.use_cuda_graph:                                     # + the kernels captured in the replayed graph
         launches += int(getattr(mdl, 'graph_launches', 0))

@@ -147,6 +147,17 @@ int vog_tc_gemm_gres(const void* A, int64_t lda, const void* W, int64_t ldw, int
                      const float* res_lang, int64_t ldl, int dv, int nfrm, int nsrl, int nppf2,
                      float* out_f32, int64_t ldc, void* out_lp, int64_t ldlp, int lp_kind, void* stream);
 
+/* The scorer: lin2[0] GEMM with lin2[2], the inverse regroup and the output masks fused into its epilogue
+ * (N <= 256 = one column tile, so a thread owns a whole output row in tensor memory):
+ *   logit = relu(A[m,:] . W^T + bias) . w2 + b2 for token m = ((b*nfrm + f)*nsrl + s)*nppf2 + p, written to
+ *   logits / scores [B,nsrl,P] (P = nfrm*nppf2 = ncmp*nfrm0*nppf) with scores = sigmoid(logit) * srl_msk[b,s] *
+ *   cmp_msk[b, vid(p)] (int64 masks).  The [M, N] hidden matrix never reaches HBM.  replaces lin2 + un-regroup +
+ * masks: code/mdl_vog.py:224-230,675-677,724-737, code/mdl_conc_single.py:39-48,118-122,144-154. */
+int vog_tc_gemm_lin2(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int tf32,
+                     const float* bias, const float* w2, const float* b2, const int64_t* srl_msk,
+                     const int64_t* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl, int nppf2,
+                     int ncmp, int nppf, int nfrm0, int spat, void* stream);
+
 /* One layer of the bidirectional LSTM recurrence of the language encoder, both directions, all
  * timesteps, in one persistent launch (packed-sequence semantics from the device-side `lens`, no
  * host synchronisation):  gx [T*Bq, ldg >= 8H] = W_ih x + b_ih + b_hh for every (t, b) (time-major

@@ -121,3 +121,29 @@ def test_factored_qkv_and_gathered_residual_match_materialised_tokens(B, nfrm, n
     got_out, _ = ops.tc_gemm_gres(a, wo, vis, lang, nfrm, nsrl, nppf2)
     torch.cuda.synchronize()
     assert torch.allclose(ref_out, got_out, atol=2e-4, rtol=0)      # split-K vs single pass: summation order only
+
+
+@pytest.mark.parametrize('B,nfrm,nsrl,nppf2,ncmp,spat,mode', [(2, 10, 5, 20, 4, True, 'tf32'), (2, 40, 5, 5, 4, False, 'tf32'),
+                                                                (1, 10, 5, 400, 4, True, 'bf16'), (3, 10, 2, 7, 1, True, 'bf16')])
+def test_fused_scorer_tail_matches_gemm_plus_tail(B, nfrm, nsrl, nppf2, ncmp, spat, mode):
+    """vog_tc_gemm_lin2 (lin2[2] + un-regroup + sigmoid*masks inside the GEMM epilogue) against
+    vog_tc_gemm followed by vog_lin2_tail, and against float64."""
+    kind = ops.LP_BF16 if mode == 'bf16' else ops.LP_TF32
+    nfrm0 = 10
+    nppf = nppf2 // ncmp if spat else nppf2
+    M, K, N = B * nfrm * nsrl * nppf2, 768, 256
+    a = ops.cast_lp(_u((M, K), 31).to(DEV), kind)
+    w1 = ops.cast_lp((_u((N, K), 32) * 0.05).to(DEV), kind)
+    b1, w2, b2 = _u((N,), 33).to(DEV), _u((1, N), 34).to(DEV), _u((1,), 35).to(DEV)
+    g = torch.Generator().manual_seed(36)
+    srl = torch.randint(0, 2, (B, nsrl), generator=g).to(DEV)
+    cmp_ = torch.randint(0, 2, (B, ncmp), generator=g).to(DEV)
+    h, _ = ops.tc_gemm(a, w1, bias=b1, relu=True)
+    lg0, sc0 = ops.lin2_tail(h, w2, b2, srl, cmp_, B, nfrm, nsrl, nppf2, ncmp, nppf, nfrm0, spat)
+    lg1, sc1 = ops.tc_gemm_lin2(a, w1, b1, w2, b2, srl, cmp_, B, nfrm, nsrl, nppf2, ncmp, nppf, nfrm0, spat)
+    torch.cuda.synchronize()
+    assert torch.allclose(lg0, lg1, atol=2e-4, rtol=0)
+    assert torch.allclose(sc0, sc1, atol=1e-4, rtol=0)
+    href = torch.relu(a.double().cpu() @ w1.double().cpu().t() + b1.double().cpu())
+    lref = (href @ w2.double().cpu().t()).view(B, nfrm, nsrl, nppf2).permute(0, 2, 1, 3).reshape(B, 1, nsrl, nfrm * nppf2) + b2.double().cpu()
+    assert (lg1.cpu().double() - lref).abs().max() < 1e-3

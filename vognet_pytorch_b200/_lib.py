@@ -58,6 +58,8 @@ _SIGNATURES = {
                         c_i64, c_int, P, c_i64, P],
     'vog_tc_gemm_qkv_factored': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_i64, c_int, c_int,
                                  c_int, P, P, P, P],
+    'vog_tc_gemm_lin2': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int,
+                         c_int, c_int, c_int, c_int, c_int, P],
     'vog_tc_gemm_gres': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64, P, c_i64,
                          c_int, c_int, c_int, c_int, P, c_i64, P, c_i64, c_int, P],
     'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],

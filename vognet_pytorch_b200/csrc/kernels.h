@@ -50,6 +50,13 @@ struct TcEpilogue {
     const float* res_vis = nullptr; long long ldv = 0;
     const float* res_lang = nullptr; long long ldl = 0;
     int dv = 0;
+    // mode 3: scorer tail fused into the lin2[0] GEMM (BN == N <= 256, one column tile per row block):
+    //   logit[m] = relu(acc[m,:] + bias) . w2 + b2, inverse regroup of token m = (b, f, s, p) to [B,nsrl,P],
+    //   score = sigmoid(logit) * srl_msk[b,s] * cmp_msk[b, vid(p)]  -  the [M, N] hidden matrix is never written
+    const float* w2 = nullptr; const float* b2 = nullptr;
+    const long long* srl_msk = nullptr; const long long* cmp_msk = nullptr;
+    float* logits = nullptr; float* scores = nullptr;
+    int ncmp = 0, nppf = 0, nfrm0 = 0, spat = 0;
 };
 int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int tf32,
             int BN, const TcEpilogue& epi, void* workspace, long long workspace_bytes, cudaStream_t st);

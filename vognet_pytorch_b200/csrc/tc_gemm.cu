@@ -118,7 +118,7 @@ __device__ __forceinline__ void epi_apply_store(const TcEpilogue& e, int M, int 
 // ---- epilogues: one per kernel instantiation so that each kernel carries only the code it runs ----
 // All three read the accumulator 32 columns at a time (thread = TMEM lane = output row); the next
 // chunk's tcgen05.ld is issued before the current chunk is stored so TMEM latency is hidden.
-enum { EPI_FAST = 0, EPI_QKV = 1, EPI_GENERIC = 2, EPI_QKVF = 3 };
+enum { EPI_FAST = 0, EPI_QKV = 1, EPI_GENERIC = 2, EPI_QKVF = 3, EPI_LIN2 = 4 };
 
 // transpose a 32x32 fp32 chunk through the warp's swizzled smem patch: row = lane on the way in ...
 __device__ __forceinline__ void patch_store(float* patch, int lane, const uint32_t (&r)[32]) {
@@ -361,6 +361,53 @@ __device__ __forceinline__ void epi_qkvf(const GemmParams& p, const TcEpilogue& 
     }
 }
 
+// EPI_LIN2 (TcEpilogue mode 3): the scorer tail inside the lin2[0] GEMM.  Thread = output row: it walks the
+// row's BN = N accumulator columns once, h = relu(acc + bias), logit = h . w2 + b2, and writes the logit and
+// the masked sigmoid score at the row's inverse-regrouped position.  Only the first warp of every TMEM lane
+// quarter works (the row dot product is not split across warps); nothing of the [M, N] hidden matrix reaches HBM.
+__device__ __forceinline__ void epi_lin2(const GemmParams& p, const TcEpilogue& pe, uint32_t t_acc, uint32_t tfull,
+                                         uint32_t parity, int m_blk, int g, int half, int lane)
+{
+    mbar_wait(tfull, parity);
+    tc_fence_after();
+    if (half != 0) return;
+    const long long m = (long long)m_blk * GM_BM + 32 * g + lane;
+    float acc = 0.f;
+    uint32_t r[32];
+    tmem_ld32(t_acc, r);
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (c0 + 32 < p.BN) tmem_ld32(t_acc + c0 + 32, r);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(pe.bias + c0) + j4);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(pe.w2 + c0) + j4);
+            acc = fmaf(fmaxf(v[4 * j4 + 0] + b4.x, 0.f), w4.x, acc);
+            acc = fmaf(fmaxf(v[4 * j4 + 1] + b4.y, 0.f), w4.y, acc);
+            acc = fmaf(fmaxf(v[4 * j4 + 2] + b4.z, 0.f), w4.z, acc);
+            acc = fmaf(fmaxf(v[4 * j4 + 3] + b4.w, 0.f), w4.w, acc);
+        }
+    }
+    if (m >= p.M) return;
+    long long t = m;
+    const int pp = (int)(t % pe.nppf2); t /= pe.nppf2;
+    const int s_ = (int)(t % pe.nsrl); t /= pe.nsrl;
+    const int f = (int)(t % pe.nfrm);
+    const int b = (int)(t / pe.nfrm);
+    const int P = pe.nfrm * pe.nppf2;
+    const int pidx = f * pe.nppf2 + pp;                     // proposal index inside the query
+    const int vid = pe.spat ? (pidx / pe.nppf) % pe.ncmp : pidx / (pe.nfrm0 * pe.nppf);
+    const float logit = acc + __ldg(pe.b2);
+    const size_t o = ((size_t)b * pe.nsrl + s_) * P + pidx;
+    pe.logits[o] = logit;
+    const float mk = (float)pe.srl_msk[(size_t)b * pe.nsrl + s_] * (float)pe.cmp_msk[(size_t)b * pe.ncmp + vid];
+    pe.scores[o] = (1.f / (1.f + expf(-logit))) * mk;
+}
+
 // EPI_GENERIC: any N / alignment / row replication (guarded element-wise fallbacks inside)
 __device__ __forceinline__ void epi_generic(const GemmParams& p, const TcEpilogue& pe, float* patch, uint32_t t_acc,
                                             uint32_t tfull, uint32_t parity, int m_blk, int n_blk, int g, int half,
@@ -517,6 +564,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 epi_qkv(p, p.e, patch, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
             } else if constexpr (kEpi == EPI_QKVF) {
                 epi_qkvf(p, p.e, patch, lqs, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
+            } else if constexpr (kEpi == EPI_LIN2) {
+                epi_lin2(p, p.e, t_acc, tf, acc_ph, m_blk, g, half, lane);
             } else {
                 epi_generic(p, p.e, patch, t_acc, tf, acc_ph, m_blk, n_blk, g, half, lane);
             }
@@ -654,6 +703,12 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
             VOG_REQUIRE(epi.ldq >= N && epi.ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.lq) & 15) == 0,
                         "tc_gemm: language projection must be 16-byte aligned rows");
         }
+    } else if (epi.mode == 3) {
+        VOG_REQUIRE(BN == N && N <= 256 && N % 32 == 0, "tc_gemm: fused scorer tail needs one column tile (N=%d, BN=%d)", N, BN);
+        VOG_REQUIRE(epi.bias && epi.w2 && epi.b2 && epi.srl_msk && epi.cmp_msk && epi.logits && epi.scores,
+                    "tc_gemm: fused scorer tail: null operand");
+        VOG_REQUIRE((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(epi.w2) & 15) == 0,
+                    "tc_gemm: fused scorer tail: bias / w2 must be 16-byte aligned");
     } else {
         VOG_REQUIRE(epi.out_f32 || epi.out_lp, "tc_gemm: no output");
     }
@@ -691,7 +746,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     p.e = epi;
     {   // unguarded float4 epilogue when every row segment the kernel touches is 16-byte aligned
         auto al = [](const void* q, int a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
-        bool ok = (N % BN == 0) && epi.rep == 1 && epi.mode == 0;
+        bool ok = (N % BN == 0) && epi.rep == 1 && epi.mode == 0;     // modes 1-3 have their own epilogues
         if (p.splits > 1) ok = (N % BN == 0) && epi.mode == 0 && al(workspace, 16);
         else {
             ok = ok && (!epi.bias || al(epi.bias, 16));
@@ -708,7 +763,8 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + GM_EPI_BYTES + p.lq_stage;
     const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
     const int grid = nitems < num_sms() ? nitems : num_sms();
-    const int epi_kind = epi.mode == 1 ? EPI_QKV : epi.mode == 2 ? EPI_QKVF : (p.fast ? EPI_FAST : EPI_GENERIC);
+    const int epi_kind = epi.mode == 1 ? EPI_QKV : epi.mode == 2 ? EPI_QKVF : epi.mode == 3 ? EPI_LIN2
+                         : (p.fast ? EPI_FAST : EPI_GENERIC);
     VOG_REQUIRE(!epi.res_vis || epi_kind == EPI_FAST, "tc_gemm: gathered residual needs the aligned fast epilogue "
                 "(N %% BN == 0, dv %% BN == 0, 16-byte aligned rows)");
 #define VOG_GEMM_LAUNCH(TF, EP)                                                                                   \
@@ -720,11 +776,13 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
         if (epi_kind == EPI_FAST) VOG_GEMM_LAUNCH(true, EPI_FAST);
         else if (epi_kind == EPI_QKV) VOG_GEMM_LAUNCH(true, EPI_QKV);
         else if (epi_kind == EPI_QKVF) VOG_GEMM_LAUNCH(true, EPI_QKVF);
+        else if (epi_kind == EPI_LIN2) VOG_GEMM_LAUNCH(true, EPI_LIN2);
         else VOG_GEMM_LAUNCH(true, EPI_GENERIC);
     } else {
         if (epi_kind == EPI_FAST) VOG_GEMM_LAUNCH(false, EPI_FAST);
         else if (epi_kind == EPI_QKV) VOG_GEMM_LAUNCH(false, EPI_QKV);
         else if (epi_kind == EPI_QKVF) VOG_GEMM_LAUNCH(false, EPI_QKVF);
+        else if (epi_kind == EPI_LIN2) VOG_GEMM_LAUNCH(false, EPI_LIN2);
         else VOG_GEMM_LAUNCH(false, EPI_GENERIC);
     }
 #undef VOG_GEMM_LAUNCH

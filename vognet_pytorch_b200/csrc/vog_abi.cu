@@ -171,6 +171,27 @@ int vog_tc_gemm_qkv_factored(const void* A, int64_t lda, const void* Wvis, int64
     return tc_gemm(A, lda, Wvis, ldw, M, 3 * n_heads * dhp, K, tf32, dhp, e, nullptr, 0, (cudaStream_t)stream);
 }
 
+int vog_tc_gemm_lin2(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int tf32,
+                     const float* bias, const float* w2, const float* b2, const int64_t* srl_msk,
+                     const int64_t* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl, int nppf2,
+                     int ncmp, int nppf, int nfrm0, int spat, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N > 0 && K > 0, "vog_tc_gemm_lin2: bad dimension");
+    if (M == 0) return 0;
+    if (require_sm100("vog_tc_gemm_lin2")) return -1;
+    VOG_REQUIRE(A && W, "vog_tc_gemm_lin2: null operand");
+    VOG_REQUIRE(B > 0 && nfrm > 0 && nsrl > 0 && nppf2 > 0 && (long long)B * nfrm * nsrl * nppf2 == M,
+                "vog_tc_gemm_lin2: M must be B*nfrm*nsrl*nppf2");
+    VOG_REQUIRE(ncmp > 0 && nppf > 0 && nfrm0 > 0 && nfrm * nppf2 == ncmp * nfrm0 * nppf,
+                "vog_tc_gemm_lin2: inconsistent frame/proposal grouping");
+    TcEpilogue e;
+    e.mode = 3; e.bias = bias; e.relu = 1; e.w2 = w2; e.b2 = b2;
+    e.srl_msk = (const long long*)srl_msk; e.cmp_msk = (const long long*)cmp_msk;
+    e.logits = logits; e.scores = scores;
+    e.nfrm = nfrm; e.nsrl = nsrl; e.nppf2 = nppf2; e.ncmp = ncmp; e.nppf = nppf; e.nfrm0 = nfrm0; e.spat = spat;
+    return tc_gemm(A, lda, W, ldw, M, N, K, tf32, N, e, nullptr, 0, (cudaStream_t)stream);
+}
+
 int vog_tc_gemm_gres(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int tf32,
                      int BN, const float* bias, int relu, const float* res_vis, int64_t ldv,
                      const float* res_lang, int64_t ldl, int dv, int nfrm, int nsrl, int nppf2,

@@ -257,9 +257,16 @@ class VOGNetB200(nn.Module):
         x = torch.empty(B * P, self.ps_dim, device=dev, dtype=torch.float32)
         x_lp = torch.empty(B * P, self.ps_dim, device=dev, dtype=lp_dtype)
         pe_ = self.prop_encoder[0].out_features
-        ops.tc_gemm(ops.cast_lp(feat.reshape(B * P, -1), kind),
-                    self._lp_weight('prop', self.prop_encoder[0].weight, kind),
-                    bias=self.prop_encoder[0].bias, relu=True, out_f32=x[:, :pe_], out_lp=x_lp[:, :pe_])
+        if kind == ops.LP_BF16:
+            # bf16 mode: the 2048-wide region features are read ONCE, as the fp32 A operand of a tf32 MMA (the
+            # tensor core drops the low mantissa bits - finer than a bf16 rounding), instead of a cast pass
+            # (read fp32 + write bf16) followed by a bf16 GEMM
+            ops.tc_gemm(feat.reshape(B * P, -1), self._lp_weight('prop_tf32', self.prop_encoder[0].weight, ops.LP_TF32),
+                        bias=self.prop_encoder[0].bias, relu=True, out_f32=x[:, :pe_], out_lp=x_lp[:, :pe_])
+        else:
+            ops.tc_gemm(ops.cast_lp(feat.reshape(B * P, -1), kind),
+                        self._lp_weight('prop', self.prop_encoder[0].weight, kind),
+                        bias=self.prop_encoder[0].bias, relu=True, out_f32=x[:, :pe_], out_lp=x_lp[:, :pe_])
         ops.tc_gemm(ops.cast_lp(seg.reshape(B * nvf, -1), kind),
                     self._lp_weight('seg', self.seg_encoder[0].weight, kind),
                     bias=self.seg_encoder[0].bias, relu=True, out_f32=x[:, pe_:], out_lp=x_lp[:, pe_:],
@@ -305,12 +312,17 @@ class VOGNetB200(nn.Module):
             xm, xm_lp = self.mult_txf._exec.run_factored(ft, bias, self.compute, need_f32=False)
         else:
             xm, xm_lp = ops.build_xmul(x.contiguous(), lang2, B, nfrm, nsrl, nppf2, kind)
-        h, _ = ops.tc_gemm(xm_lp.reshape(-1, self.vl_dim), self._lp_weight('lin2', self.lin2[0].weight, kind),
-                           bias=self.lin2[0].bias, relu=True)
-        # lin2[2] + inverse regroup + sigmoid * masks in one kernel
-        logits, ev = ops.lin2_tail(h, self.lin2[2].weight, self.lin2[2].bias, srl_msk.reshape(B, nsrl),
-                                   cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, self.num_sampled_frm,
-                                   self.CONC_TYPE == 'spat')
+        w1 = self._lp_weight('lin2', self.lin2[0].weight, kind)
+        if w1.shape[0] <= 256 and w1.shape[0] % 32 == 0:
+            # lin2[0] GEMM with lin2[2] + inverse regroup + sigmoid * masks fused into its epilogue
+            logits, ev = ops.tc_gemm_lin2(xm_lp.reshape(-1, self.vl_dim), w1, self.lin2[0].bias, self.lin2[2].weight,
+                                          self.lin2[2].bias, srl_msk.reshape(B, nsrl), cmp_msk, B, nfrm, nsrl, nppf2,
+                                          ncmp, nppf, self.num_sampled_frm, self.CONC_TYPE == 'spat')
+        else:
+            h, _ = ops.tc_gemm(xm_lp.reshape(-1, self.vl_dim), w1, bias=self.lin2[0].bias, relu=True)
+            logits, ev = ops.lin2_tail(h, self.lin2[2].weight, self.lin2[2].bias, srl_msk.reshape(B, nsrl),
+                                       cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, self.num_sampled_frm,
+                                       self.CONC_TYPE == 'spat')
         return {'mdl_outs': logits, 'mdl_outs_eval': ev}
 
     # -- CUDA-graph execution: the whole forward is ONE graph per (compute, shapes) signature with

@@ -408,6 +408,25 @@ def build_xmul(vis, lang, B, nfrm, nsrl, nppf2, kind):
     return out, out_lp
 
 
+def tc_gemm_lin2(a, w, bias, w2, b2, srl_msk, cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, nfrm0, spat):
+    """Scorer with its tail fused into the GEMM epilogue (see vog_tc_gemm_lin2) -> logits, scores [B,1,nsrl,P]."""
+    tf32 = _is_tf32(a, w)
+    M, K = a.shape
+    N = w.shape[0]
+    _req(bias, torch.float32, 'bias', 1), _req(srl_msk, torch.int64, 'srl_msk'), _req(cmp_msk, torch.int64, 'cmp_msk')
+    if w.shape[1] != K or M != B * nfrm * nsrl * nppf2 or w2.numel() != N:
+        raise ValueError('tc_gemm_lin2: inconsistent shapes')
+    P = nfrm * nppf2
+    logits = torch.empty(B, 1, nsrl, P, device=a.device, dtype=torch.float32)
+    scores = torch.empty_like(logits)
+    L = _lib.lib()
+    _lib.check(L.vog_tc_gemm_lin2(_ptr(a), _rowmajor2d(a, 'a'), _ptr(w), _rowmajor2d(w, 'w'), M, N, K, tf32,
+                                  _ptr(bias.contiguous()), _ptr(w2.contiguous()), _ptr(b2), _ptr(srl_msk.contiguous()),
+                                  _ptr(cmp_msk.contiguous()), _ptr(logits), _ptr(scores), B, nfrm, nsrl, nppf2,
+                                  ncmp, nppf, nfrm0, int(spat), _stream()), 'vog_tc_gemm_lin2')
+    return logits, scores
+
+
 def lin2_tail(h, w2, b2, srl_msk, cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, nfrm0, spat):
     """h [M,K] f32 -> logits, scores [B,1,nsrl,P] (see vog_lin2_tail)."""
     _req(h, torch.float32, 'h', 2), _req(srl_msk, torch.int64, 'srl_msk'), _req(cmp_msk, torch.int64, 'cmp_msk')
