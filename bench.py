@@ -245,6 +245,11 @@ def main():
 
     host = {k: v.pin_memory() for k, v in batch.items()}
     resident = {k: v.to(dev) for k, v in batch.items()}
+    if mdl.use_cuda_graph:
+        # "inputs already resident in HBM": the resident batch lives in the captured forward's own input tensors,
+        # so the timed step is the graph replay alone (no staging copies)
+        with torch.no_grad():
+            resident = mdl.graph_input_buffers(resident)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def barrier():

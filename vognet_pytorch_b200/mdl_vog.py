@@ -18,6 +18,8 @@ What runs where
 ``sep``/``svsq`` concatenation (code/mdl_conc_sep.py) is outside the hot-path scope (SURVEY.md
 section 2 row 7) and raises NotImplementedError in the selector.
 """
+import os
+
 import torch
 from torch import nn
 from torch.nn import functional as F
@@ -313,7 +315,10 @@ class VOGNetB200(nn.Module):
         else:
             xm, xm_lp = ops.build_xmul(x.contiguous(), lang2, B, nfrm, nsrl, nppf2, kind)
         w1 = self._lp_weight('lin2', self.lin2[0].weight, kind)
-        if w1.shape[0] <= 256 and w1.shape[0] % 32 == 0:
+        # the fused epilogue needs BN = N (one column tile per 128 rows): worth it once those tiles fill the GPU,
+        # small problems keep narrow tiles + the tail kernel
+        fuse_min = int(os.environ.get('VOG_FUSED_LIN2_MIN_ROWS', 128 * 64))
+        if w1.shape[0] <= 256 and w1.shape[0] % 32 == 0 and xm_lp.shape[0] >= fuse_min:
             # lin2[0] GEMM with lin2[2] + inverse regroup + sigmoid * masks fused into its epilogue
             logits, ev = ops.tc_gemm_lin2(xm_lp.reshape(-1, self.vl_dim), w1, self.lin2[0].bias, self.lin2[2].weight,
                                           self.lin2[2].bias, srl_msk.reshape(B, nsrl), cmp_msk, B, nfrm, nsrl, nppf2,
@@ -333,7 +338,8 @@ class VOGNetB200(nn.Module):
                    'num_cmp_msk', 'srl_arg_words_ind', 'srl_arg_word_mask', 'srl_arg_word_mask_len',
                    'srl_arg_words_capture')
 
-    def _forward_tc_graph(self, inp, ncmp):
+    def _graph_for(self, inp, ncmp):
+        """The captured forward for this (compute mode, shapes) signature; captured on first use."""
         feat = inp['pad_region_feature']
         key = (self.compute, ncmp, feat.device.index) + tuple(tuple(inp[k].shape) for k in self._GRAPH_KEYS)
         graphs = self.__dict__.setdefault('_graphs', {})
@@ -363,9 +369,26 @@ class VOGNetB200(nn.Module):
             # kernels of libvog_b200 captured into the graph = launches per replay
             g = dict(st=st, graph=graph, out=out, launches=_lib.lib().vog_launch_count() - n0)
             graphs[key] = g
+        return g
+
+    def graph_input_buffers(self, inp):
+        """The static input tensors of the captured forward for batches shaped like ``inp`` (captured now if
+        needed).  A caller that writes its batches straight into these tensors (e.g. as the destination of its
+        host-to-device copies) and passes the same dict to ``forward`` skips the staging copies: ``forward``
+        only copies inputs whose storage differs from the graph's."""
+        g = self._graph_for(inp, inp['new_srl_idxs'].shape[1])
+        buf = dict(g['st'])
+        for k, v in inp.items():                    # keys the graph does not read (only shapes matter) pass through
+            buf.setdefault(k, v)
+        return buf
+
+    def _forward_tc_graph(self, inp, ncmp):
+        g = self._graph_for(inp, ncmp)
         self.graph_launches = g['launches']
         for k, buf in g['st'].items():
-            buf.copy_(inp[k], non_blocking=True)
+            src = inp[k]
+            if src.data_ptr() != buf.data_ptr() or src.stride() != buf.stride():
+                buf.copy_(src, non_blocking=True)
         g['graph'].replay()
         return {k: v.clone() for k, v in g['out'].items()}
 
