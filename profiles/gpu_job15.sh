@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_model_tc.py -x -q > gpurun_out/pytest_model.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_model.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_model.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_model.log
 timeout 300 python bench.py --no-seq4000 > gpurun_out/bench_spat_gt5.json 2> gpurun_out/bench_spat_gt5.err
 VOG_FUSED_LIN2_MIN_ROWS=0 timeout 300 python bench.py --no-seq4000 --no-cpu-baseline > gpurun_out/bench_spat_gt5_fused.json 2> gpurun_out/bench_spat_gt5_fused.err
 timeout 300 python bench.py --workload spat_p100 --steps 20 --no-seq4000 > gpurun_out/bench_spat_p100.json 2> gpurun_out/bench_spat_p100.err

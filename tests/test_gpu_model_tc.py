@@ -105,3 +105,29 @@ def test_cuda_graph_execution_matches_eager(name, mode):
         assert torch.equal(eager, graph), (seed, (eager - graph).abs().max().item())
         outs.append(graph)
     assert not torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('B', [0, 1])
+def test_single_and_empty_query_batches(B):
+    """B = 1 (fewer rows than one 128-row GEMM tile in every language GEMM) matches the oracle; B = 0 returns
+    empty outputs instead of launching anything out of bounds."""
+    from oracle import vog_oracle as vo
+    w, batch = synth.workload('spat_gt5')
+    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
+    sel = vb.get_mdl_loss_eval(cfg)
+    mdl = sel['mdl'](cfg, comm)
+    sd = synth.make_state_dict()
+    mdl.load_state_dict(sd, strict=True)
+    mdl = mdl.to(DEV).eval().set_compute('tf32')
+    sub = {k: v[:B].clone() for k, v in batch.items()}
+    out = mdl(synth.clone_batch(sub, DEV))
+    torch.cuda.synchronize()
+    assert out['mdl_outs_eval'].shape == (B, 1, 5, 200)
+    if B:
+        with torch.no_grad():
+            ref = vo.vog_forward(sd, sub, w['conc_type'], w['nppf'])
+        assert (out['mdl_outs_eval'].cpu() - ref['mdl_outs_eval']).abs().max() < 1e-3
+        ev = sel['eval'](cfg, comm, DEV)
+        s = ev.get_out_results_boxes(out, synth.clone_batch(sub, DEV))
+        r = vo.select_boxes(out['mdl_outs_eval'].cpu(), sub['pad_proposals'], w['conc_type'], w['ncmp'], w['nppf'])
+        assert torch.equal(s['boxes'].cpu(), r['boxes']) and torch.equal(s['indexs'].cpu(), r['indexs'])

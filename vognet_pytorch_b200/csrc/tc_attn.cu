@@ -445,10 +445,17 @@ tc_attn_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
 // S is double buffered; the issue order S_0 S_1 | PV_0 S_2 | PV_1 S_3 ... makes the in-order tensor pipe
 // resolve the write-after-read on the buffer P_j was read from.  TMEM: O [0,256) | Q [256,384) | S/P 2 x 64.
 // =================================================================================================
-__global__ void __launch_bounds__(FA_THREADS, 1)
+// NPART = softmax threads per query row (2 or 4): 4*NPART softmax warps (warp w: TMEM lane quarter w % 4, key
+// columns [(w / 4) * 64/NPART, ...) of every tile) + one control warpgroup (K producer, MMA issuer, V producer).
+// With 4 threads per row every scheduler holds four softmax warps instead of two - the softmax is latency /
+// issue bound, not MUFU bound - at 104 registers per softmax thread.
+template <int NPART>
+__global__ void __launch_bounds__(128 * NPART + 128, 1)
 tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v,
                 const AttnParams p)
 {
+    constexpr int CW = 4 * NPART;                     // first control warp
+    constexpr int EL = FA_BKV / NPART;                // keys of a tile handled by one softmax thread
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t smem_base = raw_u32;              // 128B-swizzled tiles need 1024-byte alignment
@@ -479,7 +486,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
     const uint32_t q_ready = bar_base + 8u * (4 * FA_MAX_STAGES + 6);
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(
         smem_gen + bar_off + 8 * (4 * FA_MAX_STAGES + 8));
-    float* xchg = reinterpret_cast<float*>(smem_gen + bar_off + 384);     // [2 parity][128 rows][2 halves]
+    float* xchg = reinterpret_cast<float*>(smem_gen + bar_off + 384);     // [2 parity][128 rows][NPART]
 
     // thread-block cluster of C CTAs = C query tiles of the same (sequence, head): every K / V tile is fetched
     // from L2 ONCE per cluster - CTA r loads the 64/C-key slice r and multicasts it into all C shared memories
@@ -489,18 +496,18 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // roles: warps 0-7 softmax (two warpgroups), warp 8 TMA producer, warp 9 MMA issuer; the control
     // warps carry the HIGHEST warp ids because the SM's issue arbiter favours them
-    if (warp == 8 && lane == 0) {
+    if (warp == CW && lane == 0) {
         tma_prefetch_desc(&tma_k);
         tma_prefetch_desc(&tma_v);
         for (int s = 0; s < NS; ++s) {
             mbar_init(k_full(s), 1); mbar_init(k_empty(s), C);        // a slot is free when ALL CTAs of the cluster read it
             mbar_init(v_full(s), 1); mbar_init(v_empty(s), C);
         }
-        for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 256); mbar_init(pv_done(b), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 128 * NPART); mbar_init(pv_done(b), 1); }
         mbar_init(q_ready, 256);
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
+    if (warp == CW + 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     if (C > 1) cluster_sync_all();                     // peers' barriers are initialised before anyone multicasts
@@ -512,15 +519,16 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
 
     const int bh = bt * p.H + h;
 
-    if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // the control warpgroup hands registers ...
-    if (warp == 8 || warp == 10) {
+    if (warp >= CW) {
+    if constexpr (NPART == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // the control warpgroup hands registers ...
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == CW || warp == CW + 2) {
         // ================= producers: warp 8 streams the K tiles, warp 10 the V tiles =================
         // Warp-uniform loops with BLOCKING mbarrier waits (a waiting warp takes no issue slots from the softmax
         // warps of its scheduler) and one elected lane per TMA instruction.  The former single polling lane
         // under `if (lane == 0)` issued every K tile ~5000 cycles late (profiles/r1/attention.md): each
         // UTMALDG sat in an ELECT / BRA.U.ANY loop and the poll loop starved next to two busy softmax warps.
-        const bool is_k = warp == 8;
+        const bool is_k = warp == CW;
         const CUtensorMap* tm = is_k ? &tma_k : &tma_v;
         const uint32_t ring0 = is_k ? k_smem0 : v_smem0;
         for (int j = 0; j < T; ++j) {
@@ -545,7 +553,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             }
             __syncwarp();
         }
-    } else if (warp == 9) {
+    } else if (warp == CW + 1) {
         // ================= MMA issuer =================
         // The WHOLE warp runs the control flow (waits, loop counters stay warp-uniform) and one elected lane
         // issues the tcgen05 instructions: under a divergent `if (lane == 0)` the compiler has to wrap every
@@ -629,40 +637,43 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");     // ... to the two softmax warpgroups
+        if constexpr (NPART == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");     // ... to the softmax warpgroups
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= softmax / correction / epilogue =================
-        // two threads per query row: warps 0-3 take key columns [0,32) of every 64-key tile, warps 4-7
-        // columns [32,64); the pair (same TMEM lane quarter) exchanges its row maxima through smem and
-        // a 64-thread named barrier, keeps PARTIAL row sums (combined once at the end) and splits the
-        // accumulator columns between them for the lazy rescale and the epilogue
+        // NPART threads per query row: warp w takes key columns [part*EL, part*EL + EL) of every 64-key tile,
+        // part = w / 4; the threads of a row (same TMEM lane quarter) exchange their row maxima through smem
+        // and a named barrier, keep PARTIAL row sums (combined once at the end) and split the accumulator
+        // columns between them for the lazy rescale and the epilogue
         const int g = warp & 3;
-        const int half = warp >> 2;
+        const int part = warp >> 2;
         const int row = 32 * g + lane;                  // row inside the tile == TMEM lane
         const int qi = q_tile * FA_BQ + row;            // query index inside the sequence
         const bool row_ok = qi < N;
         const uint32_t lane_addr = (uint32_t)(32 * g) << 16;
-        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory"); };
+        auto row_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(32 * NPART) : "memory"); };
         float ai = 0.f;
         if (p.bias_mode == 1 && row_ok)
             ai = (__ldg(p.a + ((size_t)bt * p.nbox + qi % p.nbox) * p.H + h) + __ldg(p.bpe + h)) * p.c;
         const float* dense_row = nullptr;
         if (p.bias_mode == 2 && row_ok) dense_row = p.dense + (((size_t)bt * N + qi) * N) * p.H + h;
         float m_run = -1e30f, l_run = 0.f;
-        const int ocols = dhp >> 1;                     // accumulator columns owned by this thread's half
+        const int ocols = dhp / NPART;                  // accumulator columns owned by this thread (multiple of 16)
 
 #ifdef VOG_ATTN_PROFILE     // build with -DVOG_ATTN_PROFILE for the clock64 phase breakdown (profiles/attn_phases.py)
         const bool do_prof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0 && lane == 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tprev = do_prof ? clock64() : 0;
+#undef VOG_PROF
 #define VOG_PROF(i) if (do_prof) { const long long tn = clock64(); pc[i] += tn - tprev; tprev = tn; }
 #else
+#undef VOG_PROF
 #define VOG_PROF(i)
 #endif
-        // ---- Q tile -> tensor memory (A operand of every S = Q K^T of this CTA: never re-read from smem).  The
-        //      row's head-dim half of this thread: dhp/2 bf16 = dhp/4 packed words at columns half*dhp/4 ...
-        {
+        // ---- Q tile -> tensor memory (A operand of every S = Q K^T of this CTA: never re-read from smem): done by
+        //      the first two threads of every row, each one head-dim half = dhp/4 packed words at columns part*dhp/4
+        if (part < 2) {
             const uint4* qsrc = reinterpret_cast<const uint4*>(
-                p.q + (((size_t)bh * N + (row_ok ? qi : 0)) * dhp) + half * (dhp >> 1));
+                p.q + (((size_t)bh * N + (row_ok ? qi : 0)) * dhp) + part * (dhp >> 1));
             for (int c16 = 0; c16 < (dhp >> 6); ++c16) {           // 16 words (32 bf16) per tcgen05.st
                 uint32_t w[16];
 #pragma unroll
@@ -670,26 +681,25 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
                     const uint4 t = row_ok ? __ldg(qsrc + c16 * 4 + v4) : make_uint4(0u, 0u, 0u, 0u);
                     w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
                 }
-                tmem_st16(tmem_q + lane_addr + half * (dhp >> 2) + c16 * 16, w);
+                tmem_st16(tmem_q + lane_addr + part * (dhp >> 2) + c16 * 16, w);
             }
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(q_ready);
         }
-        // software pipeline: the score tile S_{j+1} (TMEM) and its bias factors (global, L1/L2) are
-        // requested while tile j is exponentiated / packed, so their latencies are off the critical path
-        uint32_t rn[32];
-        float4 an[8];
+        uint32_t rn[EL];
+        float4 an[EL / 4];
         auto load_bias = [&](int jj) {
             const float4* ak4 = reinterpret_cast<const float4*>(p.ak_seq + (size_t)bh * p.ak_ld +
-                                                                (size_t)jj * FA_BKV + half * 32);
+                                                                (size_t)jj * FA_BKV + part * EL);
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) an[c4] = __ldg(ak4 + c4);
+            for (int c4 = 0; c4 < EL / 4; ++c4) an[c4] = __ldg(ak4 + c4);
         };
         auto load_scores = [&](int jj) {
             mbar_wait(s_full(jj & 1), (uint32_t)((jj >> 1) & 1));
             tc_fence_after();
-            tmem_ld32(tmem_s0 + lane_addr + (jj & 1) * FA_BKV + half * 32, rn);
+            if constexpr (EL == 32) tmem_ld32(tmem_s0 + lane_addr + (jj & 1) * FA_BKV + part * EL, rn);
+            else tmem_ld16(tmem_s0 + lane_addr + (jj & 1) * FA_BKV + part * EL, rn);
         };
         if (p.bias_mode == 1) load_bias(0);
         load_scores(0);
@@ -697,63 +707,63 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             const int sb = j & 1;
             tmem_wait_ld();
             VOG_PROF(0)
-            uint32_t (&r0)[32] = rn;
-            float4 (&a4)[8] = an;
             VOG_PROF(1)
-            float sv[32];
+            float sv[EL];
             if (p.bias_mode == 1) {
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    sv[4 * c4 + 0] = fmaf(__uint_as_float(r0[4 * c4 + 0]), p.c, fmaxf(ai - a4[c4].x, 0.f));
-                    sv[4 * c4 + 1] = fmaf(__uint_as_float(r0[4 * c4 + 1]), p.c, fmaxf(ai - a4[c4].y, 0.f));
-                    sv[4 * c4 + 2] = fmaf(__uint_as_float(r0[4 * c4 + 2]), p.c, fmaxf(ai - a4[c4].z, 0.f));
-                    sv[4 * c4 + 3] = fmaf(__uint_as_float(r0[4 * c4 + 3]), p.c, fmaxf(ai - a4[c4].w, 0.f));
+                for (int c4 = 0; c4 < EL / 4; ++c4) {
+                    sv[4 * c4 + 0] = fmaf(__uint_as_float(rn[4 * c4 + 0]), p.c, fmaxf(ai - an[c4].x, 0.f));
+                    sv[4 * c4 + 1] = fmaf(__uint_as_float(rn[4 * c4 + 1]), p.c, fmaxf(ai - an[c4].y, 0.f));
+                    sv[4 * c4 + 2] = fmaf(__uint_as_float(rn[4 * c4 + 2]), p.c, fmaxf(ai - an[c4].z, 0.f));
+                    sv[4 * c4 + 3] = fmaf(__uint_as_float(rn[4 * c4 + 3]), p.c, fmaxf(ai - an[c4].w, 0.f));
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(r0[c]) * p.c;
+                for (int c = 0; c < EL; ++c) sv[c] = __uint_as_float(rn[c]) * p.c;
                 if (p.bias_mode == 2 && row_ok) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int key = j * FA_BKV + half * 32 + c;
+                    for (int c = 0; c < EL; ++c) {
+                        const int key = j * FA_BKV + part * EL + c;
                         if (key < N) sv[c] += __ldg(dense_row + (size_t)key * p.H) * p.c;
                     }
                 }
             }
             if ((j + 1) * FA_BKV > N) {                // ragged last tile: keys >= N do not exist
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (j * FA_BKV + half * 32 + c >= N) sv[c] = -INFINITY;
+                for (int c = 0; c < EL; ++c)
+                    if (j * FA_BKV + part * EL + c >= N) sv[c] = -INFINITY;
             }
             float mx0 = fmaxf(sv[0], sv[1]), mx1 = fmaxf(sv[2], sv[3]), mx2 = fmaxf(sv[4], sv[5]), mx3 = fmaxf(sv[6], sv[7]);
 #pragma unroll
-            for (int c = 8; c < 32; c += 4) {
+            for (int c = 8; c < EL; c += 4) {
                 mx0 = fmaxf(mx0, sv[c]); mx1 = fmaxf(mx1, sv[c + 1]); mx2 = fmaxf(mx2, sv[c + 2]); mx3 = fmaxf(mx3, sv[c + 3]);
             }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));     // -inf when this half has no valid key
-            float* xr = xchg + ((j & 1) * FA_BQ + row) * 2;
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));     // -inf when this slice has no valid key
+            float* xr = xchg + ((j & 1) * FA_BQ + row) * NPART;
             VOG_PROF(2)
-            xr[half] = mx;
-            pair_sync();
+            xr[part] = mx;
+            row_sync();
             VOG_PROF(3)
-            const float m_new = fmaxf(m_run, fmaxf(mx, xr[half ^ 1]));
+            float m_new = m_run;
+#pragma unroll
+            for (int q = 0; q < NPART; ++q) m_new = fmaxf(m_new, xr[q]);
             if (j == 0) {
                 m_run = m_new;
             } else {
                 const bool grow = (m_new - m_run) > FA_RESCALE_T;
                 if (__any_sync(0xffffffffu, grow)) {
-                    // rescale this thread's half of the accumulator row; PV_{j-1} must have landed first
+                    // rescale this thread's slice of the accumulator row; PV_{j-1} must have landed first
                     const float alpha = grow ? fast_exp2(m_run - m_new) : 1.f;
                     if (grow) { m_run = m_new; l_run *= alpha; }
                     mbar_wait(pv_done((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
                     tc_fence_after();
-                    for (int c0 = half * ocols; c0 < (half + 1) * ocols; c0 += 32) {
-                        uint32_t o[32];
-                        tmem_ld32(tmem_o + lane_addr + c0, o);
+                    for (int c0 = part * ocols; c0 < (part + 1) * ocols; c0 += 16) {
+                        uint32_t o[16];
+                        tmem_ld16(tmem_o + lane_addr + c0, o);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-                        tmem_st32(tmem_o + lane_addr + c0, o);
+                        for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+                        tmem_st16(tmem_o + lane_addr + c0, o);
                     }
                     tmem_wait_st();
                 }
@@ -762,7 +772,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             VOG_PROF(7)
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
+            for (int c = 0; c < EL; c += 4) {
                 sv[c] = fast_exp2(sv[c] - m_run); s0 += sv[c];
                 sv[c + 1] = fast_exp2(sv[c + 1] - m_run); s1 += sv[c + 1];
                 sv[c + 2] = fast_exp2(sv[c + 2] - m_run); s2 += sv[c + 2];
@@ -771,13 +781,14 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             l_run += (s0 + s1) + (s2 + s3);
             VOG_PROF(4)
             VOG_PROF(5)
-            // P_j (bf16 pairs) overwrites S_j in place: this thread's 32 probabilities -> 16 words at columns
-            // half*16 of buffer j&1.  Every S_j column was read (both threads of the row passed pair_sync)
+            // P_j (bf16 pairs) overwrites S_j in place: this thread's EL probabilities -> EL/2 words at columns
+            // part*EL/2 of buffer j&1.  Every S_j column was read (all threads of the row passed row_sync)
             {
-                uint32_t pw[16];
+                uint32_t pw[EL / 2];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) pw[i] = pack_bf16(sv[2 * i], sv[2 * i + 1]);
-                tmem_st16(tmem_s0 + lane_addr + sb * FA_BKV + half * 16, pw);
+                for (int i = 0; i < EL / 2; ++i) pw[i] = pack_bf16(sv[2 * i], sv[2 * i + 1]);
+                if constexpr (EL == 32) tmem_st16(tmem_s0 + lane_addr + sb * FA_BKV + part * (EL / 2), pw);
+                else tmem_st8(tmem_s0 + lane_addr + sb * FA_BKV + part * (EL / 2), pw);
                 tmem_wait_st();
             }
             tc_fence_before();
@@ -789,39 +800,41 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
 #ifdef VOG_ATTN_PROFILE
         if (do_prof) { for (int i = 0; i < 8; ++i) p.prof[i] = pc[i]; p.prof[12] = T; }
 #endif
-        // ---- epilogue: O / l  (row sum = the two partial sums of the pair)
+        // ---- epilogue: O / l  (row sum = the partial sums of the row's threads)
         {
-            float* xr = xchg + ((T & 1) * FA_BQ + row) * 2;
-            xr[half] = l_run;
-            pair_sync();
-            l_run += xr[half ^ 1];
+            float* xr = xchg + ((T & 1) * FA_BQ + row) * NPART;
+            xr[part] = l_run;
+            row_sync();
+            l_run = 0.f;
+#pragma unroll
+            for (int q = 0; q < NPART; ++q) l_run += xr[q];
         }
         mbar_wait(pv_done((T - 1) & 1), (uint32_t)(((T - 1) >> 1) & 1));
         tc_fence_after();
         const float inv_l = 1.f / l_run;
         const int n_pv = (dh + 15) & ~15;
-        for (int c0 = half * ocols; c0 < (half + 1) * ocols; c0 += 32) {
-            uint32_t o[32];
-            float v[32];
+        for (int c0 = part * ocols; c0 < (part + 1) * ocols; c0 += 16) {
+            uint32_t o[16];
+            float v[16];
             if (c0 < n_pv) {
-                tmem_ld32(tmem_o + lane_addr + c0, o);
+                tmem_ld16(tmem_o + lane_addr + c0, o);
                 tmem_wait_ld();
             }
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = (c0 + c < n_pv) ? __uint_as_float(o[c]) * inv_l : 0.f;
+            for (int c = 0; c < 16; ++c) v[c] = (c0 + c < n_pv) ? __uint_as_float(o[c]) * inv_l : 0.f;
             if (row_ok) {
                 const size_t off = ((size_t)bt * N + qi) * p.ldo + (size_t)h * dhp + c0;
                 if (p.out_kind == 1) {
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
 #pragma unroll
-                    for (int c = 0; c < 32; c += 8)
+                    for (int c = 0; c < 16; c += 8)
                         *reinterpret_cast<uint4*>(dst + c) =
                             make_uint4(pack_bf16(v[c], v[c + 1]), pack_bf16(v[c + 2], v[c + 3]),
                                        pack_bf16(v[c + 4], v[c + 5]), pack_bf16(v[c + 6], v[c + 7]));
                 } else {
                     float* dst = reinterpret_cast<float*>(p.out) + off;
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4)
+                    for (int c = 0; c < 16; c += 4)
                         *reinterpret_cast<float4*>(dst + c) =
                             make_float4(to_tf32(v[c]), to_tf32(v[c + 1]), to_tf32(v[c + 2]), to_tf32(v[c + 3]));
                 }
@@ -830,7 +843,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (warp == CW + 1) tmem_dealloc(tmem_base, p.tmem_cols);
     if (C > 1) cluster_sync_all();                     // no CTA leaves while a peer may still signal its barriers
 }
 
@@ -854,9 +867,9 @@ long long tc_attn_workspace_bytes(int Bt, int N, int H)
 }
 
 static long long* g_attn_prof = nullptr;
-static int g_attn_impl = 2;             // 1 = Q/P through shared memory (v1), 2 = Q/P in tensor memory (v2)
+static int g_attn_impl = 2;             // 1 = Q/P through smem (v1); Q/P in tensor memory with 2 (v2) / 4 (v3) softmax threads per row
 static int g_attn_cluster = 0;          // 0 = default (no cluster); 2 / 4 = multicast K/V loads across query tiles
-void tc_attn_set_impl(int impl) { g_attn_impl = impl == 1 ? 1 : 2; }
+void tc_attn_set_impl(int impl) { g_attn_impl = (impl >= 1 && impl <= 3) ? impl : 2; }
 void tc_attn_set_cluster(int c) { g_attn_cluster = c; }
 void tc_attn_set_prof(long long* buf) { g_attn_prof = buf; }
 
@@ -896,7 +909,8 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
         if (check_launch("bias_expand")) return -1;
     }
     p.q = reinterpret_cast<const __nv_bfloat16*>(q);
-    if (g_attn_impl == 2) {
+    if (g_attn_impl >= 2) {
+        const int npart = g_attn_impl == 2 ? 2 : 4;
         p.tmem_cols = 512;
         const int qtiles = cdiv(N, FA_BQ);
         // measured on B200 (profiles/r1/attention.md): multicast clusters LOSE 13-30 % here - the limiter is each SM's
@@ -912,23 +926,25 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
         uint32_t bk2[3] = {64, (uint32_t)(FA_BKV / C), 1};       // every CTA of a cluster loads a 64/C-key slice
         if (make_tmap(&tk2, k, 2, 1, 3, dq2, sq2, bk2)) return -1;
         if (make_tmap(&tv2, v, 2, 1, 3, dq2, sq2, bk2)) return -1;
-        const int fixed2 = 384 /*barriers*/ + 2 * FA_BQ * 2 * 4 /*pair exchange*/;
+        const int fixed2 = 384 /*barriers*/ + 2 * FA_BQ * npart * 4 /*row-max exchange*/;
         const int stage_bytes2 = 2 * FA_BKV * dhp * 2;
         int stages2 = (227 * 1024 - fixed2) / stage_bytes2;
         if (stages2 > FA_MAX_STAGES) stages2 = FA_MAX_STAGES;
         p.stages = stages2;
         const size_t smem2 = (size_t)fixed2 + (size_t)stages2 * stage_bytes2;
-        VOG_CUDA(cudaFuncSetAttribute(tc_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        if (npart == 2) VOG_CUDA(cudaFuncSetAttribute(tc_attn2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        else VOG_CUDA(cudaFuncSetAttribute(tc_attn2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(qtiles, H, Bt);
-        cfg.blockDim = dim3(FA_THREADS, 1, 1);
+        cfg.blockDim = dim3(128 * npart + 128, 1, 1);
         cfg.dynamicSmemBytes = smem2;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        VOG_CUDA(cudaLaunchKernelEx(&cfg, tc_attn2_kernel, tk2, tv2, p));
+        if (npart == 2) VOG_CUDA(cudaLaunchKernelEx(&cfg, tc_attn2_kernel<2>, tk2, tv2, p));
+        else VOG_CUDA(cudaLaunchKernelEx(&cfg, tc_attn2_kernel<4>, tk2, tv2, p));
         return check_launch("tc_attn2");
     }
     const int cols = dhp + 3 * FA_BKV;

@@ -217,6 +217,9 @@ class VOGNetB200(nn.Module):
         if not feat.is_cuda:
             raise RuntimeError('vognet_pytorch_b200 runs on CUDA only (no CPU path); move the batch '
                                'and the module to a B200 device')
+        if feat.shape[0] == 0:                       # empty batch: nothing to launch
+            z = feat.new_zeros(0, 1, inp['srl_arg_words_ind'].shape[2], feat.shape[1])
+            return {'mdl_outs': z, 'mdl_outs_eval': z.clone()}
         with torch.no_grad():
             if self.compute == 'fp32x':
                 return self._forward_fp32x(inp)
