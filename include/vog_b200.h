@@ -202,6 +202,22 @@ int vog_lang_gather(const float* full, int D, const int64_t* cap, int T, int Bq,
 int vog_mask_rows(const float* x, const int64_t* msk, int rows, int D, float* out, void* out_lp, int lp_kind,
                   void* stream);
 
+/* Grounding loss, forward (LossB_SPAT / LossB_TEMP): logits [B,nsrl,P] f32,
+ * props [B,P,pdim] (x1,y1,x2,y2,...), gt [B,K,5], frm_mask [B,P,K] u8 (1 = frames differ / padded),
+ * pnt_mask [B,P] u8, srl_boxes / srl_lens [B,nsrl,nb] int64 (gt-box index and 0/1 validity per argument slot),
+ * arg_boxes_mask [B,nsrl], cmp_msk [B,ncmp], target_cmp [B] int64.  target(b,s,p) = max_i(IoU(p, gt[srl_boxes
+ * [b,s,i]]) * frm|pnt mask * [vid(p) == target_cmp[b]] * srl_lens[b,s,i]) > 0.5 (bit-exact: IEEE fp32 in the
+ * reference's operation order); loss[0] = mean over {arg_boxes_mask[b,s] * cmp_msk[b,vid(p)] != 0} of
+ * BCE-with-logits(logit, target) * P * loss_lambda (plain mean when no argument has boxes).  targets
+ * [B,nsrl,P] u8 may be NULL; workspace: vog_loss_workspace_bytes().  replaces
+ * code/mdl_conc_single.py:191-311,342-433 + utils/box_utils.py:54-118. */
+int64_t vog_loss_workspace_bytes(int B, int nsrl, int P);
+int vog_loss_fwd(const float* logits, const float* props, int pdim, const float* gt, const uint8_t* frm_mask,
+                 const uint8_t* pnt_mask, const int64_t* srl_boxes, const int64_t* srl_lens,
+                 const int64_t* arg_boxes_mask, const int64_t* cmp_msk, const int64_t* target_cmp, int B, int nsrl,
+                 int nb, int P, int K, int ncmp, int nppf, int spat, float loss_lambda, uint8_t* targets,
+                 void* workspace, float* loss, void* stream);
+
 /* ---- debug hooks (not part of the data path) ----------------------------------------------------
  * vog_debug_gemm_trace: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of every
  * following vog_tc_gemm launch (entry, setup done, first TMA issued, first stage landed, last MMA

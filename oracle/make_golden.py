@@ -90,6 +90,23 @@ def model_case(name):
           f'obj {tuple(keep["obj_out"].shape)} mul {tuple(keep["mul_out"].shape)}  {sz:.2f} MB')
 
 
+def loss_case(name):
+    """LossB_SPAT / LossB_TEMP of the unmodified reference on the golden logits of `name` and the synthetic
+    loss inputs -> tests/golden/loss_{name}.npz (loss value, boolean targets packed as uint8)."""
+    w, batch = synth.workload(name)
+    gold = np.load(os.path.join(GOLD, f'{name}.npz'))
+    out = {'mdl_outs': torch.from_numpy(gold['mdl_outs'])}
+    inp = dict(batch)
+    inp.update(synth.make_loss_inputs(batch, **w))
+    loss_fn = rh.build_reference_loss(w['conc_type'], w['nppf'])
+    with torch.no_grad():
+        res = loss_fn(out, {k: v.clone() for k, v in inp.items()})
+        tg = loss_fn.compute_loss_targets({k: v.clone() for k, v in inp.items()})['targets_one']
+    np.savez(os.path.join(GOLD, f'loss_{name}.npz'), loss=res['loss'].numpy(), mdl_out_loss=res['mdl_out_loss'].numpy(),
+             targets=np.packbits(tg.numpy().astype(np.uint8)), targets_shape=np.array(tg.shape))
+    print(f'loss_{name}: loss {float(res["loss"]):.6f}  positives {int(tg.sum())} of {tg.numel()}')
+
+
 OPS = {
     'rel_d512_h3_l2':  dict(d=512, n_heads=3, n_layers=2, Bt=2, N=37, rel=True),
     'rel_d768_h3_l1':  dict(d=768, n_heads=3, n_layers=1, Bt=3, N=50, rel=True),
@@ -107,3 +124,6 @@ if __name__ == '__main__':
     for nm in synth.WORKLOADS:
         if not want or nm in want:
             model_case(nm)
+    for nm in synth.WORKLOADS:
+        if not want or ('loss_' + nm) in want:
+            loss_case(nm)

@@ -119,6 +119,32 @@ def build_reference_evaluator(conc_type, nppf, ncmp):
     return ev
 
 
+def _byte_mask_compat():
+    """The reference targets PyTorch 1.1, where ``torch.masked_select`` took uint8 masks
+    (code/mdl_conc_single.py:306,410 pass ``boxes_msk.byte()``); torch >= 1.2 wants bool.  Version shim only:
+    the mask is reinterpreted, no arithmetic changes."""
+    import torch
+    if getattr(torch.masked_select, '_vog_compat', False):
+        return
+    orig = torch.masked_select
+
+    def masked_select(inp, mask, *a, **k):
+        return orig(inp, mask.bool() if mask.dtype == torch.uint8 else mask, *a, **k)
+    masked_select._vog_compat = True
+    torch.masked_select = masked_select
+
+
+def build_reference_loss(conc_type, nppf):
+    """Unmodified LossB_SPAT / LossB_TEMP (code/mdl_conc_single.py:180-433)."""
+    _install_stubs()
+    _byte_mask_compat()
+    import mdl_conc_single  # noqa
+    cfg = reference_cfg(conc_type)
+    comm = Munch(vocab_size=1000, detect_size=10, itod={}, wtoi={'UNK': 0}, num_prop_per_frm=nppf)
+    cls = {'spat': mdl_conc_single.LossB_SPAT, 'temp': mdl_conc_single.LossB_TEMP}[conc_type]
+    return cls(cfg, comm)
+
+
 def reference_transformers():
     _install_stubs()
     import transformer_code  # noqa

@@ -256,3 +256,52 @@ def select_boxes(mdl_outs_eval, pad_proposals, conc_type, ncmp, nppf, nfrm0=10):
     pr = pad_proposals.view(B, 1, ncmp, nfrm0, nppf, pd).expand(B, nsrl, ncmp, nfrm0, nppf, pd)
     bx = torch.gather(pr, -2, ix[..., None, None].expand(B, nsrl, ncmp, nfrm0, 1, pd)).squeeze(-2)
     return {'boxes': bx, 'scores': sc, 'indexs': torch.zeros(B, nsrl, nfrm0, dtype=torch.int64)}
+
+
+# ---------------------------------------------------------------------------------------------
+# loss: code/mdl_conc_single.py:180-433 + utils/box_utils.py:54-118
+# ---------------------------------------------------------------------------------------------
+def bbox_overlaps_batch(anchors, gt_boxes, frm_mask):
+    """utils/box_utils.py:61-118 restated: +1 pixel convention, overlaps MULTIPLIED by frm_mask (:108-110),
+    zero-area gt boxes -> 0, zero-area anchors -> -1."""
+    a, g = anchors[..., :4], gt_boxes[..., :4]
+    gx, gy = g[..., 2] - g[..., 0] + 1, g[..., 3] - g[..., 1] + 1
+    ax, ay = a[..., 2] - a[..., 0] + 1, a[..., 3] - a[..., 1] + 1
+    g_area, a_area = (gx * gy)[:, None, :], (ax * ay)[:, :, None]
+    iw = (torch.min(a[:, :, None, 2], g[:, None, :, 2]) - torch.max(a[:, :, None, 0], g[:, None, :, 0]) + 1).clamp(min=0)
+    ih = (torch.min(a[:, :, None, 3], g[:, None, :, 3]) - torch.max(a[:, :, None, 1], g[:, None, :, 1]) + 1).clamp(min=0)
+    ua = a_area + g_area - iw * ih
+    ov = iw * ih / ua
+    ov = ov * frm_mask.to(ov.dtype)
+    ov = ov.masked_fill(((gx == 1) & (gy == 1))[:, None, :].expand_as(ov), 0)
+    ov = ov.masked_fill(((ax == 1) & (ay == 1))[:, :, None].expand_as(ov), -1)
+    return ov
+
+
+def loss_forward(mdl_outs, inp, conc_type, ncmp, nppf, nfrm0=10, loss_lambda=1.0):
+    """LossB_SPAT / LossB_TEMP.forward restated (code/mdl_conc_single.py:191-311 TEMP, :342-433 SPAT):
+    IoU targets of the target video's proposals against the gt boxes of every SRL argument (> 0.5), BCE with
+    logits, mean over the (argument has boxes) x (video valid) mask, times the number of proposals.
+    -> {'loss', 'mdl_out_loss'} and the boolean targets [B,1,nsrl,P]."""
+    props, gt = inp['pad_proposals'], inp['pad_gt_bboxs']
+    frm = inp['pad_frm_mask'] | inp['pad_pnt_mask'].unsqueeze(-1)                   # :229-231
+    ov = bbox_overlaps_batch(props[:, :, :5], gt[:, :, :5], frm)
+    B, P, K = ov.shape
+    idx = torch.arange(P)
+    vid = (idx // nppf) % ncmp if conc_type == 'spat' else idx // (P // ncmp)      # :255-263 / :350-363
+    ov = ov * (vid[None, :] == inp['target_cmp'].view(B, 1)).to(ov.dtype)[:, :, None]
+    sb, sl = inp['srl_boxes'], inp['srl_boxes_lens']                              # [B,1,nsrl,nb]
+    nsrl, nb = sb.shape[2], sb.shape[3]
+    g = torch.gather(ov.view(B, 1, 1, P, K).expand(B, 1, nsrl, P, K), -1,
+                     sb.view(B, 1, nsrl, 1, nb).expand(B, 1, nsrl, P, nb))        # :207-218
+    g = g * sl.float().unsqueeze(-2)
+    targets = g.max(dim=-1)[0] > 0.5                                              # :226
+    tot = torch.nn.functional.binary_cross_entropy_with_logits(mdl_outs, targets.float(), reduction='none')
+    bm = inp['srl_arg_boxes_mask'].view(B, 1, nsrl, 1).float() * inp['num_cmp_msk'].view(B, 1, 1, ncmp).float()
+    if conc_type == 'spat':                                                      # :399-407
+        bm = bm.view(B, 1, nsrl, 1, ncmp, 1).expand(B, 1, nsrl, nfrm0, ncmp, nppf).reshape(B, 1, nsrl, P)
+    else:                                                                        # :296-301
+        bm = bm.unsqueeze(-1).expand(B, 1, nsrl, ncmp, P // ncmp).reshape(B, 1, nsrl, P)
+    sel = torch.masked_select(tot, bm.bool()) if inp['srl_arg_boxes_mask'].max() > 0 else tot
+    loss = sel.mean() * tot.size(-1) * loss_lambda
+    return {'loss': loss, 'mdl_out_loss': loss, 'targets': targets}

@@ -1,0 +1,98 @@
+"""Grounding loss.  CPU: the oracle restatement against golden values of the
+UNMODIFIED reference LossB_SPAT / LossB_TEMP (tests/golden/loss_*.npz, made by oracle/make_golden.py).  GPU:
+vog_loss_fwd through the LossB_* modules against the same fixtures - boolean IoU targets bit-exact, loss value
+within 2e-6 relative (transcendentals + summation order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import vognet_pytorch_b200 as vb
+from vognet_pytorch_b200 import synth
+from oracle import vog_oracle as vo          # checker
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+NAMES = list(synth.WORKLOADS)
+
+
+def _case(name):
+    w, batch = synth.workload(name)
+    g = np.load(os.path.join(GOLD, f'{name}.npz'))
+    gl = np.load(os.path.join(GOLD, f'loss_{name}.npz'))
+    inp = dict(batch)
+    inp.update(synth.make_loss_inputs(batch, **w))
+    tg = np.unpackbits(gl['targets'])[:int(np.prod(gl['targets_shape']))].reshape(gl['targets_shape']).astype(bool)
+    return w, inp, torch.from_numpy(g['mdl_outs']), float(gl['loss']), tg
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_oracle_loss_matches_reference(name):
+    w, inp, logits, loss, tg = _case(name)
+    r = vo.loss_forward(logits, inp, w['conc_type'], w['ncmp'], w['nppf'])
+    assert np.array_equal(r['targets'].numpy(), tg)
+    assert tg.sum() > 0, 'fixture must contain positive targets'
+    assert abs(float(r['loss']) - loss) <= 1e-6 * abs(loss)
+
+
+def test_oracle_loss_without_groundable_arguments_is_the_plain_mean():
+    w, inp, logits, _, _ = _case('spat_gt5')
+    inp['srl_arg_boxes_mask'] = torch.zeros_like(inp['srl_arg_boxes_mask'])        # code/mdl_conc_single.py:409-413
+    r = vo.loss_forward(logits, inp, w['conc_type'], w['ncmp'], w['nppf'])
+    tot = torch.nn.functional.binary_cross_entropy_with_logits(logits, r['targets'].float(), reduction='none')
+    assert torch.allclose(r['loss'], tot.mean() * logits.shape[-1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', NAMES)
+def test_cuda_loss_matches_reference(name):
+    w, inp, logits, loss, tg = _case(name)
+    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
+    fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
+    dinp = {k: v.cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        out = fn({'mdl_outs': logits.cuda()}, dinp)
+        got_t = fn.compute_loss_targets(dinp)['targets_one']
+    torch.cuda.synchronize()
+    assert set(out) == {'loss', 'mdl_out_loss'} and out['loss'].shape == ()
+    assert np.array_equal(got_t.cpu().numpy(), tg), 'IoU targets must be bit-exact'
+    assert abs(float(out['loss']) - loss) <= 2e-6 * abs(loss), (float(out['loss']), loss)
+    assert float(out['mdl_out_loss']) == float(out['loss'])
+
+
+@pytest.mark.gpu
+def test_cuda_loss_edge_cases():
+    """no groundable argument -> plain mean; masked-out videos; zero-area proposals (-1 overlap rule)."""
+    w, inp, logits, _, _ = _case('temp_gt5')
+    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
+    fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
+    variants = []
+    a = {k: v.clone() for k, v in inp.items()}
+    a['srl_arg_boxes_mask'] = torch.zeros_like(a['srl_arg_boxes_mask'])
+    variants.append(a)
+    b = {k: v.clone() for k, v in inp.items()}
+    b['num_cmp_msk'][:, 1:3] = 0
+    variants.append(b)
+    c = {k: v.clone() for k, v in inp.items()}
+    c['pad_proposals'][:, ::7, 2] = c['pad_proposals'][:, ::7, 0]          # x2 == x1 and y2 == y1: zero-area anchors
+    c['pad_proposals'][:, ::7, 3] = c['pad_proposals'][:, ::7, 1]
+    c['pad_gt_bboxs'][:, 3] = 0                                             # a zero-area gt box that arguments point at
+    variants.append(c)
+    for v in variants:
+        ref = vo.loss_forward(logits, v, w['conc_type'], w['ncmp'], w['nppf'])
+        with torch.no_grad():
+            dv = {k: t.cuda() for k, t in v.items()}
+            out = fn({'mdl_outs': logits.cuda()}, dv)
+            got_t = fn.compute_loss_targets(dv)['targets_one']
+        assert torch.equal(got_t.cpu(), ref['targets'])
+        assert abs(float(out['loss']) - float(ref['loss'])) <= 2e-6 * abs(float(ref['loss']))
+
+
+@pytest.mark.gpu
+def test_cuda_loss_refuses_autograd():
+    w, inp, logits, _, _ = _case('cpu_ref')
+    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
+    fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
+    x = logits.cuda().requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        fn({'mdl_outs': x}, {k: v.cuda() for k, v in inp.items()})

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libvog_b200.so')
-SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'lstm_rec.cu', 'fused_glue.cu']
+SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'lstm_rec.cu', 'fused_glue.cu', 'loss_fwd.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -44,6 +44,9 @@ _SIGNATURES = {
     'vog_lang_embed': [P, c_int, P, c_int, P, c_int, c_i64, c_int, P, c_int, P],
     'vog_lang_gather': [P, c_int, P, c_int, c_int, c_int, P, c_int, P],
     'vog_mask_rows': [P, P, c_int, c_int, P, P, c_int, P],
+    'vog_loss_workspace_bytes': [c_int, c_int, c_int],
+    'vog_loss_fwd': [P, P, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                     c_float, P, P, P, P],
     'vog_lstm_workspace_bytes': [c_int, c_int],
     'vog_debug_lstm_force_streaming': [c_int],
     'vog_debug_gemm_trace': [P],
@@ -66,7 +69,7 @@ _SIGNATURES = {
 }
 _RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong,
             'vog_tc_gemm_workspace_bytes': ctypes.c_int64, 'vog_lstm_workspace_bytes': ctypes.c_int64,
-            'vog_tc_attn_workspace_bytes': ctypes.c_int64}
+            'vog_tc_attn_workspace_bytes': ctypes.c_int64, 'vog_loss_workspace_bytes': ctypes.c_int64}
 
 
 def sources():

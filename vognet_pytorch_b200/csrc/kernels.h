@@ -97,4 +97,12 @@ int lang_gather(const float* full, int D, const long long* cap, int T, int Bq, i
 int mask_rows(const float* x, const long long* msk, int rows, int D, float* out, void* out_lp, int lp_kind,
               cudaStream_t st);
 
+// ---- loss_fwd.cu : grounding loss, forward ----------------------------------------------------
+long long loss_workspace_bytes(int B, int nsrl, int P);
+int loss_fwd(const float* logits, const float* props, int pdim, const float* gt, const unsigned char* frm_mask,
+             const unsigned char* pnt_mask, const long long* srl_boxes, const long long* srl_lens,
+             const long long* arg_boxes_mask, const long long* cmp_msk, const long long* target_cmp, int B,
+             int nsrl, int nb, int P, int K, int ncmp, int nppf, int spat, float lambda, unsigned char* targets,
+             void* workspace, float* loss, cudaStream_t st);
+
 }  // namespace vog

@@ -317,4 +317,26 @@ int vog_mask_rows(const float* x, const int64_t* msk, int rows, int D, float* ou
     return mask_rows(x, (const long long*)msk, rows, D, out, out_lp, lp_kind, (cudaStream_t)stream);
 }
 
+int64_t vog_loss_workspace_bytes(int B, int nsrl, int P)
+{
+    if (B <= 0 || nsrl <= 0 || P <= 0) return 0;
+    return loss_workspace_bytes(B, nsrl, P);
+}
+
+int vog_loss_fwd(const float* logits, const float* props, int pdim, const float* gt, const uint8_t* frm_mask,
+                 const uint8_t* pnt_mask, const int64_t* srl_boxes, const int64_t* srl_lens,
+                 const int64_t* arg_boxes_mask, const int64_t* cmp_msk, const int64_t* target_cmp, int B, int nsrl,
+                 int nb, int P, int K, int ncmp, int nppf, int spat, float loss_lambda, uint8_t* targets,
+                 void* workspace, float* loss, void* stream)
+{
+    VOG_REQUIRE(B >= 0, "vog_loss_fwd: negative batch");
+    VOG_REQUIRE(B > 0, "vog_loss_fwd: the mean over an empty batch is undefined");
+    VOG_REQUIRE(logits && props && gt && frm_mask && pnt_mask && srl_boxes && srl_lens && arg_boxes_mask && cmp_msk &&
+                target_cmp && workspace && loss, "vog_loss_fwd: null operand");
+    VOG_REQUIRE(pdim >= 4, "vog_loss_fwd: proposals need >= 4 columns");
+    return loss_fwd(logits, props, pdim, gt, frm_mask, pnt_mask, (const long long*)srl_boxes, (const long long*)srl_lens,
+                    (const long long*)arg_boxes_mask, (const long long*)cmp_msk, (const long long*)target_cmp, B, nsrl,
+                    nb, P, K, ncmp, nppf, spat, loss_lambda, targets, workspace, loss, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -3,6 +3,7 @@
 ``eval(cfg, comm, device)``: code/main_dist.py:33-53)."""
 from . import mdl_vog
 from .eval_vsrl_corr import EvaluatorSPAT, EvaluatorTEMP
+from .mdl_conc_single import LossB_SPAT, LossB_TEMP
 
 _MODELS = {
     ('temp', 'igrnd'): mdl_vog.ImgGrnd_TEMP, ('temp', 'vgrnd'): mdl_vog.VidGrnd_TEMP,
@@ -13,14 +14,7 @@ _MODELS = {
 _EVALS = {'temp': EvaluatorTEMP, 'spat': EvaluatorSPAT}
 
 
-class _LossNotBuilt:
-    """LossB_{TEMP,SPAT} (code/mdl_conc_single.py:180-433) is the first 'next' row (SURVEY.md
-    section 8f): the forward-only build exports the name so the selector's dict shape is kept and
-    fails loudly if a training loop tries to instantiate it."""
-
-    def __init__(self, *a, **k):
-        raise NotImplementedError('LossB_* is not built yet (forward/inference scope); '
-                                  'SURVEY.md section 8f row 1')
+_LOSSES = {'temp': LossB_TEMP, 'spat': LossB_SPAT}
 
 
 def get_mdl_loss_eval(cfg):
@@ -30,4 +24,4 @@ def get_mdl_loss_eval(cfg):
                                   'hot-path scope of this build (SURVEY.md section 2 row 7)')
     if (conc_type, mdl_type) not in _MODELS:
         raise NotImplementedError((conc_type, mdl_type))
-    return {'mdl': _MODELS[(conc_type, mdl_type)], 'loss': _LossNotBuilt, 'eval': _EVALS[conc_type]}
+    return {'mdl': _MODELS[(conc_type, mdl_type)], 'loss': _LOSSES[conc_type], 'eval': _EVALS[conc_type]}

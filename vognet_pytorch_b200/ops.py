@@ -438,3 +438,29 @@ def lin2_tail(h, w2, b2, srl_msk, cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, nfr
                                _ptr(cmp_msk.contiguous()), _ptr(logits), _ptr(scores), B, nfrm, nsrl, nppf2,
                                h.shape[1], ncmp, nppf, nfrm0, int(spat), _stream()), 'vog_lin2_tail')
     return logits, scores
+
+
+def loss_fwd(logits, props, gt, frm_mask, pnt_mask, srl_boxes, srl_lens, arg_boxes_mask, cmp_msk, target_cmp,
+             ncmp, nppf, spat, loss_lambda=1.0, want_targets=False):
+    """Grounding loss forward (see vog_loss_fwd): logits [B,nsrl,P] -> loss [1] f32 (and bool targets [B,nsrl,P])."""
+    _req(logits, torch.float32, 'logits', 3), _req(props, torch.float32, 'props', 3), _req(gt, torch.float32, 'gt', 3)
+    _req(frm_mask, torch.uint8, 'frm_mask', 3), _req(pnt_mask, torch.uint8, 'pnt_mask', 2)
+    for t, n in ((srl_boxes, 'srl_boxes'), (srl_lens, 'srl_lens'), (arg_boxes_mask, 'arg_boxes_mask'),
+                 (cmp_msk, 'cmp_msk'), (target_cmp, 'target_cmp')):
+        _req(t, torch.int64, n)
+    B, nsrl, P = logits.shape
+    K, nb = gt.shape[1], srl_boxes.shape[-1]
+    if props.shape[:2] != (B, P) or gt.shape[2] < 4 or frm_mask.shape != (B, P, K) or pnt_mask.shape != (B, P) or \
+            srl_boxes.numel() != B * nsrl * nb or srl_lens.numel() != B * nsrl * nb:
+        raise ValueError('loss_fwd: inconsistent shapes')
+    logits, props, gt = logits.contiguous(), props.contiguous(), gt[:, :, :5].contiguous()
+    L = _lib.lib()
+    ws = torch.empty(L.vog_loss_workspace_bytes(B, nsrl, P), device=logits.device, dtype=torch.uint8)
+    loss = torch.empty(1, device=logits.device, dtype=torch.float32)
+    tg = torch.empty(B, nsrl, P, device=logits.device, dtype=torch.uint8) if want_targets else None
+    _lib.check(L.vog_loss_fwd(_ptr(logits), _ptr(props), props.shape[2], _ptr(gt), _ptr(frm_mask.contiguous()),
+                              _ptr(pnt_mask.contiguous()), _ptr(srl_boxes.contiguous()), _ptr(srl_lens.contiguous()),
+                              _ptr(arg_boxes_mask.contiguous()), _ptr(cmp_msk.contiguous()),
+                              _ptr(target_cmp.contiguous()), B, nsrl, nb, P, K, ncmp, nppf, int(spat),
+                              float(loss_lambda), _ptr(tg), _ptr(ws), _ptr(loss), _stream()), 'vog_loss_fwd')
+    return (loss, tg.bool()) if want_targets else loss

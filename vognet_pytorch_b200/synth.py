@@ -58,7 +58,7 @@ def to_attr(d):
 def default_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
     return to_attr({
         'ds': {'conc_type': conc_type, 'resized_width': 720, 'resized_height': 405,
-               'num_sampled_frm': 10, 't_attn_size': 480, 'max_seq_length': 20},
+               'num_sampled_frm': 10, 't_attn_size': 480, 'max_seq_length': 20, 'max_gt_box': 100},
         'mdl': {
             'name': 'vog', 'seg_feat_dim': 3072, 'prop_feat_dim': 2048,
             'input_encoding_size': 512,
@@ -69,7 +69,8 @@ def default_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
             'mul_tx': {'use_ddp': False, 'to_use': True, 'n_layers': n_layers, 'n_heads': n_heads,
                        'attn_drop': 0.2, 'use_rel': use_rel, 'one_frm': True, 'cross_frm': False},
         },
-        'misc': {'srl_arg_length': 5},
+        'misc': {'srl_arg_length': 5, 'box_per_srl_arg': 4},
+        'loss': {'loss_lambda': 1},
     })
 
 
@@ -262,6 +263,56 @@ def make_batch(conc_type='spat', B=4, ncmp=4, nppf=5, nvalid=None, seed=1, vocab
         'new_srl_idxs': torch.zeros(B, ncmp, dtype=torch.int64),
         'num_cmp_msk': torch.ones(B, ncmp, dtype=torch.int64),
     }
+
+
+MAX_GT_BOX = 100       # ds.max_gt_box
+BOX_PER_SRL = 4        # misc.box_per_srl_arg
+
+
+def make_loss_inputs(batch, conc_type='spat', ncmp=4, nppf=5, seed=1, num_box=12, **_unused):
+    """The extra batch keys the reference loss reads (code/mdl_conc_single.py:191-311, layouts from
+    code/dat_loader_simple.py:405-456,703-779,1170-1200): ground-truth boxes, frame / padding masks, the gt-box
+    indices of every SRL argument, the target video.  Drawn from their own RNG stream, so the forward batch of
+    ``make_batch`` stays bit-identical.  Ground-truth boxes are jittered copies of proposals of the target
+    video placed on the NEXT frame: ``pad_frm_mask`` is 1 where the frames of a proposal and a gt box DIFFER
+    (dat_loader_simple.py:237-255) and the reference multiplies the overlaps by it (utils/box_utils.py:108-110),
+    so this is what produces positive targets."""
+    props = batch['pad_proposals'].numpy()
+    B, P, _ = props.shape
+    nfrm = NFRM0
+    r = _rng(f'loss/{conc_type}/{B}/{ncmp}/{nppf}', seed)
+    idx = np.arange(P)
+    vid = (idx // nppf) % ncmp if conc_type == 'spat' else idx // (nfrm * nppf)
+    gt = np.zeros((B, MAX_GT_BOX, 5), np.float32)
+    target_cmp = r.integers(0, ncmp, size=B).astype(np.int64)
+    srl_boxes = np.zeros((B, 1, NSRL, BOX_PER_SRL), np.int64)
+    srl_lens = np.zeros((B, 1, NSRL, BOX_PER_SRL), np.int64)
+    arg_boxes_mask = np.zeros((B, 1, NSRL), np.int64)
+    inds = batch['srl_arg_inds_msk'].numpy()
+    frame_col = props[..., 4]
+    fmin = frame_col.min()
+    for b in range(B):
+        cand = np.nonzero(vid == target_cmp[b])[0]
+        pick = r.choice(cand, size=num_box, replace=len(cand) < num_box)
+        jit = r.integers(-6, 7, size=(num_box, 4)).astype(np.float32)
+        gt[b, :num_box, :4] = props[b, pick, :4] + jit
+        # next frame of the same video (wraps inside the video's own frame range)
+        f = frame_col[b, pick]
+        base = np.floor((f - fmin) / nfrm) * nfrm + fmin if conc_type == 'temp' else fmin
+        gt[b, :num_box, 4] = base + np.mod(f - base + 1, nfrm)
+        for s_ in range(NSRL):
+            if inds[b, 0, s_] and s_ % 3 != 2:                 # some populated arguments are not groundable
+                n = int(r.integers(1, BOX_PER_SRL + 1))
+                srl_boxes[b, 0, s_, :n] = r.integers(0, num_box, size=n)
+                srl_lens[b, 0, s_, :n] = 1
+                arg_boxes_mask[b, 0, s_] = 1
+    frm_mask = np.ones((B, P, MAX_GT_BOX), np.uint8)
+    frm_mask[:, :, :num_box] = (frame_col[:, :, None] != gt[:, None, :num_box, 4]).astype(np.uint8)
+    pnt_mask = (r.random(size=(B, P)) < 0.02).astype(np.uint8)   # a few padded proposal slots
+    t = torch.from_numpy
+    return {'pad_gt_bboxs': t(gt), 'pad_frm_mask': t(frm_mask), 'pad_pnt_mask': t(pnt_mask),
+            'srl_boxes': t(srl_boxes), 'srl_boxes_lens': t(srl_lens), 'srl_arg_boxes_mask': t(arg_boxes_mask),
+            'target_cmp': t(target_cmp)}
 
 
 def clone_batch(batch, device=None):
