@@ -163,7 +163,7 @@ int vog_tc_gemm_lin2(const void* A, int64_t lda, const void* W, int64_t ldw, int
  * host synchronisation):  gx [T*Bq, ldg >= 8H] = W_ih x + b_ih + b_hh for every (t, b) (time-major
  * rows t*Bq+b; forward gates in columns [0,4H), reverse in [4H,8H), gate order i,f,g,o), whh
  * [2,4H,H] fp32, lens [Bq] int64.  Writes h as [T*Bq, ld_out >= 2H] (forward | reverse) in bf16 or
- * tf32-rounded fp32, zeros where t >= len.  Bq <= 8 per call.  workspace:
+ * tf32-rounded fp32, zeros where t >= len.  Any Bq (groups of 8 sequences per launch).  workspace:
  * vog_lstm_workspace_bytes() bytes.  replaces nn.LSTM + pack/pad:
  * utils/mdl_srl_utils.py:102-108,135-152. */
 int64_t vog_lstm_workspace_bytes(int Bq, int H);

@@ -60,9 +60,10 @@ def _ref_recurrence(gx, whh, lens, T, Bq, H):
 
 @pytest.mark.parametrize('streaming,xmode', [(0, 0), (0, 1), (1, 0)], ids=['resident-tagged', 'resident-flags', 'streaming'])
 @pytest.mark.parametrize('lens_list', [[1, 20, 7, 13], [5], [20, 3], [2, 9, 4], [1, 1, 1, 1], [20] * 8,
-                                       [3, 17, 20, 1, 8, 12]])
+                                       [3, 17, 20, 1, 8, 12], [4, 9, 20, 1, 13, 7, 2, 18, 5, 11, 16]])
 def test_ragged_lengths_and_zero_rows(lens_list, streaming, xmode):
-    """lengths 1..20, including full-length and single-token sentences, 1..8 sequences per launch;
+    """lengths 1..20, including full-length and single-token sentences, 1..11 sequences (more than 8 = several
+    launches over groups of 8);
     both recurrence kernels (weight-resident: W_hh in registers + shared memory, tagged h exchange;
     weight-streaming: W_hh from L2 every step, counter barrier) against a float64 host recurrence."""
     from vognet_pytorch_b200 import ops, _lib

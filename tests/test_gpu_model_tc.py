@@ -131,3 +131,25 @@ def test_single_and_empty_query_batches(B):
         s = ev.get_out_results_boxes(out, synth.clone_batch(sub, DEV))
         r = vo.select_boxes(out['mdl_outs_eval'].cpu(), sub['pad_proposals'], w['conc_type'], w['ncmp'], w['nppf'])
         assert torch.equal(s['boxes'].cpu(), r['boxes']) and torch.equal(s['indexs'].cpu(), r['indexs'])
+
+
+def test_batch_larger_than_one_lstm_group():
+    """B = 10 queries: the language recurrence runs as two launches (8 + 2 sequences), everything else scales."""
+    from oracle import vog_oracle as vo
+    w = dict(synth.WORKLOADS['spat_gt5'])
+    w['B'] = 10
+    batch = synth.make_batch(seed=5, **w)
+    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
+    mdl = vb.get_mdl_loss_eval(cfg)['mdl'](cfg, comm)
+    sd = synth.make_state_dict()
+    mdl.load_state_dict(sd, strict=True)
+    mdl = mdl.to(DEV).eval().set_compute('tf32')
+    mdl.use_cuda_graph = True
+    db = synth.clone_batch(batch, DEV)
+    out = mdl(db)
+    out2 = mdl(db)                                   # graph replay
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = vo.vog_forward(sd, batch, w['conc_type'], w['nppf'])
+    assert (out['mdl_outs_eval'].cpu() - ref['mdl_outs_eval']).abs().max() < 1e-3
+    assert torch.equal(out['mdl_outs_eval'], out2['mdl_outs_eval'])

@@ -33,6 +33,7 @@ struct LstmParams {
     unsigned* counters;                   // [2], zeroed before launch
     void* out_lp; long long ld_out; int lp_kind;   // [T*Bq, 2H] bf16 / tf32-rounded fp32
     int T, Bq, H, U, ctas_per_dir;
+    int bq_total;                         // sequences per timestep row block of gx / out (>= Bq: chunked batches)
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -122,7 +123,7 @@ lstm_rec_kernel(const LstmParams p)
 #pragma unroll
                     for (int b = 0; b < LS_MAXB; ++b)
                         if (b == lane) v = acc[b];
-                    v += p.gx[((size_t)t * Bq + lane) * p.ldg + (size_t)d * 4 * H + row_of(ri)];
+                    v += p.gx[((size_t)t * p.bq_total + lane) * p.ldg + (size_t)d * 4 * H + row_of(ri)];
                     gate_s[(gate * LS_MAXU + uu) * LS_MAXB + lane] = v;
                 }
             }
@@ -145,7 +146,7 @@ lstm_rec_kernel(const LstmParams p)
                 hc_s[uu * LS_MAXB + b] = hval;
             }
             hb[(size_t)b * H + u0 + uu] = hc_s[uu * LS_MAXB + b];
-            store_lp(p.out_lp, ((long long)t * Bq + b) * p.ld_out + (long long)d * H + u0 + uu, hval, p.lp_kind);
+            store_lp(p.out_lp, ((long long)t * p.bq_total + b) * p.ld_out + (long long)d * H + u0 + uu, hval, p.lp_kind);
         }
         // ---- direction-wide barrier, then fetch the complete h_t (bypassing the non-coherent L1)
         __threadfence();
@@ -173,7 +174,7 @@ lstm_rec_kernel(const LstmParams p)
     // rows past the longest sentence: zeros (pad_packed_sequence padding_value=0)
     for (int i = tid; i < (p.T - Tmax) * Bq * nu; i += LS_THREADS) {
         const int uu = i % nu, b = (i / nu) % Bq, t = Tmax + i / (nu * Bq);
-        store_lp(p.out_lp, ((long long)t * Bq + b) * p.ld_out + (long long)d * H + u0 + uu, 0.f, p.lp_kind);
+        store_lp(p.out_lp, ((long long)t * p.bq_total + b) * p.ld_out + (long long)d * H + u0 + uu, 0.f, p.lp_kind);
     }
 }
 
@@ -241,6 +242,7 @@ struct LstmResParams {
     int xmode;
     void* out_lp; long long ld_out; int lp_kind;
     int T, Bq, U, ctas_per_dir;
+    int bq_total;                         // sequences per timestep row block of gx / out (>= Bq: chunked batches)
     long long* trace;                     // debug: [8] accumulated clock64 phases of CTA 0 / thread 0
 };
 
@@ -337,7 +339,7 @@ lstm_rec_resident_kernel(const LstmResParams p)
         const int t = d == 0 ? step : Tmax - 1 - step;
         const float* hcur = h_s + (step & 1) * BQ * H;
         float gxv = 0.f;
-        if (gx_lane) gxv = __ldg(p.gx + ((size_t)t * Bq + my_b) * p.ldg + (size_t)d * 4 * H + (size_t)my_g * H + u);
+        if (gx_lane) gxv = __ldg(p.gx + ((size_t)t * p.bq_total + my_b) * p.ldg + (size_t)d * 4 * H + (size_t)my_g * H + u);
         float acc[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] = 0.f;
@@ -416,7 +418,7 @@ lstm_rec_resident_kernel(const LstmResParams p)
                 else
                     __stcg(reinterpret_cast<float*>(p.hx) + xi, h_reg);
             }
-            store_lp(p.out_lp, ((long long)t * Bq + lane) * p.ld_out + (long long)d * H + u, hval, p.lp_kind);
+            store_lp(p.out_lp, ((long long)t * p.bq_total + lane) * p.ld_out + (long long)d * H + u, hval, p.lp_kind);
         }
         __syncwarp();
         LR_TRACE(2)
@@ -497,7 +499,7 @@ lstm_rec_resident_kernel(const LstmResParams p)
     // rows past the longest sentence: zeros (pad_packed_sequence padding_value=0)
     if (lane < Bq && unit_ok)
         for (int t = Tmax; t < p.T; ++t)
-            store_lp(p.out_lp, ((long long)t * Bq + lane) * p.ld_out + (long long)d * H + u, 0.f, p.lp_kind);
+            store_lp(p.out_lp, ((long long)t * p.bq_total + lane) * p.ld_out + (long long)d * H + u, 0.f, p.lp_kind);
 }
 
 template <int BQ>
@@ -518,10 +520,11 @@ void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
 
 long long lstm_workspace_bytes(int Bq, int H)
 {
+    if (Bq > LS_MAXB) Bq = LS_MAXB;            // larger batches run in groups of LS_MAXB over the same workspace
     return (long long)2 * 2 * Bq * H * 8 + LS_WS_HEADER;   // header (counters / flags) + exchange words
 }
 
-int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
+static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq, int bq_total,
                    int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st)
 {
     if (T == 0 || Bq == 0) return 0;
@@ -545,7 +548,7 @@ int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long 
         rp.xmode = g_lstm_xmode;
         VOG_REQUIRE(2 * per_dir_u * 4 <= LS_WS_HEADER, "lstm_layer_fwd: too many CTAs for the flag header");
         rp.out_lp = out_lp; rp.ld_out = ld_out; rp.lp_kind = lp_kind;
-        rp.T = T; rp.Bq = Bq; rp.U = U; rp.ctas_per_dir = per_dir_u;
+        rp.T = T; rp.Bq = Bq; rp.U = U; rp.ctas_per_dir = per_dir_u; rp.bq_total = bq_total;
         rp.trace = g_lstm_trace;
         VOG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)lstm_workspace_bytes(Bq, H), st));
         const int ctas = 2 * per_dir_u, threads = 32 * U;
@@ -565,12 +568,28 @@ int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long 
     p.counters = reinterpret_cast<unsigned*>(workspace);
     p.hbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + LS_WS_HEADER);
     p.out_lp = out_lp; p.ld_out = ld_out; p.lp_kind = lp_kind;
-    p.T = T; p.Bq = Bq; p.H = H; p.U = U; p.ctas_per_dir = per_dir;
+    p.T = T; p.Bq = Bq; p.H = H; p.U = U; p.ctas_per_dir = per_dir; p.bq_total = bq_total;
     VOG_CUDA(cudaMemsetAsync(workspace, 0, 64, st));
     const size_t smem = sizeof(float) * ((size_t)LS_MAXB * H + 6 * LS_MAXU * LS_MAXB);
     VOG_CUDA(cudaFuncSetAttribute(lstm_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lstm_rec_kernel<<<2 * per_dir, LS_THREADS, smem, st>>>(p);
     return check_launch("lstm_rec");
+}
+
+// Batches of more than LS_MAXB sequences run as consecutive launches over groups of LS_MAXB (the recurrences of
+// different sentences are independent); gx / out rows stay time-major over the WHOLE batch.
+int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
+                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st)
+{
+    VOG_REQUIRE(lp_kind == 1 || lp_kind == 2, "lstm_layer_fwd: bad lp_kind");
+    const size_t esz = lp_kind == 1 ? 2 : 4;
+    for (int b0 = 0; b0 < Bq; b0 += LS_MAXB) {
+        const int nb = Bq - b0 < LS_MAXB ? Bq - b0 : LS_MAXB;
+        if (lstm_layer_chunk(gx + (size_t)b0 * ldg, ldg, whh, lens + b0, T, nb, Bq, H,
+                             reinterpret_cast<char*>(out_lp) + (size_t)b0 * ld_out * esz, ld_out, lp_kind, workspace, st))
+            return -1;
+    }
+    return 0;
 }
 
 }  // namespace vog

@@ -346,14 +346,10 @@ def lstm_layer_fwd(gx, whh, lens, T, Bq, kind):
         raise ValueError('lstm_layer_fwd: inconsistent shapes')
     L = _lib.lib()
     out = torch.empty(T * Bq, 2 * H, device=gx.device, dtype=_LP_DTYPE[kind])
-    for b0 in range(0, Bq, 8):                      # the kernel takes <= 8 sequences per launch
-        nb = min(8, Bq - b0)
-        if Bq > 8:
-            raise NotImplementedError('lstm_layer_fwd: more than 8 sequences per batch')
-        ws = torch.empty(L.vog_lstm_workspace_bytes(nb, H), device=gx.device, dtype=torch.uint8)
-        _lib.check(L.vog_lstm_layer_fwd(_ptr(gx), _rowmajor2d(gx, 'gx'), _ptr(whh), _ptr(lens), T, nb, H,
-                                        _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _stream()),
-                   'vog_lstm_layer_fwd')
+    ws = torch.empty(L.vog_lstm_workspace_bytes(Bq, H), device=gx.device, dtype=torch.uint8)
+    _lib.check(L.vog_lstm_layer_fwd(_ptr(gx), _rowmajor2d(gx, 'gx'), _ptr(whh), _ptr(lens), T, Bq, H,
+                                    _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _stream()),
+               'vog_lstm_layer_fwd')
     return out
 
 
