@@ -435,66 +435,54 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
     return v > bv || (v == bv && i < bi);
 }
 
+// one warp per (b, s, frame): the per-video proposal max / argmax + box gather for each of the ncmp videos, then the
+// argmax over the videos (SPAT) - a single launch, no intermediate round trip
 __global__ void __launch_bounds__(256)
 select_kernel(const float* __restrict__ scores, const float* __restrict__ props, int pdim,
-              float* __restrict__ boxes, float* __restrict__ out_scores,
+              float* __restrict__ boxes, float* __restrict__ out_scores, long long* __restrict__ indexs,
               int B, int nsrl, int ncmp, int nfrm, int nppf, int spat)
 {
-    int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    int ngroups = B * nsrl * ncmp * nfrm;
-    if (g >= ngroups) return;
-    // output order [b][s][vid][frm]
-    int frm = g % nfrm, vid = (g / nfrm) % ncmp, s = (g / (nfrm * ncmp)) % nsrl, b = g / (nfrm * ncmp * nsrl);
-    int P = ncmp * nfrm * nppf;
-    int base = spat ? (frm * ncmp + vid) * nppf : (vid * nfrm + frm) * nppf;
-    const float* sc = scores + ((size_t)b * nsrl + s) * P + base;
-    float bv = 0.f; int bi = 0x7fffffff;
-    bool have = false;
-    for (int i = lane; i < nppf; i += 32) {
-        float v = sc[i];
-        if (!have || better(v, i, bv, bi)) { bv = v; bi = i; have = true; }
-    }
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= B * nsrl * nfrm) return;
+    const int frm = w % nfrm, bs = w / nfrm;            // bs = b*nsrl + s
+    const int b = bs / nsrl;
+    const int P = ncmp * nfrm * nppf;
+    float vbest = 0.f; int vidx = 0;
+    for (int vid = 0; vid < ncmp; ++vid) {
+        const int base = spat ? (frm * ncmp + vid) * nppf : (vid * nfrm + frm) * nppf;
+        const float* sc = scores + (size_t)bs * P + base;
+        float bv = 0.f; int bi = 0x7fffffff;
+        bool have = false;
+        for (int i = lane; i < nppf; i += 32) {
+            float v = sc[i];
+            if (!have || better(v, i, bv, bi)) { bv = v; bi = i; have = true; }
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        bool oh = __shfl_xor_sync(0xffffffffu, (int)have, o);
-        if (oh && (!have || better(ov, oi, bv, bi))) { bv = ov; bi = oi; have = true; }
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            bool oh = __shfl_xor_sync(0xffffffffu, (int)have, o);
+            if (oh && (!have || better(ov, oi, bv, bi))) { bv = ov; bi = oi; have = true; }
+        }
+        const size_t g = ((size_t)bs * ncmp + vid) * nfrm + frm;         // output order [b][s][vid][frm]
+        if (lane == 0) out_scores[g] = bv;
+        const float* pr = props + ((size_t)b * P + base + bi) * pdim;
+        for (int c = lane; c < pdim; c += 32) boxes[g * pdim + c] = pr[c];
+        if (vid == 0 || better(bv, vid, vbest, vidx)) { vbest = bv; vidx = vid; }
     }
-    if (lane == 0) out_scores[g] = bv;
-    const float* pr = props + ((size_t)b * P + base + bi) * pdim;
-    for (int c = lane; c < pdim; c += 32) boxes[(size_t)g * pdim + c] = pr[c];
-}
-
-__global__ void select_vid_kernel(const float* __restrict__ out_scores, long long* __restrict__ indexs,
-                                  int B, int nsrl, int ncmp, int nfrm, int spat)
-{
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * nsrl * nfrm) return;
-    if (!spat) { indexs[idx] = 0; return; }
-    int frm = idx % nfrm, bs = idx / nfrm;
-    float bv = 0.f; int bi = 0;
-    for (int v = 0; v < ncmp; ++v) {
-        float x = out_scores[((size_t)bs * ncmp + v) * nfrm + frm];
-        if (v == 0 || better(x, v, bv, bi)) { bv = x; bi = v; }
-    }
-    indexs[idx] = bi;
+    if (lane == 0) indexs[w] = spat ? vidx : 0;
 }
 
 int select_fwd(const float* scores, const float* props, int pdim, float* boxes, float* out_scores,
                long long* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, int spat,
                cudaStream_t st)
 {
-    int ngroups = B * nsrl * ncmp * nfrm;
-    if (ngroups == 0) return 0;
-    select_kernel<<<cdiv(ngroups, 8), 256, 0, st>>>(scores, props, pdim, boxes, out_scores, B, nsrl,
-                                                    ncmp, nfrm, nppf, spat);
-    int rc = check_launch("select");
-    if (rc) return rc;
-    int n = B * nsrl * nfrm;
-    select_vid_kernel<<<cdiv(n, 256), 256, 0, st>>>(out_scores, indexs, B, nsrl, ncmp, nfrm, spat);
-    return check_launch("select_vid");
+    const int nwarps = B * nsrl * nfrm;
+    if (nwarps == 0) return 0;
+    select_kernel<<<cdiv(nwarps, 8), 256, 0, st>>>(scores, props, pdim, boxes, out_scores, indexs, B, nsrl,
+                                                   ncmp, nfrm, nppf, spat);
+    return check_launch("select");
 }
 
 // =============================================================================================

@@ -670,7 +670,7 @@ int tc_gemm_splits(int M, int N, int K, int tf32, int BN, int qkv_mode)
     const int nkb = cdiv(K, bk);
     const int tiles = cdiv(M, GM_BM) * cdiv(N, BN);
     const int sms = num_sms() > 0 ? num_sms() : 148;
-    if (tiles * 2 > sms || nkb < 8) return 1;
+    if (tiles * 2 > sms || nkb < 16) return 1;          // shallow K: a second (reduction) launch costs more than it saves
     int s = sms / tiles;
     if (s > nkb / 4) s = nkb / 4;            // at least 4 k-blocks per split
     if (s > 32) s = 32;

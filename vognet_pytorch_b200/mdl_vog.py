@@ -291,6 +291,12 @@ class VOGNetB200(nn.Module):
             x, x_lp = self.obj_txf._exec.run(x.view(Bt_o, N_o, self.ps_dim), bias, self.compute,
                                              x_lp=x_lp, want_lp=True)
             x = x.reshape(B * P, self.ps_dim)
+        if self.USE_MUL_TX and self.cfg.mdl.mul_tx.to_use and self.cfg.mdl.mul_tx.use_rel:
+            # the multimodal transformer's bias factors depend on the boxes only: projected here, on the visual
+            # branch, so they are off the critical path after the language/visual join
+            nfrm_m, _ = self._groups(ncmp)
+            self._a_mul = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
+                                         self.vid_w, self.vid_h, float(nfrm_m))
         return x, x_lp
 
     def _fusion_tc(self, x, x_lp, lang, props, srl_msk, cmp_msk, ncmp):
@@ -307,8 +313,10 @@ class VOGNetB200(nn.Module):
             mtx = self.cfg.mdl.mul_tx
             bias = None
             if mtx.use_rel:
-                a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
-                                   self.vid_w, self.vid_h, float(nfrm))
+                a = self.__dict__.pop('_a_mul', None)
+                if a is None or a.shape[0] != B * P:
+                    a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
+                                       self.vid_w, self.vid_h, float(nfrm))
                 bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
             lang_lp = self.__dict__.pop('_lang_lp', None)       # produced next to `lang` by language_encode_tc
             if lang_lp is None or lang_lp.shape != lang2.shape:
