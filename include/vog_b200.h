@@ -172,6 +172,14 @@ int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int
                        int Bq, int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace,
                        void* stream);
 
+/* SM partitioning between the concurrent branches of one forward (host-side state, read at launch / graph-capture
+ * time).  vog_lstm_set_max_ctas(n > 0): the following vog_lstm_layer_fwd launches use at most n SMs (weight-streaming
+ * kernel, many hidden units per CTA) instead of the weight-resident kernel that needs every SM; vog_set_reserved_sms(n):
+ * the persistent vog_tc_gemm* grids leave n SMs free.  Used when the visual branch is much longer than the language
+ * branch (100 proposals per frame): the recurrence then hides behind it instead of serialising with it.  0 resets. */
+void vog_lstm_set_max_ctas(int n);
+void vog_set_reserved_sms(int n);
+
 /* Multimodal-transformer input: row ((b*nfrm+f)*nsrl+s)*nppf2+p of out / out_lp =
  * [vis[b*nfrm*nppf2 + f*nppf2 + p, 0:dv] | lang[b*nsrl + s, 0:dl]] as fp32 and/or low precision.
  * replaces concate_vis_lang_feats + the per-frame regroup: code/mdl_vog.py:316-344,693-699. */

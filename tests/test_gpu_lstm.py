@@ -109,3 +109,27 @@ def test_resident_kernel_in_cuda_graph_replays():
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, eager)
+
+
+@pytest.mark.parametrize('max_ctas', [32, 16, 64])
+def test_recurrence_on_a_few_sms(max_ctas):
+    """vog_lstm_set_max_ctas: the weight-streaming kernel with 64 / 64 (clamped: at most 64 units per CTA) / 32 hidden
+    units per CTA (the SM-partitioned launch used next to a long visual branch) against the float64 host recurrence."""
+    from vognet_pytorch_b200 import ops, _lib
+    w, batch, mdl = _model('spat_gt5')
+    mdl.set_compute('tf32')
+    T, H = 20, 1024
+    lens_list = [6, 20, 1, 13, 9]
+    Bq = len(lens_list)
+    lens = torch.tensor(lens_list, device=DEV)
+    gx = (torch.rand(T * Bq, 8 * H, generator=torch.Generator().manual_seed(7)) - 0.5).to(DEV)
+    _, _, whh = mdl._lang_weights(ops.LP_TF32)[0][0]
+    L = _lib.lib()
+    L.vog_lstm_set_max_ctas(max_ctas)
+    try:
+        out = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32).view(T, Bq, 2 * H)
+        torch.cuda.synchronize()
+    finally:
+        L.vog_lstm_set_max_ctas(0)
+    ref = _ref_recurrence(gx, whh, lens, T, Bq, H)
+    assert (out.cpu().double() - ref).abs().max() < 1e-3

@@ -47,6 +47,8 @@ _SIGNATURES = {
     'vog_loss_workspace_bytes': [c_int, c_int, c_int],
     'vog_loss_fwd': [P, P, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                      c_float, P, P, P, P],
+    'vog_lstm_set_max_ctas': [c_int],
+    'vog_set_reserved_sms': [c_int],
     'vog_lstm_workspace_bytes': [c_int, c_int],
     'vog_debug_lstm_force_streaming': [c_int],
     'vog_debug_gemm_trace': [P],

@@ -62,6 +62,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
             int BN, const TcEpilogue& epi, void* workspace, long long workspace_bytes, cudaStream_t st);
 long long tc_gemm_workspace_bytes(int M, int N, int K, int tf32, int BN);
 int num_sms();
+void tc_gemm_set_reserved_sms(int n);    // persistent GEMM grids leave n SMs to a concurrent branch
 void tc_gemm_set_trace(long long* buf);  // debug: 8 clock64 stamps of CTA 0
 // ---- tc_attn.cu : fused relative-position-bias attention (tcgen05) ---------------------------
 int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
@@ -79,6 +80,7 @@ int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long
 long long lstm_workspace_bytes(int Bq, int H);
 void lstm_set_trace(long long* buf);     // debug: phase cycle counters of CTA 0
 void lstm_set_exchange(int mode);        // debug: 0 tagged 64-bit words, 1 per-CTA release flags
+void lstm_set_max_ctas(int n);           // > 0: run the recurrence on at most n SMs (weight-streaming kernel)
 void lstm_force_streaming(int on);       // debug: disable the weight-resident kernel
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
                    int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st);

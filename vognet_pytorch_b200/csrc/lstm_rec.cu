@@ -22,7 +22,7 @@ namespace vog {
 
 constexpr int LS_THREADS = 512;
 constexpr int LS_MAXB = 8;          // sequences per launch
-constexpr int LS_MAXU = 16;         // hidden units per CTA
+constexpr int LS_MAXU = 64;         // hidden units per CTA (streaming kernel; 64 = a 32-CTA launch at H = 1024)
 constexpr int LS_WS_HEADER = 1024;  // workspace header: barrier counters / per-CTA flags
 
 struct LstmParams {
@@ -512,6 +512,8 @@ static int launch_resident(const LstmResParams& p, int ctas, int threads, cudaSt
 }
 
 static int g_lstm_force_streaming = 0;
+static int g_lstm_max_ctas = 0;
+void lstm_set_max_ctas(int n) { g_lstm_max_ctas = n > 0 ? n : 0; }
 static int g_lstm_xmode = 0;
 void lstm_set_exchange(int mode) { g_lstm_xmode = mode ? 1 : 0; }
 static long long* g_lstm_trace = nullptr;
@@ -536,7 +538,12 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
                 "lstm_layer_fwd: whh and workspace must be 16-byte aligned");
     int sms = num_sms();
     if (sms < 2) sms = 2;
-    if (H == LR_H && cdiv(H, sms / 2) <= LR_MAXU && !g_lstm_force_streaming) {
+    // SM budget (vog_lstm_set_max_ctas): when the caller runs the recurrence NEXT TO a long independent branch it asks
+    // for a launch on a few SMs only - the weight-streaming kernel with many hidden units per CTA - so that the other
+    // branch keeps the rest of the GPU (the weight-resident kernel needs every SM's registers and shared memory)
+    const bool few = g_lstm_max_ctas > 0 && g_lstm_max_ctas < sms;
+    if (few) sms = g_lstm_max_ctas < 2 ? 2 : g_lstm_max_ctas;
+    if (!few && H == LR_H && cdiv(H, sms / 2) <= LR_MAXU && !g_lstm_force_streaming) {
         // weight-resident kernel: one warp per hidden unit, <= 16 units per CTA
         const int per_dir_r = sms / 2;
         const int U = cdiv(H, per_dir_r);
@@ -561,8 +568,9 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
     int U = cdiv(H, per_dir);
     if (U > LS_MAXU) { U = LS_MAXU; }
     per_dir = cdiv(H, U);
-    VOG_REQUIRE(2 * per_dir <= sms, "lstm_layer_fwd: H=%d needs %d co-resident CTAs but the device has %d SMs",
-                H, 2 * per_dir, sms);
+    VOG_REQUIRE(2 * per_dir <= num_sms(), "lstm_layer_fwd: H=%d needs %d co-resident CTAs but the device has %d SMs",
+                H, 2 * per_dir, num_sms());
+    VOG_REQUIRE(U * Bq <= LS_THREADS, "lstm_layer_fwd: %d units x %d sequences per CTA exceed the cell-update threads", U, Bq);
     LstmParams p;
     p.gx = gx; p.ldg = ldg; p.whh = whh; p.lens = lens;
     p.counters = reinterpret_cast<unsigned*>(workspace);

@@ -584,6 +584,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 static long long* g_gemm_trace = nullptr;
+static int g_reserved_sms = 0;
+void tc_gemm_set_reserved_sms(int n) { g_reserved_sms = n > 0 ? n : 0; }
 void tc_gemm_set_trace(long long* buf) { g_gemm_trace = buf; }
 
 // sum of split-K partials + epilogue, one float4 per thread
@@ -762,7 +764,11 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + GM_EPI_BYTES + p.lq_stage;
     const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
-    const int grid = nitems < num_sms() ? nitems : num_sms();
+    // vog_set_reserved_sms: SMs left to a concurrently running kernel of another branch (the persistent tile
+    // schedule is static, so CTAs that would have to wait for those SMs double the kernel's time)
+    int avail = num_sms() - g_reserved_sms;
+    if (avail < 1) avail = 1;
+    const int grid = nitems < avail ? nitems : avail;
     const int epi_kind = epi.mode == 1 ? EPI_QKV : epi.mode == 2 ? EPI_QKVF : epi.mode == 3 ? EPI_LIN2
                          : (p.fast ? EPI_FAST : EPI_GENERIC);
     VOG_REQUIRE(!epi.res_vis || epi_kind == EPI_FAST, "tc_gemm: gathered residual needs the aligned fast epilogue "

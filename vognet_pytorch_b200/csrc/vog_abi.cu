@@ -245,6 +245,12 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* v, int Bt, int N, 
 
 int64_t vog_lstm_workspace_bytes(int Bq, int H) { return lstm_workspace_bytes(Bq, H); }
 
+/* SM partitioning between concurrent branches of one forward (host-side state read at launch / graph-capture time):
+ * vog_lstm_set_max_ctas(n > 0) runs the following recurrence launches on at most n SMs (weight-streaming kernel with
+ * many hidden units per CTA); vog_set_reserved_sms(n) makes the persistent GEMMs size their grids to SMs - n.  0 resets. */
+void vog_lstm_set_max_ctas(int n) { vog::lstm_set_max_ctas(n); }
+void vog_set_reserved_sms(int n) { vog::tc_gemm_set_reserved_sms(n); }
+
 /* debug / A-B testing: 1 = always use the weight-streaming recurrence kernel */
 void vog_debug_lstm_force_streaming(int on) { vog::lstm_force_streaming(on); }
 /* A/B switch of the h_t exchange of the weight-resident kernel: 0 = tagged 64-bit words, 1 = per-CTA flags */

@@ -28,6 +28,11 @@ from . import ops
 from .transformer_code import COMPUTE_MODES, FactoredTokens, RelBias, RelTransformer, Transformer
 
 
+def P_of(batch):
+    """proposals per query of a batch dict"""
+    return int(batch['pad_region_feature'].shape[1])
+
+
 class _LangEncoder(nn.Module):
     """Parameter layout of the reference LSTMEncoder (utils/mdl_srl_utils.py:72-112)."""
 
@@ -358,13 +363,28 @@ class VOGNetB200(nn.Module):
         if g is None:
             st = {k: inp[k].clone() for k in self._GRAPH_KEYS}
 
+            # Optional SM partition between the concurrent branches (VOG_LANG_SMS=n, off by default): the language
+            # recurrence on n SMs (weight-streaming kernel) while the visual branch's persistent GEMMs leave those SMs
+            # alone.  Measured at spat/p100 (profiles/r1/lstm_trace.txt): 16 / 32 / 48 SMs -> 3.17 / 3.09 / 2.47 ms
+            # per step against 1.94 ms unpartitioned - the few-SM streaming recurrence is far too slow to hide.
+            from . import _lib
+            L = _lib.lib()
+            share = int(os.environ.get('VOG_LANG_SMS', 0)) if P_of(st) >= int(os.environ.get('VOG_LANG_SPLIT_MIN_P', 2000)) else 0
+
             def body(side):
                 cur = torch.cuda.current_stream()
                 side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    lang = self.language_encode_tc(st)
-                x, x_lp = self._visual_tc(st['pad_region_feature'], st['seg_feature_for_frms'],
-                                          st['pad_proposals'], ncmp)
+                try:
+                    L.vog_lstm_set_max_ctas(share)
+                    with torch.cuda.stream(side):
+                        lang = self.language_encode_tc(st)
+                    L.vog_lstm_set_max_ctas(0)
+                    L.vog_set_reserved_sms(share)
+                    x, x_lp = self._visual_tc(st['pad_region_feature'], st['seg_feature_for_frms'],
+                                              st['pad_proposals'], ncmp)
+                finally:
+                    L.vog_lstm_set_max_ctas(0)
+                    L.vog_set_reserved_sms(0)
                 cur.wait_stream(side)
                 return self._fusion_tc(x, x_lp, lang, st['pad_proposals'], st['srl_arg_inds_msk'],
                                        st['num_cmp_msk'], ncmp)
@@ -373,7 +393,6 @@ class VOGNetB200(nn.Module):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             cap = torch.cuda.Stream(device=feat.device)
-            from . import _lib
             n0 = _lib.lib().vog_launch_count()
             with torch.cuda.graph(graph, stream=cap):
                 out = body(side)
