@@ -429,12 +429,14 @@ def main():
         'metric': f'{METRIC} ({args.workload})', 'value': value, 'unit': 'queries/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_ms / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'tf32': 'tf32 GEMM + bf16 attention operands, fp32 accumulate/softmax/LayerNorm',
-                  'bf16': 'bf16 operands, fp32 accumulate/softmax/LayerNorm', 'fp32x': 'f32'}[compute],
+        'dtype': {'tf32': 'tf32', 'bf16': 'bf16', 'fp32x': 'f32'}[compute],
         'data': 'synthetic',
         'config': {'workload': args.workload, 'conc_type': w['conc_type'], 'per_gpu_batch': B,
                    'global_batch': B * world, 'ncmp': w['ncmp'], 'nfrm': 10, 'nppf': w['nppf'],
                    'obj_attn': list(shapes['obj']), 'mul_attn': list(shapes['mul']), 'compute': compute,
+                   'compute_detail': {'tf32': 'tf32 tcgen05 GEMMs, bf16 attention operands, fp32 accumulate / softmax / LayerNorm / residual stream',
+                                      'bf16': 'bf16 tcgen05 operands, fp32 accumulate / softmax / LayerNorm / residual stream',
+                                      'fp32x': 'exact fp32 CUDA-core path'}[compute],
                    'parallelism': f'dp{world} (queries sharded, no data-path collective)',
                    'l2': 'flushed (256 MB memset) between timed iterations',
                    'gflop_per_query_algorithmic': flops_query(w) / 1e9},

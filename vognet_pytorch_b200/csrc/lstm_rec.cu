@@ -37,6 +37,9 @@ struct LstmParams {
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// tanh(x) = 1 - 2 / (exp(2x) + 1): no cancellation for |x| >~ 0.1, absolute error ~1e-7 near 0
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 __device__ __forceinline__ void store_lp(void* base, long long idx, float v, int kind) {
     if (kind == 1) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
@@ -402,13 +405,15 @@ lstm_rec_resident_kernel(const LstmResParams p)
             const bool live = t < len_s[lane];
             float hval = 0.f;
             if (live) {
+                // the cell update sits on the per-step critical path of every CTA: sigmoid / tanh through the fast
+                // exp (ex2.approx + fast divide, ~2 ulp) instead of the ~40-instruction libm versions
                 const float* gs = gate_s + warp * V + lane * 4;
-                const float gi = sigmoidf_(gs[0]);
-                const float gf = sigmoidf_(gs[1]);
-                const float gg = tanhf(gs[2]);
-                const float go = sigmoidf_(gs[3]);
+                const float gi = fast_sigmoid(gs[0]);
+                const float gf = fast_sigmoid(gs[1]);
+                const float gg = fast_tanh(gs[2]);
+                const float go = fast_sigmoid(gs[3]);
                 c_reg = gf * c_reg + gi * gg;
-                hval = go * tanhf(c_reg);
+                hval = go * fast_tanh(c_reg);
                 h_reg = hval;
             }
             if (step + 1 < Tmax) {
