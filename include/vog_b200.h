@@ -82,6 +82,20 @@ int vog_select_fwd(const float* scores, const float* props, int pdim, float* box
                    float* out_scores, int64_t* indexs, int B, int nsrl, int ncmp, int nfrm,
                    int nppf, int spat, void* stream);
 
+/* SEP selection: scores [B,ncmp,nsrl,nfrm*nppf] (= mdl_outs_eval of the SEP forward), props [B,ncmp,nfrm*nppf,pdim],
+ * fin_scores [B,ncmp] -> boxes [B,nsrl,ncmp,nfrm,pdim], out_scores [B,nsrl,ncmp,nfrm], indexs [B,nsrl,nfrm] =
+ * argmax over videos of fin_scores (lowest index wins ties).
+ * replaces EvaluatorSEP.get_out_results_boxes: code/eval_vsrl_corr.py:162-220. */
+int vog_select_sep_fwd(const float* scores, const float* props, int pdim, const float* fin_scores, float* boxes,
+                       float* out_scores, int64_t* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, void* stream);
+
+/* SEP fused per-video score: logits [Bq,nsrl,P1] (Bq = B*ncmp), vidf [Bq] (video-level verb logit), srl_msk [Bq,nsrl],
+ * verb_ind [Bq], cmp_msk [Bq] (int64) -> fin_loss [Bq,nsrl] = max_p sigmoid(logits) with the verb slot replaced by
+ * sigmoid(vidf), times srl_msk and cmp_msk; fin_eval [Bq] = sum_s(.. * srl_msk) / sum_s srl_msk * cmp_msk.
+ * replaces ConcSEP.compute_fin_scores (use_vis_msk): code/mdl_conc_sep.py:62-117. */
+int vog_sep_fin_scores(const float* logits, const float* vidf, const int64_t* srl_msk, const int64_t* verb_ind,
+                       const int64_t* cmp_msk, float* fin_loss, float* fin_eval, int Bq, int nsrl, int P1, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * tensor-core path (tcgen05.mma + TMA + TMEM, sm_100a only; these refuse to run elsewhere)
  * ------------------------------------------------------------------------------------------- */

@@ -90,6 +90,24 @@ def model_case(name):
           f'obj {tuple(keep["obj_out"].shape)} mul {tuple(keep["mul_out"].shape)}  {sz:.2f} MB')
 
 
+def sep_case(name):
+    """VOG_SEP + EvaluatorSEP of the unmodified reference (code/mdl_conc_sep.py:131-217,
+    code/eval_vsrl_corr.py:162-220) -> tests/golden/{name}.npz."""
+    w, batch = synth.workload(name)
+    sd = synth.make_state_dict()
+    mdl = rh.build_reference_model('sep', w['nppf'], sd)
+    with torch.no_grad():
+        out = mdl(synth.clone_batch(batch))
+        ev = rh.build_reference_evaluator('sep', w['nppf'], w['ncmp'])
+        sel = ev.get_out_results_boxes(out, batch)
+    save = {k: out[k].contiguous().numpy() for k in ('mdl_outs', 'mdl_outs_eval', 'vidf_outs', 'fin_scores_loss', 'fin_scores')}
+    save.update(boxes=sel['boxes'].contiguous().numpy(), scores=sel['scores'].contiguous().numpy(),
+                indexs=sel['indexs'].contiguous().numpy().astype(np.int64))
+    np.savez(os.path.join(GOLD, f'{name}.npz'), **save)
+    print(f'{name}: logits {tuple(out["mdl_outs"].shape)} std {out["mdl_outs"].std():.3f} '
+          f'fin_scores {out["fin_scores"].numpy().round(4).tolist()}')
+
+
 def loss_case(name):
     """LossB_SPAT / LossB_TEMP of the unmodified reference on the golden logits of `name` and the synthetic
     loss inputs -> tests/golden/loss_{name}.npz (loss value, boolean targets packed as uint8)."""
@@ -127,3 +145,6 @@ if __name__ == '__main__':
     for nm in synth.WORKLOADS:
         if not want or ('loss_' + nm) in want:
             loss_case(nm)
+    for nm in synth.WORKLOADS_SEP:
+        if not want or nm in want:
+            sep_case(nm)

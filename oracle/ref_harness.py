@@ -99,7 +99,7 @@ def build_reference_model(conc_type, nppf, state_dict, vocab_size=1000, **cfg_kw
     cfg = reference_cfg(conc_type, **cfg_kw)
     comm = Munch(vocab_size=vocab_size, detect_size=10, itod={}, wtoi={'UNK': 0},
                  num_prop_per_frm=nppf)
-    cls = {'spat': mdl_vog.VOG_SPAT, 'temp': mdl_vog.VOG_TEMP}[conc_type]
+    cls = {'spat': mdl_vog.VOG_SPAT, 'temp': mdl_vog.VOG_TEMP, 'sep': mdl_vog.VOG_SEP}[conc_type]
     mdl = cls(cfg, comm)
     mdl.load_state_dict(state_dict, strict=True)
     return mdl.eval()
@@ -109,7 +109,8 @@ def build_reference_evaluator(conc_type, nppf, ncmp):
     """EvaluatorSPAT/TEMP without its dataset-reading ctor (code/eval_fn_corr.py:54-67)."""
     _install_stubs()
     import eval_vsrl_corr  # noqa
-    cls = {'spat': eval_vsrl_corr.EvaluatorSPAT, 'temp': eval_vsrl_corr.EvaluatorTEMP}[conc_type]
+    cls = {'spat': eval_vsrl_corr.EvaluatorSPAT, 'temp': eval_vsrl_corr.EvaluatorTEMP,
+           'sep': eval_vsrl_corr.EvaluatorSEP}[conc_type]
     ev = cls.__new__(cls)
     import torch
     torch.nn.Module.__init__(ev)

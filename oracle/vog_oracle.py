@@ -232,6 +232,95 @@ def vog_forward(sd, inp, conc_type, nppf, n_heads=3, vocab_size=1000, nfrm0=10,
 
 
 # ---------------------------------------------------------------------------------------------
+# SEP concatenation: code/mdl_conc_sep.py:13-217
+# ---------------------------------------------------------------------------------------------
+def _final_hidden(sd, inp, vocab_size):
+    """lang_encode's 'final_hidden' (code/mdl_vog.py:265-279): last layer's final forward|backward hidden state
+    (utils/mdl_srl_utils.py:147-162 combine_bidir) through lstm_out_feat_proj -> [B*nv, 256]."""
+    words = inp['srl_arg_words_ind']
+    B, nv, nsrl, L = words.shape
+    flat = words.reshape(B * nv, nsrl * L)
+    wm = inp['srl_arg_word_mask'].reshape(B * nv, -1).clone()
+    pad = wm == -1
+    wm[pad] = 0
+    toks = torch.gather(flat, 1, wm)
+    toks[pad] = vocab_size
+    lens = inp['srl_arg_word_mask_len'].reshape(B * nv)
+    toks = toks[:, :int(lens.max())].contiguous()
+    emb = F.embedding(toks, sd['lstm_encoder.embed_tokens.weight'])
+    packed = torch.nn.utils.rnn.pack_padded_sequence(emb.transpose(0, 1), lens.tolist(), enforce_sorted=False)
+    _, (hn, _) = _lstm_from_state_dict(sd)(packed)
+    last = torch.cat([hn[-2], hn[-1]], -1)                   # layer 1: forward | backward
+    return F.relu(last @ sd['lstm_out_feat_proj.0.weight'].t() + sd['lstm_out_feat_proj.0.bias'])
+
+
+def vog_forward_sep(sd, inp, nppf, n_heads=3, vocab_size=1000, nfrm0=10):
+    """Restated ConcSEP.forward for mdl.name='vog' (code/mdl_conc_sep.py:131-217).
+
+    Every (query b, video c) pair is an independent single-video problem: the object transformer runs over the
+    video's own nfrm*nppf proposals (simple_obj_interact with B*ncmp sequences, code/mdl_vog.py:505-516), the
+    multimodal transformer over [B*ncmp*nfrm, nsrl*nppf] (conc_encode_item -> conc_encode2, :681-744), i.e. the
+    TEMP forward with one video per query applied to the B*ncmp pairs.  On top of that: the video-level verb
+    score (:365-398) and the fused per-video score fin_scores (mdl_conc_sep.py:62-117)."""
+    B, nv, nsrl, L = inp['srl_arg_words_ind'].shape
+    ncmp = inp['new_srl_idxs'].shape[1]
+    assert nv == ncmp, 'append_everywhere batches carry the sentence for every video'
+    Bq = B * ncmp
+    flat = {
+        'srl_arg_words_ind': inp['srl_arg_words_ind'].reshape(Bq, 1, nsrl, L),
+        'srl_arg_word_mask': inp['srl_arg_word_mask'].reshape(Bq, 1, -1),
+        'srl_arg_word_mask_len': inp['srl_arg_word_mask_len'].reshape(Bq, 1),
+        'srl_arg_words_capture': inp['srl_arg_words_capture'].reshape(Bq, 1, nsrl, 2),
+        'srl_arg_inds_msk': inp['srl_arg_inds_msk'].reshape(Bq, 1, nsrl),
+        'pad_region_feature': inp['pad_region_feature'].reshape(Bq, *inp['pad_region_feature'].shape[2:]),
+        'seg_feature_for_frms': inp['seg_feature_for_frms'].reshape(Bq, *inp['seg_feature_for_frms'].shape[2:]),
+        'pad_proposals': inp['pad_proposals'].reshape(Bq, *inp['pad_proposals'].shape[2:]),
+        'new_srl_idxs': inp['new_srl_idxs'].reshape(Bq, 1),
+        'num_cmp_msk': inp['num_cmp_msk'].reshape(Bq, 1),
+    }
+    single = vog_forward(sd, flat, 'temp', nppf, n_heads=n_heads, vocab_size=vocab_size, nfrm0=nfrm0)
+    P1 = single['mdl_outs'].shape[-1]
+    logits = single['mdl_outs'].view(B, ncmp, nsrl, P1)
+    ev = single['mdl_outs_eval'].view(B, ncmp, nsrl, P1)                   # mdl_conc_sep.py:196-208
+
+    # ---- video-level verb score: mean segment feature | sentence encoding -> seg_verb_classf (:365-398)
+    seg = F.relu(inp['seg_feature_for_frms'] @ sd['seg_encoder.0.weight'].t() + sd['seg_encoder.0.bias'])
+    seg_for_verb = seg.mean(dim=-2)                                        # [B,ncmp,256]
+    verb = _final_hidden(sd, inp, vocab_size).view(B, nv, -1)
+    sv = torch.cat([verb, seg_for_verb], -1)
+    hv = F.relu(sv @ sd['seg_verb_classf.0.weight'].t() + sd['seg_verb_classf.0.bias'])
+    vidf = (hv @ sd['seg_verb_classf.2.weight'].t() + sd['seg_verb_classf.2.bias']).squeeze(-1)   # [B,ncmp]
+
+    # ---- fin_scores (mdl_conc_sep.py:62-117, use_vis_msk=True): best box per argument of the UNMASKED
+    # sigmoid scores, the verb slot replaced by the video-level score, averaged over the populated slots
+    best = torch.sigmoid(logits).max(dim=-1)[0]                            # [B,ncmp,nsrl]
+    smsk = inp['srl_arg_inds_msk'].float()
+    vm = inp['verb_ind_in_srl'].view(B, ncmp, 1)
+    best = best.scatter(2, vm, torch.sigmoid(vidf).unsqueeze(-1))
+    best = best * smsk
+    cm = inp['num_cmp_msk'].float()
+    fin_eval = best.sum(-1) / smsk.sum(-1) * cm
+    fin_loss = best * cm.unsqueeze(-1)
+    return {'mdl_outs': logits, 'mdl_outs_eval': ev, 'vidf_outs': vidf, 'fin_scores_loss': fin_loss,
+            'fin_scores': fin_eval}
+
+
+def select_boxes_sep(out, pad_proposals, nppf, nfrm0=10):
+    """EvaluatorSEP.get_out_results_boxes (code/eval_vsrl_corr.py:162-220): per (argument, video, frame) best
+    proposal and its 7-float row; the predicted video is argmax over fin_scores, broadcast over arguments and
+    frames.  -> boxes [B,nsrl,ncmp,nfrm,7], scores [B,nsrl,ncmp,nfrm], indexs [B,nsrl,nfrm] int64."""
+    ev = out['mdl_outs_eval']
+    B, ncmp, nsrl, P1 = ev.shape
+    pd = pad_proposals.shape[-1]
+    s = ev.transpose(1, 2).contiguous().view(B, nsrl, ncmp, nfrm0, nppf)
+    sc, ix = torch.max(s, dim=-1)
+    pr = pad_proposals.view(B, 1, ncmp, nfrm0, nppf, pd).expand(B, nsrl, ncmp, nfrm0, nppf, pd)
+    bx = torch.gather(pr, -2, ix[..., None, None].expand(B, nsrl, ncmp, nfrm0, 1, pd)).squeeze(-2)
+    vid = torch.argmax(out['fin_scores'], dim=-1)
+    return {'boxes': bx, 'scores': sc, 'indexs': vid.view(B, 1, 1).expand(B, nsrl, nfrm0).contiguous()}
+
+
+# ---------------------------------------------------------------------------------------------
 # selection: code/eval_vsrl_corr.py:289-345 (TEMP) / :357-424 (SPAT)
 # ---------------------------------------------------------------------------------------------
 def select_boxes(mdl_outs_eval, pad_proposals, conc_type, ncmp, nppf, nfrm0=10):

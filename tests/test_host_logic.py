@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert L.vog_last_error() is not None
 
 
-@pytest.mark.parametrize('conc', ['spat', 'temp'])
+@pytest.mark.parametrize('conc', ['spat', 'temp', 'sep'])
 def test_checkpoint_contract(conc):
     cfg, comm = synth.default_cfg(conc), synth.default_comm(5)
     sel = vb.get_mdl_loss_eval(cfg)
@@ -47,11 +47,13 @@ def test_selector_surface():
         out = vb.get_mdl_loss_eval(cfg)
         assert set(out) == {'mdl', 'loss', 'eval'}
         assert out['mdl'].__name__ == cls
+    for conc in ('sep', 'svsq'):                     # code/mdl_selector.py:29 - both select the SEP classes
+        cfg = synth.default_cfg(conc)
+        out = vb.get_mdl_loss_eval(cfg)
+        assert out['mdl'].__name__ == 'VOG_SEP' and out['eval'].__name__ == 'EvaluatorSEP'
+        with pytest.raises(NotImplementedError):    # LossB_SEP is not rebuilt: asking for it fails loudly
+            out['loss'](cfg, synth.default_comm(5))
     cfg = synth.default_cfg('spat')
-    cfg.ds.conc_type = 'sep'
-    with pytest.raises(NotImplementedError):
-        vb.get_mdl_loss_eval(cfg)
-    cfg.ds.conc_type = 'spat'
     cfg.mdl.name = 'nope'
     with pytest.raises(NotImplementedError):
         vb.get_mdl_loss_eval(cfg)
@@ -82,3 +84,18 @@ def test_synth_is_deterministic():
     _, b1 = synth.workload('spat_gt5')
     _, b2 = synth.workload('spat_gt5')
     assert all(torch.equal(b1[k], b2[k]) for k in b1)
+
+
+def test_sep_batch_layout():
+    """SEP batches carry an [ncmp] axis everywhere (code/mdl_conc_sep.py:131-160) and are the unfolded single-video
+    pairs: video c of query b is pseudo-query b*ncmp+c."""
+    w, batch = synth.workload('sep_gt5')
+    B, ncmp, nppf = w['B'], w['ncmp'], w['nppf']
+    assert tuple(batch['pad_region_feature'].shape) == (B, ncmp, 10 * nppf, 2048)
+    assert tuple(batch['seg_feature_for_frms'].shape) == (B, ncmp, 10, 3072)
+    assert tuple(batch['pad_proposals'].shape) == (B, ncmp, 10 * nppf, 7)
+    assert tuple(batch['srl_arg_words_ind'].shape) == (B, ncmp, 5, 20)
+    assert tuple(batch['verb_ind_in_srl'].shape) == (B, ncmp)
+    assert (batch['verb_ind_in_srl'] < batch['srl_arg_inds_msk'].sum(-1)).all()
+    assert batch['pad_proposals'][..., 4].max() == 9 and batch['pad_proposals'][..., 0].max() < 720
+    assert batch['num_cmp_msk'][1, -1] == 0 and batch['num_cmp_msk'].sum() == B * ncmp - B // 2

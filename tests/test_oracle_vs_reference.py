@@ -39,3 +39,18 @@ def test_oracle_matches_live_reference_3layer_6head():
         ref = mdl(synth.clone_batch(batch))
         got = vo.vog_forward(sd, batch, 'spat', 5, n_heads=6)
     assert (got['mdl_outs'] - ref['mdl_outs']).abs().max() < 1e-4
+
+
+def test_sep_oracle_matches_live_reference():
+    sd = synth.make_state_dict(seed=21)
+    batch = synth.make_batch_sep(B=2, ncmp=3, nppf=5, seed=21)
+    mdl = rh.build_reference_model('sep', 5, sd)
+    with torch.no_grad():
+        ref = mdl(synth.clone_batch(batch))
+        got = vo.vog_forward_sep(sd, synth.clone_batch(batch), 5)
+        sel_ref = rh.build_reference_evaluator('sep', 5, 3).get_out_results_boxes(ref, batch)
+        sel = vo.select_boxes_sep(ref, batch['pad_proposals'], 5)
+    for k in ('mdl_outs', 'mdl_outs_eval', 'vidf_outs', 'fin_scores_loss', 'fin_scores'):
+        assert (got[k] - ref[k]).abs().max() < 5e-5, k
+    for k in ('boxes', 'scores', 'indexs'):
+        assert torch.equal(sel[k], sel_ref[k].contiguous()), k

@@ -440,8 +440,10 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
 __global__ void __launch_bounds__(256)
 select_kernel(const float* __restrict__ scores, const float* __restrict__ props, int pdim,
               float* __restrict__ boxes, float* __restrict__ out_scores, long long* __restrict__ indexs,
-              int B, int nsrl, int ncmp, int nfrm, int nppf, int spat)
+              int B, int nsrl, int ncmp, int nfrm, int nppf, int spat, const float* __restrict__ fin)
 {
+    // fin != nullptr: SEP layout - scores [B,ncmp,nsrl,nfrm*nppf], one proposal block per video, and the predicted
+    // video is the argmax of the fused per-video score fin [B,ncmp] (code/eval_vsrl_corr.py:162-220)
     const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= B * nsrl * nfrm) return;
@@ -451,7 +453,8 @@ select_kernel(const float* __restrict__ scores, const float* __restrict__ props,
     float vbest = 0.f; int vidx = 0;
     for (int vid = 0; vid < ncmp; ++vid) {
         const int base = spat ? (frm * ncmp + vid) * nppf : (vid * nfrm + frm) * nppf;
-        const float* sc = scores + (size_t)bs * P + base;
+        const float* sc = fin ? scores + (((size_t)b * ncmp + vid) * nsrl + (bs - b * nsrl)) * (nfrm * nppf) + frm * nppf
+                              : scores + (size_t)bs * P + base;
         float bv = 0.f; int bi = 0x7fffffff;
         bool have = false;
         for (int i = lane; i < nppf; i += 32) {
@@ -471,18 +474,73 @@ select_kernel(const float* __restrict__ scores, const float* __restrict__ props,
         for (int c = lane; c < pdim; c += 32) boxes[g * pdim + c] = pr[c];
         if (vid == 0 || better(bv, vid, vbest, vidx)) { vbest = bv; vidx = vid; }
     }
-    if (lane == 0) indexs[w] = spat ? vidx : 0;
+    if (fin) {
+        vbest = fin[(size_t)b * ncmp]; vidx = 0;
+        for (int vid = 1; vid < ncmp; ++vid) {
+            const float v = fin[(size_t)b * ncmp + vid];
+            if (better(v, vid, vbest, vidx)) { vbest = v; vidx = vid; }
+        }
+    }
+    if (lane == 0) indexs[w] = (spat || fin) ? vidx : 0;
 }
 
 int select_fwd(const float* scores, const float* props, int pdim, float* boxes, float* out_scores,
                long long* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, int spat,
-               cudaStream_t st)
+               cudaStream_t st, const float* fin)
 {
     const int nwarps = B * nsrl * nfrm;
     if (nwarps == 0) return 0;
     select_kernel<<<cdiv(nwarps, 8), 256, 0, st>>>(scores, props, pdim, boxes, out_scores, indexs, B, nsrl,
-                                                   ncmp, nfrm, nppf, spat);
+                                                   ncmp, nfrm, nppf, spat, fin);
     return check_launch("select");
+}
+
+// =============================================================================================
+// SEP: fused per-video score (code/mdl_conc_sep.py:62-117, use_vis_msk).  One block per (query, video): one warp per
+// SRL argument takes the max proposal logit (sigmoid is monotone: max of sigmoids = sigmoid of the max), the verb
+// slot is replaced by the video-level verb score, then masked mean over the populated slots.
+// =============================================================================================
+__global__ void sep_fin_kernel(const float* __restrict__ logits, const float* __restrict__ vidf,
+                               const long long* __restrict__ srl_msk, const long long* __restrict__ verb_ind,
+                               const long long* __restrict__ cmp_msk, float* __restrict__ fin_loss,
+                               float* __restrict__ fin_eval, int nsrl, int P1)
+{
+    __shared__ float best[32];
+    const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nsrl) {
+        const float* lg = logits + ((size_t)q * nsrl + warp) * P1;
+        float m = -INFINITY; bool nan = false;
+        for (int i = lane; i < P1; i += 32) { const float v = lg[i]; nan |= (v != v); m = fmaxf(m, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            nan |= (bool)__shfl_xor_sync(0xffffffffu, (int)nan, o);
+        }
+        if (lane == 0) best[warp] = nan ? NAN : 1.f / (1.f + expf(-m));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long vi = verb_ind[q];
+        if (vi >= 0 && vi < nsrl) best[vi] = 1.f / (1.f + expf(-vidf[q]));
+        const float cm = (float)cmp_msk[q];
+        float sum = 0.f, cnt = 0.f;
+        for (int s = 0; s < nsrl; ++s) {
+            const float mk = (float)srl_msk[(size_t)q * nsrl + s];
+            const float v = best[s] * mk;
+            sum += v; cnt += mk;
+            fin_loss[(size_t)q * nsrl + s] = v * cm;
+        }
+        fin_eval[q] = sum / cnt * cm;
+    }
+}
+
+int sep_fin_scores(const float* logits, const float* vidf, const long long* srl_msk, const long long* verb_ind,
+                   const long long* cmp_msk, float* fin_loss, float* fin_eval, int Bq, int nsrl, int P1, cudaStream_t st)
+{
+    if (Bq == 0) return 0;
+    VOG_REQUIRE(nsrl >= 1 && nsrl <= 32 && P1 >= 1, "sep_fin_scores: nsrl=%d must be 1..32", nsrl);
+    sep_fin_kernel<<<Bq, 32 * nsrl, 0, st>>>(logits, vidf, srl_msk, verb_ind, cmp_msk, fin_loss, fin_eval, nsrl, P1);
+    return check_launch("sep_fin_scores");
 }
 
 // =============================================================================================

@@ -23,7 +23,9 @@ int pe_project(const float* props, int ldp, const float* W, float* a, int rows, 
                float vh, float fdiv, float scale, cudaStream_t st);
 int select_fwd(const float* scores, const float* props, int pdim, float* boxes, float* out_scores,
                long long* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, int spat,
-               cudaStream_t st);
+               cudaStream_t st, const float* fin = nullptr);
+int sep_fin_scores(const float* logits, const float* vidf, const long long* srl_msk, const long long* verb_ind,
+                   const long long* cmp_msk, float* fin_loss, float* fin_eval, int Bq, int nsrl, int P1, cudaStream_t st);
 
 // ---- tc_gemm.cu : tcgen05 / TMA / TMEM GEMM ---------------------------------------------------
 struct TcEpilogue {

@@ -102,6 +102,23 @@ int vog_select_fwd(const float* scores, const float* props, int pdim, float* box
                       nfrm, nppf, spat, (cudaStream_t)stream);
 }
 
+int vog_select_sep_fwd(const float* scores, const float* props, int pdim, const float* fin_scores, float* boxes,
+                       float* out_scores, int64_t* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, void* stream)
+{
+    VOG_REQUIRE(scores && props && fin_scores && boxes && out_scores && indexs, "vog_select_sep_fwd: null operand");
+    VOG_REQUIRE(nppf > 0 && ncmp > 0 && nfrm > 0, "vog_select_sep_fwd: empty proposal group");
+    return select_fwd(scores, props, pdim, boxes, out_scores, (long long*)indexs, B, nsrl, ncmp,
+                      nfrm, nppf, 0, (cudaStream_t)stream, fin_scores);
+}
+
+int vog_sep_fin_scores(const float* logits, const float* vidf, const int64_t* srl_msk, const int64_t* verb_ind,
+                       const int64_t* cmp_msk, float* fin_loss, float* fin_eval, int Bq, int nsrl, int P1, void* stream)
+{
+    VOG_REQUIRE(logits && vidf && srl_msk && verb_ind && cmp_msk && fin_loss && fin_eval, "vog_sep_fin_scores: null operand");
+    return sep_fin_scores(logits, vidf, (const long long*)srl_msk, (const long long*)verb_ind, (const long long*)cmp_msk,
+                          fin_loss, fin_eval, Bq, nsrl, P1, (cudaStream_t)stream);
+}
+
 static int require_sm100(const char* who)
 {
     VOG_REQUIRE(vog_device_is_sm100(), "%s: needs an sm_100 (B200) device - tcgen05/TMEM kernels have no other path", who);

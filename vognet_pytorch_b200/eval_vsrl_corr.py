@@ -47,3 +47,15 @@ class EvaluatorSPAT(_EvaluatorBase):
 
 class EvaluatorTEMP(_EvaluatorBase):
     SPAT = False
+
+
+class EvaluatorSEP(_EvaluatorBase):
+    """code/eval_vsrl_corr.py:153-220: SEP outputs keep the [ncmp] axis; the predicted video is the argmax of the
+    fused per-video score ``fin_scores``."""
+
+    def get_out_results_boxes(self, out_result_dict, inp):
+        assert isinstance(out_result_dict, dict)
+        scores, fin = out_result_dict['mdl_outs_eval'], out_result_dict['fin_scores']
+        boxes, sc, ix = ops.select_sep_fwd(scores, inp['pad_proposals'], fin, self.num_sampled_frm,
+                                           self.num_prop_per_frm)
+        return {'boxes': boxes, 'scores': sc, 'indexs': ix}

@@ -2,7 +2,7 @@
 (classes, instantiated by the caller as ``mdl(cfg, comm)``, ``loss(cfg, comm)``,
 ``eval(cfg, comm, device)``: code/main_dist.py:33-53)."""
 from . import mdl_vog
-from .eval_vsrl_corr import EvaluatorSPAT, EvaluatorTEMP
+from .eval_vsrl_corr import EvaluatorSEP, EvaluatorSPAT, EvaluatorTEMP
 from .mdl_conc_single import LossB_SPAT, LossB_TEMP
 
 _MODELS = {
@@ -10,18 +10,29 @@ _MODELS = {
     ('temp', 'vog'): mdl_vog.VOG_TEMP,
     ('spat', 'igrnd'): mdl_vog.ImgGrnd_SPAT, ('spat', 'vgrnd'): mdl_vog.VidGrnd_SPAT,
     ('spat', 'vog'): mdl_vog.VOG_SPAT,
+    ('sep', 'igrnd'): mdl_vog.ImgGrnd_SEP, ('sep', 'vgrnd'): mdl_vog.VidGrnd_SEP,
+    ('sep', 'vog'): mdl_vog.VOG_SEP,
 }
-_EVALS = {'temp': EvaluatorTEMP, 'spat': EvaluatorSPAT}
+_EVALS = {'temp': EvaluatorTEMP, 'spat': EvaluatorSPAT, 'sep': EvaluatorSEP}
 
 
 _LOSSES = {'temp': LossB_TEMP, 'spat': LossB_SPAT}
 
 
+class _LossSEPUnavailable:
+    """LossB_SEP (code/mdl_conc_sep.py:219-447) is a training-side component that has not been rebuilt: the SEP
+    forward and evaluator are available, asking for the loss fails loudly instead of silently returning another."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError('LossB_SEP (code/mdl_conc_sep.py:219-447) is not part of this build; '
+                                  "conc_type 'sep'/'svsq' supports the forward and the evaluator")
+
+
 def get_mdl_loss_eval(cfg):
     conc_type, mdl_type = cfg.ds.conc_type, cfg.mdl.name
-    if conc_type in ('sep', 'svsq'):
-        raise NotImplementedError("conc_type 'sep'/'svsq' (code/mdl_conc_sep.py) is outside the "
-                                  'hot-path scope of this build (SURVEY.md section 2 row 7)')
+    if conc_type == 'svsq':          # same classes, one video per query (code/mdl_selector.py:29)
+        conc_type = 'sep'
     if (conc_type, mdl_type) not in _MODELS:
         raise NotImplementedError((conc_type, mdl_type))
-    return {'mdl': _MODELS[(conc_type, mdl_type)], 'loss': _LOSSES[conc_type], 'eval': _EVALS[conc_type]}
+    return {'mdl': _MODELS[(conc_type, mdl_type)], 'loss': _LOSSES.get(conc_type, _LossSEPUnavailable),
+            'eval': _EVALS[conc_type]}

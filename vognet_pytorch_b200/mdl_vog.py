@@ -53,7 +53,7 @@ def _scorer(i):
 
 
 class VOGNetB200(nn.Module):
-    CONC_TYPE = None       # 'spat' | 'temp'
+    CONC_TYPE = None       # 'spat' | 'temp' | 'sep'
     USE_OBJ_TX = True      # VidGrnd / VOGNet
     USE_MUL_TX = True      # VOGNet
 
@@ -136,8 +136,10 @@ class VOGNetB200(nn.Module):
         toks = toks[:, :max(lens_cpu)]
         emb = self.lstm_encoder.embed_tokens(toks).transpose(0, 1)
         packed = nn.utils.rnn.pack_padded_sequence(emb, lens_cpu, enforce_sorted=False)
-        out, _ = self.lstm_encoder.lstm(packed)
+        out, (hn, _) = self.lstm_encoder.lstm(packed)
         out, _ = nn.utils.rnn.pad_packed_sequence(out, padding_value=0.)
+        if self.CONC_TYPE == 'sep':          # 'final_hidden' of lang_encode (code/mdl_vog.py:265-279)
+            self._sep_verb = self.lstm_out_feat_proj(torch.cat([hn[-2], hn[-1]], -1))
         full = self.lstm_out_feat_proj(out.transpose(0, 1))          # [B*nv, T, le]
         cap = inp['srl_arg_words_capture'].reshape(B * nv, nsrl, 2)
         D = full.shape[-1]
@@ -196,6 +198,15 @@ class VOGNetB200(nn.Module):
             if l > 0:
                 gx, _ = ops.tc_gemm(x_lp, wih_lp, bias=bias)
             x_lp = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, kind)
+        if self.CONC_TYPE == 'sep':
+            # 'final_hidden' (code/mdl_vog.py:265-279): last layer's forward state at the last word | backward state
+            # at the first word (rows are time-major), through lstm_out_feat_proj
+            xl = x_lp.view(T, Bq, -1)
+            Hh = xl.shape[-1] // 2
+            ar = torch.arange(Bq, device=xl.device)
+            last = torch.cat([xl[(lens - 1).clamp(min=0), ar, :Hh], xl[0, :, Hh:]], -1).float()
+            self._sep_verb = ops.sgemm_nt(last, self.lstm_out_feat_proj[0].weight, self.lstm_out_feat_proj[0].bias,
+                                          relu=True)
         full, _ = ops.tc_gemm(x_lp, self._lp_weight('lstm_proj', self.lstm_out_feat_proj[0].weight, kind),
                               bias=self.lstm_out_feat_proj[0].bias, relu=True)               # [T*Bq, le]
         D = full.shape[-1]
@@ -213,7 +224,7 @@ class VOGNetB200(nn.Module):
         """(nfrm, nppf') of the per-frame multimodal sequences (code/mdl_conc_single.py:24-28,131-135)."""
         if self.CONC_TYPE == 'spat':
             return self.num_sampled_frm, ncmp * self.num_prop_per_frm
-        return ncmp * self.num_sampled_frm, self.num_prop_per_frm
+        return ncmp * self.num_sampled_frm, self.num_prop_per_frm      # 'sep' arrives here with ncmp = 1
 
     def forward(self, inp):
         if self.training:
@@ -222,13 +233,76 @@ class VOGNetB200(nn.Module):
         if not feat.is_cuda:
             raise RuntimeError('vognet_pytorch_b200 runs on CUDA only (no CPU path); move the batch '
                                'and the module to a B200 device')
+        sep = self.CONC_TYPE == 'sep'
         if feat.shape[0] == 0:                       # empty batch: nothing to launch
-            z = feat.new_zeros(0, 1, inp['srl_arg_words_ind'].shape[2], feat.shape[1])
+            nsrl = inp['srl_arg_words_ind'].shape[2]
+            if sep:
+                ncmp = feat.shape[1]
+                z = feat.new_zeros(0, ncmp, nsrl, feat.shape[2])
+                return {'mdl_outs': z, 'mdl_outs_eval': z.clone(), 'vidf_outs': feat.new_zeros(0, ncmp),
+                        'fin_scores_loss': feat.new_zeros(0, ncmp, nsrl), 'fin_scores': feat.new_zeros(0, ncmp)}
+            z = feat.new_zeros(0, 1, nsrl, feat.shape[1])
             return {'mdl_outs': z, 'mdl_outs_eval': z.clone()}
         with torch.no_grad():
-            if self.compute == 'fp32x':
-                return self._forward_fp32x(inp)
-            return self._forward_tc(inp)
+            if sep:
+                inp, (B, ncmp) = self._sep_flatten(inp)
+            out = self._forward_fp32x(inp) if self.compute == 'fp32x' else self._forward_tc(inp)
+            if sep:
+                nsrl, P1 = out['mdl_outs'].shape[2:]
+                out = {'mdl_outs': out['mdl_outs'].view(B, ncmp, nsrl, P1),
+                       'mdl_outs_eval': out['mdl_outs_eval'].view(B, ncmp, nsrl, P1),
+                       'vidf_outs': out['vidf_outs'].view(B, ncmp),
+                       'fin_scores_loss': out['fin_scores_loss'].view(B, ncmp, nsrl),
+                       'fin_scores': out['fin_scores'].view(B, ncmp)}
+            return out
+
+    # -----------------------------------------------------------------------------------------
+    # SEP concatenation (code/mdl_conc_sep.py:13-217)
+    # -----------------------------------------------------------------------------------------
+    _SEP_LANG_KEYS = ('srl_arg_words_ind', 'srl_arg_word_mask', 'srl_arg_word_mask_len', 'srl_arg_words_capture',
+                      'srl_arg_inds_msk', 'verb_ind_in_srl')
+
+    def _sep_flatten(self, inp):
+        """ConcSEP scores every (query, video) pair on its own: the object transformer sees the video's nfrm*nppf
+        proposals (code/mdl_vog.py:505-516 with B*ncmp sequences), the multimodal transformer [B*ncmp*nfrm,
+        nsrl*nppf] (:681-744), the language encoding of slot c goes with video c (mdl_conc_sep.py:165-173).  That is
+        the single-video TEMP forward over B*ncmp pseudo-queries, so the batch is re-viewed as such (no copies
+        for append_everywhere batches)."""
+        feat = inp['pad_region_feature']
+        if feat.dim() != 4:
+            raise ValueError("conc_type 'sep' expects pad_region_feature [B,ncmp,nfrm*nppf,D] "
+                             f'(code/mdl_conc_sep.py:131-160), got {tuple(feat.shape)}')
+        B, ncmp = feat.shape[:2]
+        if inp['new_srl_idxs'].shape[1] != ncmp:
+            raise AssertionError('new_srl_idxs and pad_region_feature disagree on ncmp')
+        Bq = B * ncmp
+        nv = inp['srl_arg_words_ind'].shape[1]
+        if nv not in (1, ncmp):
+            raise AssertionError(f'{nv} sentence slots for {ncmp} videos (code/mdl_conc_sep.py:165-173 expands 1 -> ncmp)')
+        flat = {}
+        for k in self._SEP_LANG_KEYS:
+            v = inp[k]
+            if v.shape[1] == 1 and ncmp > 1:
+                v = v.expand(B, ncmp, *v.shape[2:])
+            flat[k] = v.reshape(Bq, 1, *v.shape[2:]) if k != 'verb_ind_in_srl' else v.reshape(Bq).contiguous()
+        for k in ('pad_region_feature', 'seg_feature_for_frms', 'pad_proposals'):
+            flat[k] = inp[k].reshape(Bq, *inp[k].shape[2:])
+        flat['new_srl_idxs'] = inp['new_srl_idxs'].reshape(Bq, 1)
+        flat['num_cmp_msk'] = inp['num_cmp_msk'].reshape(Bq, 1)
+        return flat, (B, ncmp)
+
+    def _sep_heads(self, out, seg_mean, verb, srl_msk, verb_ind, cmp_msk):
+        """Video-level verb score (code/mdl_vog.py:365-398) and the fused per-video score (mdl_conc_sep.py:62-117)."""
+        logits = out['mdl_outs']
+        Bq, _, nsrl, P1 = logits.shape
+        sv = torch.cat([verb, seg_mean], -1).contiguous()
+        hv = ops.sgemm_nt(sv, self.seg_verb_classf[0].weight, self.seg_verb_classf[0].bias, relu=True)
+        vidf = ops.sgemm_nt(hv, self.seg_verb_classf[2].weight, self.seg_verb_classf[2].bias).view(Bq)
+        fin_loss, fin_eval = ops.sep_fin_scores(logits.view(Bq, nsrl, P1), vidf, srl_msk.reshape(Bq, nsrl),
+                                                verb_ind.reshape(Bq), cmp_msk.reshape(Bq))
+        out = dict(out)
+        out.update(vidf_outs=vidf, fin_scores_loss=fin_loss, fin_scores=fin_eval)
+        return out
 
     # -----------------------------------------------------------------------------------------
     # tensor-core path ('tf32' / 'bf16')
@@ -250,7 +324,11 @@ class VOGNetB200(nn.Module):
             return self._forward_tc_graph(inp, ncmp)
         lang = self.language_encode_tc(inp)                           # [B, nsrl, 256] fp32
         x, x_lp = self._visual_tc(feat, seg, props, ncmp)
-        return self._fusion_tc(x, x_lp, lang, props, inp['srl_arg_inds_msk'], inp['num_cmp_msk'], ncmp)
+        out = self._fusion_tc(x, x_lp, lang, props, inp['srl_arg_inds_msk'], inp['num_cmp_msk'], ncmp)
+        if self.CONC_TYPE == 'sep':
+            out = self._sep_heads(out, self.__dict__.pop('_sep_seg_mean'), self.__dict__.pop('_sep_verb'),
+                                  inp['srl_arg_inds_msk'], inp['verb_ind_in_srl'], inp['num_cmp_msk'])
+        return out
 
     def _visual_tc(self, feat, seg, props, ncmp):
         """prop/seg encoders -> prop|seg rows -> object transformer.  Independent of the language
@@ -281,6 +359,8 @@ class VOGNetB200(nn.Module):
                     self._lp_weight('seg', self.seg_encoder[0].weight, kind),
                     bias=self.seg_encoder[0].bias, relu=True, out_f32=x[:, pe_:], out_lp=x_lp[:, pe_:],
                     rep=nppf)
+        if self.CONC_TYPE == 'sep':      # seg_feats.mean(dim=-2) of get_seg_verb_feats_to_process (code/mdl_vog.py:374)
+            self._sep_seg_mean = x.view(B, nvf, nppf, self.ps_dim)[:, :, 0, pe_:].mean(1)
         if self.USE_OBJ_TX and self.cfg.mdl.obj_tx.to_use:
             otx = self.cfg.mdl.obj_tx
             if otx.one_frm:
@@ -357,11 +437,12 @@ class VOGNetB200(nn.Module):
     def _graph_for(self, inp, ncmp):
         """The captured forward for this (compute mode, shapes) signature; captured on first use."""
         feat = inp['pad_region_feature']
-        key = (self.compute, ncmp, feat.device.index) + tuple(tuple(inp[k].shape) for k in self._GRAPH_KEYS)
+        keys = self._GRAPH_KEYS + (('verb_ind_in_srl',) if self.CONC_TYPE == 'sep' else ())
+        key = (self.compute, ncmp, feat.device.index) + tuple(tuple(inp[k].shape) for k in keys)
         graphs = self.__dict__.setdefault('_graphs', {})
         g = graphs.get(key)
         if g is None:
-            st = {k: inp[k].clone() for k in self._GRAPH_KEYS}
+            st = {k: inp[k].clone() for k in keys}
 
             # Optional SM partition between the concurrent branches (VOG_LANG_SMS=n, off by default): the language
             # recurrence on n SMs (weight-streaming kernel) while the visual branch's persistent GEMMs leave those SMs
@@ -386,8 +467,12 @@ class VOGNetB200(nn.Module):
                     L.vog_lstm_set_max_ctas(0)
                     L.vog_set_reserved_sms(0)
                 cur.wait_stream(side)
-                return self._fusion_tc(x, x_lp, lang, st['pad_proposals'], st['srl_arg_inds_msk'],
-                                       st['num_cmp_msk'], ncmp)
+                out = self._fusion_tc(x, x_lp, lang, st['pad_proposals'], st['srl_arg_inds_msk'],
+                                      st['num_cmp_msk'], ncmp)
+                if self.CONC_TYPE == 'sep':
+                    out = self._sep_heads(out, self.__dict__.pop('_sep_seg_mean'), self.__dict__.pop('_sep_verb'),
+                                          st['srl_arg_inds_msk'], st['verb_ind_in_srl'], st['num_cmp_msk'])
+                return out
             side = torch.cuda.Stream(device=feat.device)
             body(side)                              # eager warm-up: packs weights, sets kernel attributes
             torch.cuda.synchronize()
@@ -495,7 +580,11 @@ class VOGNetB200(nn.Module):
             cmsk = cm.view(B, 1, 1, ncmp, 1).expand(B, 1, nsrl, ncmp, self.num_sampled_frm * nppf)
         smsk = inp['srl_arg_inds_msk'].float().view(B, 1, nsrl, 1)
         ev = torch.sigmoid(logits) * smsk * cmsk.reshape(B, 1, nsrl, P)
-        return {'mdl_outs': logits, 'mdl_outs_eval': ev}
+        out = {'mdl_outs': logits, 'mdl_outs_eval': ev}
+        if self.CONC_TYPE == 'sep':
+            out = self._sep_heads(out, segf.view(B, nvf, -1).mean(1), self.__dict__.pop('_sep_verb'),
+                                  inp['srl_arg_inds_msk'], inp['verb_ind_in_srl'], inp['num_cmp_msk'])
+        return out
 
 
 def _variant(name, conc, obj, mul):
@@ -509,3 +598,6 @@ VidGrnd_TEMP = _variant('VidGrnd_TEMP', 'temp', True, False)
 VidGrnd_SPAT = _variant('VidGrnd_SPAT', 'spat', True, False)
 VOG_TEMP = _variant('VOG_TEMP', 'temp', True, True)
 VOG_SPAT = _variant('VOG_SPAT', 'spat', True, True)
+ImgGrnd_SEP = _variant('ImgGrnd_SEP', 'sep', False, False)
+VidGrnd_SEP = _variant('VidGrnd_SEP', 'sep', True, False)
+VOG_SEP = _variant('VOG_SEP', 'sep', True, True)

@@ -150,6 +150,44 @@ def select_fwd(scores, props, ncmp, nfrm, nppf, spat):
     return boxes, sc, ix
 
 
+def select_sep_fwd(scores, props, fin_scores, nfrm, nppf):
+    """scores [B,ncmp,nsrl,nfrm*nppf], props [B,ncmp,nfrm*nppf,pdim], fin_scores [B,ncmp] -> boxes, scores, indexs
+    (see vog_select_sep_fwd)."""
+    _req(scores, torch.float32, 'scores', 4), _req(props, torch.float32, 'props', 4)
+    _req(fin_scores, torch.float32, 'fin_scores', 2)
+    B, ncmp, nsrl, P1 = scores.shape
+    pdim = props.shape[-1]
+    if P1 != nfrm * nppf or tuple(props.shape[:3]) != (B, ncmp, P1) or tuple(fin_scores.shape) != (B, ncmp):
+        raise ValueError(f'select_sep_fwd: scores {tuple(scores.shape)} / props {tuple(props.shape)} / fin_scores '
+                         f'{tuple(fin_scores.shape)} do not describe [B,ncmp,nsrl,{nfrm}*{nppf}]')
+    scores, props, fin_scores = scores.contiguous(), props.contiguous(), fin_scores.contiguous()
+    boxes = torch.empty(B, nsrl, ncmp, nfrm, pdim, device=scores.device, dtype=torch.float32)
+    sc = torch.empty(B, nsrl, ncmp, nfrm, device=scores.device, dtype=torch.float32)
+    ix = torch.empty(B, nsrl, nfrm, device=scores.device, dtype=torch.int64)
+    L = _lib.lib()
+    _lib.check(L.vog_select_sep_fwd(_ptr(scores), _ptr(props), pdim, _ptr(fin_scores), _ptr(boxes), _ptr(sc), _ptr(ix),
+                                    B, nsrl, ncmp, nfrm, nppf, _stream()), 'vog_select_sep_fwd')
+    return boxes, sc, ix
+
+
+def sep_fin_scores(logits, vidf, srl_msk, verb_ind, cmp_msk):
+    """logits [Bq,nsrl,P1], vidf [Bq], srl_msk [Bq,nsrl] / verb_ind [Bq] / cmp_msk [Bq] int64 -> fin_loss [Bq,nsrl],
+    fin_eval [Bq] (see vog_sep_fin_scores)."""
+    _req(logits, torch.float32, 'logits', 3), _req(vidf, torch.float32, 'vidf', 1)
+    Bq, nsrl, P1 = logits.shape
+    for t, nm, shp in ((srl_msk, 'srl_msk', (Bq, nsrl)), (verb_ind, 'verb_ind', (Bq,)), (cmp_msk, 'cmp_msk', (Bq,))):
+        if t.dtype != torch.int64 or tuple(t.shape) != shp or not t.is_cuda:
+            raise ValueError(f'sep_fin_scores: {nm} must be a CUDA int64 tensor of shape {shp}')
+    logits, vidf = logits.contiguous(), vidf.contiguous()
+    srl_msk, verb_ind, cmp_msk = srl_msk.contiguous(), verb_ind.contiguous(), cmp_msk.contiguous()
+    fin_loss = torch.empty(Bq, nsrl, device=logits.device, dtype=torch.float32)
+    fin_eval = torch.empty(Bq, device=logits.device, dtype=torch.float32)
+    L = _lib.lib()
+    _lib.check(L.vog_sep_fin_scores(_ptr(logits), _ptr(vidf), _ptr(srl_msk), _ptr(verb_ind), _ptr(cmp_msk),
+                                    _ptr(fin_loss), _ptr(fin_eval), Bq, nsrl, P1, _stream()), 'vog_sep_fin_scores')
+    return fin_loss, fin_eval
+
+
 def inv_sqrt(d_model):
     return 1.0 / math.sqrt(d_model)
 

@@ -88,6 +88,14 @@ WORKLOADS = OrderedDict([
     ('temp_p100', dict(conc_type='temp', B=4, ncmp=4, nppf=100, nvalid=None, compute='bf16')),
 ])
 
+# conc_type 'sep' (code/mdl_conc_sep.py): every contrastive video is scored on its own,
+# batch tensors carry an extra [ncmp] axis and every video has the sentence appended (append_everywhere,
+# code/dat_loader_simple.py:942-945).  Not BASELINE configs: parity cases for the widened path.
+WORKLOADS_SEP = OrderedDict([
+    ('sep_gt5',  dict(conc_type='sep', B=2, ncmp=4, nppf=5,   nvalid=None, compute='fp32')),
+    ('sep_p100', dict(conc_type='sep', B=1, ncmp=2, nppf=100, nvalid=None, compute='bf16')),
+])
+
 NFRM0 = 10     # ds.num_sampled_frm
 NSRL = 5       # misc.srl_arg_length
 SEQ_L = 20     # ds.max_seq_length
@@ -315,12 +323,48 @@ def make_loss_inputs(batch, conc_type='spat', ncmp=4, nppf=5, seed=1, num_box=12
             'target_cmp': t(target_cmp)}
 
 
+def make_batch_sep(B=2, ncmp=4, nppf=5, nvalid=None, seed=1, vocab_size=1000, **_unused):
+    """SEP batch (code/mdl_conc_sep.py:131-217 reads these shapes): the B*ncmp (query, video) pairs of a
+    single-video batch with the [ncmp] axis unfolded -
+
+      srl_arg_words_ind [B,ncmp,nsrl,L]   srl_arg_word_mask [B,ncmp,L]   srl_arg_word_mask_len [B,ncmp]
+      srl_arg_words_capture [B,ncmp,nsrl,2]   srl_arg_inds_msk [B,ncmp,nsrl]   verb_ind_in_srl [B,ncmp]
+      pad_region_feature [B,ncmp,nfrm*nppf,2048]   seg_feature_for_frms [B,ncmp,nfrm,3072]
+      pad_proposals [B,ncmp,nfrm*nppf,7]   new_srl_idxs / num_cmp_msk [B,ncmp]
+
+    Every video keeps its own frame ids 0..nfrm-1 and un-shifted boxes.  The last video of odd queries is masked
+    out (num_cmp_msk = 0) to exercise the mask path."""
+    one = make_batch(conc_type='temp', B=B * ncmp, ncmp=1, nppf=nppf, nvalid=nvalid, seed=seed,
+                     vocab_size=vocab_size)
+    out = {}
+    for k, v in one.items():
+        if k in ('new_srl_idxs', 'num_cmp_msk'):
+            continue
+        if k in ('pad_region_feature', 'seg_feature_for_frms', 'pad_proposals'):
+            out[k] = v.reshape(B, ncmp, *v.shape[1:]).contiguous()
+        else:                                           # language tensors [B*ncmp, 1, ...] -> [B, ncmp, ...]
+            out[k] = v.reshape(B, ncmp, *v.shape[2:]).contiguous()
+    r = _rng(f'batch_sep/{B}/{ncmp}/{nppf}', seed)
+    nval = out['srl_arg_inds_msk'].sum(-1).numpy()     # populated argument slots of every (query, video)
+    verb = (r.integers(0, 1 << 30, size=(B, ncmp)) % nval).astype(np.int64)
+    out['verb_ind_in_srl'] = torch.from_numpy(verb)
+    out['new_srl_idxs'] = torch.zeros(B, ncmp, dtype=torch.int64)
+    msk = torch.ones(B, ncmp, dtype=torch.int64)
+    if ncmp > 1:
+        msk[1::2, -1] = 0
+    out['num_cmp_msk'] = msk
+    return out
+
+
 def clone_batch(batch, device=None):
     """The reference forward mutates ``srl_arg_word_mask`` in place (code/mdl_vog.py:80-82)."""
     return {k: (v.clone() if device is None else v.to(device, copy=True)) for k, v in batch.items()}
 
 
 def workload(name, seed=1):
+    if name in WORKLOADS_SEP:
+        w = dict(WORKLOADS_SEP[name])
+        return w, make_batch_sep(seed=seed, **w)
     w = dict(WORKLOADS[name])
     return w, make_batch(seed=seed, **w)
 
