@@ -232,13 +232,23 @@ int vog_mask_rows(const float* x, const int64_t* msk, int rows, int D, float* ou
  * reference's operation order); loss[0] = mean over {arg_boxes_mask[b,s] * cmp_msk[b,vid(p)] != 0} of
  * BCE-with-logits(logit, target) * P * loss_lambda (plain mean when no argument has boxes).  targets
  * [B,nsrl,P] u8 may be NULL; workspace: vog_loss_workspace_bytes().  replaces
- * code/mdl_conc_single.py:191-311,342-433 + utils/box_utils.py:54-118. */
+ * code/mdl_conc_single.py:191-311,342-433 + utils/box_utils.py:54-118.
+ * `spat` is the layout mode: 0 = temp rows [vid][frame][prop], 1 = spat rows [frame][vid][prop], 2 = sep
+ * (LossB_SEP grounding term, code/mdl_conc_sep.py:236-365): B = (query, video) pairs, ncmp = 1, target_cmp[b] = 0
+ * for the target video of its query and anything else otherwise, cmp_msk [B,1]; the mean selects by cmp_msk alone
+ * and arg_boxes_mask only decides masked-vs-plain mean. */
 int64_t vog_loss_workspace_bytes(int B, int nsrl, int P);
 int vog_loss_fwd(const float* logits, const float* props, int pdim, const float* gt, const uint8_t* frm_mask,
                  const uint8_t* pnt_mask, const int64_t* srl_boxes, const int64_t* srl_lens,
                  const int64_t* arg_boxes_mask, const int64_t* cmp_msk, const int64_t* target_cmp, int B, int nsrl,
                  int nb, int P, int K, int ncmp, int nppf, int spat, float loss_lambda, uint8_t* targets,
                  void* workspace, float* loss, void* stream);
+
+/* Verb loss of LossB_SEP (code/mdl_conc_sep.py:418-434): vidf [n] video-level logits (n = B*ncmp), verb_cmp [n] int64
+ * 0/1 targets, verb_cross_cmp_msk [n,m] int64; loss[0] = mean over rows with any mask entry set of
+ * BCE-with-logits(vidf, verb_cmp) * loss_lambda (NaN when no row is selected, like the reference's empty mean). */
+int vog_verb_loss_fwd(const float* vidf, const int64_t* verb_cmp, const int64_t* verb_cross_cmp_msk, int n, int m,
+                      float loss_lambda, float* loss, void* stream);
 
 /* ---- debug hooks (not part of the data path) ----------------------------------------------------
  * vog_debug_gemm_trace: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of every

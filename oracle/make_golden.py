@@ -108,6 +108,24 @@ def sep_case(name):
           f'fin_scores {out["fin_scores"].numpy().round(4).tolist()}')
 
 
+def loss_sep_case(name):
+    """LossB_SEP of the unmodified reference on the golden SEP outputs -> tests/golden/loss_{name}.npz."""
+    w, batch = synth.workload(name)
+    gold = np.load(os.path.join(GOLD, f'{name}.npz'))
+    out = {'mdl_outs': torch.from_numpy(gold['mdl_outs']), 'vidf_outs': torch.from_numpy(gold['vidf_outs'])}
+    inp = dict(batch)
+    inp.update(synth.make_loss_inputs_sep(batch, **w))
+    loss_fn = rh.build_reference_loss('sep', w['nppf'])
+    with torch.no_grad():
+        res = loss_fn(out, {k: v.clone() for k, v in inp.items()})
+        tg = loss_fn.compute_loss_targets({k: v.clone() for k, v in inp.items()})['targets_one']
+    np.savez(os.path.join(GOLD, f'loss_{name}.npz'), loss=res['loss'].numpy(), mdl_out_loss=res['mdl_out_loss'].numpy(),
+             verb_loss=res['verb_loss'].numpy(), targets=np.packbits(tg.numpy().astype(np.uint8)),
+             targets_shape=np.array(tg.shape))
+    print(f'loss_{name}: loss {float(res["loss"]):.6f} verb_loss {float(res["verb_loss"]):.6f} '
+          f'positives {int(tg.sum())} of {tg.numel()}')
+
+
 def loss_case(name):
     """LossB_SPAT / LossB_TEMP of the unmodified reference on the golden logits of `name` and the synthetic
     loss inputs -> tests/golden/loss_{name}.npz (loss value, boolean targets packed as uint8)."""
@@ -148,3 +166,6 @@ if __name__ == '__main__':
     for nm in synth.WORKLOADS_SEP:
         if not want or nm in want:
             sep_case(nm)
+    for nm in synth.WORKLOADS_SEP:
+        if not want or ('loss_' + nm) in want:
+            loss_sep_case(nm)

@@ -136,13 +136,15 @@ def _byte_mask_compat():
 
 
 def build_reference_loss(conc_type, nppf):
-    """Unmodified LossB_SPAT / LossB_TEMP (code/mdl_conc_single.py:180-433)."""
+    """Unmodified LossB_SPAT / LossB_TEMP (code/mdl_conc_single.py:180-433) / LossB_SEP (code/mdl_conc_sep.py:219-447)."""
     _install_stubs()
     _byte_mask_compat()
     import mdl_conc_single  # noqa
+    import mdl_conc_sep  # noqa
     cfg = reference_cfg(conc_type)
     comm = Munch(vocab_size=1000, detect_size=10, itod={}, wtoi={'UNK': 0}, num_prop_per_frm=nppf)
-    cls = {'spat': mdl_conc_single.LossB_SPAT, 'temp': mdl_conc_single.LossB_TEMP}[conc_type]
+    cls = {'spat': mdl_conc_single.LossB_SPAT, 'temp': mdl_conc_single.LossB_TEMP,
+           'sep': mdl_conc_sep.LossB_SEP}[conc_type]
     return cls(cfg, comm)
 
 

@@ -394,3 +394,36 @@ def loss_forward(mdl_outs, inp, conc_type, ncmp, nppf, nfrm0=10, loss_lambda=1.0
     sel = torch.masked_select(tot, bm.bool()) if inp['srl_arg_boxes_mask'].max() > 0 else tot
     loss = sel.mean() * tot.size(-1) * loss_lambda
     return {'loss': loss, 'mdl_out_loss': loss, 'targets': targets}
+
+
+def loss_forward_sep(out, inp, loss_lambda=1.0):
+    """LossB_SEP.forward restated (code/mdl_conc_sep.py:236-447): per-video IoU targets (only the target video of
+    a query keeps its overlaps, :301-321), BCE with logits masked by num_cmp_msk alone (:341-365; the argument
+    mask only decides masked-vs-plain mean), and the verb loss on the video-level logits (:418-434).  'loss' is
+    the grounding term only (:436-437).  -> {'loss','mdl_out_loss','verb_loss'} and targets [B,ncmp,nsrl,P1]."""
+    props, gt = inp['pad_proposals'], inp['pad_gt_bboxs']
+    B, ncmp, P1 = props.shape[:3]
+    frm = inp['pad_frm_mask'] | inp['pad_pnt_mask'].unsqueeze(-1)                     # :283-290
+    ov = bbox_overlaps_batch(props.reshape(B * ncmp, P1, -1)[:, :, :5], gt.reshape(B * ncmp, *gt.shape[2:])[:, :, :5],
+                             frm.reshape(B * ncmp, P1, -1)).view(B, ncmp, P1, -1)
+    K = ov.shape[-1]
+    onehot = (torch.arange(ncmp).view(1, ncmp) == inp['target_cmp'].view(B, 1)).to(ov.dtype)
+    ov = ov * onehot.view(B, ncmp, 1, 1)                                               # :306-314
+    sb, sl = inp['srl_boxes'], inp['srl_boxes_lens']
+    if sb.shape[1] == 1 and ncmp > 1:
+        sb = sb.expand(-1, ncmp, -1, -1)
+    nsrl, nb = sb.shape[2], sb.shape[3]
+    g = torch.gather(ov.view(B, ncmp, 1, P1, K).expand(B, ncmp, nsrl, P1, K), -1,
+                     sb.view(B, ncmp, nsrl, 1, nb).expand(B, ncmp, nsrl, P1, nb))      # :250-262
+    g = g * sl.float().unsqueeze(-2)
+    targets = g.max(dim=-1)[0] > 0.5
+    tot = F.binary_cross_entropy_with_logits(out['mdl_outs'], targets.float(), reduction='none')
+    bm = inp['num_cmp_msk'].view(B, ncmp, 1, 1).expand(B, ncmp, nsrl, P1).float()
+    tot = tot * bm
+    sel = torch.masked_select(tot, bm.bool()) if inp['srl_arg_boxes_mask'].max() > 0 else tot
+    mdl_loss = sel.mean() * P1
+    vl = F.binary_cross_entropy_with_logits(out['vidf_outs'], inp['verb_cmp'].float(), reduction='none')
+    vm = (inp['verb_cross_cmp_msk'].float().sum(-1) > 0)
+    verb_loss = torch.masked_select(vl * vm.float(), vm).mean()
+    return {'loss': mdl_loss * loss_lambda, 'mdl_out_loss': mdl_loss * loss_lambda, 'verb_loss': verb_loss * loss_lambda,
+            'targets': targets}

@@ -51,8 +51,8 @@ def test_selector_surface():
         cfg = synth.default_cfg(conc)
         out = vb.get_mdl_loss_eval(cfg)
         assert out['mdl'].__name__ == 'VOG_SEP' and out['eval'].__name__ == 'EvaluatorSEP'
-        with pytest.raises(NotImplementedError):    # LossB_SEP is not rebuilt: asking for it fails loudly
-            out['loss'](cfg, synth.default_comm(5))
+        assert out['loss'].__name__ == 'LossB_SEP'
+        assert out['loss'](cfg, synth.default_comm(5)).loss_keys == ['loss', 'mdl_out_loss', 'verb_loss']
     cfg = synth.default_cfg('spat')
     cfg.mdl.name = 'nope'
     with pytest.raises(NotImplementedError):

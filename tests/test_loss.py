@@ -96,3 +96,70 @@ def test_cuda_loss_refuses_autograd():
     x = logits.cuda().requires_grad_(True)
     with pytest.raises(NotImplementedError):
         fn({'mdl_outs': x}, {k: v.cuda() for k, v in inp.items()})
+
+
+# ---------------------------------------------------------------------------------------------
+# LossB_SEP (code/mdl_conc_sep.py:219-447)
+# ---------------------------------------------------------------------------------------------
+def _case_sep(name):
+    w, batch = synth.workload(name)
+    g = np.load(os.path.join(GOLD, f'{name}.npz'))
+    gl = np.load(os.path.join(GOLD, f'loss_{name}.npz'))
+    inp = dict(batch)
+    inp.update(synth.make_loss_inputs_sep(batch, **w))
+    tg = np.unpackbits(gl['targets'])[:int(np.prod(gl['targets_shape']))].reshape(gl['targets_shape']).astype(bool)
+    out = {'mdl_outs': torch.from_numpy(g['mdl_outs']), 'vidf_outs': torch.from_numpy(g['vidf_outs'])}
+    return w, inp, out, float(gl['loss']), float(gl['verb_loss']), tg
+
+
+@pytest.mark.parametrize('name', list(synth.WORKLOADS_SEP))
+def test_oracle_sep_loss_matches_reference(name):
+    w, inp, out, loss, verb, tg = _case_sep(name)
+    r = vo.loss_forward_sep(out, inp)
+    assert np.array_equal(r['targets'].numpy(), tg) and tg.sum() > 0
+    assert abs(float(r['loss']) - loss) <= 1e-6 * abs(loss)
+    assert abs(float(r['verb_loss']) - verb) <= 1e-6 * abs(verb)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', list(synth.WORKLOADS_SEP))
+def test_cuda_sep_loss_matches_reference(name):
+    w, inp, out, loss, verb, tg = _case_sep(name)
+    cfg, comm = synth.default_cfg('sep'), synth.default_comm(w['nppf'])
+    fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
+    dinp = {k: v.cuda() for k, v in inp.items()}
+    with torch.no_grad():
+        res = fn({k: v.cuda() for k, v in out.items()}, dinp)
+        got_t = fn.compute_loss_targets(dinp)['targets_one']
+    torch.cuda.synchronize()
+    assert set(res) == {'loss', 'mdl_out_loss', 'verb_loss'}
+    assert np.array_equal(got_t.cpu().numpy(), tg), 'IoU targets must be bit-exact'
+    assert abs(float(res['loss']) - loss) <= 2e-6 * abs(loss), (float(res['loss']), loss)
+    assert abs(float(res['verb_loss']) - verb) <= 2e-6 * abs(verb), (float(res['verb_loss']), verb)
+
+
+@pytest.mark.gpu
+def test_cuda_sep_loss_edge_cases():
+    """no groundable argument -> mean of the video-masked losses over ALL elements (code/mdl_conc_sep.py:355-363);
+    single sentence slot expanded over the videos; no verb target at all -> NaN like the reference's empty mean."""
+    w, inp, out, _, _, _ = _case_sep('sep_gt5')
+    cfg, comm = synth.default_cfg('sep'), synth.default_comm(w['nppf'])
+    fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
+    dout = {k: v.cuda() for k, v in out.items()}
+    a = {k: v.clone() for k, v in inp.items()}
+    a['srl_arg_boxes_mask'] = torch.zeros_like(a['srl_arg_boxes_mask'])
+    b = {k: v.clone() for k, v in inp.items()}
+    for k in ('srl_boxes', 'srl_boxes_lens', 'srl_arg_boxes_mask'):
+        b[k] = b[k][:, :1].contiguous()
+    for v in (a, b):
+        ref = vo.loss_forward_sep(out, v)
+        with torch.no_grad():
+            got = fn(dout, {k: t.cuda() for k, t in v.items()})
+            tg = fn.compute_loss_targets({k: t.cuda() for k, t in v.items()})['targets_one']
+        assert torch.equal(tg.cpu(), ref['targets'])
+        assert abs(float(got['loss']) - float(ref['loss'])) <= 2e-6 * abs(float(ref['loss']))
+    c = {k: v.clone() for k, v in inp.items()}
+    c['verb_cross_cmp_msk'] = torch.zeros_like(c['verb_cross_cmp_msk'])
+    with torch.no_grad():
+        got = fn(dout, {k: t.cuda() for k, t in c.items()})
+    assert torch.isnan(got['verb_loss']) and torch.isnan(vo.loss_forward_sep(out, c)['verb_loss'])

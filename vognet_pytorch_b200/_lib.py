@@ -37,6 +37,7 @@ _SIGNATURES = {
     'vog_select_fwd': [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'vog_select_sep_fwd': [P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'vog_sep_fin_scores': [P, P, P, P, P, P, P, c_int, c_int, c_int, P],
+    'vog_verb_loss_fwd': [P, P, P, c_int, c_int, c_float, P, P],
     'vog_cast_lp': [P, c_i64, P, c_i64, c_i64, c_int, c_int, P],
     'vog_tc_gemm_workspace_bytes': [c_int, c_int, c_int, c_int, c_int],
     'vog_tc_gemm': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64,

@@ -24,6 +24,8 @@ int pe_project(const float* props, int ldp, const float* W, float* a, int rows, 
 int select_fwd(const float* scores, const float* props, int pdim, float* boxes, float* out_scores,
                long long* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, int spat,
                cudaStream_t st, const float* fin = nullptr);
+int verb_loss_fwd(const float* vidf, const long long* verb_cmp, const long long* vcc, int n, int m, float lambda,
+                  float* loss, cudaStream_t st);
 int sep_fin_scores(const float* logits, const float* vidf, const long long* srl_msk, const long long* verb_ind,
                    const long long* cmp_msk, float* fin_loss, float* fin_eval, int Bq, int nsrl, int P1, cudaStream_t st);
 

@@ -32,7 +32,7 @@ loss_targets_kernel(const float* __restrict__ logits, const float* __restrict__ 
     const float ax = __fadd_rn(__fsub_rn(ax2, ax1), 1.f), ay = __fadd_rn(__fsub_rn(ay2, ay1), 1.f);
     const float a_area = __fmul_rn(ax, ay);
     const bool a_zero = (ax == 1.f) && (ay == 1.f);
-    const int vid = spat ? (p / nppf) % ncmp : p / (P / ncmp);
+    const int vid = spat == 1 ? (p / nppf) % ncmp : p / (P / ncmp);
     const bool on_target = (long long)vid == target_cmp[b];
     const unsigned char pm = pnt_mask[(size_t)b * P + p];
 
@@ -77,7 +77,10 @@ loss_targets_kernel(const float* __restrict__ logits, const float* __restrict__ 
             // binary_cross_entropy_with_logits: (1 - t) x + m + log(exp(-m) + exp(-x - m)),  m = max(-x, 0)
             const float m = fmaxf(-x, 0.f);
             el[o] = (1.f - t) * x + m + logf(expf(-m) + expf(-x - m));
-            msk[o] = (unsigned char)((arg_boxes_mask[(size_t)b * nsrl + s0] != 0) && (cmp_msk[(size_t)b * ncmp + vid] != 0));
+            // mode 2 (SEP, code/mdl_conc_sep.py:341-355): the video mask alone selects; the argument mask only decides
+            // masked-vs-plain mean in the reduction
+            msk[o] = (unsigned char)((spat == 2 || arg_boxes_mask[(size_t)b * nsrl + s0] != 0) &&
+                                     (cmp_msk[(size_t)b * ncmp + vid] != 0));
             if (tgt) tgt[o] = hit ? 1 : 0;
         }
     }
@@ -87,7 +90,7 @@ loss_targets_kernel(const float* __restrict__ logits, const float* __restrict__ 
 __global__ void __launch_bounds__(1024)
 loss_reduce_kernel(const float* __restrict__ el, const unsigned char* __restrict__ msk,
                    const long long* __restrict__ arg_boxes_mask, int n_args, long long n, int P, float lambda,
-                   float* __restrict__ loss)
+                   float* __restrict__ loss, int sep)
 {
     __shared__ double s_sum[1024];
     __shared__ double s_all[1024];
@@ -113,7 +116,9 @@ loss_reduce_kernel(const float* __restrict__ el, const unsigned char* __restrict
     }
     if (tid == 0) {
         // code/mdl_conc_single.py:304-311,408-414: masked mean if any argument has boxes, plain mean otherwise
-        const double mean = s_any ? s_sum[0] / (double)s_cnt[0] : s_all[0] / (double)n;
+        // SEP multiplies by the video mask BEFORE the branch (code/mdl_conc_sep.py:355-363): its plain mean is the
+        // masked sum over all elements
+        const double mean = s_any ? s_sum[0] / (double)s_cnt[0] : (sep ? s_sum[0] : s_all[0]) / (double)n;
         loss[0] = (float)(mean * (double)P) * lambda;
     }
 }
@@ -127,7 +132,9 @@ int loss_fwd(const float* logits, const float* props, int pdim, const float* gt,
              void* workspace, float* loss, cudaStream_t st)
 {
     VOG_REQUIRE(B > 0 && nsrl > 0 && nb > 0 && P > 0 && K > 0 && ncmp > 0 && P % ncmp == 0, "loss_fwd: bad dimension");
-    VOG_REQUIRE(!spat || (nppf > 0 && P % (ncmp * nppf) == 0), "loss_fwd: spat grouping needs P %% (ncmp*nppf) == 0");
+    VOG_REQUIRE(spat >= 0 && spat <= 2, "loss_fwd: mode must be 0 (temp), 1 (spat) or 2 (sep)");
+    VOG_REQUIRE(spat != 1 || (nppf > 0 && P % (ncmp * nppf) == 0), "loss_fwd: spat grouping needs P %% (ncmp*nppf) == 0");
+    VOG_REQUIRE(spat != 2 || ncmp == 1, "loss_fwd: sep mode takes one video per (query, video) pair");
     const long long n = (long long)B * nsrl * P;
     float* el = reinterpret_cast<float*>(workspace);
     unsigned char* msk = reinterpret_cast<unsigned char*>(workspace) + n * 4;
@@ -136,8 +143,45 @@ int loss_fwd(const float* logits, const float* props, int pdim, const float* gt,
                                                                     srl_lens, arg_boxes_mask, cmp_msk, target_cmp, B, nsrl,
                                                                     nb, P, K, ncmp, nppf, spat, el, msk, targets);
     if (check_launch("loss_targets")) return -1;
-    loss_reduce_kernel<<<1, 1024, 0, st>>>(el, msk, arg_boxes_mask, B * nsrl, n, P, lambda, loss);
+    loss_reduce_kernel<<<1, 1024, 0, st>>>(el, msk, arg_boxes_mask, B * nsrl, n, P, lambda, loss, spat == 2);
     return check_launch("loss_reduce");
+}
+
+// Verb loss of LossB_SEP (code/mdl_conc_sep.py:418-434): BCE-with-logits of the video-level logits against verb_cmp,
+// mean over the (query, video) pairs whose verb_cross_cmp_msk row has any entry set (NaN when there is none, like the
+// mean of an empty selection).  n = B*ncmp pairs, m = row length of the mask.
+__global__ void verb_loss_kernel(const float* __restrict__ vidf, const long long* __restrict__ verb_cmp,
+                                 const long long* __restrict__ vcc, int n, int m, float lambda, float* __restrict__ loss)
+{
+    __shared__ double s_sum[256];
+    __shared__ int s_cnt[256];
+    const int tid = threadIdx.x;
+    double sum = 0.0; int cnt = 0;
+    for (int i = tid; i < n; i += 256) {
+        double rs = 0.0;                                    // float sum of 0/1 entries: exact
+        for (int j = 0; j < m; ++j) rs += (double)(float)vcc[(size_t)i * m + j];
+        if (rs > 0.0) {
+            const float x = vidf[i], t = (float)verb_cmp[i];
+            const float mx = fmaxf(-x, 0.f);
+            sum += (double)((1.f - t) * x + mx + logf(expf(-mx) + expf(-x - mx)));
+            ++cnt;
+        }
+    }
+    s_sum[tid] = sum; s_cnt[tid] = cnt;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) { s_sum[tid] += s_sum[tid + off]; s_cnt[tid] += s_cnt[tid + off]; }
+        __syncthreads();
+    }
+    if (tid == 0) loss[0] = (float)(s_sum[0] / (double)s_cnt[0]) * lambda;
+}
+
+int verb_loss_fwd(const float* vidf, const long long* verb_cmp, const long long* vcc, int n, int m, float lambda,
+                  float* loss, cudaStream_t st)
+{
+    VOG_REQUIRE(n > 0 && m > 0, "verb_loss_fwd: empty input");
+    verb_loss_kernel<<<1, 256, 0, st>>>(vidf, verb_cmp, vcc, n, m, lambda, loss);
+    return check_launch("verb_loss");
 }
 
 }  // namespace vog

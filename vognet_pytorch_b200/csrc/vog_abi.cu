@@ -119,6 +119,14 @@ int vog_sep_fin_scores(const float* logits, const float* vidf, const int64_t* sr
                           fin_loss, fin_eval, Bq, nsrl, P1, (cudaStream_t)stream);
 }
 
+int vog_verb_loss_fwd(const float* vidf, const int64_t* verb_cmp, const int64_t* verb_cross_cmp_msk, int n, int m,
+                      float loss_lambda, float* loss, void* stream)
+{
+    VOG_REQUIRE(vidf && verb_cmp && verb_cross_cmp_msk && loss, "vog_verb_loss_fwd: null operand");
+    return verb_loss_fwd(vidf, (const long long*)verb_cmp, (const long long*)verb_cross_cmp_msk, n, m, loss_lambda, loss,
+                         (cudaStream_t)stream);
+}
+
 static int require_sm100(const char* who)
 {
     VOG_REQUIRE(vog_device_is_sm100(), "%s: needs an sm_100 (B200) device - tcgen05/TMEM kernels have no other path", who);

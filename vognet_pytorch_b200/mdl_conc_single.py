@@ -64,3 +64,64 @@ class LossB_SPAT(_LossB):
 class LossB_TEMP(_LossB):
     """code/mdl_conc_single.py:180-332"""
     SPAT = False
+
+
+class LossB_SEP(nn.Module):
+    """code/mdl_conc_sep.py:219-447: grounding loss of the SEP concatenation + the verb loss on the video-level
+    logits.  ``forward(out, inp) -> {'loss', 'mdl_out_loss', 'verb_loss'}`` ('loss' is the grounding term only,
+    :436-437).  Every (query, video) pair goes through ``vog_loss_fwd`` in its sep mode as one single-video problem
+    whose overlaps survive only for the query's target video (:301-314); forward only, like LossB_SPAT/TEMP."""
+
+    def __init__(self, cfg, comm):
+        super().__init__()
+        self.cfg, self.comm = cfg, comm
+        self.loss_keys = ['loss', 'mdl_out_loss', 'verb_loss']
+        self.loss_lambda = float(cfg.loss.loss_lambda)
+        self.num_prop_per_frm = int(comm['num_prop_per_frm'])
+
+    def _run(self, inp, mdl_outs, want_targets=False):
+        props = inp['pad_proposals']
+        if not props.is_cuda:
+            raise RuntimeError('vognet_pytorch_b200 runs on CUDA only (no CPU path)')
+        if props.dim() != 4:
+            raise ValueError(f"conc_type 'sep' expects pad_proposals [B,ncmp,P1,7], got {tuple(props.shape)}")
+        B, ncmp, P1 = props.shape[:3]
+        Bq = B * ncmp
+        sb, sl, am = inp['srl_boxes'], inp['srl_boxes_lens'], inp['srl_arg_boxes_mask']
+        if sb.shape[1] == 1 and ncmp > 1:                  # one sentence slot for all videos (:246-247,336-337)
+            sb, sl, am = (t.expand(B, ncmp, *t.shape[2:]) for t in (sb, sl, am))
+        nsrl = sb.shape[2]
+        if mdl_outs is None:
+            mdl_outs = props.new_zeros(B, ncmp, nsrl, P1)
+        if inp['pad_pnt_mask'].dim() != 3:
+            raise AssertionError('pad_pnt_mask must be [B,ncmp,P1] (code/mdl_conc_sep.py:276)')
+        # pair (b,c): target video index 0 iff c is the query's target, else 1 (never matches -> all-zero overlaps)
+        tc = (torch.arange(ncmp, device=props.device).view(1, ncmp) != inp['target_cmp'].view(B, 1)).long().reshape(Bq)
+        # the argument mask only decides masked-vs-plain mean (srl_arg_boxes_mask.max() > 0, :358-363)
+        res = ops.loss_fwd(mdl_outs.detach().reshape(Bq, nsrl, P1).float(), props.reshape(Bq, P1, -1),
+                           inp['pad_gt_bboxs'].reshape(Bq, *inp['pad_gt_bboxs'].shape[2:]),
+                           inp['pad_frm_mask'].reshape(Bq, P1, -1), inp['pad_pnt_mask'].reshape(Bq, P1),
+                           sb.reshape(Bq, nsrl, -1), sl.reshape(Bq, nsrl, -1), am.reshape(Bq, nsrl),
+                           inp['num_cmp_msk'].reshape(Bq, 1), tc, 1, self.num_prop_per_frm, 2, self.loss_lambda,
+                           want_targets=want_targets)
+        if want_targets:
+            return res[0], res[1].view(B, ncmp, nsrl, P1)
+        return res, None
+
+    def compute_loss_targets(self, inp, mdl_outs=None):
+        """-> {'targets_one': bool [B,ncmp,nsrl,P1]} (code/mdl_conc_sep.py:293-321)."""
+        _, tg = self._run(inp, mdl_outs, want_targets=True)
+        return {'targets_one': tg}
+
+    def forward(self, out, inp):
+        mdl_outs = out['mdl_outs']
+        if torch.is_grad_enabled() and mdl_outs.requires_grad:
+            raise NotImplementedError('vognet_pytorch_b200: forward-only loss (no backward yet, SURVEY.md section 8f); '
+                                      'call it under torch.no_grad()')
+        loss, _ = self._run(inp, mdl_outs)
+        loss = loss.reshape(())
+        vidf = out['vidf_outs'].detach().float()
+        n = vidf.numel()
+        verb = ops.verb_loss_fwd(vidf.reshape(n), inp['verb_cmp'].reshape(n),
+                                 inp['verb_cross_cmp_msk'].reshape(n, -1), self.loss_lambda).reshape(())
+        return {'loss': loss, 'mdl_out_loss': loss.clone(), 'verb_loss': verb}

@@ -3,7 +3,7 @@
 ``eval(cfg, comm, device)``: code/main_dist.py:33-53)."""
 from . import mdl_vog
 from .eval_vsrl_corr import EvaluatorSEP, EvaluatorSPAT, EvaluatorTEMP
-from .mdl_conc_single import LossB_SPAT, LossB_TEMP
+from .mdl_conc_single import LossB_SEP, LossB_SPAT, LossB_TEMP
 
 _MODELS = {
     ('temp', 'igrnd'): mdl_vog.ImgGrnd_TEMP, ('temp', 'vgrnd'): mdl_vog.VidGrnd_TEMP,
@@ -16,16 +16,7 @@ _MODELS = {
 _EVALS = {'temp': EvaluatorTEMP, 'spat': EvaluatorSPAT, 'sep': EvaluatorSEP}
 
 
-_LOSSES = {'temp': LossB_TEMP, 'spat': LossB_SPAT}
-
-
-class _LossSEPUnavailable:
-    """LossB_SEP (code/mdl_conc_sep.py:219-447) is a training-side component that has not been rebuilt: the SEP
-    forward and evaluator are available, asking for the loss fails loudly instead of silently returning another."""
-
-    def __init__(self, *a, **k):
-        raise NotImplementedError('LossB_SEP (code/mdl_conc_sep.py:219-447) is not part of this build; '
-                                  "conc_type 'sep'/'svsq' supports the forward and the evaluator")
+_LOSSES = {'temp': LossB_TEMP, 'spat': LossB_SPAT, 'sep': LossB_SEP}
 
 
 def get_mdl_loss_eval(cfg):
@@ -34,5 +25,5 @@ def get_mdl_loss_eval(cfg):
         conc_type = 'sep'
     if (conc_type, mdl_type) not in _MODELS:
         raise NotImplementedError((conc_type, mdl_type))
-    return {'mdl': _MODELS[(conc_type, mdl_type)], 'loss': _LOSSES.get(conc_type, _LossSEPUnavailable),
+    return {'mdl': _MODELS[(conc_type, mdl_type)], 'loss': _LOSSES[conc_type],
             'eval': _EVALS[conc_type]}

@@ -150,6 +150,18 @@ def select_fwd(scores, props, ncmp, nfrm, nppf, spat):
     return boxes, sc, ix
 
 
+def verb_loss_fwd(vidf, verb_cmp, vcc_msk, loss_lambda=1.0):
+    """vidf [n] f32, verb_cmp [n] int64, vcc_msk [n,m] int64 -> loss [1] (see vog_verb_loss_fwd)."""
+    _req(vidf, torch.float32, 'vidf', 1), _req(verb_cmp, torch.int64, 'verb_cmp', 1), _req(vcc_msk, torch.int64, 'vcc_msk', 2)
+    n, m = vcc_msk.shape
+    if vidf.shape[0] != n or verb_cmp.shape[0] != n:
+        raise ValueError('verb_loss_fwd: inconsistent shapes')
+    loss = torch.empty(1, device=vidf.device, dtype=torch.float32)
+    _lib.check(_lib.lib().vog_verb_loss_fwd(_ptr(vidf.contiguous()), _ptr(verb_cmp.contiguous()), _ptr(vcc_msk.contiguous()),
+                                            n, m, float(loss_lambda), _ptr(loss), _stream()), 'vog_verb_loss_fwd')
+    return loss
+
+
 def select_sep_fwd(scores, props, fin_scores, nfrm, nppf):
     """scores [B,ncmp,nsrl,nfrm*nppf], props [B,ncmp,nfrm*nppf,pdim], fin_scores [B,ncmp] -> boxes, scores, indexs
     (see vog_select_sep_fwd)."""

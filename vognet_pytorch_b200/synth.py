@@ -323,6 +323,31 @@ def make_loss_inputs(batch, conc_type='spat', ncmp=4, nppf=5, seed=1, num_box=12
             'target_cmp': t(target_cmp)}
 
 
+def make_loss_inputs_sep(batch, ncmp=4, nppf=5, seed=1, num_box=12, **_unused):
+    """Loss inputs of LossB_SEP (code/mdl_conc_sep.py:236-447): the single-video loss inputs of every (query, video)
+    pair with the [ncmp] axis unfolded (gt boxes, masks and SRL box indices per video), the target video of every
+    query, and the verb targets ``verb_cmp`` [B,ncmp] / ``verb_cross_cmp_msk`` [B,ncmp,ncmp]."""
+    B = batch['pad_proposals'].shape[0]
+    Bq = B * ncmp
+    flat = {'pad_proposals': batch['pad_proposals'].reshape(Bq, *batch['pad_proposals'].shape[2:]),
+            'srl_arg_inds_msk': batch['srl_arg_inds_msk'].reshape(Bq, 1, -1)}
+    one = make_loss_inputs(flat, conc_type='temp', ncmp=1, nppf=nppf, seed=seed, num_box=num_box)
+    out = {}
+    for k, v in one.items():
+        if k == 'target_cmp':
+            continue
+        out[k] = (v.reshape(B, ncmp, *v.shape[2:]) if k in ('srl_boxes', 'srl_boxes_lens', 'srl_arg_boxes_mask')
+                  else v.reshape(B, ncmp, *v.shape[1:])).contiguous()
+    r = _rng(f'loss_sep/{B}/{ncmp}/{nppf}', seed)
+    out['target_cmp'] = torch.from_numpy(r.integers(0, ncmp, size=B).astype(np.int64))
+    out['verb_cmp'] = torch.from_numpy(r.integers(0, 2, size=(B, ncmp)).astype(np.int64))
+    vcc = r.integers(0, 2, size=(B, ncmp, ncmp)).astype(np.int64)
+    vcc[:, 0, :] = 0                                    # one video per query without a verb target
+    vcc[:, 1:, 0] = 1
+    out['verb_cross_cmp_msk'] = torch.from_numpy(vcc)
+    return out
+
+
 def make_batch_sep(B=2, ncmp=4, nppf=5, nvalid=None, seed=1, vocab_size=1000, **_unused):
     """SEP batch (code/mdl_conc_sep.py:131-217 reads these shapes): the B*ncmp (query, video) pairs of a
     single-video batch with the [ncmp] axis unfolded -
