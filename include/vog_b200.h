@@ -250,6 +250,17 @@ int vog_loss_fwd(const float* logits, const float* props, int pdim, const float*
 int vog_verb_loss_fwd(const float* vidf, const int64_t* verb_cmp, const int64_t* verb_cross_cmp_msk, int n, int m,
                       float loss_lambda, float* loss, void* stream);
 
+/* Contrastive-sample concatenation on the device: per-video tensors feat [B,ncmp,nfrm*nppf,D],
+ * seg [B,ncmp,nfrm,Ds], props [B,ncmp,nfrm*nppf,pdim] -> the single "concatenated video" the SPAT / TEMP models read.
+ * spat=1: rows reordered [vid][frame][prop] -> [frame][vid][prop] (seg: [vid][frame] -> [frame][vid]) and props columns
+ * 0,2 += shift*vid (shift = 720); spat=0: row order kept, props column 4 += shift*vid (shift = 10) - feat_out / seg_out
+ * must be NULL then (the inputs already are the concatenated tensors).  Any of the three outputs may be NULL to skip it.
+ * Bit-identical to the host code it replaces: reshuffle_boxes / process_props and the seg transpose,
+ * code/dat_loader_simple.py:1067-1103,1147-1153,1196-1207 (SPAT), :1231-1252,1290-1292 (TEMP). */
+int vog_concat_videos(const float* feat, int D, const float* seg, int Ds, const float* props, int pdim, float* feat_out,
+                      float* seg_out, float* props_out, int B, int ncmp, int nfrm, int nppf, int spat, float shift,
+                      void* stream);
+
 /* ---- debug hooks (not part of the data path) ----------------------------------------------------
  * vog_debug_gemm_trace: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of every
  * following vog_tc_gemm launch (entry, setup done, first TMA issued, first stage landed, last MMA

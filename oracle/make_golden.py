@@ -126,6 +126,25 @@ def loss_sep_case(name):
           f'positives {int(tg.sum())} of {tg.numel()}')
 
 
+def relayout_case(name):
+    """The reference's own host-side concatenation helpers (lifted from code/dat_loader_simple.py by
+    ref_harness.reference_item_closures) on the per-video batch -> tests/golden/relayout_{name}.npz: the full
+    proposal tensors and, for the wide feature tensors, every row's first 4 columns + float64 row sum (which pin
+    the row permutation without storing megabytes)."""
+    w, batch = synth.workload(name)
+    save = {}
+    for conc in ('spat', 'temp'):
+        f, s_, p = rh.reference_concat_videos(batch, conc, synth.NFRM0, w['nppf'])
+        save[f'{conc}_props'] = p.numpy()
+        save[f'{conc}_feat_head'] = f[..., :4].contiguous().numpy()
+        save[f'{conc}_feat_sum'] = f.double().sum(-1).numpy()
+        save[f'{conc}_seg_head'] = s_[..., :4].contiguous().numpy()
+        save[f'{conc}_seg_sum'] = s_.double().sum(-1).numpy()
+    np.savez_compressed(os.path.join(GOLD, f'relayout_{name}.npz'), **save)
+    print(f'relayout_{name}: spat props {save["spat_props"].shape} max x {save["spat_props"][..., 2].max():.1f} '
+          f'temp max frame {save["temp_props"][..., 4].max():.0f}')
+
+
 def loss_case(name):
     """LossB_SPAT / LossB_TEMP of the unmodified reference on the golden logits of `name` and the synthetic
     loss inputs -> tests/golden/loss_{name}.npz (loss value, boolean targets packed as uint8)."""
@@ -169,3 +188,6 @@ if __name__ == '__main__':
     for nm in synth.WORKLOADS_SEP:
         if not want or ('loss_' + nm) in want:
             loss_sep_case(nm)
+    for nm in synth.WORKLOADS_SEP:
+        if not want or ('relayout_' + nm) in want:
+            relayout_case(nm)

@@ -152,3 +152,42 @@ def reference_transformers():
     _install_stubs()
     import transformer_code  # noqa
     return transformer_code
+
+
+def reference_item_closures(conc_type, nfrm, nppf):
+    """The nested helpers ``reshuffle_boxes`` / ``process_props`` of ``verb_item_getter_SPAT`` / ``_TEMP``
+    (code/dat_loader_simple.py:1067-1103 / :1231-1252), compiled from the UNMODIFIED source text: they are closures
+    of a dataset method whose class needs the 530 GB dataset to construct, so their definitions are lifted out of
+    the parsed file and executed with a stand-in ``self`` carrying the two attributes they read."""
+    import ast
+    import torch
+    path = os.path.join(REF_ROOT, 'code', 'dat_loader_simple.py')
+    tree = ast.parse(open(path).read())
+    getter = 'verb_item_getter_' + conc_type.upper()
+    meth = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == getter)
+    defs = [n for n in meth.body if isinstance(n, ast.FunctionDef) and n.name in ('reshuffle_boxes', 'process_props')]
+    ns = {'torch': torch, 'self': types.SimpleNamespace(num_frms=nfrm, num_prop_per_frm=nppf)}
+    exec(compile(ast.Module(body=defs, type_ignores=[]), path, 'exec'), ns)
+    _install_stubs()
+    import mdl_srl_utils  # noqa: utils/mdl_srl_utils.py:11-17 combine_first_ax
+    ns['combine_first_ax'] = mdl_srl_utils.combine_first_ax
+    return ns
+
+
+def reference_concat_videos(batch, conc_type, nfrm, nppf):
+    """What the reference's item getters do to the per-video visual tensors of every sample
+    (code/dat_loader_simple.py:1147-1153,1196-1207 SPAT; :1290-1292 + stacking TEMP), stacked over the batch."""
+    import torch
+    ns = reference_item_closures(conc_type, nfrm, nppf)
+    feats, segs, props = [], [], []
+    for b in range(batch['pad_proposals'].shape[0]):
+        p, f, s = batch['pad_proposals'][b], batch['pad_region_feature'][b], batch['seg_feature_for_frms'][b]
+        if conc_type == 'spat':
+            props.append(ns['process_props'](p, keepdim=False, reshuffle_box=True))
+            feats.append(ns['reshuffle_boxes'](f))
+            segs.append(ns['combine_first_ax'](s.transpose(0, 1).contiguous(), keepdim=False))
+        else:
+            props.append(ns['process_props'](p, keepdim=False))
+            feats.append(ns['combine_first_ax'](f, keepdim=False))           # temporal stacking: rows stay [vid][frame][prop]
+            segs.append(ns['combine_first_ax'](s, keepdim=False))
+    return torch.stack(feats), torch.stack(segs), torch.stack(props)

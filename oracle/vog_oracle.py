@@ -427,3 +427,30 @@ def loss_forward_sep(out, inp, loss_lambda=1.0):
     verb_loss = torch.masked_select(vl * vm.float(), vm).mean()
     return {'loss': mdl_loss * loss_lambda, 'mdl_out_loss': mdl_loss * loss_lambda, 'verb_loss': verb_loss * loss_lambda,
             'targets': targets}
+
+
+# ---------------------------------------------------------------------------------------------
+# contrastive-sample concatenation: code/dat_loader_simple.py:1067-1207 (SPAT),
+# :1231-1292 (TEMP)
+# ---------------------------------------------------------------------------------------------
+def concat_videos(feat, seg, props, conc_type, nfrm, nppf):
+    """Per-video feat [B,ncmp,nfrm*nppf,D], seg [B,ncmp,nfrm,Ds], props [B,ncmp,nfrm*nppf,pdim] -> the concatenated
+    single-video tensors.  SPAT: x1,x2 += 720*vid (process_props :1081-1103), rows [vid][frame][prop] ->
+    [frame][vid][prop] (reshuffle_boxes :1067-1078), seg [vid][frame] -> [frame][vid] (:1200-1203).
+    TEMP: frame id += 10*vid (:1231-1252), order unchanged."""
+    B, ncmp, P1, D = feat.shape
+    pdim = props.shape[-1]
+    v = torch.arange(ncmp, dtype=torch.float32).view(1, ncmp, 1)
+    props = props.clone()
+    if conc_type == 'spat':
+        props[..., 0] = props[..., 0] + v * 720.0
+        props[..., 2] = props[..., 2] + v * 720.0
+        props = props.view(B, ncmp, nfrm, nppf, pdim).transpose(1, 2).reshape(B, ncmp * P1, pdim)
+        feat = feat.view(B, ncmp, nfrm, nppf, D).transpose(1, 2).reshape(B, ncmp * P1, D)
+        seg = seg.transpose(1, 2).reshape(B, ncmp * nfrm, seg.shape[-1])
+    else:
+        props[..., 4] = props[..., 4] + v * 10.0
+        props = props.reshape(B, ncmp * P1, pdim)
+        feat = feat.reshape(B, ncmp * P1, D)
+        seg = seg.reshape(B, ncmp * nfrm, seg.shape[-1])
+    return feat.contiguous(), seg.contiguous(), props.contiguous()

@@ -54,3 +54,12 @@ def test_sep_oracle_matches_live_reference():
         assert (got[k] - ref[k]).abs().max() < 5e-5, k
     for k in ('boxes', 'scores', 'indexs'):
         assert torch.equal(sel[k], sel_ref[k].contiguous()), k
+
+
+@pytest.mark.parametrize('conc', ['spat', 'temp'])
+def test_concat_oracle_matches_live_reference_helpers(conc):
+    batch = synth.make_batch_sep(B=3, ncmp=3, nppf=5, seed=31)
+    ref = rh.reference_concat_videos(batch, conc, 10, 5)
+    got = vo.concat_videos(batch['pad_region_feature'], batch['seg_feature_for_frms'], batch['pad_proposals'], conc, 10, 5)
+    for r, g in zip(ref, got):
+        assert torch.equal(r, g)

@@ -24,6 +24,9 @@ int pe_project(const float* props, int ldp, const float* W, float* a, int rows, 
 int select_fwd(const float* scores, const float* props, int pdim, float* boxes, float* out_scores,
                long long* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, int spat,
                cudaStream_t st, const float* fin = nullptr);
+int concat_videos(const float* feat, int D, const float* seg, int Ds, const float* props, int pdim, float* feat_out,
+                  float* seg_out, float* props_out, int B, int ncmp, int nfrm, int nppf, int spat, float shift,
+                  cudaStream_t st);
 int verb_loss_fwd(const float* vidf, const long long* verb_cmp, const long long* vcc, int n, int m, float lambda,
                   float* loss, cudaStream_t st);
 int sep_fin_scores(const float* logits, const float* vidf, const long long* srl_msk, const long long* verb_ind,

@@ -127,6 +127,14 @@ int vog_verb_loss_fwd(const float* vidf, const int64_t* verb_cmp, const int64_t*
                          (cudaStream_t)stream);
 }
 
+int vog_concat_videos(const float* feat, int D, const float* seg, int Ds, const float* props, int pdim, float* feat_out,
+                      float* seg_out, float* props_out, int B, int ncmp, int nfrm, int nppf, int spat, float shift,
+                      void* stream)
+{
+    return concat_videos(feat, D, seg, Ds, props, pdim, feat_out, seg_out, props_out, B, ncmp, nfrm, nppf, spat, shift,
+                         (cudaStream_t)stream);
+}
+
 static int require_sm100(const char* who)
 {
     VOG_REQUIRE(vog_device_is_sm100(), "%s: needs an sm_100 (B200) device - tcgen05/TMEM kernels have no other path", who);

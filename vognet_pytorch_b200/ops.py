@@ -150,6 +150,34 @@ def select_fwd(scores, props, ncmp, nfrm, nppf, spat):
     return boxes, sc, ix
 
 
+def concat_videos(feat, seg, props, conc_type, nfrm, nppf, vid_shift=None):
+    """Per-video tensors feat [B,ncmp,nfrm*nppf,D], seg [B,ncmp,nfrm,Ds], props [B,ncmp,nfrm*nppf,pdim] -> the
+    concatenated (feat [B,P,D], seg [B,ncmp*nfrm,Ds], props [B,P,pdim]) of conc_type 'spat' / 'temp' (see
+    vog_concat_videos).  TEMP keeps the row order: its feat / seg results are views of the inputs."""
+    if conc_type not in ('spat', 'temp'):
+        raise ValueError("concat_videos: conc_type must be 'spat' or 'temp'")
+    _req(feat, torch.float32, 'feat', 4), _req(seg, torch.float32, 'seg', 4), _req(props, torch.float32, 'props', 4)
+    B, ncmp, P1, D = feat.shape
+    if P1 != nfrm * nppf or tuple(seg.shape[:3]) != (B, ncmp, nfrm) or tuple(props.shape[:3]) != (B, ncmp, P1):
+        raise ValueError(f'concat_videos: feat {tuple(feat.shape)} / seg {tuple(seg.shape)} / props {tuple(props.shape)} '
+                         f'do not describe [B,ncmp,{nfrm}*{nppf}]')
+    spat = conc_type == 'spat'
+    shift = float(vid_shift if vid_shift is not None else (720.0 if spat else 10.0))
+    feat, seg, props = feat.contiguous(), seg.contiguous(), props.contiguous()
+    props_out = torch.empty(B, ncmp * P1, props.shape[-1], device=props.device, dtype=torch.float32)
+    if spat:
+        feat_out = torch.empty(B, ncmp * P1, D, device=feat.device, dtype=torch.float32)
+        seg_out = torch.empty(B, ncmp * nfrm, seg.shape[-1], device=seg.device, dtype=torch.float32)
+    else:
+        feat_out, seg_out = None, None
+    _lib.check(_lib.lib().vog_concat_videos(_ptr(feat), D, _ptr(seg), seg.shape[-1], _ptr(props), props.shape[-1],
+                                            _ptr(feat_out), _ptr(seg_out), _ptr(props_out), B, ncmp, nfrm, nppf,
+                                            int(spat), shift, _stream()), 'vog_concat_videos')
+    if not spat:
+        feat_out, seg_out = feat.view(B, ncmp * P1, D), seg.view(B, ncmp * nfrm, seg.shape[-1])
+    return feat_out, seg_out, props_out
+
+
 def verb_loss_fwd(vidf, verb_cmp, vcc_msk, loss_lambda=1.0):
     """vidf [n] f32, verb_cmp [n] int64, vcc_msk [n,m] int64 -> loss [1] (see vog_verb_loss_fwd)."""
     _req(vidf, torch.float32, 'vidf', 1), _req(verb_cmp, torch.int64, 'verb_cmp', 1), _req(vcc_msk, torch.int64, 'vcc_msk', 2)

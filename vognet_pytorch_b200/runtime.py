@@ -41,6 +41,24 @@ def gather_predictions(pred, world=None, group=None):
     return out
 
 
+def concat_batch(sep_batch, conc_type, nfrm, nppf, sentence_slot=0):
+    """SPAT / TEMP batch dict from a per-video (SEP-layout) batch that is already on the GPU: the visual tensors go
+    through ``vog_concat_videos`` (what the reference's dataset does per sample on the host,
+    code/dat_loader_simple.py:1067-1207,1231-1292), the language tensors keep the one sentence slot the concatenated
+    models read (``[B,1,...]``; SPAT/TEMP samples carry the query sentence once, append_everywhere=False :934-941)."""
+    from . import ops
+    feat, seg, props = ops.concat_videos(sep_batch['pad_region_feature'], sep_batch['seg_feature_for_frms'],
+                                         sep_batch['pad_proposals'], conc_type, nfrm, nppf)
+    out = {'pad_region_feature': feat, 'seg_feature_for_frms': seg, 'pad_proposals': props,
+           'new_srl_idxs': sep_batch['new_srl_idxs'], 'num_cmp_msk': sep_batch['num_cmp_msk']}
+    for k in ('srl_arg_words_ind', 'srl_arg_word_mask', 'srl_tag_word_ind', 'srl_arg_word_mask_len',
+              'srl_arg_words_capture', 'srl_arg_inds_msk'):
+        if k in sep_batch:
+            v = sep_batch[k]
+            out[k] = v[:, sentence_slot:sentence_slot + 1].contiguous() if v.shape[1] > 1 else v
+    return out
+
+
 def max_over_ranks(seconds, device):
     """Device-side max of a per-rank duration (the multi-GPU timing rule of bench.py)."""
     t = torch.tensor([seconds], device=device, dtype=torch.float64)
