@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Print the kernels of the last complete forward in an ncu launch list (eager bench run):
-from the last lang_embed_kernel to the following select_vid_kernel.  usage: last_forward.py launches.csv"""
+from the last lang_embed_kernel to the following select_kernel.  usage: last_forward.py launches.csv"""
 import csv
 import re
 import sys
@@ -10,7 +10,7 @@ lines = [l for l in open(f) if not l.startswith('==')]
 rows = [r for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
 names = [re.sub(r'\(.*', '', re.sub(r'<.*', '', r['Kernel Name'])).replace('void ', '').replace('vog::', '') for r in rows]
 starts = [i for i, n in enumerate(names) if n.startswith('lang_embed')]
-ends = [i for i, n in enumerate(names) if n.startswith('select_vid')]
+ends = [i for i, n in enumerate(names) if n.startswith('select_kernel')]
 pairs = [(s, min(e for e in ends if e > s)) for s in starts if any(e > s for e in ends)]
 s, e = pairs[-1]
 tot = 0.0
