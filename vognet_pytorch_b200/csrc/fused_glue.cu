@@ -133,7 +133,16 @@ lang_embed_kernel(const long long* __restrict__ words, int nwords, const long lo
     long long tok = pad_idx;
     if (mk != -1) tok = words[(size_t)b * nwords + (mk < 0 ? 0 : (mk >= nwords ? nwords - 1 : mk))];
     const float4* src = reinterpret_cast<const float4*>(emb + (size_t)tok * E);
-    for (int c = threadIdx.x; c < E / 4; c += blockDim.x) store_lp4(out_lp, (size_t)row * E + 4 * c, __ldg(src + c), lp_kind);
+    // blockIdx.y owns a 512-float4 column chunk: four independent 16-byte loads per thread, and enough CTAs to fill
+    // the GPU when the rows are the 32 KB lines of the layer-0 projection table (80 rows at spat/gt5)
+    const int c0 = blockIdx.y * 512 + threadIdx.x, n4 = E / 4;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (c0 + 128 * k < n4) v[k] = __ldg(src + c0 + 128 * k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (c0 + 128 * k < n4) store_lp4(out_lp, (size_t)row * E + 4 * (c0 + 128 * k), v[k], lp_kind);
 }
 
 int lang_embed(const long long* words, int nwords, const long long* mask, int T, const float* emb, int E,
@@ -141,7 +150,7 @@ int lang_embed(const long long* words, int nwords, const long long* mask, int T,
 {
     VOG_REQUIRE(E % 4 == 0, "lang_embed: embedding width must be a multiple of 4");
     if (T * Bq == 0) return 0;
-    lang_embed_kernel<<<T * Bq, 128, 0, st>>>(words, nwords, mask, T, emb, E, pad_idx, Bq, out_lp, lp_kind);
+    lang_embed_kernel<<<dim3(T * Bq, (E / 4 + 511) / 512), 128, 0, st>>>(words, nwords, mask, T, emb, E, pad_idx, Bq, out_lp, lp_kind);
     return check_launch("lang_embed");
 }
 
