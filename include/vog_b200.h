@@ -244,6 +244,14 @@ int vog_loss_fwd(const float* logits, const float* props, int pdim, const float*
                  int nb, int P, int K, int ncmp, int nppf, int spat, float loss_lambda, uint8_t* targets,
                  void* workspace, float* loss, void* stream);
 
+/* Backward of vog_loss_fwd with respect to the logits (first link of the backward chain):
+ * grad_logits[i] = grad_out[0] * d loss / d logits[i] = grad_out * coef * w_i * (sigmoid(logits_i) - targets_i), with the
+ * selection mask w and coef = P * loss_lambda / count taken from the workspace the forward call filled (pass the SAME
+ * workspace and the `targets` it wrote).  grad_out: device pointer to one float.  What torch autograd derives for
+ * code/mdl_conc_single.py:277-311 / code/mdl_conc_sep.py:323-365. */
+int vog_loss_bwd(const float* logits, const uint8_t* targets, const void* workspace, const float* grad_out, float* grad_logits,
+                 int B, int nsrl, int P, void* stream);
+
 /* Verb loss of LossB_SEP (code/mdl_conc_sep.py:418-434): vidf [n] video-level logits (n = B*ncmp), verb_cmp [n] int64
  * 0/1 targets, verb_cross_cmp_msk [n,m] int64; loss[0] = mean over rows with any mask entry set of
  * BCE-with-logits(vidf, verb_cmp) * loss_lambda (NaN when no row is selected, like the reference's empty mean). */

@@ -108,6 +108,21 @@ def sep_case(name):
           f'fin_scores {out["fin_scores"].numpy().round(4).tolist()}')
 
 
+GRAD_STRIDE = 7
+
+
+def _reference_logit_grad(loss_fn, out, inp):
+    """d loss / d mdl_outs through torch autograd on the UNMODIFIED reference loss: every GRAD_STRIDE-th element of
+    the flattened gradient plus its float64 sum and absolute sum."""
+    o = {k: v.clone() for k, v in out.items()}
+    o['mdl_outs'] = o['mdl_outs'].clone().requires_grad_(True)
+    res = loss_fn(o, {k: v.clone() for k, v in inp.items()})
+    res['loss'].backward()
+    g = o['mdl_outs'].grad.reshape(-1)
+    return {'grad_sample': g[::GRAD_STRIDE].contiguous().numpy(), 'grad_sum': np.array(g.double().sum().item()),
+            'grad_abs_sum': np.array(g.double().abs().sum().item())}
+
+
 def loss_sep_case(name):
     """LossB_SEP of the unmodified reference on the golden SEP outputs -> tests/golden/loss_{name}.npz."""
     w, batch = synth.workload(name)
@@ -119,8 +134,9 @@ def loss_sep_case(name):
     with torch.no_grad():
         res = loss_fn(out, {k: v.clone() for k, v in inp.items()})
         tg = loss_fn.compute_loss_targets({k: v.clone() for k, v in inp.items()})['targets_one']
+    grad = _reference_logit_grad(loss_fn, out, inp)
     np.savez(os.path.join(GOLD, f'loss_{name}.npz'), loss=res['loss'].numpy(), mdl_out_loss=res['mdl_out_loss'].numpy(),
-             verb_loss=res['verb_loss'].numpy(), targets=np.packbits(tg.numpy().astype(np.uint8)),
+             verb_loss=res['verb_loss'].numpy(), **grad, targets=np.packbits(tg.numpy().astype(np.uint8)),
              targets_shape=np.array(tg.shape))
     print(f'loss_{name}: loss {float(res["loss"]):.6f} verb_loss {float(res["verb_loss"]):.6f} '
           f'positives {int(tg.sum())} of {tg.numel()}')
@@ -157,8 +173,9 @@ def loss_case(name):
     with torch.no_grad():
         res = loss_fn(out, {k: v.clone() for k, v in inp.items()})
         tg = loss_fn.compute_loss_targets({k: v.clone() for k, v in inp.items()})['targets_one']
+    grad = _reference_logit_grad(loss_fn, out, inp)
     np.savez(os.path.join(GOLD, f'loss_{name}.npz'), loss=res['loss'].numpy(), mdl_out_loss=res['mdl_out_loss'].numpy(),
-             targets=np.packbits(tg.numpy().astype(np.uint8)), targets_shape=np.array(tg.shape))
+             targets=np.packbits(tg.numpy().astype(np.uint8)), targets_shape=np.array(tg.shape), **grad)
     print(f'loss_{name}: loss {float(res["loss"]):.6f}  positives {int(tg.sum())} of {tg.numel()}')
 
 

@@ -88,14 +88,57 @@ def test_cuda_loss_edge_cases():
         assert abs(float(out['loss']) - float(ref['loss'])) <= 2e-6 * abs(float(ref['loss']))
 
 
+def _golden_grad(name):
+    gl = np.load(os.path.join(GOLD, f'loss_{name}.npz'))
+    return gl['grad_sample'], float(gl['grad_sum']), float(gl['grad_abs_sum'])
+
+
+def _check_grad(g, name):
+    sample, gsum, gabs = _golden_grad(name)
+    g = g.detach().cpu().reshape(-1)
+    scale = float(np.abs(sample).max())
+    assert np.abs(g[::7].numpy() - sample).max() <= 2e-6 * scale
+    assert abs(float(g.double().sum()) - gsum) <= 1e-5 * gabs
+    assert abs(float(g.double().abs().sum()) - gabs) <= 1e-5 * gabs
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_oracle_loss_gradient_matches_reference(name):
+    """d loss / d logits (first link): autograd through the oracle restatement against the
+    gradient autograd derives for the unmodified reference loss."""
+    w, inp, logits, _, _ = _case(name)
+    x = logits.clone().requires_grad_(True)
+    vo.loss_forward(x, inp, w['conc_type'], w['ncmp'], w['nppf'])['loss'].backward()
+    _check_grad(x.grad, name)
+
+
 @pytest.mark.gpu
-def test_cuda_loss_refuses_autograd():
-    w, inp, logits, _, _ = _case('cpu_ref')
+@pytest.mark.parametrize('name', NAMES)
+def test_cuda_loss_gradient_matches_reference(name):
+    w, inp, logits, loss, _ = _case(name)
     cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
     fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
     x = logits.cuda().requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        fn({'mdl_outs': x}, {k: v.cuda() for k, v in inp.items()})
+    out = fn({'mdl_outs': x}, {k: v.cuda() for k, v in inp.items()})
+    assert abs(float(out['loss'].detach()) - loss) <= 2e-6 * abs(loss)
+    (out['loss'] * 0.5).backward()                                     # a non-trivial upstream gradient
+    assert x.grad.shape == x.shape
+    _check_grad(x.grad * 2.0, name)
+
+
+@pytest.mark.gpu
+def test_cuda_loss_gradient_plain_mean_branch():
+    """no groundable argument -> plain mean: every element gets weight P / n."""
+    w, inp, logits, _, _ = _case('temp_gt5')
+    inp = dict(inp)
+    inp['srl_arg_boxes_mask'] = torch.zeros_like(inp['srl_arg_boxes_mask'])
+    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
+    fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
+    x = logits.cuda().requires_grad_(True)
+    fn({'mdl_outs': x}, {k: v.cuda() for k, v in inp.items()})['loss'].backward()
+    xr = logits.clone().requires_grad_(True)
+    vo.loss_forward(xr, inp, w['conc_type'], w['ncmp'], w['nppf'])['loss'].backward()
+    assert torch.allclose(x.grad.cpu(), xr.grad, rtol=1e-5, atol=1e-9)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -163,3 +206,25 @@ def test_cuda_sep_loss_edge_cases():
     with torch.no_grad():
         got = fn(dout, {k: t.cuda() for k, t in c.items()})
     assert torch.isnan(got['verb_loss']) and torch.isnan(vo.loss_forward_sep(out, c)['verb_loss'])
+
+
+@pytest.mark.parametrize('name', list(synth.WORKLOADS_SEP))
+def test_oracle_sep_loss_gradient_matches_reference(name):
+    w, inp, out, _, _, _ = _case_sep(name)
+    o = dict(out)
+    o['mdl_outs'] = out['mdl_outs'].clone().requires_grad_(True)
+    vo.loss_forward_sep(o, inp)['loss'].backward()
+    _check_grad(o['mdl_outs'].grad, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', list(synth.WORKLOADS_SEP))
+def test_cuda_sep_loss_gradient_matches_reference(name):
+    w, inp, out, loss, _, _ = _case_sep(name)
+    cfg, comm = synth.default_cfg('sep'), synth.default_comm(w['nppf'])
+    fn = vb.get_mdl_loss_eval(cfg)['loss'](cfg, comm)
+    x = out['mdl_outs'].cuda().requires_grad_(True)
+    res = fn({'mdl_outs': x, 'vidf_outs': out['vidf_outs'].cuda()}, {k: v.cuda() for k, v in inp.items()})
+    assert abs(float(res['loss'].detach()) - loss) <= 2e-6 * abs(loss)
+    res['loss'].backward()
+    _check_grad(x.grad, name)

@@ -50,6 +50,7 @@ _SIGNATURES = {
     'vog_lang_gather': [P, c_int, P, c_int, c_int, c_int, P, c_int, P],
     'vog_mask_rows': [P, P, c_int, c_int, P, P, c_int, P],
     'vog_loss_workspace_bytes': [c_int, c_int, c_int],
+    'vog_loss_bwd': [P, P, P, P, P, c_int, c_int, c_int, P],
     'vog_loss_fwd': [P, P, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                      c_float, P, P, P, P],
     'vog_lstm_set_max_ctas': [c_int],

@@ -108,6 +108,8 @@ int mask_rows(const float* x, const long long* msk, int rows, int D, float* out,
 
 // ---- loss_fwd.cu : grounding loss, forward ----------------------------------------------------
 long long loss_workspace_bytes(int B, int nsrl, int P);
+int loss_bwd(const float* logits, const unsigned char* targets, const void* workspace, const float* grad_out, float* grad,
+             int B, int nsrl, int P, cudaStream_t st);
 int loss_fwd(const float* logits, const float* props, int pdim, const float* gt, const unsigned char* frm_mask,
              const unsigned char* pnt_mask, const long long* srl_boxes, const long long* srl_lens,
              const long long* arg_boxes_mask, const long long* cmp_msk, const long long* target_cmp, int B,

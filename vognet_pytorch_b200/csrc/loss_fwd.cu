@@ -90,7 +90,7 @@ loss_targets_kernel(const float* __restrict__ logits, const float* __restrict__ 
 __global__ void __launch_bounds__(1024)
 loss_reduce_kernel(const float* __restrict__ el, const unsigned char* __restrict__ msk,
                    const long long* __restrict__ arg_boxes_mask, int n_args, long long n, int P, float lambda,
-                   float* __restrict__ loss, int sep)
+                   float* __restrict__ loss, int sep, float* __restrict__ stats)
 {
     __shared__ double s_sum[1024];
     __shared__ double s_all[1024];
@@ -120,10 +120,15 @@ loss_reduce_kernel(const float* __restrict__ el, const unsigned char* __restrict
         // masked sum over all elements
         const double mean = s_any ? s_sum[0] / (double)s_cnt[0] : (sep ? s_sum[0] : s_all[0]) / (double)n;
         loss[0] = (float)(mean * (double)P) * lambda;
+        // for the backward: d loss / d el[i] = coef * (masked ? msk[i] : 1)
+        stats[0] = (float)((double)P / (s_any ? (double)s_cnt[0] : (double)n)) * lambda;
+        stats[1] = (s_any || sep) ? 1.f : 0.f;
     }
 }
 
-long long loss_workspace_bytes(int B, int nsrl, int P) { return (long long)B * nsrl * P * 5 + 16; }
+// workspace: el [n] f32 | msk [n] u8 | (16-byte aligned) stats {coef, masked} f32
+static long long loss_stats_offset(long long n) { return (n * 5 + 15) / 16 * 16; }
+long long loss_workspace_bytes(int B, int nsrl, int P) { return loss_stats_offset((long long)B * nsrl * P) + 16; }
 
 int loss_fwd(const float* logits, const float* props, int pdim, const float* gt, const unsigned char* frm_mask,
              const unsigned char* pnt_mask, const long long* srl_boxes, const long long* srl_lens,
@@ -143,8 +148,39 @@ int loss_fwd(const float* logits, const float* props, int pdim, const float* gt,
                                                                     srl_lens, arg_boxes_mask, cmp_msk, target_cmp, B, nsrl,
                                                                     nb, P, K, ncmp, nppf, spat, el, msk, targets);
     if (check_launch("loss_targets")) return -1;
-    loss_reduce_kernel<<<1, 1024, 0, st>>>(el, msk, arg_boxes_mask, B * nsrl, n, P, lambda, loss, spat == 2);
+    float* stats = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + loss_stats_offset(n));
+    loss_reduce_kernel<<<1, 1024, 0, st>>>(el, msk, arg_boxes_mask, B * nsrl, n, P, lambda, loss, spat == 2, stats);
     return check_launch("loss_reduce");
+}
+
+// Backward of the grounding loss with respect to the logits (first link of SURVEY.md section 8f row 2): the loss is
+// coef * sum_i w_i * BCE(x_i, t_i) with w_i the selection mask (or 1 for the plain mean), so
+//     d loss / d x_i = grad_out * coef * w_i * (sigmoid(x_i) - t_i)
+// - what autograd derives for binary_cross_entropy_with_logits + masked_select + mean in the reference
+// (code/mdl_conc_single.py:277-311).  Reads the mask and the reduction statistics the forward left in its workspace.
+__global__ void __launch_bounds__(256)
+loss_bwd_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ tgt, const unsigned char* __restrict__ msk,
+                const float* __restrict__ stats, const float* __restrict__ grad_out, float* __restrict__ grad, long long n)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float coef = stats[0] * grad_out[0];
+    const float w = (stats[1] != 0.f) ? (float)msk[i] : 1.f;
+    const float x = logits[i];
+    const float sg = 1.f / (1.f + expf(-x));
+    grad[i] = coef * w * (sg - (float)tgt[i]);
+}
+
+int loss_bwd(const float* logits, const unsigned char* targets, const void* workspace, const float* grad_out, float* grad,
+             int B, int nsrl, int P, cudaStream_t st)
+{
+    const long long n = (long long)B * nsrl * P;
+    if (n == 0) return 0;
+    const unsigned char* ws = reinterpret_cast<const unsigned char*>(workspace);
+    loss_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logits, targets, ws + n * 4,
+                                                                reinterpret_cast<const float*>(ws + loss_stats_offset(n)),
+                                                                grad_out, grad, n);
+    return check_launch("loss_bwd");
 }
 
 // Verb loss of LossB_SEP (code/mdl_conc_sep.py:418-434): BCE-with-logits of the video-level logits against verb_cmp,

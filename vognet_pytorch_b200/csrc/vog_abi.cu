@@ -356,6 +356,13 @@ int vog_mask_rows(const float* x, const int64_t* msk, int rows, int D, float* ou
     return mask_rows(x, (const long long*)msk, rows, D, out, out_lp, lp_kind, (cudaStream_t)stream);
 }
 
+int vog_loss_bwd(const float* logits, const uint8_t* targets, const void* workspace, const float* grad_out, float* grad_logits,
+                 int B, int nsrl, int P, void* stream)
+{
+    VOG_REQUIRE(logits && targets && workspace && grad_out && grad_logits, "vog_loss_bwd: null operand");
+    return loss_bwd(logits, targets, workspace, grad_out, grad_logits, B, nsrl, P, (cudaStream_t)stream);
+}
+
 int64_t vog_loss_workspace_bytes(int B, int nsrl, int P)
 {
     if (B <= 0 || nsrl <= 0 || P <= 0) return 0;

@@ -3,14 +3,35 @@ constructor ``(cfg, comm)`` and ``forward(out, inp) -> {'loss', 'mdl_out_loss'}`
 180-433), the arithmetic running in ``vog_loss_fwd``: IoU targets against the gt boxes of every SRL argument
 (utils/box_utils.py:61-118), BCE with logits, masked mean * number of proposals * ``cfg.loss.loss_lambda``.
 
-Forward only: the returned scalars carry no autograd graph (the backward of the path is a later row), which is
-what validation (`code/eval_vsrl_corr.py:118-123`, `utils/trn_utils.py:443-483`) needs; training through it is
-rejected loudly instead of silently producing zero gradients.
+The loss is differentiable with respect to the logits: when ``out['mdl_outs']`` requires grad the value comes from an
+autograd Function whose backward is ``vog_loss_bwd`` (d loss / d logits, the first link of the backward chain of
+SURVEY.md section 8f row 2; the model's own backward is not built, so in practice this serves callers that hold
+logits as a leaf).  Under ``torch.no_grad()`` - validation, `code/eval_vsrl_corr.py:118-123`,
+`utils/trn_utils.py:443-483` - nothing is saved.
 """
 import torch
 from torch import nn
 
 from . import ops
+
+
+class _GroundingLoss(torch.autograd.Function):
+    """loss = vog_loss_fwd(logits, ...); backward = vog_loss_bwd on the targets / mask / statistics the forward left."""
+
+    @staticmethod
+    def forward(ctx, logits, args, kw):
+        loss, tg, ws = ops.loss_fwd(logits, *args, want_targets=True, keep_ws=True, **kw)
+        ctx.save_for_backward(logits, tg, ws)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, tg, ws = ctx.saved_tensors
+        return ops.loss_bwd(logits, tg, ws, grad_out.float()), None, None
+
+
+def _differentiable(mdl_outs):
+    return torch.is_grad_enabled() and mdl_outs is not None and mdl_outs.requires_grad
 
 
 class _LossB(nn.Module):
@@ -40,18 +61,16 @@ class _LossB(nn.Module):
         if mdl_outs is None:
             mdl_outs = props.new_zeros(B, 1, nsrl, P)
         ncmp = inp['new_srl_idxs'].shape[1]
-        res = ops.loss_fwd(mdl_outs.detach().reshape(B, nsrl, P).float(), props, inp['pad_gt_bboxs'],
-                           inp['pad_frm_mask'], inp['pad_pnt_mask'], inp['srl_boxes'], inp['srl_boxes_lens'],
-                           inp['srl_arg_boxes_mask'].reshape(B, nsrl), inp['num_cmp_msk'], inp['target_cmp'].reshape(B),
-                           ncmp, self.num_prop_per_frm, self.SPAT, self.loss_lambda, want_targets=want_targets)
+        args = (props, inp['pad_gt_bboxs'], inp['pad_frm_mask'], inp['pad_pnt_mask'], inp['srl_boxes'],
+                inp['srl_boxes_lens'], inp['srl_arg_boxes_mask'].reshape(B, nsrl), inp['num_cmp_msk'],
+                inp['target_cmp'].reshape(B), ncmp, self.num_prop_per_frm, self.SPAT)
+        if _differentiable(mdl_outs) and not want_targets:
+            return _GroundingLoss.apply(mdl_outs.reshape(B, nsrl, P).float(), args, dict(loss_lambda=self.loss_lambda)), None
+        res = ops.loss_fwd(mdl_outs.detach().reshape(B, nsrl, P).float(), *args, self.loss_lambda, want_targets=want_targets)
         return res if want_targets else (res, None)
 
     def forward(self, out, inp):
-        mdl_outs = out['mdl_outs']
-        if torch.is_grad_enabled() and mdl_outs.requires_grad:
-            raise NotImplementedError('vognet_pytorch_b200: forward-only loss (no backward yet, SURVEY.md section 8f); '
-                                      'call it under torch.no_grad()')
-        loss, _ = self._run(inp, mdl_outs)
+        loss, _ = self._run(inp, out['mdl_outs'])
         loss = loss.reshape(())
         return {'loss': loss, 'mdl_out_loss': loss.clone()}
 
@@ -98,11 +117,13 @@ class LossB_SEP(nn.Module):
         # pair (b,c): target video index 0 iff c is the query's target, else 1 (never matches -> all-zero overlaps)
         tc = (torch.arange(ncmp, device=props.device).view(1, ncmp) != inp['target_cmp'].view(B, 1)).long().reshape(Bq)
         # the argument mask only decides masked-vs-plain mean (srl_arg_boxes_mask.max() > 0, :358-363)
-        res = ops.loss_fwd(mdl_outs.detach().reshape(Bq, nsrl, P1).float(), props.reshape(Bq, P1, -1),
-                           inp['pad_gt_bboxs'].reshape(Bq, *inp['pad_gt_bboxs'].shape[2:]),
-                           inp['pad_frm_mask'].reshape(Bq, P1, -1), inp['pad_pnt_mask'].reshape(Bq, P1),
-                           sb.reshape(Bq, nsrl, -1), sl.reshape(Bq, nsrl, -1), am.reshape(Bq, nsrl),
-                           inp['num_cmp_msk'].reshape(Bq, 1), tc, 1, self.num_prop_per_frm, 2, self.loss_lambda,
+        args = (props.reshape(Bq, P1, -1), inp['pad_gt_bboxs'].reshape(Bq, *inp['pad_gt_bboxs'].shape[2:]),
+                inp['pad_frm_mask'].reshape(Bq, P1, -1), inp['pad_pnt_mask'].reshape(Bq, P1),
+                sb.reshape(Bq, nsrl, -1), sl.reshape(Bq, nsrl, -1), am.reshape(Bq, nsrl),
+                inp['num_cmp_msk'].reshape(Bq, 1), tc, 1, self.num_prop_per_frm, 2)
+        if _differentiable(mdl_outs) and not want_targets:
+            return _GroundingLoss.apply(mdl_outs.reshape(Bq, nsrl, P1).float(), args, dict(loss_lambda=self.loss_lambda)), None
+        res = ops.loss_fwd(mdl_outs.detach().reshape(Bq, nsrl, P1).float(), *args, self.loss_lambda,
                            want_targets=want_targets)
         if want_targets:
             return res[0], res[1].view(B, ncmp, nsrl, P1)
@@ -114,13 +135,9 @@ class LossB_SEP(nn.Module):
         return {'targets_one': tg}
 
     def forward(self, out, inp):
-        mdl_outs = out['mdl_outs']
-        if torch.is_grad_enabled() and mdl_outs.requires_grad:
-            raise NotImplementedError('vognet_pytorch_b200: forward-only loss (no backward yet, SURVEY.md section 8f); '
-                                      'call it under torch.no_grad()')
-        loss, _ = self._run(inp, mdl_outs)
+        loss, _ = self._run(inp, out['mdl_outs'])
         loss = loss.reshape(())
-        vidf = out['vidf_outs'].detach().float()
+        vidf = out['vidf_outs'].detach().float()         # verb_loss is reported only: 'loss' excludes it (:436-437)
         n = vidf.numel()
         verb = ops.verb_loss_fwd(vidf.reshape(n), inp['verb_cmp'].reshape(n),
                                  inp['verb_cross_cmp_msk'].reshape(n, -1), self.loss_lambda).reshape(())

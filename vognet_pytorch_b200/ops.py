@@ -515,7 +515,7 @@ def lin2_tail(h, w2, b2, srl_msk, cmp_msk, B, nfrm, nsrl, nppf2, ncmp, nppf, nfr
 
 
 def loss_fwd(logits, props, gt, frm_mask, pnt_mask, srl_boxes, srl_lens, arg_boxes_mask, cmp_msk, target_cmp,
-             ncmp, nppf, spat, loss_lambda=1.0, want_targets=False):
+             ncmp, nppf, spat, loss_lambda=1.0, want_targets=False, keep_ws=False):
     """Grounding loss forward (see vog_loss_fwd): logits [B,nsrl,P] -> loss [1] f32 (and bool targets [B,nsrl,P])."""
     _req(logits, torch.float32, 'logits', 3), _req(props, torch.float32, 'props', 3), _req(gt, torch.float32, 'gt', 3)
     _req(frm_mask, torch.uint8, 'frm_mask', 3), _req(pnt_mask, torch.uint8, 'pnt_mask', 2)
@@ -537,4 +537,16 @@ def loss_fwd(logits, props, gt, frm_mask, pnt_mask, srl_boxes, srl_lens, arg_box
                               _ptr(arg_boxes_mask.contiguous()), _ptr(cmp_msk.contiguous()),
                               _ptr(target_cmp.contiguous()), B, nsrl, nb, P, K, ncmp, nppf, int(spat),
                               float(loss_lambda), _ptr(tg), _ptr(ws), _ptr(loss), _stream()), 'vog_loss_fwd')
+    if keep_ws:                      # for loss_bwd: the raw u8 targets and the workspace with mask + statistics
+        return loss, tg, ws
     return (loss, tg.bool()) if want_targets else loss
+
+
+def loss_bwd(logits, targets_u8, ws, grad_out):
+    """d loss / d logits from the state a ``loss_fwd(..., want_targets=True, keep_ws=True)`` call left (see vog_loss_bwd)."""
+    _req(logits, torch.float32, 'logits', 3), _req(targets_u8, torch.uint8, 'targets', 3), _req(grad_out, torch.float32, 'grad_out')
+    B, nsrl, P = logits.shape
+    grad = torch.empty_like(logits, memory_format=torch.contiguous_format)
+    _lib.check(_lib.lib().vog_loss_bwd(_ptr(logits.contiguous()), _ptr(targets_u8), _ptr(ws), _ptr(grad_out.reshape(1).contiguous()),
+                                       _ptr(grad), B, nsrl, P, _stream()), 'vog_loss_bwd')
+    return grad
