@@ -252,6 +252,14 @@ int vog_loss_fwd(const float* logits, const float* props, int pdim, const float*
 int vog_loss_bwd(const float* logits, const uint8_t* targets, const void* workspace, const float* grad_out, float* grad_logits,
                  int B, int nsrl, int P, void* stream);
 
+/* Fused Adam step on flat fp32 buffers of n elements (parameters, gradients, first / second moments), one launch:
+ * torch.optim.Adam semantics (no weight decay, no amsgrad) with `step` the 1-based step count and the bias corrections
+ * evaluated in double on the host; the gradient is multiplied by grad_scale first (1/world after a summed all-reduce).
+ * replaces torch.optim.Adam(betas=(0.9, 0.99)).step() over ~110 tensors: code/main_dist.py:55,
+ * utils/trn_utils.py:505,799-803. */
+int vog_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, double grad_scale, void* stream);
+
 /* Verb loss of LossB_SEP (code/mdl_conc_sep.py:418-434): vidf [n] video-level logits (n = B*ncmp), verb_cmp [n] int64
  * 0/1 targets, verb_cross_cmp_msk [n,m] int64; loss[0] = mean over rows with any mask entry set of
  * BCE-with-logits(vidf, verb_cmp) * loss_lambda (NaN when no row is selected, like the reference's empty mean). */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libvog_b200.so')
 SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'lstm_rec.cu', 'fused_glue.cu', 'loss_fwd.cu',
-           'relayout.cu']
+           'relayout.cu', 'optim.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -38,6 +38,8 @@ _SIGNATURES = {
     'vog_select_fwd': [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     'vog_select_sep_fwd': [P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     'vog_sep_fin_scores': [P, P, P, P, P, P, P, c_int, c_int, c_int, P],
+    'vog_adam_step': [P, P, P, P, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_i64,
+                      ctypes.c_double, P],
     'vog_verb_loss_fwd': [P, P, P, c_int, c_int, c_float, P, P],
     'vog_concat_videos': [P, c_int, P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     'vog_cast_lp': [P, c_i64, P, c_i64, c_i64, c_int, c_int, P],

@@ -27,6 +27,8 @@ int select_fwd(const float* scores, const float* props, int pdim, float* boxes, 
 int concat_videos(const float* feat, int D, const float* seg, int Ds, const float* props, int pdim, float* feat_out,
                   float* seg_out, float* props_out, int B, int ncmp, int nfrm, int nppf, int spat, float shift,
                   cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2, double eps,
+              long long step, double grad_scale, cudaStream_t st);
 int verb_loss_fwd(const float* vidf, const long long* verb_cmp, const long long* vcc, int n, int m, float lambda,
                   float* loss, cudaStream_t st);
 int sep_fin_scores(const float* logits, const float* vidf, const long long* srl_msk, const long long* verb_ind,

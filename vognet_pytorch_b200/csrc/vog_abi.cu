@@ -135,6 +135,13 @@ int vog_concat_videos(const float* feat, int D, const float* seg, int Ds, const 
                          (cudaStream_t)stream);
 }
 
+int vog_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, int64_t step, double grad_scale, void* stream)
+{
+    VOG_REQUIRE((param && grad && exp_avg && exp_avg_sq) || n == 0, "vog_adam_step: null operand");
+    return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+}
+
 static int require_sm100(const char* who)
 {
     VOG_REQUIRE(vog_device_is_sm100(), "%s: needs an sm_100 (B200) device - tcgen05/TMEM kernels have no other path", who);

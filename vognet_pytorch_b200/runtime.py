@@ -59,6 +59,15 @@ def concat_batch(sep_batch, conc_type, nfrm, nppf, sentence_slot=0):
     return out
 
 
+def allreduce_flat_sum_(flat, group=None):
+    """In-place SUM of one flat gradient buffer over the ranks - a single collective for the whole model - and the
+    factor that turns it into the mean DistributedDataParallel produces (code/main_dist.py:76-85).  -> 1/world."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / dist.get_world_size(group)
+
+
 def max_over_ranks(seconds, device):
     """Device-side max of a per-rank duration (the multi-GPU timing rule of bench.py)."""
     t = torch.tensor([seconds], device=device, dtype=torch.float64)
