@@ -190,7 +190,13 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': f'{METRIC} ({args.workload})', 'value': v, 'unit': 'queries/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic', 'config': {'workload': args.workload, 'per_step_queries': B},
+            'data': 'synthetic',
+            # same workload description as the b200 arm's line; `sample_queries_per_step` is the bounded sample
+            'config': {'workload': args.workload, 'conc_type': w['conc_type'], 'per_gpu_batch': w['B'],
+                       'global_batch': w['B'], 'ncmp': w['ncmp'], 'nfrm': 10, 'nppf': w['nppf'],
+                       'obj_attn': list(workload_shapes(w)['obj']), 'mul_attn': list(workload_shapes(w)['mul']),
+                       'compute': 'fp32 (torch CPU ops of the restated reference)',
+                       'parallelism': 'host cores of rank 0', 'sample_queries_per_step': B},
             'cpu_baseline': {'value': v, 'unit': 'queries/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
