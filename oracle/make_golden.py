@@ -123,6 +123,34 @@ def _reference_logit_grad(loss_fn, out, inp):
             'grad_abs_sum': np.array(g.double().abs().sum().item())}
 
 
+def param_grad_case(name='cpu_ref'):
+    """d loss / d parameter for EVERY parameter of the unmodified reference (eval mode: dropout off, so the result is
+    deterministic), through its own forward + LossB_SPAT and torch autograd -> tests/golden/grad_{name}.npz: per
+    parameter the float64 L2 norm, sum and the first 8 elements.  Pins the oracle for the backward row."""
+    w, batch = synth.workload(name)
+    sd = synth.make_state_dict()
+    mdl = rh.build_reference_model(w['conc_type'], w['nppf'], sd)
+    inp = dict(batch)
+    inp.update(synth.make_loss_inputs(batch, **w))
+    loss_fn = rh.build_reference_loss(w['conc_type'], w['nppf'])
+    out = mdl(synth.clone_batch(inp))
+    loss = loss_fn(out, {k: v.clone() for k, v in inp.items()})['loss']
+    loss.backward()
+    save = {'loss': loss.detach().numpy()}
+    unused = []
+    for k, p in mdl.named_parameters():
+        if p.grad is None:
+            unused.append(k)
+            continue
+        g = p.grad.double().reshape(-1)
+        save['norm/' + k] = np.array(g.norm().item())
+        save['sum/' + k] = np.array(g.sum().item())
+        save['head/' + k] = g[:8].numpy()
+    save['unused'] = np.array(unused)
+    np.savez(os.path.join(GOLD, f'grad_{name}.npz'), **save)
+    print(f'grad_{name}: loss {float(loss):.6f}, {len(save) // 3} parameters with gradients, unused: {unused}')
+
+
 def loss_sep_case(name):
     """LossB_SEP of the unmodified reference on the golden SEP outputs -> tests/golden/loss_{name}.npz."""
     w, batch = synth.workload(name)
@@ -208,3 +236,5 @@ if __name__ == '__main__':
     for nm in synth.WORKLOADS_SEP:
         if not want or ('relayout_' + nm) in want:
             relayout_case(nm)
+    if not want or 'grad_cpu_ref' in want:
+        param_grad_case('cpu_ref')

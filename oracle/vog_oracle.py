@@ -117,14 +117,20 @@ def compute_pe(props5, nsrl, nfrm, nppf, W, b, vid_w=720.0, vid_h=405.0):
 # ---------------------------------------------------------------------------------------------
 # language side: code/mdl_vog.py:67-140,250-283 ; utils/mdl_srl_utils.py:114-169
 # ---------------------------------------------------------------------------------------------
+_LSTM_SKELETON = {}
+
+
 def _lstm_from_state_dict(sd):
-    lstm = torch.nn.LSTM(input_size=512, hidden_size=1024, num_layers=2, dropout=0.0,
-                         bidirectional=True)
-    own = lstm.state_dict()
-    for k in own:
-        own[k] = sd['lstm_encoder.lstm.' + k]
-    lstm.load_state_dict(own)
-    return lstm.eval()
+    """nn.LSTM evaluated functionally on the state_dict's own tensors (torch.func.functional_call), so that autograd
+    reaches them - the restated path is differentiable end to end for the backward parity checks."""
+    w = sd['lstm_encoder.lstm.weight_ih_l0']
+    key = (w.shape[1], w.shape[0] // 4)
+    if key not in _LSTM_SKELETON:
+        _LSTM_SKELETON[key] = torch.nn.LSTM(input_size=key[0], hidden_size=key[1], num_layers=2, dropout=0.0,
+                                            bidirectional=True).eval()
+    lstm = _LSTM_SKELETON[key]
+    params = {k: sd['lstm_encoder.lstm.' + k] for k in lstm.state_dict()}
+    return lambda packed: torch.func.functional_call(lstm, params, (packed,))
 
 
 def language_encode(sd, inp, vocab_size):
