@@ -151,6 +151,21 @@ def param_grad_case(name='cpu_ref'):
     print(f'grad_{name}: loss {float(loss):.6f}, {len(save) // 3} parameters with gradients, unused: {unused}')
 
 
+def ablation_case(name, mdl_name):
+    """ImgGrnd_* / VidGrnd_* (mdl.name 'igrnd' / 'vgrnd', code/mdl_vog.py:400-410,526-535) of the unmodified reference
+    on the workload `name` -> tests/golden/{mdl_name}_{name}.npz."""
+    w, batch = synth.workload(name)
+    mdl = rh.build_reference_model(w['conc_type'], w['nppf'], synth.make_state_dict(), mdl_name=mdl_name)
+    with torch.no_grad():
+        out = mdl(synth.clone_batch(batch))
+    np.savez(os.path.join(GOLD, f'{mdl_name}_{name}.npz'), mdl_outs=out['mdl_outs'].numpy(),
+             mdl_outs_eval=out['mdl_outs_eval'].numpy())
+    print(f'{mdl_name}_{name}: logits {tuple(out["mdl_outs"].shape)} std {out["mdl_outs"].std():.3f}')
+
+
+ABLATIONS = [('spat_gt5', 'igrnd'), ('spat_gt5', 'vgrnd'), ('temp_gt5', 'igrnd'), ('temp_gt5', 'vgrnd')]
+
+
 def loss_sep_case(name):
     """LossB_SEP of the unmodified reference on the golden SEP outputs -> tests/golden/loss_{name}.npz."""
     w, batch = synth.workload(name)
@@ -236,5 +251,8 @@ if __name__ == '__main__':
     for nm in synth.WORKLOADS_SEP:
         if not want or ('relayout_' + nm) in want:
             relayout_case(nm)
+    for nm, mn in ABLATIONS:
+        if not want or f'{mn}_{nm}' in want:
+            ablation_case(nm, mn)
     if not want or 'grad_cpu_ref' in want:
         param_grad_case('cpu_ref')

@@ -92,16 +92,21 @@ def reference_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
     return cfg
 
 
-def build_reference_model(conc_type, nppf, state_dict, vocab_size=1000, **cfg_kw):
-    """Unmodified reference VOG_SPAT / VOG_TEMP in eval mode with ``state_dict`` loaded strictly."""
+def build_reference_model(conc_type, nppf, state_dict, vocab_size=1000, mdl_name='vog', **cfg_kw):
+    """Unmodified reference VOG_SPAT / VOG_TEMP / VOG_SEP (or the ImgGrnd_* / VidGrnd_* ablations with
+    ``mdl_name='igrnd' | 'vgrnd'``) in eval mode with ``state_dict`` loaded strictly (restricted to the parameters
+    the variant owns)."""
     _install_stubs()
     import mdl_vog  # noqa: from /root/reference/code
     cfg = reference_cfg(conc_type, **cfg_kw)
     comm = Munch(vocab_size=vocab_size, detect_size=10, itod={}, wtoi={'UNK': 0},
                  num_prop_per_frm=nppf)
-    cls = {'spat': mdl_vog.VOG_SPAT, 'temp': mdl_vog.VOG_TEMP, 'sep': mdl_vog.VOG_SEP}[conc_type]
+    prefix = {'vog': 'VOG', 'vgrnd': 'VidGrnd', 'igrnd': 'ImgGrnd'}[mdl_name]
+    cls = getattr(mdl_vog, f'{prefix}_{conc_type.upper()}')
+    cfg.mdl.name = mdl_name
     mdl = cls(cfg, comm)
-    mdl.load_state_dict(state_dict, strict=True)
+    own = set(mdl.state_dict())
+    mdl.load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=True)
     return mdl.eval()
 
 

@@ -165,8 +165,10 @@ def language_encode(sd, inp, vocab_size):
 # whole forward: code/mdl_conc_single.py:68-127 (TEMP) / :130-177 (SPAT)
 # ---------------------------------------------------------------------------------------------
 def vog_forward(sd, inp, conc_type, nppf, n_heads=3, vocab_size=1000, nfrm0=10,
-                use_rel=True, keep=False):
-    """Restated ConcTEMP.forward / ConcSPAT.forward for mdl.name='vog'.
+                use_rel=True, keep=False, mdl_name='vog'):
+    """Restated ConcTEMP.forward / ConcSPAT.forward for mdl.name='vog'; ``mdl_name='vgrnd'`` drops the multimodal
+    transformer (VidGrnd: conc_encode_simple, code/mdl_vog.py:346-363), ``'igrnd'`` also the object transformer
+    (ImgGrnd.simple_obj_interact :285-289).
 
     returns {'mdl_outs': logits [B,1,nsrl,P], 'mdl_outs_eval': masked sigmoid} (+ intermediates
     when keep=True)."""
@@ -189,12 +191,14 @@ def vog_forward(sd, inp, conc_type, nppf, n_heads=3, vocab_size=1000, nfrm0=10,
     # ---- object transformer over ALL proposals of the query (mdl_vog.py:492-523, one_frm False)
     props5 = inp['pad_proposals'][..., :5].clone()
     x_obj = ps.reshape(B, P, -1)
-    if use_rel:
+    if mdl_name == 'igrnd':
+        bias_obj = None
+    elif use_rel:
         # compute_pe(props, nsrl=1, nfrm=1, nppf=P): frame id divided by 1 (:507-510)
         bias_obj = compute_pe(props5, 1, 1, P, sd['pe_obj_sub_enc.0.weight'], sd['pe_obj_sub_enc.0.bias'])
     else:
         bias_obj = None
-    y_obj = transformer(x_obj, sd, 'obj_txf', n_heads, bias_obj)
+    y_obj = x_obj if mdl_name == 'igrnd' else transformer(x_obj, sd, 'obj_txf', n_heads, bias_obj)
     del bias_obj
     vis = y_obj.view(B, 1, P, -1)
 
@@ -210,12 +214,15 @@ def vog_forward(sd, inp, conc_type, nppf, n_heads=3, vocab_size=1000, nfrm0=10,
     D = conc.shape[-1]
     x_mul = conc.view(B, nsrl, nfrm, nppf2, D).transpose(1, 2).contiguous().view(
         B * nfrm, nsrl * nppf2, D)                                         # mdl_vog.py:693-699
-    if use_rel:
+    if mdl_name != 'vog':
+        bias_mul = None
+    elif use_rel:
         bias_mul = compute_pe(inp['pad_proposals'][..., :5].clone(), nsrl, nfrm, nppf2,
                               sd['pe_mul_sub_enc.0.weight'], sd['pe_mul_sub_enc.0.bias'])  # :710-713
     else:
         bias_mul = None
-    y_mul = transformer(x_mul, sd, 'mult_txf', n_heads, bias_mul)
+    # igrnd / vgrnd: lin2 directly on the concatenated tokens (the regroup is a pure permutation around a row-wise map)
+    y_mul = x_mul if mdl_name != 'vog' else transformer(x_mul, sd, 'mult_txf', n_heads, bias_mul)
     del bias_mul
     y = y_mul.view(B, nfrm, nsrl, nppf2, D).transpose(1, 2).contiguous().view(B, 1, nsrl, P, D)  # :724-737
 

@@ -153,3 +153,25 @@ def test_batch_larger_than_one_lstm_group():
         ref = vo.vog_forward(sd, batch, w['conc_type'], w['nppf'])
     assert (out['mdl_outs_eval'].cpu() - ref['mdl_outs_eval']).abs().max() < 1e-3
     assert torch.equal(out['mdl_outs_eval'], out2['mdl_outs_eval'])
+
+
+@pytest.mark.parametrize('name', ['spat_gt5', 'temp_gt5'])
+@pytest.mark.parametrize('mdl_name', ['igrnd', 'vgrnd'])
+@pytest.mark.parametrize('mode', ['fp32x', 'tf32', 'bf16'])
+def test_ablation_variants_golden(golden, name, mdl_name, mode):
+    """cfg.mdl.name = 'igrnd' / 'vgrnd' (ImgGrnd_*: no transformer, VidGrnd_*: object transformer only) against the
+    unmodified reference's ImgGrnd_* / VidGrnd_* outputs; a full VOG checkpoint loads with strict=False."""
+    g = golden(f'{mdl_name}_{name}')
+    w, batch = synth.workload(name)
+    cfg = synth.default_cfg(w['conc_type'])
+    cfg.mdl.name = mdl_name
+    comm = synth.default_comm(w['nppf'])
+    mdl = vb.get_mdl_loss_eval(cfg)['mdl'](cfg, comm)
+    own = set(mdl.state_dict())
+    mdl.load_state_dict({k: v for k, v in synth.make_state_dict().items() if k in own}, strict=True)
+    mdl = mdl.to(DEV).eval().set_compute(mode)
+    out = mdl(synth.clone_batch(batch, DEV))
+    torch.cuda.synchronize()
+    err = np.abs(out['mdl_outs_eval'].cpu().numpy() - g['mdl_outs_eval']).max()
+    print(f'\n[{mdl_name}/{name}/{mode}] max|dscore| {err:.2e}')
+    assert err < {'fp32x': 1e-4, 'tf32': 1e-3, 'bf16': 1e-2}[mode]
