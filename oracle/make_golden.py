@@ -163,6 +163,27 @@ def ablation_case(name, mdl_name):
     print(f'{mdl_name}_{name}: logits {tuple(out["mdl_outs"].shape)} std {out["mdl_outs"].std():.3f}')
 
 
+CFG_VARIANTS = {          # model-level configuration surface beyond the BASELINE settings (B=2 of spat/gt5, temp/gt5)
+    'onefrm_spat': dict(conc='spat', cfg=dict(obj_one_frm=True), sd={}),
+    'onefrm_temp': dict(conc='temp', cfg=dict(obj_one_frm=True), sd={}),
+    'norel_spat': dict(conc='spat', cfg=dict(use_rel=False), sd={}),
+    'l3h6_spat': dict(conc='spat', cfg=dict(n_layers=3, n_heads=6), sd=dict(n_layers_obj=3, n_layers_mul=3, n_heads=6)),
+}
+
+
+def cfg_variant_case(tag):
+    """cfg.mdl.obj_tx.one_frm / use_rel=False / 3 layers x 6 heads (EXPTS.md:186-189) through the unmodified reference
+    -> tests/golden/cfgvar_{tag}.npz."""
+    v = CFG_VARIANTS[tag]
+    batch = synth.make_batch(v['conc'], B=2, ncmp=4, nppf=5, seed=9)
+    sd = synth.make_state_dict(seed=4, **v['sd'])
+    mdl = rh.build_reference_model(v['conc'], 5, sd, **v['cfg'])
+    with torch.no_grad():
+        out = mdl(synth.clone_batch(batch))
+    np.savez(os.path.join(GOLD, f'cfgvar_{tag}.npz'), mdl_outs=out['mdl_outs'].numpy(), mdl_outs_eval=out['mdl_outs_eval'].numpy())
+    print(f'cfgvar_{tag}: logits std {out["mdl_outs"].std():.3f}')
+
+
 ABLATIONS = [('spat_gt5', 'igrnd'), ('spat_gt5', 'vgrnd'), ('temp_gt5', 'igrnd'), ('temp_gt5', 'vgrnd')]
 
 
@@ -254,5 +275,8 @@ if __name__ == '__main__':
     for nm, mn in ABLATIONS:
         if not want or f'{mn}_{nm}' in want:
             ablation_case(nm, mn)
+    for tag in CFG_VARIANTS:
+        if not want or f'cfgvar_{tag}' in want:
+            cfg_variant_case(tag)
     if not want or 'grad_cpu_ref' in want:
         param_grad_case('cpu_ref')

@@ -81,7 +81,7 @@ def to_munch(d):
     return d
 
 
-def reference_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
+def reference_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True, obj_one_frm=False):
     import yaml
     cfg = to_munch(yaml.safe_load(open(os.path.join(REF_ROOT, 'configs', 'anet_srl_cfg.yml'))))
     cfg.ds.conc_type = conc_type
@@ -89,6 +89,7 @@ def reference_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
         tx.use_rel = use_rel
         tx.n_layers = n_layers
         tx.n_heads = n_heads
+    cfg.mdl.obj_tx.one_frm = obj_one_frm
     return cfg
 
 

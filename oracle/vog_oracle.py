@@ -165,7 +165,7 @@ def language_encode(sd, inp, vocab_size):
 # whole forward: code/mdl_conc_single.py:68-127 (TEMP) / :130-177 (SPAT)
 # ---------------------------------------------------------------------------------------------
 def vog_forward(sd, inp, conc_type, nppf, n_heads=3, vocab_size=1000, nfrm0=10,
-                use_rel=True, keep=False, mdl_name='vog'):
+                use_rel=True, keep=False, mdl_name='vog', obj_one_frm=False):
     """Restated ConcTEMP.forward / ConcSPAT.forward for mdl.name='vog'; ``mdl_name='vgrnd'`` drops the multimodal
     transformer (VidGrnd: conc_encode_simple, code/mdl_vog.py:346-363), ``'igrnd'`` also the object transformer
     (ImgGrnd.simple_obj_interact :285-289).
@@ -190,12 +190,17 @@ def vog_forward(sd, inp, conc_type, nppf, n_heads=3, vocab_size=1000, nfrm0=10,
 
     # ---- object transformer over ALL proposals of the query (mdl_vog.py:492-523, one_frm False)
     props5 = inp['pad_proposals'][..., :5].clone()
-    x_obj = ps.reshape(B, P, -1)
+    if obj_one_frm:
+        # obj_tx.one_frm (:496-504): one sequence per frame group, the groups of simple_obj_interact_input
+        # (mdl_conc_single.py:30-37 TEMP, :137-142 SPAT); frame id divided by the number of groups
+        nfo, npo = (nfrm0, ncmp * nppf) if conc_type == 'spat' else (ncmp * nfrm0, nppf)
+    else:
+        nfo, npo = 1, P          # compute_pe(props, nsrl=1, nfrm=1, nppf=P): frame id divided by 1 (:507-510)
+    x_obj = ps.reshape(B * nfo, npo, -1)
     if mdl_name == 'igrnd':
         bias_obj = None
     elif use_rel:
-        # compute_pe(props, nsrl=1, nfrm=1, nppf=P): frame id divided by 1 (:507-510)
-        bias_obj = compute_pe(props5, 1, 1, P, sd['pe_obj_sub_enc.0.weight'], sd['pe_obj_sub_enc.0.bias'])
+        bias_obj = compute_pe(props5, 1, nfo, npo, sd['pe_obj_sub_enc.0.weight'], sd['pe_obj_sub_enc.0.bias'])
     else:
         bias_obj = None
     y_obj = x_obj if mdl_name == 'igrnd' else transformer(x_obj, sd, 'obj_txf', n_heads, bias_obj)

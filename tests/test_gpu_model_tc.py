@@ -175,3 +175,32 @@ def test_ablation_variants_golden(golden, name, mdl_name, mode):
     err = np.abs(out['mdl_outs_eval'].cpu().numpy() - g['mdl_outs_eval']).max()
     print(f'\n[{mdl_name}/{name}/{mode}] max|dscore| {err:.2e}')
     assert err < {'fp32x': 1e-4, 'tf32': 1e-3, 'bf16': 1e-2}[mode]
+
+
+CFG_VARIANTS = {
+    'onefrm_spat': dict(conc='spat', cfg=dict(obj_one_frm=True), sd={}),
+    'onefrm_temp': dict(conc='temp', cfg=dict(obj_one_frm=True), sd={}),
+    'norel_spat': dict(conc='spat', cfg=dict(use_rel=False), sd={}),
+    'l3h6_spat': dict(conc='spat', cfg=dict(n_layers=3, n_heads=6), sd=dict(n_layers_obj=3, n_layers_mul=3, n_heads=6)),
+}
+
+
+@pytest.mark.parametrize('tag', list(CFG_VARIANTS))
+@pytest.mark.parametrize('mode', ['fp32x', 'tf32', 'bf16'])
+def test_config_variants_golden(golden, tag, mode):
+    """Model-level configuration surface against the unmodified reference: cfg.mdl.obj_tx.one_frm (object transformer
+    per frame group), use_rel=False (plain Transformer stacks, no bias), n_layers=3 / n_heads=6 (EXPTS.md:186-189)."""
+    v = CFG_VARIANTS[tag]
+    g = golden(f'cfgvar_{tag}')
+    batch = synth.make_batch(v['conc'], B=2, ncmp=4, nppf=5, seed=9)
+    cfg, comm = synth.default_cfg(v['conc'], **v['cfg']), synth.default_comm(5)
+    mdl = vb.get_mdl_loss_eval(cfg)['mdl'](cfg, comm)
+    mdl.load_state_dict(synth.make_state_dict(seed=4, **v['sd']), strict=True)
+    mdl = mdl.to(DEV).eval().set_compute(mode)
+    out = mdl(synth.clone_batch(batch, DEV))
+    torch.cuda.synchronize()
+    err = np.abs(out['mdl_outs_eval'].cpu().numpy() - g['mdl_outs_eval']).max()
+    print(f'\n[{tag}/{mode}] max|dscore| {err:.2e}')
+    # three stacked low-precision layers accumulate more rounding than one: the 3-layer case gets 2x the tolerance
+    scale = 2.0 if tag.startswith('l3') else 1.0
+    assert err < scale * {'fp32x': 1e-4, 'tf32': 1e-3, 'bf16': 1e-2}[mode]

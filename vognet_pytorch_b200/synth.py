@@ -55,7 +55,7 @@ def to_attr(d):
 
 # The cfg keys the forward path reads (configs/anet_srl_cfg.yml:16-24,57-81,98-104),
 # with use_rel=True as in every published command (README.md:53, EXPTS.md:14-15).
-def default_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
+def default_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True, obj_one_frm=False):
     return to_attr({
         'ds': {'conc_type': conc_type, 'resized_width': 720, 'resized_height': 405,
                'num_sampled_frm': 10, 't_attn_size': 480, 'max_seq_length': 20, 'max_gt_box': 100},
@@ -65,7 +65,7 @@ def default_cfg(conc_type='spat', n_layers=1, n_heads=3, use_rel=True):
             'rnn': {'rnn_size': 1024, 'num_layers': 2, 'drop_prob_lm': 0.5},
             'vsrl': {'prop_encode_size': 256, 'seg_encode_size': 256, 'lang_encode_size': 256},
             'obj_tx': {'use_ddp': False, 'to_use': True, 'n_layers': n_layers, 'n_heads': n_heads,
-                       'attn_drop': 0.2, 'use_rel': use_rel, 'one_frm': False},
+                       'attn_drop': 0.2, 'use_rel': use_rel, 'one_frm': obj_one_frm},
             'mul_tx': {'use_ddp': False, 'to_use': True, 'n_layers': n_layers, 'n_heads': n_heads,
                        'attn_drop': 0.2, 'use_rel': use_rel, 'one_frm': True, 'cross_frm': False},
         },
