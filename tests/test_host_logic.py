@@ -99,3 +99,30 @@ def test_sep_batch_layout():
     assert (batch['verb_ind_in_srl'] < batch['srl_arg_inds_msk'].sum(-1)).all()
     assert batch['pad_proposals'][..., 4].max() == 9 and batch['pad_proposals'][..., 0].max() < 720
     assert batch['num_cmp_msk'][1, -1] == 0 and batch['num_cmp_msk'].sum() == B * ncmp - B // 2
+
+
+def test_sep_flatten_is_the_single_video_batch():
+    """VOG_SEP re-views the [B,ncmp,...] batch as B*ncmp single-video queries (host logic only, no kernels): the result
+    equals the temp batch the SEP fixture was unfolded from, without copying the visual tensors; one sentence slot is
+    expanded over the videos (code/mdl_conc_sep.py:165-173)."""
+    w, batch = synth.workload('sep_gt5')
+    B, ncmp, nppf = w['B'], w['ncmp'], w['nppf']
+    cfg, comm = synth.default_cfg('sep'), synth.default_comm(nppf)
+    mdl = vb.get_mdl_loss_eval(cfg)['mdl'](cfg, comm)
+    flat, (b_, c_) = mdl._sep_flatten(batch)
+    assert (b_, c_) == (B, ncmp)
+    one = synth.make_batch(conc_type='temp', B=B * ncmp, ncmp=1, nppf=nppf, seed=1)
+    for k in ('pad_region_feature', 'seg_feature_for_frms', 'pad_proposals', 'srl_arg_words_ind', 'srl_arg_word_mask',
+              'srl_arg_word_mask_len', 'srl_arg_words_capture', 'srl_arg_inds_msk'):
+        assert torch.equal(flat[k], one[k]), k
+    assert flat['pad_region_feature'].data_ptr() == batch['pad_region_feature'].data_ptr()      # a view, not a copy
+    assert tuple(flat['num_cmp_msk'].shape) == (B * ncmp, 1) and tuple(flat['verb_ind_in_srl'].shape) == (B * ncmp,)
+    single = dict(batch)
+    for k in mdl._SEP_LANG_KEYS:
+        single[k] = batch[k][:, :1].contiguous()
+    flat1, _ = mdl._sep_flatten(single)
+    assert torch.equal(flat1['srl_arg_words_ind'].view(B, ncmp, 5, 20)[:, 3], batch['srl_arg_words_ind'][:, 0])
+    bad = dict(batch)
+    bad['pad_region_feature'] = batch['pad_region_feature'].reshape(B, -1, 2048)
+    with pytest.raises(ValueError):
+        mdl._sep_flatten(bad)
