@@ -1,7 +1,6 @@
 """Language side through the persistent LSTM recurrence kernel + tcgen05 projections
 (language_encode_tc) against torch/cuDNN packed-sequence LSTM (language_encode) and the golden
 language vectors of the reference."""
-import numpy as np
 import pytest
 import torch
 

@@ -6,7 +6,6 @@ reference (same value AND same derivative with respect to all 57 live parameters
 import os
 
 import numpy as np
-import torch
 
 from oracle import vog_oracle as vo
 from vognet_pytorch_b200 import synth

@@ -1,7 +1,6 @@
 """Live check of the oracle against the UNMODIFIED reference (only where /root/reference exists,
 i.e. in the build container; skipped on the GPU box).  Uses inputs and weights that are NOT in the
 golden fixtures (other seeds, 3-layer / 6-head ablation config of EXPTS.md:186-189)."""
-import numpy as np
 import pytest
 import torch
 

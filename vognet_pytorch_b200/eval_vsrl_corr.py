@@ -9,7 +9,6 @@ pandas accuracy computation: :101-150, code/eval_fn_corr.py) is file-I/O glue ou
  and is not rebuilt here; ``Evaluator*`` keep the constructor
 signature ``(cfg, comm, device)`` so ``get_mdl_loss_eval`` stays source-compatible.
 """
-import torch
 from torch import nn
 
 from . import ops

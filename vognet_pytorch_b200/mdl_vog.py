@@ -22,7 +22,6 @@ import os
 
 import torch
 from torch import nn
-from torch.nn import functional as F
 
 from . import ops
 from .transformer_code import COMPUTE_MODES, FactoredTokens, RelBias, RelTransformer, Transformer
