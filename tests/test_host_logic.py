@@ -126,3 +126,25 @@ def test_sep_flatten_is_the_single_video_batch():
     bad['pad_region_feature'] = batch['pad_region_feature'].reshape(B, -1, 2048)
     with pytest.raises(ValueError):
         mdl._sep_flatten(bad)
+
+
+def test_ctypes_signatures_match_the_header():
+    """ABI drift guard: for every declaration in include/vog_b200.h the ctypes binding has the same number of
+    arguments, pointer arguments are bound as void*, and int / int64_t / float / double map to the matching ctypes."""
+    import ctypes
+    hdr = open(os.path.join(ROOT, 'include', 'vog_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', ' ', hdr, flags=re.S)
+    decls = re.findall(r'\b(vog_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', hdr, flags=re.S)
+    assert len(decls) >= 40
+    ctype_of = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float, 'double': ctypes.c_double}
+    for name, args in decls:
+        args = ' '.join(args.split())
+        params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+        bound = _lib._SIGNATURES[name]
+        assert len(params) == len(bound), (name, params, bound)
+        for prm, ct in zip(params, bound):
+            if '*' in prm:
+                assert ct is ctypes.c_void_p, (name, prm, ct)
+            else:
+                base = prm.replace('const ', '').split()[0]
+                assert ct is ctype_of[base], (name, prm, ct)
