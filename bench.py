@@ -157,11 +157,36 @@ def flops_query(w):
     return tot / B
 
 
-def run_reference(args):
-    """--impl reference: the CPU oracle port (oracle/vog_oracle.py - the restated reference
-    algorithm; the Python reference itself cannot travel to the GPU box) on the host cores."""
+def _reference_step_fn(w, sd, device):
+    """One forward + box selection of the CPU/GPU baseline: the UNMODIFIED reference (from /root/reference or the
+    baseline/_ref copy build() installs) when present, else the oracle port.  -> (step(batch), kind)."""
     import torch
+    from oracle import ref_harness as rh
+    if rh.reference_available():
+        mdl = rh.build_reference_model(w['conc_type'], w['nppf'], sd).to(device)
+        ev = rh.build_reference_evaluator(w['conc_type'], w['nppf'], w['ncmp'])
+
+        def step(batch):
+            b = dict(batch)                      # the reference edits this key in place (code/mdl_vog.py:80-82)
+            b['srl_arg_word_mask'] = batch['srl_arg_word_mask'].clone()
+            with torch.no_grad():
+                out = mdl(b)
+                return ev.get_out_results_boxes(out, b)
+        return step, 'reference'
     from oracle import vog_oracle as vo
+    sdd = {k: v.to(device) for k, v in sd.items()}
+
+    def step(batch):
+        with torch.no_grad():
+            out = vo.vog_forward(sdd, batch, w['conc_type'], w['nppf'])
+            return vo.select_boxes(out['mdl_outs_eval'], batch['pad_proposals'], w['conc_type'], w['ncmp'], w['nppf'])
+    return step, 'port'
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (the unmodified
+    reference from baseline/_ref, installed by build(); the oracle port only if that copy is missing)."""
+    import torch
     from vognet_pytorch_b200 import synth
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -171,36 +196,84 @@ def run_reference(args):
     w, batch = synth.workload(args.workload)
     sd = synth.make_state_dict()
     B = w['B']
-    sample = f'whole batch B={B}'
+    sample = f'whole per-GPU batch B={B} on rank 0 only'
     if w['nppf'] >= 100:           # ~2 s per query on 8 cores: bound the sample to one query
         batch = {k: v[:1].clone() for k, v in batch.items()}
-        B, sample = 1, 'first query of the batch (B=1)'
-
-    def step():
-        with torch.no_grad():
-            out = vo.vog_forward(sd, batch, w['conc_type'], w['nppf'])
-            vo.select_boxes(out['mdl_outs_eval'], batch['pad_proposals'], w['conc_type'], w['ncmp'], w['nppf'])
+        B, sample = 1, 'first query of the batch (B=1) on rank 0 only'
+    step, kind = _reference_step_fn(w, sd, 'cpu')
     for _ in range(args.warmup):
-        step()
+        step(batch)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        step(batch)
     dt = (time.perf_counter() - t0) / args.steps
     v = B / dt
     line = {'impl': 'reference', 'metric': f'{METRIC} ({args.workload})', 'value': v, 'unit': 'queries/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            # same workload description as the b200 arm's line; `sample_queries_per_step` is the bounded sample
+            # same workload description as the b200 arm's line; the CPU arm always runs ONE per-GPU batch on ONE
+            # host (rank 0), whatever --gpus says: at N > 1 the b200 arm processes N x as many queries per step
             'config': {'workload': args.workload, 'conc_type': w['conc_type'], 'per_gpu_batch': w['B'],
                        'global_batch': w['B'], 'ncmp': w['ncmp'], 'nfrm': 10, 'nppf': w['nppf'],
                        'obj_attn': list(workload_shapes(w)['obj']), 'mul_attn': list(workload_shapes(w)['mul']),
-                       'compute': 'fp32 (torch CPU ops of the restated reference)',
+                       'compute': 'fp32 (torch CPU ops, eval mode, no_grad)',
                        'parallelism': 'host cores of rank 0', 'sample_queries_per_step': B},
-            'cpu_baseline': {'value': v, 'unit': 'queries/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'reference_n_queries': B * args.steps, 'reference_ranks': 1,
+            'cpu_baseline': {'value': v, 'unit': 'queries/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': v, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
+
+
+def train_step_object(dev, world, rank, flush, barrier, max_ranks, steps):
+    """BASELINE.json configs[4]: spat/p100 TRAINING step, bs=4 per GPU (bs=32 at 8 GPUs): forward + LossB_SPAT +
+    backward + ONE flat NCCL gradient all-reduce + fused Adam (utils/trn_utils.py:497-505, code/main_dist.py:55,75-80)."""
+    from vognet_pytorch_b200 import training
+    return training.bench_train_step('spat_p100', 'bf16', dev, world, rank, flush, barrier, max_ranks, steps)
+
+
+def run_train(args, dev, world, rank, sampler, flush, barrier, max_ranks):
+    from vognet_pytorch_b200 import training
+    compute = args.compute or COMPUTE[args.workload]
+    sampler.mark_begin()
+    obj = training.bench_train_step(args.workload, compute, dev, world, rank, flush, barrier, max_ranks, args.steps,
+                                    warmup=args.warmup)
+    sampler.mark_end()
+    clocks = sampler.stop()
+    if rank == 0:
+        obj['clocks'] = clocks
+        print(json.dumps(obj), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def gpu_eager_object(w, batch, sd, dev, flush, steps):
+    """The in-box GPU comparator: the unmodified reference (or the oracle port when baseline/_ref is missing) on
+    cuda under torch eager - ATen / cuBLAS / cuDNN kernels, fp32 - same batch, inputs resident, L2 flushed
+    between steps, CUDA events."""
+    import torch
+    step, kind = _reference_step_fn(w, sd, dev)
+    b = {k: v.to(dev) for k, v in batch.items()}
+    for _ in range(3):
+        step(b)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(b); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del step
+    torch.cuda.empty_cache()
+    return {'value': w['B'] / (ms * 1e-3), 'unit': 'queries/s', 'ms_per_step': ms, 'steps': steps, 'kind': kind,
+            'dtype': 'f32', 'torch': torch.__version__, 'tf32_matmul': bool(torch.backends.cuda.matmul.allow_tf32),
+            'peak_mem_gib': peak,
+            'note': 'reference forward + evaluator selection under torch eager on the same B200 (library kernels only)'}
 
 
 def main():
@@ -213,7 +286,11 @@ def main():
     ap.add_argument('--compute', default=None, help="override: fp32x | tf32 | bf16")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-seq4000', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the sub-objects (north_star_forward, '
+                    'gpu_eager_baseline, value_fp32x, temp_gt5, train_step)')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA graphs')
+    ap.add_argument('--train', action='store_true', help='time the TRAINING step (forward + loss + backward + '
+                    'flat gradient all-reduce + fused Adam) instead of the forward')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
@@ -237,62 +314,83 @@ def main():
     L = _lib.lib()
     sampler = ClockSampler(local)
     sampler.start()              # side process: up and polling NVML long before the timed region starts
-
-    w, batch = synth.workload(args.workload, seed=1 + rank)       # every rank its own shard of queries
-    compute = args.compute or COMPUTE[args.workload]
-    cfg, comm = synth.default_cfg(w['conc_type']), synth.default_comm(w['nppf'])
-    sel = vb.get_mdl_loss_eval(cfg)
-    mdl = sel['mdl'](cfg, comm)
-    mdl.load_state_dict(synth.make_state_dict(), strict=True)
-    mdl = mdl.to(dev).eval().set_compute(compute)
-    mdl.use_cuda_graph = not args.no_graph and compute != 'fp32x'
-    ev = sel['eval'](cfg, comm, dev)
-    B = w['B']
-
-    host = {k: v.pin_memory() for k, v in batch.items()}
-    resident = {k: v.to(dev) for k, v in batch.items()}
-    if mdl.use_cuda_graph:
-        # "inputs already resident in HBM": the resident batch lives in the captured forward's own input tensors,
-        # so the timed step is the graph replay alone (no staging copies)
-        with torch.no_grad():
-            resident = mdl.graph_input_buffers(resident)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+    sd_cpu = synth.make_state_dict()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def build(workload, compute, graph=True):
+        """model + evaluator + (host, resident) batches of one workload; every rank its own shard of queries"""
+        w_, batch_ = synth.workload(workload, seed=1 + rank)
+        cfg, comm = synth.default_cfg(w_['conc_type']), synth.default_comm(w_['nppf'])
+        sel = vb.get_mdl_loss_eval(cfg)
+        m = sel['mdl'](cfg, comm)
+        m.load_state_dict(sd_cpu, strict=True)
+        m = m.to(dev).eval().set_compute(compute)
+        m.use_cuda_graph = graph and compute != 'fp32x'
+        e = sel['eval'](cfg, comm, dev)
+        res = {k: v.to(dev) for k, v in batch_.items()}
+        if m.use_cuda_graph:
+            # "inputs already resident in HBM": the resident batch lives in the captured forward's own input
+            # tensors, so the timed step is the graph replay alone (no staging copies)
+            with torch.no_grad():
+                res = m.graph_input_buffers(res)
+        return dict(w=w_, batch=batch_, mdl=m, ev=e, resident=res, sel=sel, cfg=cfg, comm=comm)
+
+    def fwd_step(ctx, b):
+        out = ctx['mdl'](b)
+        return out, ctx['ev'].get_out_results_boxes(out, b)
+
+    def time_resident(ctx, steps, warmup):
+        """K steps on the resident batch, L2 flushed between steps, one CUDA-event pair per step; max over ranks."""
+        for _ in range(warmup):
+            fwd_step(ctx, ctx['resident'])
+        barrier()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        n0 = L.vog_launch_count()
+        barrier()
+        for i in range(steps):
+            flush.zero_()
+            e0[i].record()
+            fwd_step(ctx, ctx['resident'])
+            e1[i].record()
+        barrier()
+        launches = (L.vog_launch_count() - n0) // steps          # eager launches of libvog_b200 per step
+        if ctx['mdl'].use_cuda_graph:                             # + the kernels captured in the replayed graph
+            launches += int(getattr(ctx['mdl'], 'graph_launches', 0))
+        per = [a.elapsed_time(b) for a, b in zip(e0, e1)]
+        return max_ranks(sum(per)), per, launches
+
+    if args.train:
+        return run_train(args, dev, world, rank, sampler, flush, barrier, max_ranks)
+
+    compute = args.compute or COMPUTE[args.workload]
+    ctx = build(args.workload, compute, not args.no_graph)
+    w, batch, mdl, ev, resident = ctx['w'], ctx['batch'], ctx['mdl'], ctx['ev'], ctx['resident']
+    B = w['B']
+    host = {k: v.pin_memory() for k, v in batch.items()}
+
     def step(b):
-        out = mdl(b)
-        sel_out = ev.get_out_results_boxes(out, b)
-        return out, sel_out
+        return fwd_step(ctx, b)
 
     # ---- kernel-resident timing: K steps, L2 flushed between steps, CUDA events per step ---------
     for _ in range(args.warmup):
         step(resident)
     barrier()
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    n0 = L.vog_launch_count()
-    barrier()
     sampler.mark_begin()
-    for i in range(args.steps):
-        flush.zero_()
-        ev0[i].record()
-        step(resident)
-        ev1[i].record()
-    barrier()
+    t_ms, per_step, launches = time_resident(ctx, args.steps, 0)
     sampler.mark_end()
-    launches = (L.vog_launch_count() - n0) // args.steps      # eager launches of libvog_b200 per step
-    if mdl.use_cuda_graph:                                     # + the kernels captured in the replayed graph
-        launches += int(getattr(mdl, 'graph_launches', 0))
-    t_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     clocks = sampler.stop()
-    tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms = tt.item()
     value = world * B * args.steps / (t_ms / 1e3)
 
     # ---- end to end: pinned host batch -> H2D -> forward + selection -> D2H of the predictions ----
@@ -343,13 +441,70 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * B * args.steps / te.item()
 
+    # ---- sub-objects that every rank takes part in (weak scaling, same rules as the headline) --------------
+    extras = {}
+    if not args.no_extras:
+        sub_steps = max(5, min(args.steps, 20))
+        if args.workload != 'temp_gt5':
+            # BASELINE.json configs[3]: temp/gt5, bs=4 per GPU (bs=8 global on 2 GPUs)
+            c2 = build('temp_gt5', COMPUTE['temp_gt5'])
+            t2, _, l2 = time_resident(c2, sub_steps, 3)
+            extras['temp_gt5'] = {'value': world * c2['w']['B'] * sub_steps / (t2 / 1e3), 'unit': 'queries/s',
+                                  'ms_per_step': t2 / sub_steps, 'steps': sub_steps, 'n_gpus': world,
+                                  'global_batch': world * c2['w']['B'], 'compute': COMPUTE['temp_gt5'],
+                                  'gpu_launches': int(l2), 'note': 'BASELINE.json configs[3] (bs=8 global at 2 GPUs); '
+                                  'resident inputs, CUDA graph, L2 flushed between steps'}
+            del c2
+        try:
+            extras['train_step'] = train_step_object(dev, world, rank, flush, barrier, max_ranks, sub_steps)
+        except (NotImplementedError, ImportError) as e:        # backward not built for this configuration
+            extras['train_step'] = {'unavailable': str(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (fused attention), timed alone with CUDA events ---------
+    # ---- rank-0 sub-objects ---------------------------------------------------------------------------------
     pk, pk_kind = peaks()
+    if not args.no_extras:
+        sub_steps = max(5, min(args.steps, 20))
+        # (a) the exact-fp32 CUDA-core path on the headline workload (BASELINE config 2 says fp32: this is the
+        #     number with fp32 arithmetic end to end; the headline runs tf32 GEMMs + bf16 attention operands)
+        if compute != 'fp32x':
+            cx = build(args.workload, 'fp32x', False)
+            tx, _, lx = time_resident(cx, sub_steps, 3)
+            extras['value_fp32x'] = {'value': B * sub_steps / (tx / 1e3), 'unit': 'queries/s', 'ms_per_step': tx / sub_steps,
+                                     'steps': sub_steps, 'gpu_launches': int(lx),
+                                     'note': "compute='fp32x': every product and sum in IEEE fp32 on CUDA cores, eager launches"}
+            del cx
+        # (b) the in-box GPU comparator: the UNMODIFIED reference under torch eager on this B200,
+        #     same batch, resident inputs, CUDA events
+        try:
+            extras['gpu_eager_baseline'] = gpu_eager_object(w, batch, sd_cpu, dev, flush, sub_steps)
+        except Exception as e:                                 # never let a baseline leg take the line down
+            extras['gpu_eager_baseline'] = {'unavailable': repr(e)[:300]}
+        # (c) the north-star shape: full spat/p100 bs=4 forward (obj N=4000, mul N=2000), resident, CUDA graph
+        if args.workload != 'spat_p100' and world == 1:
+            cn = build('spat_p100', 'bf16')
+            tn, _, ln = time_resident(cn, sub_steps, 3)
+            fq = flops_query(cn['w']) * cn['w']['B']
+            tf = fq / (tn / sub_steps * 1e-3) / 1e12
+            ns = {'workload': 'spat_p100', 'per_gpu_batch': cn['w']['B'], 'value': cn['w']['B'] * sub_steps / (tn / 1e3),
+                  'unit': 'queries/s', 'ms_per_step': tn / sub_steps, 'steps': sub_steps, 'compute': 'bf16',
+                  'gpu_launches': int(ln), 'tflops_algorithmic': tf,
+                  'frac_of_sustained_bf16': tf / pk['bf16_tflops_sustained'],
+                  'note': 'BASELINE.json configs[2]; algorithmic FLOPs of SURVEY 8d (dense QKV formula) / measured time'}
+            try:
+                ge = gpu_eager_object(cn['w'], cn['batch'], sd_cpu, dev, flush, 5)
+                ns['gpu_eager_baseline'] = ge
+            except Exception as e:
+                ns['gpu_eager_baseline'] = {'unavailable': repr(e)[:300]}
+            extras['north_star_forward'] = ns
+            del cn
+        torch.cuda.empty_cache()
+
+    # ---- roofline of the dominant kernel (fused attention), timed alone with CUDA events ---------
 
     def traffic_of(kernel, shape_key):
         """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
@@ -465,25 +620,25 @@ def main():
                                     'obj_tx': r_obj, 'mul_tx': r_mul,
                                     'note': 'fused obj_tx+mul_tx attention at spat/p100 bs=4 (N=4000 / 2000)'}
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import vog_oracle as vo                           # cpu_baseline leg only
         cores = os.cpu_count()
         torch.set_num_threads(cores)
-        sd = synth.make_state_dict()
         cb = batch
         nq, sample = B, f'whole batch B={B}, median of 3 after 1 warm-up'
         if w['nppf'] >= 100:
             cb = {k: v[:1].clone() for k, v in batch.items()}
             nq, sample = 1, 'first query of the batch (B=1), median of 3 after 1 warm-up'
+        cstep, ckind = _reference_step_fn(w, sd_cpu, 'cpu')             # cpu_baseline leg only
         ts = []
-        with torch.no_grad():
-            for i in range(4):
-                t0 = time.perf_counter()
-                o = vo.vog_forward(sd, cb, w['conc_type'], w['nppf'])
-                vo.select_boxes(o['mdl_outs_eval'], cb['pad_proposals'], w['conc_type'], w['ncmp'], w['nppf'])
-                if i:
-                    ts.append(time.perf_counter() - t0)
+        for i in range(4):
+            t0 = time.perf_counter()
+            cstep(cb)
+            if i:
+                ts.append(time.perf_counter() - t0)
         line['cpu_baseline'] = {'value': nq / statistics.median(ts), 'unit': 'queries/s', 'cores': cores,
-                                'kind': 'port', 'sample': sample}
+                                'kind': ckind, 'sample': sample}
+    line.update(extras)
+    line['ms_per_step_median'] = statistics.median(per_step)
+    line['ms_per_step_min'] = min(per_step)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

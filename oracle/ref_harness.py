@@ -1,10 +1,14 @@
 """TEST INFRASTRUCTURE ONLY - imports the UNMODIFIED reference from /root/reference.
 
-Only usable in the build container (the GPU box has no /root/reference).  Used by
-``oracle/make_golden.py`` to produce the committed golden vectors under ``tests/golden/`` and by
-``tests/test_oracle_vs_reference.py`` (skipped when the reference tree is absent) to pin the
-restatement in ``oracle/vog_oracle.py`` against the real code.  Nothing in the product path may
-import this module.
+Root of the reference tree: ``$VOG_REFERENCE_ROOT``, else ``/root/reference`` (build container), else
+``baseline/_ref`` - the git-ignored copy of the reference's ``code/``, ``utils/`` and ``configs/`` that
+``__graft_entry__.build()`` installs so that the unmodified reference travels to the GPU box (the
+reference has no setup.py / pyproject, so ``pip install --target baseline/_ref`` has nothing to install;
+the files are copied verbatim instead and never enter the git history).  Used by ``oracle/make_golden.py``
+to produce the committed golden vectors under ``tests/golden/``, by ``tests/test_oracle_vs_reference.py``
+(skipped when no reference tree is present) to pin the restatement in ``oracle/vog_oracle.py`` against the
+real code, and by ``bench.py`` for its two baseline legs (``--impl reference`` on the host cores and
+``gpu_eager_baseline`` on cuda:0).  Nothing in the product path may import this module.
 
 The reference needs two third-party modules that are not installed and carry no arithmetic on
 this path: ``munch.Munch`` (attribute dict; pinned munch==2.5.0,
@@ -16,7 +20,34 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('VOG_REFERENCE_ROOT', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INSTALLED_ROOT = os.path.join(_REPO, 'baseline', '_ref')
+
+
+def _pick_root():
+    for r in (os.environ.get('VOG_REFERENCE_ROOT'), '/root/reference', INSTALLED_ROOT):
+        if r and os.path.isfile(os.path.join(r, 'code', 'mdl_vog.py')):
+            return r
+    return '/root/reference'
+
+
+REF_ROOT = _pick_root()
+
+
+def install_reference(src='/root/reference', dst=INSTALLED_ROOT):
+    """Copy the reference's python sources + config verbatim into baseline/_ref (git-ignored, travels with the
+    gpurun snapshot).  No-op when the source tree is absent.  -> number of files copied."""
+    import shutil
+    if not os.path.isfile(os.path.join(src, 'code', 'mdl_vog.py')):
+        return 0
+    n = 0
+    for sub, pat in (('code', '.py'), ('utils', '.py'), ('configs', '.yml')):
+        os.makedirs(os.path.join(dst, sub), exist_ok=True)
+        for f in sorted(os.listdir(os.path.join(src, sub))):
+            if f.endswith(pat):
+                shutil.copyfile(os.path.join(src, sub, f), os.path.join(dst, sub, f))
+                n += 1
+    return n
 
 
 def reference_available():

@@ -16,7 +16,10 @@ def test_reference_arm_line():
     assert line['impl'] == 'reference' and line['unit'] == 'queries/s' and line['higher_is_better'] is True
     assert line['metric'].startswith('VOGNet fwd queries/sec') and line['value'] > 0
     assert line['steps'] == 1 and line['warmup'] >= 3 and line['n_gpus'] == 1
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    # the unmodified reference (baseline/_ref or /root/reference) when installed, the oracle port otherwise
+    from oracle import ref_harness
+    assert line['cpu_baseline']['kind'] == ('reference' if ref_harness.reference_available() else 'port')
+    assert line['cpu_baseline']['cores'] >= 1 and line['reference_ranks'] == 1 and line['reference_n_queries'] == 1
     assert line['cpu_baseline']['value'] == line['value'] == line['e2e']['value']
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
     cfg = line['config']

@@ -37,7 +37,7 @@ def _worker(rank, world, port, nq, ret):
         assert torch.equal(full['indexs'], batch['srl_arg_word_mask_len'])
         # flat gradient all-reduce of the data-parallel training step: one collective, mean = sum * 1/world
         g = torch.arange(10, dtype=torch.float32) * (rank + 1)
-        scale = runtime.allreduce_flat_sum_(g)
+        scale, _ = runtime.allreduce_flat_sum_(g)
         assert scale == 1.0 / world and torch.equal(g * scale, torch.arange(10, dtype=torch.float32) * 1.5)
         t = runtime.max_over_ranks(1.0 + rank, 'cpu')
         assert t == float(world)

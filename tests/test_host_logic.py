@@ -148,3 +148,27 @@ def test_ctypes_signatures_match_the_header():
             else:
                 base = prm.replace('const ', '').split()[0]
                 assert ct is ctype_of[base], (name, prm, ct)
+
+
+def test_pack_cache_refreshes_in_place_and_follows_raw_pointer_updates():
+    """ADVICE r1 (high/medium): packed weight copies must follow in-place edits (``_version``), raw-pointer updates
+    (``packing.bump_generation``, what FlatAdam.step calls) and keep their addresses so captured graphs stay valid."""
+    import torch
+    from vognet_pytorch_b200 import packing
+    pc = packing.PackCache()
+    p = torch.nn.Parameter(torch.ones(3))
+    v = pc.get('w', (p,), lambda: p.detach() * 2)
+    addr = v.data_ptr()
+    assert pc.get('w', (p,), lambda: 1 / 0) is v                       # fresh: build is not called
+    with torch.no_grad():
+        p.add_(1)
+    v2 = pc.get('w', (p,), lambda: p.detach() * 2)
+    assert v2.data_ptr() == addr and v2.tolist() == [4.0, 4.0, 4.0]
+    p.data[0] = 5                                                      # no version bump through .data
+    sig = packing.params_signature([p])
+    packing.bump_generation()
+    assert packing.params_signature([p]) != sig
+    assert pc.refresh() == 1 and v2.tolist() == [10.0, 4.0, 4.0] and pc.relocations == 0
+    p.data = torch.zeros(5)                                            # shape change: storage must move
+    v3 = pc.get('w', (p,), lambda: p.detach() * 2)
+    assert v3.shape == (5,) and pc.relocations == 1

@@ -132,6 +132,8 @@ lang_embed_kernel(const long long* __restrict__ words, int nwords, const long lo
     const long long mk = mask[(size_t)b * T + t];
     long long tok = pad_idx;
     if (mk != -1) tok = words[(size_t)b * nwords + (mk < 0 ? 0 : (mk >= nwords ? nwords - 1 : mk))];
+    // nn.Embedding raises on ids outside [0, pad_idx]; a kernel cannot, so out-of-range ids read the (zero) padding row
+    if (tok < 0 || tok > pad_idx) tok = pad_idx;
     const float4* src = reinterpret_cast<const float4*>(emb + (size_t)tok * E);
     // blockIdx.y owns a 512-float4 column chunk: four independent 16-byte loads per thread, and enough CTAs to fill
     // the GPU when the rows are the 32 KB lines of the layer-0 projection table (80 rows at spat/gt5)

@@ -8,6 +8,7 @@
 //     p  = fma(-(lr / bc1), m / (sqrt(v) / sqrt(bc2) + eps), p)   (addcdiv_)
 // with the bias corrections bc1 = 1 - b1^t, bc2 = 1 - b2^t evaluated in double on the host like torch does in Python.
 // `grad_scale` folds the 1/world of a summed gradient all-reduce into the same pass.
+#include <math.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -52,9 +53,8 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, double 
     if (n == 0) return 0;
     VOG_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                   reinterpret_cast<uintptr_t>(v)) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
-    double bc1 = 1.0, bc2 = 1.0, p1 = 1.0, p2 = 1.0;
-    for (long long i = 0; i < step && (p1 > 1e-300 || p2 > 1e-300); ++i) { p1 *= beta1; p2 *= beta2; }
-    bc1 = 1.0 - p1; bc2 = 1.0 - p2;
+    // bias corrections 1 - beta^t exactly as torch.optim.Adam computes them (beta ** step in double precision)
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
     const long long n4 = n >> 2;
     long long blocks = (n4 + 255) / 256;
     const long long cap = (long long)num_sms() * 16;

@@ -5,7 +5,9 @@ state_dict key names, so ``code/main_dist.py`` can build,
 DDP-wrap, checkpoint and call them unchanged.
 
 What runs where
-  language side (a13)   torch + cuDNN LSTM, optionally on a side stream (code/mdl_vog.py:67-140,250-283)
+  language side (a13)   libvog_b200: embedding gather, tcgen05 input/output projections, persistent LSTM
+                        recurrence kernel (code/mdl_vog.py:67-140,250-283); torch + cuDNN only in the exact
+                        'fp32x' bring-up mode
   everything else       libvog_b200 CUDA kernels through vognet_pytorch_b200.ops:
       prop/seg encoders                       code/mdl_vog.py:291-314
       prop|seg concat                         code/mdl_conc_single.py:50-66,156-174
@@ -15,15 +17,16 @@ What runs where
       multimodal transformer                  code/mdl_vog.py:681-744
       lin2 scorer, un-regroup, sigmoid*masks  code/mdl_vog.py:675-677, code/mdl_conc_single.py:118-127
 
-``sep``/``svsq`` concatenation (code/mdl_conc_sep.py) is outside the hot-path scope (SURVEY.md
-section 2 row 7) and raises NotImplementedError in the selector.
+``sep``/``svsq`` concatenation (code/mdl_conc_sep.py:13-217) runs through the same kernels: every (query, video)
+pair becomes one single-video pseudo-query (``_sep_flatten``), plus the video-level verb head.
 """
 import os
 
 import torch
 from torch import nn
 
-from . import ops
+from . import ops, packing
+from .packing import PackCache
 from .transformer_code import COMPUTE_MODES, FactoredTokens, RelBias, RelTransformer, Transformer
 
 
@@ -53,6 +56,7 @@ def _scorer(i):
 
 class VOGNetB200(nn.Module):
     CONC_TYPE = None       # 'spat' | 'temp' | 'sep'
+    MAX_GRAPHS = 8         # captured forwards kept per module (one per batch-shape signature, LRU)
     USE_OBJ_TX = True      # VidGrnd / VOGNet
     USE_MUL_TX = True      # VOGNet
 
@@ -148,33 +152,35 @@ class VOGNetB200(nn.Module):
         enc = enc * inp['srl_arg_inds_msk'].reshape(B * nv, nsrl, 1).float()
         return enc.view(B, nv * nsrl, D)
 
+    def _packs(self):
+        pk = self.__dict__.get('_pack')
+        if pk is None:
+            pk = self.__dict__['_pack'] = PackCache()
+        return pk
+
     def _lang_weights(self, kind):
         """cached tensor-core operands of the language side: per layer the forward|reverse W_ih
         stacked to [8H, in] (low precision) with b_ih+b_hh, and W_hh stacked to [2,4H,H] fp32."""
         lstm = self.lstm_encoder.lstm
         params = [p for p in lstm.parameters()] + [self.lstm_encoder.embed_tokens.weight]
-        cache = self.__dict__.setdefault('_lang_cache', {})
-        sig = tuple((p.data_ptr(), p._version) for p in params) + (kind,)
-        ent = cache.get(kind)
-        if ent is None or ent[0] != sig:
+
+        def build():
             layers = []
-            with torch.no_grad():
-                for l in range(lstm.num_layers):
-                    g = lambda n: getattr(lstm, f'{n}_l{l}').detach()              # noqa: E731
-                    gr = lambda n: getattr(lstm, f'{n}_l{l}_reverse').detach()     # noqa: E731
-                    wih = torch.cat([g('weight_ih'), gr('weight_ih')], 0).float().contiguous()
-                    bias = torch.cat([g('bias_ih') + g('bias_hh'), gr('bias_ih') + gr('bias_hh')], 0).float().contiguous()
-                    whh = torch.stack([g('weight_hh'), gr('weight_hh')], 0).float().contiguous()
-                    layers.append((ops.cast_lp(wih, kind), bias, whh))
-                # layer 0 sees only embedding rows: its input projection W_ih.emb[tok] + b is a function of the
-                # token id alone, so it is tabulated once per weight version (exact fp32) and the per-step GEMM
-                # becomes a row gather
-                emb = self.lstm_encoder.embed_tokens.weight.detach().float().contiguous()
-                wih0 = torch.cat([lstm.weight_ih_l0.detach(), lstm.weight_ih_l0_reverse.detach()], 0).float().contiguous()
-                table = ops.sgemm_nt(emb, wih0, layers[0][1])                            # [V+1, 8H], exact fp32
-            ent = (sig, layers, table)
-            cache[kind] = ent
-        return ent[1], ent[2]
+            for l in range(lstm.num_layers):
+                g = lambda n: getattr(lstm, f'{n}_l{l}').detach()              # noqa: E731
+                gr = lambda n: getattr(lstm, f'{n}_l{l}_reverse').detach()     # noqa: E731
+                wih = torch.cat([g('weight_ih'), gr('weight_ih')], 0).float().contiguous()
+                bias = torch.cat([g('bias_ih') + g('bias_hh'), gr('bias_ih') + gr('bias_hh')], 0).float().contiguous()
+                whh = torch.stack([g('weight_hh'), gr('weight_hh')], 0).float().contiguous()
+                layers.append((ops.cast_lp(wih, kind), bias, whh))
+            # layer 0 sees only embedding rows: its input projection W_ih.emb[tok] + b is a function of the
+            # token id alone, so it is tabulated once per weight version (exact fp32) and the per-step GEMM
+            # becomes a row gather
+            emb = self.lstm_encoder.embed_tokens.weight.detach().float().contiguous()
+            wih0 = torch.cat([lstm.weight_ih_l0.detach(), lstm.weight_ih_l0_reverse.detach()], 0).float().contiguous()
+            table = ops.sgemm_nt(emb, wih0, layers[0][1])                            # [V+1, 8H], exact fp32
+            return (layers, table)
+        return self._packs().get(('lang', kind), params, build)
 
     def language_encode_tc(self, inp):
         """Language side without host synchronisation (CUDA-graph capturable): embedding gather,
@@ -307,13 +313,22 @@ class VOGNetB200(nn.Module):
     # tensor-core path ('tf32' / 'bf16')
     # -----------------------------------------------------------------------------------------
     def _lp_weight(self, name, param, kind):
-        cache = self.__dict__.setdefault('_lp_cache', {})
-        sig = (param.data_ptr(), param._version, kind)
-        ent = cache.get(name)
-        if ent is None or ent[0] != sig:
-            ent = (sig, ops.cast_lp(param.detach().contiguous(), kind))
-            cache[name] = ent
-        return ent[1]
+        return self._packs().get((name, kind), (param,), lambda: ops.cast_lp(param.detach().contiguous(), kind))
+
+    def _weights_sig(self):
+        ps = self.__dict__.get('_sig_params')
+        if ps is None:
+            ps = self.__dict__['_sig_params'] = list(self.parameters())
+        return packing.params_signature(ps)
+
+    def _refresh_packs(self):
+        """Re-pack every stale low-precision / padded weight copy in place (addresses are stable, so captured
+        graphs keep working) -> True if some entry had to be re-allocated (graphs must then be recaptured)."""
+        caches = [self._packs()] + [getattr(self, t)._exec._pack for t in ('obj_txf', 'mult_txf') if hasattr(self, t)]
+        before = sum(c.relocations for c in caches)
+        for c in caches:
+            c.refresh()
+        return sum(c.relocations for c in caches) != before
 
     def _forward_tc(self, inp):
         feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
@@ -481,8 +496,13 @@ class VOGNetB200(nn.Module):
             with torch.cuda.graph(graph, stream=cap):
                 out = body(side)
             # kernels of libvog_b200 captured into the graph = launches per replay
-            g = dict(st=st, graph=graph, out=out, launches=_lib.lib().vog_launch_count() - n0)
+            g = dict(st=st, graph=graph, out=out, launches=_lib.lib().vog_launch_count() - n0,
+                     wsig=self._weights_sig())
             graphs[key] = g
+            while len(graphs) > self.MAX_GRAPHS:            # least recently used first (dicts keep insertion order)
+                graphs.pop(next(iter(graphs)))
+        else:
+            graphs[key] = graphs.pop(key)                    # mark as most recently used
         return g
 
     def graph_input_buffers(self, inp):
@@ -490,6 +510,8 @@ class VOGNetB200(nn.Module):
         needed).  A caller that writes its batches straight into these tensors (e.g. as the destination of its
         host-to-device copies) and passes the same dict to ``forward`` skips the staging copies: ``forward``
         only copies inputs whose storage differs from the graph's."""
+        if self.CONC_TYPE == 'sep':                  # forward() replays the graph on the flattened pseudo-queries
+            inp, _ = self._sep_flatten(inp)
         g = self._graph_for(inp, inp['new_srl_idxs'].shape[1])
         buf = dict(g['st'])
         for k, v in inp.items():                    # keys the graph does not read (only shapes matter) pass through
@@ -498,6 +520,15 @@ class VOGNetB200(nn.Module):
 
     def _forward_tc_graph(self, inp, ncmp):
         g = self._graph_for(inp, ncmp)
+        # The captured kernels read the PACKED weight copies through baked-in addresses.  When a parameter changed
+        # since the last replay (optimizer step, load_state_dict, in-place edit) the copies are re-packed in place;
+        # only if one had to move (shape / dtype change) are the graphs dropped and this one captured again.
+        wsig = self._weights_sig()
+        if g['wsig'] != wsig:
+            if self._refresh_packs():
+                self.__dict__['_graphs'] = {}
+                g = self._graph_for(inp, ncmp)
+            g['wsig'] = wsig
         self.graph_launches = g['launches']
         for k, buf in g['st'].items():
             src = inp[k]

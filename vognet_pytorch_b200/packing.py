@@ -1,0 +1,97 @@
+"""Packed-weight caches with STABLE device addresses.
+
+The tensor-core path reads every weight through a packed copy (bf16 / tf32-rounded, per-head zero padding of
+Wq|Wk|Wv / Wo: code/transformer_code.py:169-186 splits heads with ``chunk``; stacked LSTM matrices).  Those copies are
+derived state and have to follow the parameters:
+
+  * an entry is keyed on ``(data_ptr, _version)`` of its source parameters AND on a process-wide weights
+    generation that optimizers writing through raw pointers bump (``optim.FlatAdam.step`` updates the flat buffer
+    in a kernel, which changes neither ``data_ptr`` nor ``_version``);
+  * a stale entry is rebuilt IN PLACE (``copy_`` into the tensors it already owns), so device addresses that a
+    captured CUDA graph baked in stay valid - ``refresh()`` re-packs everything that is stale without running a
+    forward, which is what a graph replay calls first.
+"""
+import torch
+
+_GENERATION = 0
+
+
+def bump_generation():
+    """Parameters were modified behind autograd's back (raw-pointer kernels): every packed copy is stale."""
+    global _GENERATION
+    _GENERATION += 1
+    return _GENERATION
+
+
+def generation():
+    return _GENERATION
+
+
+def params_signature(params):
+    """Cheap per-forward staleness probe over many parameters."""
+    v, d = 0, 0
+    for p in params:
+        v += p._version
+        d ^= p.data_ptr()
+    return (_GENERATION, v, d)
+
+
+def _same_layout(a, b):
+    if isinstance(a, torch.Tensor):
+        return isinstance(b, torch.Tensor) and a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
+    if isinstance(a, dict):
+        return isinstance(b, dict) and a.keys() == b.keys() and all(_same_layout(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)):
+        return isinstance(b, (list, tuple)) and len(a) == len(b) and all(_same_layout(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+def _copy_into(dst, src):
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_into(dst[k], src[k])
+    elif isinstance(dst, (list, tuple)):
+        for x, y in zip(dst, src):
+            _copy_into(x, y)
+
+
+class PackCache:
+    def __init__(self):
+        self._ent = {}
+        self.relocations = 0          # entries whose storage had to be replaced (captured graphs must be dropped)
+
+    @staticmethod
+    def _sig(params):
+        return tuple((p.data_ptr(), p._version) for p in params) + (_GENERATION,)
+
+    def get(self, key, params, build):
+        """The packed value for `key`; `build()` (run under no_grad) derives it from `params`."""
+        params = tuple(params)
+        ent = self._ent.get(key)
+        sig = self._sig(params)
+        if ent is not None and ent[0] == sig:
+            return ent[3]
+        with torch.no_grad():
+            val = build()
+        if ent is not None and _same_layout(ent[3], val):
+            _copy_into(ent[3], val)                 # same addresses: captured graphs keep reading valid, fresh data
+            val = ent[3]
+        elif ent is not None:
+            self.relocations += 1
+        self._ent[key] = (sig, params, build, val)
+        return val
+
+    def refresh(self):
+        """Re-pack every stale entry in place (no forward needed).  -> number of entries rebuilt."""
+        n = 0
+        for key, (sig, params, build, _) in list(self._ent.items()):
+            if self._sig(params) != sig:
+                self.get(key, params, build)
+                n += 1
+        return n
+
+    def clear(self):
+        self._ent.clear()
+        self.relocations += 1

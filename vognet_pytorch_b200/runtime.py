@@ -59,13 +59,15 @@ def concat_batch(sep_batch, conc_type, nfrm, nppf, sentence_slot=0):
     return out
 
 
-def allreduce_flat_sum_(flat, group=None):
+def allreduce_flat_sum_(flat, group=None, async_op=False):
     """In-place SUM of one flat gradient buffer over the ranks - a single collective for the whole model - and the
-    factor that turns it into the mean DistributedDataParallel produces (code/main_dist.py:76-85).  -> 1/world."""
+    factor that turns it into the mean DistributedDataParallel produces (code/main_dist.py:76-85).
+    -> (1/world, work handle or None).  With ``async_op`` the collective is only enqueued (NCCL: on its own stream);
+    ``work.wait()`` orders the caller's current stream after it."""
     if not (dist.is_available() and dist.is_initialized()):
-        return 1.0
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    return 1.0 / dist.get_world_size(group)
+        return 1.0, None
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return 1.0 / dist.get_world_size(group), (work if async_op else None)
 
 
 def max_over_ranks(seconds, device):

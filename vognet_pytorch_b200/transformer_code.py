@@ -20,6 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .packing import PackCache
 
 COMPUTE_MODES = ('fp32x', 'tf32', 'bf16')
 
@@ -99,17 +100,11 @@ class EncoderExecutor:
         self.drop = drop_ratio
         self.head_dims = ops.chunk_sizes(d_model, n_heads)
         self.dhp = ops.round_up(max(self.head_dims), 64)
-        self._pack = {}
+        self._pack = PackCache()
 
     # -- packed weights, rebuilt whenever a parameter was updated in place or replaced ---------
     def _cached(self, key, params, build):
-        sig = tuple((p.data_ptr(), p._version) for p in params)
-        ent = self._pack.get(key)
-        if ent is None or ent[0] != sig:
-            with torch.no_grad():
-                ent = (sig, build())
-            self._pack[key] = ent
-        return ent[1]
+        return self._pack.get(key, params, build)
 
     def _packed(self, l, layer):
         att = layer.selfattn.layer
