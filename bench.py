@@ -457,7 +457,7 @@ def main():
             del c2
         try:
             extras['train_step'] = train_step_object(dev, world, rank, flush, barrier, max_ranks, sub_steps)
-        except (NotImplementedError, ImportError) as e:        # backward not built for this configuration
+        except (NotImplementedError, ImportError, AttributeError) as e:   # backward not built for this configuration
             extras['train_step'] = {'unavailable': str(e)}
 
     if rank != 0:

@@ -61,7 +61,8 @@ int vog_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* 
 int vog_attn_fwd_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
                      int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
                      int bias_mode, const float* a, int nbox, const float* bpe,
-                     const float* dense, void* stream);
+                     const float* dense, float* lse, void* stream);
+/* lse (nullable): [Bt,H,N] log-sum-exp of the scaled scores, kept by the training forward for vog_attn_bwd_f32. */
 
 /* out = LayerNorm(x + r) * w + b (eps inside the sqrt), r nullable; optional low-precision copy
  * out_lp (VOG_LP_*) for the next GEMM.  replaces ResidualBlock: code/transformer_code.py:21-31. */
@@ -276,6 +277,93 @@ int vog_verb_loss_fwd(const float* vidf, const int64_t* verb_cmp, const int64_t*
 int vog_concat_videos(const float* feat, int D, const float* seg, int Ds, const float* props, int pdim, float* feat_out,
                       float* seg_out, float* props_out, int B, int ncmp, int nfrm, int nppf, int spat, float shift,
                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * training step: backward of the path.  The reference's backward is torch autograd
+ * over its forward (utils/trn_utils.py:500-505: mdl(batch) -> loss_fn -> loss.backward() -> optimizer.step());
+ * every entry point below is the analytic gradient of the forward operation it cites.  Gradient buffers marked
+ * "accumulated" must be zero-initialised by the caller (they are added to atomically).
+ * ------------------------------------------------------------------------------------------- */
+
+/* C[M,N] = epi(sum_k A(m,k) B(k,n)),  A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn]  (one unit stride each);
+ * epi: (+bias[n]); relu; (+C when accumulate).  Exact fp32.  dX = dY.W (sbk = ldw, sbn = 1) and dW = dY^T.X
+ * (sam = 1, sak = ldy) of every nn.Linear on the path: code/transformer_code.py:57-60,80-81,169-172,180,186;
+ * code/mdl_vog.py:182-193,202-207,224-230.  Deep reductions (accumulate, no bias/relu) are split over K. */
+int vog_sgemm_strided(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn,
+                      const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, int accumulate,
+                      void* stream);
+
+/* out[n] += sum_m x[m,n]   (accumulated): bias gradients of the nn.Linear layers. */
+int vog_colsum_acc(const float* x, int64_t ldx, float* out, int64_t M, int N, void* stream);
+
+/* g = dy * [act > 0] -> out (fp32, nullable; may alias dy) and / or out_lp (VOG_LP_*), dbias[n] += sum_m g (nullable,
+ * accumulated).  act = the forward's post-ReLU activation, fp32 (act_kind 0 / 2) or bf16 (act_kind 1).
+ * Gradient of nn.ReLU after nn.Linear: code/transformer_code.py:80-81, code/mdl_vog.py:202-207,224-230. */
+int vog_relu_bwd(const float* dy, int64_t ldy, const void* act, int64_t lda, int act_kind, float* out, int64_t ldo,
+                 void* out_lp, int64_t ldlp, int lp_kind, float* dbias, int64_t M, int N, void* stream);
+
+/* LayerNorm backward of the post-LN ResidualBlock (code/transformer_code.py:21-31): x = saved pre-normalisation sum
+ * [M,d]; dx (fp32, nullable) / dx_lp (VOG_LP_*, nullable) = gradient w.r.t. x (= w.r.t. the residual AND the branch);
+ * dgamma, dbeta, dxsum [d] accumulated (dxsum = column sums of dx = bias gradient of the branch's last nn.Linear;
+ * nullable). */
+int vog_layernorm_bwd(const float* dy, int64_t ldy, const float* x, int64_t ldx, const float* gamma, float* dx,
+                      int64_t lddx, void* dx_lp, int64_t ldlp, int lp_kind, float* dgamma, float* dbeta, float* dxsum,
+                      int64_t M, int d, float eps, void* stream);
+
+/* Attention backward, exact fp32, flash-style recompute from the saved log-sum-exp (nothing N x N is stored).
+ * q,k,v / dq,dk,dv: [Bt*N, ld] / [Bt*N, ldg] with heads as column chunks (off, dh host arrays), out / dout the
+ * forward output and its gradient, lse [Bt,H,N] from vog_attn_fwd_f32, delta [Bt,H,N] scratch.  Rank-1 bias:
+ * da [Bt*nbox, H] and dbpe [H] accumulated; dense bias: ddense [Bt,N,N,H] written (nullable).
+ * Gradient of RelAttention / Attention (code/transformer_code.py:41-50,136-160) and of the bias construction
+ * relu(Linear(5,H)(p_i - p_j)) (code/mdl_vog.py:477-488, utils/mdl_srl_utils.py:30-69). */
+int vog_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ld, const float* out, int64_t ldo,
+                     const float* dout, int64_t lddo, const float* lse, float* delta, float* dq, float* dk, float* dv,
+                     int64_t ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
+                     const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe,
+                     float* ddense, void* stream);
+
+/* dW[h,c] += sum_rows da[row,h] * normalised(props[row, c])  (accumulated): gradient of vog_pe_project w.r.t. the
+ * pe_{obj,mul}_sub_enc weight (code/mdl_vog.py:446-451,459-463,580-585); the boxes carry no gradient (:497,506,624). */
+int vog_pe_project_bwd(const float* props, int ldp, const float* da, float* dW, int rows, int H, float vid_w,
+                       float vid_h, float fdiv, void* stream);
+
+/* Gradient of the multimodal token matrix w.r.t. its factors (token (b,f,s,p) = [vis | lang], code/mdl_vog.py:316-344,
+ * 693-699): dvis [B*nfrm*nppf2, dv] = sum over the nsrl slots (written); dlang [B*nsrl, dl] += sum over frames and
+ * proposals (accumulated).  dtok [B*nfrm*nsrl*nppf2, dv+dl] fp32. */
+int vog_xmul_bwd(const float* dtok, float* dvis, float* dlang, int B, int nfrm, int nsrl, int nppf2, int dv, int dl,
+                 void* stream);
+
+/* Segment half of the prop|seg rows (code/mdl_conc_single.py:50-66,156-174): dseg[slot, c] = [x[slot*nppf, pe+c] > 0]
+ * * sum_p dx[slot*nppf + p, pe+c]  (gradient of the replicated relu(seg_encoder) rows; written). */
+int vog_seg_rep_bwd(const float* dx, const float* x, int ld, int pe, int se, int nppf, float* dseg, int64_t nslots,
+                    void* stream);
+
+/* Scorer tail backward (lin2[2] on relu(lin2[0]) + inverse regroup, code/mdl_vog.py:224-230,675-677,724-737):
+ * dlogits [B,nsrl,nfrm*nppf2]; h [M,K] post-ReLU hidden (fp32 or bf16 by h_kind); dh (fp32, nullable) / dh_lp
+ * (VOG_LP_*, nullable) [M,K]; dw2 [K], db2 [1], db1 [K] accumulated. */
+int vog_lin2_bwd(const float* dlogits, const void* h, int64_t ldh, int h_kind, const float* w2, float* dh, void* dh_lp,
+                 int lp_kind, float* dw2, float* db2, float* db1, int64_t M, int K, int nfrm, int nsrl, int nppf2,
+                 void* stream);
+
+/* Language-side glue backward (code/mdl_vog.py:97-140; utils/mdl_srl_utils.py:96-128): scatter of the first / last
+ * word gather (dfull [T*Bq, D] accumulated) and of the embedding lookup (demb [V+1, E] accumulated; the padding row and
+ * steps beyond lens get nothing). */
+int vog_lang_gather_bwd(const float* dcat, int D, const int64_t* cap, int T, int Bq, int nsrl, float* dfull,
+                        void* stream);
+int vog_lang_embed_bwd(const int64_t* words, int nwords, const int64_t* mask, int T, const float* dx, int E,
+                       int64_t pad_idx, int Bq, const int64_t* lens, float* demb, void* stream);
+
+/* LSTM backward building blocks (nn.LSTM, bidirectional, packed sequences: utils/mdl_srl_utils.py:100-152).
+ * hout [T*Bq, 2H] fp32 hidden states of the layer (time-major), lens [Bq].
+ *   vog_lstm_hprev     hprev [T*Bq, 2H]: the state each step started from (t-1 forward, t+1 reverse, 0 at the ends)
+ *   vog_lstm_scan      G [T*Bq, 8H] gate pre-activations (gx + hprev.W_hh^T, recomputed by a GEMM) -> acts
+ *                      [T*Bq, 2, 6, H]: i, f, g, o, tanh(c_t), c_{t-1}
+ *   vog_lstm_bwd_steps dout [T*Bq, 2H] -> dG [T*Bq, 8H] (zeros beyond lens): T dependent launches, each one
+ *                      dh_{prev} = dG_t . W_hh; carry_ws: 8*Bq*H floats of scratch; Bq <= 8 per call. */
+int vog_lstm_hprev(const float* hout, const int64_t* lens, float* hprev, int T, int Bq, int H, void* stream);
+int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int Bq, int H, void* stream);
+int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const int64_t* lens, float* dG,
+                       float* carry_ws, int T, int Bq, int H, void* stream);
 
 /* ---- debug hooks (not part of the data path) ----------------------------------------------------
  * vog_debug_gemm_trace: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of every

@@ -1,0 +1,280 @@
+"""Backward of the path on the GPU.
+
+Model level: ``model.train()(batch)`` -> ``LossB_SPAT`` -> ``loss.backward()`` through the hand-written kernel chain
+(vognet_pytorch_b200.training), compared with
+  * tests/golden/grad_cpu_ref.npz - parameter gradients torch autograd derived for the UNMODIFIED reference
+    (oracle/make_golden.py; norms, leading elements and sums of all 57 live parameters), and
+  * autograd through the oracle restatement on the CPU, element by element.
+Kernel level: every backward entry point against torch autograd of the operation it differentiates, on odd shapes.
+Tolerance: 1e-3 relative to the largest element of each gradient in the exact 'fp32x' mode."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import vognet_pytorch_b200 as vb                                   # noqa: E402
+from vognet_pytorch_b200 import ops, ops_bwd as ob, synth          # noqa: E402
+from oracle import vog_oracle as vo                                # noqa: E402  (checker)
+
+DEV = 'cuda:0'
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _rel(a, b):
+    b = b.double()
+    return float((a.double().cpu() - b.cpu()).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+def _model(name, compute, **cfg_kw):
+    w, batch = synth.workload(name)
+    inp = dict(batch)
+    inp.update(synth.make_loss_inputs(batch, **w))
+    cfg, comm = synth.default_cfg(w['conc_type'], **cfg_kw), synth.default_comm(w['nppf'])
+    sel = vb.get_mdl_loss_eval(cfg)
+    mdl = sel['mdl'](cfg, comm)
+    sd = synth.make_state_dict(**({k: v for k, v in cfg_kw.items() if k in ('n_layers', 'n_heads')}))
+    mdl.load_state_dict(sd, strict=True)
+    mdl = mdl.to(DEV).set_compute(compute)
+    mdl.train_dropout = False
+    loss_fn = sel['loss'](cfg, comm)
+    return w, inp, sd, mdl, loss_fn
+
+
+def _oracle_grads(w, inp, sd, **kw):
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = vo.vog_forward(sdg, synth.clone_batch(inp), w['conc_type'], w['nppf'], **kw)
+    loss = vo.loss_forward(out['mdl_outs'], inp, w['conc_type'], w['ncmp'], w['nppf'])['loss']
+    loss.backward()
+    return float(loss.detach()), {k: v.grad for k, v in sdg.items()}
+
+
+def test_fp32x_parameter_gradients_match_the_reference_golden():
+    g = np.load(os.path.join(GOLD, 'grad_cpu_ref.npz'))
+    w, inp, sd, mdl, loss_fn = _model('cpu_ref', 'fp32x')
+    mdl.train()
+    dinp = synth.clone_batch(inp, DEV)
+    out = mdl(dinp)
+    assert out['mdl_outs'].requires_grad and set(out) == {'mdl_outs', 'mdl_outs_eval'}
+    loss = loss_fn(out, dinp)['loss']
+    assert abs(float(loss.detach()) - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    loss.backward()
+    torch.cuda.synchronize()
+    unused = set(g['unused'].tolist())
+    assert unused == {k for k, p in mdl.named_parameters() if p.grad is None}
+    checked = 0
+    for k, p in mdl.named_parameters():
+        if k in unused:
+            continue
+        gr = p.grad.double().reshape(-1).cpu()
+        norm = float(g['norm/' + k])
+        assert abs(float(gr.norm()) - norm) <= 1e-3 * norm + 1e-9, (k, float(gr.norm()), norm)
+        head = g['head/' + k]
+        assert np.abs(gr[:8].numpy() - head).max() <= 1e-3 * max(np.abs(head).max(), norm * 1e-3), k
+        checked += 1
+    assert checked == 57
+
+
+@pytest.mark.parametrize('name', ['cpu_ref', 'temp_gt5'])
+def test_fp32x_gradients_match_oracle_autograd_elementwise(name):
+    w, inp, sd, mdl, loss_fn = _model(name, 'fp32x')
+    if name != 'cpu_ref':                      # keep the CPU autograd pass small: two queries
+        inp = {k: v[:2].clone() for k, v in inp.items()}
+    ref_loss, ref = _oracle_grads(w, inp, sd)
+    mdl.train()
+    dinp = synth.clone_batch(inp, DEV)
+    loss = loss_fn(mdl(dinp), dinp)['loss']
+    loss.backward()
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-5 * abs(ref_loss)
+    worst = {}
+    for k, p in mdl.named_parameters():
+        if ref[k] is None:
+            assert p.grad is None, k
+            continue
+        worst[k] = _rel(p.grad, ref[k])
+    bad = {k: v for k, v in worst.items() if v > 1e-3}
+    assert not bad, bad
+
+
+def test_eval_mode_and_no_grad_keep_the_inference_path():
+    w, inp, sd, mdl, loss_fn = _model('cpu_ref', 'fp32x')
+    dinp = synth.clone_batch(inp, DEV)
+    mdl.eval()
+    ref = mdl(dinp)['mdl_outs']
+    mdl.train()
+    with torch.no_grad():                           # train mode without autograd: same forward, nothing recorded
+        out = mdl(dinp)
+    assert not out['mdl_outs'].requires_grad and float((out['mdl_outs'] - ref).abs().max()) <= 2e-5
+    got = mdl(dinp)['mdl_outs']                    # training forward without dropout = the same function
+    assert got.requires_grad and float((got - ref).abs().max()) <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel level
+# ---------------------------------------------------------------------------------------------
+def test_sgemm_strided_views():
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(70, 37, generator=g).to(DEV)
+    w = torch.randn(53, 37, generator=g).to(DEV)
+    dy = torch.randn(70, 53, generator=g).to(DEV)
+    assert _rel(ob.sgemm(dy, w), dy.double() @ w.double()) < 1e-5               # dX = dY W
+    assert _rel(ob.sgemm(dy.t(), a), dy.double().t() @ a.double()) < 1e-5       # dW = dY^T X
+    assert _rel(ob.sgemm(a, w.t()), a.double() @ w.double().t()) < 1e-5         # forward NT
+    big = torch.randn(5000, 40, generator=g).to(DEV)
+    big2 = torch.randn(5000, 24, generator=g).to(DEV)
+    out = torch.ones(40, 24, device=DEV)
+    ob.sgemm(big.t(), big2, out=out, accumulate=True)                              # split-K path, accumulates
+    assert _rel(out, big.double().t() @ big2.double() + 1) < 1e-5
+    sl = torch.zeros(70, 100, device=DEV)
+    ob.sgemm(dy[:, 3:40], w[3:40, :30], out=sl[:, 10:40], accumulate=True)          # column-slice views everywhere
+    assert _rel(sl[:, 10:40], dy[:, 3:40].double() @ w[3:40, :30].double()) < 1e-5
+    assert float(sl[:, :10].abs().sum()) == 0 and float(sl[:, 40:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize('d', [256, 512, 768, 100])
+def test_layernorm_bwd(d):
+    g = torch.Generator().manual_seed(d)
+    M = 333
+    x = torch.randn(M, d, generator=g, dtype=torch.float64).requires_grad_(True)
+    gamma = (torch.rand(d, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True)
+    beta = torch.randn(d, generator=g, dtype=torch.float64).requires_grad_(True)
+    dy = torch.randn(M, d, generator=g, dtype=torch.float64)
+    torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5).backward(dy)
+    dg, db, ds = (torch.zeros(d, device=DEV) for _ in range(3))
+    dx, dx_lp = ob.layernorm_bwd(dy.float().to(DEV), x.detach().float().to(DEV), gamma.detach().float().to(DEV), dg, db, ds,
+                                 lp_kind=ops.LP_BF16)
+    assert _rel(dx, x.grad) < 2e-5 and _rel(dg, gamma.grad) < 2e-5 and _rel(db, beta.grad) < 2e-5
+    assert _rel(ds, x.grad.sum(0)) < 1e-4 * math.sqrt(M)
+    assert _rel(dx_lp.float(), x.grad) < 5e-3
+
+
+@pytest.mark.parametrize('bias_mode', ['none', 'rank1', 'dense'])
+@pytest.mark.parametrize('N,heads', [(50, [171, 171, 170]), (77, [64, 40]), (130, [256])])
+def test_attn_bwd_f32(bias_mode, N, heads):
+    g = torch.Generator().manual_seed(N)
+    Bt, H, d = 2, len(heads), sum(heads)
+    nbox = N // 5 if (bias_mode == 'rank1' and N % 5 == 0) else N
+    qkv = (torch.randn(Bt * N, 3 * d, generator=g, dtype=torch.float64) * 0.5).requires_grad_(True)
+    a = torch.randn(Bt * nbox, H, generator=g, dtype=torch.float64).requires_grad_(True)
+    bpe = (torch.randn(H, generator=g, dtype=torch.float64) * 0.3).requires_grad_(True)
+    dense = torch.randn(Bt, N, N, H, generator=g, dtype=torch.float64).requires_grad_(True)
+    dout = torch.randn(Bt * N, d, generator=g, dtype=torch.float64)
+    c = 1.0 / math.sqrt(d)
+    outs, off = [], 0
+    q3, k3, v3 = (qkv[:, i * d:(i + 1) * d].view(Bt, N, d) for i in range(3))
+    for h, dh in enumerate(heads):
+        s = q3[..., off:off + dh] @ k3[..., off:off + dh].transpose(1, 2)
+        if bias_mode == 'rank1':
+            ai = a.view(Bt, nbox, H)[:, torch.arange(N) % nbox, h]
+            s = s + torch.relu(ai.unsqueeze(2) - ai.unsqueeze(1) + bpe[h])
+        elif bias_mode == 'dense':
+            s = s + dense[..., h]
+        outs.append(torch.softmax(s * c, -1) @ v3[..., off:off + dh])
+        off += dh
+    ref_out = torch.cat(outs, -1).view(Bt * N, d)
+    ref_out.backward(dout)
+    dq = qkv.detach().float().to(DEV)
+    kw = {}
+    da = dbpe = None
+    if bias_mode == 'rank1':
+        da, dbpe = torch.zeros(Bt * nbox, H, device=DEV), torch.zeros(H, device=DEV)
+        kw = dict(bias_mode=ops.BIAS_RANK1, a=a.detach().float().to(DEV), nbox=nbox, bpe=bpe.detach().float().to(DEV))
+    elif bias_mode == 'dense':
+        kw = dict(bias_mode=ops.BIAS_DENSE, dense=dense.detach().float().to(DEV))
+    lse = torch.empty(Bt * H * N, device=DEV)
+    o = ops.attn_fwd_f32(dq[:, :d], dq[:, d:2 * d], dq[:, 2 * d:], Bt, N, heads, c, lse=lse, **kw)
+    assert _rel(o, ref_out) < 1e-5
+    dqkv, dd = ob.attn_bwd_f32(dq[:, :d], dq[:, d:2 * d], dq[:, 2 * d:], o, dout.float().to(DEV), lse, Bt, N, heads, c,
+                               da=da, dbpe=dbpe, want_ddense=True, **kw)
+    assert _rel(dqkv, qkv.grad) < 2e-5
+    if bias_mode == 'rank1':
+        assert _rel(da, a.grad) < 1e-4 and _rel(dbpe, bpe.grad) < 1e-4
+    if bias_mode == 'dense':
+        assert _rel(dd, dense.grad) < 2e-5
+
+
+@pytest.mark.parametrize('lens', [[20, 20, 20, 20], [7, 20, 1, 13], [5]])
+def test_lstm_backward_building_blocks_match_nn_lstm(lens):
+    """recompute-gates + scan + per-step kernels + GEMMs == autograd through nn.LSTM on packed sequences."""
+    torch.manual_seed(len(lens))
+    T, Bq, E, Hh = 20, len(lens), 48, 64
+    lstm = torch.nn.LSTM(E, Hh, num_layers=1, bidirectional=True).double()
+    x = torch.randn(T, Bq, E, dtype=torch.float64, requires_grad=True)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(x, lens, enforce_sorted=False)
+    out, _ = lstm(packed)
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, total_length=T)
+    dout = torch.randn(T, Bq, 2 * Hh, dtype=torch.float64)
+    out.backward(dout)
+    f = lambda t: t.detach().float().to(DEV).contiguous()                               # noqa: E731
+    wih = f(torch.cat([lstm.weight_ih_l0, lstm.weight_ih_l0_reverse], 0))
+    bias = f(torch.cat([lstm.bias_ih_l0 + lstm.bias_hh_l0, lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse], 0))
+    whh = f(torch.stack([lstm.weight_hh_l0, lstm.weight_hh_l0_reverse], 0))
+    lens_d = torch.tensor(lens, device=DEV)
+    x2 = f(x).view(T * Bq, E)
+    gx = ops.sgemm_nt(x2, wih, bias)
+    hout = ops.lstm_layer_fwd(gx, whh, lens_d, T, Bq, ops.LP_NONE)
+    assert _rel(hout, out.view(T * Bq, 2 * Hh)) < 1e-5
+    hprev = ob.lstm_hprev(hout, lens_d, T, Bq)
+    G = gx.clone()
+    for d_ in range(2):
+        ob.sgemm(hprev[:, d_ * Hh:(d_ + 1) * Hh], whh[d_].t(), out=G[:, d_ * 4 * Hh:(d_ + 1) * 4 * Hh], accumulate=True)
+    acts = ob.lstm_scan(G, lens_d, T, Bq)
+    dG = ob.lstm_bwd_steps(f(dout).view(T * Bq, 2 * Hh), acts, whh, lens_d, T, Bq)
+    dx = ob.sgemm(dG, wih)
+    assert _rel(dx, x.grad.view(T * Bq, E)) < 1e-4
+    dwih = ob.sgemm(dG.t(), x2)
+    ref_wih = torch.cat([lstm.weight_ih_l0.grad, lstm.weight_ih_l0_reverse.grad], 0)
+    assert _rel(dwih, ref_wih) < 1e-4
+    for d_, nm in enumerate(('weight_hh_l0', 'weight_hh_l0_reverse')):
+        dwhh = ob.sgemm(dG[:, d_ * 4 * Hh:(d_ + 1) * 4 * Hh].t(), hprev[:, d_ * Hh:(d_ + 1) * Hh])
+        assert _rel(dwhh, getattr(lstm, nm).grad) < 1e-4
+    db = torch.zeros(8 * Hh, device=DEV)
+    ob.colsum_acc(dG, db)
+    assert _rel(db, torch.cat([lstm.bias_ih_l0.grad, lstm.bias_ih_l0_reverse.grad], 0)) < 1e-4
+
+
+def test_lin2_xmul_seg_relu_glue_backward():
+    g = torch.Generator().manual_seed(5)
+    B, nfrm, nsrl, nppf2, K, dv, dl = 2, 3, 4, 7, 96, 32, 16
+    M = B * nfrm * nsrl * nppf2
+    h = torch.relu(torch.randn(M, K, generator=g, dtype=torch.float64)).requires_grad_(True)
+    w2 = torch.randn(K, generator=g, dtype=torch.float64).requires_grad_(True)
+    b2 = torch.zeros(1, dtype=torch.float64, requires_grad=True)
+    logits = (h @ w2 + b2).view(B, nfrm, nsrl, nppf2).transpose(1, 2).reshape(B, nsrl, nfrm * nppf2)
+    dlg = torch.randn(B, nsrl, nfrm * nppf2, generator=g, dtype=torch.float64)
+    logits.backward(dlg)
+    dw2, db2, db1 = torch.zeros(K, device=DEV), torch.zeros(1, device=DEV), torch.zeros(K, device=DEV)
+    dh, dh_lp = ob.lin2_bwd(dlg.float().to(DEV), h.detach().float().to(DEV), w2.detach().float().to(DEV), dw2, db2, db1,
+                            nfrm, nsrl, nppf2, lp_kind=ops.LP_BF16)
+    mask = (h.detach() > 0).double()
+    assert _rel(dh, h.grad * mask) < 1e-5 and _rel(dw2, w2.grad) < 1e-5 and _rel(db2, b2.grad) < 1e-5
+    assert _rel(db1, (h.grad * mask).sum(0)) < 1e-5 and _rel(dh_lp.float(), h.grad * mask) < 5e-3
+    # token factors
+    vis = torch.randn(B * nfrm * nppf2, dv, generator=g, dtype=torch.float64, requires_grad=True)
+    lang = torch.randn(B * nsrl, dl, generator=g, dtype=torch.float64, requires_grad=True)
+    tok = torch.cat([vis.view(B, nfrm, 1, nppf2, dv).expand(B, nfrm, nsrl, nppf2, dv),
+                     lang.view(B, 1, nsrl, 1, dl).expand(B, nfrm, nsrl, nppf2, dl)], -1).reshape(M, dv + dl)
+    dtok = torch.randn(M, dv + dl, generator=g, dtype=torch.float64)
+    tok.backward(dtok)
+    dlang = torch.zeros(B * nsrl, dl, device=DEV)
+    dvis = ob.xmul_bwd(dtok.float().to(DEV), dlang, B, nfrm, nsrl, nppf2, dv)
+    assert _rel(dvis, vis.grad) < 1e-5 and _rel(dlang, lang.grad) < 1e-5
+    # replicated segment half
+    nslots, nppf, pe, se = 6, 5, 8, 12
+    seg = torch.randn(nslots, se, generator=g, dtype=torch.float64, requires_grad=True)
+    x = torch.cat([torch.zeros(nslots, nppf, pe, dtype=torch.float64),
+                   torch.relu(seg).unsqueeze(1).expand(nslots, nppf, se)], -1).reshape(nslots * nppf, pe + se)
+    dx = torch.randn(nslots * nppf, pe + se, generator=g, dtype=torch.float64)
+    x.backward(dx)
+    dseg = ob.seg_rep_bwd(dx.float().to(DEV), x.detach().float().to(DEV), pe, se, nppf)
+    assert _rel(dseg, seg.grad) < 1e-5
+    # relu backward with bias gradient, bf16 activations
+    act = torch.relu(torch.randn(100, 40, generator=g)).to(DEV)
+    dy = torch.randn(100, 40, generator=g).to(DEV)
+    dbias = torch.zeros(40, device=DEV)
+    o, o_lp = ob.relu_bwd(dy, act.bfloat16(), dbias=dbias, lp_kind=ops.LP_TF32)
+    refg = dy * (act.bfloat16() > 0)
+    assert torch.equal(o, refg) and _rel(dbias, refg.sum(0)) < 1e-5 and _rel(o_lp, refg) < 1e-3

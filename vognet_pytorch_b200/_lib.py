@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libvog_b200.so')
 SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'lstm_rec.cu', 'fused_glue.cu', 'loss_fwd.cu',
-           'relayout.cu', 'optim.cu']
+           'relayout.cu', 'optim.cu', 'train_f32.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -23,63 +23,37 @@ _lib = None
 c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64
 P = c_void_p
 
-# name -> argtypes (restype is int unless listed in _RESTYPE)
-_SIGNATURES = {
-    'vog_last_error': [],
-    'vog_abi_version': [],
-    'vog_launch_count': [],
-    'vog_device_is_sm100': [],
-    'vog_sgemm_nt': [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P],
-    'vog_attn_fwd_f32': [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, c_float, c_int, P,
-                         c_int, P, P, P],
-    'vog_add_layernorm': [P, c_int, P, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,
-                          c_float, P],
-    'vog_pe_project': [P, c_int, P, P, c_int, c_int, c_float, c_float, c_float, c_float, P],
-    'vog_select_fwd': [P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
-    'vog_select_sep_fwd': [P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
-    'vog_sep_fin_scores': [P, P, P, P, P, P, P, c_int, c_int, c_int, P],
-    'vog_adam_step': [P, P, P, P, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_i64,
-                      ctypes.c_double, P],
-    'vog_verb_loss_fwd': [P, P, P, c_int, c_int, c_float, P, P],
-    'vog_concat_videos': [P, c_int, P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
-    'vog_cast_lp': [P, c_i64, P, c_i64, c_i64, c_int, c_int, P],
-    'vog_tc_gemm_workspace_bytes': [c_int, c_int, c_int, c_int, c_int],
-    'vog_tc_gemm': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64,
-                    P, c_i64, P, c_i64, c_int, c_int, P, c_i64, P],
-    'vog_build_xmul': [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
-    'vog_lin2_tail': [P, c_int, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
-    'vog_lang_embed': [P, c_int, P, c_int, P, c_int, c_i64, c_int, P, c_int, P],
-    'vog_lang_gather': [P, c_int, P, c_int, c_int, c_int, P, c_int, P],
-    'vog_mask_rows': [P, P, c_int, c_int, P, P, c_int, P],
-    'vog_loss_workspace_bytes': [c_int, c_int, c_int],
-    'vog_loss_bwd': [P, P, P, P, P, c_int, c_int, c_int, P],
-    'vog_loss_fwd': [P, P, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                     c_float, P, P, P, P],
-    'vog_lstm_set_max_ctas': [c_int],
-    'vog_set_reserved_sms': [c_int],
-    'vog_lstm_workspace_bytes': [c_int, c_int],
-    'vog_debug_lstm_force_streaming': [c_int],
-    'vog_debug_gemm_trace': [P],
-    'vog_debug_lstm_trace': [P],
-    'vog_debug_lstm_exchange': [c_int],
-    'vog_debug_attn_prof': [P],
-    'vog_debug_attn_impl': [c_int],
-    'vog_debug_attn_cluster': [c_int],
-    'vog_lstm_layer_fwd': [P, c_i64, P, P, c_int, c_int, c_int, P, c_i64, c_int, P, P],
-    'vog_tc_attn_workspace_bytes': [c_int, c_int, c_int],
-    'vog_tc_attn_fwd': [P, P, P, c_int, c_int, c_int, c_int, P, c_float, c_int, P, c_int, P, P, P,
-                        c_i64, c_int, P, c_i64, P],
-    'vog_tc_gemm_qkv_factored': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_i64, c_int, c_int,
-                                 c_int, P, P, P, P],
-    'vog_tc_gemm_lin2': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int,
-                         c_int, c_int, c_int, c_int, c_int, P],
-    'vog_tc_gemm_gres': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_i64, P, c_i64,
-                         c_int, c_int, c_int, c_int, P, c_i64, P, c_i64, c_int, P],
-    'vog_tc_gemm_qkv': [P, c_i64, P, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
-}
-_RESTYPE = {'vog_last_error': ctypes.c_char_p, 'vog_launch_count': ctypes.c_longlong,
-            'vog_tc_gemm_workspace_bytes': ctypes.c_int64, 'vog_lstm_workspace_bytes': ctypes.c_int64,
-            'vog_tc_attn_workspace_bytes': ctypes.c_int64, 'vog_loss_workspace_bytes': ctypes.c_int64}
+HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'vog_b200.h')
+_CTYPE = {'int': c_int, 'int64_t': c_i64, 'float': c_float, 'double': ctypes.c_double, 'void': None,
+          'long long': ctypes.c_longlong}
+
+
+def _parse_header(path=HEADER):
+    """The C ABI is declared ONCE, in include/vog_b200.h; the ctypes prototypes are derived from those declarations
+    (pointer -> void*, int / int64_t / float / double by value), so binding and header cannot drift apart."""
+    import re
+    hdr = re.sub(r'/\*.*?\*/', ' ', open(path).read(), flags=re.S)
+    sigs, res = {}, {}
+    for ret, name, args in re.findall(r'\b(const char\s*\*|long long|int64_t|int|void)\s+(vog_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;',
+                                      hdr, flags=re.S):
+        args = ' '.join(args.split())
+        params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+        at = []
+        for prm in params:
+            if '*' in prm:
+                at.append(c_void_p)
+            else:
+                base = prm.replace('const ', '').replace('unsigned ', '')
+                base = 'long long' if base.startswith('long long') else base.split()[0]
+                at.append(_CTYPE[base])
+        sigs[name] = at
+        ret = ' '.join(ret.split())
+        res[name] = ctypes.c_char_p if '*' in ret else (_CTYPE[ret] if ret != 'int' else c_int)
+    return sigs, res
+
+
+# name -> argtypes / restype
+_SIGNATURES, _RESTYPE = _parse_header()
 
 
 def sources():
@@ -124,7 +98,7 @@ def lib():
             for name, argtypes in _SIGNATURES.items():
                 fn = getattr(l, name)          # AttributeError if the symbol is not exported
                 fn.argtypes = argtypes
-                fn.restype = _RESTYPE.get(name, c_int)
+                fn.restype = _RESTYPE[name]
             _lib = l
     return _lib
 

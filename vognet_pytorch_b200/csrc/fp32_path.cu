@@ -100,6 +100,7 @@ struct AttnF32Params {
     const float* a; int nbox;   // mode 1: a [Bt*nbox, H]
     const float* bpe;           // mode 1: device [H]
     const float* dense;         // mode 2
+    float* lse;                 // optional [Bt,H,N]: log-sum-exp of the scaled scores (saved for the backward)
 };
 
 template <int KPT>   // accumulator columns per thread: dh <= 8*KPT
@@ -221,7 +222,11 @@ attn_f32_kernel(const AttnF32Params p)
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) linv_s[warp * 4 + r] = 1.f / l_run[r];
+        for (int r = 0; r < 4; ++r) {
+            linv_s[warp * 4 + r] = 1.f / l_run[r];
+            const int gr = q0 + warp * 4 + r;
+            if (p.lse && gr < N) p.lse[((size_t)bt * p.H + h) * N + gr] = m_run[r] + logf(l_run[r]);
+        }
     }
     __syncthreads();
     int gi = q0 + orow;
@@ -238,7 +243,7 @@ attn_f32_kernel(const AttnF32Params p)
 int attn_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
              int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
              int bias_mode, const float* a, int nbox, const float* bpe, const float* dense,
-             cudaStream_t st)
+             cudaStream_t st, float* lse)
 {
     VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS, "attn_f32: H=%d out of range (max %d)", H, VOG_MAX_HEADS);
     VOG_REQUIRE(Bt <= 65535, "attn_f32: Bt=%d exceeds grid.z", Bt);
@@ -246,7 +251,7 @@ int attn_f32(const float* q, const float* k, const float* v, int ld, float* out,
     AttnF32Params p;
     p.q = q; p.k = k; p.v = v; p.ld = ld; p.out = out; p.ldo = ldo;
     p.Bt = Bt; p.N = N; p.H = H; p.inv_scale = inv_scale;
-    p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.dense = dense; p.bpe = bpe;
+    p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.dense = dense; p.bpe = bpe; p.lse = lse;
     int dhmax = 0;
     for (int h = 0; h < H; ++h) {
         p.off[h] = off[h]; p.dh[h] = dh[h];

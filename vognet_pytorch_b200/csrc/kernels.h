@@ -15,7 +15,7 @@ int sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias
 int attn_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
              int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
              int bias_mode, const float* a, int nbox, const float* bpe, const float* dense,
-             cudaStream_t st);
+             cudaStream_t st, float* lse = nullptr);
 int add_layernorm(const float* x, int ldx, const float* r, int ldr, const float* w, const float* b,
                   float* out, int ldo, void* out_lp, int ldlp, int lp_kind, int M, int d, float eps,
                   cudaStream_t st);
@@ -107,6 +107,38 @@ int lang_gather(const float* full, int D, const long long* cap, int T, int Bq, i
                 cudaStream_t st);
 int mask_rows(const float* x, const long long* msk, int rows, int D, float* out, void* out_lp, int lp_kind,
               cudaStream_t st);
+
+// ---- train_f32.cu : backward kernels (exact fp32 + element-wise kernels shared by every compute mode) ----------
+int sgemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
+                  const float* bias, float* C, long long ldc, int M, int N, int K, int relu, int accumulate,
+                  cudaStream_t st);
+int colsum_acc(const float* x, long long ldx, float* out, long long M, int N, cudaStream_t st);
+int relu_bwd(const float* dy, long long ldy, const void* act, long long lda, int act_kind, float* out, long long ldo,
+             void* out_lp, long long ldlp, int lp_kind, float* dbias, long long M, int N, cudaStream_t st);
+int layernorm_bwd(const float* dy, long long ldy, const float* x, long long ldx, const float* gamma, float* dx,
+                  long long lddx, void* dx_lp, long long ldlp, int lp_kind, float* dgamma, float* dbeta, float* dxsum,
+                  long long M, int d, float eps, cudaStream_t st);
+int attn_bwd_f32(const float* q, const float* k, const float* v, long long ld, const float* out, long long ldo,
+                 const float* dout, long long lddo, const float* lse, float* delta, float* dq, float* dk, float* dv,
+                 long long ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
+                 const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe, float* ddense,
+                 cudaStream_t st);
+int pe_project_bwd(const float* props, int ldp, const float* da, float* dW, int rows, int H, float vw, float vh,
+                   float fdiv, cudaStream_t st);
+int xmul_bwd(const float* dtok, float* dvis, float* dlang, int B, int nfrm, int nsrl, int nppf2, int dv, int dl,
+             cudaStream_t st);
+int seg_rep_bwd(const float* dx, const float* x, int ld, int pe, int se, int nppf, float* dseg, long long nslots,
+                cudaStream_t st);
+int lin2_bwd(const float* dlogits, const void* h, long long ldh, int h_kind, const float* w2, float* dh, void* dh_lp,
+             int lp_kind, float* dw2, float* db2, float* db1, long long M, int K, int nfrm, int nsrl, int nppf2,
+             cudaStream_t st);
+int lang_gather_bwd(const float* dcat, int D, const long long* cap, int T, int Bq, int nsrl, float* dfull, cudaStream_t st);
+int lang_embed_bwd(const long long* words, int nwords, const long long* mask, int T, const float* dx, int E,
+                   long long pad_idx, int Bq, const long long* lens, float* demb, cudaStream_t st);
+int lstm_hprev(const float* hout, const long long* lens, float* hprev, int T, int Bq, int H, cudaStream_t st);
+int lstm_scan(const float* G, const long long* lens, float* acts, int T, int Bq, int H, cudaStream_t st);
+int lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const long long* lens, float* dG,
+                   float* carry_ws, int T, int Bq, int H, cudaStream_t st);
 
 // ---- loss_fwd.cu : grounding loss, forward ----------------------------------------------------
 long long loss_workspace_bytes(int B, int nsrl, int P);

@@ -43,7 +43,8 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 
 __device__ __forceinline__ void store_lp(void* base, long long idx, float v, int kind) {
     if (kind == 1) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(base)[idx] = to_tf32(v);
+    else if (kind == 2) reinterpret_cast<float*>(base)[idx] = to_tf32(v);
+    else reinterpret_cast<float*>(base)[idx] = v;          // kind 0: exact fp32 (training keeps the states for the backward)
 }
 
 __global__ void __launch_bounds__(LS_THREADS, 1)
@@ -537,7 +538,7 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
     if (T == 0 || Bq == 0) return 0;
     VOG_REQUIRE(Bq <= LS_MAXB, "lstm_layer_fwd: at most %d sequences per call (got %d)", LS_MAXB, Bq);
     VOG_REQUIRE(H % 4 == 0 && H >= 4 && H <= 1024, "lstm_layer_fwd: H must be a multiple of 4, <= 1024");
-    VOG_REQUIRE(lp_kind == 1 || lp_kind == 2, "lstm_layer_fwd: bad lp_kind");
+    VOG_REQUIRE(lp_kind >= 0 && lp_kind <= 2, "lstm_layer_fwd: bad lp_kind");
     VOG_REQUIRE(ldg >= 8LL * H && ld_out >= 2LL * H, "lstm_layer_fwd: bad leading dimension");
     VOG_REQUIRE((reinterpret_cast<uintptr_t>(whh) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                 "lstm_layer_fwd: whh and workspace must be 16-byte aligned");
@@ -594,7 +595,7 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
                    int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st)
 {
-    VOG_REQUIRE(lp_kind == 1 || lp_kind == 2, "lstm_layer_fwd: bad lp_kind");
+    VOG_REQUIRE(lp_kind >= 0 && lp_kind <= 2, "lstm_layer_fwd: bad lp_kind");
     const size_t esz = lp_kind == 1 ? 2 : 4;
     for (int b0 = 0; b0 < Bq; b0 += LS_MAXB) {
         const int nb = Bq - b0 < LS_MAXB ? Bq - b0 : LS_MAXB;

@@ -39,7 +39,7 @@ using namespace vog;
 extern "C" {
 
 const char* vog_last_error(void) { return g_err; }
-int vog_abi_version(void) { return 1; }
+int vog_abi_version(void) { return 2; }
 long long vog_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int vog_device_is_sm100(void)
@@ -64,14 +64,14 @@ int vog_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* 
 int vog_attn_fwd_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
                      int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
                      int bias_mode, const float* a, int nbox, const float* bpe,
-                     const float* dense, void* stream)
+                     const float* dense, float* lse, void* stream)
 {
     VOG_REQUIRE(q && k && v && out && off && dh, "vog_attn_fwd_f32: null operand");
     VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_attn_fwd_f32: negative dimension");
     VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_attn_fwd_f32: bad bias_mode %d", bias_mode);
     VOG_REQUIRE(bias_mode != VOG_BIAS_RANK1 || nbox > 0, "vog_attn_fwd_f32: nbox must be > 0");
     return attn_f32(q, k, v, ld, out, ldo, Bt, N, H, off, dh, inv_scale, bias_mode, a, nbox, bpe,
-                    dense, (cudaStream_t)stream);
+                    dense, (cudaStream_t)stream, lse);
 }
 
 int vog_add_layernorm(const float* x, int ldx, const float* r, int ldr, const float* w,
@@ -349,7 +349,7 @@ int vog_lang_gather(const float* full, int D, const int64_t* cap, int T, int Bq,
     VOG_REQUIRE(T > 0 && Bq >= 0 && nsrl >= 0 && D > 0, "vog_lang_gather: bad dimension");
     if (Bq * nsrl == 0) return 0;
     VOG_REQUIRE(full && cap && out_lp, "vog_lang_gather: null operand");
-    VOG_REQUIRE(lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_lang_gather: bad lp_kind");
+    VOG_REQUIRE(lp_kind == 0 || lp_kind == VOG_LP_BF16 || lp_kind == VOG_LP_TF32, "vog_lang_gather: bad lp_kind");
     return lang_gather(full, D, (const long long*)cap, T, Bq, nsrl, out_lp, lp_kind, (cudaStream_t)stream);
 }
 
@@ -390,6 +390,139 @@ int vog_loss_fwd(const float* logits, const float* props, int pdim, const float*
     return loss_fwd(logits, props, pdim, gt, frm_mask, pnt_mask, (const long long*)srl_boxes, (const long long*)srl_lens,
                     (const long long*)arg_boxes_mask, (const long long*)cmp_msk, (const long long*)target_cmp, B, nsrl,
                     nb, P, K, ncmp, nppf, spat, loss_lambda, targets, workspace, loss, (cudaStream_t)stream);
+}
+
+// ---- training step: backward entry points (train_f32.cu) ------------------------------------------------------
+int vog_sgemm_strided(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn,
+                      const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, int accumulate,
+                      void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "vog_sgemm_strided: negative dimension");
+    if (M == 0 || N == 0) return 0;
+    VOG_REQUIRE(A && B && C && ldc >= N, "vog_sgemm_strided: null operand / bad ldc");
+    return sgemm_strided(A, sam, sak, B, sbk, sbn, bias, C, ldc, M, N, K, relu, accumulate, (cudaStream_t)stream);
+}
+
+int vog_colsum_acc(const float* x, int64_t ldx, float* out, int64_t M, int N, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N >= 0, "vog_colsum_acc: negative dimension");
+    if (M == 0 || N == 0) return 0;
+    VOG_REQUIRE(x && out && ldx >= N, "vog_colsum_acc: null operand / bad ldx");
+    return colsum_acc(x, ldx, out, M, N, (cudaStream_t)stream);
+}
+
+int vog_relu_bwd(const float* dy, int64_t ldy, const void* act, int64_t lda, int act_kind, float* out, int64_t ldo,
+                 void* out_lp, int64_t ldlp, int lp_kind, float* dbias, int64_t M, int N, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N >= 0, "vog_relu_bwd: negative dimension");
+    if (M == 0 || N == 0) return 0;
+    VOG_REQUIRE(dy && act && (out || out_lp || dbias), "vog_relu_bwd: null operand");
+    VOG_REQUIRE(!out_lp || (lp_kind >= 0 && lp_kind <= 2), "vog_relu_bwd: bad lp_kind");
+    return relu_bwd(dy, ldy, act, lda, act_kind, out, ldo, out_lp, ldlp, lp_kind, dbias, M, N, (cudaStream_t)stream);
+}
+
+int vog_layernorm_bwd(const float* dy, int64_t ldy, const float* x, int64_t ldx, const float* gamma, float* dx,
+                      int64_t lddx, void* dx_lp, int64_t ldlp, int lp_kind, float* dgamma, float* dbeta, float* dxsum,
+                      int64_t M, int d, float eps, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && d > 0, "vog_layernorm_bwd: bad dimension");
+    if (M == 0) return 0;
+    VOG_REQUIRE(dy && x && gamma && dgamma && dbeta, "vog_layernorm_bwd: null operand");
+    VOG_REQUIRE(!dx_lp || (lp_kind >= 0 && lp_kind <= 2), "vog_layernorm_bwd: bad lp_kind");
+    return layernorm_bwd(dy, ldy, x, ldx, gamma, dx, lddx, dx_lp, ldlp, lp_kind, dgamma, dbeta, dxsum, M, d, eps,
+                         (cudaStream_t)stream);
+}
+
+int vog_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ld, const float* out, int64_t ldo,
+                     const float* dout, int64_t lddo, const float* lse, float* delta, float* dq, float* dk, float* dv,
+                     int64_t ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
+                     const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe,
+                     float* ddense, void* stream)
+{
+    VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_attn_bwd_f32: negative dimension");
+    if (Bt == 0 || N == 0) return 0;
+    VOG_REQUIRE(q && k && v && out && dout && lse && delta && dq && dk && dv && off && dh, "vog_attn_bwd_f32: null operand");
+    VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_attn_bwd_f32: bad bias_mode %d", bias_mode);
+    return attn_bwd_f32(q, k, v, ld, out, ldo, dout, lddo, lse, delta, dq, dk, dv, ldg, Bt, N, H, off, dh, inv_scale,
+                        bias_mode, a, nbox, bpe, dense, da, dbpe, ddense, (cudaStream_t)stream);
+}
+
+int vog_pe_project_bwd(const float* props, int ldp, const float* da, float* dW, int rows, int H, float vid_w,
+                       float vid_h, float fdiv, void* stream)
+{
+    VOG_REQUIRE(rows >= 0, "vog_pe_project_bwd: negative dimension");
+    if (rows == 0) return 0;
+    VOG_REQUIRE(props && da && dW && ldp >= 5, "vog_pe_project_bwd: null operand / bad ldp");
+    return pe_project_bwd(props, ldp, da, dW, rows, H, vid_w, vid_h, fdiv, (cudaStream_t)stream);
+}
+
+int vog_xmul_bwd(const float* dtok, float* dvis, float* dlang, int B, int nfrm, int nsrl, int nppf2, int dv, int dl,
+                 void* stream)
+{
+    VOG_REQUIRE(B >= 0 && nfrm >= 0 && nsrl >= 0 && nppf2 >= 0, "vog_xmul_bwd: negative dimension");
+    if ((long long)B * nfrm * nsrl * nppf2 == 0) return 0;
+    VOG_REQUIRE(dtok && dvis && dlang, "vog_xmul_bwd: null operand");
+    return xmul_bwd(dtok, dvis, dlang, B, nfrm, nsrl, nppf2, dv, dl, (cudaStream_t)stream);
+}
+
+int vog_seg_rep_bwd(const float* dx, const float* x, int ld, int pe, int se, int nppf, float* dseg, int64_t nslots,
+                    void* stream)
+{
+    VOG_REQUIRE(nslots >= 0 && nppf >= 1, "vog_seg_rep_bwd: bad dimension");
+    if (nslots == 0) return 0;
+    VOG_REQUIRE(dx && x && dseg && ld >= pe + se, "vog_seg_rep_bwd: null operand / bad ld");
+    return seg_rep_bwd(dx, x, ld, pe, se, nppf, dseg, nslots, (cudaStream_t)stream);
+}
+
+int vog_lin2_bwd(const float* dlogits, const void* h, int64_t ldh, int h_kind, const float* w2, float* dh, void* dh_lp,
+                 int lp_kind, float* dw2, float* db2, float* db1, int64_t M, int K, int nfrm, int nsrl, int nppf2,
+                 void* stream)
+{
+    VOG_REQUIRE(M >= 0, "vog_lin2_bwd: negative dimension");
+    if (M == 0) return 0;
+    VOG_REQUIRE(dlogits && h && w2 && dw2 && db2 && db1 && (dh || dh_lp), "vog_lin2_bwd: null operand");
+    VOG_REQUIRE(nfrm > 0 && nsrl > 0 && nppf2 > 0 && M % ((long long)nfrm * nsrl * nppf2) == 0, "vog_lin2_bwd: bad geometry");
+    return lin2_bwd(dlogits, h, ldh, h_kind, w2, dh, dh_lp, lp_kind, dw2, db2, db1, M, K, nfrm, nsrl, nppf2,
+                    (cudaStream_t)stream);
+}
+
+int vog_lang_gather_bwd(const float* dcat, int D, const int64_t* cap, int T, int Bq, int nsrl, float* dfull,
+                        void* stream)
+{
+    if (Bq * nsrl == 0) return 0;
+    VOG_REQUIRE(dcat && cap && dfull, "vog_lang_gather_bwd: null operand");
+    return lang_gather_bwd(dcat, D, (const long long*)cap, T, Bq, nsrl, dfull, (cudaStream_t)stream);
+}
+
+int vog_lang_embed_bwd(const int64_t* words, int nwords, const int64_t* mask, int T, const float* dx, int E,
+                       int64_t pad_idx, int Bq, const int64_t* lens, float* demb, void* stream)
+{
+    if (T * Bq == 0) return 0;
+    VOG_REQUIRE(words && mask && dx && demb, "vog_lang_embed_bwd: null operand");
+    return lang_embed_bwd((const long long*)words, nwords, (const long long*)mask, T, dx, E, pad_idx, Bq,
+                          (const long long*)lens, demb, (cudaStream_t)stream);
+}
+
+int vog_lstm_hprev(const float* hout, const int64_t* lens, float* hprev, int T, int Bq, int H, void* stream)
+{
+    if (T * Bq == 0) return 0;
+    VOG_REQUIRE(hout && lens && hprev && H > 0, "vog_lstm_hprev: null operand");
+    return lstm_hprev(hout, (const long long*)lens, hprev, T, Bq, H, (cudaStream_t)stream);
+}
+
+int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int Bq, int H, void* stream)
+{
+    if (T * Bq == 0) return 0;
+    VOG_REQUIRE(G && lens && acts && H > 0, "vog_lstm_scan: null operand");
+    return lstm_scan(G, (const long long*)lens, acts, T, Bq, H, (cudaStream_t)stream);
+}
+
+int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const int64_t* lens, float* dG,
+                       float* carry_ws, int T, int Bq, int H, void* stream)
+{
+    if (T * Bq == 0) return 0;
+    VOG_REQUIRE(dout && acts && whh && lens && dG && carry_ws && H > 0, "vog_lstm_bwd_steps: null operand");
+    return lstm_bwd_steps(dout, acts, whh, (const long long*)lens, dG, carry_ws, T, Bq, H, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -102,6 +102,8 @@ class VOGNetB200(nn.Module):
 
         self.compute = 'fp32x'
         self.use_cuda_graph = False
+        # training: False runs the training forward without dropout (deterministic; what the gradient-parity tests use)
+        self.train_dropout = True
 
     @staticmethod
     def _make_tx(d, tx_cfg):
@@ -232,12 +234,15 @@ class VOGNetB200(nn.Module):
         return ncmp * self.num_sampled_frm, self.num_prop_per_frm      # 'sep' arrives here with ncmp = 1
 
     def forward(self, inp):
-        if self.training:
-            raise NotImplementedError('vognet_pytorch_b200: forward-only build; call .eval()')
         feat = inp['pad_region_feature']
         if not feat.is_cuda:
             raise RuntimeError('vognet_pytorch_b200 runs on CUDA only (no CPU path); move the batch '
                                'and the module to a B200 device')
+        if self.training and feat.shape[0] > 0:
+            # the training step (utils/trn_utils.py:497-505): one autograd node whose backward is the hand-written
+            # kernel chain of vognet_pytorch_b200.training
+            from . import training
+            return training.forward_train(self, inp)
         sep = self.CONC_TYPE == 'sep'
         if feat.shape[0] == 0:                       # empty batch: nothing to launch
             nsrl = inp['srl_arg_words_ind'].shape[2]
@@ -525,7 +530,11 @@ class VOGNetB200(nn.Module):
         # only if one had to move (shape / dtype change) are the graphs dropped and this one captured again.
         wsig = self._weights_sig()
         if g['wsig'] != wsig:
-            if self._refresh_packs():
+            # wsig[2] folds the parameters' own addresses: biases, LayerNorm weights, W_hh ... are read by the captured
+            # kernels straight from the parameter storage, so a parameter that moved (FlatAdam re-homing, .to(),
+            # p.data = ...) invalidates the capture itself
+            moved = g['wsig'][2] != wsig[2]
+            if self._refresh_packs() or moved:
                 self.__dict__['_graphs'] = {}
                 g = self._graph_for(inp, ncmp)
             g['wsig'] = wsig

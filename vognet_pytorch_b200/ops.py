@@ -74,8 +74,9 @@ def sgemm_nt(a, w, bias=None, residual=None, relu=False, out=None):
 
 
 def attn_fwd_f32(q, k, v, Bt, N, head_dims, inv_scale, out=None, bias_mode=BIAS_NONE, a=None,
-                 nbox=0, bpe=None, dense=None):
-    """q,k,v: [Bt*N, d] (row-major views, same ld); heads are consecutive column chunks."""
+                 nbox=0, bpe=None, dense=None, lse=None):
+    """q,k,v: [Bt*N, d] (row-major views, same ld); heads are consecutive column chunks.  ``lse`` (optional
+    [Bt,H,N] fp32) receives the log-sum-exp of the scaled scores for the backward."""
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
         _req(t, torch.float32, n, 2)
     ld = _rowmajor2d(q, 'q')
@@ -100,7 +101,7 @@ def attn_fwd_f32(q, k, v, Bt, N, head_dims, inv_scale, out=None, bias_mode=BIAS_
     L = _lib.lib()
     _lib.check(L.vog_attn_fwd_f32(_ptr(q), _ptr(k), _ptr(v), ld, _ptr(out), _rowmajor2d(out, 'out'),
                                   Bt, N, H, off_arr, dh_arr, float(inv_scale), bias_mode, _ptr(a),
-                                  nbox, _ptr(bpe), _ptr(dense), _stream()), 'vog_attn_fwd_f32')
+                                  nbox, _ptr(bpe), _ptr(dense), _ptr(lse), _stream()), 'vog_attn_fwd_f32')
     return out
 
 
@@ -423,7 +424,7 @@ def lstm_layer_fwd(gx, whh, lens, T, Bq, kind):
     if whh.shape != (2, 4 * H, H) or not whh.is_contiguous() or gx.shape != (T * Bq, 8 * H):
         raise ValueError('lstm_layer_fwd: inconsistent shapes')
     L = _lib.lib()
-    out = torch.empty(T * Bq, 2 * H, device=gx.device, dtype=_LP_DTYPE[kind])
+    out = torch.empty(T * Bq, 2 * H, device=gx.device, dtype=_LP_DTYPE.get(kind, torch.float32))
     ws = torch.empty(L.vog_lstm_workspace_bytes(Bq, H), device=gx.device, dtype=torch.uint8)
     _lib.check(L.vog_lstm_layer_fwd(_ptr(gx), _rowmajor2d(gx, 'gx'), _ptr(whh), _ptr(lens), T, Bq, H,
                                     _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _stream()),
@@ -448,7 +449,7 @@ def lang_gather(full, cap, T, Bq, kind):
     _req(full, torch.float32, 'full', 2), _req(cap, torch.int64, 'cap', 3)
     full, cap = full.contiguous(), cap.contiguous()
     D, nsrl = full.shape[1], cap.shape[1]
-    out = torch.empty(Bq * nsrl, 2 * D, device=full.device, dtype=_LP_DTYPE[kind])
+    out = torch.empty(Bq * nsrl, 2 * D, device=full.device, dtype=_LP_DTYPE.get(kind, torch.float32))
     L = _lib.lib()
     _lib.check(L.vog_lang_gather(_ptr(full), D, _ptr(cap), T, Bq, nsrl, _ptr(out), kind, _stream()),
                'vog_lang_gather')
