@@ -365,6 +365,36 @@ int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int B
 int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const int64_t* lens, float* dG,
                        float* carry_ws, int T, int Bq, int H, void* stream);
 
+/* ---- training step on the tensor cores (compute mode 'bf16') ---------------------------------------------------
+ * vog_tc_attn_fwd_train: vog_tc_attn_fwd that also keeps lse [Bt,H,N] (log2-domain log-sum-exp of every score row -
+ * all the backward needs instead of the N x N probabilities) and applies dropout with probability drop_p to the
+ * probabilities after the softmax (code/transformer_code.py:153); the mask is a counter-based function of
+ * (seed, sequence, head, query, key) that vog_tc_attn_bwd regenerates.  Rank-1 bias or none. */
+int vog_tc_attn_fwd_train(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp, const int* dh,
+                          float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe, void* out,
+                          int64_t ldo, int out_kind, void* workspace, int64_t workspace_bytes, float* lse, float drop_p,
+                          uint64_t seed, void* stream);
+
+/* Attention backward on tcgen05 (recompute from lse): q,k,v [Bt,H,N,dhp] bf16 as written by vog_tc_gemm_qkv, o / dout
+ * [Bt*N, ld >= H*dhp] bf16 (forward output and its gradient, heads in padded slots), lse from the forward.  Writes
+ * dqkv [Bt*N, ldg >= 3*H*dhp] bf16: dQ | dK | dV in the row order of the packed Wq|Wk|Wv operand (column
+ * (which*H + h)*dhp + c).  Rank-1 bias: da [Bt*nbox, H] and dbpe [H] (fp32) are ACCUMULATED.  workspace:
+ * vog_tc_attn_bwd_workspace_bytes() bytes, 256-byte aligned (the bf16 probabilities and score gradients
+ * [Bt*H, Npad, Npad] live there between the kernels of this call).  Gradient of RelAttention / Attention
+ * (code/transformer_code.py:41-50,136-160) and of relu(Linear(5,H)(p_i - p_j)) (code/mdl_vog.py:477-488). */
+int64_t vog_tc_attn_bwd_workspace_bytes(int Bt, int N, int H);
+int vog_tc_attn_bwd(const void* q, const void* k, const void* v, const void* o, int64_t ldo, const void* dout,
+                    int64_t lddo, const float* lse, int Bt, int N, int H, int dhp, const int* dh, float inv_scale,
+                    int bias_mode, const float* a, int nbox, const float* bpe, void* dqkv, int64_t ldg, float* da,
+                    float* dbpe, void* workspace, int64_t workspace_bytes, float drop_p, uint64_t seed, void* stream);
+
+/* Weight gradient on tcgen05: C[N1,N2] (fp32, ldc) += A[K,N1]^T . B[K,N2], A / B bf16 row-major (the contraction
+ * index is the slow index of both: dY and X as the forward / backward kernels leave them; nothing is transposed in
+ * HBM).  C must be zero-initialised or hold a running gradient.  Replaces autograd's mm(dY^T, X) of every nn.Linear
+ * on the path (code/transformer_code.py:57-60,80-81,169-172,180,186; code/mdl_vog.py:202-207,224-230). */
+int vog_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int K, int N1, int N2, float* C,
+                   int64_t ldc, void* stream);
+
 /* ---- debug hooks (not part of the data path) ----------------------------------------------------
  * vog_debug_gemm_trace: device buffer of 8 int64 that receives clock64 stamps of CTA 0 of every
  * following vog_tc_gemm launch (entry, setup done, first TMA issued, first stage landed, last MMA

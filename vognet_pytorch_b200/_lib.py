@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libvog_b200.so')
 SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'lstm_rec.cu', 'fused_glue.cu', 'loss_fwd.cu',
-           'relayout.cu', 'optim.cu', 'train_f32.cu']
+           'relayout.cu', 'optim.cu', 'train_f32.cu', 'tc_gemm_tn.cu', 'tc_attn_bwd.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -24,7 +24,7 @@ c_int, c_float, c_void_p, c_i64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
 P = c_void_p
 
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'vog_b200.h')
-_CTYPE = {'int': c_int, 'int64_t': c_i64, 'float': c_float, 'double': ctypes.c_double, 'void': None,
+_CTYPE = {'int': c_int, 'int64_t': c_i64, 'uint64_t': ctypes.c_uint64, 'float': c_float, 'double': ctypes.c_double, 'void': None,
           'long long': ctypes.c_longlong}
 
 
@@ -70,16 +70,42 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> vognet_pytorch_b200/libvog_b200.so"""
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> vognet_pytorch_b200/libvog_b200.so.  One object per source
+    (csrc/_obj/, rebuilt only when the source or a header is newer), compiled in parallel, then linked."""
     if not force and not needs_build():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     extra = os.environ.get('VOG_NVCC_EXTRA', '').split()       # e.g. -DVOG_ATTN_PROFILE
-    cmd = ['nvcc'] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH] + sources()
+    objdir = os.path.join(CSRC, '_obj')
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
+    hdrs.append(HEADER)
+    t_hdr = max(os.path.getmtime(h) for h in hdrs if os.path.exists(h))
+    tag = os.path.join(objdir, 'flags.txt')
+    flags_now = ' '.join(NVCC_FLAGS + extra)
+    if force or not os.path.exists(tag) or open(tag).read() != flags_now:
+        for f in os.listdir(objdir):
+            os.remove(os.path.join(objdir, f))
+        open(tag, 'w').write(flags_now)
+    cflags = [f for f in NVCC_FLAGS if f != '-shared']
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + '.o')
+        if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), t_hdr):
+            return obj, ''
+        cmd = ['nvcc'] + cflags + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', obj, src]
+        r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n' + r.stdout + r.stderr)
+        return obj, r.stderr
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        res = list(ex.map(compile_one, sources()))
+    if verbose:
+        print(''.join(e for _, e in res))
+    cmd = ['nvcc', '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', SO_PATH] + [o for o, _ in res]
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
     return SO_PATH
 
 

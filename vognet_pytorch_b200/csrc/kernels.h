@@ -77,8 +77,18 @@ void tc_gemm_set_trace(long long* buf);  // debug: 8 clock64 stamps of CTA 0
 int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
             const float* dense, void* out, long long ldo, int out_kind, void* workspace,
-            long long workspace_bytes, cudaStream_t st);
+            long long workspace_bytes, cudaStream_t st, float* lse = nullptr, float drop_p = 0.f,
+            unsigned long long seed = 0);
 long long tc_attn_workspace_bytes(int Bt, int N, int H);
+// ---- tc_attn_bwd.cu : attention backward on the tensor cores ------------------------------------
+long long tc_attn_bwd_workspace_bytes(int Bt, int N, int H);
+int tc_attn_bwd(const void* q, const void* k, const void* v, const void* o, long long ldo, const void* dout, long long lddo,
+                const float* lse, int Bt, int N, int H, int dhp, const int* dh, float inv_scale, int bias_mode,
+                const float* a, int nbox, const float* bpe, void* dqkv, long long ldg, float* da, float* dbpe,
+                void* workspace, long long workspace_bytes, float drop_p, unsigned long long seed, cudaStream_t st);
+// ---- tc_gemm_tn.cu : C[N1,N2] += A[K,N1]^T . B[K,N2] (weight gradients) --------------------------
+int tc_gemm_tn(const void* A, long long lda, const void* B, long long ldb, int K, int N1, int N2, float* C,
+               long long ldc, cudaStream_t st);
 void tc_attn_set_impl(int impl);         // debug: 1 = Q/P via shared memory, 2 = Q/P in tensor memory (default)
 void tc_attn_set_cluster(int c);         // debug: force the v2 cluster size (0 = auto)
 void tc_attn_set_prof(long long* buf);   // debug: phase cycle counters of one softmax warp

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "philox.cuh"
 
 namespace vog {
 
@@ -51,6 +52,9 @@ struct AttnParams {
     int cluster;                // v2: CTAs (query tiles of one sequence/head) that share multicast K / V loads
     uint32_t tmem_cols;
     long long* prof;            // optional [8] phase cycle counters (block 0, first softmax warp)
+    float* lse;                 // optional [Bt*H, N]: log2-domain log-sum-exp of every row (kept for the backward; v2 kernel)
+    float drop_p;               // training: dropout on the probabilities (code/transformer_code.py:153), 0 = off
+    unsigned long long seed;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -780,6 +784,20 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             }
             l_run += (s0 + s1) + (s2 + s3);
             VOG_PROF(4)
+            if (p.drop_p > 0.f) {
+                // dropout AFTER the softmax: the row sum keeps every probability, the PV product only the kept ones,
+                // scaled by 1/(1-p); the mask is regenerated by the backward from the same counters
+                const float inv_keep = 1.f / (1.f - p.drop_p);
+                const uint32_t thr = drop_threshold16(p.drop_p);
+#pragma unroll
+                for (int c = 0; c < EL; c += 8) {
+                    uint32_t rnd[4];
+                    attn_rand16x8(p.seed, (uint32_t)bh, (uint32_t)qi, (uint32_t)(j * FA_BKV + part * EL + c), rnd);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        sv[c + e] = ((rnd[e >> 1] >> (16 * (e & 1))) & 0xffffu) >= thr ? sv[c + e] * inv_keep : 0.f;
+                }
+            }
             VOG_PROF(5)
             // P_j (bf16 pairs) overwrites S_j in place: this thread's EL probabilities -> EL/2 words at columns
             // part*EL/2 of buffer j&1.  Every S_j column was read (all threads of the row passed row_sync)
@@ -812,6 +830,7 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
         mbar_wait(pv_done((T - 1) & 1), (uint32_t)(((T - 1) >> 1) & 1));
         tc_fence_after();
         const float inv_l = 1.f / l_run;
+        if (p.lse != nullptr && part == 0 && row_ok) p.lse[(size_t)bh * N + qi] = m_run + log2f(l_run);
         const int n_pv = (dh + 15) & ~15;
         for (int c0 = part * ocols; c0 < (part + 1) * ocols; c0 += 16) {
             uint32_t o[16];
@@ -876,9 +895,11 @@ void tc_attn_set_prof(long long* buf) { g_attn_prof = buf; }
 int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp,
             const int* dh, float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe,
             const float* dense, void* out, long long ldo, int out_kind, void* workspace,
-            long long workspace_bytes, cudaStream_t st)
+            long long workspace_bytes, cudaStream_t st, float* lse, float drop_p, unsigned long long seed)
 {
     if (Bt == 0 || N == 0) return 0;
+    VOG_REQUIRE((lse == nullptr && drop_p == 0.f) || g_attn_impl >= 2, "tc_attn: lse / dropout need the v2 kernel");
+    VOG_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "tc_attn: dropout probability %f", (double)drop_p);
     VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS, "tc_attn: H=%d out of range", H);
     VOG_REQUIRE(dhp == 64 || dhp == 128 || dhp == 192 || dhp == 256, "tc_attn: dhp=%d must be 64/128/192/256", dhp);
     VOG_REQUIRE(Bt <= 65535 && H <= 65535, "tc_attn: grid too large");
@@ -897,6 +918,7 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
     p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.bpe = bpe; p.dense = dense;
     p.out = out; p.ldo = ldo; p.out_kind = out_kind;
     p.prof = g_attn_prof;
+    p.lse = lse; p.drop_p = drop_p; p.seed = seed;
     p.ak_seq = nullptr; p.ak_ld = round_up(N, FA_BKV);
     if (bias_mode == 1) {
         VOG_REQUIRE(workspace && workspace_bytes >= tc_attn_workspace_bytes(Bt, N, H) &&

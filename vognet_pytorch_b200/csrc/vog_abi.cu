@@ -283,6 +283,49 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* v, int Bt, int N, 
                    out_kind, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int vog_tc_attn_fwd_train(const void* q, const void* k, const void* v, int Bt, int N, int H, int dhp, const int* dh,
+                          float inv_scale, int bias_mode, const float* a, int nbox, const float* bpe, void* out,
+                          int64_t ldo, int out_kind, void* workspace, int64_t workspace_bytes, float* lse, float drop_p,
+                          uint64_t seed, void* stream)
+{
+    VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_tc_attn_fwd_train: negative dimension");
+    if (Bt == 0 || N == 0) return 0;
+    if (require_sm100("vog_tc_attn_fwd_train")) return -1;
+    VOG_REQUIRE(q && k && v && out && dh && lse, "vog_tc_attn_fwd_train: null operand");
+    VOG_REQUIRE(bias_mode == 0 || bias_mode == 1, "vog_tc_attn_fwd_train: bias_mode %d (rank-1 or none)", bias_mode);
+    return tc_attn(q, k, v, Bt, N, H, dhp, dh, inv_scale, bias_mode, a, nbox, bpe, nullptr, out, ldo, out_kind, workspace,
+                   workspace_bytes, (cudaStream_t)stream, lse, drop_p, (unsigned long long)seed);
+}
+
+int64_t vog_tc_attn_bwd_workspace_bytes(int Bt, int N, int H)
+{
+    if (Bt <= 0 || N <= 0 || H <= 0) return 0;
+    return tc_attn_bwd_workspace_bytes(Bt, N, H);
+}
+
+int vog_tc_attn_bwd(const void* q, const void* k, const void* v, const void* o, int64_t ldo, const void* dout,
+                    int64_t lddo, const float* lse, int Bt, int N, int H, int dhp, const int* dh, float inv_scale,
+                    int bias_mode, const float* a, int nbox, const float* bpe, void* dqkv, int64_t ldg, float* da,
+                    float* dbpe, void* workspace, int64_t workspace_bytes, float drop_p, uint64_t seed, void* stream)
+{
+    VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_tc_attn_bwd: negative dimension");
+    if (Bt == 0 || N == 0) return 0;
+    if (require_sm100("vog_tc_attn_bwd")) return -1;
+    VOG_REQUIRE(q && k && v && o && dout && lse && dqkv && dh, "vog_tc_attn_bwd: null operand");
+    return tc_attn_bwd(q, k, v, o, ldo, dout, lddo, lse, Bt, N, H, dhp, dh, inv_scale, bias_mode, a, nbox, bpe, dqkv, ldg,
+                       da, dbpe, workspace, workspace_bytes, drop_p, (unsigned long long)seed, (cudaStream_t)stream);
+}
+
+int vog_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int K, int N1, int N2, float* C,
+                   int64_t ldc, void* stream)
+{
+    VOG_REQUIRE(K >= 0 && N1 >= 0 && N2 >= 0, "vog_tc_gemm_tn: negative dimension");
+    if (K == 0 || N1 == 0 || N2 == 0) return 0;
+    if (require_sm100("vog_tc_gemm_tn")) return -1;
+    VOG_REQUIRE(A && B && C, "vog_tc_gemm_tn: null operand");
+    return tc_gemm_tn(A, lda, B, ldb, K, N1, N2, C, ldc, (cudaStream_t)stream);
+}
+
 int64_t vog_lstm_workspace_bytes(int Bq, int H) { return lstm_workspace_bytes(Bq, H); }
 
 /* SM partitioning between concurrent branches of one forward (host-side state read at launch / graph-capture time):

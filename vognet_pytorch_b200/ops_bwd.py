@@ -186,3 +186,77 @@ def lstm_bwd_steps(dout, acts, whh, lens, T, Bq):
     _lib.check(_lib.lib().vog_lstm_bwd_steps(_ptr(dout.contiguous()), _ptr(acts), _ptr(whh), _ptr(lens), _ptr(dG), _ptr(ws),
                                              T, Bq, H, _stream()), 'vog_lstm_bwd_steps')
     return dG
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core training step ('bf16')
+# ---------------------------------------------------------------------------------------------
+def _bf16_2d(t, name):
+    if t.dim() != 2 or not t.is_cuda or t.dtype != torch.bfloat16 or t.stride(1) != 1:
+        raise TypeError(f'{name}: expected a 2-D CUDA bfloat16 tensor with unit column stride')
+    return t.stride(0)
+
+
+def tc_gemm_tn(a, b, out=None):
+    """out[N1,N2] (fp32) += a[K,N1]^T @ b[K,N2]; a, b bf16 row-major views (vog_tc_gemm_tn).  out=None: fresh zeros."""
+    lda, ldb = _bf16_2d(a, 'a'), _bf16_2d(b, 'b')
+    K, N1 = a.shape
+    if b.shape[0] != K:
+        raise ValueError(f'tc_gemm_tn: a is {tuple(a.shape)} but b is {tuple(b.shape)}')
+    N2 = b.shape[1]
+    if out is None:
+        out = torch.zeros(N1, N2, device=a.device, dtype=torch.float32)
+    _req(out, torch.float32, 'out', 2)
+    _lib.check(_lib.lib().vog_tc_gemm_tn(_ptr(a), lda, _ptr(b), ldb, K, N1, N2, _ptr(out), _rowmajor2d(out, 'out'), _stream()),
+               'vog_tc_gemm_tn')
+    return out
+
+
+def tc_attn_fwd_train(q, k, v, N, head_dims, inv_scale, bias_mode=BIAS_NONE, a=None, nbox=0, bpe=None, drop_p=0.0, seed=0):
+    """q,k,v [Bt,H,N,dhp] bf16 -> (out [Bt*N, H*dhp] bf16, lse [Bt,H,N] fp32 in the log2 domain)."""
+    Bt, H, Nq, dhp = q.shape
+    if Nq != N or k.shape != q.shape or v.shape != q.shape or len(head_dims) != H:
+        raise ValueError('tc_attn_fwd_train: inconsistent shapes')
+    for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
+        _req(t, torch.bfloat16, n, 4)
+        if not t.is_contiguous():
+            raise ValueError(f'tc_attn_fwd_train: {n} must be contiguous')
+    out = torch.empty(Bt * N, H * dhp, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(Bt, H, N, device=q.device, dtype=torch.float32)
+    dh_arr = (ctypes.c_int * H)(*head_dims)
+    L = _lib.lib()
+    ws, ws_bytes = None, 0
+    if bias_mode == BIAS_RANK1:
+        _req(a, torch.float32, 'a', 2), _req(bpe, torch.float32, 'bpe', 1)
+        if a.shape != (Bt * nbox, H) or not a.is_contiguous():
+            raise ValueError(f'tc_attn_fwd_train: a must be contiguous [{Bt * nbox},{H}], got {tuple(a.shape)}')
+        ws_bytes = L.vog_tc_attn_workspace_bytes(Bt, N, H)
+        ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+    elif bias_mode != BIAS_NONE:
+        raise ValueError('tc_attn_fwd_train: rank-1 bias or none (a dense x_pe trains in the fp32x mode)')
+    _lib.check(L.vog_tc_attn_fwd_train(_ptr(q), _ptr(k), _ptr(v), Bt, N, H, dhp, dh_arr, float(inv_scale), bias_mode,
+                                       _ptr(a), nbox, _ptr(bpe), _ptr(out), H * dhp, LP_BF16, _ptr(ws), ws_bytes,
+                                       _ptr(lse), float(drop_p), int(seed), _stream()), 'vog_tc_attn_fwd_train')
+    return out, lse
+
+
+def tc_attn_bwd(q, k, v, out, dout, lse, N, head_dims, inv_scale, bias_mode=BIAS_NONE, a=None, nbox=0, bpe=None, da=None,
+                dbpe=None, drop_p=0.0, seed=0):
+    """-> dqkv [Bt*N, 3*H*dhp] bf16 (dQ | dK | dV, padded head slots); da [Bt*nbox,H] / dbpe [H] accumulated."""
+    Bt, H, Nq, dhp = q.shape
+    ldo, lddo = _bf16_2d(out, 'out'), _bf16_2d(dout, 'dout')
+    dqkv = torch.empty(Bt * N, 3 * H * dhp, device=q.device, dtype=torch.bfloat16)
+    L = _lib.lib()
+    ws_bytes = L.vog_tc_attn_bwd_workspace_bytes(Bt, N, H)
+    ws = torch.empty(ws_bytes + 256, device=q.device, dtype=torch.uint8)
+    off = (-ws.data_ptr()) % 256
+    dh_arr = (ctypes.c_int * H)(*head_dims)
+    if bias_mode == BIAS_RANK1:
+        _req(da, torch.float32, 'da', 2), _req(dbpe, torch.float32, 'dbpe', 1)
+        if da.shape != a.shape or not da.is_contiguous():
+            raise ValueError('tc_attn_bwd: da must be contiguous with the shape of a')
+    _lib.check(L.vog_tc_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), ldo, _ptr(dout), lddo, _ptr(lse), Bt, N, H, dhp,
+                                 dh_arr, float(inv_scale), bias_mode, _ptr(a), nbox, _ptr(bpe), _ptr(dqkv), 3 * H * dhp,
+                                 _ptr(da), _ptr(dbpe), ws.data_ptr() + off, ws_bytes, float(drop_p), int(seed), _stream()),
+               'vog_tc_attn_bwd')
+    return dqkv
