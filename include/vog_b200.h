@@ -388,6 +388,14 @@ int vog_tc_attn_bwd(const void* q, const void* k, const void* v, const void* o, 
                     int bias_mode, const float* a, int nbox, const float* bpe, void* dqkv, int64_t ldg, float* da,
                     float* dbpe, void* workspace, int64_t workspace_bytes, float drop_p, uint64_t seed, void* stream);
 
+/* Element-wise dropout of the training forward and its backward: out (fp32, nullable; may alias x) / out_lp
+ * (VOG_LP_*, nullable) = x * keep / (1-p) + residual (nullable), keep = counter-based function of (seed, stream_id,
+ * row, column) - calling it on the output gradient with the same ids is the backward.  nn.Dropout of the two
+ * ResidualBlock branches (code/transformer_code.py:26,31) and the LSTM input / inter-layer / output dropouts
+ * (utils/mdl_srl_utils.py:104,128,150). */
+int vog_dropout(const float* x, int64_t ldx, const float* residual, int64_t ldr, float* out, int64_t ldo, void* out_lp,
+                int64_t ldlp, int lp_kind, int64_t M, int N, float p, uint64_t seed, int stream_id, void* stream);
+
 /* Weight gradient on tcgen05: C[N1,N2] (fp32, ldc) += A[K,N1]^T . B[K,N2], A / B bf16 row-major (the contraction
  * index is the slow index of both: dY and X as the forward / backward kernels leave them; nothing is transposed in
  * HBM).  C must be zero-initialised or hold a running gradient.  Replaces autograd's mm(dY^T, X) of every nn.Linear

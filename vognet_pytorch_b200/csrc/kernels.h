@@ -133,6 +133,9 @@ int attn_bwd_f32(const float* q, const float* k, const float* v, long long ld, c
                  long long ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
                  const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe, float* ddense,
                  cudaStream_t st);
+int dropout_apply(const float* x, long long ldx, const float* res, long long ldr, float* out, long long ldo, void* out_lp,
+                  long long ldlp, int lp_kind, long long M, int N, float p, unsigned long long seed, unsigned int stream,
+                  cudaStream_t st);
 int pe_project_bwd(const float* props, int ldp, const float* da, float* dW, int rows, int H, float vw, float vh,
                    float fdiv, cudaStream_t st);
 int xmul_bwd(const float* dtok, float* dvis, float* dlang, int B, int nfrm, int nsrl, int nppf2, int dv, int dl,

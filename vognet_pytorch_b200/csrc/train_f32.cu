@@ -8,6 +8,7 @@
 // torch autograd derives for the UNMODIFIED reference (tests/golden/grad_cpu_ref.npz, oracle/make_golden.py).
 #include "common.cuh"
 #include "kernels.h"
+#include "philox.cuh"
 
 namespace vog {
 
@@ -1024,6 +1025,52 @@ int lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const
         if (check_launch("lstm_bwd_step")) return -1;
     }
     return 0;
+}
+
+
+// =============================================================================================
+// Element-wise dropout (nn.Dropout / F.dropout on a [M,N] activation): the two residual branches of a
+// ResidualBlock (code/transformer_code.py:26,31) and the LSTM input / inter-layer / output dropouts
+// (utils/mdl_srl_utils.py:104,128,150).  out = x * keep / (1-p) (+ residual); keep is a counter-based function of
+// (seed, stream, row, column) - the backward calls the same kernel on the output gradient with the same ids.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res, long long ldr,
+               float* __restrict__ out, long long ldo, void* __restrict__ out_lp, long long ldlp, int lp_kind,
+               long long M, int N, float p, unsigned long long seed, unsigned int stream)
+{
+    const int n8 = (N + 7) >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * n8) return;
+    const long long r = idx / n8;
+    const int c0 = (int)(idx - r * n8) * 8;
+    uint32_t rnd[4];
+    attn_rand16x8(seed, stream, (uint32_t)r, (uint32_t)c0, rnd);
+    const uint32_t thr = drop_threshold16(p);
+    const float inv_keep = 1.f / (1.f - p);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        if (c >= N) break;
+        const bool keep = ((rnd[e >> 1] >> (16 * (e & 1))) & 0xffffu) >= thr;
+        float v = keep ? x[r * ldx + c] * inv_keep : 0.f;
+        if (res) v += res[r * ldr + c];
+        if (out) out[r * ldo + c] = v;
+        if (out_lp) store_lp1(out_lp, r * ldlp + c, v, lp_kind);
+    }
+}
+
+int dropout_apply(const float* x, long long ldx, const float* res, long long ldr, float* out, long long ldo, void* out_lp,
+                  long long ldlp, int lp_kind, long long M, int N, float p, unsigned long long seed, unsigned int stream,
+                  cudaStream_t st)
+{
+    if (M == 0 || N == 0) return 0;
+    VOG_REQUIRE(p >= 0.f && p < 1.f, "dropout: probability %f", (double)p);
+    VOG_REQUIRE(M < (1LL << 32), "dropout: too many rows");
+    const long long n = M * ((N + 7) >> 3);
+    dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ldx, res, ldr, out, ldo, out_lp, ldlp, lp_kind, M, N, p,
+                                                                seed, stream);
+    return check_launch("dropout");
 }
 
 }  // namespace vog

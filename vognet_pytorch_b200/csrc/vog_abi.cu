@@ -316,6 +316,16 @@ int vog_tc_attn_bwd(const void* q, const void* k, const void* v, const void* o, 
                        da, dbpe, workspace, workspace_bytes, drop_p, (unsigned long long)seed, (cudaStream_t)stream);
 }
 
+int vog_dropout(const float* x, int64_t ldx, const float* residual, int64_t ldr, float* out, int64_t ldo, void* out_lp,
+                int64_t ldlp, int lp_kind, int64_t M, int N, float p, uint64_t seed, int stream_id, void* stream)
+{
+    VOG_REQUIRE(M >= 0 && N >= 0, "vog_dropout: negative dimension");
+    if (M == 0 || N == 0) return 0;
+    VOG_REQUIRE(x && (out || out_lp), "vog_dropout: null operand");
+    return dropout_apply(x, ldx, residual, ldr, out, ldo, out_lp, ldlp, lp_kind, M, N, p, (unsigned long long)seed,
+                         (unsigned int)stream_id, (cudaStream_t)stream);
+}
+
 int vog_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int K, int N1, int N2, float* C,
                    int64_t ldc, void* stream)
 {

@@ -260,3 +260,21 @@ def tc_attn_bwd(q, k, v, out, dout, lse, N, head_dims, inv_scale, bias_mode=BIAS
                                  _ptr(da), _ptr(dbpe), ws.data_ptr() + off, ws_bytes, float(drop_p), int(seed), _stream()),
                'vog_tc_attn_bwd')
     return dqkv
+
+
+def dropout(x, p, seed, stream_id, residual=None, out=None, lp_kind=LP_NONE, want_f32=True):
+    """x [M,N] fp32 -> (x * keep/(1-p) + residual as fp32 or None, low-precision copy or None); the mask is a function of
+    (seed, stream_id, row, column) (vog_dropout).  The backward is the same call on the output gradient."""
+    _req(x, torch.float32, 'x', 2)
+    M, N = x.shape
+    if out is None and want_f32:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    out_lp = torch.empty(M, N, device=x.device, dtype=_LP_DTYPE[lp_kind]) if lp_kind != LP_NONE else None
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.float32, 'residual', 2)
+        ldr = _rowmajor2d(residual, 'residual')
+    _lib.check(_lib.lib().vog_dropout(_ptr(x), _rowmajor2d(x, 'x'), _ptr(residual), ldr, _ptr(out),
+                                      _rowmajor2d(out, 'out') if out is not None else 0, _ptr(out_lp), N, lp_kind, M, N,
+                                      float(p), int(seed), int(stream_id), _stream()), 'vog_dropout')
+    return out, out_lp

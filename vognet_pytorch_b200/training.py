@@ -150,6 +150,9 @@ def stack_backward_f32(ex, prefix, tapes, dout, Bt, N, bias, sink, be, da=None, 
 def _check_supported(mdl):
     if mdl.CONC_TYPE == 'sep':
         raise NotImplementedError('vognet_pytorch_b200: training of the SEP concatenation is not built (temp / spat are)')
+    if mdl.compute == 'tf32':
+        raise NotImplementedError("vognet_pytorch_b200: the training step runs in compute modes 'bf16' (tcgen05) and "
+                                  "'fp32x' (exact); 'tf32' is an inference mode")
 
 
 def dropout_active(mdl):
@@ -159,21 +162,37 @@ def dropout_active(mdl):
     return bool(mdl.train_dropout)
 
 
-def forward_train_f32(mdl, inp):
-    """Training forward in exact fp32.  -> (logits [B,1,nsrl,P], tape)."""
-    be = F32Backend()
-    tp = Tape(be=be)
-    feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
-    B, P, _ = feat.shape
-    ncmp = inp['new_srl_idxs'].shape[1]
-    nppf = mdl.num_prop_per_frm
-    nvf = seg.shape[1]
-    words = inp['srl_arg_words_ind']
-    _, nv, nsrl, L = words.shape
-    assert nv == 1 and nvf * nppf == P
-    tp.update(B=B, P=P, ncmp=ncmp, nppf=nppf, nvf=nvf, nsrl=nsrl)
+class DropCtx:
+    """Dropout bookkeeping of one training forward: ONE host-side seed per call (drawn from torch's CPU generator, so
+    torch.manual_seed makes runs repeatable and nothing synchronises with the device) and a fixed id per call site; the
+    backward regenerates every mask from (seed, site)."""
+    LSTM_IN, LSTM_MID, LSTM_OUT = 1, 2, 3          # utils/mdl_srl_utils.py:128,104,150
+    OBJ, MUL = 100, 200                            # + 2*layer (+1 for the feed-forward branch); attention: 1000 + ...
 
-    # ---- language side (code/mdl_vog.py:67-140,250-283; utils/mdl_srl_utils.py:114-169)
+    def __init__(self, mdl, active):
+        self.active = bool(active)
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.active else 0
+        self.p_lstm = 0.1 if self.active else 0.0  # LSTMEncoder defaults dropout_in = dropout_out = 0.1 (:77)
+
+    def site_seed(self, site):
+        return (self.seed + site * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+    def p_tx(self, ex):
+        return float(ex.drop) if self.active else 0.0
+
+
+def _drop(x, dc, p, site, **kw):
+    """dropout call site (forward and backward use the same ids)"""
+    if p <= 0.0:
+        return x
+    return ob.dropout(x, p, dc.seed, site, **kw)[0]
+
+
+def lang_forward(mdl, inp, tp, dc):
+    """Language side of the training forward, exact fp32 in every compute mode (code/mdl_vog.py:67-140,250-283;
+    utils/mdl_srl_utils.py:114-169).  -> lang [B*nsrl, 256] fp32; activations into `tp`."""
+    words = inp['srl_arg_words_ind']
+    B, nv, nsrl, L = words.shape
     Bq = B * nv
     wm = inp['srl_arg_word_mask'].reshape(Bq, -1).contiguous()
     T = wm.shape[1]
@@ -181,6 +200,7 @@ def forward_train_f32(mdl, inp):
     tp.update(Bq=Bq, T=T, lens=lens, wm=wm, words=words.reshape(Bq, nsrl * L).contiguous())
     lstm = mdl.lstm_encoder.lstm
     x = ops.lang_embed(tp.words, wm, mdl.lstm_encoder.embed_tokens.weight, mdl.vocab_size, ops.LP_NONE)
+    x = _drop(x, dc, dc.p_lstm, dc.LSTM_IN)
     tp.lstm = []
     for l in range(lstm.num_layers):
         wih = torch.cat([getattr(lstm, f'weight_ih_l{l}'), getattr(lstm, f'weight_ih_l{l}_reverse')], 0).detach()
@@ -190,7 +210,9 @@ def forward_train_f32(mdl, inp):
         gx = ops.sgemm_nt(x, wih, bias)
         hout = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_NONE)
         tp.lstm.append(Tape(x=x, gx=gx, hout=hout, wih=wih, whh=whh))
-        x = hout
+        last = l == lstm.num_layers - 1
+        x = _drop(hout, dc, dc.p_lstm, dc.LSTM_OUT if last else dc.LSTM_MID + 10 * l)
+    tp.top = x
     proj, enc = mdl.lstm_out_feat_proj[0], mdl.srl_arg_words_out_enc[0]
     tp.full = ops.sgemm_nt(x, proj.weight, proj.bias, relu=True)                                  # [T*Bq, 256]
     tp.cap = inp['srl_arg_words_capture'].reshape(Bq, nsrl, 2).contiguous()
@@ -198,6 +220,45 @@ def forward_train_f32(mdl, inp):
     tp.enc = ops.sgemm_nt(tp.cat, enc.weight, enc.bias, relu=True)
     tp.smsk = inp['srl_arg_inds_msk'].reshape(Bq * nsrl).contiguous()
     lang, _ = ops.mask_rows(tp.enc, tp.smsk)                                                      # [B*nsrl, 256]
+    return lang
+
+
+def lang_backward(mdl, tp, dlang, sink, dc):
+    """dlang [B*nsrl, 256] -> parameter gradients of the language side into `sink`."""
+    be = F32Backend()
+    Bq, T = tp.Bq, tp.T
+    denc, _ = ops.mask_rows(dlang, tp.smsk)                                                # mask_rows backward
+    ob.relu_bwd(denc, tp.enc, dbias=sink.get('srl_arg_words_out_enc.0.bias'), inplace=True)
+    sink.set('srl_arg_words_out_enc.0.weight', be.lin_dw(denc, tp.cat))
+    dcat = be.lin_dx(denc, mdl.srl_arg_words_out_enc[0].weight)
+    dfull = ob.lang_gather_bwd(dcat, tp.cap, T, Bq)
+    ob.relu_bwd(dfull, tp.full, dbias=sink.get('lstm_out_feat_proj.0.bias'), inplace=True)
+    sink.set('lstm_out_feat_proj.0.weight', be.lin_dw(dfull, tp.top))
+    dtop = be.lin_dx(dfull, mdl.lstm_out_feat_proj[0].weight)
+    _lstm_backward(mdl, tp, dtop, sink, be, dc)
+
+
+def forward_train_f32(mdl, inp):
+    """Training forward in exact fp32.  -> (logits [B,1,nsrl,P], tape)."""
+    be = F32Backend()
+    dc = DropCtx(mdl, dropout_active(mdl))
+    if dc.active and ((mdl.USE_OBJ_TX and mdl.cfg.mdl.obj_tx.to_use and mdl.obj_txf._exec.drop > 0) or
+                      (mdl.USE_MUL_TX and mdl.cfg.mdl.mul_tx.to_use and mdl.mult_txf._exec.drop > 0)):
+        raise NotImplementedError(
+            "vognet_pytorch_b200: the exact-fp32 mode trains without dropout (model.train_dropout = False, or "
+            "attn_drop = 0); dropout (code/transformer_code.py:26,31,153) is part of the tensor-core training step: "
+            "model.set_compute('bf16')")
+    tp = Tape(be=be, dc=dc)
+    feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
+    B, P, _ = feat.shape
+    ncmp = inp['new_srl_idxs'].shape[1]
+    nppf = mdl.num_prop_per_frm
+    nvf = seg.shape[1]
+    words = inp['srl_arg_words_ind']
+    _, nv, nsrl, L = words.shape
+    assert nv == 1 and nvf * nppf == P
+    tp.update(B=B, P=P, ncmp=ncmp, nppf=nppf, nvf=nvf, nsrl=nsrl)
+    lang = lang_forward(mdl, inp, tp, dc)
 
     # ---- visual side: prop | seg rows (code/mdl_vog.py:291-314; code/mdl_conc_single.py:50-66,156-174)
     pe_ = mdl.prop_encoder[0].out_features
@@ -250,7 +311,7 @@ def forward_train_f32(mdl, inp):
     return logits, tp
 
 
-def _lstm_backward(mdl, tp, dx_top, sink, be):
+def _lstm_backward(mdl, tp, dx_top, sink, be, dc):
     """Backward through the stacked bidirectional LSTM.  dx_top [T*Bq, 2H] = gradient of the top layer's output."""
     lstm = mdl.lstm_encoder.lstm
     T, Bq, lens = tp.T, tp.Bq, tp.lens
@@ -259,6 +320,8 @@ def _lstm_backward(mdl, tp, dx_top, sink, be):
     dout = dx_top
     for l in reversed(range(lstm.num_layers)):
         lt = tp.lstm[l]
+        last = l == lstm.num_layers - 1
+        dout = _drop(dout, dc, dc.p_lstm, dc.LSTM_OUT if last else dc.LSTM_MID + 10 * l)   # output / inter-layer dropout
         Hh = lt.whh.shape[2]
         hprev = ob.lstm_hprev(lt.hout, lens, T, Bq)
         G = lt.gx.clone()                                            # gate pre-activations of all steps (recomputed)
@@ -278,6 +341,7 @@ def _lstm_backward(mdl, tp, dx_top, sink, be):
             sink.set(f'lstm_encoder.lstm.bias_hh_l{l}{sfx[d_]}', db[sl].clone())
             sink.set(f'lstm_encoder.lstm.weight_hh_l{l}{sfx[d_]}', be.lin_dw(dG[:, sl], hprev[:, d_ * Hh:(d_ + 1) * Hh]))
         dout = be.lin_dx(dG, lt.wih)                                 # [T*Bq, in]
+    dout = _drop(dout, dc, dc.p_lstm, dc.LSTM_IN)
     ob.lang_embed_bwd(tp.words, tp.wm, dout, mdl.vocab_size, lens, sink.get('lstm_encoder.embed_tokens.weight'))
 
 
@@ -324,17 +388,7 @@ def backward_train_f32(mdl, tp, dlogits):
     ob.colsum_acc(dseg, sink.get('seg_encoder.0.bias'))
     sink.set('seg_encoder.0.weight', be.lin_dw(dseg, tp.seg2))
     # ---- language side
-    Bq, T = tp.Bq, tp.T
-    denc, _ = ops.mask_rows(dlang, tp.smsk)                                                # mask_rows backward
-    ob.relu_bwd(denc, tp.enc, dbias=sink.get('srl_arg_words_out_enc.0.bias'), inplace=True)
-    sink.set('srl_arg_words_out_enc.0.weight', be.lin_dw(denc, tp.cat))
-    dcat = be.lin_dx(denc, mdl.srl_arg_words_out_enc[0].weight)
-    dfull = ob.lang_gather_bwd(dcat, tp.cap, T, Bq)
-    ob.relu_bwd(dfull, tp.full, dbias=sink.get('lstm_out_feat_proj.0.bias'), inplace=True)
-    top = tp.lstm[-1].hout
-    sink.set('lstm_out_feat_proj.0.weight', be.lin_dw(dfull, top))
-    dtop = be.lin_dx(dfull, mdl.lstm_out_feat_proj[0].weight)
-    _lstm_backward(mdl, tp, dtop, sink, be)
+    lang_backward(mdl, tp, dlang, sink, tp.dc)
     return sink.g
 
 
@@ -366,9 +420,6 @@ class _TrainFn(torch.autograd.Function):
 def forward_train(mdl, inp):
     """model(batch) in .train() mode -> {'mdl_outs': differentiable logits, 'mdl_outs_eval': masked scores}."""
     _check_supported(mdl)
-    if dropout_active(mdl):
-        raise NotImplementedError('vognet_pytorch_b200: dropout in the training forward is being built; set '
-                                  'model.train_dropout = False for the deterministic training step')
     names, params = zip(*[(n, p) for n, p in mdl.named_parameters() if p.requires_grad])
     logits = _TrainFn.apply(mdl, inp, names, *params)
     B, _, nsrl, P = logits.shape
