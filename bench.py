@@ -229,15 +229,15 @@ def run_reference(args):
 def train_step_object(dev, world, rank, flush, barrier, max_ranks, steps):
     """BASELINE.json configs[4]: spat/p100 TRAINING step, bs=4 per GPU (bs=32 at 8 GPUs): forward + LossB_SPAT +
     backward + ONE flat NCCL gradient all-reduce + fused Adam (utils/trn_utils.py:497-505, code/main_dist.py:55,75-80)."""
-    from vognet_pytorch_b200 import training
-    return training.bench_train_step('spat_p100', 'bf16', dev, world, rank, flush, barrier, max_ranks, steps)
+    from vognet_pytorch_b200 import train_step
+    return train_step.bench_train_step('spat_p100', 'bf16', dev, world, rank, flush, barrier, max_ranks, steps)
 
 
 def run_train(args, dev, world, rank, sampler, flush, barrier, max_ranks):
-    from vognet_pytorch_b200 import training
-    compute = args.compute or COMPUTE[args.workload]
+    from vognet_pytorch_b200 import train_step
+    compute = args.compute or ('bf16' if COMPUTE[args.workload] != 'fp32x' else 'fp32x')
     sampler.mark_begin()
-    obj = training.bench_train_step(args.workload, compute, dev, world, rank, flush, barrier, max_ranks, args.steps,
+    obj = train_step.bench_train_step(args.workload, compute, dev, world, rank, flush, barrier, max_ranks, args.steps,
                                     warmup=args.warmup)
     sampler.mark_end()
     clocks = sampler.stop()

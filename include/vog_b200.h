@@ -187,6 +187,12 @@ int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int
                        int Bq, int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace,
                        void* stream);
 
+/* Training variant: additionally keeps, for every live (t, b), the activations the step used - acts
+ * [T*Bq, 2 dir, 6, H] = i, f, g, o, tanh(c_t), c_{t-1} - which is all vog_lstm_bwd_steps needs (no recompute). */
+int vog_lstm_layer_fwd_train(const float* gx, int64_t ldg, const float* whh, const int64_t* lens, int T, int Bq,
+                             int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace, float* acts,
+                             void* stream);
+
 /* SM partitioning between the concurrent branches of one forward (host-side state, read at launch / graph-capture
  * time).  vog_lstm_set_max_ctas(n > 0): the following vog_lstm_layer_fwd launches use at most n SMs (weight-streaming
  * kernel, many hidden units per CTA) instead of the weight-resident kernel that needs every SM; vog_set_reserved_sms(n):
@@ -359,10 +365,11 @@ int vog_lang_embed_bwd(const int64_t* words, int nwords, const int64_t* mask, in
  *   vog_lstm_scan      G [T*Bq, 8H] gate pre-activations (gx + hprev.W_hh^T, recomputed by a GEMM) -> acts
  *                      [T*Bq, 2, 6, H]: i, f, g, o, tanh(c_t), c_{t-1}
  *   vog_lstm_bwd_steps dout [T*Bq, 2H] -> dG [T*Bq, 8H] (zeros beyond lens): T dependent launches, each one
- *                      dh_{prev} = dG_t . W_hh; carry_ws: 8*Bq*H floats of scratch; Bq <= 8 per call. */
+ *                      dh_{prev} = dG_t . W_hh, read from the TRANSPOSED recurrent weight whh_t [2,H,4H] (one
+ *                      contiguous row per output unit); carry_ws: 8*Bq*H floats of scratch; Bq <= 8 per call. */
 int vog_lstm_hprev(const float* hout, const int64_t* lens, float* hprev, int T, int Bq, int H, void* stream);
 int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int Bq, int H, void* stream);
-int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const int64_t* lens, float* dG,
+int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const int64_t* lens, float* dG,
                        float* carry_ws, int T, int Bq, int H, void* stream);
 
 /* ---- training step on the tensor cores (compute mode 'bf16') ---------------------------------------------------

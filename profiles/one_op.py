@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run ONE hot-path op a few times (for `ncu --set full -k regex:<kernel>` captures).
-usage: one_op.py gemm M N K [bf16|tf32] [residual] | attn Bt N d | lstm"""
+usage: one_op.py gemm M N K [bf16|tf32] [residual] | attn Bt N d | attn_bwd Bt N d [drop] | lstm"""
 import os
 import sys
 
@@ -35,6 +35,34 @@ elif what == 'attn':
     bpe = torch.zeros(3, device=dev)
     for _ in range(4):
         ops.tc_attn_fwd(q, k, vt, N, hd, 1.0 / d ** 0.5, bias_mode=ops.BIAS_RANK1, a=a, nbox=nbox, bpe=bpe)
+elif what == 'attn_bwd':                   # training forward + backward of the fused attention (spat/p100: 40 2000 768, 4 4000 512)
+    from vognet_pytorch_b200 import ops_bwd as ob
+    Bt, N, d = [int(v) for v in sys.argv[2:5]]
+    drop = 0.2 if 'drop' in sys.argv else 0.0
+    hd = ops.chunk_sizes(d, 3)
+    dhp = ops.round_up(max(hd), 64)
+    q = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
+    k = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
+    vt = (torch.rand(Bt, 3, N, dhp, device=dev) - 0.5).bfloat16()
+    do = (torch.rand(Bt * N, 3 * dhp, device=dev) - 0.5).bfloat16()
+    nbox = N // 5 if N % 5 == 0 else N
+    a = torch.rand(Bt * nbox, 3, device=dev)
+    bpe = torch.zeros(3, device=dev)
+    da, dbpe = torch.zeros_like(a), torch.zeros_like(bpe)
+    kw = dict(bias_mode=ops.BIAS_RANK1, a=a, nbox=nbox, bpe=bpe, drop_p=drop, seed=7)
+    ts = []
+    for it in range(4):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out, lse = ob.tc_attn_fwd_train(q, k, vt, N, hd, 1.0 / d ** 0.5, **kw)
+        e[1].record()
+        ob.tc_attn_bwd(q, k, vt, out, do, lse, N, hd, 1.0 / d ** 0.5, da=da, dbpe=dbpe, **kw)
+        e[2].record()
+        torch.cuda.synchronize()
+        ts.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
+    fl = 4.0 * Bt * N * N * d
+    print(f'attn_bwd Bt={Bt} N={N} d={d} drop={drop}: fwd {ts[-1][0]:.3f} ms ({fl / ts[-1][0] / 1e9:.0f} TF/s), '
+          f'bwd {ts[-1][1]:.3f} ms ({2.5 * fl / ts[-1][1] / 1e9:.0f} TF/s)')
 elif what == 'qkvf':                       # factorised mul_tx QKV at spat/p100: B=4, nfrm=10, nsrl=5, nppf2=400
     B, nfrm, nsrl, nppf2 = [int(v) for v in sys.argv[2:6]]
     kind = ops.LP_TF32 if 'tf32' in sys.argv else ops.LP_BF16

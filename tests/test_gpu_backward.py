@@ -222,7 +222,11 @@ def test_lstm_backward_building_blocks_match_nn_lstm(lens):
     for d_ in range(2):
         ob.sgemm(hprev[:, d_ * Hh:(d_ + 1) * Hh], whh[d_].t(), out=G[:, d_ * 4 * Hh:(d_ + 1) * 4 * Hh], accumulate=True)
     acts = ob.lstm_scan(G, lens_d, T, Bq)
-    dG = ob.lstm_bwd_steps(f(dout).view(T * Bq, 2 * Hh), acts, whh, lens_d, T, Bq)
+    # the training forward keeps the same activations itself (no recompute in the model's backward)
+    hout2, acts2 = ops.lstm_layer_fwd(gx, whh, lens_d, T, Bq, ops.LP_NONE, want_acts=True)
+    live = (torch.arange(T, device=DEV).view(T, 1) < lens_d.view(1, Bq)).reshape(T * Bq)
+    assert torch.equal(hout2, hout) and float((acts2[live] - acts[live]).abs().max()) < 1e-5
+    dG = ob.lstm_bwd_steps(f(dout).view(T * Bq, 2 * Hh), acts2, whh.transpose(1, 2).contiguous(), lens_d, T, Bq)
     dx = ob.sgemm(dG, wih)
     assert _rel(dx, x.grad.view(T * Bq, E)) < 1e-4
     dwih = ob.sgemm(dG.t(), x2)
@@ -234,6 +238,28 @@ def test_lstm_backward_building_blocks_match_nn_lstm(lens):
     db = torch.zeros(8 * Hh, device=DEV)
     ob.colsum_acc(dG, db)
     assert _rel(db, torch.cat([lstm.bias_ih_l0.grad, lstm.bias_ih_l0_reverse.grad], 0)) < 1e-4
+
+
+def test_lstm_resident_kernel_keeps_its_activations():
+    """H = 1024 runs the weight-resident recurrence kernel (fast exp): its saved activations agree with the exact
+    scan over recomputed gates to 1e-5, and the backward kernel accepts them."""
+    g = torch.Generator().manual_seed(9)
+    T, Bq, Hh = 20, 4, 1024
+    gx = (torch.randn(T * Bq, 8 * Hh, generator=g) * 0.5).to(DEV)
+    whh = (torch.randn(2, 4 * Hh, Hh, generator=g) / 48).to(DEV)
+    lens_d = torch.tensor([20, 9, 14, 3], device=DEV)
+    hout, acts = ops.lstm_layer_fwd(gx, whh, lens_d, T, Bq, ops.LP_NONE, want_acts=True)
+    hprev = ob.lstm_hprev(hout, lens_d, T, Bq)
+    G = gx.clone()
+    for d_ in range(2):
+        ob.sgemm(hprev[:, d_ * Hh:(d_ + 1) * Hh], whh[d_].t(), out=G[:, d_ * 4 * Hh:(d_ + 1) * 4 * Hh], accumulate=True)
+    ref = ob.lstm_scan(G, lens_d, T, Bq)
+    live = (torch.arange(T, device=DEV).view(T, 1) < lens_d.view(1, Bq)).reshape(T * Bq)
+    assert float((acts[live] - ref[live]).abs().max()) < 2e-5
+    dout = torch.randn(T * Bq, 2 * Hh, generator=g).to(DEV)
+    wt = whh.transpose(1, 2).contiguous()
+    a, b = ob.lstm_bwd_steps(dout, acts, wt, lens_d, T, Bq), ob.lstm_bwd_steps(dout, ref, wt, lens_d, T, Bq)
+    assert _rel(a, b) < 1e-4 and float(a[~live].abs().max()) == 0.0
 
 
 def test_lin2_xmul_seg_relu_glue_backward():
@@ -290,7 +316,7 @@ def _rel_l2(a, b):
 
 @pytest.mark.parametrize('name', ['cpu_ref', 'temp_gt5', 'spat_gt5'])
 def test_bf16_training_step_gradients_track_the_oracle(name):
-    """bf16 operands, fp32 accumulation: every parameter gradient within 4e-2 (relative L2) of torch autograd through
+    """bf16 operands, fp32 accumulation: every parameter gradient within 5e-2 (relative L2) of torch autograd through
     the fp32 oracle, loss within 2e-3 relative (north_star: 1e-2 on bf16 scores).  The 2 x (3 + 15) parameters of the
     relative-position encoders get 1.5e-1: each is a sum of ~1e5 signed score gradients that cancel to a few per cent
     of their absolute mass, so the bf16 rounding of q / k / v / dO shows up amplified (measured 4-9e-2)."""
@@ -313,7 +339,7 @@ def test_bf16_training_step_gradients_track_the_oracle(name):
         assert p.grad is not None and p.grad.dtype == torch.float32 and bool(torch.isfinite(p.grad).all()), k
         worst[k] = _rel_l2(p.grad, ref[k])
     print('bf16 gradient errors (relative L2), worst five:', sorted(worst.items(), key=lambda kv: -kv[1])[:5])
-    bad = {k: v for k, v in worst.items() if v > (1.5e-1 if k.startswith('pe_') else 4e-2)}
+    bad = {k: v for k, v in worst.items() if v > (1.5e-1 if k.startswith('pe_') else 5e-2)}
     assert len(worst) == 57 and not bad, bad
     # the bf16 training forward without dropout is the bf16 inference forward
     mdl.eval()

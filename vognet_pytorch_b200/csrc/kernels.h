@@ -102,7 +102,8 @@ void lstm_set_exchange(int mode);        // debug: 0 tagged 64-bit words, 1 per-
 void lstm_set_max_ctas(int n);           // > 0: run the recurrence on at most n SMs (weight-streaming kernel)
 void lstm_force_streaming(int on);       // debug: disable the weight-resident kernel
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
-                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st);
+                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st,
+                   float* acts = nullptr);
 
 // ---- fused_glue.cu ------------------------------------------------------------------------------
 int build_xmul(const float* vis, const float* lang, float* out, void* out_lp, int lp_kind, int B, int nfrm,
@@ -150,7 +151,7 @@ int lang_embed_bwd(const long long* words, int nwords, const long long* mask, in
                    long long pad_idx, int Bq, const long long* lens, float* demb, cudaStream_t st);
 int lstm_hprev(const float* hout, const long long* lens, float* hprev, int T, int Bq, int H, cudaStream_t st);
 int lstm_scan(const float* G, const long long* lens, float* acts, int T, int Bq, int H, cudaStream_t st);
-int lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const long long* lens, float* dG,
+int lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const long long* lens, float* dG,
                    float* carry_ws, int T, int Bq, int H, cudaStream_t st);
 
 // ---- loss_fwd.cu : grounding loss, forward ----------------------------------------------------

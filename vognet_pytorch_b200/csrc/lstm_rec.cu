@@ -34,6 +34,7 @@ struct LstmParams {
     void* out_lp; long long ld_out; int lp_kind;   // [T*Bq, 2H] bf16 / tf32-rounded fp32
     int T, Bq, H, U, ctas_per_dir;
     int bq_total;                         // sequences per timestep row block of gx / out (>= Bq: chunked batches)
+    float* acts;                          // training: [T*bq_total, 2, 6, H] i, f, g, o, tanh(c_t), c_{t-1} (nullable)
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -144,10 +145,16 @@ lstm_rec_kernel(const LstmParams p)
                 const float gf = sigmoidf_(gate_s[(1 * LS_MAXU + uu) * LS_MAXB + b]);
                 const float gg = tanhf(gate_s[(2 * LS_MAXU + uu) * LS_MAXB + b]);
                 const float go = sigmoidf_(gate_s[(3 * LS_MAXU + uu) * LS_MAXB + b]);
-                const float cn = gf * c_s[uu * LS_MAXB + b] + gi * gg;
+                const float cp = c_s[uu * LS_MAXB + b];
+                const float cn = gf * cp + gi * gg;
                 c_s[uu * LS_MAXB + b] = cn;
-                hval = go * tanhf(cn);
+                const float tcn = tanhf(cn);
+                hval = go * tcn;
                 hc_s[uu * LS_MAXB + b] = hval;
+                if (p.acts != nullptr) {
+                    float* a = p.acts + ((((size_t)t * p.bq_total + b) * 2 + d) * 6) * H + u0 + uu;
+                    a[0] = gi; a[H] = gf; a[2 * (size_t)H] = gg; a[3 * (size_t)H] = go; a[4 * (size_t)H] = tcn; a[5 * (size_t)H] = cp;
+                }
             }
             hb[(size_t)b * H + u0 + uu] = hc_s[uu * LS_MAXB + b];
             store_lp(p.out_lp, ((long long)t * p.bq_total + b) * p.ld_out + (long long)d * H + u0 + uu, hval, p.lp_kind);
@@ -248,6 +255,7 @@ struct LstmResParams {
     int T, Bq, U, ctas_per_dir;
     int bq_total;                         // sequences per timestep row block of gx / out (>= Bq: chunked batches)
     long long* trace;                     // debug: [8] accumulated clock64 phases of CTA 0 / thread 0
+    float* acts;                          // training: [T*bq_total, 2, 6, H] i, f, g, o, tanh(c_t), c_{t-1} (nullable)
 };
 
 // v[0..V) per lane -> lane holds the warp-wide sum of v[idx], idx = the top log2(V) bits of (lane >> (5 - log2 V))
@@ -413,9 +421,15 @@ lstm_rec_resident_kernel(const LstmResParams p)
                 const float gf = fast_sigmoid(gs[1]);
                 const float gg = fast_tanh(gs[2]);
                 const float go = fast_sigmoid(gs[3]);
+                const float cp = c_reg;
                 c_reg = gf * c_reg + gi * gg;
-                hval = go * fast_tanh(c_reg);
+                const float tcn = fast_tanh(c_reg);
+                hval = go * tcn;
                 h_reg = hval;
+                if (p.acts != nullptr) {             // kept for the backward: exactly the activations this step used
+                    float* a = p.acts + ((((size_t)t * p.bq_total + lane) * 2 + d) * 6) * H + u;
+                    a[0] = gi; a[H] = gf; a[2 * (size_t)H] = gg; a[3 * (size_t)H] = go; a[4 * (size_t)H] = tcn; a[5 * (size_t)H] = cp;
+                }
             }
             if (step + 1 < Tmax) {
                 const size_t xi = (((size_t)(step & 1) * 2 + d) * Bq + lane) * H + u;
@@ -533,7 +547,7 @@ long long lstm_workspace_bytes(int Bq, int H)
 }
 
 static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq, int bq_total,
-                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st)
+                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st, float* acts)
 {
     if (T == 0 || Bq == 0) return 0;
     VOG_REQUIRE(Bq <= LS_MAXB, "lstm_layer_fwd: at most %d sequences per call (got %d)", LS_MAXB, Bq);
@@ -563,6 +577,7 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
         rp.out_lp = out_lp; rp.ld_out = ld_out; rp.lp_kind = lp_kind;
         rp.T = T; rp.Bq = Bq; rp.U = U; rp.ctas_per_dir = per_dir_u; rp.bq_total = bq_total;
         rp.trace = g_lstm_trace;
+        rp.acts = acts;
         VOG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)lstm_workspace_bytes(Bq, H), st));
         const int ctas = 2 * per_dir_u, threads = 32 * U;
         if (Bq == 1) return launch_resident<1>(rp, ctas, threads, st);
@@ -583,6 +598,7 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
     p.hbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + LS_WS_HEADER);
     p.out_lp = out_lp; p.ld_out = ld_out; p.lp_kind = lp_kind;
     p.T = T; p.Bq = Bq; p.H = H; p.U = U; p.ctas_per_dir = per_dir; p.bq_total = bq_total;
+    p.acts = acts;
     VOG_CUDA(cudaMemsetAsync(workspace, 0, 64, st));
     const size_t smem = sizeof(float) * ((size_t)LS_MAXB * H + 6 * LS_MAXU * LS_MAXB);
     VOG_CUDA(cudaFuncSetAttribute(lstm_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -593,14 +609,15 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
 // Batches of more than LS_MAXB sequences run as consecutive launches over groups of LS_MAXB (the recurrences of
 // different sentences are independent); gx / out rows stay time-major over the WHOLE batch.
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,
-                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st)
+                   int H, void* out_lp, long long ld_out, int lp_kind, void* workspace, cudaStream_t st, float* acts)
 {
     VOG_REQUIRE(lp_kind >= 0 && lp_kind <= 2, "lstm_layer_fwd: bad lp_kind");
     const size_t esz = lp_kind == 1 ? 2 : 4;
     for (int b0 = 0; b0 < Bq; b0 += LS_MAXB) {
         const int nb = Bq - b0 < LS_MAXB ? Bq - b0 : LS_MAXB;
         if (lstm_layer_chunk(gx + (size_t)b0 * ldg, ldg, whh, lens + b0, T, nb, Bq, H,
-                             reinterpret_cast<char*>(out_lp) + (size_t)b0 * ld_out * esz, ld_out, lp_kind, workspace, st))
+                             reinterpret_cast<char*>(out_lp) + (size_t)b0 * ld_out * esz, ld_out, lp_kind, workspace, st,
+                             acts ? acts + (size_t)b0 * 2 * 6 * H : nullptr))
             return -1;
     }
     return 0;

@@ -930,20 +930,23 @@ int lstm_scan(const float* G, const long long* lens, float* acts, int T, int Bq,
     return check_launch("lstm_scan");
 }
 
-// One backward timestep for both directions.  grid (H / LB_CH, 2); every CTA recomputes the element-wise gate
-// gradients of ALL hidden units of its direction (they are cheap and it needs all of them as the matvec input),
-// writes the ones of its own chunk to dG and the carried cell gradient, then produces its chunk of
-//     dh_{prev}[b, u'] = sum_r dG_t[b, r] * W_hh[r, u'],  r over the 4H gate rows.
+// One backward timestep for both directions.  grid (H / LB_CH, 2), one warp per output hidden unit; every CTA
+// recomputes the element-wise gate gradients of ALL hidden units of its direction (cheap, and the matvec needs all
+// of them), writes the ones of its own chunk to dG and the carried cell gradient, then produces its chunk of
+//     dh_{prev}[b, u'] = sum_r dG_t[b, r] * W_hh[r, u'],  r over the 4H gate rows
+// from the TRANSPOSED recurrent weight whh_t [2][H][4H]: row u' is one contiguous 16 KB stream per warp (float4 per
+// lane, fully coalesced, L2 resident after the first step) against the gate gradients in shared memory.
 // carry buffers are double buffered by step parity: [2][2 dir][Bq][H].
-constexpr int LB_CH = 16;          // hidden units (columns of W_hh) per CTA: 64 CTAs x 2 directions at H = 1024
+constexpr int LB_CH = 16;          // hidden units (rows of W_hh^T) per CTA = warps per CTA: 64 CTAs x 2 directions at H = 1024
 constexpr int LB_MAXB = 8;
+constexpr int LB_THREADS = 32 * LB_CH;
 
-__global__ void __launch_bounds__(256)
-lstm_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ acts, const float* __restrict__ whh,
+__global__ void __launch_bounds__(LB_THREADS)
+lstm_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ acts, const float* __restrict__ whh_t,
                      const long long* __restrict__ lens, float* __restrict__ dG, float* __restrict__ dh_carry,
                      float* __restrict__ dc_carry, int step, int T, int Bq, int H)
 {
-    extern __shared__ float dgs[];               // [Bq][4H] gate-pre-activation gradients of this step
+    extern __shared__ __align__(16) float dgs[];     // [Bq][4H] gate-pre-activation gradients of this step
     const int d = blockIdx.y, u0 = blockIdx.x * LB_CH;
     const int t = d == 0 ? T - 1 - step : step;
     const int par = step & 1;
@@ -951,7 +954,7 @@ lstm_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ a
     const float* dc_in = dc_carry + ((long long)(par * 2 + d) * Bq) * H;
     float* dh_out = dh_carry + ((long long)((par ^ 1) * 2 + d) * Bq) * H;
     float* dc_out = dc_carry + ((long long)((par ^ 1) * 2 + d) * Bq) * H;
-    for (int e = threadIdx.x; e < Bq * H; e += 256) {
+    for (int e = threadIdx.x; e < Bq * H; e += LB_THREADS) {
         const int b = e / H, u = e % H;
         const bool active = t < (int)lens[b];
         const long long row = (long long)t * Bq + b;
@@ -977,42 +980,40 @@ lstm_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ a
         }
     }
     __syncthreads();
-    // matvec: thread = (row group rg of 16, column uu); rows r = rg, rg + 16, ...
-    const int uu = threadIdx.x % LB_CH, rg = threadIdx.x / LB_CH;      // 16 x 16
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int uo = u0 + w;
+    const float4* wrow = reinterpret_cast<const float4*>(whh_t + ((long long)d * H + uo) * 4 * H);
     float acc[LB_MAXB];
 #pragma unroll
     for (int b = 0; b < LB_MAXB; ++b) acc[b] = 0.f;
-    const float* wbase = whh + (long long)d * 4 * H * H + u0 + uu;
-    for (int r = rg; r < 4 * H; r += 256 / LB_CH) {
-        const float w = __ldg(wbase + (long long)r * H);
+    for (int r4 = lane; r4 < H; r4 += 32) {          // 4H / 4 float4 per row
+        const float4 wv = __ldg(wrow + r4);
 #pragma unroll
         for (int b = 0; b < LB_MAXB; ++b)
-            if (b < Bq) acc[b] = fmaf(dgs[(long long)b * 4 * H + r], w, acc[b]);
+            if (b < Bq) {
+                const float4 g = *reinterpret_cast<const float4*>(dgs + (long long)b * 4 * H + 4 * r4);
+                acc[b] = fmaf(g.x, wv.x, fmaf(g.y, wv.y, fmaf(g.z, wv.z, fmaf(g.w, wv.w, acc[b]))));
+            }
     }
-    // reduce the 16 row groups: two warps share a row-group pair -> through shared memory
-    __shared__ float red2[256 / LB_CH][LB_MAXB][LB_CH];
 #pragma unroll
-    for (int b = 0; b < LB_MAXB; ++b) red2[rg][b][uu] = acc[b];
-    __syncthreads();
-    if (threadIdx.x < LB_CH * LB_MAXB) {
-        const int b = threadIdx.x / LB_CH, u = threadIdx.x % LB_CH;
+    for (int b = 0; b < LB_MAXB; ++b)
         if (b < Bq) {
-            float s = 0.f;
-#pragma unroll
-            for (int g = 0; g < 256 / LB_CH; ++g) s += red2[g][b][u];
-            const bool active = t < (int)lens[b];
-            const long long e = (long long)b * H + u0 + u;
-            dh_out[e] = active ? s : dh_in[e];
+            const float s = warp_sum(acc[b]);
+            if (lane == 0) {
+                const bool active = t < (int)lens[b];
+                const long long e = (long long)b * H + uo;
+                dh_out[e] = active ? s : dh_in[e];
+            }
         }
-    }
 }
 
-int lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const long long* lens, float* dG,
+int lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const long long* lens, float* dG,
                    float* carry_ws, int T, int Bq, int H, cudaStream_t st)
 {
     if (T == 0 || Bq == 0) return 0;
     VOG_REQUIRE(Bq <= LB_MAXB, "lstm_bwd_steps: at most %d sequences per call (got %d)", LB_MAXB, Bq);
-    VOG_REQUIRE(H % LB_CH == 0, "lstm_bwd_steps: H=%d must be a multiple of %d", H, LB_CH);
+    VOG_REQUIRE(H % LB_CH == 0 && H % 32 == 0, "lstm_bwd_steps: H=%d must be a multiple of 32", H);
+    VOG_REQUIRE((reinterpret_cast<uintptr_t>(whh_t) & 15) == 0, "lstm_bwd_steps: whh_t must be 16-byte aligned");
     const size_t carry = (size_t)2 * 2 * Bq * H;
     VOG_CUDA(cudaMemsetAsync(carry_ws, 0, 2 * carry * sizeof(float), st));
     float* dh_carry = carry_ws;
@@ -1021,7 +1022,7 @@ int lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const
     VOG_CUDA(cudaFuncSetAttribute(lstm_bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(H / LB_CH, 2);
     for (int s = 0; s < T; ++s) {
-        lstm_bwd_step_kernel<<<grid, 256, smem, st>>>(dout, acts, whh, lens, dG, dh_carry, dc_carry, s, T, Bq, H);
+        lstm_bwd_step_kernel<<<grid, LB_THREADS, smem, st>>>(dout, acts, whh_t, lens, dG, dh_carry, dc_carry, s, T, Bq, H);
         if (check_launch("lstm_bwd_step")) return -1;
     }
     return 0;

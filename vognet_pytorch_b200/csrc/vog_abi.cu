@@ -362,6 +362,17 @@ int vog_lstm_layer_fwd(const float* gx, int64_t ldg, const float* whh, const int
                           (cudaStream_t)stream);
 }
 
+int vog_lstm_layer_fwd_train(const float* gx, int64_t ldg, const float* whh, const int64_t* lens, int T, int Bq,
+                             int H, void* out_lp, int64_t ld_out, int lp_kind, void* workspace, float* acts,
+                             void* stream)
+{
+    VOG_REQUIRE(T >= 0 && Bq >= 0 && H > 0, "vog_lstm_layer_fwd_train: bad dimension");
+    if (T == 0 || Bq == 0) return 0;
+    VOG_REQUIRE(gx && whh && lens && out_lp && workspace && acts, "vog_lstm_layer_fwd_train: null operand");
+    return lstm_layer_fwd(gx, ldg, whh, (const long long*)lens, T, Bq, H, out_lp, ld_out, lp_kind, workspace,
+                          (cudaStream_t)stream, acts);
+}
+
 int vog_build_xmul(const float* vis, const float* lang, float* out, void* out_lp, int lp_kind, int B,
                    int nfrm, int nsrl, int nppf2, int dv, int dl, void* stream)
 {
@@ -570,12 +581,12 @@ int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int B
     return lstm_scan(G, (const long long*)lens, acts, T, Bq, H, (cudaStream_t)stream);
 }
 
-int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh, const int64_t* lens, float* dG,
+int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const int64_t* lens, float* dG,
                        float* carry_ws, int T, int Bq, int H, void* stream)
 {
     if (T * Bq == 0) return 0;
-    VOG_REQUIRE(dout && acts && whh && lens && dG && carry_ws && H > 0, "vog_lstm_bwd_steps: null operand");
-    return lstm_bwd_steps(dout, acts, whh, (const long long*)lens, dG, carry_ws, T, Bq, H, (cudaStream_t)stream);
+    VOG_REQUIRE(dout && acts && whh_t && lens && dG && carry_ws && H > 0, "vog_lstm_bwd_steps: null operand");
+    return lstm_bwd_steps(dout, acts, whh_t, (const long long*)lens, dG, carry_ws, T, Bq, H, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -417,8 +417,9 @@ def tc_attn_fwd(q, k, v, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, bi
     return out
 
 
-def lstm_layer_fwd(gx, whh, lens, T, Bq, kind):
-    """gx [T*Bq, 8H] fp32, whh [2,4H,H] fp32, lens [Bq] int64 -> h [T*Bq, 2H] (bf16 / tf32-rounded)."""
+def lstm_layer_fwd(gx, whh, lens, T, Bq, kind, want_acts=False):
+    """gx [T*Bq, 8H] fp32, whh [2,4H,H] fp32, lens [Bq] int64 -> h [T*Bq, 2H] (bf16 / tf32-rounded); with want_acts
+    also the per-step activations [T*Bq, 2, 6, H] the backward consumes (vog_lstm_layer_fwd_train)."""
     _req(gx, torch.float32, 'gx', 2), _req(whh, torch.float32, 'whh', 3), _req(lens, torch.int64, 'lens', 1)
     H = whh.shape[2]
     if whh.shape != (2, 4 * H, H) or not whh.is_contiguous() or gx.shape != (T * Bq, 8 * H):
@@ -426,6 +427,12 @@ def lstm_layer_fwd(gx, whh, lens, T, Bq, kind):
     L = _lib.lib()
     out = torch.empty(T * Bq, 2 * H, device=gx.device, dtype=_LP_DTYPE.get(kind, torch.float32))
     ws = torch.empty(L.vog_lstm_workspace_bytes(Bq, H), device=gx.device, dtype=torch.uint8)
+    if want_acts:
+        acts = torch.empty(T * Bq, 2, 6, H, device=gx.device, dtype=torch.float32)
+        _lib.check(L.vog_lstm_layer_fwd_train(_ptr(gx), _rowmajor2d(gx, 'gx'), _ptr(whh), _ptr(lens), T, Bq, H,
+                                              _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _ptr(acts), _stream()),
+                   'vog_lstm_layer_fwd_train')
+        return out, acts
     _lib.check(L.vog_lstm_layer_fwd(_ptr(gx), _rowmajor2d(gx, 'gx'), _ptr(whh), _ptr(lens), T, Bq, H,
                                     _ptr(out), _rowmajor2d(out, 'out'), kind, _ptr(ws), _stream()),
                'vog_lstm_layer_fwd')

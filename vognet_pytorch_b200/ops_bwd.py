@@ -178,12 +178,15 @@ def lstm_scan(G, lens, T, Bq):
     return acts
 
 
-def lstm_bwd_steps(dout, acts, whh, lens, T, Bq):
-    """dout [T*Bq, 2H] -> dG [T*Bq, 8H]; at most 8 sequences per call (callers chunk the batch)."""
-    H = whh.shape[2]
+def lstm_bwd_steps(dout, acts, whh_t, lens, T, Bq):
+    """dout [T*Bq, 2H] -> dG [T*Bq, 8H]; whh_t [2,H,4H] = the recurrent weights TRANSPOSED (whh.transpose(1,2));
+    at most 8 sequences per call (callers chunk the batch)."""
+    H = whh_t.shape[1]
+    if whh_t.shape != (2, H, 4 * H) or not whh_t.is_contiguous():
+        raise ValueError(f'lstm_bwd_steps: whh_t must be contiguous [2,H,4H], got {tuple(whh_t.shape)}')
     dG = torch.empty(T * Bq, 8 * H, device=dout.device, dtype=torch.float32)
     ws = torch.empty(8 * Bq * H, device=dout.device, dtype=torch.float32)
-    _lib.check(_lib.lib().vog_lstm_bwd_steps(_ptr(dout.contiguous()), _ptr(acts), _ptr(whh), _ptr(lens), _ptr(dG), _ptr(ws),
+    _lib.check(_lib.lib().vog_lstm_bwd_steps(_ptr(dout.contiguous()), _ptr(acts), _ptr(whh_t), _ptr(lens), _ptr(dG), _ptr(ws),
                                              T, Bq, H, _stream()), 'vog_lstm_bwd_steps')
     return dG
 

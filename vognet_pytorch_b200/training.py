@@ -35,21 +35,23 @@ def _zeros_like_param(p):
 
 
 class GradSink:
-    """name -> gradient tensor (fp32, zero-initialised on first touch; kernels accumulate into them)."""
+    """name -> gradient tensor (fp32, zero on first touch; kernels accumulate into them).  With `views` (name -> view
+    of an optimizer's flat gradient buffer, already zeroed) the kernels write straight into that buffer."""
 
-    def __init__(self, named_params):
+    def __init__(self, named_params, views=None):
         self.params = dict(named_params)
+        self.views = views
         self.g = {}
 
     def get(self, name):
         t = self.g.get(name)
         if t is None:
-            t = self.g[name] = _zeros_like_param(self.params[name])
+            t = self.g[name] = self.views[name] if self.views is not None else _zeros_like_param(self.params[name])
         return t
 
     def set(self, name, val):
-        if name in self.g:
-            self.g[name].add_(val.view_as(self.g[name]))
+        if self.views is not None or name in self.g:
+            self.get(name).add_(val.view_as(self.params[name]))
         else:
             self.g[name] = val.reshape(self.params[name].shape).contiguous()
 
@@ -61,11 +63,12 @@ class F32Backend:
     """Linear algebra of the training step in exact fp32 (vog_sgemm_nt / vog_sgemm_strided / vog_attn_*_f32)."""
     name = 'fp32x'
 
-    def linear(self, x, w, b=None, relu=False, residual=None):
-        return ops.sgemm_nt(x, w, b, residual=residual, relu=relu)
+    def linear(self, x, w, b=None, relu=False, residual=None, key=None, out=None, params=None):
+        return ops.sgemm_nt(x, w() if callable(w) else w, b, residual=residual, relu=relu, out=out)
 
-    def lin_dx(self, dy, w, residual=None):
+    def lin_dx(self, dy, w, residual=None, key=None, params=None):
         """dy [M,N] @ w [N,K] (+ residual)"""
+        w = w() if callable(w) else w
         if residual is None:
             return ob.sgemm(dy, w)
         out = residual.clone() if residual.is_contiguous() else residual.contiguous()
@@ -75,6 +78,43 @@ class F32Backend:
         """dy^T @ x -> [N,K]"""
         out = torch.zeros(dy.shape[1], x.shape[1], device=dy.device, dtype=torch.float32)
         return ob.sgemm(dy.t(), x, out=out, accumulate=True)
+
+
+class TcBackend:
+    """The same three contractions on tcgen05 with bf16 operands (fp32 accumulate): the skinny language-side GEMMs
+    (M = 20 words x B sentences against 8192 x 2048 LSTM matrices) are bound by streaming the weights, which the
+    bf16 copies halve and the TMA / tensor-core kernels actually reach.  Weight copies (plain and transposed) are
+    cached per parameter version in the model's PackCache under `key`."""
+    name = 'bf16'
+
+    def __init__(self, mdl):
+        self.packs = mdl._packs()
+
+    @staticmethod
+    def lp(x):
+        return x if x.dtype == torch.bfloat16 else ops.cast_lp(x, ops.LP_BF16)
+
+    def _w(self, w, key, params, transposed):
+        # `w` is a parameter, or a zero-argument callable that derives the matrix from LIVE parameters (the cache
+        # re-runs `build` when those change, so it must not close over a stale copy)
+        def build():
+            m = w() if callable(w) else w
+            t = m.detach().t() if transposed else m.detach()
+            return t.contiguous().to(torch.bfloat16)
+        if key is None:
+            return build()
+        return self.packs.get(('be', key, transposed), params if params is not None else (w,), build)
+
+    def linear(self, x, w, b=None, relu=False, residual=None, key=None, out=None, params=None):
+        o, _ = ops.tc_gemm(self.lp(x), self._w(w, key, params, False), bias=b, relu=relu, residual=residual, out_f32=out)
+        return o
+
+    def lin_dx(self, dy, w, residual=None, key=None, params=None):
+        o, _ = ops.tc_gemm(self.lp(dy), self._w(w, key, params, True), residual=residual)
+        return o
+
+    def lin_dw(self, dy, x):
+        return ob.tc_gemm_tn(self.lp(dy), self.lp(x))
 
 
 # =============================================================================================
@@ -188,9 +228,23 @@ def _drop(x, dc, p, site, **kw):
     return ob.dropout(x, p, dc.seed, site, **kw)[0]
 
 
-def lang_forward(mdl, inp, tp, dc):
-    """Language side of the training forward, exact fp32 in every compute mode (code/mdl_vog.py:67-140,250-283;
-    utils/mdl_srl_utils.py:114-169).  -> lang [B*nsrl, 256] fp32; activations into `tp`."""
+def _lstm_stacked(lstm, l):
+    """forward|reverse stacked matrices of layer l (fresh copies) and the parameters they derive from"""
+    names = [f'{n}_l{l}{s}' for n in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh') for s in ('', '_reverse')]
+    ps = tuple(getattr(lstm, n) for n in names)
+    with torch.no_grad():
+        wih = torch.cat([ps[0], ps[1]], 0)
+        whh = torch.stack([ps[2], ps[3]], 0).contiguous()
+        bias = torch.cat([ps[4] + ps[6], ps[5] + ps[7]], 0)
+    return wih, whh, bias, ps
+
+
+def lang_forward(mdl, inp, tp, dc, be=None):
+    """Language side of the training forward (code/mdl_vog.py:67-140,250-283; utils/mdl_srl_utils.py:114-169): exact
+    fp32 with the F32Backend, bf16 tensor-core GEMMs around the fp32 recurrence with the TcBackend.
+    -> lang [B*nsrl, 256] fp32; activations into `tp`."""
+    be = be if be is not None else F32Backend()
+    tp.lbe = be
     words = inp['srl_arg_words_ind']
     B, nv, nsrl, L = words.shape
     Bq = B * nv
@@ -202,22 +256,23 @@ def lang_forward(mdl, inp, tp, dc):
     x = ops.lang_embed(tp.words, wm, mdl.lstm_encoder.embed_tokens.weight, mdl.vocab_size, ops.LP_NONE)
     x = _drop(x, dc, dc.p_lstm, dc.LSTM_IN)
     tp.lstm = []
+    packs = mdl._packs()
     for l in range(lstm.num_layers):
-        wih = torch.cat([getattr(lstm, f'weight_ih_l{l}'), getattr(lstm, f'weight_ih_l{l}_reverse')], 0).detach()
-        bias = torch.cat([getattr(lstm, f'bias_ih_l{l}') + getattr(lstm, f'bias_hh_l{l}'),
-                          getattr(lstm, f'bias_ih_l{l}_reverse') + getattr(lstm, f'bias_hh_l{l}_reverse')], 0).detach()
-        whh = torch.stack([getattr(lstm, f'weight_hh_l{l}'), getattr(lstm, f'weight_hh_l{l}_reverse')], 0).detach().contiguous()
-        gx = ops.sgemm_nt(x, wih, bias)
-        hout = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_NONE)
-        tp.lstm.append(Tape(x=x, gx=gx, hout=hout, wih=wih, whh=whh))
+        ps = _lstm_stacked(lstm, l)[3]
+        # stacked forward|reverse matrices, rebuilt from the live parameters whenever those change
+        wih, whh, bias = packs.get(('lstm32', l), ps, lambda l=l: _lstm_stacked(lstm, l)[:3])
+        gx = be.linear(x, (lambda l=l: _lstm_stacked(lstm, l)[0]) if be.name != 'fp32x' else wih, bias, key=('wih', l),
+                       params=ps)
+        hout, acts = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_NONE, want_acts=True)
+        tp.lstm.append(Tape(x=x, hout=hout, acts=acts, wih=wih, ps=ps))
         last = l == lstm.num_layers - 1
         x = _drop(hout, dc, dc.p_lstm, dc.LSTM_OUT if last else dc.LSTM_MID + 10 * l)
     tp.top = x
     proj, enc = mdl.lstm_out_feat_proj[0], mdl.srl_arg_words_out_enc[0]
-    tp.full = ops.sgemm_nt(x, proj.weight, proj.bias, relu=True)                                  # [T*Bq, 256]
+    tp.full = be.linear(x, proj.weight, proj.bias, relu=True, key='proj')                         # [T*Bq, 256]
     tp.cap = inp['srl_arg_words_capture'].reshape(Bq, nsrl, 2).contiguous()
     tp.cat = ops.lang_gather(tp.full, tp.cap, T, Bq, ops.LP_NONE)
-    tp.enc = ops.sgemm_nt(tp.cat, enc.weight, enc.bias, relu=True)
+    tp.enc = be.linear(tp.cat, enc.weight, enc.bias, relu=True, key='enc')
     tp.smsk = inp['srl_arg_inds_msk'].reshape(Bq * nsrl).contiguous()
     lang, _ = ops.mask_rows(tp.enc, tp.smsk)                                                      # [B*nsrl, 256]
     return lang
@@ -225,16 +280,16 @@ def lang_forward(mdl, inp, tp, dc):
 
 def lang_backward(mdl, tp, dlang, sink, dc):
     """dlang [B*nsrl, 256] -> parameter gradients of the language side into `sink`."""
-    be = F32Backend()
+    be = tp.lbe
     Bq, T = tp.Bq, tp.T
     denc, _ = ops.mask_rows(dlang, tp.smsk)                                                # mask_rows backward
     ob.relu_bwd(denc, tp.enc, dbias=sink.get('srl_arg_words_out_enc.0.bias'), inplace=True)
     sink.set('srl_arg_words_out_enc.0.weight', be.lin_dw(denc, tp.cat))
-    dcat = be.lin_dx(denc, mdl.srl_arg_words_out_enc[0].weight)
+    dcat = be.lin_dx(denc, mdl.srl_arg_words_out_enc[0].weight, key='enc')
     dfull = ob.lang_gather_bwd(dcat, tp.cap, T, Bq)
     ob.relu_bwd(dfull, tp.full, dbias=sink.get('lstm_out_feat_proj.0.bias'), inplace=True)
     sink.set('lstm_out_feat_proj.0.weight', be.lin_dw(dfull, tp.top))
-    dtop = be.lin_dx(dfull, mdl.lstm_out_feat_proj[0].weight)
+    dtop = be.lin_dx(dfull, mdl.lstm_out_feat_proj[0].weight, key='proj')
     _lstm_backward(mdl, tp, dtop, sink, be, dc)
 
 
@@ -322,33 +377,35 @@ def _lstm_backward(mdl, tp, dx_top, sink, be, dc):
         lt = tp.lstm[l]
         last = l == lstm.num_layers - 1
         dout = _drop(dout, dc, dc.p_lstm, dc.LSTM_OUT if last else dc.LSTM_MID + 10 * l)   # output / inter-layer dropout
-        Hh = lt.whh.shape[2]
+        Hh = lstm.hidden_size
+        tc = be.name != 'fp32x'
         hprev = ob.lstm_hprev(lt.hout, lens, T, Bq)
-        G = lt.gx.clone()                                            # gate pre-activations of all steps (recomputed)
-        for d_ in range(2):
-            ob.sgemm(hprev[:, d_ * Hh:(d_ + 1) * Hh], lt.whh[d_].t(), out=G[:, d_ * 4 * Hh:(d_ + 1) * 4 * Hh],
-                     accumulate=True)
-        acts = ob.lstm_scan(G, lens, T, Bq)
-        dG = ob.lstm_bwd_steps(dout, acts, lt.whh, lens, T, Bq)        # [T*Bq, 8H]
+        whh_t = mdl._packs().get(('whhT', l), lt.ps, lambda l=l: _lstm_stacked(lstm, l)[1].transpose(1, 2).contiguous())
+        dG = ob.lstm_bwd_steps(dout, lt.acts, whh_t, lens, T, Bq)     # [T*Bq, 8H]; activations kept by the forward
         sfx = ('', '_reverse')
-        dwih = be.lin_dw(dG, lt.x)                                   # [8H, in]
+        dG_lp = be.lp(dG) if tc else dG
+        dwih = be.lin_dw(dG_lp, lt.x)                                # [8H, in]
         db = torch.zeros(8 * Hh, device=dG.device, dtype=torch.float32)
         ob.colsum_acc(dG, db)
+        hprev_lp = be.lp(hprev) if tc else hprev
         for d_ in range(2):
             sl = slice(d_ * 4 * Hh, (d_ + 1) * 4 * Hh)
             sink.set(f'lstm_encoder.lstm.weight_ih_l{l}{sfx[d_]}', dwih[sl])
             sink.set(f'lstm_encoder.lstm.bias_ih_l{l}{sfx[d_]}', db[sl])
             sink.set(f'lstm_encoder.lstm.bias_hh_l{l}{sfx[d_]}', db[sl].clone())
-            sink.set(f'lstm_encoder.lstm.weight_hh_l{l}{sfx[d_]}', be.lin_dw(dG[:, sl], hprev[:, d_ * Hh:(d_ + 1) * Hh]))
-        dout = be.lin_dx(dG, lt.wih)                                 # [T*Bq, in]
+            sink.set(f'lstm_encoder.lstm.weight_hh_l{l}{sfx[d_]}', be.lin_dw(dG_lp[:, sl], hprev_lp[:, d_ * Hh:(d_ + 1) * Hh]))
+        dout = be.lin_dx(dG_lp, (lambda l=l: _lstm_stacked(lstm, l)[0]) if tc else lt.wih, key=('wih', l),
+                         params=lt.ps)                                # [T*Bq, in]
     dout = _drop(dout, dc, dc.p_lstm, dc.LSTM_IN)
     ob.lang_embed_bwd(tp.words, tp.wm, dout, mdl.vocab_size, lens, sink.get('lstm_encoder.embed_tokens.weight'))
 
 
-def backward_train_f32(mdl, tp, dlogits):
-    """dlogits [B,1,nsrl,P] -> {parameter name: gradient}."""
+def backward_train_f32(mdl, tp, dlogits, sink=None, on_lang_done=None):
+    """dlogits [B,1,nsrl,P] -> {parameter name: gradient}.  The language side (82 % of the parameters: the LSTM) is
+    differentiated right after the multimodal transformer; `on_lang_done()` is called once its gradients are enqueued
+    (a data-parallel step starts their all-reduce there, behind the object transformer's backward)."""
     be = tp.be
-    sink = GradSink(mdl.named_parameters())
+    sink = sink if sink is not None else GradSink(mdl.named_parameters())
     B, P, nsrl, nfrm, nppf2, nppf, nvf, ncmp = tp.B, tp.P, tp.nsrl, tp.nfrm, tp.nppf2, tp.nppf, tp.nvf, tp.ncmp
     dl = dlogits.reshape(B, nsrl, P).contiguous().float()
     # ---- scorer
@@ -369,6 +426,10 @@ def backward_train_f32(mdl, tp, dlogits):
     # ---- tokens -> factors
     dlang = torch.zeros(B * nsrl, mdl.lang_dim, device=dxm.device, dtype=torch.float32)
     dvis = ob.xmul_bwd(dxm.contiguous(), dlang, B, nfrm, nsrl, nppf2, mdl.ps_dim)          # [B*P, 512]
+    # ---- language side
+    lang_backward(mdl, tp, dlang, sink, tp.dc)
+    if on_lang_done is not None:
+        on_lang_done()
     # ---- object transformer
     if tp.obj is not None:
         da = dbpe = None
@@ -387,8 +448,6 @@ def backward_train_f32(mdl, tp, dlogits):
     dseg = ob.seg_rep_bwd(dvis, tp.x0, pe_, se_, nppf)                                    # [B*nvf, 256] (ReLU applied)
     ob.colsum_acc(dseg, sink.get('seg_encoder.0.bias'))
     sink.set('seg_encoder.0.weight', be.lin_dw(dseg, tp.seg2))
-    # ---- language side
-    lang_backward(mdl, tp, dlang, sink, tp.dc)
     return sink.g
 
 

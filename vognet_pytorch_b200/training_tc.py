@@ -19,7 +19,7 @@ import math
 import torch
 
 from . import ops, ops_bwd as ob
-from .training import DropCtx, GradSink, Tape, dropout_active, lang_backward, lang_forward
+from .training import DropCtx, GradSink, Tape, TcBackend, dropout_active, lang_backward, lang_forward
 from .transformer_code import RelBias
 
 KIND = ops.LP_BF16
@@ -149,7 +149,7 @@ def forward_train_tc(mdl, inp):
     assert nv == 1 and nvf * nppf == P
     tp.update(B=B, P=P, ncmp=ncmp, nppf=nppf, nvf=nvf, nsrl=nsrl)
     dev = feat.device
-    lang = lang_forward(mdl, inp, tp, dc)
+    lang = lang_forward(mdl, inp, tp, dc, TcBackend(mdl))
 
     # ---- visual side: prop | seg rows written by the two encoder GEMMs (the seg half replicated over the proposals)
     pe_ = mdl.prop_encoder[0].out_features
@@ -159,7 +159,8 @@ def forward_train_tc(mdl, inp):
     tp.seg2 = seg.reshape(B * nvf, -1)
     ops.tc_gemm(tp.feat_lp, mdl._lp_weight('prop', mdl.prop_encoder[0].weight, KIND), bias=mdl.prop_encoder[0].bias,
                 relu=True, out_f32=x0[:, :pe_], out_lp=x0_lp[:, :pe_])
-    ops.tc_gemm(ops.cast_lp(tp.seg2, KIND), mdl._lp_weight('seg', mdl.seg_encoder[0].weight, KIND),
+    tp.seg_lp = ops.cast_lp(tp.seg2, KIND)
+    ops.tc_gemm(tp.seg_lp, mdl._lp_weight('seg', mdl.seg_encoder[0].weight, KIND),
                 bias=mdl.seg_encoder[0].bias, relu=True, out_f32=x0[:, pe_:], out_lp=x0_lp[:, pe_:], rep=nppf)
     tp.x0 = x0
     props2 = props.reshape(B * P, props.shape[-1])
@@ -205,10 +206,10 @@ def forward_train_tc(mdl, inp):
     return logits, tp
 
 
-def backward_train_tc(mdl, tp, dlogits):
-    """dlogits [B,1,nsrl,P] -> {parameter name: gradient (fp32)}."""
+def backward_train_tc(mdl, tp, dlogits, sink=None, on_lang_done=None):
+    """dlogits [B,1,nsrl,P] -> {parameter name: gradient (fp32)}; `sink` / `on_lang_done` as in training.backward_train_f32."""
     dc = tp.dc
-    sink = GradSink(mdl.named_parameters())
+    sink = sink if sink is not None else GradSink(mdl.named_parameters())
     B, P, nsrl, nfrm, nppf2, nppf = tp.B, tp.P, tp.nsrl, tp.nfrm, tp.nppf2, tp.nppf
     dl = dlogits.reshape(B, nsrl, P).contiguous().float()
     # ---- scorer
@@ -230,6 +231,10 @@ def backward_train_tc(mdl, tp, dlogits):
     # ---- tokens -> factors
     dlang = torch.zeros(B * nsrl, mdl.lang_dim, device=dxm.device, dtype=torch.float32)
     dvis = ob.xmul_bwd(dxm.contiguous(), dlang, B, nfrm, nsrl, nppf2, mdl.ps_dim)          # [B*P, 512]
+    # ---- language side (exact fp32), before the object transformer: see training.backward_train_f32
+    lang_backward(mdl, tp, dlang, sink, dc)
+    if on_lang_done is not None:
+        on_lang_done()
     # ---- object transformer
     if tp.obj is not None:
         da = dbpe = None
@@ -248,8 +253,5 @@ def backward_train_tc(mdl, tp, dlogits):
     sink.set('prop_encoder.0.weight', ob.tc_gemm_tn(dprop_lp, tp.feat_lp))
     dseg = ob.seg_rep_bwd(dvis, tp.x0, pe_, se_, nppf)                                    # [B*nvf, 256] (ReLU applied)
     ob.colsum_acc(dseg, sink.get('seg_encoder.0.bias'))
-    dwseg = torch.zeros_like(mdl.seg_encoder[0].weight)
-    sink.set('seg_encoder.0.weight', ob.sgemm(dseg.t(), tp.seg2, out=dwseg, accumulate=True))
-    # ---- language side (exact fp32)
-    lang_backward(mdl, tp, dlang, sink, dc)
+    sink.set('seg_encoder.0.weight', ob.tc_gemm_tn(ops.cast_lp(dseg, KIND), tp.seg_lp))
     return sink.g
