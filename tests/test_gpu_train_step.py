@@ -73,7 +73,11 @@ import torch, torch.distributed as dist
 rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
 torch.cuda.set_device(rank)
 dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
-from tests.test_gpu_train_step import _setup
+import importlib.util
+_spec = importlib.util.spec_from_file_location('vog_train_step_tests', os.path.join(sys.argv[1], 'tests', 'test_gpu_train_step.py'))
+_mod = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_mod)
+_setup = _mod._setup
 from vognet_pytorch_b200.train_step import FusedTrainStep
 from vognet_pytorch_b200 import runtime
 dev = f'cuda:{rank}'

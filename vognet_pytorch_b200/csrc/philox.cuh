@@ -39,4 +39,20 @@ __device__ __forceinline__ void attn_rand16x8(unsigned long long seed, uint32_t 
     out[0] = r[0]; out[1] = r[1]; out[2] = r[2]; out[3] = r[3];
 }
 
+// Attention probabilities (N x N elements per head: the only call site where the generator itself shows up in the
+// profile) use 8-bit uniforms, sixteen per Philox call: keep iff byte >= round(p * 256), and 1 / keep-probability is
+// taken from the REALISED threshold so that E[mask / (1 - p_eff)] = 1 exactly (p = 0.2 -> p_eff = 51/256 = 0.1992).
+__host__ __device__ inline uint32_t drop_threshold8(float p) {
+    const float t = p * 256.f + 0.5f;
+    return t <= 0.f ? 0u : (t >= 255.f ? 255u : (uint32_t)t);
+}
+__host__ __device__ inline float drop_inv_keep8(float p) { return 256.f / (256.f - (float)drop_threshold8(p)); }
+
+// sixteen 8-bit uniforms for columns col0 .. col0+15 (col0 % 16 == 0) of (stream, row): byte e & 3 of out[e >> 2]
+__device__ __forceinline__ void attn_rand8x16(unsigned long long seed, uint32_t stream, uint32_t row, uint32_t col0,
+                                              uint32_t (&out)[4])
+{
+    philox4x32_7(col0 >> 4, row, stream, 0xa77eu, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+}
+
 }  // namespace vog

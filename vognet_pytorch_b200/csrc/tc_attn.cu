@@ -787,15 +787,15 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
             if (p.drop_p > 0.f) {
                 // dropout AFTER the softmax: the row sum keeps every probability, the PV product only the kept ones,
                 // scaled by 1/(1-p); the mask is regenerated by the backward from the same counters
-                const float inv_keep = 1.f / (1.f - p.drop_p);
-                const uint32_t thr = drop_threshold16(p.drop_p);
+                const float inv_keep = drop_inv_keep8(p.drop_p);
+                const uint32_t thr = drop_threshold8(p.drop_p);
 #pragma unroll
-                for (int c = 0; c < EL; c += 8) {
+                for (int c = 0; c < EL; c += 16) {
                     uint32_t rnd[4];
-                    attn_rand16x8(p.seed, (uint32_t)bh, (uint32_t)qi, (uint32_t)(j * FA_BKV + part * EL + c), rnd);
+                    attn_rand8x16(p.seed, (uint32_t)bh, (uint32_t)qi, (uint32_t)(j * FA_BKV + part * EL + c), rnd);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        sv[c + e] = ((rnd[e >> 1] >> (16 * (e & 1))) & 0xffffu) >= thr ? sv[c + e] * inv_keep : 0.f;
+                    for (int e = 0; e < 16; ++e)
+                        sv[c + e] = ((rnd[e >> 2] >> (8 * (e & 3))) & 0xffu) >= thr ? sv[c + e] * inv_keep : 0.f;
                 }
             }
             VOG_PROF(5)

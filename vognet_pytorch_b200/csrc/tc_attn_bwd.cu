@@ -30,7 +30,8 @@ namespace vog {
 using namespace tc;
 
 constexpr int AB_T = 128;                          // tile edge: 128 queries x 128 keys
-constexpr int AB_EPI_WARPS = 8;
+constexpr int AB_EPI_WARPS = 8;                    // two per TMEM lane quarter: 64 key columns each, 16 at a time
+constexpr int AB_WCOLS = AB_T / (AB_EPI_WARPS / 4);  // key columns per epilogue warp
 constexpr int AB_THREADS = 64 + 32 * AB_EPI_WARPS;
 constexpr int AB_STAGES = 3;
 constexpr int AB_CHUNK = AB_T * 128;               // [128 rows x 64 bf16], 128B-swizzled
@@ -166,14 +167,17 @@ tc_attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_c
             }
         }
     } else {
-        // ================= epilogue: thread = query row, warp (g, half) = lane quarter g, key columns [64*half, +64) ====
-        const int g = warp & 3, half = (warp - 2) >> 2;
-        const int et = threadIdx.x - 64;                         // 0..255
+        // ================= epilogue: thread = query row; warp (g, cq) = TMEM lane quarter g, key columns
+        // [AB_WCOLS*cq, +AB_WCOLS), processed 16 at a time (one Philox call, one 32-byte store per tensor; no spills:
+        // local-memory reloads miss the L1 that the streaming stores keep flushing) ====
+        const int g = warp & 3, cq = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;                         // 0..511
         const uint32_t lane_addr = (uint32_t)(32 * g) << 16;
         const bool rel = p.bias_mode == 1;
         const bool drop = p.drop_p > 0.f;
-        const float inv_keep = drop ? 1.f / (1.f - p.drop_p) : 1.f;
-        const uint32_t thr = drop_threshold16(p.drop_p);
+        const float inv_keep = drop ? drop_inv_keep8(p.drop_p) : 1.f;
+        const uint32_t thr = drop_threshold8(p.drop_p);
+        const float k2 = p.inv_scale * inv_keep;
         int acc = 0; uint32_t acc_ph = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int bh = item / p.qtiles, qt = item - bh * p.qtiles;
@@ -183,88 +187,88 @@ tc_attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_c
             float lse = 0.f, dlt = 0.f, ai = 0.f;
             if (row_ok) {
                 lse = __ldg(p.lse + (size_t)bh * p.N + qi);
-                dlt = __ldg(p.delta + (size_t)bh * p.N + qi);
+                dlt = __ldg(p.delta + (size_t)bh * p.N + qi) * p.inv_scale;
                 if (rel) ai = (__ldg(p.a + ((size_t)bt * p.nbox + qi % p.nbox) * p.H + h) + __ldg(p.bpe + h)) * p.c;
             }
-            float rowsum = 0.f;
+            float rowsum0 = 0.f, rowsum1 = 0.f;
             const size_t rowoff = ((size_t)bh * p.Npad + qi) * p.Npad;
+            const float* akrow = p.ak + (size_t)bh * p.ak_ld + AB_WCOLS * cq;
+            float4 an[4];                                        // bias factors of the NEXT half: loaded one half ahead
+            if (rel) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) an[j4] = __ldg(reinterpret_cast<const float4*>(akrow) + j4);
+            }
             for (int kt = 0; kt < p.ktiles; ++kt) {
                 mbar_wait(tfull_bar(acc), acc_ph);
                 tc_fence_after();
-                const uint32_t t_s = tmem_base + lane_addr + acc * 256, t_dp = t_s + 128;
+                const uint32_t t_s = tmem_base + lane_addr + acc * 256 + AB_WCOLS * cq, t_dp = t_s + 128;
+                const bool edge = (qt == p.qtiles - 1 || kt == p.ktiles - 1) && p.N != p.Npad;
 #pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c0 = half * 64 + cc * 32;
-                    const int key0 = kt * AB_T + c0;
-                    uint32_t rs[32], rp[32];
-                    tmem_ld32(t_s + c0, rs);
-                    tmem_ld32(t_dp + c0, rp);
-                    float aj[32];
+                for (int hh = 0; hh < AB_WCOLS / 16; ++hh) {
+                    const int key0 = kt * AB_T + AB_WCOLS * cq + 16 * hh;
+                    uint32_t rs[16], rp[16];
+                    tmem_ld16(t_s + 16 * hh, rs);
+                    tmem_ld16(t_dp + 16 * hh, rp);
+                    float aj[16];
                     if (rel) {
-                        const float4* ak4 = reinterpret_cast<const float4*>(p.ak + (size_t)bh * p.ak_ld + key0);
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 t = __ldg(ak4 + j4);
-                            aj[4 * j4] = t.x; aj[4 * j4 + 1] = t.y; aj[4 * j4 + 2] = t.z; aj[4 * j4 + 3] = t.w;
+                        for (int j4 = 0; j4 < 4; ++j4) { aj[4 * j4] = an[j4].x; aj[4 * j4 + 1] = an[j4].y; aj[4 * j4 + 2] = an[j4].z; aj[4 * j4 + 3] = an[j4].w; }
+                        // next half (next tile's first half after the second one); the row is padded to Npad
+                        const int nk = hh + 1 < AB_WCOLS / 16 ? key0 + 16 : (kt + 1 < p.ktiles ? key0 + AB_T - AB_WCOLS + 16 : -1);
+                        if (nk >= 0) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4)
+                                an[j4] = __ldg(reinterpret_cast<const float4*>(p.ak + (size_t)bh * p.ak_ld + nk) + j4);
                         }
                     }
-                    uint32_t rnd[16];
-                    if (drop) {
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) attn_rand16x8(p.seed, (uint32_t)bh, (uint32_t)qi, (uint32_t)(key0 + 8 * j8), &rnd[4 * j8]);
-                    }
+                    uint32_t rnd[4];
+                    if (drop) attn_rand8x16(p.seed, (uint32_t)bh, (uint32_t)qi, (uint32_t)key0, rnd);
                     tmem_wait_ld();
-                    float gv[32];
-                    uint32_t pw[16], gw[16];
+                    float gv[16];
+                    uint32_t pw[8], gw[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
+                    for (int j = 0; j < 16; j += 2) {
                         float pj[2], gj[2];
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int jj = j + e;
-                            const float sraw = __uint_as_float(rs[jj]);
-                            float dp = __uint_as_float(rp[jj]);
                             const float bdiff = rel ? ai - aj[jj] : 0.f;
-                            const float t = fmaf(sraw, p.c, fmaxf(bdiff, 0.f));
-                            const bool valid = row_ok && (key0 + jj < p.N);
-                            float pr = valid ? ab_exp2(t - lse) : 0.f;
+                            const float t = fmaf(__uint_as_float(rs[jj]), p.c, fmaxf(bdiff, 0.f)) - lse;
+                            float pr = ab_exp2(t);
+                            if (edge) pr = (row_ok && key0 + jj < p.N) ? pr : 0.f;
+                            float base = fmaf(__uint_as_float(rp[jj]), k2, -dlt);   // (dP o mask / keep - delta) / sqrt(d_model)
                             float pstore = pr;
                             if (drop) {
-                                const bool keep = ((rnd[jj >> 1] >> (16 * (jj & 1))) & 0xffffu) >= thr;
+                                const bool keep = ((rnd[jj >> 2] >> (8 * (jj & 3))) & 0xffu) >= thr;
                                 pstore = keep ? pr * inv_keep : 0.f;
-                                dp = keep ? dp * inv_keep : 0.f;
+                                base = keep ? base : -dlt;
                             }
-                            const float gg = pr * (dp - dlt) * p.inv_scale;
+                            const float gg = pr * base;
                             pj[e] = pstore; gj[e] = gg;
                             const float gm = bdiff > 0.f ? gg : 0.f;
                             gv[jj] = gm;
-                            rowsum += gm;
+                            if (e == 0) rowsum0 += gm; else rowsum1 += gm;
                         }
                         pw[j >> 1] = pack_bf16(pj[0], pj[1]);
                         gw[j >> 1] = pack_bf16(gj[0], gj[1]);
                     }
-                    {
-                        uint4* pd = reinterpret_cast<uint4*>(p.P + rowoff + key0);
-                        uint4* gd = reinterpret_cast<uint4*>(p.dS + rowoff + key0);
-#pragma unroll
-                        for (int v4 = 0; v4 < 4; ++v4) {
-                            pd[v4] = make_uint4(pw[4 * v4], pw[4 * v4 + 1], pw[4 * v4 + 2], pw[4 * v4 + 3]);
-                            gd[v4] = make_uint4(gw[4 * v4], gw[4 * v4 + 1], gw[4 * v4 + 2], gw[4 * v4 + 3]);
-                        }
-                    }
+                    st_global_v8(p.P + rowoff + key0, pw);            // 16 bf16 = one 32-byte sector per thread
+                    st_global_v8(p.dS + rowoff + key0, gw);
                     if (rel) {
-                        // column sums over the warp's 32 rows: butterfly reduce-scatter, lane l ends with column c0 + l
+                        // column sums over the warp's 32 rows: butterfly reduce-scatter of 16 values, lanes 2c and 2c+1
+                        // end with column key0 + c
 #pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) {
+                        for (int off = 16; off >= 2; off >>= 1) {
 #pragma unroll
-                            for (int k = 0; k < off; ++k) {
+                            for (int k = 0; k < off / 2; ++k) {
                                 const bool up = (lane & off) != 0;
-                                const float send = up ? gv[k] : gv[k + off];
-                                const float keepv = up ? gv[k + off] : gv[k];
+                                const float send = up ? gv[k] : gv[k + off / 2];
+                                const float keepv = up ? gv[k + off / 2] : gv[k];
                                 gv[k] = keepv + __shfl_xor_sync(0xffffffffu, send, off);
                             }
                         }
-                        colsc[g * AB_T + c0 + lane] = gv[0];
+                        gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 1);
+                        if ((lane & 1) == 0) colsc[g * AB_T + AB_WCOLS * cq + 16 * hh + (lane >> 1)] = gv[0];
                     }
                 }
                 tc_fence_before();
@@ -282,7 +286,7 @@ tc_attn_bwd_sdp_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_c
                     ab_epi_bar();
                 }
             }
-            if (rel && row_ok) atomicAdd(p.drow + (size_t)bh * p.N + qi, rowsum);
+            if (rel && row_ok) atomicAdd(p.drow + (size_t)bh * p.N + qi, rowsum0 + rowsum1);
         }
     }
     tc_fence_before();
@@ -410,13 +414,11 @@ tc_bgemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                 tmem_ld32(t_acc + c0, r);
                 tmem_wait_ld();
                 if (m < p.N) {
-                    uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+                    uint32_t w[16];
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4)
-                        dst[v4] = make_uint4(pack_bf16(__uint_as_float(r[8 * v4]), __uint_as_float(r[8 * v4 + 1])),
-                                             pack_bf16(__uint_as_float(r[8 * v4 + 2]), __uint_as_float(r[8 * v4 + 3])),
-                                             pack_bf16(__uint_as_float(r[8 * v4 + 4]), __uint_as_float(r[8 * v4 + 5])),
-                                             pack_bf16(__uint_as_float(r[8 * v4 + 6]), __uint_as_float(r[8 * v4 + 7])));
+                    for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                    st_global_v8(orow + c0, w);
+                    st_global_v8(orow + c0 + 16, w + 8);
                 }
             }
             tc_fence_before();

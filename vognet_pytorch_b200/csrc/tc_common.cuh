@@ -279,6 +279,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per thread and request - row-per-thread epilogues
+// that scatter 16-byte pieces over 32 different rows are bound by the number of partial-sector requests
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
