@@ -308,7 +308,9 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        # a rank that dies must not leave the others (and the box) waiting for the default 10-minute watchdog
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     L = _lib.lib()
@@ -350,26 +352,28 @@ def main():
         out = ctx['mdl'](b)
         return out, ctx['ev'].get_out_results_boxes(out, b)
 
-    def time_resident(ctx, steps, warmup):
-        """K steps on the resident batch, L2 flushed between steps, one CUDA-event pair per step; max over ranks."""
+    def time_resident(ctx, steps, warmup, local=False):
+        """K steps on the resident batch, L2 flushed between steps, one CUDA-event pair per step; max over ranks.
+        local=True: a rank-0-only sub-object - NO collective (the other ranks have left by then)."""
+        sync = torch.cuda.synchronize if local else barrier
         for _ in range(warmup):
             fwd_step(ctx, ctx['resident'])
-        barrier()
+        sync()
         e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         n0 = L.vog_launch_count()
-        barrier()
+        sync()
         for i in range(steps):
             flush.zero_()
             e0[i].record()
             fwd_step(ctx, ctx['resident'])
             e1[i].record()
-        barrier()
+        sync()
         launches = (L.vog_launch_count() - n0) // steps          # eager launches of libvog_b200 per step
         if ctx['mdl'].use_cuda_graph:                             # + the kernels captured in the replayed graph
             launches += int(getattr(ctx['mdl'], 'graph_launches', 0))
         per = [a.elapsed_time(b) for a, b in zip(e0, e1)]
-        return max_ranks(sum(per)), per, launches
+        return (sum(per) if local else max_ranks(sum(per))), per, launches
 
     if args.train:
         return run_train(args, dev, world, rank, sampler, flush, barrier, max_ranks)
@@ -473,7 +477,7 @@ def main():
         #     number with fp32 arithmetic end to end; the headline runs tf32 GEMMs + bf16 attention operands)
         if compute != 'fp32x':
             cx = build(args.workload, 'fp32x', False)
-            tx, _, lx = time_resident(cx, sub_steps, 3)
+            tx, _, lx = time_resident(cx, sub_steps, 3, local=True)
             extras['value_fp32x'] = {'value': B * sub_steps / (tx / 1e3), 'unit': 'queries/s', 'ms_per_step': tx / sub_steps,
                                      'steps': sub_steps, 'gpu_launches': int(lx),
                                      'note': "compute='fp32x': every product and sum in IEEE fp32 on CUDA cores, eager launches"}
@@ -487,7 +491,7 @@ def main():
         # (c) the north-star shape: full spat/p100 bs=4 forward (obj N=4000, mul N=2000), resident, CUDA graph
         if args.workload != 'spat_p100' and world == 1:
             cn = build('spat_p100', 'bf16')
-            tn, _, ln = time_resident(cn, sub_steps, 3)
+            tn, _, ln = time_resident(cn, sub_steps, 3, local=True)
             fq = flops_query(cn['w']) * cn['w']['B']
             tf = fq / (tn / sub_steps * 1e-3) / 1e12
             ns = {'workload': 'spat_p100', 'per_gpu_batch': cn['w']['B'], 'value': cn['w']['B'] * sub_steps / (tn / 1e3),

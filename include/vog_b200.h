@@ -372,6 +372,19 @@ int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int B
 int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const int64_t* lens, float* dG,
                        float* carry_ws, int T, int Bq, int H, void* stream);
 
+/* Weight packing of one attention block for the tensor-core entry points: wq, wk, wv, wo
+ * fp32 [d,d] (nn.Linear layout) -> wqkv [3*H*dhp, d] with the rows of every head zero-padded to dhp (row
+ * (which*H + h)*dhp + r) and wo_p [d, H*dhp] with the matching zero-padded columns, as bf16 (VOG_LP_BF16) or
+ * tf32-rounded fp32 (VOG_LP_TF32).  dh[H] = torch.chunk head widths (code/transformer_code.py:169-186). */
+int vog_pack_weights(const float* wq, const float* wk, const float* wv, const float* wo, int d, int H, const int* dh,
+                     int dhp, int lp_kind, void* wqkv, void* wo_p, void* stream);
+
+/* One workspace query for every entry point that takes a caller-provided workspace: op = VOG_WS_* ; the
+ * dimensions a, b, c, d, e mean (M, N, K, tf32, BN) for VOG_WS_TC_GEMM, (Bt, N, H) for VOG_WS_TC_ATTN and
+ * VOG_WS_TC_ATTN_BWD, (Bq, H) for VOG_WS_LSTM, (B, nsrl, P) for VOG_WS_LOSS; unused ones are ignored. */
+enum { VOG_WS_TC_GEMM = 0, VOG_WS_TC_ATTN = 1, VOG_WS_TC_ATTN_BWD = 2, VOG_WS_LSTM = 3, VOG_WS_LOSS = 4 };
+int64_t vog_workspace_bytes(int op, int a, int b, int c, int d, int e);
+
 /* ---- training step on the tensor cores (compute mode 'bf16') ---------------------------------------------------
  * vog_tc_attn_fwd_train: vog_tc_attn_fwd that also keeps lse [Bt,H,N] (log2-domain log-sum-exp of every score row -
  * all the backward needs instead of the N x N probabilities) and applies dropout with probability drop_p to the

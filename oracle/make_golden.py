@@ -243,6 +243,55 @@ def loss_case(name):
     print(f'loss_{name}: loss {float(res["loss"]):.6f}  positives {int(tg.sum())} of {tg.numel()}')
 
 
+# (weight seed, input seed, feature scale) combinations of the parity sweep: scores of the
+# unmodified reference for every BASELINE configuration under different weights, inputs and feature magnitudes
+SWEEP = {
+    'spat_gt5': [(0, 1, 1.0), (1, 2, 1.0), (2, 3, 0.5), (3, 4, 2.0), (4, 5, 1.0), (5, 6, 0.5), (6, 7, 2.0), (7, 8, 1.0)],
+    'temp_gt5': [(0, 1, 1.0), (1, 2, 1.0), (2, 3, 0.5), (3, 4, 2.0), (4, 5, 1.0), (5, 6, 0.5), (6, 7, 2.0), (7, 8, 1.0)],
+    'spat_p100': [(1, 2, 1.0), (2, 3, 0.5), (3, 4, 2.0), (4, 5, 1.0)],
+}
+
+
+def sweep_batch(name, iseed, fscale):
+    """the workload `name` with another input seed and the visual features scaled by `fscale`"""
+    w, batch = synth.workload(name, seed=iseed)
+    batch = dict(batch)
+    for k in ('pad_region_feature', 'seg_feature_for_frms'):
+        batch[k] = batch[k] * fscale
+    return w, batch
+
+
+def sweep_case(name):
+    """-> tests/golden/sweep_{name}.npz: masked scores of the unmodified reference for every combination of SWEEP
+    (fp16 storage would lose the 1e-3 tolerance: kept as fp32, compressed)."""
+    save = {'combos': np.array(SWEEP[name], dtype=np.float64)}
+    for i, (ws, iseed, fs) in enumerate(SWEEP[name]):
+        w, batch = sweep_batch(name, iseed, fs)
+        mdl = rh.build_reference_model(w['conc_type'], w['nppf'], synth.make_state_dict(seed=ws))
+        with torch.no_grad():
+            out = mdl(synth.clone_batch(batch))
+        save[f'scores_{i}'] = out['mdl_outs_eval'].numpy()
+        print(f'sweep_{name}[{i}] weights {ws} inputs {iseed} x{fs}: logits std {out["mdl_outs"].std():.3f} '
+              f'score range {float(out["mdl_outs_eval"].min()):.3f}..{float(out["mdl_outs_eval"].max()):.3f}')
+    np.savez_compressed(os.path.join(GOLD, f'sweep_{name}.npz'), **save)
+
+
+def operator_case_n2000(name='rel_d768_h3_l1_n2000', d=768, n_heads=3, Bt=2, N=2000, seed=5, stride=16):
+    """The operator-level boundary at the north-star sequence length: RelTransformer(x, x_pe) with the reference's
+    DENSE x_pe [Bt,N,N,H] (96 MB) -> every `stride`-th output row."""
+    tc = rh.reference_transformers()
+    sd = synth.make_operator_state_dict(d, 1, seed=seed)
+    x, pe = synth.make_operator_inputs(d, n_heads, Bt, N, seed=seed)
+    m = tc.RelTransformer(d, 0, 0, d_hidden=d // 2, n_layers=1, n_heads=n_heads, drop_ratio=0.2, pe=False, d_pe=5)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        y = m(x, pe)
+    np.savez_compressed(os.path.join(GOLD, f'op_{name}.npz'), y_rows=y.reshape(-1, d)[::stride].contiguous().numpy(),
+                        meta=np.array([d, n_heads, 1, Bt, N, 1, seed, stride]))
+    print(f'op_{name}: y {tuple(y.shape)} std {y.std():.3f}, {y.reshape(-1, d)[::stride].shape[0]} rows kept')
+
+
 OPS = {
     'rel_d512_h3_l2':  dict(d=512, n_heads=3, n_layers=2, Bt=2, N=37, rel=True),
     'rel_d768_h3_l1':  dict(d=768, n_heads=3, n_layers=1, Bt=3, N=50, rel=True),
@@ -280,3 +329,8 @@ if __name__ == '__main__':
             cfg_variant_case(tag)
     if not want or 'grad_cpu_ref' in want:
         param_grad_case('cpu_ref')
+    for nm in SWEEP:
+        if not want or ('sweep_' + nm) in want:
+            sweep_case(nm)
+    if not want or 'op_rel_d768_h3_l1_n2000' in want:
+        operator_case_n2000()

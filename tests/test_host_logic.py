@@ -136,7 +136,8 @@ def test_ctypes_signatures_match_the_header():
     hdr = re.sub(r'/\*.*?\*/', ' ', hdr, flags=re.S)
     decls = re.findall(r'\b(vog_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', hdr, flags=re.S)
     assert len(decls) >= 40
-    ctype_of = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float, 'double': ctypes.c_double}
+    ctype_of = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64, 'float': ctypes.c_float,
+                'double': ctypes.c_double}
     for name, args in decls:
         args = ' '.join(args.split())
         params = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]

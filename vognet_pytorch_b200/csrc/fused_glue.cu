@@ -206,4 +206,58 @@ int mask_rows(const float* x, const long long* msk, int rows, int D, float* out,
     return check_launch("mask_rows");
 }
 
+
+// =============================================================================================
+// Weight packing of one attention block for the tensor-core path: per-head zero-padded Wq | Wk | Wv rows
+// ([3*H*dhp, d]: row (which*H + h)*dhp + r = W_which[off_h + r, :] for r < dh_h, else 0) and Wo with matching
+// zero-padded columns ([d, H*dhp]), cast to bf16 or tf32-rounded fp32.  torch.chunk head split of
+// code/transformer_code.py:169-186.
+// =============================================================================================
+struct PackParams { int d, H, dhp, kind; int off[VOG_MAX_HEADS], dh[VOG_MAX_HEADS]; };
+
+__device__ __forceinline__ void pack_store(void* dst, long long idx, float v, int kind) {
+    if (kind == 1) reinterpret_cast<__nv_bfloat16*>(dst)[idx] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dst)[idx] = to_tf32(v);
+}
+
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ wq, const float* __restrict__ wk, const float* __restrict__ wv,
+                    const float* __restrict__ wo, void* __restrict__ wqkv, void* __restrict__ wo_p, PackParams p)
+{
+    const long long n1 = 3LL * p.H * p.dhp * p.d, n2 = (long long)p.d * p.H * p.dhp;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n1) {
+        const int c = (int)(idx % p.d);
+        const int row = (int)(idx / p.d);
+        const int r = row % p.dhp, wh = row / p.dhp;
+        const int h = wh % p.H, which = wh / p.H;
+        const float* w = which == 0 ? wq : (which == 1 ? wk : wv);
+        pack_store(wqkv, idx, r < p.dh[h] ? w[(size_t)(p.off[h] + r) * p.d + c] : 0.f, p.kind);
+    } else if (idx < n1 + n2) {
+        const long long j = idx - n1;
+        const int col = (int)(j % (p.H * p.dhp));
+        const int row = (int)(j / (p.H * p.dhp));
+        const int h = col / p.dhp, r = col % p.dhp;
+        pack_store(wo_p, j, r < p.dh[h] ? wo[(size_t)row * p.d + p.off[h] + r] : 0.f, p.kind);
+    }
+}
+
+int pack_weights(const float* wq, const float* wk, const float* wv, const float* wo, int d, int H, const int* dh, int dhp,
+                 int lp_kind, void* wqkv, void* wo_p, cudaStream_t st)
+{
+    VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS && d > 0 && dhp > 0, "pack_weights: bad geometry");
+    VOG_REQUIRE(lp_kind == 1 || lp_kind == 2, "pack_weights: lp_kind must be VOG_LP_BF16 or VOG_LP_TF32");
+    PackParams p;
+    p.d = d; p.H = H; p.dhp = dhp; p.kind = lp_kind;
+    int off = 0;
+    for (int h = 0; h < H; ++h) {
+        VOG_REQUIRE(dh[h] >= 1 && dh[h] <= dhp, "pack_weights: head dim %d does not fit dhp=%d", dh[h], dhp);
+        p.off[h] = off; p.dh[h] = dh[h]; off += dh[h];
+    }
+    VOG_REQUIRE(off == d, "pack_weights: head dims sum to %d, d_model is %d", off, d);
+    const long long n = 4LL * H * dhp * d;
+    pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wq, wk, wv, wo, wqkv, wo_p, p);
+    return check_launch("pack_weights");
+}
+
 }  // namespace vog

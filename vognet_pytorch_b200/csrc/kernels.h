@@ -112,6 +112,8 @@ int lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const l
               const long long* cmp_msk, float* logits, float* scores, int B, int nfrm, int nsrl, int nppf2,
               int K, int ncmp, int nppf, int nfrm0, int spat, cudaStream_t st);
 
+int pack_weights(const float* wq, const float* wk, const float* wv, const float* wo, int d, int H, const int* dh, int dhp,
+                 int lp_kind, void* wqkv, void* wo_p, cudaStream_t st);
 int lang_embed(const long long* words, int nwords, const long long* mask, int T, const float* emb, int E,
                long long pad_idx, int Bq, void* out_lp, int lp_kind, cudaStream_t st);
 int lang_gather(const float* full, int D, const long long* cap, int T, int Bq, int nsrl, void* out_lp, int lp_kind,

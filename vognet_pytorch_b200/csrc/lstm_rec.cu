@@ -531,12 +531,12 @@ static int launch_resident(const LstmResParams& p, int ctas, int threads, cudaSt
     return check_launch("lstm_rec_resident");
 }
 
-static int g_lstm_force_streaming = 0;
-static int g_lstm_max_ctas = 0;
+static thread_local int g_lstm_force_streaming = 0;
+static thread_local int g_lstm_max_ctas = 0;
 void lstm_set_max_ctas(int n) { g_lstm_max_ctas = n > 0 ? n : 0; }
-static int g_lstm_xmode = 0;
+static thread_local int g_lstm_xmode = 0;
 void lstm_set_exchange(int mode) { g_lstm_xmode = mode ? 1 : 0; }
-static long long* g_lstm_trace = nullptr;
+static thread_local long long* g_lstm_trace = nullptr;
 void lstm_set_trace(long long* buf) { g_lstm_trace = buf; }
 void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
 

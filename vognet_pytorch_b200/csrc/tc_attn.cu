@@ -885,9 +885,9 @@ long long tc_attn_workspace_bytes(int Bt, int N, int H)
     return (long long)Bt * H * round_up(N, FA_BKV) * 4;
 }
 
-static long long* g_attn_prof = nullptr;
-static int g_attn_impl = 2;             // 1 = Q/P through smem (v1); Q/P in tensor memory with 2 (v2) / 4 (v3) softmax threads per row
-static int g_attn_cluster = 0;          // 0 = default (no cluster); 2 / 4 = multicast K/V loads across query tiles
+static thread_local long long* g_attn_prof = nullptr;
+static thread_local int g_attn_impl = 2;             // 1 = Q/P through smem (v1); Q/P in tensor memory with 2 (v2) / 4 (v3) softmax threads per row
+static thread_local int g_attn_cluster = 0;          // 0 = default (no cluster); 2 / 4 = multicast K/V loads across query tiles
 void tc_attn_set_impl(int impl) { g_attn_impl = (impl >= 1 && impl <= 3) ? impl : 2; }
 void tc_attn_set_cluster(int c) { g_attn_cluster = c; }
 void tc_attn_set_prof(long long* buf) { g_attn_prof = buf; }

@@ -583,8 +583,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-static long long* g_gemm_trace = nullptr;
-static int g_reserved_sms = 0;
+static thread_local long long* g_gemm_trace = nullptr;
+static thread_local int g_reserved_sms = 0;
 void tc_gemm_set_reserved_sms(int n) { g_reserved_sms = n > 0 ? n : 0; }
 void tc_gemm_set_trace(long long* buf) { g_gemm_trace = buf; }
 

@@ -316,6 +316,25 @@ int vog_tc_attn_bwd(const void* q, const void* k, const void* v, const void* o, 
                        da, dbpe, workspace, workspace_bytes, drop_p, (unsigned long long)seed, (cudaStream_t)stream);
 }
 
+int vog_pack_weights(const float* wq, const float* wk, const float* wv, const float* wo, int d, int H, const int* dh,
+                     int dhp, int lp_kind, void* wqkv, void* wo_p, void* stream)
+{
+    VOG_REQUIRE(wq && wk && wv && wo && dh && wqkv && wo_p, "vog_pack_weights: null operand");
+    return pack_weights(wq, wk, wv, wo, d, H, dh, dhp, lp_kind, wqkv, wo_p, (cudaStream_t)stream);
+}
+
+int64_t vog_workspace_bytes(int op, int a, int b, int c, int d, int e)
+{
+    switch (op) {
+    case VOG_WS_TC_GEMM: return vog_tc_gemm_workspace_bytes(a, b, c, d, e);
+    case VOG_WS_TC_ATTN: return vog_tc_attn_workspace_bytes(a, b, c);
+    case VOG_WS_TC_ATTN_BWD: return vog_tc_attn_bwd_workspace_bytes(a, b, c);
+    case VOG_WS_LSTM: return vog_lstm_workspace_bytes(a, b);
+    case VOG_WS_LOSS: return vog_loss_workspace_bytes(a, b, c);
+    default: return -1;
+    }
+}
+
 int vog_dropout(const float* x, int64_t ldx, const float* residual, int64_t ldr, float* out, int64_t ldo, void* out_lp,
                 int64_t ldlp, int lp_kind, int64_t M, int N, float p, uint64_t seed, int stream_id, void* stream)
 {

@@ -463,28 +463,18 @@ class VOGNetB200(nn.Module):
         if g is None:
             st = {k: inp[k].clone() for k in keys}
 
-            # Optional SM partition between the concurrent branches (VOG_LANG_SMS=n, off by default): the language
-            # recurrence on n SMs (weight-streaming kernel) while the visual branch's persistent GEMMs leave those SMs
-            # alone.  Measured at spat/p100 (profiles/r1/lstm_trace.txt): 16 / 32 / 48 SMs -> 3.17 / 3.09 / 2.47 ms
-            # per step against 1.94 ms unpartitioned - the few-SM streaming recurrence is far too slow to hide.
+            # The language recurrence and the visual branch run as two parallel branches of the graph.  (An SM partition
+            # between them - recurrence on a few SMs, persistent GEMMs on the rest - was measured at spat/p100 in round 1,
+            # profiles/r1/lstm_trace.txt: 2.47-3.17 ms per step against 1.94 ms unpartitioned, and removed.)
             from . import _lib
-            L = _lib.lib()
-            share = int(os.environ.get('VOG_LANG_SMS', 0)) if P_of(st) >= int(os.environ.get('VOG_LANG_SPLIT_MIN_P', 2000)) else 0
 
             def body(side):
                 cur = torch.cuda.current_stream()
                 side.wait_stream(cur)
-                try:
-                    L.vog_lstm_set_max_ctas(share)
-                    with torch.cuda.stream(side):
-                        lang = self.language_encode_tc(st)
-                    L.vog_lstm_set_max_ctas(0)
-                    L.vog_set_reserved_sms(share)
-                    x, x_lp = self._visual_tc(st['pad_region_feature'], st['seg_feature_for_frms'],
-                                              st['pad_proposals'], ncmp)
-                finally:
-                    L.vog_lstm_set_max_ctas(0)
-                    L.vog_set_reserved_sms(0)
+                with torch.cuda.stream(side):
+                    lang = self.language_encode_tc(st)
+                x, x_lp = self._visual_tc(st['pad_region_feature'], st['seg_feature_for_frms'],
+                                          st['pad_proposals'], ncmp)
                 cur.wait_stream(side)
                 out = self._fusion_tc(x, x_lp, lang, st['pad_proposals'], st['srl_arg_inds_msk'],
                                       st['num_cmp_msk'], ncmp)

@@ -322,6 +322,23 @@ def round_up(a, b):
     return -(-a // b) * b
 
 
+def pack_weights(wq, wk, wv, wo, head_dims, dhp, kind):
+    """fp32 [d,d] projection weights of one attention block -> (wqkv [3*H*dhp, d], wo_p [d, H*dhp]) with per-head zero
+    padding, in bf16 / tf32-rounded fp32 (vog_pack_weights)."""
+    ws = [w.detach().float().contiguous() for w in (wq, wk, wv, wo)]
+    d, H = ws[0].shape[1], len(head_dims)
+    for w in ws:
+        _req(w, torch.float32, 'weight', 2)
+        if tuple(w.shape) != (d, d):
+            raise ValueError(f'pack_weights: expected [{d},{d}] weights, got {tuple(w.shape)}')
+    wqkv = torch.empty(3 * H * dhp, d, device=ws[0].device, dtype=_LP_DTYPE[kind])
+    wo_p = torch.empty(d, H * dhp, device=ws[0].device, dtype=_LP_DTYPE[kind])
+    dh_arr = (ctypes.c_int * H)(*head_dims)
+    _lib.check(_lib.lib().vog_pack_weights(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), d, H, dh_arr, dhp, kind,
+                                           _ptr(wqkv), _ptr(wo_p), _stream()), 'vog_pack_weights')
+    return wqkv, wo_p
+
+
 def tc_gemm_qkv(a, wqkv, Bt, N, n_heads, dhp):
     """-> q,k,v [Bt,H,N,dhp] bf16."""
     tf32 = _is_tf32(a, wqkv)

@@ -117,21 +117,14 @@ class EncoderExecutor:
         att, ffn = layer.selfattn.layer, layer.feedforward.layer
         ws = (att.wq.weight, att.wk.weight, att.wv.weight, att.wo.weight, ffn.linear1.weight,
               ffn.linear2.weight)
-        H, dhp, d = self.H, self.dhp, self.d
+        dhp = self.dhp
 
         def lp(t):
             return ops.cast_lp(t.detach().float().contiguous(), kind)
 
         def build():
-            wqkv = torch.zeros(3 * H * dhp, d, device=ws[0].device, dtype=torch.float32)
-            wo = torch.zeros(d, H * dhp, device=ws[0].device, dtype=torch.float32)
-            off = 0
-            for h, dh in enumerate(self.head_dims):
-                for i in range(3):
-                    wqkv[(i * H + h) * dhp:(i * H + h) * dhp + dh] = ws[i][off:off + dh]
-                wo[:, h * dhp:h * dhp + dh] = ws[3][:, off:off + dh]
-                off += dh
-            return dict(wqkv=lp(wqkv), wo=lp(wo), w1=lp(ws[4]), w2=lp(ws[5]))
+            wqkv, wo = ops.pack_weights(ws[0], ws[1], ws[2], ws[3], self.head_dims, dhp, kind)
+            return dict(wqkv=wqkv, wo=wo, w1=lp(ws[4]), w2=lp(ws[5]))
         return self._cached(('tc', l, kind), ws, build)
 
     def _bias_args(self, bias, Bt, N):
