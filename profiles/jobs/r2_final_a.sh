@@ -1,0 +1,9 @@
+#!/bin/bash
+# full GPU suite + the driver's bench line + the ncu launch list of the same workload (eager: graph nodes with tcgen05
+# kernels cannot be profiled)
+rm -f gpurun_out/parity_margins.json
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 > gpurun_out/t_all_r2.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_b.json 2> gpurun_out/bench_r2_b.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r2_spat_gt5.csv \
+    python bench.py --no-graph --no-extras --no-cpu-baseline --no-seq4000 --steps 2 --warmup 3 > gpurun_out/ncu_r2_gt5.log 2>&1
+python profiles/summarize_launches.py gpurun_out/launches_r2_spat_gt5.csv > gpurun_out/launches_r2_spat_gt5.txt 2>&1
