@@ -173,3 +173,27 @@ def test_pack_cache_refreshes_in_place_and_follows_raw_pointer_updates():
     p.data = torch.zeros(5)                                            # shape change: storage must move
     v3 = pc.get('w', (p,), lambda: p.detach() * 2)
     assert v3.shape == (5,) and pc.relocations == 1
+
+
+def test_packed_batch_layout_round_trips_and_exposes_the_graph_prefix():
+    """runtime.PackedLayout / pack_host_batch: one flat buffer per batch (a single host->device copy), tensors as views,
+    the model's graph inputs as a contiguous prefix."""
+    import torch
+    from vognet_pytorch_b200 import runtime, synth
+    w, batch = synth.workload('cpu_ref')
+    first = ('pad_region_feature', 'seg_feature_for_frms', 'pad_proposals')
+    pb = runtime.pack_host_batch(batch, first=first, pin=False)
+    assert set(pb) == set(batch) and all(torch.equal(pb[k], batch[k]) for k in batch)
+    assert all(e[1] % 256 == 0 for e in pb.layout.entries)
+    ents, end = pb.layout.prefix(first)
+    assert [e[0] for e in ents] == list(first) and end == pb.layout.entries[3][1]
+    assert pb.layout.prefix(('pad_proposals',)) is None                     # not a prefix in this order
+    # a layout built from the prefix keys alone describes the same bytes (what the captured forward allocates)
+    sub = runtime.PackedLayout({k: batch[k] for k in first}, first=first)
+    assert sub.prefix(first) == (ents, end) and sub.nbytes == end
+    # views alias the flat buffer
+    pb['pad_proposals'].zero_()
+    o, n = pb.layout.entries[2][1], pb.layout.entries[2][2]
+    assert int(pb.flat[o:o + n].sum()) == 0
+    with pytest.raises(ValueError):
+        pb.layout.pack_into(pb.flat, {**batch, 'pad_proposals': batch['pad_proposals'][:, :1]})

@@ -78,10 +78,72 @@ def max_over_ranks(seconds, device):
     return float(t.item())
 
 
+class PackedLayout:
+    """Byte layout of a batch dict inside ONE flat buffer (every tensor on a 256-byte boundary): lets a whole batch
+    travel host -> device as a single copy and be handed to the model as views.  `first` keys come first, in that order
+    (the model puts the inputs of its captured forward there, so staging them is one contiguous copy as well)."""
+    ALIGN = 256
+
+    def __init__(self, batch, first=()):
+        keys = [k for k in first if k in batch] + [k for k in batch if k not in first]
+        self.entries, off = [], 0
+        for k in keys:
+            t = batch[k]
+            n = t.numel() * t.element_size()
+            self.entries.append((k, off, n, t.dtype, tuple(t.shape)))
+            off += -(-n // self.ALIGN) * self.ALIGN
+        self.nbytes = off
+
+    def prefix(self, keys):
+        """(entries, nbytes) of the leading `keys` - None unless they are exactly the first len(keys) entries"""
+        keys = tuple(keys)
+        if tuple(e[0] for e in self.entries[:len(keys)]) != keys:
+            return None
+        ents = tuple(self.entries[:len(keys)])
+        end = self.entries[len(keys)][1] if len(self.entries) > len(keys) else self.nbytes
+        return ents, end
+
+    def views(self, flat):
+        """dict of tensors aliasing the flat uint8 buffer"""
+        return {k: flat[o:o + n].view(dt).view(shape) for k, o, n, dt, shape in self.entries}
+
+    def pack_into(self, flat, batch):
+        for k, o, n, dt, shape in self.entries:
+            t = batch[k]
+            if t.dtype != dt or tuple(t.shape) != shape:
+                raise ValueError(f'PackedLayout: {k} is {t.dtype} {tuple(t.shape)}, layout has {dt} {shape}')
+            flat[o:o + n].view(dt).view(shape).copy_(t)
+        return flat
+
+
+class PackedBatch(dict):
+    """A batch dict whose tensors are views of one flat buffer (`.flat`, uint8) described by `.layout`."""
+
+    def __init__(self, flat, layout, slot=None):
+        super().__init__(layout.views(flat))
+        self.flat, self.layout, self.slot = flat, layout, slot
+
+
+def pack_host_batch(batch, first=(), layout=None, pin=True):
+    """Collate step for the packed path: copy a (CPU) batch dict into one flat, optionally pinned, buffer."""
+    layout = layout or PackedLayout(batch, first)
+    flat = torch.empty(layout.nbytes, dtype=torch.uint8)
+    if pin and torch.cuda.is_available():
+        flat = flat.pin_memory()
+    layout.pack_into(flat, batch)
+    return PackedBatch(flat, layout)
+
+
 class BatchPrefetcher:
     """Double-buffered host -> device staging: while the model works on batch i (compute stream),
     batch i+1 is copied from pinned host memory on a dedicated copy stream.  ``next()`` returns a
-    device batch dict whose copies are ordered before the caller's current stream."""
+    device batch dict whose copies are ordered before the caller's current stream.
+
+    Host batches may be plain dicts (one copy per tensor, buffers from the caching allocator) or ``PackedBatch``es
+    (``pack_host_batch``): then every batch is ONE host->device copy into a ring of ``depth + 1`` preallocated flat
+    device buffers and ``next()`` returns a ``PackedBatch`` of views.  A ring slot is overwritten only after the
+    event passed to ``release(batch, event)`` for its previous occupant - call it once the step that consumed the
+    batch has been enqueued."""
 
     def __init__(self, host_batches, device, depth=2):
         self.it = iter(host_batches)
@@ -89,6 +151,7 @@ class BatchPrefetcher:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.depth = depth
         self.queue = []
+        self.ring, self.consumed, self.n_enq = None, None, 0
         for _ in range(depth):
             self._enqueue()
 
@@ -98,17 +161,36 @@ class BatchPrefetcher:
         except StopIteration:
             return
         with torch.cuda.stream(self.copy_stream):
-            db = {k: v.to(self.device, non_blocking=True) for k, v in hb.items()}
+            if isinstance(hb, PackedBatch):
+                if self.ring is None or self.ring[0].numel() != hb.layout.nbytes:
+                    self.ring = [torch.empty(hb.layout.nbytes, dtype=torch.uint8, device=self.device)
+                                 for _ in range(self.depth + 1)]
+                    self.consumed = [None] * (self.depth + 1)
+                slot = self.n_enq % (self.depth + 1)
+                self.n_enq += 1
+                if self.consumed[slot] is not None:             # the step that read this slot last has finished
+                    self.copy_stream.wait_event(self.consumed[slot])
+                self.ring[slot].copy_(hb.flat, non_blocking=True)
+                db = PackedBatch(self.ring[slot], hb.layout, slot)
+            else:
+                db = {k: v.to(self.device, non_blocking=True) for k, v in hb.items()}
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self.queue.append((db, ev))
+
+    def release(self, batch, event):
+        """the work recorded by `event` (on the compute stream) is the last reader of a packed `batch`"""
+        if isinstance(batch, PackedBatch) and batch.slot is not None and self.consumed is not None:
+            self.consumed[batch.slot] = event
 
     def next(self):
         if not self.queue:
             return None
         db, ev = self.queue.pop(0)
-        torch.cuda.current_stream(self.device).wait_event(ev)
-        for v in db.values():                       # the compute stream now owns these buffers
-            v.record_stream(torch.cuda.current_stream(self.device))
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        if not isinstance(db, PackedBatch):
+            for v in db.values():                       # the compute stream now owns these buffers
+                v.record_stream(cur)
         self._enqueue()
         return db
