@@ -430,6 +430,7 @@ int vog_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int K
  * vog_debug_attn_prof: device buffer of 16 int64 for the per-phase cycle counters of one softmax
  * warp / the MMA issuer of vog_tc_attn_fwd (library built with -DVOG_ATTN_PROFILE). */
 void vog_debug_gemm_trace(void* buf);
+void vog_debug_pdl(int on);                   /* A/B: 0 = plain stream-ordered launches instead of programmatic dependent launches */
 void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 0 tagged 64-bit words, 1 per-CTA release flags */
 void vog_debug_lstm_trace(void* buf);          /* 8 int64: matvec, reduce, cell+publish, poll, barrier cycles, steps */
 void vog_debug_attn_prof(void* buf);

@@ -125,6 +125,8 @@ def lib():
                 fn = getattr(l, name)          # AttributeError if the symbol is not exported
                 fn.argtypes = argtypes
                 fn.restype = _RESTYPE[name]
+            if os.environ.get('VOG_PDL', '0') == '1':       # A/B: programmatic dependent launches (measured: no gain)
+                l.vog_debug_pdl(1)
             _lib = l
     return _lib
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 namespace vog {
 
@@ -28,6 +29,31 @@ int check_launch(const char* what);     // cudaGetLastError() -> 0 / -1 (+messag
             return -1;                                                                   \
         }                                                                                \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// The forward at the gt5 sizes is a chain of ~25 short dependent kernels: each one's launch latency and on-chip set-up
+// (barrier init, TMEM allocation, tensor-map prefetch, weight loads) would otherwise sit on the critical path.  Kernels
+// launched through launch_pdl() may START as soon as every CTA of the preceding kernel of the stream has executed
+// pdl_trigger(); they must call pdl_wait() before their first access to memory another kernel of the stream produces
+// (it returns once the preceding grid has completed and its writes are visible).  Only data written by plain launches
+// (parameters, packed weights) may be read before pdl_wait().  Both are no-ops under a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();             // thread-local switch (vog_debug_pdl / VOG_PDL=1), default OFF: see DESIGN.md section 6.0
+void pdl_set(bool on);
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return cdiv(a, b) * b; }

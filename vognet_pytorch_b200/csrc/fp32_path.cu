@@ -288,6 +288,8 @@ add_layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restri
 {
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (row >= M) return;
     const float* xr = x + (size_t)row * ldx;
     const float* rr = r ? r + (size_t)row * ldr : nullptr;
@@ -323,6 +325,8 @@ add_layernorm_vec_kernel(const float* __restrict__ x, int ldx, const float* __re
     constexpr int d = NV * 128;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (row >= M) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
     float4 v[NV];
@@ -382,8 +386,8 @@ int add_layernorm(const float* x, int ldx, const float* r, int ldr, const float*
     if (vec) {
 #define VOG_LN_CASE(NV)                                                                                   \
     case NV:                                                                                              \
-        add_layernorm_vec_kernel<NV><<<cdiv(M, 8), 256, 0, st>>>(x, ldx, r, ldr, w, b, out, ldo, out_lp,  \
-                                                                 ldlp, lp_kind, M, eps);                  \
+        VOG_CUDA(launch_pdl(add_layernorm_vec_kernel<NV>, dim3(cdiv(M, 8)), dim3(256), 0, st, x, ldx, r, ldr, w, b, out, ldo, \
+                            out_lp, ldlp, lp_kind, M, eps));                                              \
         break;
         switch (d / 128) {
             VOG_LN_CASE(1) VOG_LN_CASE(2) VOG_LN_CASE(3) VOG_LN_CASE(4) VOG_LN_CASE(5) VOG_LN_CASE(6)
@@ -392,8 +396,8 @@ int add_layernorm(const float* x, int ldx, const float* r, int ldr, const float*
 #undef VOG_LN_CASE
         return check_launch("add_layernorm_vec");
     }
-    add_layernorm_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, ldx, r, ldr, w, b, out, ldo, out_lp, ldlp,
-                                                     lp_kind, M, d, eps);
+    VOG_CUDA(launch_pdl(add_layernorm_kernel, dim3(cdiv(M, 8)), dim3(256), 0, st, x, ldx, r, ldr, w, b, out, ldo, out_lp, ldlp,
+                        lp_kind, M, d, eps));
     return check_launch("add_layernorm");
 }
 
@@ -405,6 +409,8 @@ __global__ void pe_project_kernel(const float* __restrict__ props, int ldp, cons
                                   float scale)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (idx >= rows * H) return;
     int row = idx / H, h = idx % H;
     const float* p = props + (size_t)row * ldp;
@@ -424,7 +430,7 @@ int pe_project(const float* props, int ldp, const float* W, float* a, int rows, 
 {
     if (rows == 0) return 0;
     int n = rows * H;
-    pe_project_kernel<<<cdiv(n, 256), 256, 0, st>>>(props, ldp, W, a, rows, H, vw, vh, fdiv, scale);
+    VOG_CUDA(launch_pdl(pe_project_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, props, ldp, W, a, rows, H, vw, vh, fdiv, scale));
     return check_launch("pe_project");
 }
 

@@ -65,6 +65,8 @@ lin2_tail_kernel(const float* __restrict__ h, int ldh, const float* __restrict__
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const long long M = (long long)B * nfrm * nsrl * nppf2;
+    pdl_trigger();
+    pdl_wait();
     if (row >= M) return;
     const float* hr = h + (size_t)row * ldh;
     float acc = 0.f;
@@ -99,8 +101,8 @@ int lin2_tail(const float* h, int ldh, const float* w2, const float* b2, const l
     VOG_REQUIRE(K % 4 == 0 && ldh % 4 == 0, "lin2_tail: K and ldh must be multiples of 4");
     const long long M = (long long)B * nfrm * nsrl * nppf2;
     if (M == 0) return 0;
-    lin2_tail_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(h, ldh, w2, b2, srl_msk, cmp_msk, logits, scores, B,
-                                                             nfrm, nsrl, nppf2, K, ncmp, nppf, nfrm0, spat);
+    VOG_CUDA(launch_pdl(lin2_tail_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, st, h, ldh, w2, b2, srl_msk, cmp_msk,
+                        logits, scores, B, nfrm, nsrl, nppf2, K, ncmp, nppf, nfrm0, spat));
     return check_launch("lin2_tail");
 }
 
@@ -129,6 +131,8 @@ lang_embed_kernel(const long long* __restrict__ words, int nwords, const long lo
 {
     const int row = blockIdx.x;                 // t*Bq + b
     const int t = row / Bq, b = row % Bq;
+    pdl_trigger();
+    pdl_wait();
     const long long mk = mask[(size_t)b * T + t];
     long long tok = pad_idx;
     if (mk != -1) tok = words[(size_t)b * nwords + (mk < 0 ? 0 : (mk >= nwords ? nwords - 1 : mk))];
@@ -152,7 +156,8 @@ int lang_embed(const long long* words, int nwords, const long long* mask, int T,
 {
     VOG_REQUIRE(E % 4 == 0, "lang_embed: embedding width must be a multiple of 4");
     if (T * Bq == 0) return 0;
-    lang_embed_kernel<<<dim3(T * Bq, (E / 4 + 511) / 512), 128, 0, st>>>(words, nwords, mask, T, emb, E, pad_idx, Bq, out_lp, lp_kind);
+    VOG_CUDA(launch_pdl(lang_embed_kernel, dim3(T * Bq, (E / 4 + 511) / 512), dim3(128), 0, st, words, nwords, mask, T, emb, E,
+                        pad_idx, Bq, out_lp, lp_kind));
     return check_launch("lang_embed");
 }
 
@@ -164,6 +169,8 @@ lang_gather_kernel(const float* __restrict__ full, int D, const long long* __res
 {
     const int row = blockIdx.x;                 // b*nsrl + s
     const int b = row / nsrl;
+    pdl_trigger();
+    pdl_wait();
     for (int c = threadIdx.x; c < 2 * D / 4; c += blockDim.x) {
         const int which = (4 * c) / D, col = 4 * c - which * D;
         long long t = cap[(size_t)row * 2 + which];
@@ -178,7 +185,7 @@ int lang_gather(const float* full, int D, const long long* cap, int T, int Bq, i
 {
     VOG_REQUIRE(D % 4 == 0, "lang_gather: feature width must be a multiple of 4");
     if (Bq * nsrl == 0) return 0;
-    lang_gather_kernel<<<Bq * nsrl, 128, 0, st>>>(full, D, cap, T, Bq, nsrl, out_lp, lp_kind);
+    VOG_CUDA(launch_pdl(lang_gather_kernel, dim3(Bq * nsrl), dim3(128), 0, st, full, D, cap, T, Bq, nsrl, out_lp, lp_kind));
     return check_launch("lang_gather");
 }
 
@@ -188,6 +195,8 @@ mask_rows_kernel(const float* __restrict__ x, const long long* __restrict__ msk,
                  void* __restrict__ out_lp, int lp_kind)
 {
     const int row = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const float m = (float)msk[row];
     for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
         float4 v = *reinterpret_cast<const float4*>(x + (size_t)row * D + 4 * c);
@@ -202,7 +211,7 @@ int mask_rows(const float* x, const long long* msk, int rows, int D, float* out,
 {
     VOG_REQUIRE(D % 4 == 0, "mask_rows: feature width must be a multiple of 4");
     if (rows == 0) return 0;
-    mask_rows_kernel<<<rows, 128, 0, st>>>(x, msk, D, out, out_lp, lp_kind);
+    VOG_CUDA(launch_pdl(mask_rows_kernel, dim3(rows), dim3(128), 0, st, x, msk, D, out, out_lp, lp_kind));
     return check_launch("mask_rows");
 }
 

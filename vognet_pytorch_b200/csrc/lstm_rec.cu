@@ -304,9 +304,11 @@ lstm_rec_resident_kernel(const LstmResParams p)
     const int u = c * p.U + warp;                            // hidden unit of this warp
     const bool unit_ok = u < H;
 
-    if (tid < LS_MAXB) len_s[tid] = tid < Bq ? (int)min((long long)p.T, max(0LL, p.lens[tid])) : 0;
+    pdl_trigger();
     for (int i = tid; i < 2 * BQ * H; i += NT) h_s[i] = 0.f;
-    // ---- one-time weight load: row (gate, u), columns 128 i + 4 lane
+    // ---- one-time weight load: row (gate, u), columns 128 i + 4 lane.  W_hh is a parameter (written by plain launches
+    //      only), so these 33 MB are fetched BEFORE pdl_wait(): behind the input-projection GEMM that precedes this
+    //      kernel in the stream
     float4 wr[4][LR_NREG];
     {
         const float* wbase = p.whh + (size_t)d * 4 * H * H;
@@ -321,6 +323,8 @@ lstm_rec_resident_kernel(const LstmResParams p)
             }
         }
     }
+    pdl_wait();                                      // gx, lens and the zeroed exchange workspace are ready
+    if (tid < LS_MAXB) len_s[tid] = tid < Bq ? (int)min((long long)p.T, max(0LL, p.lens[tid])) : 0;
     __syncthreads();
     if (tid == 0) {
         int m = 0;
@@ -522,12 +526,20 @@ lstm_rec_resident_kernel(const LstmResParams p)
             store_lp(p.out_lp, ((long long)t * p.bq_total + lane) * p.ld_out + (long long)d * H + u, 0.f, p.lp_kind);
 }
 
+__global__ void __launch_bounds__(256) zero16_kernel(uint4* __restrict__ p, long long n16)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 template <int BQ>
 static int launch_resident(const LstmResParams& p, int ctas, int threads, cudaStream_t st)
 {
     const size_t smem = (size_t)4 * (LR_NI - LrCfg<BQ>::NREG) * threads * 16 + (size_t)2 * BQ * LR_H * 4 + (size_t)LR_MAXU * 4 * BQ * 4;
     VOG_CUDA(cudaFuncSetAttribute(lstm_rec_resident_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_rec_resident_kernel<BQ><<<ctas, threads, smem, st>>>(p);
+    VOG_CUDA(launch_pdl(lstm_rec_resident_kernel<BQ>, dim3(ctas), dim3(threads), smem, st, p));
     return check_launch("lstm_rec_resident");
 }
 
@@ -543,7 +555,7 @@ void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
 long long lstm_workspace_bytes(int Bq, int H)
 {
     if (Bq > LS_MAXB) Bq = LS_MAXB;            // larger batches run in groups of LS_MAXB over the same workspace
-    return (long long)2 * 2 * Bq * H * 8 + LS_WS_HEADER;   // header (counters / flags) + exchange words
+    return (((long long)2 * 2 * Bq * H * 8 + LS_WS_HEADER) + 15) & ~15LL;   // header (counters / flags) + exchange words
 }
 
 static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq, int bq_total,
@@ -578,7 +590,13 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
         rp.T = T; rp.Bq = Bq; rp.U = U; rp.ctas_per_dir = per_dir_u; rp.bq_total = bq_total;
         rp.trace = g_lstm_trace;
         rp.acts = acts;
-        VOG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)lstm_workspace_bytes(Bq, H), st));
+        // the exchange workspace is zeroed by a KERNEL (not a memset node) so that the chain GEMM -> zero -> recurrence
+        // stays kernel-to-kernel and the recurrence can start (and load its weights) behind the GEMM
+        {
+            const long long n16 = (lstm_workspace_bytes(Bq, H) + 15) / 16;
+            VOG_CUDA(launch_pdl(zero16_kernel, dim3((unsigned)((n16 + 255) / 256)), dim3(256), 0, st,
+                                reinterpret_cast<uint4*>(workspace), n16));
+        }
         const int ctas = 2 * per_dir_u, threads = 32 * U;
         if (Bq == 1) return launch_resident<1>(rp, ctas, threads, st);
         if (Bq == 2) return launch_resident<2>(rp, ctas, threads, st);

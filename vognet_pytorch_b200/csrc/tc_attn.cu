@@ -517,6 +517,8 @@ tc_attn2_kernel(const __grid_constant__ CUtensorMap tma_k, const __grid_constant
     if (C > 1) cluster_sync_all();                     // peers' barriers are initialised before anyone multicasts
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_trigger();
+    pdl_wait();                                        // set-up above overlapped the previous kernel's tail
     const uint32_t tmem_o = tmem_base;                 // columns [0, 256): O accumulator (dhp <= 256 used)
     const uint32_t tmem_q = tmem_base + 256;           // columns [256, 384): Q tile, bf16 pairs (A operand of S = Q K^T)
     const uint32_t tmem_s0 = tmem_base + 384;          // 2 x 64 columns: S_j (fp32), overwritten in place by P_j (bf16 pairs)
@@ -873,6 +875,8 @@ __global__ void bias_expand_kernel(const float* __restrict__ a, float* __restric
                                    int nbox, int ld, float c)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (idx >= (long long)Bt * H * ld) return;
     const int key = (int)(idx % ld);
     const int bh = (int)(idx / ld);
@@ -926,8 +930,8 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
                     "tc_attn: rank-1 bias needs a 16-byte aligned workspace of tc_attn_workspace_bytes()");
         p.ak_seq = reinterpret_cast<const float*>(workspace);
         const long long n = (long long)Bt * H * p.ak_ld;
-        bias_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<float*>(workspace), Bt, N, H,
-                                                                         p.nbox, p.ak_ld, p.c);
+        VOG_CUDA(launch_pdl(bias_expand_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a,
+                            reinterpret_cast<float*>(workspace), Bt, N, H, p.nbox, p.ak_ld, p.c));
         if (check_launch("bias_expand")) return -1;
     }
     p.q = reinterpret_cast<const __nv_bfloat16*>(q);
@@ -961,10 +965,12 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
         cfg.blockDim = dim3(128 * npart + 128, 1, 1);
         cfg.dynamicSmemBytes = smem2;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 2;
         if (npart == 2) VOG_CUDA(cudaLaunchKernelEx(&cfg, tc_attn2_kernel<2>, tk2, tv2, p));
         else VOG_CUDA(cudaLaunchKernelEx(&cfg, tc_attn2_kernel<4>, tk2, tv2, p));
         return check_launch("tc_attn2");

@@ -467,10 +467,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), p.tmem_cols);
+    pdl_trigger();                                   // the next kernel of the stream may set itself up behind this one
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                                      // everything above overlapped the previous kernel's tail
     if (threadIdx.x == 0) GM_TRACE(1);
     const int nitems = p.num_m_blocks * p.num_n_blocks * p.splits;
     // item -> (m_blk, n_blk, split): splits innermost so that the CTAs of one wave share A/W tiles in L2
@@ -594,6 +596,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N
 {
     const int n4 = (N + 3) / 4;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (idx >= (long long)M * n4) return;
     const int m = (int)(idx / n4), n = (int)(idx % n4) * 4;
     float x[4] = {0.f, 0.f, 0.f, 0.f};
@@ -776,7 +780,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
 #define VOG_GEMM_LAUNCH(TF, EP)                                                                                   \
     do {                                                                                                          \
         VOG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TF, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        tc_gemm_kernel<TF, EP><<<grid, GM_THREADS, smem, st>>>(ta, tb, p);                                         \
+        VOG_CUDA(launch_pdl(tc_gemm_kernel<TF, EP>, dim3(grid), dim3(GM_THREADS), smem, st, ta, tb, p));                  \
     } while (0)
     if (tf32) {
         if (epi_kind == EPI_FAST) VOG_GEMM_LAUNCH(true, EPI_FAST);
@@ -795,7 +799,7 @@ int tc_gemm(const void* A, long long lda, const void* W, long long ldw, int M, i
     if (check_launch("tc_gemm")) return -1;
     if (p.splits > 1) {
         const long long n = (long long)M * ((N + 3) / 4);
-        splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.partial, p.splits, M, N, epi);
+        VOG_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const float*)p.partial, p.splits, M, N, epi));
         return check_launch("splitk_reduce");
     }
     return 0;

@@ -20,6 +20,9 @@ void set_error(const char* fmt, ...)
 }
 
 static std::atomic<long long> g_launches{0};
+static thread_local bool g_pdl = false;         // measured: 0.5 % on the gt5 graph replay, nothing at p100 - off by default
+bool pdl_enabled() { return g_pdl; }
+void pdl_set(bool on) { g_pdl = on; }
 
 int check_launch(const char* what)
 {
@@ -41,6 +44,7 @@ extern "C" {
 const char* vog_last_error(void) { return g_err; }
 int vog_abi_version(void) { return 2; }
 long long vog_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void vog_debug_pdl(int on) { vog::pdl_set(on != 0); }
 
 int vog_device_is_sm100(void)
 {
