@@ -61,8 +61,10 @@ int vog_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* 
 int vog_attn_fwd_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
                      int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
                      int bias_mode, const float* a, int nbox, const float* bpe,
-                     const float* dense, float* lse, void* stream);
-/* lse (nullable): [Bt,H,N] log-sum-exp of the scaled scores, kept by the training forward for vog_attn_bwd_f32. */
+                     const float* dense, float* lse, float drop_p, uint64_t seed, void* stream);
+/* lse (nullable): [Bt,H,N] log-sum-exp of the scaled scores, kept by the training forward for vog_attn_bwd_f32.
+ * drop_p > 0: dropout on the probabilities after the softmax (code/transformer_code.py:153) with the same
+ * counter-based mask (seed, sequence*H + head, query, key) as vog_tc_attn_fwd_train. */
 
 /* out = LayerNorm(x + r) * w + b (eps inside the sqrt), r nullable; optional low-precision copy
  * out_lp (VOG_LP_*) for the next GEMM.  replaces ResidualBlock: code/transformer_code.py:21-31. */
@@ -326,7 +328,7 @@ int vog_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ld,
                      const float* dout, int64_t lddo, const float* lse, float* delta, float* dq, float* dk, float* dv,
                      int64_t ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
                      const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe,
-                     float* ddense, void* stream);
+                     float* ddense, float drop_p, uint64_t seed, void* stream);
 
 /* dW[h,c] += sum_rows da[row,h] * normalised(props[row, c])  (accumulated): gradient of vog_pe_project w.r.t. the
  * pe_{obj,mul}_sub_enc weight (code/mdl_vog.py:446-451,459-463,580-585); the boxes carry no gradient (:497,506,624). */

@@ -174,3 +174,35 @@ def test_tc_attn_dropout_is_consistent_and_calibrated():
     got = dqkv.view(Bt, N, 3, H, dhp).permute(2, 0, 3, 1, 4)
     for name, g_, r_ in (('dq', got[0], qd.grad), ('dk', got[1], kd.grad), ('dv', got[2], vd.grad)):
         assert _relmax(g_, r_) < 2e-2, name
+
+
+def test_fp32_and_tcgen05_attention_draw_the_same_dropout_mask():
+    """vog_attn_fwd_f32 / vog_attn_bwd_f32 with drop_p use the same counter-based mask as the tensor-core kernels:
+    same seed -> same dropped probabilities (outputs agree to bf16 rounding), forward and backward."""
+    ops, ob = _ops()
+    Bt, N, nbox, head_dims, dhp = 2, 150, 30, (171, 171, 170), 192
+    H, d = len(head_dims), sum(head_dims)
+    inv = 1.0 / math.sqrt(d)
+    q, k, v, a, bpe, dout = _attn_case(Bt, N, nbox, head_dims, dhp, 7, True)
+    kw = dict(bias_mode=ops.BIAS_RANK1, a=a, nbox=nbox, bpe=bpe)
+    out_tc, lse_tc = ob.tc_attn_fwd_train(q, k, v, N, head_dims, inv, drop_p=0.2, seed=99, **kw)
+    da_tc, db_tc = torch.zeros_like(a), torch.zeros_like(bpe)
+    dqkv_tc = ob.tc_attn_bwd(q, k, v, out_tc, dout, lse_tc, N, head_dims, inv, da=da_tc, dbpe=db_tc, drop_p=0.2, seed=99, **kw)
+
+    def unpad(t):                                   # [Bt,H,N,dhp] -> [Bt*N, d]
+        return torch.cat([t[:, h, :, :dh] for h, dh in enumerate(head_dims)], -1).reshape(Bt * N, d).float().contiguous()
+    qf, kf, vf = unpad(q), unpad(k), unpad(v)
+    dof = torch.cat([dout.view(Bt * N, H, dhp)[:, h, :dh] for h, dh in enumerate(head_dims)], -1).float().contiguous()
+    lse = torch.empty(Bt * H * N, device=DEV)
+    out_f = ops.attn_fwd_f32(qf, kf, vf, Bt, N, head_dims, inv, lse=lse, drop_p=0.2, seed=99, **kw)
+    out_f0 = ops.attn_fwd_f32(qf, kf, vf, Bt, N, head_dims, inv)
+    got = torch.cat([out_tc.view(Bt * N, H, dhp)[:, h, :dh] for h, dh in enumerate(head_dims)], -1).float()
+    assert _relmax(got, out_f) < 1.5e-2                         # same mask
+    assert _relmax(out_f0, out_f) > 1e-1                        # ... and the mask matters
+    da_f, db_f = torch.zeros_like(a), torch.zeros_like(bpe)
+    dqkv_f, _ = ob.attn_bwd_f32(qf, kf, vf, out_f, dof, lse, Bt, N, head_dims, inv, da=da_f, dbpe=db_f, drop_p=0.2, seed=99, **kw)
+    tc = dqkv_tc.view(Bt * N, 3, H, dhp)
+    for i, name in enumerate(('dq', 'dk', 'dv')):
+        g_tc = torch.cat([tc[:, i, h, :dh] for h, dh in enumerate(head_dims)], -1).float()
+        assert _relmax(g_tc, dqkv_f[:, i * d:(i + 1) * d]) < 2.5e-2, name
+    assert _relmax(da_tc, da_f) < 1e-2 and _relmax(db_tc, db_f) < 1e-2

@@ -6,6 +6,7 @@
 // point in vog_abi.cu / include/vog_b200.h.
 #include "common.cuh"
 #include "kernels.h"
+#include "philox.cuh"
 
 namespace vog {
 
@@ -101,6 +102,8 @@ struct AttnF32Params {
     const float* bpe;           // mode 1: device [H]
     const float* dense;         // mode 2
     float* lse;                 // optional [Bt,H,N]: log-sum-exp of the scaled scores (saved for the backward)
+    float drop_p;               // training: dropout on the probabilities (same counter-based mask as the tcgen05 kernels)
+    unsigned long long seed;
 };
 
 template <int KPT>   // accumulator columns per thread: dh <= 8*KPT
@@ -195,6 +198,17 @@ attn_f32_kernel(const AttnF32Params p)
             float rs = warp_sum(p0 + p1);
             l_run[r] = l_run[r] * al + rs;
             m_run[r] = m_new;
+            if (p.drop_p > 0.f) {
+                // dropout after the softmax (code/transformer_code.py:153): the row sum keeps every probability
+                const uint32_t thr = drop_threshold8(p.drop_p);
+                const float ik = drop_inv_keep8(p.drop_p);
+                uint32_t rnd[4];
+                const int g0 = j0 + lane, g1 = j0 + lane + 32;
+                attn_rand8x16(p.seed, (uint32_t)(bt * p.H + h), (uint32_t)gi, (uint32_t)(g0 & ~15), rnd);
+                p0 = ((rnd[(g0 & 15) >> 2] >> (8 * (g0 & 3))) & 0xffu) >= thr ? p0 * ik : 0.f;
+                attn_rand8x16(p.seed, (uint32_t)(bt * p.H + h), (uint32_t)gi, (uint32_t)(g1 & ~15), rnd);
+                p1 = ((rnd[(g1 & 15) >> 2] >> (8 * (g1 & 3))) & 0xffu) >= thr ? p1 * ik : 0.f;
+            }
             Ss[(warp * 4 + r) * 65 + lane] = p0;
             Ss[(warp * 4 + r) * 65 + lane + 32] = p1;
             if (lane == 0) alpha_s[warp * 4 + r] = al;
@@ -243,15 +257,17 @@ attn_f32_kernel(const AttnF32Params p)
 int attn_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
              int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
              int bias_mode, const float* a, int nbox, const float* bpe, const float* dense,
-             cudaStream_t st, float* lse)
+             cudaStream_t st, float* lse, float drop_p, unsigned long long seed)
 {
     VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS, "attn_f32: H=%d out of range (max %d)", H, VOG_MAX_HEADS);
+    VOG_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attn_f32: dropout probability %f", (double)drop_p);
     VOG_REQUIRE(Bt <= 65535, "attn_f32: Bt=%d exceeds grid.z", Bt);
     if (Bt == 0 || N == 0) return 0;
     AttnF32Params p;
     p.q = q; p.k = k; p.v = v; p.ld = ld; p.out = out; p.ldo = ldo;
     p.Bt = Bt; p.N = N; p.H = H; p.inv_scale = inv_scale;
     p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.dense = dense; p.bpe = bpe; p.lse = lse;
+    p.drop_p = drop_p; p.seed = seed;
     int dhmax = 0;
     for (int h = 0; h < H; ++h) {
         p.off[h] = off[h]; p.dh[h] = dh[h];

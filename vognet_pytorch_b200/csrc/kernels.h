@@ -15,7 +15,7 @@ int sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias
 int attn_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
              int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
              int bias_mode, const float* a, int nbox, const float* bpe, const float* dense,
-             cudaStream_t st, float* lse = nullptr);
+             cudaStream_t st, float* lse = nullptr, float drop_p = 0.f, unsigned long long seed = 0);
 int add_layernorm(const float* x, int ldx, const float* r, int ldr, const float* w, const float* b,
                   float* out, int ldo, void* out_lp, int ldlp, int lp_kind, int M, int d, float eps,
                   cudaStream_t st);
@@ -135,7 +135,7 @@ int attn_bwd_f32(const float* q, const float* k, const float* v, long long ld, c
                  const float* dout, long long lddo, const float* lse, float* delta, float* dq, float* dk, float* dv,
                  long long ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
                  const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe, float* ddense,
-                 cudaStream_t st);
+                 cudaStream_t st, float drop_p = 0.f, unsigned long long seed = 0);
 int dropout_apply(const float* x, long long ldx, const float* res, long long ldr, float* out, long long ldo, void* out_lp,
                   long long ldlp, int lp_kind, long long M, int N, float p, unsigned long long seed, unsigned int stream,
                   cudaStream_t st);

@@ -364,6 +364,7 @@ struct AttnBwdF32Params {
     int bias_mode; const float* a; int nbox; const float* bpe; const float* dense;
     float* da; float* dbpe; float* ddense;
     int kv_pass;
+    float drop_p; unsigned long long seed;       // the forward's dropout on the probabilities, regenerated
 };
 
 template <int KPT>
@@ -478,7 +479,17 @@ attn_bwd_f32_kernel(const AttnBwdF32Params p)
                     const float lse = kv ? c_lse[cc] : r_lse[r];
                     const float dl = kv ? c_delta[cc] : r_delta[r];
                     pval = expf(z - lse);
-                    ds = pval * (dp[r][cc] - dl) * p.inv_scale;
+                    float dpe = dp[r][cc];
+                    if (p.drop_p > 0.f) {
+                        uint32_t rnd[4];
+                        attn_rand8x16(p.seed, (uint32_t)(bt * p.H + h), (uint32_t)qi, (uint32_t)(kj & ~15), rnd);
+                        const bool keep = ((rnd[(kj & 15) >> 2] >> (8 * (kj & 3))) & 0xffu) >= drop_threshold8(p.drop_p);
+                        const float ik = drop_inv_keep8(p.drop_p);
+                        dpe = keep ? dpe * ik : 0.f;
+                        ds = pval * (dpe - dl) * p.inv_scale;
+                        pval = keep ? pval * ik : 0.f;           // what multiplied V in the forward (dV = P_drop^T dO)
+                    } else
+                    ds = pval * (dpe - dl) * p.inv_scale;
                     if (gate) bias_acc[r] += ds;
                     if (!kv && p.bias_mode == 2 && p.ddense)
                         p.ddense[(((long long)bt * N + qi) * N + kj) * p.H + h] = ds;
@@ -551,9 +562,10 @@ int attn_bwd_f32(const float* q, const float* k, const float* v, long long ld, c
                  const float* dout, long long lddo, const float* lse, float* delta, float* dq, float* dk, float* dv,
                  long long ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
                  const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe, float* ddense,
-                 cudaStream_t st)
+                 cudaStream_t st, float drop_p, unsigned long long seed)
 {
     VOG_REQUIRE(H >= 1 && H <= VOG_MAX_HEADS, "attn_bwd_f32: H=%d out of range", H);
+    VOG_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attn_bwd_f32: dropout probability %f", (double)drop_p);
     VOG_REQUIRE(Bt <= 65535, "attn_bwd_f32: Bt=%d exceeds grid.z", Bt);
     if (Bt == 0 || N == 0) return 0;
     AttnBwdF32Params p;
@@ -561,6 +573,7 @@ int attn_bwd_f32(const float* q, const float* k, const float* v, long long ld, c
     p.dq = dq; p.dk = dk; p.dv = dv; p.ldg = ldg; p.Bt = Bt; p.N = N; p.H = H; p.inv_scale = inv_scale;
     p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.bpe = bpe; p.dense = dense;
     p.da = da; p.dbpe = dbpe; p.ddense = ddense;
+    p.drop_p = drop_p; p.seed = seed;
     int dhmax = 0;
     HeadSplit hs = {};
     for (int h = 0; h < H; ++h) {

@@ -42,7 +42,7 @@ using namespace vog;
 extern "C" {
 
 const char* vog_last_error(void) { return g_err; }
-int vog_abi_version(void) { return 2; }
+int vog_abi_version(void) { return 3; }
 long long vog_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void vog_debug_pdl(int on) { vog::pdl_set(on != 0); }
 
@@ -68,14 +68,14 @@ int vog_sgemm_nt(const float* A, int lda, const float* W, int ldw, const float* 
 int vog_attn_fwd_f32(const float* q, const float* k, const float* v, int ld, float* out, int ldo,
                      int Bt, int N, int H, const int* off, const int* dh, float inv_scale,
                      int bias_mode, const float* a, int nbox, const float* bpe,
-                     const float* dense, float* lse, void* stream)
+                     const float* dense, float* lse, float drop_p, uint64_t seed, void* stream)
 {
     VOG_REQUIRE(q && k && v && out && off && dh, "vog_attn_fwd_f32: null operand");
     VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_attn_fwd_f32: negative dimension");
     VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_attn_fwd_f32: bad bias_mode %d", bias_mode);
     VOG_REQUIRE(bias_mode != VOG_BIAS_RANK1 || nbox > 0, "vog_attn_fwd_f32: nbox must be > 0");
     return attn_f32(q, k, v, ld, out, ldo, Bt, N, H, off, dh, inv_scale, bias_mode, a, nbox, bpe,
-                    dense, (cudaStream_t)stream, lse);
+                    dense, (cudaStream_t)stream, lse, drop_p, (unsigned long long)seed);
 }
 
 int vog_add_layernorm(const float* x, int ldx, const float* r, int ldr, const float* w,
@@ -524,14 +524,14 @@ int vog_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ld,
                      const float* dout, int64_t lddo, const float* lse, float* delta, float* dq, float* dk, float* dv,
                      int64_t ldg, int Bt, int N, int H, const int* off, const int* dh, float inv_scale, int bias_mode,
                      const float* a, int nbox, const float* bpe, const float* dense, float* da, float* dbpe,
-                     float* ddense, void* stream)
+                     float* ddense, float drop_p, uint64_t seed, void* stream)
 {
     VOG_REQUIRE(Bt >= 0 && N >= 0, "vog_attn_bwd_f32: negative dimension");
     if (Bt == 0 || N == 0) return 0;
     VOG_REQUIRE(q && k && v && out && dout && lse && delta && dq && dk && dv && off && dh, "vog_attn_bwd_f32: null operand");
     VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_attn_bwd_f32: bad bias_mode %d", bias_mode);
     return attn_bwd_f32(q, k, v, ld, out, ldo, dout, lddo, lse, delta, dq, dk, dv, ldg, Bt, N, H, off, dh, inv_scale,
-                        bias_mode, a, nbox, bpe, dense, da, dbpe, ddense, (cudaStream_t)stream);
+                        bias_mode, a, nbox, bpe, dense, da, dbpe, ddense, (cudaStream_t)stream, drop_p, (unsigned long long)seed);
 }
 
 int vog_pe_project_bwd(const float* props, int ldp, const float* da, float* dW, int rows, int H, float vid_w,

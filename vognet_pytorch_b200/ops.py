@@ -74,9 +74,10 @@ def sgemm_nt(a, w, bias=None, residual=None, relu=False, out=None):
 
 
 def attn_fwd_f32(q, k, v, Bt, N, head_dims, inv_scale, out=None, bias_mode=BIAS_NONE, a=None,
-                 nbox=0, bpe=None, dense=None, lse=None):
+                 nbox=0, bpe=None, dense=None, lse=None, drop_p=0.0, seed=0):
     """q,k,v: [Bt*N, d] (row-major views, same ld); heads are consecutive column chunks.  ``lse`` (optional
-    [Bt,H,N] fp32) receives the log-sum-exp of the scaled scores for the backward."""
+    [Bt,H,N] fp32) receives the log-sum-exp of the scaled scores for the backward; ``drop_p`` / ``seed``: training-mode
+    dropout on the probabilities."""
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
         _req(t, torch.float32, n, 2)
     ld = _rowmajor2d(q, 'q')
@@ -101,7 +102,8 @@ def attn_fwd_f32(q, k, v, Bt, N, head_dims, inv_scale, out=None, bias_mode=BIAS_
     L = _lib.lib()
     _lib.check(L.vog_attn_fwd_f32(_ptr(q), _ptr(k), _ptr(v), ld, _ptr(out), _rowmajor2d(out, 'out'),
                                   Bt, N, H, off_arr, dh_arr, float(inv_scale), bias_mode, _ptr(a),
-                                  nbox, _ptr(bpe), _ptr(dense), _ptr(lse), _stream()), 'vog_attn_fwd_f32')
+                                  nbox, _ptr(bpe), _ptr(dense), _ptr(lse), float(drop_p), int(seed), _stream()),
+               'vog_attn_fwd_f32')
     return out
 
 

@@ -83,7 +83,7 @@ def layernorm_bwd(dy, x, gamma, dgamma, dbeta, dxsum=None, eps=1e-5, want_f32=Tr
 
 
 def attn_bwd_f32(q, k, v, out, dout, lse, Bt, N, head_dims, inv_scale, bias_mode=BIAS_NONE, a=None, nbox=0, bpe=None,
-                 dense=None, da=None, dbpe=None, want_ddense=False):
+                 dense=None, da=None, dbpe=None, want_ddense=False, drop_p=0.0, seed=0):
     """q,k,v [Bt*N, ld] views (heads = column chunks), out/dout [Bt*N, d] -> dqkv [Bt*N, 3d] (dq | dk | dv) and, for a
     dense bias, its gradient [Bt,N,N,H]; da / dbpe accumulated for the rank-1 bias."""
     H, d = len(head_dims), sum(head_dims)
@@ -100,7 +100,7 @@ def attn_bwd_f32(q, k, v, out, dout, lse, Bt, N, head_dims, inv_scale, bias_mode
                                            _rowmajor2d(dout, 'dout'), _ptr(lse), _ptr(delta), _ptr(dqkv[:, :d]),
                                            _ptr(dqkv[:, d:2 * d]), _ptr(dqkv[:, 2 * d:]), 3 * d, Bt, N, H, off_arr, dh_arr,
                                            float(inv_scale), bias_mode, _ptr(a), nbox, _ptr(bpe), _ptr(dense), _ptr(da),
-                                           _ptr(dbpe), _ptr(ddense), _stream()), 'vog_attn_bwd_f32')
+                                           _ptr(dbpe), _ptr(ddense), float(drop_p), int(seed), _stream()), 'vog_attn_bwd_f32')
     return dqkv, ddense
 
 

@@ -128,55 +128,71 @@ def _bias_kw(bias):
     return dict(bias_mode=ops.BIAS_NONE)
 
 
-def stack_forward_f32(ex, x2, Bt, N, bias, be):
-    """EncoderExecutor._run_fp32x with a tape.  x2 [Bt*N, d] -> (y [Bt*N, d], [layer tapes])."""
+def _res_ln_f32(branch, x2, ln, dc, p, site):
+    """LN(x + drop(branch)) (code/transformer_code.py:30-31); `branch` already holds x + branch when p == 0."""
+    pre = branch if p <= 0.0 else ob.dropout(branch, p, dc.seed, site, residual=x2, out=branch)[0]
+    return pre, ops.add_layernorm(pre, None, ln.weight, ln.bias, ln.eps)
+
+
+def stack_forward_f32(ex, x2, Bt, N, bias, be, dc=None, site0=0):
+    """EncoderExecutor._run_fp32x with a tape.  x2 [Bt*N, d] -> (y [Bt*N, d], [layer tapes]).  Dropout (dc active):
+    the same call sites, seeds and counter-based masks as the tensor-core step (training_tc.stack_forward_tc)."""
     d, H = ex.d, ex.H
     inv_scale = 1.0 / math.sqrt(d)
     tapes = []
     bkw = _bias_kw(bias)
+    p = dc.p_tx(ex) if dc is not None else 0.0
     for l, layer in enumerate(ex.stack.layers):
         att, ffn = layer.selfattn, layer.feedforward
         t = Tape(x=x2)
         t.qkv = ops.sgemm_nt(x2, ex._packed(l, layer))
         t.lse = torch.empty(Bt * H * N, device=x2.device, dtype=torch.float32)
+        t.seed = dc.site_seed(1000 + site0 + l) if p > 0.0 else 0
         t.o = ops.attn_fwd_f32(t.qkv[:, :d], t.qkv[:, d:2 * d], t.qkv[:, 2 * d:], Bt, N, ex.head_dims, inv_scale,
-                               lse=t.lse, **bkw)
-        t.pre = ops.sgemm_nt(t.o, att.layer.wo.weight, residual=x2)
-        t.y = ops.add_layernorm(t.pre, None, att.layernorm.weight, att.layernorm.bias, att.layernorm.eps)
+                               lse=t.lse, drop_p=p, seed=t.seed, **bkw)
+        br = ops.sgemm_nt(t.o, att.layer.wo.weight, residual=x2 if p <= 0.0 else None)
+        t.pre, t.y = _res_ln_f32(br, x2, att.layernorm, dc, p, site0 + 2 * l)
         t.h = ops.sgemm_nt(t.y, ffn.layer.linear1.weight, ffn.layer.linear1.bias, relu=True)
-        t.pre2 = ops.sgemm_nt(t.h, ffn.layer.linear2.weight, ffn.layer.linear2.bias, residual=t.y)
-        x2 = ops.add_layernorm(t.pre2, None, ffn.layernorm.weight, ffn.layernorm.bias, ffn.layernorm.eps)
+        br2 = ops.sgemm_nt(t.h, ffn.layer.linear2.weight, ffn.layer.linear2.bias, residual=t.y if p <= 0.0 else None)
+        t.pre2, x2 = _res_ln_f32(br2, t.y, ffn.layernorm, dc, p, site0 + 2 * l + 1)
         tapes.append(t)
     return x2, tapes
 
 
-def stack_backward_f32(ex, prefix, tapes, dout, Bt, N, bias, sink, be, da=None, dbpe=None):
+def stack_backward_f32(ex, prefix, tapes, dout, Bt, N, bias, sink, be, da=None, dbpe=None, dc=None, site0=0):
     """Gradient of a post-LN encoder stack (code/transformer_code.py:84-125,189-241).  dout [Bt*N, d] ->
     d input [Bt*N, d]; parameter gradients into `sink` under `prefix`.encoder.layers.{l}...; da / dbpe accumulate
     the relative-position bias gradients (rank-1 form)."""
     d, H = ex.d, ex.H
     inv_scale = 1.0 / math.sqrt(d)
     bkw = _bias_kw(bias)
+    p = dc.p_tx(ex) if dc is not None else 0.0
     for l in reversed(range(len(tapes))):
         layer, t = ex.stack.layers[l], tapes[l]
         att, ffn = layer.selfattn, layer.feedforward
         pl = f'{prefix}.encoder.layers.{l}'
-        # ---- feed-forward residual block: out = LN(y + W2 relu(W1 y + b1) + b2)
+        # ---- feed-forward residual block: out = LN(y + drop(W2 relu(W1 y + b1) + b2))
         dpre2, _ = ob.layernorm_bwd(dout, t.pre2, ffn.layernorm.weight, sink.get(pl + '.feedforward.layernorm.weight'),
                                     sink.get(pl + '.feedforward.layernorm.bias'),
-                                    dxsum=sink.get(pl + '.feedforward.layer.linear2.bias'), eps=ffn.layernorm.eps)
-        sink.set(pl + '.feedforward.layer.linear2.weight', be.lin_dw(dpre2, t.h))
-        dh = be.lin_dx(dpre2, ffn.layer.linear2.weight)
+                                    dxsum=sink.get(pl + '.feedforward.layer.linear2.bias') if p <= 0.0 else None,
+                                    eps=ffn.layernorm.eps)
+        dbr = dpre2
+        if p > 0.0:
+            dbr = ob.dropout(dpre2, p, dc.seed, site0 + 2 * l + 1)[0]
+            ob.colsum_acc(dbr, sink.get(pl + '.feedforward.layer.linear2.bias'))
+        sink.set(pl + '.feedforward.layer.linear2.weight', be.lin_dw(dbr, t.h))
+        dh = be.lin_dx(dbr, ffn.layer.linear2.weight)
         ob.relu_bwd(dh, t.h, dbias=sink.get(pl + '.feedforward.layer.linear1.bias'), inplace=True)
         sink.set(pl + '.feedforward.layer.linear1.weight', be.lin_dw(dh, t.y))
         dy = be.lin_dx(dh, ffn.layer.linear1.weight, residual=dpre2)
-        # ---- attention residual block: y = LN(x + Wo attn(x))
+        # ---- attention residual block: y = LN(x + drop(Wo attn(x)))
         dpre, _ = ob.layernorm_bwd(dy, t.pre, att.layernorm.weight, sink.get(pl + '.selfattn.layernorm.weight'),
                                    sink.get(pl + '.selfattn.layernorm.bias'), eps=att.layernorm.eps)
-        sink.set(pl + '.selfattn.layer.wo.weight', be.lin_dw(dpre, t.o))
-        do = be.lin_dx(dpre, att.layer.wo.weight)
+        dbr = dpre if p <= 0.0 else ob.dropout(dpre, p, dc.seed, site0 + 2 * l)[0]
+        sink.set(pl + '.selfattn.layer.wo.weight', be.lin_dw(dbr, t.o))
+        do = be.lin_dx(dbr, att.layer.wo.weight)
         dqkv, _ = ob.attn_bwd_f32(t.qkv[:, :d], t.qkv[:, d:2 * d], t.qkv[:, 2 * d:], t.o, do, t.lse, Bt, N,
-                                  ex.head_dims, inv_scale, da=da, dbpe=dbpe, **bkw)
+                                  ex.head_dims, inv_scale, da=da, dbpe=dbpe, drop_p=p, seed=t.seed, **bkw)
         dwqkv = be.lin_dw(dqkv, t.x)                                   # [3d, d] = dWq | dWk | dWv
         for i, nm in enumerate(('wq', 'wk', 'wv')):
             sink.set(f'{pl}.selfattn.layer.{nm}.weight', dwqkv[i * d:(i + 1) * d])
@@ -297,12 +313,6 @@ def forward_train_f32(mdl, inp):
     """Training forward in exact fp32.  -> (logits [B,1,nsrl,P], tape)."""
     be = F32Backend()
     dc = DropCtx(mdl, dropout_active(mdl))
-    if dc.active and ((mdl.USE_OBJ_TX and mdl.cfg.mdl.obj_tx.to_use and mdl.obj_txf._exec.drop > 0) or
-                      (mdl.USE_MUL_TX and mdl.cfg.mdl.mul_tx.to_use and mdl.mult_txf._exec.drop > 0)):
-        raise NotImplementedError(
-            "vognet_pytorch_b200: the exact-fp32 mode trains without dropout (model.train_dropout = False, or "
-            "attn_drop = 0); dropout (code/transformer_code.py:26,31,153) is part of the tensor-core training step: "
-            "model.set_compute('bf16')")
     tp = Tape(be=be, dc=dc)
     feat, seg, props = inp['pad_region_feature'], inp['seg_feature_for_frms'], inp['pad_proposals']
     B, P, _ = feat.shape
@@ -340,7 +350,7 @@ def forward_train_f32(mdl, inp):
         if otx.use_rel:
             a = ops.pe_project(props2, mdl.pe_obj_sub_enc[0].weight, mdl.vid_w, mdl.vid_h, fdiv)
             bias = RelBias(a, mdl.pe_obj_sub_enc[0].bias, N_o)
-        xv, tapes = stack_forward_f32(mdl.obj_txf._exec, x0, Bt_o, N_o, bias, be)
+        xv, tapes = stack_forward_f32(mdl.obj_txf._exec, x0, Bt_o, N_o, bias, be, dc, DropCtx.OBJ)
         tp.obj = Tape(tapes=tapes, Bt=Bt_o, N=N_o, bias=bias, fdiv=fdiv)
 
     # ---- tokens [vis | lang] regrouped per frame (code/mdl_vog.py:316-344,693-699) + multimodal transformer
@@ -356,7 +366,7 @@ def forward_train_f32(mdl, inp):
         if mtx.use_rel:
             a = ops.pe_project(props2, mdl.pe_mul_sub_enc[0].weight, mdl.vid_w, mdl.vid_h, float(nfrm))
             bias = RelBias(a, mdl.pe_mul_sub_enc[0].bias, nppf2)
-        xm, tapes = stack_forward_f32(mdl.mult_txf._exec, xm, B * nfrm, nsrl * nppf2, bias, be)
+        xm, tapes = stack_forward_f32(mdl.mult_txf._exec, xm, B * nfrm, nsrl * nppf2, bias, be, dc, DropCtx.MUL)
         tp.mul = Tape(tapes=tapes, Bt=B * nfrm, N=nsrl * nppf2, bias=bias)
     tp.xm = xm
     # ---- scorer (code/mdl_vog.py:224-230,675-677) + inverse regroup (:724-737)
@@ -420,7 +430,7 @@ def backward_train_f32(mdl, tp, dlogits, sink=None, on_lang_done=None):
             da = torch.zeros_like(tp.mul.bias.a)
             dbpe = sink.get('pe_mul_sub_enc.0.bias')
         dxm = stack_backward_f32(mdl.mult_txf._exec, 'mult_txf', tp.mul.tapes, dxm, tp.mul.Bt, tp.mul.N, tp.mul.bias,
-                                 sink, be, da=da, dbpe=dbpe)
+                                 sink, be, da=da, dbpe=dbpe, dc=tp.dc, site0=DropCtx.MUL)
         if da is not None:
             ob.pe_project_bwd(tp.props2, da, sink.get('pe_mul_sub_enc.0.weight'), mdl.vid_w, mdl.vid_h, float(nfrm))
     # ---- tokens -> factors
@@ -437,7 +447,7 @@ def backward_train_f32(mdl, tp, dlogits, sink=None, on_lang_done=None):
             da = torch.zeros_like(tp.obj.bias.a)
             dbpe = sink.get('pe_obj_sub_enc.0.bias')
         dvis = stack_backward_f32(mdl.obj_txf._exec, 'obj_txf', tp.obj.tapes, dvis, tp.obj.Bt, tp.obj.N, tp.obj.bias,
-                                  sink, be, da=da, dbpe=dbpe)
+                                  sink, be, da=da, dbpe=dbpe, dc=tp.dc, site0=DropCtx.OBJ)
         if da is not None:
             ob.pe_project_bwd(tp.props2, da, sink.get('pe_obj_sub_enc.0.weight'), mdl.vid_w, mdl.vid_h, tp.obj.fdiv)
     # ---- encoders
