@@ -1048,6 +1048,7 @@ int lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, con
 // (utils/mdl_srl_utils.py:104,128,150).  out = x * keep / (1-p) (+ residual); keep is a counter-based function of
 // (seed, stream, row, column) - the backward calls the same kernel on the output gradient with the same ids.
 // =============================================================================================
+template <bool kVec>
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ res, long long ldr,
                float* __restrict__ out, long long ldo, void* __restrict__ out_lp, long long ldlp, int lp_kind,
@@ -1062,15 +1063,47 @@ dropout_kernel(const float* __restrict__ x, long long ldx, const float* __restri
     attn_rand16x8(seed, stream, (uint32_t)r, (uint32_t)c0, rnd);
     const uint32_t thr = drop_threshold16(p);
     const float inv_keep = 1.f / (1.f - p);
+    if constexpr (kVec) {
+        // N % 8 == 0 and 16-byte aligned rows (host-checked): two float4 per operand, one 32-byte segment per thread
+        float v[8];
+        {
+            const float4 a = *reinterpret_cast<const float4*>(x + r * ldx + c0), b = *reinterpret_cast<const float4*>(x + r * ldx + c0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int c = c0 + e;
-        if (c >= N) break;
-        const bool keep = ((rnd[e >> 1] >> (16 * (e & 1))) & 0xffffu) >= thr;
-        float v = keep ? x[r * ldx + c] * inv_keep : 0.f;
-        if (res) v += res[r * ldr + c];
-        if (out) out[r * ldo + c] = v;
-        if (out_lp) store_lp1(out_lp, r * ldlp + c, v, lp_kind);
+        for (int e = 0; e < 8; ++e)
+            v[e] = ((rnd[e >> 1] >> (16 * (e & 1))) & 0xffffu) >= thr ? v[e] * inv_keep : 0.f;
+        if (res) {
+            const float4 a = *reinterpret_cast<const float4*>(res + r * ldr + c0), b = *reinterpret_cast<const float4*>(res + r * ldr + c0 + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        if (out) {
+            *reinterpret_cast<float4*>(out + r * ldo + c0) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(out + r * ldo + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (out_lp) {
+            if (lp_kind == 1) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_lp) + r * ldlp + c0) =
+                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) store_lp1(out_lp, r * ldlp + c0 + e, v[e], lp_kind);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c0 + e;
+            if (c >= N) break;
+            const bool keep = ((rnd[e >> 1] >> (16 * (e & 1))) & 0xffffu) >= thr;
+            float v = keep ? x[r * ldx + c] * inv_keep : 0.f;
+            if (res) v += res[r * ldr + c];
+            if (out) out[r * ldo + c] = v;
+            if (out_lp) store_lp1(out_lp, r * ldlp + c, v, lp_kind);
+        }
     }
 }
 
@@ -1082,8 +1115,15 @@ int dropout_apply(const float* x, long long ldx, const float* res, long long ldr
     VOG_REQUIRE(p >= 0.f && p < 1.f, "dropout: probability %f", (double)p);
     VOG_REQUIRE(M < (1LL << 32), "dropout: too many rows");
     const long long n = M * ((N + 7) >> 3);
-    dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ldx, res, ldr, out, ldo, out_lp, ldlp, lp_kind, M, N, p,
-                                                                seed, stream);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec = N % 8 == 0 && al16(x) && ldx % 4 == 0 && (!res || (al16(res) && ldr % 4 == 0)) &&
+                     (!out || (al16(out) && ldo % 4 == 0)) && (!out_lp || (al16(out_lp) && ldlp % 8 == 0));
+    if (vec)
+        dropout_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ldx, res, ldr, out, ldo, out_lp, ldlp, lp_kind, M,
+                                                                          N, p, seed, stream);
+    else
+        dropout_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, ldx, res, ldr, out, ldo, out_lp, ldlp, lp_kind, M,
+                                                                           N, p, seed, stream);
     return check_launch("dropout");
 }
 
