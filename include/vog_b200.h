@@ -433,7 +433,7 @@ int vog_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int K
  * warp / the MMA issuer of vog_tc_attn_fwd (library built with -DVOG_ATTN_PROFILE). */
 void vog_debug_gemm_trace(void* buf);
 void vog_debug_pdl(int on);                   /* A/B: 0 = plain stream-ordered launches instead of programmatic dependent launches */
-void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 0 tagged 64-bit words, 1 per-CTA release flags */
+void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 2 self-tagged per-CTA records (default), 0 tagged 64-bit words, 1 per-CTA release flags; bits 8-23: poll back-off in ns */
 void vog_debug_lstm_trace(void* buf);          /* 8 int64: matvec, reduce, cell+publish, poll, barrier cycles, steps */
 void vog_debug_attn_prof(void* buf);
 void vog_debug_attn_cluster(int c);            /* v2 attention cluster size: 1, 2, 4, or 0 = automatic */

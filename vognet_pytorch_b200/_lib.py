@@ -120,13 +120,16 @@ def lib():
                 raise RuntimeError(
                     f'{SO_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
                     '(nvcc, sm_100a).  vognet_pytorch_b200 has no fallback path.')
-            l = ctypes.CDLL(SO_PATH)
+            # VOG_B200_SO: an instrumented build of the SAME sources (profiles/: -DVOG_LSTM_TRACE, -DVOG_ATTN_PROFILE)
+            l = ctypes.CDLL(os.environ.get('VOG_B200_SO') or SO_PATH)
             for name, argtypes in _SIGNATURES.items():
                 fn = getattr(l, name)          # AttributeError if the symbol is not exported
                 fn.argtypes = argtypes
                 fn.restype = _RESTYPE[name]
             if os.environ.get('VOG_PDL', '0') == '1':       # A/B: programmatic dependent launches (measured: no gain)
                 l.vog_debug_pdl(1)
+            if os.environ.get('VOG_LSTM_XMODE'):            # A/B: h_t exchange protocol of the recurrence kernel
+                l.vog_debug_lstm_exchange(int(os.environ['VOG_LSTM_XMODE'], 0))
             _lib = l
     return _lib
 

@@ -24,6 +24,7 @@ constexpr int LS_THREADS = 512;
 constexpr int LS_MAXB = 8;          // sequences per launch
 constexpr int LS_MAXU = 64;         // hidden units per CTA (streaming kernel; 64 = a 32-CTA launch at H = 1024)
 constexpr int LS_WS_HEADER = 1024;  // workspace header: barrier counters / per-CTA flags
+constexpr int LS_REC_MAX_CTAS = 128;  // record exchange: CTAs per direction the workspace is sized for
 
 struct LstmParams {
     const float* gx; long long ldg;       // [T*Bq, ldg]; direction d at columns d*4H
@@ -202,10 +203,18 @@ lstm_rec_kernel(const LstmParams p)
 // Per step a warp computes its 4 x BQ partial dot products, reduce-scatters them over the 32 lanes
 // (4*BQ - 1 + log-tail shuffles instead of 5 * 4 * BQ), adds the input projection and runs the cell
 // update for its unit in-warp.  h_t is exchanged between the CTAs of a direction WITHOUT a grid
-// barrier: every value travels as one 64-bit word {fp32 bits, step tag} written with a relaxed
-// gpu-scope store into a double-buffered global array; consumers poll the words they need until
-// the tag matches (one L2 round trip after the producer's store instead of atomic + flag + reload).
-// The array is zeroed by a memset node in front of the launch, so tags never alias across replays.
+// barrier, through a double-buffered global array that a kernel in front of the launch zeroes (so
+// tags never alias across graph replays).  Three protocols (template parameter XM):
+//   2 (default) self-tagged RECORDS: a CTA gathers its U x BQ values in shared memory and ONE warp
+//     writes them as one record (full 128-byte lines, one writer per line, one write per line and
+//     step); the lowest mantissa bit of every fp32 word carries a step-derived tag, so consumers
+//     validate each 16-byte load by itself - no flag, no fence, no {value, tag} pairs.  Measured
+//     (profiles/r2/lstm_records.txt): the poll + barrier phase went from 9.6 k to 1.2 k cycles per
+//     step - with per-unit stores every line of the array was written by 16 warps of 2 CTAs at 16
+//     different times while 74 CTAs polled it, and each partial write invalidated and re-fetched
+//     the line across the two L2 partitions;
+//   0 every value as one 64-bit word {fp32 bits, step tag} stored by its producer lane, consumers
+//     poll pairs of words;  1 plain values + one release flag per CTA (kept for A/B).
 // -------------------------------------------------------------------------------------------------
 constexpr int LR_H = 1024;
 constexpr int LR_NI = LR_H / 128;          // float4 per gate row per lane
@@ -235,6 +244,20 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
+template <int VW> struct XVec { unsigned w[VW]; };
+template <int VW>
+__device__ __forceinline__ XVec<VW> ld_relaxed_words(const unsigned* p) {        // VW = 1, 2, 4 words, naturally aligned
+    XVec<VW> v;
+    if constexpr (VW == 4)
+        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    else if constexpr (VW == 2)
+        asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.w[0]), "=r"(v.w[1]) : "l"(p) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v.w[0]) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {      // (a.x*b.x + c.x, a.y*b.y + c.y), one FFMA2
     unsigned long long d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;"
@@ -248,7 +271,9 @@ struct LstmResParams {
     const float* gx; long long ldg;
     const float* whh;
     const long long* lens;
-    unsigned long long* hx;               // [2 parity, 2 dir, Bq, H] {value, tag} (xmode 0) / fp32 values (xmode 1)
+    unsigned long long* hx;               // [2 parity, 2 dir, Bq, H] {value, tag} (xmode 0) / fp32 values (xmode 1) /
+                                          // [2 parity, 2 dir, ctas_per_dir, 16 units, BQ] self-tagged fp32 words (xmode 2)
+    int backoff_ns;                       // xmode 2: __nanosleep between two polls of a word group that is not there yet
     unsigned* flags;                      // [2 dir * ctas_per_dir] last published step + 1 (xmode 1)
     int xmode;
     void* out_lp; long long ld_out; int lp_kind;
@@ -281,10 +306,13 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[V], int lane) {
 
 // float4 per gate row per lane that stay in registers (the rest lives in shared memory): bounded by the
 // 128-register budget of a 448-thread CTA on one side and by 227 KB of shared memory on the other
+// (144 registers per thread would hold a third weight group, but 448 threads x 144 registers do not launch:
+//  "too many resources requested" - the register file is allocated in larger units than ptxas' 128 suggests)
 template <int BQ> struct LrCfg { static constexpr int NREG = BQ <= 4 ? 2 : 3; };
+#define LR_BOUNDS __launch_bounds__(LR_THREADS, 1)
 
-template <int BQ>
-__global__ void __launch_bounds__(LR_THREADS, 1)
+template <int BQ, int XM>          // XM: h_t exchange protocol (0 tagged 64-bit words, 1 per-CTA flags, 2 self-tagged records)
+__global__ void LR_BOUNDS
 lstm_rec_resident_kernel(const LstmResParams p)
 {
     constexpr int H = LR_H;
@@ -295,6 +323,7 @@ lstm_rec_resident_kernel(const LstmResParams p)
     float4* w_s = reinterpret_cast<float4*>(sm);             // [4 gates][NI - NREG][NT]
     float* h_s = sm + 4 * (LR_NI - LR_NREG) * NT * 4;        // [2 parity][BQ][H]
     float* gate_s = h_s + 2 * BQ * H;                        // [U][V]
+    unsigned* x_s = reinterpret_cast<unsigned*>(gate_s + LR_MAXU * V);   // [U][BQ] this CTA's record of h_t (xmode 2)
     __shared__ int len_s[LS_MAXB];
     __shared__ int tmax_s;
 
@@ -304,6 +333,9 @@ lstm_rec_resident_kernel(const LstmResParams p)
     const int u = c * p.U + warp;                            // hidden unit of this warp
     const bool unit_ok = u < H;
 
+#ifdef VOG_LSTM_TRACE
+    const long long t_entry = clock64();
+#endif
     pdl_trigger();
     for (int i = tid; i < 2 * BQ * H; i += NT) h_s[i] = 0.f;
     // ---- one-time weight load: row (gate, u), columns 128 i + 4 lane.  W_hh is a parameter (written by plain launches
@@ -346,6 +378,7 @@ lstm_rec_resident_kernel(const LstmResParams p)
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
     long long tc[5] = {0, 0, 0, 0, 0};
     long long tprev = tr ? clock64() : 0;
+    const long long t_loop = tprev;                          // entry -> first step: zero h, weight load, lens
 #define LR_TRACE(i) if (tr) { const long long tn = clock64(); tc[i] += tn - tprev; tprev = tn; }
 #else
 #define LR_TRACE(i)
@@ -435,9 +468,9 @@ lstm_rec_resident_kernel(const LstmResParams p)
                     a[0] = gi; a[H] = gf; a[2 * (size_t)H] = gg; a[3 * (size_t)H] = go; a[4 * (size_t)H] = tcn; a[5 * (size_t)H] = cp;
                 }
             }
-            if (step + 1 < Tmax) {
+            if (step + 1 < Tmax && XM != 2) {
                 const size_t xi = (((size_t)(step & 1) * 2 + d) * Bq + lane) * H + u;
-                if (p.xmode == 0)
+                if (XM == 0)
                     st_relaxed_u64(p.hx + xi, ((unsigned long long)(unsigned)(step + 1) << 32) | __float_as_uint(h_reg));
                 else
                     __stcg(reinterpret_cast<float*>(p.hx) + xi, h_reg);
@@ -445,8 +478,73 @@ lstm_rec_resident_kernel(const LstmResParams p)
             store_lp(p.out_lp, ((long long)t * p.bq_total + lane) * p.ld_out + (long long)d * H + u, hval, p.lp_kind);
         }
         __syncwarp();
+        // ---- record exchange (xmode 2): the CTA's U x BQ values leave as ONE record written by one warp - every 128-byte
+        //      line of the exchange array has a single writer and is written once per step (one coherence event per
+        //      line and step instead of one per hidden unit).  Every 32-bit word validates itself: the lowest mantissa
+        //      bit carries ((step >> 1) & 1) ^ 1, which differs from what the slot held two steps ago and from the
+        //      zeroed array, so no flag, no fence and no 64-bit {value, tag} pairs are needed; the consumer clears the
+        //      bit (h_t is used with a 23-bit mantissa whose last bit is zero: |error| <= 2^-24 relative).
+        const unsigned tagbit = (((unsigned)step >> 1) & 1u) ^ 1u;
+        constexpr int RS = 16 * BQ;                              // words per record (16 unit slots, U <= 14 used)
+        unsigned* xrec = reinterpret_cast<unsigned*>(p.hx) + (((size_t)(step & 1) * 2 + d) * p.ctas_per_dir) * RS;
+        if (XM == 2 && step + 1 < Tmax) {
+            if (lane < BQ) x_s[warp * BQ + lane] = (__float_as_uint(h_reg) & ~1u) | tagbit;   // lanes >= Bq: h_reg == 0
+            __syncthreads();
+            if (warp == 0) {
+                unsigned* mine = xrec + (size_t)c * RS;
+                const int nw = (NT >> 5) * BQ;
+                for (int i = lane; i < nw; i += 32) st_relaxed_u32(mine + i, x_s[i]);
+            }
+        }
         LR_TRACE(2)
-        if (step + 1 < Tmax && p.xmode == 1) {
+        if (XM == 2 && step + 1 < Tmax) {
+            // ---- collect: word groups of (unit, sequences): item q -> (record q >> 4, unit slot q & 15[, half])
+            constexpr int VW = BQ < 4 ? BQ : 4, NV = BQ / VW, MAXI = BQ <= 4 ? 3 : 6;
+            const int nitems = p.ctas_per_dir * 16 * NV;
+            float* hnext = h_s + ((step + 1) & 1) * BQ * H;
+            unsigned pend = 0;
+#pragma unroll
+            for (int k = 0; k < MAXI; ++k) {
+                const int q = tid + k * NT, slot = q / NV, j = slot & 15;
+                if (q < nitems && j < p.U && (slot >> 4) * p.U + j < H) pend |= 1u << k;
+            }
+            XVec<VW> w[MAXI];
+            long long t0 = 0;
+            while (pend) {
+#pragma unroll
+                for (int k = 0; k < MAXI; ++k)
+                    if (pend & (1u << k)) {
+                        const int q = tid + k * NT, slot = q / NV, part = q % NV;
+                        w[k] = ld_relaxed_words<VW>(xrec + (size_t)(slot >> 4) * RS + (slot & 15) * BQ + part * VW);
+                    }
+#pragma unroll
+                for (int k = 0; k < MAXI; ++k)
+                    if (pend & (1u << k)) {
+                        bool ok = true;
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) ok = ok && (w[k].w[e] & 1u) == tagbit;
+                        if (ok) {
+                            pend &= ~(1u << k);
+                            const int q = tid + k * NT, slot = q / NV, part = q % NV;
+                            const int unit = (slot >> 4) * p.U + (slot & 15);
+#pragma unroll
+                            for (int e = 0; e < VW; ++e) hnext[(part * VW + e) * H + unit] = __uint_as_float(w[k].w[e] & ~1u);
+                        }
+                    }
+                if (pend) {
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > 4000000000LL) {
+                        printf("vog: lstm record-exchange timeout block %d step %d\n", (int)blockIdx.x, step);
+                        __trap();
+                    }
+                    if (p.backoff_ns > 0) __nanosleep((unsigned)p.backoff_ns);
+                }
+            }
+            LR_TRACE(3)
+            __syncthreads();
+            LR_TRACE(4)
+        }
+        if (XM == 1 && step + 1 < Tmax) {
             // ---- flag exchange: plain fp32 values + one release flag per producer CTA; consumers poll the
             //      <= 74 flags of their direction (little L2 traffic), then read the values once
             __syncthreads();
@@ -475,7 +573,7 @@ lstm_rec_resident_kernel(const LstmResParams p)
             LR_TRACE(4)
         }
         // ---- collect h_t of the whole direction: poll the tagged words
-        if (step + 1 < Tmax && p.xmode == 0) {
+        if (XM == 0 && step + 1 < Tmax) {
             const unsigned long long* src = p.hx + ((size_t)(step & 1) * 2 + d) * Bq * H;
             float* hnext = h_s + ((step + 1) & 1) * BQ * H;
             const unsigned want = (unsigned)(step + 1);
@@ -518,7 +616,7 @@ lstm_rec_resident_kernel(const LstmResParams p)
         }
     }
 #ifdef VOG_LSTM_TRACE
-    if (tr) { for (int i = 0; i < 5; ++i) p.trace[i] = tc[i]; p.trace[5] = Tmax; }
+    if (tr) { for (int i = 0; i < 5; ++i) p.trace[i] = tc[i]; p.trace[5] = Tmax; p.trace[6] = t_loop - t_entry; }
 #endif
     // rows past the longest sentence: zeros (pad_packed_sequence padding_value=0)
     if (lane < Bq && unit_ok)
@@ -534,20 +632,34 @@ __global__ void __launch_bounds__(256) zero16_kernel(uint4* __restrict__ p, long
     if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+template <int BQ, int XM>
+static int launch_resident_x(const LstmResParams& p, int ctas, int threads, cudaStream_t st)
+{
+    const size_t smem = (size_t)4 * (LR_NI - LrCfg<BQ>::NREG) * threads * 16 + (size_t)2 * BQ * LR_H * 4 + (size_t)LR_MAXU * 4 * BQ * 4 +
+                        (size_t)16 * BQ * 4;
+    VOG_CUDA(cudaFuncSetAttribute(lstm_rec_resident_kernel<BQ, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VOG_CUDA(launch_pdl(lstm_rec_resident_kernel<BQ, XM>, dim3(ctas), dim3(threads), smem, st, p));
+    return check_launch("lstm_rec_resident");
+}
+
 template <int BQ>
 static int launch_resident(const LstmResParams& p, int ctas, int threads, cudaStream_t st)
 {
-    const size_t smem = (size_t)4 * (LR_NI - LrCfg<BQ>::NREG) * threads * 16 + (size_t)2 * BQ * LR_H * 4 + (size_t)LR_MAXU * 4 * BQ * 4;
-    VOG_CUDA(cudaFuncSetAttribute(lstm_rec_resident_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VOG_CUDA(launch_pdl(lstm_rec_resident_kernel<BQ>, dim3(ctas), dim3(threads), smem, st, p));
-    return check_launch("lstm_rec_resident");
+    if (p.xmode == 2) return launch_resident_x<BQ, 2>(p, ctas, threads, st);
+    if (p.xmode == 1) return launch_resident_x<BQ, 1>(p, ctas, threads, st);
+    return launch_resident_x<BQ, 0>(p, ctas, threads, st);
 }
 
 static thread_local int g_lstm_force_streaming = 0;
 static thread_local int g_lstm_max_ctas = 0;
 void lstm_set_max_ctas(int n) { g_lstm_max_ctas = n > 0 ? n : 0; }
-static thread_local int g_lstm_xmode = 0;
-void lstm_set_exchange(int mode) { g_lstm_xmode = mode ? 1 : 0; }
+static thread_local int g_lstm_xmode = 2;          // default: self-tagged records (profiles/r2/lstm_records.txt)
+static thread_local int g_lstm_backoff = 0;
+void lstm_set_exchange(int mode)          // bits 0-7: protocol (0 tagged words, 1 flags, 2 records), bits 8-23: poll back-off in ns
+{
+    g_lstm_xmode = (mode & 0xff) <= 2 ? (mode & 0xff) : 0;
+    g_lstm_backoff = (mode >> 8) & 0xffff;
+}
 static thread_local long long* g_lstm_trace = nullptr;
 void lstm_set_trace(long long* buf) { g_lstm_trace = buf; }
 void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
@@ -555,7 +667,10 @@ void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
 long long lstm_workspace_bytes(int Bq, int H)
 {
     if (Bq > LS_MAXB) Bq = LS_MAXB;            // larger batches run in groups of LS_MAXB over the same workspace
-    return (((long long)2 * 2 * Bq * H * 8 + LS_WS_HEADER) + 15) & ~15LL;   // header (counters / flags) + exchange words
+    const long long tagged = (long long)2 * 2 * Bq * H * 8;                 // {value, tag} words
+    const int bqt = Bq <= 1 ? 1 : Bq <= 2 ? 2 : Bq <= 4 ? 4 : 8;            // kernel instantiation
+    const long long records = (long long)2 * 2 * LS_REC_MAX_CTAS * 16 * bqt * 4;   // 16-slot records, <= LS_REC_MAX_CTAS per direction
+    return (((tagged > records ? tagged : records) + LS_WS_HEADER) + 15) & ~15LL;   // header (counters / flags) + exchange
 }
 
 static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq, int bq_total,
@@ -585,6 +700,12 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
         rp.hx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + LS_WS_HEADER);
         rp.flags = reinterpret_cast<unsigned*>(workspace);
         rp.xmode = g_lstm_xmode;
+        rp.backoff_ns = g_lstm_backoff;
+        {   // the record exchange needs its item count to fit the unrolled poll and the workspace; else tagged words
+            const int bqt = Bq <= 1 ? 1 : Bq <= 2 ? 2 : Bq <= 4 ? 4 : 8;
+            const int nv = bqt > 4 ? 2 : 1, maxi = bqt <= 4 ? 3 : 6;
+            if (rp.xmode == 2 && (per_dir_u > LS_REC_MAX_CTAS || per_dir_u * 16 * nv > maxi * 32 * U)) rp.xmode = 0;
+        }
         VOG_REQUIRE(2 * per_dir_u * 4 <= LS_WS_HEADER, "lstm_layer_fwd: too many CTAs for the flag header");
         rp.out_lp = out_lp; rp.ld_out = ld_out; rp.lp_kind = lp_kind;
         rp.T = T; rp.Bq = Bq; rp.U = U; rp.ctas_per_dir = per_dir_u; rp.bq_total = bq_total;
