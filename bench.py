@@ -464,27 +464,19 @@ def main():
     # Two steps are in flight: while step i runs on the GPU the host stages step i+1 and then collects the
     # predictions of step i from pinned memory (event wait).  Every step still pays its own H2D copy (from
     # pinned host memory, on the copy stream) and its own D2H read of boxes / scores / indexs.
-    host_out = [None, None]
-    done = [None, None]
+    from vognet_pytorch_b200.runtime import PredictionFetcher
+    fetcher = PredictionFetcher(dev)        # D2H on its own stream: the next step's forward does not queue behind it
 
     def launch(i):
         nonlocal d2h
         b = pre.next()
         out, s = step(b)
-        res = (s['boxes'], s['scores'], s['indexs'])
-        if host_out[i & 1] is None:
-            host_out[i & 1] = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
-        for h_, r in zip(host_out[i & 1], res):
-            h_.copy_(r, non_blocking=True)
-        ev_ = torch.cuda.Event()
-        ev_.record()
-        done[i & 1] = ev_
+        ev_ = fetcher.fetch(i, (s['boxes'], s['scores'], s['indexs']))     # event: the step's compute is enqueued
         pre.release(b, ev_)                                # the batch's ring slot may be refilled after this step
-        d2h = sum(r.numel() * r.element_size() for r in res)
+        d2h = fetcher.nbytes
 
     def collect(i):
-        done[i & 1].synchronize()                          # the step's predictions are on the host
-        return host_out[i & 1]
+        return fetcher.get(i)                              # the step's predictions are on the host
 
     def e2e_run(n):
         for i in range(n):

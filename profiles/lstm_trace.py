@@ -13,15 +13,15 @@ dev = 'cuda:0'
 L = _lib.lib()
 T, H = 20, 1024
 NAMES = {0: 'tagged', 1: 'flags', 2: 'records'}
-CASES = [(4, 0), (4, 2), (4, 2 | (100 << 8)), (4, 2 | (400 << 8)), (4, 1), (8, 0), (8, 2), (1, 0), (1, 2)]
+CASES = [(4, 0), (4, 2), (4, 2 | (100 << 8)), (4, 1), (8, 0), (8, 2), (1, 0), (1, 2), (2, 2)]
 for Bq, mode in CASES:
     xmode, backoff = mode & 0xff, mode >> 8
     L.vog_debug_lstm_exchange(mode)
     gx = torch.rand(T * Bq, 8 * H, device=dev) - 0.5
     whh = (torch.rand(2, 4 * H, H, device=dev) - 0.5) / 32
     lens = torch.tensor([7, 18, 11, 7, 20, 3, 9, 14], device=dev)[:Bq]
-    if Bq == 1:
-        lens = torch.tensor([18], device=dev)
+    if Bq <= 2:
+        lens = torch.tensor([18, 11], device=dev)[:Bq]
     buf = torch.zeros(8, dtype=torch.int64, device=dev)
     for _ in range(3):
         ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_TF32)
@@ -43,7 +43,7 @@ for Bq, mode in CASES:
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
-    tag = f'Bq={Bq} exchange={NAMES[xmode]}' + (f' backoff={backoff}ns' if backoff else '')
+    tag = f'Bq={Bq} exchange={NAMES[xmode]}' + (f' backoff/delay={backoff}' if backoff else '')
     print(f'{tag}: median {sorted(ts)[10]:.1f} us, min {min(ts):.1f} us (20 launches incl. the zero kernel)')
     if v[5]:
         print(f'   traced launch: {v[5]} steps; per step (cycles): '

@@ -144,9 +144,13 @@ def select_fwd(scores, props, ncmp, nfrm, nppf, spat):
     if Pn != ncmp * nfrm * nppf or props.shape[1] != Pn:
         raise ValueError(f'select_fwd: P={Pn} != ncmp*nfrm*nppf={ncmp * nfrm * nppf}')
     scores, props = scores.contiguous(), props.contiguous()
-    boxes = torch.empty(B, nsrl, ncmp, nfrm, pdim, device=scores.device, dtype=torch.float32)
-    sc = torch.empty(B, nsrl, ncmp, nfrm, device=scores.device, dtype=torch.float32)
-    ix = torch.empty(B, nsrl, nfrm, device=scores.device, dtype=torch.int64)
+    # the three results are views of ONE allocation (int64 first: alignment), so a caller that wants them on the host
+    # can move them with a single copy (runtime.PredictionFetcher)
+    n_ix, n_bx, n_sc = B * nsrl * nfrm * 8, B * nsrl * ncmp * nfrm * pdim * 4, B * nsrl * ncmp * nfrm * 4
+    flat = torch.empty(n_ix + n_bx + n_sc, device=scores.device, dtype=torch.uint8)
+    ix = flat[:n_ix].view(torch.int64).view(B, nsrl, nfrm)
+    boxes = flat[n_ix:n_ix + n_bx].view(torch.float32).view(B, nsrl, ncmp, nfrm, pdim)
+    sc = flat[n_ix + n_bx:].view(torch.float32).view(B, nsrl, ncmp, nfrm)
     L = _lib.lib()
     _lib.check(L.vog_select_fwd(_ptr(scores), _ptr(props), pdim, _ptr(boxes), _ptr(sc), _ptr(ix),
                                 B, nsrl, ncmp, nfrm, nppf, int(spat), _stream()), 'vog_select_fwd')

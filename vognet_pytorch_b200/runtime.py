@@ -194,3 +194,73 @@ class BatchPrefetcher:
                 v.record_stream(cur)
         self._enqueue()
         return db
+
+
+class PredictionFetcher:
+    """Device -> host read of a step's predictions without stalling the compute stream: the copies run on a dedicated
+    stream (ordered after the producing work through an event), into a ring of pinned host buffers.  Tensors that are
+    views of one allocation (``ops.select_fwd`` returns boxes / scores / indexs that way) travel as ONE copy.
+
+        f = PredictionFetcher(device)
+        f.fetch(i, (boxes, scores, indexs))      # enqueue; returns immediately
+        ... enqueue step i + 1 ...
+        boxes_h, scores_h, indexs_h = f.get(i)   # blocks until step i's copy has landed
+    """
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self.slots = [None] * depth          # (signature, pinned flat / list, host views)
+        self.done = [None] * depth
+        self.nbytes = 0
+
+    @staticmethod
+    def _shared(tensors):
+        st = tensors[0].untyped_storage()
+        if not all(t.untyped_storage().data_ptr() == st.data_ptr() and t.is_contiguous() for t in tensors):
+            return False
+        return sum(t.numel() * t.element_size() for t in tensors) == st.nbytes()     # the allocation holds nothing else
+
+    def fetch(self, i, tensors):
+        tensors = tuple(tensors)
+        k = i % self.depth
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        sig = tuple((t.dtype, tuple(t.shape), t.storage_offset()) for t in tensors)
+        if self._shared(tensors):
+            st = tensors[0].untyped_storage()
+            dflat = torch.empty(0, dtype=torch.uint8, device=self.device).set_(st)
+            if self.slots[k] is None or self.slots[k][0] != sig:
+                hflat = torch.empty(dflat.numel(), dtype=torch.uint8).pin_memory()
+                views = []
+                for t in tensors:
+                    o, n = t.storage_offset() * t.element_size(), t.numel() * t.element_size()
+                    views.append(hflat[o:o + n].view(t.dtype).view(t.shape))
+                self.slots[k] = (sig, hflat, views)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                self.slots[k][1].copy_(dflat, non_blocking=True)
+            dflat.record_stream(self.stream)
+            self.nbytes = dflat.numel()
+        else:
+            if self.slots[k] is None or self.slots[k][0] != sig:
+                views = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in tensors]
+                self.slots[k] = (sig, None, views)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                for h, t in zip(self.slots[k][2], tensors):
+                    h.copy_(t, non_blocking=True)
+            for t in tensors:
+                t.record_stream(self.stream)
+            self.nbytes = sum(t.numel() * t.element_size() for t in tensors)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.done[k] = ev
+        return ready
+
+    def get(self, i):
+        k = i % self.depth
+        self.done[k].synchronize()
+        return self.slots[k][2]
