@@ -366,13 +366,19 @@ int vog_lang_embed_bwd(const int64_t* words, int nwords, const int64_t* mask, in
  *   vog_lstm_hprev     hprev [T*Bq, 2H]: the state each step started from (t-1 forward, t+1 reverse, 0 at the ends)
  *   vog_lstm_scan      G [T*Bq, 8H] gate pre-activations (gx + hprev.W_hh^T, recomputed by a GEMM) -> acts
  *                      [T*Bq, 2, 6, H]: i, f, g, o, tanh(c_t), c_{t-1}
- *   vog_lstm_bwd_steps dout [T*Bq, 2H] -> dG [T*Bq, 8H] (zeros beyond lens): T dependent launches, each one
- *                      dh_{prev} = dG_t . W_hh, read from the TRANSPOSED recurrent weight whh_t [2,H,4H] (one
- *                      contiguous row per output unit); carry_ws: 8*Bq*H floats of scratch; Bq <= 8 per call. */
+ *   vog_lstm_bwd_steps dout [T*Bq, 2H] -> dG [T*Bq, 8H] (zeros beyond lens); dh_{prev} = dG_t . W_hh is taken from the
+ *                      TRANSPOSED recurrent weight whh_t [2,H,4H].  H = 1024, Bq <= 4 on a 148-SM device: ONE persistent
+ *                      launch with the weights resident on chip (csrc/lstm_bwd.cu: every CTA multiplies the gate rows
+ *                      it owns into a partial sum over all columns and the CTAs exchange those through self-tagged
+ *                      records; whh [2,4H,H], the untransposed weight, is optional (NULL allowed) and only makes that
+ *                      kernel's one-time weight load coalesced); otherwise T dependent launches that stream whh_t from
+ *                      L2.  workspace:
+ *                      vog_lstm_bwd_workspace_bytes(Bq, H) bytes, 16-byte aligned; Bq <= 8 per call. */
 int vog_lstm_hprev(const float* hout, const int64_t* lens, float* hprev, int T, int Bq, int H, void* stream);
 int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int Bq, int H, void* stream);
-int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const int64_t* lens, float* dG,
-                       float* carry_ws, int T, int Bq, int H, void* stream);
+int64_t vog_lstm_bwd_workspace_bytes(int Bq, int H);
+int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const float* whh, const int64_t* lens,
+                       float* dG, void* workspace, int64_t workspace_bytes, int T, int Bq, int H, void* stream);
 
 /* Weight packing of one attention block for the tensor-core entry points: wq, wk, wv, wo
  * fp32 [d,d] (nn.Linear layout) -> wqkv [3*H*dhp, d] with the rows of every head zero-padded to dhp (row
@@ -383,8 +389,8 @@ int vog_pack_weights(const float* wq, const float* wk, const float* wv, const fl
 
 /* One workspace query for every entry point that takes a caller-provided workspace: op = VOG_WS_* ; the
  * dimensions a, b, c, d, e mean (M, N, K, tf32, BN) for VOG_WS_TC_GEMM, (Bt, N, H) for VOG_WS_TC_ATTN and
- * VOG_WS_TC_ATTN_BWD, (Bq, H) for VOG_WS_LSTM, (B, nsrl, P) for VOG_WS_LOSS; unused ones are ignored. */
-enum { VOG_WS_TC_GEMM = 0, VOG_WS_TC_ATTN = 1, VOG_WS_TC_ATTN_BWD = 2, VOG_WS_LSTM = 3, VOG_WS_LOSS = 4 };
+ * VOG_WS_TC_ATTN_BWD, (Bq, H) for VOG_WS_LSTM and VOG_WS_LSTM_BWD, (B, nsrl, P) for VOG_WS_LOSS; unused ones are ignored. */
+enum { VOG_WS_TC_GEMM = 0, VOG_WS_TC_ATTN = 1, VOG_WS_TC_ATTN_BWD = 2, VOG_WS_LSTM = 3, VOG_WS_LOSS = 4, VOG_WS_LSTM_BWD = 5 };
 int64_t vog_workspace_bytes(int op, int a, int b, int c, int d, int e);
 
 /* ---- training step on the tensor cores (compute mode 'bf16') ---------------------------------------------------
@@ -434,6 +440,7 @@ int vog_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int K
 void vog_debug_gemm_trace(void* buf);
 void vog_debug_pdl(int on);                   /* A/B: 0 = plain stream-ordered launches instead of programmatic dependent launches */
 void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 2 self-tagged per-CTA records (default), 0 tagged 64-bit words, 1 per-CTA release flags; bits 8-23: poll back-off in ns */
+void vog_debug_lstm_bwd_resident(int on);      /* 0 = per-step LSTM backward launches even where the persistent kernel applies */
 void vog_debug_lstm_trace(void* buf);          /* 8 int64: matvec, reduce, cell+publish, poll, barrier cycles, steps */
 void vog_debug_attn_prof(void* buf);
 void vog_debug_attn_cluster(int c);            /* v2 attention cluster size: 1, 2, 4, or 0 = automatic */

@@ -262,6 +262,47 @@ def test_lstm_resident_kernel_keeps_its_activations():
     assert _rel(a, b) < 1e-4 and float(a[~live].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('lens', [[20, 20, 20, 20], [20, 9, 14, 3], [5], [1, 1], [7, 20, 1], [2, 18, 18, 11]])
+def test_lstm_backward_persistent_kernel_matches_the_per_step_kernels(lens):
+    """H = 1024, <= 4 sequences: vog_lstm_bwd_steps runs ONE weight-resident launch (csrc/lstm_bwd.cu: per-CTA partial
+    sums exchanged as self-tagged records).  Against the T per-step launches on the same inputs, ragged lengths
+    included; repeated launches are bit-identical (no atomics, fixed summation order) and rows beyond lens are zero."""
+    from vognet_pytorch_b200 import _lib
+    g = torch.Generator().manual_seed(11 + len(lens))
+    T, Bq, Hh = 20, len(lens), 1024
+    gx = (torch.randn(T * Bq, 8 * Hh, generator=g) * 0.5).to(DEV)
+    whh = (torch.randn(2, 4 * Hh, Hh, generator=g) / 48).to(DEV)
+    lens_d = torch.tensor(lens, device=DEV)
+    _, acts = ops.lstm_layer_fwd(gx, whh, lens_d, T, Bq, ops.LP_NONE, want_acts=True)
+    dout = torch.randn(T * Bq, 2 * Hh, generator=g).to(DEV)
+    wt = whh.transpose(1, 2).contiguous()
+    L = _lib.lib()
+    L.vog_debug_lstm_bwd_resident(0)
+    try:
+        ref = ob.lstm_bwd_steps(dout, acts, wt, lens_d, T, Bq)
+    finally:
+        L.vog_debug_lstm_bwd_resident(1)
+    got = [ob.lstm_bwd_steps(dout, acts, wt, lens_d, T, Bq) for _ in range(3)]
+    got.append(ob.lstm_bwd_steps(dout, acts, wt, lens_d, T, Bq, whh=whh))       # weights loaded from W_hh itself
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], got[1]) and torch.equal(got[0], got[2]) and torch.equal(got[0], got[3])
+    live = (torch.arange(T, device=DEV).view(T, 1) < lens_d.view(1, Bq)).reshape(T * Bq)
+    assert float(got[0][~live].abs().max()) == 0.0 if bool((~live).any()) else True
+    # the two kernels add the 4096 products of a step in different orders (one warp per output unit vs 74 per-CTA
+    # partial sums): fp32 rounding differences of ~1e-6 per step, carried through up to 20 dependent steps.
+    # every direction and every timestep separately, so a broken half / a broken late step cannot hide
+    rels = []
+    for d_ in range(2):
+        sl = slice(d_ * 4 * Hh, (d_ + 1) * 4 * Hh)
+        rels.append(_rel(got[0][:, sl], ref[:, sl]))
+        gt, rt = got[0][:, sl].view(T, Bq, -1), ref[:, sl].view(T, Bq, -1)
+        for t in range(T):
+            if float(rt[t].abs().max()) > 0:
+                rels.append(_rel(gt[t], rt[t]))
+    print(f'\n[lstm bwd persistent vs per-step] lens {lens}: worst relative difference {max(rels):.2e}')
+    assert max(rels) < 5e-5
+
+
 def test_lin2_xmul_seg_relu_glue_backward():
     g = torch.Generator().manual_seed(5)
     B, nfrm, nsrl, nppf2, K, dv, dl = 2, 3, 4, 7, 96, 32, 16

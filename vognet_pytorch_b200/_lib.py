@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libvog_b200.so')
 SOURCES = ['vog_abi.cu', 'fp32_path.cu', 'tc_gemm.cu', 'tc_attn.cu', 'lstm_rec.cu', 'fused_glue.cu', 'loss_fwd.cu',
-           'relayout.cu', 'optim.cu', 'train_f32.cu', 'tc_gemm_tn.cu', 'tc_attn_bwd.cu']
+           'relayout.cu', 'optim.cu', 'train_f32.cu', 'tc_gemm_tn.cu', 'tc_attn_bwd.cu', 'lstm_bwd.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 

@@ -98,6 +98,7 @@ int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long
 // ---- lstm_rec.cu : persistent bidirectional LSTM recurrence -----------------------------------
 long long lstm_workspace_bytes(int Bq, int H);
 void lstm_set_trace(long long* buf);     // debug: phase cycle counters of CTA 0
+long long* lstm_get_trace();
 void lstm_set_exchange(int mode);        // debug: 2 self-tagged records (default), 0 tagged 64-bit words, 1 per-CTA release flags
 void lstm_set_max_ctas(int n);           // > 0: run the recurrence on at most n SMs (weight-streaming kernel)
 void lstm_force_streaming(int on);       // debug: disable the weight-resident kernel
@@ -153,8 +154,13 @@ int lang_embed_bwd(const long long* words, int nwords, const long long* mask, in
                    long long pad_idx, int Bq, const long long* lens, float* demb, cudaStream_t st);
 int lstm_hprev(const float* hout, const long long* lens, float* hprev, int T, int Bq, int H, cudaStream_t st);
 int lstm_scan(const float* G, const long long* lens, float* acts, int T, int Bq, int H, cudaStream_t st);
-int lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const long long* lens, float* dG,
-                   float* carry_ws, int T, int Bq, int H, cudaStream_t st);
+int lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const float* whh, const long long* lens, float* dG,
+                   float* carry_ws, long long ws_bytes, int T, int Bq, int H, cudaStream_t st);
+// ---- lstm_bwd.cu : weight-resident persistent backward through time -----------------------------
+long long lstm_bwd_workspace_bytes(int Bq, int H);
+void lstm_bwd_set_resident(int on);     // debug: 0 = per-step kernels even where the persistent kernel applies
+int lstm_bwd_resident(const float* dout, const float* acts, const float* whh_t, const float* whh, const long long* lens, float* dG,
+                      void* ws, long long ws_bytes, int T, int Bq, int H, cudaStream_t st);   // 1 launched, 0 n/a, -1 error
 
 // ---- loss_fwd.cu : grounding loss, forward ----------------------------------------------------
 long long loss_workspace_bytes(int B, int nsrl, int P);

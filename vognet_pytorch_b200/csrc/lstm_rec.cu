@@ -17,6 +17,7 @@
 // makes the whole language side CUDA-graph capturable.
 #include "common.cuh"
 #include "kernels.h"
+#include "lstm_xchg.cuh"
 
 namespace vog {
 
@@ -221,42 +222,6 @@ constexpr int LR_NI = LR_H / 128;          // float4 per gate row per lane
 constexpr int LR_MAXU = 14;                // warps (= hidden units) per CTA
 constexpr int LR_THREADS = 32 * LR_MAXU;   // 448 threads
 constexpr int LR_PB = 5;                   // 16-byte exchange loads in flight per thread
-
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
-    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ ulonglong2 ld_relaxed_u64x2(const unsigned long long* p) {
-    ulonglong2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <int VW> struct XVec { unsigned w[VW]; };
-template <int VW>
-__device__ __forceinline__ XVec<VW> ld_relaxed_words(const unsigned* p) {        // VW = 1, 2, 4 words, naturally aligned
-    XVec<VW> v;
-    if constexpr (VW == 4)
-        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
-    else if constexpr (VW == 2)
-        asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.w[0]), "=r"(v.w[1]) : "l"(p) : "memory");
-    else
-        asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v.w[0]) : "l"(p) : "memory");
-    return v;
-}
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {      // (a.x*b.x + c.x, a.y*b.y + c.y), one FFMA2
     unsigned long long d;
@@ -662,6 +627,7 @@ void lstm_set_exchange(int mode)          // bits 0-7: protocol (0 tagged words,
 }
 static thread_local long long* g_lstm_trace = nullptr;
 void lstm_set_trace(long long* buf) { g_lstm_trace = buf; }
+long long* lstm_get_trace() { return g_lstm_trace; }
 void lstm_force_streaming(int on) { g_lstm_force_streaming = on; }
 
 long long lstm_workspace_bytes(int Bq, int H)

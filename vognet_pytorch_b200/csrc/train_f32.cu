@@ -1020,10 +1020,15 @@ lstm_bwd_step_kernel(const float* __restrict__ dout, const float* __restrict__ a
         }
 }
 
-int lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const long long* lens, float* dG,
-                   float* carry_ws, int T, int Bq, int H, cudaStream_t st)
+int lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const float* whh, const long long* lens, float* dG,
+                   float* carry_ws, long long ws_bytes, int T, int Bq, int H, cudaStream_t st)
 {
     if (T == 0 || Bq == 0) return 0;
+    VOG_REQUIRE(ws_bytes >= (long long)8 * Bq * H * 4, "lstm_bwd_steps: workspace of %lld bytes is too small", ws_bytes);
+    {   // H = 1024, <= 4 sequences, 148 SMs: one persistent weight-resident launch (lstm_bwd.cu)
+        const int r = lstm_bwd_resident(dout, acts, whh_t, whh, lens, dG, carry_ws, ws_bytes, T, Bq, H, st);
+        if (r != 0) return r < 0 ? -1 : 0;
+    }
     VOG_REQUIRE(Bq <= LB_MAXB, "lstm_bwd_steps: at most %d sequences per call (got %d)", LB_MAXB, Bq);
     VOG_REQUIRE(H % LB_CH == 0 && H % 32 == 0, "lstm_bwd_steps: H=%d must be a multiple of 32", H);
     VOG_REQUIRE((reinterpret_cast<uintptr_t>(whh_t) & 15) == 0, "lstm_bwd_steps: whh_t must be 16-byte aligned");

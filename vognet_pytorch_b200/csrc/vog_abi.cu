@@ -42,7 +42,7 @@ using namespace vog;
 extern "C" {
 
 const char* vog_last_error(void) { return g_err; }
-int vog_abi_version(void) { return 3; }
+int vog_abi_version(void) { return 4; }
 long long vog_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void vog_debug_pdl(int on) { vog::pdl_set(on != 0); }
 
@@ -335,6 +335,7 @@ int64_t vog_workspace_bytes(int op, int a, int b, int c, int d, int e)
     case VOG_WS_TC_ATTN_BWD: return vog_tc_attn_bwd_workspace_bytes(a, b, c);
     case VOG_WS_LSTM: return vog_lstm_workspace_bytes(a, b);
     case VOG_WS_LOSS: return vog_loss_workspace_bytes(a, b, c);
+    case VOG_WS_LSTM_BWD: return vog_lstm_bwd_workspace_bytes(a, b);
     default: return -1;
     }
 }
@@ -604,12 +605,17 @@ int vog_lstm_scan(const float* G, const int64_t* lens, float* acts, int T, int B
     return lstm_scan(G, (const long long*)lens, acts, T, Bq, H, (cudaStream_t)stream);
 }
 
-int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const int64_t* lens, float* dG,
-                       float* carry_ws, int T, int Bq, int H, void* stream)
+int64_t vog_lstm_bwd_workspace_bytes(int Bq, int H) { return lstm_bwd_workspace_bytes(Bq, H); }
+/* A/B switch: 0 = T per-step launches even where the persistent weight-resident backward kernel applies */
+void vog_debug_lstm_bwd_resident(int on) { vog::lstm_bwd_set_resident(on); }
+
+int vog_lstm_bwd_steps(const float* dout, const float* acts, const float* whh_t, const float* whh, const int64_t* lens,
+                       float* dG, void* workspace, int64_t workspace_bytes, int T, int Bq, int H, void* stream)
 {
     if (T * Bq == 0) return 0;
-    VOG_REQUIRE(dout && acts && whh_t && lens && dG && carry_ws && H > 0, "vog_lstm_bwd_steps: null operand");
-    return lstm_bwd_steps(dout, acts, whh_t, (const long long*)lens, dG, carry_ws, T, Bq, H, (cudaStream_t)stream);
+    VOG_REQUIRE(dout && acts && whh_t && lens && dG && workspace && H > 0, "vog_lstm_bwd_steps: null operand");
+    return lstm_bwd_steps(dout, acts, whh_t, whh, (const long long*)lens, dG, (float*)workspace, workspace_bytes, T, Bq, H,
+                          (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -178,16 +178,20 @@ def lstm_scan(G, lens, T, Bq):
     return acts
 
 
-def lstm_bwd_steps(dout, acts, whh_t, lens, T, Bq):
+def lstm_bwd_steps(dout, acts, whh_t, lens, T, Bq, whh=None):
     """dout [T*Bq, 2H] -> dG [T*Bq, 8H]; whh_t [2,H,4H] = the recurrent weights TRANSPOSED (whh.transpose(1,2));
     at most 8 sequences per call (callers chunk the batch)."""
     H = whh_t.shape[1]
     if whh_t.shape != (2, H, 4 * H) or not whh_t.is_contiguous():
         raise ValueError(f'lstm_bwd_steps: whh_t must be contiguous [2,H,4H], got {tuple(whh_t.shape)}')
     dG = torch.empty(T * Bq, 8 * H, device=dout.device, dtype=torch.float32)
-    ws = torch.empty(8 * Bq * H, device=dout.device, dtype=torch.float32)
-    _lib.check(_lib.lib().vog_lstm_bwd_steps(_ptr(dout.contiguous()), _ptr(acts), _ptr(whh_t), _ptr(lens), _ptr(dG), _ptr(ws),
-                                             T, Bq, H, _stream()), 'vog_lstm_bwd_steps')
+    L = _lib.lib()
+    nws = int(L.vog_lstm_bwd_workspace_bytes(Bq, H))
+    ws = torch.empty(nws, device=dout.device, dtype=torch.uint8)
+    if whh is not None and (whh.shape != (2, 4 * H, H) or not whh.is_contiguous() or whh.dtype != torch.float32):
+        raise ValueError(f'lstm_bwd_steps: whh must be contiguous fp32 [2,4H,H], got {tuple(whh.shape)}')
+    _lib.check(L.vog_lstm_bwd_steps(_ptr(dout.contiguous()), _ptr(acts), _ptr(whh_t), _ptr(whh), _ptr(lens), _ptr(dG), _ptr(ws), nws,
+                                    T, Bq, H, _stream()), 'vog_lstm_bwd_steps')
     return dG
 
 

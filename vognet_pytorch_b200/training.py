@@ -280,7 +280,7 @@ def lang_forward(mdl, inp, tp, dc, be=None):
         gx = be.linear(x, (lambda l=l: _lstm_stacked(lstm, l)[0]) if be.name != 'fp32x' else wih, bias, key=('wih', l),
                        params=ps)
         hout, acts = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_NONE, want_acts=True)
-        tp.lstm.append(Tape(x=x, hout=hout, acts=acts, wih=wih, ps=ps))
+        tp.lstm.append(Tape(x=x, hout=hout, acts=acts, wih=wih, whh=whh, ps=ps))
         last = l == lstm.num_layers - 1
         x = _drop(hout, dc, dc.p_lstm, dc.LSTM_OUT if last else dc.LSTM_MID + 10 * l)
     tp.top = x
@@ -391,7 +391,7 @@ def _lstm_backward(mdl, tp, dx_top, sink, be, dc):
         tc = be.name != 'fp32x'
         hprev = ob.lstm_hprev(lt.hout, lens, T, Bq)
         whh_t = mdl._packs().get(('whhT', l), lt.ps, lambda l=l: _lstm_stacked(lstm, l)[1].transpose(1, 2).contiguous())
-        dG = ob.lstm_bwd_steps(dout, lt.acts, whh_t, lens, T, Bq)     # [T*Bq, 8H]; activations kept by the forward
+        dG = ob.lstm_bwd_steps(dout, lt.acts, whh_t, lens, T, Bq, whh=lt.whh)    # [T*Bq, 8H]; activations kept by the forward
         sfx = ('', '_reverse')
         dG_lp = be.lp(dG) if tc else dG
         dwih = be.lin_dw(dG_lp, lt.x)                                # [8H, in]
