@@ -572,12 +572,16 @@ def main():
 
     def traffic_of(kernel, shape_key):
         """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-        (profiles/r1/traffic.json); None when this shape was not captured."""
-        try:
-            t = json.load(open(os.path.join(ROOT, 'profiles', 'r1', 'traffic.json')))
-            return t.get(kernel, {}).get(shape_key)
-        except Exception:
-            return None
+        (profiles/r2/traffic.json, else profiles/r1/traffic.json); None when this shape was not captured."""
+        for rnd in ('r2', 'r1'):                       # the newest capture of this kernel / shape wins
+            try:
+                t = json.load(open(os.path.join(ROOT, 'profiles', rnd, 'traffic.json')))
+            except Exception:
+                continue
+            v = t.get(kernel, {}).get(shape_key)
+            if v is not None:
+                return v
+        return None
 
     def attn_roofline(shape, n_iter=10):
         Bt, N, d = shape

@@ -6,8 +6,8 @@ DDP-wrap, checkpoint and call them unchanged.
 
 What runs where
   language side (a13)   libvog_b200: embedding gather, tcgen05 input/output projections, persistent LSTM
-                        recurrence kernel (code/mdl_vog.py:67-140,250-283); torch + cuDNN only in the exact
-                        'fp32x' bring-up mode
+                        recurrence kernel (code/mdl_vog.py:67-140,250-283); the exact 'fp32x' mode runs the same
+                        recurrence kernel between fp32 CUDA-core GEMMs (torch + cuDNN only for its SEP variant)
   everything else       libvog_b200 CUDA kernels through vognet_pytorch_b200.ops:
       prop/seg encoders                       code/mdl_vog.py:291-314
       prop|seg concat                         code/mdl_conc_single.py:50-66,156-174
@@ -125,7 +125,8 @@ class VOGNetB200(nn.Module):
         return self
 
     # -----------------------------------------------------------------------------------------
-    # language side: torch + cuDNN
+    # language side through torch + cuDNN: the reference formulation, kept as an in-repo cross-check
+    # (tests/test_gpu_lstm.py) and for the SEP variant of the exact 'fp32x' mode
     # -----------------------------------------------------------------------------------------
     def language_encode(self, inp):
         """-> [B, nsrl, lang_dim] (num_verbs == 1 for temp/spat)."""
@@ -576,7 +577,13 @@ class VOGNetB200(nn.Module):
         nv = inp['srl_arg_words_ind'].shape[1]
         assert nv == 1, 'temp/spat concatenation has one verb slot per query'
         nsrl = inp['srl_arg_words_ind'].shape[2]
-        lang = self.language_encode(inp)                              # [B, nsrl, 256]
+        if self.CONC_TYPE == 'sep':
+            lang = self.language_encode(inp)                          # needs the final LSTM states (verb head): nn.LSTM
+        else:
+            # the repo's own kernels in exact fp32 (the language half of the exact training forward, dropout off):
+            # embedding gather, vog_sgemm projections, the fp32 recurrence kernel - no library call on this path
+            from . import training
+            lang = training.lang_forward(self, inp, training.Tape(), training.DropCtx(self, False)).view(B, nv * nsrl, -1)
 
         # prop|seg features: [B*P, 512], prop half written in place by the GEMM
         x = torch.empty(B * P, self.ps_dim, device=feat.device, dtype=torch.float32)
