@@ -175,6 +175,43 @@ def test_pack_cache_refreshes_in_place_and_follows_raw_pointer_updates():
     assert v3.shape == (5,) and pc.relocations == 1
 
 
+def test_pack_cache_build_into_rederives_in_place_without_temporaries():
+    """A training step re-packs every weight after each optimizer update: `build_into` re-derives a stale entry
+    straight into the tensors it already owns (same addresses), `refresh()` uses it too, and a `False` return (layout
+    changed) falls back to build + relocate."""
+    import torch
+    from vognet_pytorch_b200 import packing
+    pc = packing.PackCache()
+    a, b = torch.nn.Parameter(torch.ones(2, 3)), torch.nn.Parameter(torch.full((2, 3), 2.0))
+    calls = {'build': 0, 'into': 0}
+
+    def build():
+        calls['build'] += 1
+        return torch.cat([a.detach(), b.detach()], 0), a.detach().sum(0) + b.detach().sum(0)
+
+    def into(dst):
+        calls['into'] += 1
+        if dst[0].shape[0] != a.shape[0] + b.shape[0]:
+            return False
+        dst[0][:a.shape[0]].copy_(a); dst[0][a.shape[0]:].copy_(b)
+        dst[1].copy_(a.detach().sum(0) + b.detach().sum(0))
+    v = pc.get('k', (a, b), build, into)
+    addr = v[0].data_ptr()
+    assert calls == {'build': 1, 'into': 0}
+    with torch.no_grad():
+        a.mul_(3)
+    v2 = pc.get('k', (a, b), build, into)
+    assert v2 is v and v[0].data_ptr() == addr and calls == {'build': 1, 'into': 1}
+    assert v[0][:2].eq(3).all() and v[0][2:].eq(2).all() and v[1].tolist() == [10.0, 10.0, 10.0]
+    packing.bump_generation()
+    with torch.no_grad():
+        b.data.fill_(1.0)
+    assert pc.refresh() == 1 and calls['into'] == 2 and v[1].tolist() == [8.0, 8.0, 8.0]
+    a.data = torch.ones(4, 3)                                          # layout change: into declines, build relocates
+    v3 = pc.get('k', (a, b), build, into)
+    assert v3[0].shape == (6, 3) and calls['build'] == 2 and pc.relocations == 1
+
+
 def test_packed_batch_layout_round_trips_and_exposes_the_graph_prefix():
     """runtime.PackedLayout / pack_host_batch: one flat buffer per batch (a single host->device copy), tensors as views,
     the model's graph inputs as a contiguous prefix."""

@@ -66,29 +66,34 @@ class PackCache:
     def _sig(params):
         return tuple((p.data_ptr(), p._version) for p in params) + (_GENERATION,)
 
-    def get(self, key, params, build):
-        """The packed value for `key`; `build()` (run under no_grad) derives it from `params`."""
+    def get(self, key, params, build, build_into=None):
+        """The packed value for `key`; `build()` (run under no_grad) derives it from `params`.  `build_into(val)`,
+        when given, re-derives it straight INTO the tensors of an existing entry (one pass instead of build + copy:
+        a training step re-packs every weight after each optimizer update) and returns False if it cannot."""
         params = tuple(params)
         ent = self._ent.get(key)
         sig = self._sig(params)
         if ent is not None and ent[0] == sig:
             return ent[3]
         with torch.no_grad():
+            if ent is not None and build_into is not None and build_into(ent[3]) is not False:
+                self._ent[key] = (sig, params, build, ent[3], build_into)
+                return ent[3]
             val = build()
         if ent is not None and _same_layout(ent[3], val):
             _copy_into(ent[3], val)                 # same addresses: captured graphs keep reading valid, fresh data
             val = ent[3]
         elif ent is not None:
             self.relocations += 1
-        self._ent[key] = (sig, params, build, val)
+        self._ent[key] = (sig, params, build, val, build_into)
         return val
 
     def refresh(self):
         """Re-pack every stale entry in place (no forward needed).  -> number of entries rebuilt."""
         n = 0
-        for key, (sig, params, build, _) in list(self._ent.items()):
+        for key, (sig, params, build, _, build_into) in list(self._ent.items()):
             if self._sig(params) != sig:
-                self.get(key, params, build)
+                self.get(key, params, build, build_into)
                 n += 1
         return n
 

@@ -49,6 +49,12 @@ class GradSink:
             t = self.g[name] = self.views[name] if self.views is not None else _zeros_like_param(self.params[name])
         return t
 
+    def acc(self, name):
+        """the tensor a weight-gradient GEMM accumulates into directly (no temporary + add): the flat-buffer view, or
+        zeros on first touch"""
+        t = self.get(name)
+        return t if t.dim() == 2 and t.is_contiguous() else None
+
     def set(self, name, val):
         if self.views is not None or name in self.g:
             self.get(name).add_(val.view_as(self.params[name]))
@@ -74,9 +80,10 @@ class F32Backend:
         out = residual.clone() if residual.is_contiguous() else residual.contiguous()
         return ob.sgemm(dy, w, out=out, accumulate=True)
 
-    def lin_dw(self, dy, x):
-        """dy^T @ x -> [N,K]"""
-        out = torch.zeros(dy.shape[1], x.shape[1], device=dy.device, dtype=torch.float32)
+    def lin_dw(self, dy, x, out=None):
+        """dy^T @ x -> [N,K]; `out` (fp32 [N,K]): accumulated into, e.g. a view of the flat gradient buffer"""
+        if out is None:
+            out = torch.zeros(dy.shape[1], x.shape[1], device=dy.device, dtype=torch.float32)
         return ob.sgemm(dy.t(), x, out=out, accumulate=True)
 
 
@@ -101,9 +108,16 @@ class TcBackend:
             m = w() if callable(w) else w
             t = m.detach().t() if transposed else m.detach()
             return t.contiguous().to(torch.bfloat16)
+
+        def into(dst):                       # one fused (transposing) cast-copy into the existing bf16 pack
+            m = w() if callable(w) else w
+            t = m.detach().t() if transposed else m.detach()
+            if dst.shape != t.shape:
+                return False
+            dst.copy_(t)
         if key is None:
             return build()
-        return self.packs.get(('be', key, transposed), params if params is not None else (w,), build)
+        return self.packs.get(('be', key, transposed), params if params is not None else (w,), build, into)
 
     def linear(self, x, w, b=None, relu=False, residual=None, key=None, out=None, params=None):
         o, _ = ops.tc_gemm(self.lp(x), self._w(w, key, params, False), bias=b, relu=relu, residual=residual, out_f32=out)
@@ -113,8 +127,8 @@ class TcBackend:
         o, _ = ops.tc_gemm(self.lp(dy), self._w(w, key, params, True), residual=residual)
         return o
 
-    def lin_dw(self, dy, x):
-        return ob.tc_gemm_tn(self.lp(dy), self.lp(x))
+    def lin_dw(self, dy, x, out=None):
+        return ob.tc_gemm_tn(self.lp(dy), self.lp(x), out=out)
 
 
 # =============================================================================================
@@ -244,15 +258,35 @@ def _drop(x, dc, p, site, **kw):
     return ob.dropout(x, p, dc.seed, site, **kw)[0]
 
 
+def _lstm_params(lstm, l):
+    """the eight parameters of layer l: weight_ih, weight_hh, bias_ih, bias_hh, each forward then reverse"""
+    names = [f'{n}_l{l}{s}' for n in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh') for s in ('', '_reverse')]
+    return tuple(getattr(lstm, n) for n in names)
+
+
 def _lstm_stacked(lstm, l):
     """forward|reverse stacked matrices of layer l (fresh copies) and the parameters they derive from"""
-    names = [f'{n}_l{l}{s}' for n in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh') for s in ('', '_reverse')]
-    ps = tuple(getattr(lstm, n) for n in names)
+    ps = _lstm_params(lstm, l)
     with torch.no_grad():
         wih = torch.cat([ps[0], ps[1]], 0)
         whh = torch.stack([ps[2], ps[3]], 0).contiguous()
         bias = torch.cat([ps[4] + ps[6], ps[5] + ps[7]], 0)
     return wih, whh, bias, ps
+
+
+def _lstm_pack(mdl, lstm, l):
+    """(wih [8H,in], whh [2,4H,H], bias [8H]) fp32, cached in the model's PackCache and re-derived IN PLACE from the
+    live parameters when those change (every training step: one pass over the 150 MB of a layer, no temporaries)
+    -> (pack, parameters)"""
+    ps = _lstm_params(lstm, l)
+
+    def into(dst):
+        wih, whh, bias = dst
+        n = ps[0].shape[0]
+        wih[:n].copy_(ps[0]); wih[n:].copy_(ps[1])
+        whh[0].copy_(ps[2]); whh[1].copy_(ps[3])
+        torch.add(ps[4], ps[6], out=bias[:n]); torch.add(ps[5], ps[7], out=bias[n:])
+    return mdl._packs().get(('lstm32', l), ps, lambda: _lstm_stacked(lstm, l)[:3], into), ps
 
 
 def lang_forward(mdl, inp, tp, dc, be=None):
@@ -272,12 +306,11 @@ def lang_forward(mdl, inp, tp, dc, be=None):
     x = ops.lang_embed(tp.words, wm, mdl.lstm_encoder.embed_tokens.weight, mdl.vocab_size, ops.LP_NONE)
     x = _drop(x, dc, dc.p_lstm, dc.LSTM_IN)
     tp.lstm = []
-    packs = mdl._packs()
     for l in range(lstm.num_layers):
-        ps = _lstm_stacked(lstm, l)[3]
-        # stacked forward|reverse matrices, rebuilt from the live parameters whenever those change
-        wih, whh, bias = packs.get(('lstm32', l), ps, lambda l=l: _lstm_stacked(lstm, l)[:3])
-        gx = be.linear(x, (lambda l=l: _lstm_stacked(lstm, l)[0]) if be.name != 'fp32x' else wih, bias, key=('wih', l),
+        # stacked forward|reverse matrices, re-derived from the live parameters whenever those change; the low-precision
+        # copies of the tensor-core backend derive from this pack (a callable: the cache may re-run it later)
+        (wih, whh, bias), ps = _lstm_pack(mdl, lstm, l)
+        gx = be.linear(x, (lambda l=l: _lstm_pack(mdl, lstm, l)[0][0]) if be.name != 'fp32x' else wih, bias, key=('wih', l),
                        params=ps)
         hout, acts = ops.lstm_layer_fwd(gx, whh, lens, T, Bq, ops.LP_NONE, want_acts=True)
         tp.lstm.append(Tape(x=x, hout=hout, acts=acts, wih=wih, whh=whh, ps=ps))
@@ -390,21 +423,23 @@ def _lstm_backward(mdl, tp, dx_top, sink, be, dc):
         Hh = lstm.hidden_size
         tc = be.name != 'fp32x'
         hprev = ob.lstm_hprev(lt.hout, lens, T, Bq)
-        whh_t = mdl._packs().get(('whhT', l), lt.ps, lambda l=l: _lstm_stacked(lstm, l)[1].transpose(1, 2).contiguous())
+        whh_t = mdl._packs().get(('whhT', l), lt.ps, lambda l=l: _lstm_pack(mdl, lstm, l)[0][1].transpose(1, 2).contiguous(),
+                                 lambda dst, l=l: dst.copy_(_lstm_pack(mdl, lstm, l)[0][1].transpose(1, 2)))
         dG = ob.lstm_bwd_steps(dout, lt.acts, whh_t, lens, T, Bq, whh=lt.whh)    # [T*Bq, 8H]; activations kept by the forward
         sfx = ('', '_reverse')
         dG_lp = be.lp(dG) if tc else dG
-        dwih = be.lin_dw(dG_lp, lt.x)                                # [8H, in]
+        x_lp = be.lp(lt.x) if tc else lt.x
         db = torch.zeros(8 * Hh, device=dG.device, dtype=torch.float32)
         ob.colsum_acc(dG, db)
         hprev_lp = be.lp(hprev) if tc else hprev
         for d_ in range(2):
             sl = slice(d_ * 4 * Hh, (d_ + 1) * 4 * Hh)
-            sink.set(f'lstm_encoder.lstm.weight_ih_l{l}{sfx[d_]}', dwih[sl])
+            # the two big weight gradients of a direction accumulate straight into their gradient tensors
+            be.lin_dw(dG_lp[:, sl], x_lp, out=sink.get(f'lstm_encoder.lstm.weight_ih_l{l}{sfx[d_]}'))
             sink.set(f'lstm_encoder.lstm.bias_ih_l{l}{sfx[d_]}', db[sl])
             sink.set(f'lstm_encoder.lstm.bias_hh_l{l}{sfx[d_]}', db[sl].clone())
-            sink.set(f'lstm_encoder.lstm.weight_hh_l{l}{sfx[d_]}', be.lin_dw(dG_lp[:, sl], hprev_lp[:, d_ * Hh:(d_ + 1) * Hh]))
-        dout = be.lin_dx(dG_lp, (lambda l=l: _lstm_stacked(lstm, l)[0]) if tc else lt.wih, key=('wih', l),
+            be.lin_dw(dG_lp[:, sl], hprev_lp[:, d_ * Hh:(d_ + 1) * Hh], out=sink.get(f'lstm_encoder.lstm.weight_hh_l{l}{sfx[d_]}'))
+        dout = be.lin_dx(dG_lp, (lambda l=l: _lstm_pack(mdl, lstm, l)[0][0]) if tc else lt.wih, key=('wih', l),
                          params=lt.ps)                                # [T*Bq, in]
     dout = _drop(dout, dc, dc.p_lstm, dc.LSTM_IN)
     ob.lang_embed_bwd(tp.words, tp.wm, dout, mdl.vocab_size, lens, sink.get('lstm_encoder.embed_tokens.weight'))
