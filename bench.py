@@ -643,9 +643,11 @@ def main():
         steps_t = int(lens.max().item())
         by = whh.numel() * 4 + steps_t * Bq * 8 * Hh * 4 + T * Bq * 2 * Hh * (2 if lp == ops.LP_BF16 else 4)
         ach = by / (ms * 1e-3) / 1e9
+        # 3-4 sentences per launch run the two-units-per-warp variant of the weight-resident kernel (csrc/lstm_rec.cu)
+        kname = 'lstm_rec_pair_kernel' if 3 <= Bq <= 4 else 'lstm_rec_resident_kernel'
         return {'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
-                'traffic': traffic_of('lstm_rec_resident_kernel', f'T{T}_B{Bq}_H{Hh}'),
-                'kernel': 'lstm_rec_resident_kernel', 'shape': {'T': T, 'Bq': Bq, 'H': Hh, 'steps': steps_t},
+                'traffic': traffic_of(kname, f'T{T}_B{Bq}_H{Hh}'),
+                'kernel': kname, 'shape': {'T': T, 'Bq': Bq, 'H': Hh, 'steps': steps_t},
                 'ms_per_launch': ms, 'bytes_per_launch': by, 'launches_per_step': 2,
                 'peak_source': f'{pk_kind} HBM copy bandwidth',
                 'note': 'latency-bound: one cross-SM h_t exchange per timestep and direction (18 dependent steps); '

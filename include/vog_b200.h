@@ -439,7 +439,7 @@ int vog_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int K
  * warp / the MMA issuer of vog_tc_attn_fwd (library built with -DVOG_ATTN_PROFILE). */
 void vog_debug_gemm_trace(void* buf);
 void vog_debug_pdl(int on);                   /* A/B: 0 = plain stream-ordered launches instead of programmatic dependent launches */
-void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 2 self-tagged per-CTA records (default), 0 tagged 64-bit words, 1 per-CTA release flags; bits 8-23: poll back-off in ns */
+void vog_debug_lstm_exchange(int mode);        /* h_t exchange protocol: 4 automatic (default: 3 for 3-4 sequences, else 2), 2 self-tagged per-CTA records, 3 records + two hidden units per warp, 0 tagged 64-bit words, 1 per-CTA release flags; bits 8-23: poll back-off in ns (protocol 2) */
 void vog_debug_lstm_bwd_resident(int on);      /* 0 = per-step LSTM backward launches even where the persistent kernel applies */
 void vog_debug_lstm_trace(void* buf);          /* 8 int64: matvec, reduce, cell+publish, poll, barrier cycles, steps */
 void vog_debug_attn_prof(void* buf);

@@ -12,8 +12,8 @@ from vognet_pytorch_b200 import ops, _lib  # noqa: E402
 dev = 'cuda:0'
 L = _lib.lib()
 T, H = 20, 1024
-NAMES = {0: 'tagged', 1: 'flags', 2: 'records'}
-CASES = [(4, 0), (4, 2), (4, 2 | (100 << 8)), (4, 1), (8, 0), (8, 2), (1, 0), (1, 2), (2, 2)]
+NAMES = {0: 'tagged', 1: 'flags', 2: 'records', 3: 'records, two units per warp'}
+CASES = [(4, 0), (4, 2), (4, 3), (8, 2), (1, 2), (1, 3), (2, 2), (2, 3), (3, 2), (3, 3)]
 for Bq, mode in CASES:
     xmode, backoff = mode & 0xff, mode >> 8
     L.vog_debug_lstm_exchange(mode)
@@ -49,4 +49,4 @@ for Bq, mode in CASES:
         print(f'   traced launch: {v[5]} steps; per step (cycles): '
               f'matvec {v[0] / n:.0f}  reduce {v[1] / n:.0f}  cell+publish {v[2] / n:.0f}  poll {v[3] / n:.0f}  barrier {v[4] / n:.0f}'
               f'   | entry -> first step {v[6]} cycles')
-L.vog_debug_lstm_exchange(2)
+L.vog_debug_lstm_exchange(4)

@@ -57,8 +57,8 @@ def _ref_recurrence(gx, whh, lens, T, Bq, H):
     return ref
 
 
-@pytest.mark.parametrize('streaming,xmode', [(0, 0), (0, 1), (0, 2), (1, 0)],
-                         ids=['resident-tagged', 'resident-flags', 'resident-records', 'streaming'])
+@pytest.mark.parametrize('streaming,xmode', [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0)],
+                         ids=['resident-tagged', 'resident-flags', 'resident-records', 'resident-pair', 'streaming'])
 @pytest.mark.parametrize('lens_list', [[1, 20, 7, 13], [5], [20, 3], [2, 9, 4], [1, 1, 1, 1], [20] * 8,
                                        [3, 17, 20, 1, 8, 12], [4, 9, 20, 1, 13, 7, 2, 18, 5, 11, 16]])
 def test_ragged_lengths_and_zero_rows(lens_list, streaming, xmode):
@@ -80,7 +80,7 @@ def test_ragged_lengths_and_zero_rows(lens_list, streaming, xmode):
         torch.cuda.synchronize()
     finally:
         _lib.lib().vog_debug_lstm_force_streaming(0)
-        _lib.lib().vog_debug_lstm_exchange(2)          # the default protocol
+        _lib.lib().vog_debug_lstm_exchange(4)          # the default (automatic) protocol
     out = outs[0]
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])      # deterministic across launches
     ref = _ref_recurrence(gx, whh, lens, T, Bq, H)
@@ -89,7 +89,7 @@ def test_ragged_lengths_and_zero_rows(lens_list, streaming, xmode):
         assert out[int(lens[b]):, b].abs().max() == 0 if int(lens[b]) < T else True
 
 
-@pytest.mark.parametrize('xmode', [0, 2], ids=['tagged', 'records'])
+@pytest.mark.parametrize('xmode', [0, 2, 3], ids=['tagged', 'records', 'pair'])
 def test_resident_kernel_in_cuda_graph_replays(xmode):
     """the exchange buffer is re-zeroed by a kernel inside the captured work, so graph
     replays (same kernel parameters every time) never see stale tags"""
@@ -98,7 +98,7 @@ def test_resident_kernel_in_cuda_graph_replays(xmode):
     try:
         _graph_replay_case(ops)
     finally:
-        _lib.lib().vog_debug_lstm_exchange(2)          # the default protocol
+        _lib.lib().vog_debug_lstm_exchange(4)          # the default (automatic) protocol
 
 
 def _graph_replay_case(ops):

@@ -99,7 +99,7 @@ int cast_lp(const float* src, long long lds, void* dst, long long ldd, long long
 long long lstm_workspace_bytes(int Bq, int H);
 void lstm_set_trace(long long* buf);     // debug: phase cycle counters of CTA 0
 long long* lstm_get_trace();
-void lstm_set_exchange(int mode);        // debug: 2 self-tagged records (default), 0 tagged 64-bit words, 1 per-CTA release flags
+void lstm_set_exchange(int mode);        // debug: 4 automatic (default), 2 self-tagged records, 3 records + two units per warp, 0 tagged words, 1 flags
 void lstm_set_max_ctas(int n);           // > 0: run the recurrence on at most n SMs (weight-streaming kernel)
 void lstm_force_streaming(int on);       // debug: disable the weight-resident kernel
 int lstm_layer_fwd(const float* gx, long long ldg, const float* whh, const long long* lens, int T, int Bq,

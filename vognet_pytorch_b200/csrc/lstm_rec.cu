@@ -589,6 +589,230 @@ lstm_rec_resident_kernel(const LstmResParams p)
             store_lp(p.out_lp, ((long long)t * p.bq_total + lane) * p.ld_out + (long long)d * H + u, 0.f, p.lp_kind);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Two hidden units per warp (exchange protocol 3 = protocol 2's records, <= 4 sequences per launch).  The matvec of
+// the kernel above is bound by shared-memory reads: per step and CTA 172 KB of weights and 229 KB of h_{t-1} - every
+// one of the 14 warps reads ALL of h for its single unit.  Here a warp owns two units (8 gate rows): 7 warps read h
+// once for two units each (115 KB), the weight traffic stays, the FFMA2 count per SM is unchanged; accumulators
+// (8 rows x BQ, as register pairs) and 64 register-resident weights fit the 255-register budget of a 224-thread CTA.
+// -------------------------------------------------------------------------------------------------
+constexpr int LP_NREG = 2;                     // float4 per gate row per lane kept in registers
+
+template <int BQ>
+__global__ void __launch_bounds__(32 * (LR_MAXU / 2), 1)
+lstm_rec_pair_kernel(const LstmResParams p)
+{
+    constexpr int H = LR_H;
+    constexpr int V = 8 * BQ;                                // values a warp reduces per step: 2 units x 4 gates x BQ
+    constexpr int NS = LR_NI - LP_NREG;                      // float4 per gate row per lane in shared memory
+    extern __shared__ __align__(16) float sm[];
+    const int NT = blockDim.x;                               // 32 * U / 2
+    float4* w_s = reinterpret_cast<float4*>(sm);             // [2 units][4 gates][NS][NT]
+    float* h_s = sm + 8 * NS * NT * 4;                       // [2 parity][BQ][H]
+    float* gate_s = h_s + 2 * BQ * H;                        // [warps][V]
+    unsigned* x_s = reinterpret_cast<unsigned*>(gate_s + (LR_MAXU / 2) * V);   // [16 unit slots][BQ]
+    __shared__ int len_s[LS_MAXB];
+    __shared__ int tmax_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = blockIdx.x / p.ctas_per_dir, c = blockIdx.x % p.ctas_per_dir;
+    const int Bq = p.Bq;
+    const int u0 = c * p.U + 2 * warp;                       // the warp's units: u0, u0 + 1
+
+    pdl_trigger();
+    for (int i = tid; i < 2 * BQ * H; i += NT) h_s[i] = 0.f;
+    float4 wr[2][4][LP_NREG];
+    {
+        const float* wbase = p.whh + (size_t)d * 4 * H * H;
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+            const bool ok = u0 + uu < H;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4* row = reinterpret_cast<const float4*>(wbase + ((size_t)g * H + (ok ? u0 + uu : 0)) * H);
+#pragma unroll
+                for (int i = 0; i < LR_NI; ++i) {
+                    const float4 w4 = ok ? __ldg(row + 32 * i + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < LP_NREG) wr[uu][g][i] = w4;
+                    else w_s[((uu * 4 + g) * NS + (i - LP_NREG)) * NT + tid] = w4;
+                }
+            }
+        }
+    }
+    pdl_wait();
+    if (tid < LS_MAXB) len_s[tid] = tid < Bq ? (int)min((long long)p.T, max(0LL, p.lens[tid])) : 0;
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int b = 0; b < Bq; ++b) m = max(m, len_s[b]);
+        tmax_s = m;
+    }
+    __syncthreads();
+    const int Tmax = tmax_s;
+
+    // after the reduce-scatter lane l holds output idx = l >> (5 - log2 V), laid out idx = b * 8 + unit * 4 + gate
+    constexpr int LOGV = V == 8 ? 3 : V == 16 ? 4 : 5;
+    const int my_idx = lane >> (5 - LOGV);
+    const int my_b = my_idx >> 3, my_uu = (my_idx >> 2) & 1, my_g = my_idx & 3;
+    const bool gx_lane = u0 + my_uu < H && my_b < Bq && (lane & ((1 << (5 - LOGV)) - 1)) == 0;
+    // cell update: lane = unit * BQ + sequence
+    const int cu = lane / BQ, cb = lane % BQ;
+    const bool cell_lane = lane < 2 * BQ && cb < Bq && u0 + cu < H;
+    float c_reg = 0.f, h_reg = 0.f;
+#ifdef VOG_LSTM_TRACE
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tc[5] = {0, 0, 0, 0, 0};
+    long long tprev = tr ? clock64() : 0;
+#define LP_TRACE(i) if (tr) { const long long tn = clock64(); tc[i] += tn - tprev; tprev = tn; }
+#else
+#define LP_TRACE(i)
+#endif
+
+    for (int step = 0; step < Tmax; ++step) {
+        const int t = d == 0 ? step : Tmax - 1 - step;
+        const float* hcur = h_s + (step & 1) * BQ * H;
+        float gxv = 0.f;
+        if (gx_lane)
+            gxv = __ldg(p.gx + ((size_t)t * p.bq_total + my_b) * p.ldg + (size_t)d * 4 * H + (size_t)my_g * H + u0 + my_uu);
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        if (step > 0) {                                      // h_{-1} = 0
+            float2 acc2[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < LR_NI; ++i) {
+                float4 w4[2][4];
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        w4[uu][g] = i < LP_NREG ? wr[uu][g][i < LP_NREG ? i : 0]
+                                                : w_s[((uu * 4 + g) * NS + (i - LP_NREG)) * NT + tid];
+#pragma unroll
+                for (int b = 0; b < BQ; ++b) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hcur + b * H + 128 * i + 4 * lane);
+#pragma unroll
+                    for (int uu = 0; uu < 2; ++uu)
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int k = b * 8 + uu * 4 + g;
+                            acc2[k] = ffma2(make_float2(w4[uu][g].x, w4[uu][g].y), make_float2(hv.x, hv.y), acc2[k]);
+                            acc2[k] = ffma2(make_float2(w4[uu][g].z, w4[uu][g].w), make_float2(hv.z, hv.w), acc2[k]);
+                        }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = acc2[k].x + acc2[k].y;
+        }
+        LP_TRACE(0)
+        const float tot = warp_reduce_scatter<V>(acc, lane);
+        if (gx_lane) gate_s[warp * V + my_idx] = tot + gxv;
+        __syncwarp();
+        LP_TRACE(1)
+        if (cell_lane) {
+            const int u = u0 + cu;
+            const bool live = t < len_s[cb];
+            float hval = 0.f;
+            if (live) {
+                const float* gs = gate_s + warp * V + cb * 8 + cu * 4;
+                const float gi = fast_sigmoid(gs[0]);
+                const float gf = fast_sigmoid(gs[1]);
+                const float gg = fast_tanh(gs[2]);
+                const float go = fast_sigmoid(gs[3]);
+                const float cp = c_reg;
+                c_reg = gf * c_reg + gi * gg;
+                const float tcn = fast_tanh(c_reg);
+                hval = go * tcn;
+                h_reg = hval;
+                if (p.acts != nullptr) {
+                    float* a = p.acts + ((((size_t)t * p.bq_total + cb) * 2 + d) * 6) * H + u;
+                    a[0] = gi; a[H] = gf; a[2 * (size_t)H] = gg; a[3 * (size_t)H] = go; a[4 * (size_t)H] = tcn; a[5 * (size_t)H] = cp;
+                }
+            }
+            store_lp(p.out_lp, ((long long)t * p.bq_total + cb) * p.ld_out + (long long)d * H + u, hval, p.lp_kind);
+        }
+        __syncwarp();
+        // ---- record exchange, as protocol 2 of lstm_rec_resident_kernel (unit slot = 2 * warp + unit of the pair)
+        const unsigned tagbit = (((unsigned)step >> 1) & 1u) ^ 1u;
+        constexpr int RS = 16 * BQ;
+        unsigned* xrec = reinterpret_cast<unsigned*>(p.hx) + (((size_t)(step & 1) * 2 + d) * p.ctas_per_dir) * RS;
+        if (step + 1 < Tmax) {
+            if (lane < 2 * BQ) x_s[(2 * warp + cu) * BQ + cb] = (__float_as_uint(h_reg) & ~1u) | tagbit;   // idle lanes: h_reg == 0
+            __syncthreads();
+            if (warp == 0) {
+                unsigned* mine = xrec + (size_t)c * RS;
+                const int nw = p.U * BQ;
+                for (int i = lane; i < nw; i += 32) st_relaxed_u32(mine + i, x_s[i]);
+            }
+        }
+        LP_TRACE(2)
+        if (step + 1 < Tmax) {
+            constexpr int MAXI = 6;                            // 74 records x 16 slots over 224 threads
+            const int nitems = p.ctas_per_dir * 16;
+            float* hnext = h_s + ((step + 1) & 1) * BQ * H;
+            unsigned pend = 0;
+#pragma unroll
+            for (int k = 0; k < MAXI; ++k) {
+                const int q = tid + k * NT, j = q & 15;
+                if (q < nitems && j < p.U && (q >> 4) * p.U + j < H) pend |= 1u << k;
+            }
+            XVec<BQ> w[MAXI];
+            long long t0 = 0;
+            while (pend) {
+#pragma unroll
+                for (int k = 0; k < MAXI; ++k)
+                    if (pend & (1u << k)) {
+                        const int q = tid + k * NT;
+                        w[k] = ld_relaxed_words<BQ>(xrec + (size_t)(q >> 4) * RS + (q & 15) * BQ);
+                    }
+#pragma unroll
+                for (int k = 0; k < MAXI; ++k)
+                    if (pend & (1u << k)) {
+                        bool ok = true;
+#pragma unroll
+                        for (int e = 0; e < BQ; ++e) ok = ok && (w[k].w[e] & 1u) == tagbit;
+                        if (ok) {
+                            pend &= ~(1u << k);
+                            const int q = tid + k * NT;
+                            const int unit = (q >> 4) * p.U + (q & 15);
+#pragma unroll
+                            for (int e = 0; e < BQ; ++e) hnext[e * H + unit] = __uint_as_float(w[k].w[e] & ~1u);
+                        }
+                    }
+                if (pend) {
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > 4000000000LL) {
+                        printf("vog: lstm record-exchange timeout block %d step %d\n", (int)blockIdx.x, step);
+                        __trap();
+                    }
+                }
+            }
+            LP_TRACE(3)
+            __syncthreads();
+            LP_TRACE(4)
+        }
+    }
+#ifdef VOG_LSTM_TRACE
+    if (tr) { for (int i = 0; i < 5; ++i) p.trace[i] = tc[i]; p.trace[5] = Tmax; p.trace[6] = 0; }
+#endif
+    if (cell_lane)
+        for (int t = Tmax; t < p.T; ++t)
+            store_lp(p.out_lp, ((long long)t * p.bq_total + cb) * p.ld_out + (long long)d * H + u0 + cu, 0.f, p.lp_kind);
+}
+
+template <int BQ>
+static int launch_pair(const LstmResParams& p, int ctas, cudaStream_t st)
+{
+    const int threads = 32 * (p.U / 2);
+    const size_t smem = (size_t)8 * (LR_NI - LP_NREG) * threads * 16 + (size_t)2 * BQ * LR_H * 4 + (size_t)(LR_MAXU / 2) * 8 * BQ * 4 +
+                        (size_t)16 * BQ * 4;
+    VOG_CUDA(cudaFuncSetAttribute(lstm_rec_pair_kernel<BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VOG_CUDA(launch_pdl(lstm_rec_pair_kernel<BQ>, dim3(ctas), dim3(threads), smem, st, p));
+    return check_launch("lstm_rec_pair");
+}
+
 __global__ void __launch_bounds__(256) zero16_kernel(uint4* __restrict__ p, long long n16)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,11 +842,12 @@ static int launch_resident(const LstmResParams& p, int ctas, int threads, cudaSt
 static thread_local int g_lstm_force_streaming = 0;
 static thread_local int g_lstm_max_ctas = 0;
 void lstm_set_max_ctas(int n) { g_lstm_max_ctas = n > 0 ? n : 0; }
-static thread_local int g_lstm_xmode = 2;          // default: self-tagged records (profiles/r2/lstm_records.txt)
+static thread_local int g_lstm_xmode = 4;          // default: self-tagged records, two units per warp for 3-4 sequences
+                                                   // (profiles/r2/lstm_records.txt)
 static thread_local int g_lstm_backoff = 0;
 void lstm_set_exchange(int mode)          // bits 0-7: protocol (0 tagged words, 1 flags, 2 records), bits 8-23: poll back-off in ns
 {
-    g_lstm_xmode = (mode & 0xff) <= 2 ? (mode & 0xff) : 0;
+    g_lstm_xmode = (mode & 0xff) <= 4 ? (mode & 0xff) : 0;        // 3: records + two hidden units per warp; 4: automatic
     g_lstm_backoff = (mode >> 8) & 0xffff;
 }
 static thread_local long long* g_lstm_trace = nullptr;
@@ -666,6 +891,9 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
         rp.hx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + LS_WS_HEADER);
         rp.flags = reinterpret_cast<unsigned*>(workspace);
         rp.xmode = g_lstm_xmode;
+        // automatic: two units per warp pays from 3 sequences on (Bq=4: 104 -> 100 us per layer; Bq=1: 79 -> 85 us, the
+        // halved thread count makes the collect phase longer than the matvec gets shorter)
+        if (rp.xmode == 4) rp.xmode = (Bq >= 3 && Bq <= 4) ? 3 : 2;
         rp.backoff_ns = g_lstm_backoff;
         {   // the record exchange needs its item count to fit the unrolled poll and the workspace; else tagged words
             const int bqt = Bq <= 1 ? 1 : Bq <= 2 ? 2 : Bq <= 4 ? 4 : 8;
@@ -685,6 +913,15 @@ static int lstm_layer_chunk(const float* gx, long long ldg, const float* whh, co
                                 reinterpret_cast<uint4*>(workspace), n16));
         }
         const int ctas = 2 * per_dir_u, threads = 32 * U;
+        if (rp.xmode == 3) {
+            // two units per warp: U even, <= 4 sequences, the poll's item count within its unrolled budget
+            if (Bq <= 4 && U % 2 == 0 && U <= LR_MAXU && per_dir_u <= LS_REC_MAX_CTAS && per_dir_u * 16 <= 6 * 32 * (U / 2)) {
+                if (Bq == 1) return launch_pair<1>(rp, ctas, st);
+                if (Bq == 2) return launch_pair<2>(rp, ctas, st);
+                return launch_pair<4>(rp, ctas, st);
+            }
+            rp.xmode = 2;
+        }
         if (Bq == 1) return launch_resident<1>(rp, ctas, threads, st);
         if (Bq == 2) return launch_resident<2>(rp, ctas, threads, st);
         if (Bq <= 4) return launch_resident<4>(rp, ctas, threads, st);

@@ -370,7 +370,7 @@ void vog_set_reserved_sms(int n) { vog::tc_gemm_set_reserved_sms(n); }
 
 /* debug / A-B testing: 1 = always use the weight-streaming recurrence kernel */
 void vog_debug_lstm_force_streaming(int on) { vog::lstm_force_streaming(on); }
-/* A/B switch of the h_t exchange of the weight-resident kernel: 2 = self-tagged per-CTA records (default), 0 = tagged 64-bit words, 1 = per-CTA flags */
+/* A/B switch of the h_t exchange of the weight-resident kernel: 4 = automatic (default), 2 = self-tagged per-CTA records, 3 = records + two hidden units per warp, 0 = tagged 64-bit words, 1 = per-CTA flags */
 void vog_debug_lstm_exchange(int mode) { vog::lstm_set_exchange(mode); }
 /* debug: device buffer of 8 int64: accumulated clock64 cycles of CTA 0 in {matvec, reduce, cell + publish,
  * poll, barrier} and the step count of the weight-resident recurrence kernel */
