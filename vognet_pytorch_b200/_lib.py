@@ -126,7 +126,7 @@ def lib():
                 fn = getattr(l, name)          # AttributeError if the symbol is not exported
                 fn.argtypes = argtypes
                 fn.restype = _RESTYPE[name]
-            if os.environ.get('VOG_PDL', '0') == '1':       # A/B: programmatic dependent launches (measured: no gain)
+            if os.environ.get('VOG_PDL', '0') == '1':       # programmatic dependent launches everywhere (default: mdl_vog decides)
                 l.vog_debug_pdl(1)
             if os.environ.get('VOG_LSTM_XMODE'):            # A/B: h_t exchange protocol of the recurrence kernel
                 l.vog_debug_lstm_exchange(int(os.environ['VOG_LSTM_XMODE'], 0))

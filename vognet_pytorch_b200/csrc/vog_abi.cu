@@ -20,7 +20,7 @@ void set_error(const char* fmt, ...)
 }
 
 static std::atomic<long long> g_launches{0};
-static thread_local bool g_pdl = false;         // measured: 0.5 % on the gt5 graph replay, nothing at p100 - off by default
+static thread_local bool g_pdl = false;         // the model switches it on while it captures the forward of a small configuration
 bool pdl_enabled() { return g_pdl; }
 void pdl_set(bool on) { g_pdl = on; }
 

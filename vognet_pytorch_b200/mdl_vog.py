@@ -450,6 +450,7 @@ class VOGNetB200(nn.Module):
     #    two parallel branches - language side (embedding, LSTM, projections) and visual side
     #    (encoders, object transformer) - joined before the multimodal transformer.  Nothing in it
     #    synchronises with the host; inputs are copied into the graph's static buffers.
+    PDL_MAX_ROWS = 4096          # proposals per forward (B * P) up to which the captured forward uses dependent launches
     _GRAPH_KEYS = ('pad_region_feature', 'seg_feature_for_frms', 'pad_proposals', 'srl_arg_inds_msk',
                    'num_cmp_msk', 'srl_arg_words_ind', 'srl_arg_word_mask', 'srl_arg_word_mask_len',
                    'srl_arg_words_capture')
@@ -490,14 +491,24 @@ class VOGNetB200(nn.Module):
                     out = self._sep_heads(out, self.__dict__.pop('_sep_seg_mean'), self.__dict__.pop('_sep_verb'),
                                           st['srl_arg_inds_msk'], st['verb_ind_in_srl'], st['num_cmp_msk'])
                 return out
-            side = torch.cuda.Stream(device=feat.device)
-            body(side)                              # eager warm-up: packs weights, sets kernel attributes
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            cap = torch.cuda.Stream(device=feat.device)
-            n0 = _lib.lib().vog_launch_count()
-            with torch.cuda.graph(graph, stream=cap):
-                out = body(side)
+            # Programmatic dependent launch for the SMALL configurations: their forward is a chain of ~40 short
+            # dependent kernels, and letting each start (barrier / tensor-memory set-up, weight loads) while its
+            # predecessor drains is worth 1.8 % at spat/gt5 (profiles/r2/pdl_ab.txt); at spat/p100 it measured 0.7 %
+            # SLOWER (early CTAs of the next kernel take SMs from a busy one).  VOG_PDL=0 / 1 forces it off / on.
+            pdl_env = os.environ.get('VOG_PDL')
+            use_pdl = pdl_env == '1' or (pdl_env is None and feat.shape[0] * feat.shape[1] <= self.PDL_MAX_ROWS)
+            _lib.lib().vog_debug_pdl(1 if use_pdl else 0)        # thread-local switch of the library
+            try:
+                side = torch.cuda.Stream(device=feat.device)
+                body(side)                              # eager warm-up: packs weights, sets kernel attributes
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                cap = torch.cuda.Stream(device=feat.device)
+                n0 = _lib.lib().vog_launch_count()
+                with torch.cuda.graph(graph, stream=cap):
+                    out = body(side)
+            finally:
+                _lib.lib().vog_debug_pdl(1 if pdl_env == '1' else 0)
             # kernels of libvog_b200 captured into the graph = launches per replay
             g = dict(st=st, graph=graph, out=out, launches=_lib.lib().vog_launch_count() - n0,
                      wsig=self._weights_sig(), flat=flat, prefix=lay.prefix(keys), keys=keys)
