@@ -234,3 +234,19 @@ def test_packed_batch_layout_round_trips_and_exposes_the_graph_prefix():
     assert int(pb.flat[o:o + n].sum()) == 0
     with pytest.raises(ValueError):
         pb.layout.pack_into(pb.flat, {**batch, 'pad_proposals': batch['pad_proposals'][:, :1]})
+
+
+def test_prediction_fetcher_recognises_views_of_one_allocation():
+    """runtime.PredictionFetcher moves tensors that are contiguous views of ONE allocation (what ops.select_fwd returns)
+    with a single copy; anything else - different storages, a storage that holds more than the tensors - one copy each."""
+    import torch
+    from vognet_pytorch_b200.runtime import PredictionFetcher
+    flat = torch.zeros(8 * 3 + 4 * 6 + 4 * 2, dtype=torch.uint8)
+    ix = flat[:24].view(torch.int64)
+    bx = flat[24:48].view(torch.float32).view(2, 3)
+    sc = flat[48:].view(torch.float32)
+    assert PredictionFetcher._shared((bx, sc, ix))
+    assert not PredictionFetcher._shared((bx, sc))                       # the allocation holds something else too
+    assert not PredictionFetcher._shared((bx, torch.zeros(2)))           # different storages
+    big = torch.zeros(4, 4)
+    assert not PredictionFetcher._shared((big[:, :2], big[:, 2:]))       # non-contiguous views
