@@ -27,6 +27,8 @@ extern "C" {
 #define VOG_BIAS_NONE  0   /* plain Attention          code/transformer_code.py:41-50            */
 #define VOG_BIAS_RANK1 1   /* relu(a_i - a_j + b_h)    code/mdl_vog.py:456-490 in rank-1 form    */
 #define VOG_BIAS_DENSE 2   /* dense x_pe [Bt,N,N,H]    code/transformer_code.py:271-273 operator */
+#define VOG_BIAS_RANK1_EXPANDED 3   /* VOG_BIAS_RANK1 for vog_tc_attn_fwd when the workspace already holds the key factors
+                                       (vog_pe_project_expand): no expansion pre-kernel */
 
 /* low-precision copy kinds */
 #define VOG_LP_NONE 0
@@ -76,6 +78,13 @@ int vog_add_layernorm(const float* x, int ldx, const float* r, int ldr, const fl
  * The rank-1 factor of Linear(5,H) applied to p_i - p_j: code/mdl_vog.py:446-451,459-463,480. */
 int vog_pe_project(const float* props, int ldp, const float* W, float* a, int rows, int H,
                    float vw, float vh, float fdiv, float scale, void* stream);
+/* vog_pe_project and, in the same launch, the per-key factors of the rank-1 bias that vog_tc_attn_fwd otherwise
+ * expands in a pre-kernel of its own: key_factors (vog_tc_attn_workspace_bytes(Bt, N, H) bytes) for the attention
+ * call with the same Bt, N, H, nbox and inv_scale, passed to it as its workspace with bias_mode
+ * VOG_BIAS_RANK1_EXPANDED.  rows == Bt * nbox. */
+int vog_pe_project_expand(const float* props, int ldp, const float* W, float* a, int rows, int H, float vw, float vh,
+                          float fdiv, float scale, int Bt, int N, int nbox, float inv_scale, void* key_factors,
+                          int64_t key_factors_bytes, void* stream);
 
 /* Selection: scores [B,nsrl,P] (= mdl_outs_eval), props [B,P,pdim] ->
  *   boxes [B,nsrl,ncmp,nfrm,pdim], out_scores [B,nsrl,ncmp,nfrm], indexs [B,nsrl,nfrm] (int64;

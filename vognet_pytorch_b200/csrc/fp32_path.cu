@@ -441,6 +441,47 @@ __global__ void pe_project_kernel(const float* __restrict__ props, int ldp, cons
     a[idx] = acc * scale;
 }
 
+// The same projection plus, in the same launch, the per-key factors the fused attention kernel consumes:
+//   ak[bt*H + h, key] = c * a[(bt*nbox + key % nbox), h] for key < N, 0 up to the row end ld
+// (what tc_attn's bias_expand pre-kernel would compute from `a`; every thread RE-derives its a value with the code above,
+// so the two outputs agree bit for bit with pe_project + bias_expand).  rows == Bt * nbox.
+__global__ void pe_project_expand_kernel(const float* __restrict__ props, int ldp, const float* __restrict__ W,
+                                         float* __restrict__ a, float* __restrict__ ak, int rows, int H, float vw, float vh,
+                                         float fdiv, float scale, int Bt, int N, int nbox, int ld, float c)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    auto project = [&](int row, int h) {
+        const float* p = props + (size_t)row * ldp;
+        const float* w = W + h * 5;
+        float acc = (p[0] / vw) * w[0];
+        acc = fmaf(p[1] / vh, w[1], acc);
+        acc = fmaf(p[2] / vw, w[2], acc);
+        acc = fmaf(p[3] / vh, w[3], acc);
+        acc = fmaf(p[4] / fdiv, w[4], acc);
+        return acc * scale;
+    };
+    if (idx < (long long)rows * H) a[idx] = project((int)(idx / H), (int)(idx % H));
+    if (idx < (long long)Bt * H * ld) {
+        const int key = (int)(idx % ld);
+        const int bh = (int)(idx / ld);
+        const int bt = bh / H, h = bh % H;
+        ak[idx] = key < N ? project(bt * nbox + key % nbox, h) * c : 0.f;
+    }
+}
+
+int pe_project_expand(const float* props, int ldp, const float* W, float* a, int rows, int H, float vw, float vh,
+                      float fdiv, float scale, float* ak, int Bt, int N, int nbox, int ld, float c, cudaStream_t st)
+{
+    if (rows == 0) return 0;
+    VOG_REQUIRE(nbox > 0 && rows == Bt * nbox, "pe_project_expand: rows=%d != Bt*nbox=%d*%d", rows, Bt, nbox);
+    const long long n = (long long)rows * H > (long long)Bt * H * ld ? (long long)rows * H : (long long)Bt * H * ld;
+    VOG_CUDA(launch_pdl(pe_project_expand_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, props, ldp, W, a, ak,
+                        rows, H, vw, vh, fdiv, scale, Bt, N, nbox, ld, c));
+    return check_launch("pe_project_expand");
+}
+
 int pe_project(const float* props, int ldp, const float* W, float* a, int rows, int H, float vw,
                float vh, float fdiv, float scale, cudaStream_t st)
 {

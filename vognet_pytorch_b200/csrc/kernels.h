@@ -21,6 +21,10 @@ int add_layernorm(const float* x, int ldx, const float* r, int ldr, const float*
                   cudaStream_t st);
 int pe_project(const float* props, int ldp, const float* W, float* a, int rows, int H, float vw,
                float vh, float fdiv, float scale, cudaStream_t st);
+int pe_project_expand(const float* props, int ldp, const float* W, float* a, int rows, int H, float vw, float vh,
+                      float fdiv, float scale, float* ak, int Bt, int N, int nbox, int ld, float c, cudaStream_t st);
+int tc_attn_key_ld(int N);            // row length of the expanded key factors (N rounded up to the key tile)
+float tc_attn_key_scale(float inv_scale);   // the factor the attention kernel applies to them (exp2 domain)
 int select_fwd(const float* scores, const float* props, int pdim, float* boxes, float* out_scores,
                long long* indexs, int B, int nsrl, int ncmp, int nfrm, int nppf, int spat,
                cudaStream_t st, const float* fin = nullptr);

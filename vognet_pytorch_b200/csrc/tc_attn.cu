@@ -888,6 +888,8 @@ long long tc_attn_workspace_bytes(int Bt, int N, int H)
 {
     return (long long)Bt * H * round_up(N, FA_BKV) * 4;
 }
+int tc_attn_key_ld(int N) { return round_up(N, FA_BKV); }
+float tc_attn_key_scale(float inv_scale) { return inv_scale * 1.4426950408889634f; }
 
 static thread_local long long* g_attn_prof = nullptr;
 static thread_local int g_attn_impl = 2;             // 1 = Q/P through smem (v1); Q/P in tensor memory with 2 (v2) / 4 (v3) softmax threads per row
@@ -910,7 +912,8 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
     VOG_REQUIRE(out_kind == 1 || out_kind == 2, "tc_attn: bad out_kind");
     VOG_REQUIRE(ldo >= (long long)H * dhp && (ldo * (out_kind == 1 ? 2 : 4)) % 16 == 0, "tc_attn: bad ldo");
     VOG_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "tc_attn: output must be 16-byte aligned");
-    VOG_REQUIRE(bias_mode != 1 || (a && bpe && nbox > 0), "tc_attn: rank-1 bias needs a, bpe, nbox");
+    VOG_REQUIRE((bias_mode != 1 && bias_mode != 3) || (a && bpe && nbox > 0), "tc_attn: rank-1 bias needs a, bpe, nbox");
+    VOG_REQUIRE(bias_mode != 3 || (lse == nullptr && drop_p == 0.f), "tc_attn: pre-expanded key factors are an inference-path option");
     VOG_REQUIRE(bias_mode != 2 || dense, "tc_attn: dense bias pointer missing");
     AttnParams p;
     p.Bt = Bt; p.N = N; p.H = H; p.dhp = dhp;
@@ -918,7 +921,10 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
         VOG_REQUIRE(dh[h] >= 1 && dh[h] <= dhp, "tc_attn: head dim %d does not fit dhp=%d", dh[h], dhp);
         p.dh[h] = dh[h];
     }
-    p.c = inv_scale * 1.4426950408889634f;
+    p.c = tc_attn_key_scale(inv_scale);
+    // bias_mode 3 = rank-1 whose key factors the caller already expanded into the workspace (vog_pe_project_expand)
+    const bool pre_expanded = bias_mode == 3;
+    if (pre_expanded) bias_mode = 1;
     p.bias_mode = bias_mode; p.a = a; p.nbox = nbox > 0 ? nbox : 1; p.bpe = bpe; p.dense = dense;
     p.out = out; p.ldo = ldo; p.out_kind = out_kind;
     p.prof = g_attn_prof;
@@ -929,10 +935,12 @@ int tc_attn(const void* q, const void* k, const void* v, int Bt, int N, int H, i
                     (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                     "tc_attn: rank-1 bias needs a 16-byte aligned workspace of tc_attn_workspace_bytes()");
         p.ak_seq = reinterpret_cast<const float*>(workspace);
-        const long long n = (long long)Bt * H * p.ak_ld;
-        VOG_CUDA(launch_pdl(bias_expand_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a,
-                            reinterpret_cast<float*>(workspace), Bt, N, H, p.nbox, p.ak_ld, p.c));
-        if (check_launch("bias_expand")) return -1;
+        if (!pre_expanded) {
+            const long long n = (long long)Bt * H * p.ak_ld;
+            VOG_CUDA(launch_pdl(bias_expand_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a,
+                                reinterpret_cast<float*>(workspace), Bt, N, H, p.nbox, p.ak_ld, p.c));
+            if (check_launch("bias_expand")) return -1;
+        }
     }
     p.q = reinterpret_cast<const __nv_bfloat16*>(q);
     if (g_attn_impl >= 2) {

@@ -96,6 +96,20 @@ int vog_pe_project(const float* props, int ldp, const float* W, float* a, int ro
     return pe_project(props, ldp, W, a, rows, H, vw, vh, fdiv, scale, (cudaStream_t)stream);
 }
 
+int vog_pe_project_expand(const float* props, int ldp, const float* W, float* a, int rows, int H, float vw, float vh,
+                          float fdiv, float scale, int Bt, int N, int nbox, float inv_scale, void* key_factors,
+                          int64_t key_factors_bytes, void* stream)
+{
+    VOG_REQUIRE(props && W && a && key_factors, "vog_pe_project_expand: null operand");
+    VOG_REQUIRE(ldp >= 5, "vog_pe_project_expand: proposals need >= 5 columns");
+    VOG_REQUIRE(Bt > 0 && N > 0 && H > 0, "vog_pe_project_expand: bad dimension");
+    VOG_REQUIRE(key_factors_bytes >= vog_tc_attn_workspace_bytes(Bt, N, H) &&
+                (reinterpret_cast<uintptr_t>(key_factors) & 15) == 0,
+                "vog_pe_project_expand: key_factors needs vog_tc_attn_workspace_bytes(Bt, N, H) bytes, 16-byte aligned");
+    return pe_project_expand(props, ldp, W, a, rows, H, vw, vh, fdiv, scale, (float*)key_factors, Bt, N, nbox,
+                             tc_attn_key_ld(N), tc_attn_key_scale(inv_scale), (cudaStream_t)stream);
+}
+
 int vog_select_fwd(const float* scores, const float* props, int pdim, float* boxes,
                    float* out_scores, int64_t* indexs, int B, int nsrl, int ncmp, int nfrm,
                    int nppf, int spat, void* stream)
@@ -282,7 +296,7 @@ int vog_tc_attn_fwd(const void* q, const void* k, const void* v, int Bt, int N, 
     if (Bt == 0 || N == 0) return 0;
     if (require_sm100("vog_tc_attn_fwd")) return -1;
     VOG_REQUIRE(q && k && v && out && dh, "vog_tc_attn_fwd: null operand");
-    VOG_REQUIRE(bias_mode >= 0 && bias_mode <= 2, "vog_tc_attn_fwd: bad bias_mode %d", bias_mode);
+    VOG_REQUIRE(bias_mode >= 0 && bias_mode <= VOG_BIAS_RANK1_EXPANDED, "vog_tc_attn_fwd: bad bias_mode %d", bias_mode);
     return tc_attn(q, k, v, Bt, N, H, dhp, dh, inv_scale, bias_mode, a, nbox, bpe, dense, out, ldo,
                    out_kind, workspace, workspace_bytes, (cudaStream_t)stream);
 }

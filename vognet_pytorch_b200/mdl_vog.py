@@ -20,6 +20,7 @@ What runs where
 ``sep``/``svsq`` concatenation (code/mdl_conc_sep.py:13-217) runs through the same kernels: every (query, video)
 pair becomes one single-video pseudo-query (``_sep_flatten``), plus the video-level verb head.
 """
+import math
 import os
 
 import torch
@@ -343,14 +344,14 @@ class VOGNetB200(nn.Module):
         if self.use_cuda_graph:
             return self._forward_tc_graph(inp, ncmp)
         lang = self.language_encode_tc(inp)                           # [B, nsrl, 256] fp32
-        x, x_lp = self._visual_tc(feat, seg, props, ncmp)
+        x, x_lp = self._visual_tc(feat, seg, props, ncmp, nsrl=lang.shape[1])
         out = self._fusion_tc(x, x_lp, lang, props, inp['srl_arg_inds_msk'], inp['num_cmp_msk'], ncmp)
         if self.CONC_TYPE == 'sep':
             out = self._sep_heads(out, self.__dict__.pop('_sep_seg_mean'), self.__dict__.pop('_sep_verb'),
                                   inp['srl_arg_inds_msk'], inp['verb_ind_in_srl'], inp['num_cmp_msk'])
         return out
 
-    def _visual_tc(self, feat, seg, props, ncmp):
+    def _visual_tc(self, feat, seg, props, ncmp, nsrl=None):
         """prop/seg encoders -> prop|seg rows -> object transformer.  Independent of the language
         side.  -> x [B*P, 512] fp32 and its low-precision copy."""
         kind = ops.LP_BF16 if self.compute == 'bf16' else ops.LP_TF32
@@ -390,18 +391,31 @@ class VOGNetB200(nn.Module):
                 Bt_o, N_o, fdiv = B, P, 1.0
             bias = None
             if otx.use_rel:
-                a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_obj_sub_enc[0].weight,
-                                   self.vid_w, self.vid_h, fdiv)
-                bias = RelBias(a, self.pe_obj_sub_enc[0].bias, N_o)
+                # projection + the attention's per-key factors in ONE launch (one kernel less on the chain)
+                ex = self.obj_txf._exec
+                a, ak = ops.pe_project_expand(props.reshape(B * P, props.shape[-1]), self.pe_obj_sub_enc[0].weight,
+                                              self.vid_w, self.vid_h, fdiv, Bt_o, N_o, N_o, 1.0 / math.sqrt(ex.d))
+                bias = RelBias(a, self.pe_obj_sub_enc[0].bias, N_o, ak=ak, ak_sig=(Bt_o, N_o, ex.H, ex.d))
             x, x_lp = self.obj_txf._exec.run(x.view(Bt_o, N_o, self.ps_dim), bias, self.compute,
                                              x_lp=x_lp, want_lp=True)
             x = x.reshape(B * P, self.ps_dim)
         if self.USE_MUL_TX and self.cfg.mdl.mul_tx.to_use and self.cfg.mdl.mul_tx.use_rel:
             # the multimodal transformer's bias factors depend on the boxes only: projected here, on the visual
             # branch, so they are off the critical path after the language/visual join
-            nfrm_m, _ = self._groups(ncmp)
-            self._a_mul = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
-                                         self.vid_w, self.vid_h, float(nfrm_m))
+            nfrm_m, nppf2_m = self._groups(ncmp)
+            if nsrl is not None:
+                # ... and so do the attention's per-key factors (sequence = nsrl x nppf2 tokens of one frame, bias
+                # period nppf2): expanded in the same launch, so the attention on the fusion chain starts without its
+                # expansion pre-kernel.  _fusion_tc falls back to that pre-kernel if the geometry turns out different.
+                exm = self.mult_txf._exec
+                sig = (B * nfrm_m, nsrl * nppf2_m, exm.H, exm.d)
+                self._a_mul, ak = ops.pe_project_expand(props.reshape(B * P, props.shape[-1]),
+                                                        self.pe_mul_sub_enc[0].weight, self.vid_w, self.vid_h,
+                                                        float(nfrm_m), sig[0], sig[1], nppf2_m, 1.0 / math.sqrt(exm.d))
+                self._ak_mul = (ak, sig)
+            else:
+                self._a_mul = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
+                                             self.vid_w, self.vid_h, float(nfrm_m))
         return x, x_lp
 
     def _fusion_tc(self, x, x_lp, lang, props, srl_msk, cmp_msk, ncmp):
@@ -419,10 +433,12 @@ class VOGNetB200(nn.Module):
             bias = None
             if mtx.use_rel:
                 a = self.__dict__.pop('_a_mul', None)
+                ak, ak_sig = self.__dict__.pop('_ak_mul', (None, None))
                 if a is None or a.shape[0] != B * P:
                     a = ops.pe_project(props.reshape(B * P, props.shape[-1]), self.pe_mul_sub_enc[0].weight,
                                        self.vid_w, self.vid_h, float(nfrm))
-                bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2)
+                    ak, ak_sig = None, None
+                bias = RelBias(a, self.pe_mul_sub_enc[0].bias, nppf2, ak=ak, ak_sig=ak_sig)
             lang_lp = self.__dict__.pop('_lang_lp', None)       # produced next to `lang` by language_encode_tc
             if lang_lp is None or lang_lp.shape != lang2.shape:
                 lang_lp = ops.cast_lp(lang2, kind)
@@ -483,7 +499,8 @@ class VOGNetB200(nn.Module):
                 with torch.cuda.stream(side):
                     lang = self.language_encode_tc(st)
                 x, x_lp = self._visual_tc(st['pad_region_feature'], st['seg_feature_for_frms'],
-                                          st['pad_proposals'], ncmp)
+                                          st['pad_proposals'], ncmp,
+                                          nsrl=st['srl_arg_words_ind'].shape[1] * st['srl_arg_words_ind'].shape[2])
                 cur.wait_stream(side)
                 out = self._fusion_tc(x, x_lp, lang, st['pad_proposals'], st['srl_arg_inds_msk'],
                                       st['num_cmp_msk'], ncmp)

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-BIAS_NONE, BIAS_RANK1, BIAS_DENSE = 0, 1, 2
+BIAS_NONE, BIAS_RANK1, BIAS_DENSE, BIAS_RANK1_EXPANDED = 0, 1, 2, 3
 LP_NONE, LP_BF16, LP_TF32 = 0, 1, 2
 
 
@@ -134,6 +134,23 @@ def pe_project(props, W, vid_w, vid_h, fdiv, scale=1.0):
                                 rows, H, float(vid_w), float(vid_h), float(fdiv), float(scale),
                                 _stream()), 'vog_pe_project')
     return a
+
+
+def pe_project_expand(props, W, vid_w, vid_h, fdiv, Bt, N, nbox, inv_scale, scale=1.0):
+    """pe_project plus, in the same launch, the per-key bias factors of the attention call (Bt sequences of N tokens,
+    bias period nbox, scale inv_scale) -> (a [rows, H], key_factors): pass key_factors to tc_attn_fwd(ak=...)."""
+    _req(props, torch.float32, 'props', 2), _req(W, torch.float32, 'W', 2)
+    rows, H = props.shape[0], W.shape[0]
+    if rows != Bt * nbox:
+        raise ValueError(f'pe_project_expand: {rows} proposal rows != Bt*nbox = {Bt}*{nbox}')
+    L = _lib.lib()
+    a = torch.empty(rows, H, device=props.device, dtype=torch.float32)
+    nb = int(L.vog_tc_attn_workspace_bytes(Bt, N, H))
+    ak = torch.empty(nb, device=props.device, dtype=torch.uint8)
+    _lib.check(L.vog_pe_project_expand(_ptr(props), _rowmajor2d(props, 'props'), _ptr(W.contiguous()), _ptr(a), rows, H,
+                                       float(vid_w), float(vid_h), float(fdiv), float(scale), Bt, N, nbox,
+                                       float(inv_scale), _ptr(ak), nb, _stream()), 'vog_pe_project_expand')
+    return a, ak
 
 
 def select_fwd(scores, props, ncmp, nfrm, nppf, spat):
@@ -408,8 +425,9 @@ def tc_gemm_gres(a, w, res_vis, res_lang, nfrm, nsrl, nppf2, bias=None, relu=Fal
 
 
 def tc_attn_fwd(q, k, v, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, bias_mode=BIAS_NONE,
-                a=None, nbox=0, bpe=None, dense=None):
-    """q,k,v [Bt,H,N,dhp] bf16 -> out [Bt*N, H*dhp] (bf16 or tf32-rounded fp32)."""
+                a=None, nbox=0, bpe=None, dense=None, ak=None):
+    """q,k,v [Bt,H,N,dhp] bf16 -> out [Bt*N, H*dhp] (bf16 or tf32-rounded fp32).  ak: the key factors of a rank-1 bias
+    already expanded by pe_project_expand for exactly this (Bt, N, H, nbox, inv_scale) - skips the expansion pre-kernel."""
     for t, n in ((q, 'q'), (k, 'k'), (v, 'v')):
         _req(t, torch.bfloat16, n, 4)
         if not t.is_contiguous():
@@ -432,7 +450,12 @@ def tc_attn_fwd(q, k, v, N, head_dims, inv_scale, out_kind=LP_BF16, out=None, bi
     ws, ws_bytes = None, 0
     if bias_mode == BIAS_RANK1:
         ws_bytes = L.vog_tc_attn_workspace_bytes(Bt, N, H)
-        ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+        if ak is not None:
+            if ak.dtype != torch.uint8 or ak.numel() < ws_bytes or ak.device != q.device:
+                raise ValueError('tc_attn_fwd: ak does not belong to this attention call')
+            ws, bias_mode = ak, BIAS_RANK1_EXPANDED
+        else:
+            ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
     _lib.check(L.vog_tc_attn_fwd(_ptr(q), _ptr(k), _ptr(v), Bt, N, H, dhp, dh_arr, float(inv_scale),
                                  bias_mode, _ptr(a), nbox, _ptr(bpe), _ptr(dense), _ptr(out),
                                  _rowmajor2d(out, 'out'), out_kind, _ptr(ws), ws_bytes, _stream()),

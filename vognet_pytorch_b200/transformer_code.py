@@ -32,8 +32,11 @@ class RelBias:
     reference's Linear(5,H)+ReLU on pairwise box differences tiled nsrl x nsrl
     (code/mdl_vog.py:477-488) because the Linear is applied to p_i - p_j."""
 
-    def __init__(self, a, b, nbox):
+    def __init__(self, a, b, nbox, ak=None, ak_sig=None):
         self.a, self.b, self.nbox = a, b, int(nbox)
+        # optional: the per-key factors already expanded for ONE attention geometry by ops.pe_project_expand
+        # (ak_sig = (Bt, N, H, d_model)); the tensor-core executor then skips the attention's expansion pre-kernel
+        self.ak, self.ak_sig = ak, ak_sig
 
 
 class FactoredTokens:
@@ -158,8 +161,14 @@ class EncoderExecutor:
         kind = ops.LP_BF16 if compute == 'bf16' else ops.LP_TF32
         if x_lp is None:
             x_lp = ops.cast_lp(x2, kind)
+        self._use_expanded(bkw, bias, Bt, N)
         y, y_lp = self._run_tc(x2, x_lp.reshape(Bt * N, d), Bt, N, bkw, inv_scale, kind)
         return (y.view(Bt, N, d), y_lp) if want_lp else y.view(Bt, N, d)
+
+    def _use_expanded(self, bkw, bias, Bt, N):
+        """tensor-core modes: hand the attention the key factors the caller expanded for exactly this geometry"""
+        if isinstance(bias, RelBias) and bias.ak is not None and bias.ak_sig == (Bt, N, self.H, self.d):
+            bkw['ak'] = bias.ak
 
     def _run_fp32x(self, x2, Bt, N, bkw, inv_scale):
         d = self.d
@@ -182,6 +191,7 @@ class EncoderExecutor:
         if ft.d != self.d:
             raise ValueError(f'expected token width {self.d}, got {ft.d}')
         bkw = self._bias_args(bias, ft.Bt, ft.N)
+        self._use_expanded(bkw, bias, ft.Bt, ft.N)
         kind = ops.LP_BF16 if compute == 'bf16' else ops.LP_TF32
         y, y_lp = self._run_tc(None, None, ft.Bt, ft.N, bkw, 1.0 / math.sqrt(self.d), kind, ft=ft,
                                need_f32=need_f32)
